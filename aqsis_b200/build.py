@@ -1,0 +1,61 @@
+"""Build the in-tree native library of the hider (sm_100a only).
+
+    python -m aqsis_b200.build            # build if sources are newer than the library
+    python -m aqsis_b200.build --force
+
+The library is built IN-TREE (aqsis_b200/_lib/libaqsis_b200_hider.so) so that it travels with
+the repository snapshot to the GPU box.  -fmad=false is not a tuning choice: the reference's
+arithmetic has no fused multiply-add and bit parity depends on it.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "_lib")
+LIB = os.path.join(LIBDIR, "libaqsis_b200_hider.so")
+SOURCES = ["hider_kernels.cu", "hider_api.cpp", "host_sampling.cpp", "host_filters.cpp"]
+HEADERS = ["hider_device.h", "host_sampling.h", os.path.join("..", "..", "include", "aqsis_b200_hider.h")]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: the hider has no CPU build")
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    for f in SOURCES + HEADERS:
+        if os.path.getmtime(os.path.join(CSRC, f)) > t:
+            return True
+    return False
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    os.makedirs(LIBDIR, exist_ok=True)
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+           "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-O3", "-cudart", "static", "-shared",
+           "-o", LIB + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+        print(" ".join(cmd))
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout + r.stderr)
+    os.replace(LIB + ".tmp", LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,964 @@
+// hider_api.cpp -- host driver behind the C ABI of include/aqsis_b200_hider.h.
+//
+// Owns device memory and streams, replays the renderer-global random stream into per-pixel
+// pattern planes, lays the shaded grids out in HBM and launches the sm_100a kernels of
+// hider_kernels.cu.  There is deliberately no CPU implementation of the path in here: without
+// a usable device every entry point that would compute returns AQH_ERR_NO_DEVICE.
+#include "hider_device.h"
+#include "host_sampling.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace aqh;
+
+namespace {
+
+double nowMs()
+{
+	return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct DevBuf
+{
+	void* p = nullptr;
+	size_t cap = 0;
+	cudaError_t reserve(size_t bytes)
+	{
+		if(bytes <= cap) return cudaSuccess;
+		if(p) cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes/8 + 256;
+		cudaError_t e = cudaMalloc(&p, want);
+		if(e != cudaSuccess) { want = bytes; e = cudaMalloc(&p, want); }
+		if(e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() { if(p) cudaFree(p); p = nullptr; cap = 0; }
+	template<class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct PinnedBuf
+{
+	void* p = nullptr;
+	size_t cap = 0;
+	bool reserve(size_t bytes, bool keep = false, size_t used = 0)
+	{
+		if(bytes <= cap) return true;
+		size_t want = std::max(bytes, cap*2);
+		void* q = nullptr;
+		if(cudaHostAlloc(&q, want, cudaHostAllocDefault) != cudaSuccess) return false;
+		if(keep && p && used) std::memcpy(q, p, used);
+		if(p) cudaFreeHost(p);
+		p = q; cap = want;
+		return true;
+	}
+	void release() { if(p) cudaFreeHost(p); p = nullptr; cap = 0; }
+	template<class T> T* as() const { return static_cast<T*>(p); }
+};
+
+// One contiguous run of grids as handed over by the caller.
+struct Segment
+{
+	int64_t firstGrid = 0, nGrids = 0, nVerts = 0, nPos = 0;
+	const float* P = nullptr; const float* Ci = nullptr; const float* Oi = nullptr; const uint8_t* culled = nullptr;
+	int memorySpace = 0;     // 0 host, 1 device
+	bool staged = false;     // lives in the hider's own pinned staging (pointers are offsets to fix up)
+};
+
+int typeSize(int type)
+{
+	switch(type)
+	{
+		case AQH_FLOAT32: case AQH_UNSIGNED32: case AQH_SIGNED32: return 4;
+		case AQH_UNSIGNED16: case AQH_SIGNED16: return 2;
+		default: return 1;
+	}
+}
+// selectDataFormat, ddmanager.cpp:249-283
+int selectDataFormat(float oneVal, float minVal, float maxVal)
+{
+	if(oneVal == 0) return AQH_FLOAT32;
+	if(minVal >= 0)
+	{
+		if(maxVal <= 255.0f) return AQH_UNSIGNED8;
+		if(maxVal <= 65535.0f) return AQH_UNSIGNED16;
+		return AQH_UNSIGNED32;
+	}
+	if(minVal >= -128.0f && maxVal <= 127.0f) return AQH_SIGNED8;
+	if(minVal >= -32768.0f && maxVal <= 32767.0f) return AQH_SIGNED16;
+	return AQH_SIGNED32;
+}
+
+} // namespace
+
+struct AqhHider
+{
+	int device = 0;
+	int smCount = 0;
+	cudaStream_t stream = nullptr;
+	bool ownStream = false;
+	std::string lastError;
+	bool inFrame = false, rendered = false;
+	AqhFrameParams params{};
+	ReplayLayout layout{};
+	// frame tables (host) and the key they were built for
+	std::string tableKey;
+	SamplerTables tables;
+	std::vector<uint8_t> patPlanes;
+	std::vector<float> dither, filterTab, dofBounds;
+	std::vector<uint8_t> shuf8;
+	bool tablesUploaded = false;
+	// grids of the frame (host tables)
+	std::vector<int32_t> gcu, gcv, gnkeys;
+	std::vector<uint32_t> gflags;
+	std::vector<float> glod, gkeyTimes;
+	std::vector<Segment> segments;
+	int64_t nVerts = 0, nPos = 0;
+	bool anyCi = false, anyOi = false, anyCulled = false, allCi = true, allOi = true;
+	// pinned staging for aqh_add_grid
+	PinnedBuf stP, stCi, stOi, stCulled;
+	size_t stPUsed = 0, stVUsed = 0;   // floats*3 units: positions / vertices staged
+	// device buffers
+	DevBuf dPraw, dCi, dOi, dCulled, dP4, dGrids, dChunk, dKeyTimes, dSplit;
+	DevBuf dPosTab, dVal1d, dShuf, dPat, dFilt, dDofB, dDither;
+	DevBuf dTileSlot, dActive, dBinCount, dBinOffset, dBinEntries, dMisc, dTileFlags;
+	DevBuf dPlanes, dMask, dDeepA, dDeepUV, dChannels, dRowOwned;
+	DevBuf dDisplay[AQH_MAX_DISPLAYS];
+	// tiling
+	int tileW = 0, tileH = 0, ntx = 0, nty = 0;
+	std::vector<int32_t> tileSlot;
+	std::vector<uint32_t> activeTiles;
+	std::vector<uint8_t> rowOwned;
+	std::vector<std::pair<int,int>> strips;
+	// outputs (host)
+	PinnedBuf hChannels;
+	PinnedBuf hDisplay[AQH_MAX_DISPLAYS];
+	int dispType[AQH_MAX_DISPLAYS] = {0}, dispEntry[AQH_MAX_DISPLAYS] = {0};
+	bool haveHostImage = false;
+	cudaEvent_t ev[8] = {nullptr};
+	AqhFrameStats stats{};
+
+	int fail(int status, const std::string& msg) { lastError = msg; return status; }
+	int cudaFail(cudaError_t e, const char* what)
+	{
+		lastError = std::string(what) + ": " + cudaGetErrorString(e);
+		return (e == cudaErrorMemoryAllocation) ? AQH_ERR_NO_MEMORY : AQH_ERR_CUDA;
+	}
+};
+
+#define CU(call, what) do { cudaError_t e__ = (call); if(e__ != cudaSuccess) return h->cudaFail(e__, what); } while(0)
+
+namespace {
+
+void resetFrameGrids(AqhHider* h)
+{
+	h->gcu.clear(); h->gcv.clear(); h->gnkeys.clear(); h->gflags.clear(); h->glod.clear(); h->gkeyTimes.clear();
+	h->segments.clear();
+	h->nVerts = h->nPos = 0;
+	h->anyCi = h->anyOi = h->anyCulled = false; h->allCi = h->allOi = true;
+	h->stPUsed = h->stVUsed = 0;
+}
+
+int validateParams(AqhHider* h, const AqhFrameParams& p)
+{
+	if(p.abi_version != AQH_ABI_VERSION) return h->fail(AQH_ERR_BAD_PARAMS, "abi_version mismatch");
+	if(p.xres <= 0 || p.yres <= 0) return h->fail(AQH_ERR_BAD_PARAMS, "resolution must be positive");
+	if(p.crop_xmin < 0 || p.crop_ymin < 0 || p.crop_xmax > p.xres || p.crop_ymax > p.yres ||
+	   p.crop_xmax <= p.crop_xmin || p.crop_ymax <= p.crop_ymin)
+		return h->fail(AQH_ERR_BAD_PARAMS, "crop window must be a non-empty sub-rectangle of the image");
+	if(p.xsamples < 1 || p.ysamples < 1 || p.xsamples*p.ysamples > 256)
+		return h->fail(AQH_ERR_BAD_PARAMS, "PixelSamples must be >= 1 with at most 256 samples per pixel");
+	if(!(p.filter_xwidth > 0.f) || !(p.filter_ywidth > 0.f) || p.filter_xwidth >= 16.f || p.filter_ywidth >= 16.f)
+		return h->fail(AQH_ERR_BAD_PARAMS, "filter widths must be in (0,16)");
+	if(p.bucket_xsize < 1 || p.bucket_ysize < 1) return h->fail(AQH_ERR_BAD_PARAMS, "bucket size must be positive");
+	if(p.n_displays < 0 || p.n_displays > AQH_MAX_DISPLAYS) return h->fail(AQH_ERR_BAD_PARAMS, "too many displays");
+	for(int d = 0; d < p.n_displays; ++d)
+	{
+		const AqhDisplayDesc& dd = p.display[d];
+		if(dd.n_channels < 1 || dd.n_channels > AQH_MAX_DISPLAY_CHANNELS) return h->fail(AQH_ERR_BAD_PARAMS, "display channel count");
+		for(int c = 0; c < dd.n_channels; ++c)
+			if(dd.channel[c] < 0 || dd.channel[c] >= AQH_NUM_CHANNELS) return h->fail(AQH_ERR_BAD_PARAMS, "display channel index");
+		if(dd.type < 0 || dd.type > AQH_SIGNED8) return h->fail(AQH_ERR_BAD_PARAMS, "display data type");
+	}
+	if(p.depth_filter != AQH_DEPTHFILTER_MIN)
+		return h->fail(AQH_ERR_UNSUPPORTED, "only depthfilter \"min\" is implemented on the device");
+	if(p.world_size < 0 || (p.world_size > 0 && (p.rank < 0 || p.rank >= p.world_size)))
+		return h->fail(AQH_ERR_BAD_PARAMS, "rank/world_size");
+	if(p.use_dof && !(p.dof_one_over_focal_distance != 0.f))
+		return h->fail(AQH_ERR_BAD_PARAMS, "depth of field needs a finite focal distance");
+	return AQH_OK;
+}
+
+void chooseTile(const AqhFrameParams& p, bool mbdofHint, int& tw, int& th)
+{
+	const int n = p.xsamples*p.ysamples;
+	const int target = mbdofHint ? 2048 : 4096;
+	tw = 16; th = 16;
+	while(tw*p.xsamples > 255 && tw > 1) tw >>= 1;
+	while(th*p.ysamples > 255 && th > 1) th >>= 1;
+	while(tw*th*n > target && (tw > 1 || th > 1))
+	{
+		if(th >= tw && th > 1) th >>= 1; else tw >>= 1;
+	}
+}
+
+// Build (or reuse) the frame tables: jitter patterns, per-pixel pattern planes, dither, filter
+// weights, lens-cell bounds.  Everything here depends on the options only, not on the geometry.
+int buildTables(AqhHider* h)
+{
+	const AqhFrameParams& p = h->params;
+	char key[512];
+	std::snprintf(key, sizeof key, "%d %d|%d %d %d %d|%d %d|%a %a %p|%d %d|%d|%u %u|%d",
+	              p.xres, p.yres, p.crop_xmin, p.crop_xmax, p.crop_ymin, p.crop_ymax, p.xsamples, p.ysamples,
+	              p.filter_xwidth, p.filter_ywidth, (void*)p.filter_func, p.bucket_xsize, p.bucket_ysize, p.jitter,
+	              p.rng_seed, p.rng_predraws, p.n_displays);
+	if(h->tableKey == key && h->tablesUploaded) return AQH_OK;
+	h->layout = replayLayout(p);
+	const ReplayLayout& L = h->layout;
+	// RiWorldBegin reseeds (ri.cpp:660); RenderImage always constructs the jittered sampler
+	// (imagebuffer.cpp:694), which consumes the stream and reseeds with 19.
+	Random rng(p.rng_seed);
+	rng.discard(p.rng_predraws);
+	SamplerTables jit;
+	buildJitterTables(rng, p.xsamples, p.ysamples, jit);
+	if(p.jitter) h->tables = std::move(jit);
+	else buildGridTables(p.xsamples, p.ysamples, h->tables);
+	const size_t plane = size_t(L.sw)*L.sh;
+	h->patPlanes.assign(5*plane, 0);
+	h->dither.assign(size_t(std::max(1, p.n_displays))*p.xres*p.yres, 0.f);
+	replayFrame(p, L, rng, p.jitter != 0, h->patPlanes.data(), h->dither.data());
+	buildFilterTable(p, h->filterTab);
+	buildDofBounds(p.xsamples, p.ysamples, h->dofBounds);
+	h->shuf8.resize(h->tables.shuffled.size());
+	for(size_t i = 0; i < h->shuf8.size(); ++i) h->shuf8[i] = static_cast<uint8_t>(h->tables.shuffled[i]);
+	h->tableKey = key;
+	h->tablesUploaded = false;
+	return AQH_OK;
+}
+
+int uploadTables(AqhHider* h)
+{
+	if(h->tablesUploaded) return AQH_OK;
+	cudaStream_t st = h->stream;
+	struct Up { DevBuf* b; const void* src; size_t bytes; };
+	const Up ups[] = {
+		{&h->dPosTab, h->tables.pos.data(), h->tables.pos.size()*4},
+		{&h->dVal1d, h->tables.val1d.data(), h->tables.val1d.size()*4},
+		{&h->dShuf, h->shuf8.data(), h->shuf8.size()},
+		{&h->dPat, h->patPlanes.data(), h->patPlanes.size()},
+		{&h->dFilt, h->filterTab.data(), h->filterTab.size()*4},
+		{&h->dDofB, h->dofBounds.data(), h->dofBounds.size()*4},
+		{&h->dDither, h->dither.data(), h->dither.size()*4},
+	};
+	for(const Up& u : ups)
+	{
+		CU(u.b->reserve(std::max<size_t>(u.bytes, 16)), "cudaMalloc(frame tables)");
+		CU(cudaMemcpyAsync(u.b->p, u.src, u.bytes, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(frame tables)");
+		h->stats.h2d_bytes += (int64_t)u.bytes;
+	}
+	CU(cudaStreamSynchronize(st), "cudaStreamSynchronize(frame tables)");
+	h->tablesUploaded = true;
+	return AQH_OK;
+}
+
+// Strips of pixel rows dealt round-robin to the ranks; every rank also hides the `shift` rows
+// of halo samples its filter footprint needs.
+void buildTiling(AqhHider* h, bool mbdof)
+{
+	const AqhFrameParams& p = h->params;
+	const ReplayLayout& L = h->layout;
+	chooseTile(p, mbdof, h->tileW, h->tileH);
+	h->ntx = (L.sw + h->tileW - 1)/h->tileW;
+	h->nty = (L.sh + h->tileH - 1)/h->tileH;
+	const int world = std::max(1, p.world_size);
+	int strip = p.strip_rows > 0 ? p.strip_rows : 64;
+	strip = std::max(h->tileH, (strip/h->tileH)*h->tileH);
+	h->rowOwned.assign(p.yres, 0);
+	h->strips.clear();
+	std::vector<uint8_t> rowNeeded(L.sh, 0);
+	int si = 0;
+	for(int y0 = p.crop_ymin; y0 < p.crop_ymax; y0 += strip, ++si)
+	{
+		if(si % world != (world > 1 ? p.rank : 0)) continue;
+		const int y1 = std::min(y0 + strip, p.crop_ymax);
+		h->strips.push_back(std::make_pair(y0, y1));
+		for(int y = y0; y < y1; ++y) h->rowOwned[y] = 1;
+		for(int y = y0 - L.shiftY; y < y1 + L.shiftY; ++y) rowNeeded[y - L.sy0] = 1;
+	}
+	h->tileSlot.assign(size_t(h->ntx)*h->nty, -1);
+	h->activeTiles.clear();
+	for(int ty = 0; ty < h->nty; ++ty)
+	{
+		bool need = false;
+		for(int r = ty*h->tileH; r < std::min((ty+1)*h->tileH, L.sh) && !need; ++r) need = rowNeeded[r] != 0;
+		if(!need) continue;
+		for(int tx = 0; tx < h->ntx; ++tx)
+		{
+			h->tileSlot[size_t(ty)*h->ntx + tx] = (int32_t)h->activeTiles.size();
+			h->activeTiles.push_back(uint32_t(ty*h->ntx + tx));
+		}
+	}
+}
+
+int appendGridTables(AqhHider* h, int cu, int cv, int nkeys, uint32_t flags, const float* lod, const float* times)
+{
+	if(cu < 1 || cv < 1 || cu > 65535 || cv > 65535) return h->fail(AQH_ERR_BAD_PARAMS, "grid resolution out of range");
+	if(nkeys < 1 || nkeys > 255) return h->fail(AQH_ERR_BAD_PARAMS, "grid key count out of range");
+	if(flags & AQH_GRID_USES_CSG) return h->fail(AQH_ERR_UNSUPPORTED, "CSG grids are not supported");
+	if(nkeys > 1 && !times) return h->fail(AQH_ERR_BAD_PARAMS, "motion grid without key times");
+	h->gcu.push_back(cu); h->gcv.push_back(cv); h->gnkeys.push_back(nkeys); h->gflags.push_back(flags);
+	h->glod.push_back(lod ? lod[0] : -1.f); h->glod.push_back(lod ? lod[1] : -1.f);
+	for(int k = 0; k < nkeys; ++k) h->gkeyTimes.push_back(nkeys > 1 ? times[k] : 0.f);
+	return AQH_OK;
+}
+
+// Everything on the device for the frame.  download: copy the image(s) back to pinned host memory.
+int renderFrame(AqhHider* h, bool download)
+{
+	if(!h->inFrame) return h->fail(AQH_ERR_STATE, "no frame in progress");
+	const AqhFrameParams& p = h->params;
+	const ReplayLayout& L = h->layout;
+	cudaStream_t st = h->stream;
+	AqhFrameStats& S = h->stats;
+	const int64_t nGrids = (int64_t)h->gcu.size();
+	if(h->nPos >= (int64_t)0xfffffff0u) return h->fail(AQH_ERR_BAD_PARAMS, "more than 2^32 grid positions in one frame");
+	if(nGrids > (int64_t)VINFO_GRID_MASK) return h->fail(AQH_ERR_BAD_PARAMS, "more than 2^28 grids in one frame");
+
+	const double tUp0 = nowMs();
+	S.h2d_bytes = 0;
+	int rc = uploadTables(h);
+	if(rc) return rc;
+
+	// ---- host grid tables -> GridRec, chunk index, key times
+	bool anyMotion = false, anyLod = false, anyTri = false, anyCam = false;
+	std::vector<GridRec> recs(std::max<int64_t>(nGrids, 1));
+	{
+		uint64_t vb = 0, pb = 0, ko = 0;
+		for(int64_t g = 0; g < nGrids; ++g)
+		{
+			GridRec& r = recs[g];
+			const uint32_t nv = uint32_t(h->gcu[g]+1)*uint32_t(h->gcv[g]+1);
+			r.vbase = (uint32_t)vb; r.pbase = (uint32_t)pb; r.nverts = nv;
+			r.cu_cv = uint32_t(h->gcu[g]) | (uint32_t(h->gcv[g]) << 16);
+			r.flags = h->gflags[g];
+			r.nkeys_koff = uint32_t(h->gnkeys[g]) | (uint32_t(ko) << 8);
+			r.lod0 = h->glod[2*g]; r.lod1 = h->glod[2*g+1];
+			anyMotion |= h->gnkeys[g] > 1; anyLod |= r.lod0 >= 0.f;
+			anyTri |= (r.flags & AQH_GRID_TRIANGULAR) != 0; anyCam |= (r.flags & AQH_GRID_CAMERA_SPACE) != 0;
+			vb += nv; pb += uint64_t(nv)*h->gnkeys[g]; ko += h->gnkeys[g];
+			if(ko >= (1u << 24)) return h->fail(AQH_ERR_BAD_PARAMS, "too many motion keys in one frame");
+		}
+	}
+	const int64_t nChunks = (h->nPos + 255)/256;
+	std::vector<uint32_t> chunk(nChunks + 2, (uint32_t)std::max<int64_t>(nGrids - 1, 0));
+	{
+		int64_t g = 0;
+		for(int64_t c = 0; c < nChunks; ++c)
+		{
+			const uint64_t first = uint64_t(c)*256;
+			while(g + 1 < nGrids && recs[g+1].pbase <= first) ++g;
+			chunk[c] = (uint32_t)g;
+		}
+	}
+	const bool mbdof = anyMotion || p.use_dof;
+	buildTiling(h, mbdof);
+	const int nActive = (int)h->activeTiles.size();
+
+	// ---- device allocations
+	const size_t nPos = (size_t)h->nPos, nVerts = (size_t)h->nVerts;
+	CU(h->dGrids.reserve(recs.size()*sizeof(GridRec)), "cudaMalloc(grid table)");
+	CU(h->dChunk.reserve(chunk.size()*4), "cudaMalloc(chunk table)");
+	CU(h->dKeyTimes.reserve(std::max<size_t>(h->gkeyTimes.size(), 1)*4), "cudaMalloc(key times)");
+	CU(h->dSplit.reserve(std::max<size_t>(h->gkeyTimes.size(), 1)*16), "cudaMalloc(split lines)");
+	CU(h->dP4.reserve(std::max<size_t>(nPos, 1)*16 + 64), "cudaMalloc(P4)");
+	CU(h->dTileSlot.reserve(std::max<size_t>(h->tileSlot.size(), 1)*4), "cudaMalloc(tile slots)");
+	CU(h->dActive.reserve(std::max<size_t>(nActive, 1)*4), "cudaMalloc(active tiles)");
+	CU(h->dBinCount.reserve(std::max<size_t>(nActive, 1)*4), "cudaMalloc(bin counts)");
+	CU(h->dBinOffset.reserve((size_t(nActive) + 1)*4), "cudaMalloc(bin offsets)");
+	CU(h->dTileFlags.reserve(std::max<size_t>(nActive, 1)*4), "cudaMalloc(tile flags)");
+	CU(h->dMisc.reserve(256), "cudaMalloc(counters)");
+	CU(h->dRowOwned.reserve(p.yres), "cudaMalloc(row ownership)");
+	const size_t planeStride = size_t(L.sw)*L.sh*(p.xsamples*p.ysamples);
+	CU(h->dPlanes.reserve(planeStride*7*4), "cudaMalloc(sample planes)");
+	CU(h->dMask.reserve(planeStride*4), "cudaMalloc(sample mask plane)");
+	CU(h->dChannels.reserve(size_t(p.xres)*p.yres*9*4), "cudaMalloc(channel buffer)");
+	DevDisplays disp{};
+	disp.n = p.n_displays;
+	for(int d = 0; d < p.n_displays; ++d)
+	{
+		const AqhDisplayDesc& dd = p.display[d];
+		DevDisplay& o = disp.d[d];
+		o.nChannels = dd.n_channels;
+		for(int c = 0; c < dd.n_channels; ++c) o.channel[c] = dd.channel[c];
+		o.type = dd.type ? dd.type : selectDataFormat(dd.quantize_one, dd.quantize_min, dd.quantize_max);
+		o.entrySize = typeSize(o.type)*dd.n_channels;
+		o.qZero = dd.quantize_zero; o.qOne = dd.quantize_one; o.qMin = dd.quantize_min; o.qMax = dd.quantize_max;
+		o.qDither = dd.quantize_dither;
+		CU(h->dDisplay[d].reserve(size_t(p.xres)*p.yres*o.entrySize), "cudaMalloc(display image)");
+		o.out = h->dDisplay[d].as<unsigned char>();
+		h->dispType[d] = o.type; h->dispEntry[d] = o.entrySize;
+	}
+
+	// ---- grids into HBM
+	const float* dP = nullptr; const float* dCi = nullptr; const float* dOi = nullptr; const uint8_t* dCulled = nullptr;
+	const bool zeroCopy = h->segments.size() == 1 && h->segments[0].memorySpace == 1;
+	if(zeroCopy)
+	{
+		const Segment& s = h->segments[0];
+		dP = s.P; dCi = s.Ci; dOi = s.Oi; dCulled = s.culled;
+	}
+	else if(nPos)
+	{
+		CU(h->dPraw.reserve(nPos*12), "cudaMalloc(P)");
+		if(h->anyCi) CU(h->dCi.reserve(nVerts*12), "cudaMalloc(Ci)");
+		if(h->anyOi) CU(h->dOi.reserve(nVerts*12), "cudaMalloc(Oi)");
+		if(h->anyCulled) CU(h->dCulled.reserve(nVerts), "cudaMalloc(culled)");
+		if(h->anyCulled) CU(cudaMemsetAsync(h->dCulled.p, 0, nVerts, st), "cudaMemsetAsync(culled)");
+		std::vector<float> ones;
+		size_t po = 0, vo = 0;
+		for(const Segment& s : h->segments)
+		{
+			const float* sP = s.P; const float* sCi = s.Ci; const float* sOi = s.Oi; const uint8_t* sCu = s.culled;
+			if(s.staged)
+			{
+				sP = h->stP.as<float>() + (size_t)(uintptr_t)s.P;
+				sCi = h->stCi.as<float>() + (size_t)(uintptr_t)s.Ci;
+				sOi = h->stOi.as<float>() + (size_t)(uintptr_t)s.Oi;
+				sCu = s.culled ? h->stCulled.as<uint8_t>() + ((size_t)(uintptr_t)s.culled - 1) : nullptr;
+			}
+			const cudaMemcpyKind kind = s.memorySpace ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+			CU(cudaMemcpyAsync(h->dPraw.as<float>() + po*3, sP, size_t(s.nPos)*12, kind, st), "cudaMemcpyAsync(P)");
+			if(!s.memorySpace) S.h2d_bytes += s.nPos*12;
+			for(int which = 0; which < 2; ++which)
+			{
+				const bool any = which ? h->anyOi : h->anyCi;
+				if(!any) continue;
+				const float* src = which ? sOi : sCi;
+				float* dst = (which ? h->dOi.as<float>() : h->dCi.as<float>()) + vo*3;
+				if(src)
+				{
+					CU(cudaMemcpyAsync(dst, src, size_t(s.nVerts)*12, kind, st), "cudaMemcpyAsync(Ci/Oi)");
+					if(!s.memorySpace) S.h2d_bytes += s.nVerts*12;
+				}
+				else
+				{
+					// this run has no Ci/Oi but another one does: materialise the default 1.0
+					ones.assign(size_t(s.nVerts)*3, 1.0f);
+					CU(cudaMemcpyAsync(dst, ones.data(), ones.size()*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(default Ci/Oi)");
+					CU(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+				}
+			}
+			if(h->anyCulled && sCu)
+			{
+				CU(cudaMemcpyAsync(h->dCulled.as<uint8_t>() + vo, sCu, size_t(s.nVerts), kind, st), "cudaMemcpyAsync(culled)");
+				if(!s.memorySpace) S.h2d_bytes += s.nVerts;
+			}
+			po += s.nPos; vo += s.nVerts;
+		}
+		dP = h->dPraw.as<float>();
+		dCi = h->anyCi ? h->dCi.as<float>() : nullptr;
+		dOi = h->anyOi ? h->dOi.as<float>() : nullptr;
+		dCulled = h->anyCulled ? h->dCulled.as<uint8_t>() : nullptr;
+	}
+	CU(cudaMemcpyAsync(h->dGrids.p, recs.data(), recs.size()*sizeof(GridRec), cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(grid table)");
+	CU(cudaMemcpyAsync(h->dChunk.p, chunk.data(), chunk.size()*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(chunk table)");
+	if(!h->gkeyTimes.empty())
+		CU(cudaMemcpyAsync(h->dKeyTimes.p, h->gkeyTimes.data(), h->gkeyTimes.size()*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(key times)");
+	CU(cudaMemcpyAsync(h->dTileSlot.p, h->tileSlot.data(), h->tileSlot.size()*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(tile slots)");
+	if(nActive)
+		CU(cudaMemcpyAsync(h->dActive.p, h->activeTiles.data(), size_t(nActive)*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(active tiles)");
+	CU(cudaMemcpyAsync(h->dRowOwned.p, h->rowOwned.data(), p.yres, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(row ownership)");
+	S.h2d_bytes += (int64_t)(recs.size()*sizeof(GridRec) + chunk.size()*4 + h->gkeyTimes.size()*4 + h->tileSlot.size()*4 + size_t(nActive)*4 + p.yres);
+	CU(cudaStreamSynchronize(st), "cudaStreamSynchronize(upload)");
+	S.upload_ms = nowMs() - tUp0;
+
+	// ---- frame descriptor
+	DevFrame f{};
+	f.xres = p.xres; f.yres = p.yres;
+	f.cropX0 = p.crop_xmin; f.cropX1 = p.crop_xmax; f.cropY0 = p.crop_ymin; f.cropY1 = p.crop_ymax;
+	f.xs = p.xsamples; f.ys = p.ysamples; f.n = f.xs*f.ys;
+	f.shiftX = L.shiftX; f.shiftY = L.shiftY;
+	f.xfwo2 = std::ceil(p.filter_xwidth)*0.5f; f.yfwo2 = std::ceil(p.filter_ywidth)*0.5f;
+	f.clipNear = p.clip_near; f.clipFar = p.clip_far;
+	f.shutterOpen = p.shutter_open; f.shutterClose = p.shutter_close;
+	f.useDof = p.use_dof ? 1 : 0;
+	f.dofMult = p.dof_multiplier; f.dofInvFocal = p.dof_one_over_focal_distance;
+	f.dofScaleX = p.dof_scale_x; f.dofScaleY = p.dof_scale_y;
+	for(int k = 0; k < 3; ++k) f.zthr[k] = p.zthreshold[k];
+	f.expGain = p.exposure_gain; f.expGamma = p.exposure_gamma;
+	f.jitter = p.jitter;
+	std::memcpy(f.camToRaster, p.cam_to_raster, sizeof f.camToRaster);
+	f.anyMotion = anyMotion; f.anyTransparent = (dOi != nullptr); f.anyLod = anyLod; f.anyTriangular = anyTri; f.anyCamera = anyCam;
+	f.sx0 = L.sx0; f.sy0 = L.sy0; f.sw = L.sw; f.sh = L.sh;
+	f.tileW = h->tileW; f.tileH = h->tileH; f.ntx = h->ntx; f.nty = h->nty; f.nActiveTiles = nActive;
+	f.Praw = dP; f.Ci = dCi; f.Oi = dOi; f.culled = dCulled;
+	f.grids = h->dGrids.as<GridRec>(); f.chunkGrid = h->dChunk.as<uint32_t>();
+	f.keyTimes = h->dKeyTimes.as<float>(); f.splitLines = h->dSplit.as<float4>();
+	f.nPos = h->nPos; f.nVerts = h->nVerts; f.nGrids = (int)nGrids;
+	f.P4 = h->dP4.as<float4>();
+	f.posTab = h->dPosTab.as<float2>(); f.val1d = h->dVal1d.as<float>(); f.shufTab = h->dShuf.as<uint8_t>();
+	f.patPlanes = h->dPat.as<uint8_t>(); f.filterTab = h->dFilt.as<float>(); f.dofBounds = h->dDofB.as<float4>();
+	f.dither = h->dDither.as<float>();
+	f.tileSlot = h->dTileSlot.as<int32_t>(); f.activeTiles = h->dActive.as<uint32_t>();
+	f.binCount = h->dBinCount.as<uint32_t>(); f.binOffset = h->dBinOffset.as<uint32_t>();
+	f.tileFlags = h->dTileFlags.as<uint32_t>();
+	f.tileCursor = h->dMisc.as<uint32_t>();
+	f.errorFlags = h->dMisc.as<uint32_t>() + 1;
+	f.counters = reinterpret_cast<unsigned long long*>(h->dMisc.as<unsigned char>() + 16);
+	f.planes = h->dPlanes.as<float>(); f.maskPlane = h->dMask.as<uint32_t>(); f.planeStride = (int64_t)planeStride;
+	f.channels = h->dChannels.as<float>();
+	f.rowOwned = (std::max(1, p.world_size) > 1) ? h->dRowOwned.as<uint8_t>() : nullptr;
+
+	LaunchCfg cfg{};
+	CU(hideKernelConfig(f, h->smCount, cfg), "hide kernel configuration (shared memory / occupancy)");
+	if(f.anyTransparent)
+	{
+		const int per = p.deep_hits_per_sample > 0 ? p.deep_hits_per_sample : 8;
+		f.deepCapPerCta = uint32_t(per)*uint32_t(f.tileW*f.tileH*f.n);
+		CU(h->dDeepA.reserve(size_t(cfg.hideCtas)*f.deepCapPerCta*16), "cudaMalloc(deep hit pool)");
+		CU(h->dDeepUV.reserve(size_t(cfg.hideCtas)*f.deepCapPerCta*8), "cudaMalloc(deep hit pool)");
+		f.deepA = h->dDeepA.as<uint4>(); f.deepUV = h->dDeepUV.as<float2>();
+	}
+
+	// ---- device work
+	S.gpu_launches = 0;
+	CU(cudaEventRecord(h->ev[0], st), "cudaEventRecord");
+	CU(cudaMemsetAsync(h->dMisc.p, 0, 256, st), "cudaMemsetAsync");
+	CU(cudaMemsetAsync(h->dBinCount.p, 0, std::max<size_t>(nActive, 1)*4, st), "cudaMemsetAsync");
+	CU(cudaMemsetAsync(h->dChannels.p, 0, size_t(p.xres)*p.yres*9*4, st), "cudaMemsetAsync");
+	for(int d = 0; d < p.n_displays; ++d)
+		CU(cudaMemsetAsync(h->dDisplay[d].p, 0, size_t(p.xres)*p.yres*disp.d[d].entrySize, st), "cudaMemsetAsync");
+	CU(launchProject(f, st), "k_project"); S.gpu_launches += nPos ? 2 : 0;
+	CU(launchBinCount(f, st), "k_bin<count>"); S.gpu_launches += nPos ? 1 : 0;
+	CU(launchBinScan(f, st), "k_bin_scan"); S.gpu_launches += 1;
+	// the fill pass needs the total entry count to size the list
+	uint32_t totalEntries = 0;
+	CU(cudaMemcpyAsync(&totalEntries, f.binOffset + nActive, 4, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(bin total)");
+	CU(cudaStreamSynchronize(st), "bin count");
+	CU(h->dBinEntries.reserve(std::max<size_t>(totalEntries, 1)*4), "cudaMalloc(bin entries)");
+	f.binEntries = h->dBinEntries.as<uint32_t>();
+	CU(launchBinFill(f, st), "k_bin<fill>"); S.gpu_launches += (nPos ? 1 : 0) + (nActive ? 1 : 0);
+	CU(cudaEventRecord(h->ev[1], st), "cudaEventRecord");
+	CU(launchHide(f, cfg, st), "k_hide"); S.gpu_launches += nActive ? 1 : 0;
+	CU(cudaEventRecord(h->ev[2], st), "cudaEventRecord");
+	CU(launchFilter(f, disp, st), "k_filter"); S.gpu_launches += 1;
+	CU(cudaEventRecord(h->ev[3], st), "cudaEventRecord");
+
+	// ---- results
+	struct { uint32_t cursor, err; uint32_t pad[2]; unsigned long long ctr[3]; } misc;
+	CU(cudaMemcpyAsync(&misc, h->dMisc.p, sizeof misc, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(counters)");
+	const double tDown0 = nowMs();
+	S.d2h_bytes = 0;
+	if(download)
+	{
+		const size_t chBytes = size_t(p.xres)*p.yres*9*4;
+		if(!h->hChannels.reserve(chBytes)) return h->fail(AQH_ERR_NO_MEMORY, "cudaHostAlloc(channel image)");
+		CU(cudaMemcpyAsync(h->hChannels.p, h->dChannels.p, chBytes, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(channels)");
+		S.d2h_bytes += (int64_t)chBytes;
+		for(int d = 0; d < p.n_displays; ++d)
+		{
+			const size_t b = size_t(p.xres)*p.yres*disp.d[d].entrySize;
+			if(!h->hDisplay[d].reserve(b)) return h->fail(AQH_ERR_NO_MEMORY, "cudaHostAlloc(display image)");
+			CU(cudaMemcpyAsync(h->hDisplay[d].p, h->dDisplay[d].p, b, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(display)");
+			S.d2h_bytes += (int64_t)b;
+		}
+	}
+	CU(cudaStreamSynchronize(st), "cudaStreamSynchronize(frame)");
+	S.download_ms = download ? nowMs() - tDown0 : 0.0;
+	h->haveHostImage = download;
+	float ms = 0;
+	cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); S.project_bust_ms = ms;
+	cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); S.render_mpgs_ms = ms;
+	cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); S.filter_ms = ms; S.display_ms = 0;
+	cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]); S.device_total_ms = ms;
+	S.n_grids = nGrids; S.n_vertices = h->nVerts;
+	S.n_micropolygons = (int64_t)misc.ctr[0]; S.n_bin_entries = (int64_t)misc.ctr[1]; S.n_deep_hits = (int64_t)misc.ctr[2];
+	S.n_samples = int64_t(L.sw)*L.sh*f.n;
+	h->rendered = true;
+	if(misc.err & 1u)
+		return h->fail(AQH_ERR_DEEP_OVERFLOW, "transparent hit pool exhausted: raise AqhFrameParams::deep_hits_per_sample");
+	return AQH_OK;
+}
+
+} // namespace
+
+// =====================================================================================
+extern "C" {
+
+int aqh_abi_version(void) { return AQH_ABI_VERSION; }
+
+int aqh_create(AqhHider** out, int device)
+{
+	if(!out) return AQH_ERR_BAD_PARAMS;
+	*out = nullptr;
+	int count = 0;
+	if(cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count)
+		return AQH_ERR_NO_DEVICE;
+	if(cudaSetDevice(device) != cudaSuccess) return AQH_ERR_NO_DEVICE;
+	cudaDeviceProp prop;
+	if(cudaGetDeviceProperties(&prop, device) != cudaSuccess) return AQH_ERR_NO_DEVICE;
+	if(!kernelsArchOk()) return AQH_ERR_NO_DEVICE;   // the library only carries sm_100a code
+	AqhHider* h = new AqhHider;
+	h->device = device;
+	h->smCount = prop.multiProcessorCount;
+	if(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return AQH_ERR_CUDA; }
+	h->ownStream = true;
+	for(int i = 0; i < 8; ++i) cudaEventCreate(&h->ev[i]);
+	*out = h;
+	return AQH_OK;
+}
+
+int aqh_destroy(AqhHider* h)
+{
+	if(!h) return AQH_OK;
+	cudaSetDevice(h->device);
+	cudaStreamSynchronize(h->stream);
+	DevBuf* bufs[] = {&h->dPraw, &h->dCi, &h->dOi, &h->dCulled, &h->dP4, &h->dGrids, &h->dChunk, &h->dKeyTimes, &h->dSplit,
+	                  &h->dPosTab, &h->dVal1d, &h->dShuf, &h->dPat, &h->dFilt, &h->dDofB, &h->dDither, &h->dTileSlot, &h->dActive,
+	                  &h->dBinCount, &h->dBinOffset, &h->dBinEntries, &h->dMisc, &h->dTileFlags, &h->dPlanes, &h->dMask,
+	                  &h->dDeepA, &h->dDeepUV, &h->dChannels, &h->dRowOwned};
+	for(DevBuf* b : bufs) b->release();
+	for(int d = 0; d < AQH_MAX_DISPLAYS; ++d) { h->dDisplay[d].release(); h->hDisplay[d].release(); }
+	h->hChannels.release(); h->stP.release(); h->stCi.release(); h->stOi.release(); h->stCulled.release();
+	for(int i = 0; i < 8; ++i) if(h->ev[i]) cudaEventDestroy(h->ev[i]);
+	if(h->ownStream && h->stream) cudaStreamDestroy(h->stream);
+	delete h;
+	return AQH_OK;
+}
+
+const char* aqh_last_error(const AqhHider* h) { return h ? h->lastError.c_str() : "null hider"; }
+
+int aqh_set_stream(AqhHider* h, void* cuda_stream)
+{
+	if(!h) return AQH_ERR_BAD_PARAMS;
+	if(h->inFrame) return h->fail(AQH_ERR_STATE, "cannot change stream inside a frame");
+	if(h->ownStream && h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+	h->stream = static_cast<cudaStream_t>(cuda_stream);
+	h->ownStream = false;
+	return AQH_OK;
+}
+
+int aqh_frame_params_default(AqhFrameParams* p)
+{
+	if(!p) return AQH_ERR_BAD_PARAMS;
+	std::memset(p, 0, sizeof *p);
+	p->abi_version = AQH_ABI_VERSION;
+	// CqOptions defaults, libs/core/options.cpp:273-305
+	p->xres = 640; p->yres = 480;
+	p->crop_xmin = 0; p->crop_xmax = 640; p->crop_ymin = 0; p->crop_ymax = 480;
+	p->xsamples = 2; p->ysamples = 2;
+	p->filter_xwidth = 2.f; p->filter_ywidth = 2.f;
+	p->filter_func = aqh_gaussian_filter;
+	p->bucket_xsize = 16; p->bucket_ysize = 16;
+	p->clip_near = FLT_EPSILON; p->clip_far = FLT_MAX;
+	p->shutter_open = 0.f; p->shutter_close = 0.f;
+	p->use_dof = 0;
+	p->depth_filter = AQH_DEPTHFILTER_MIN;
+	p->zthreshold[0] = p->zthreshold[1] = p->zthreshold[2] = 1.f;
+	p->display_mode = AQH_DMODE_RGB | AQH_DMODE_A;
+	p->exposure_gain = 1.f; p->exposure_gamma = 1.f;
+	p->jitter = 1;
+	for(int i = 0; i < 4; ++i) p->cam_to_raster[i*4+i] = 1.f;
+	p->rng_seed = 545;      // CqRandom().Reseed(545), ri.cpp:660
+	p->rng_predraws = 0;
+	p->n_displays = 0;
+	p->rank = 0; p->world_size = 1;
+	return AQH_OK;
+}
+
+int aqh_frame_params_set_dof(AqhFrameParams* p, float fstop, float focallength, float focaldistance, float scale_x, float scale_y)
+{
+	if(!p) return AQH_ERR_BAD_PARAMS;
+	// CqRenderer::SetDepthOfFieldData, renderer.h:368-377
+	p->use_dof = (fstop < FLT_MAX) ? 1 : 0;
+	if(fstop < FLT_MAX)
+	{
+		float lensDiameter = focallength / fstop;
+		p->dof_multiplier = static_cast<float>(0.5 * lensDiameter * focaldistance / (focaldistance + lensDiameter));
+		p->dof_one_over_focal_distance = static_cast<float>(1.0 / focaldistance);
+	}
+	p->dof_scale_x = scale_x; p->dof_scale_y = scale_y;
+	return AQH_OK;
+}
+
+int aqh_display_from_mode(AqhDisplayDesc* d, const char* mode, int driver_order, float one, float mn, float mx, float dither)
+{
+	if(!d || !mode) return AQH_ERR_BAD_PARAMS;
+	std::memset(d, 0, sizeof *d);
+	const bool rgb = std::strstr(mode, "rgb") != nullptr;
+	const bool a = std::strchr(mode, 'a') != nullptr;
+	const bool z = std::strchr(mode, 'z') != nullptr;
+	if(!rgb && !a && !z) return AQH_ERR_BAD_PARAMS;
+	int n = 0;
+	if(!driver_order && a) d->channel[n++] = AQH_CH_ALPHA;     // core order a,r,g,b,z (ddmanager.cpp:455-480)
+	if(rgb) { d->channel[n++] = AQH_CH_CI_R; d->channel[n++] = AQH_CH_CI_G; d->channel[n++] = AQH_CH_CI_B; }
+	if(driver_order && a) d->channel[n++] = AQH_CH_ALPHA;      // file driver order r,g,b,a (display.cpp:454-490)
+	if(z) d->channel[n++] = AQH_CH_Z;
+	d->n_channels = n;
+	d->type = 0;
+	d->quantize_zero = 0.f; d->quantize_one = one; d->quantize_min = mn; d->quantize_max = mx; d->quantize_dither = dither;
+	return AQH_OK;
+}
+
+int aqh_begin_frame(AqhHider* h, const AqhFrameParams* p)
+{
+	if(!h || !p) return AQH_ERR_BAD_PARAMS;
+	if(cudaSetDevice(h->device) != cudaSuccess) return h->fail(AQH_ERR_NO_DEVICE, "cudaSetDevice failed");
+	int rc = validateParams(h, *p);
+	if(rc) return rc;
+	h->params = *p;
+	if(h->params.world_size < 1) { h->params.world_size = 1; h->params.rank = 0; }
+	if(!h->params.filter_func) h->params.filter_func = aqh_gaussian_filter;
+	std::memset(&h->stats, 0, sizeof h->stats);
+	const double t0 = nowMs();
+	rc = buildTables(h);
+	if(rc) return rc;
+	h->stats.prepare_ms = nowMs() - t0;
+	resetFrameGrids(h);
+	h->inFrame = true; h->rendered = false; h->haveHostImage = false;
+	return AQH_OK;
+}
+
+int aqh_add_grid(AqhHider* h, const AqhGridDesc* g)
+{
+	if(!h || !g) return AQH_ERR_BAD_PARAMS;
+	if(!h->inFrame) return h->fail(AQH_ERR_STATE, "aqh_add_grid outside aqh_begin_frame/aqh_end_frame");
+	if(!g->P) return h->fail(AQH_ERR_BAD_PARAMS, "grid without P");
+	int rc = appendGridTables(h, g->cu, g->cv, g->nkeys, g->flags, g->lod_bounds, g->key_times);
+	if(rc) return rc;
+	const size_t nv = size_t(g->cu+1)*(g->cv+1), np = nv*g->nkeys;
+	// copy into the pinned staging run (the caller keeps ownership of its arrays)
+	if(!h->stP.reserve((h->stPUsed + np)*12, true, h->stPUsed*12) ||
+	   !h->stCi.reserve((h->stVUsed + nv)*12, true, h->stVUsed*12) ||
+	   !h->stOi.reserve((h->stVUsed + nv)*12, true, h->stVUsed*12) ||
+	   !h->stCulled.reserve(h->stVUsed + nv, true, h->stVUsed))
+		return h->fail(AQH_ERR_NO_MEMORY, "cudaHostAlloc(grid staging)");
+	for(int k = 0; k < g->nkeys; ++k)
+	{
+		if(!g->P[k]) return h->fail(AQH_ERR_BAD_PARAMS, "grid key without P");
+		std::memcpy(h->stP.as<float>() + (h->stPUsed + size_t(k)*nv)*3, g->P[k], nv*12);
+	}
+	float* ci = h->stCi.as<float>() + h->stVUsed*3;
+	float* oi = h->stOi.as<float>() + h->stVUsed*3;
+	if(g->Ci) std::memcpy(ci, g->Ci, nv*12); else std::fill(ci, ci + nv*3, 1.0f);
+	if(g->Oi) std::memcpy(oi, g->Oi, nv*12); else std::fill(oi, oi + nv*3, 1.0f);
+	uint8_t* cu8 = h->stCulled.as<uint8_t>() + h->stVUsed;
+	if(g->culled) std::memcpy(cu8, g->culled, nv); else std::memset(cu8, 0, nv);
+	// extend the trailing staged segment or open a new one
+	if(h->segments.empty() || !h->segments.back().staged)
+	{
+		Segment s;
+		s.firstGrid = (int64_t)h->gcu.size() - 1;
+		s.staged = true; s.memorySpace = 0;
+		// staged pointers are kept as OFFSETS (the pinned buffers may move when they grow)
+		s.P = reinterpret_cast<const float*>(uintptr_t(h->stPUsed*3));
+		s.Ci = reinterpret_cast<const float*>(uintptr_t(h->stVUsed*3));
+		s.Oi = reinterpret_cast<const float*>(uintptr_t(h->stVUsed*3));
+		s.culled = reinterpret_cast<const uint8_t*>(uintptr_t(h->stVUsed + 1));
+		h->segments.push_back(s);
+	}
+	Segment& s = h->segments.back();
+	s.nGrids += 1; s.nVerts += (int64_t)nv; s.nPos += (int64_t)np;
+	h->stPUsed += np; h->stVUsed += nv;
+	h->nVerts += (int64_t)nv; h->nPos += (int64_t)np;
+	h->anyCi = h->anyOi = true;
+	if(g->culled) h->anyCulled = true;
+	return AQH_OK;
+}
+
+int aqh_add_grid_block(AqhHider* h, const AqhGridBlock* b)
+{
+	if(!h || !b) return AQH_ERR_BAD_PARAMS;
+	if(!h->inFrame) return h->fail(AQH_ERR_STATE, "aqh_add_grid_block outside aqh_begin_frame/aqh_end_frame");
+	if(b->n_grids < 0 || (b->n_grids > 0 && (!b->cu || !b->cv || !b->flags || !b->P)))
+		return h->fail(AQH_ERR_BAD_PARAMS, "grid block tables missing");
+	if(b->memory_space != 0 && b->memory_space != 1) return h->fail(AQH_ERR_BAD_PARAMS, "memory_space");
+	Segment s;
+	s.firstGrid = (int64_t)h->gcu.size();
+	s.nGrids = b->n_grids;
+	s.P = b->P; s.Ci = b->Ci; s.Oi = b->Oi; s.culled = b->culled;
+	s.memorySpace = b->memory_space;
+	size_t ko = 0;
+	for(int64_t g = 0; g < b->n_grids; ++g)
+	{
+		const int nk = b->nkeys ? b->nkeys[g] : 1;
+		int rc = appendGridTables(h, b->cu[g], b->cv[g], nk, b->flags[g], b->lod_bounds ? b->lod_bounds + 2*g : nullptr,
+		                          (b->key_times && nk > 1) ? b->key_times + ko : nullptr);
+		if(rc) return rc;
+		ko += nk;
+		const int64_t nv = int64_t(b->cu[g]+1)*(b->cv[g]+1);
+		s.nVerts += nv; s.nPos += nv*nk;
+	}
+	if(b->n_grids == 0) return AQH_OK;
+	h->segments.push_back(s);
+	h->nVerts += s.nVerts; h->nPos += s.nPos;
+	if(b->Ci) h->anyCi = true;
+	if(b->Oi) h->anyOi = true;
+	if(b->culled) h->anyCulled = true;
+	return AQH_OK;
+}
+
+int aqh_render_device(AqhHider* h)
+{
+	if(!h) return AQH_ERR_BAD_PARAMS;
+	if(cudaSetDevice(h->device) != cudaSuccess) return h->fail(AQH_ERR_NO_DEVICE, "cudaSetDevice failed");
+	return renderFrame(h, false);
+}
+
+int aqh_end_frame(AqhHider* h, const AqhCallbacks* cb)
+{
+	if(!h) return AQH_ERR_BAD_PARAMS;
+	if(cudaSetDevice(h->device) != cudaSuccess) return h->fail(AQH_ERR_NO_DEVICE, "cudaSetDevice failed");
+	int rc = renderFrame(h, true);
+	h->inFrame = false;
+	if(rc) return rc;
+	if(!cb || (!cb->on_bucket && !cb->on_data && !cb->on_progress)) return AQH_OK;
+	// Buckets in the reference's row-major order (imagebuffer.cpp:708-733, NextBucket :791-802).
+	const AqhFrameParams& p = h->params;
+	const ReplayLayout& L = h->layout;
+	std::vector<unsigned char> bucketData;
+	const int total = (L.bx1 - L.bx0)*(L.by1 - L.by0);
+	int done = 0;
+	for(int row = L.by0; row < L.by1; ++row)
+		for(int col = L.bx0; col < L.bx1; ++col)
+		{
+			const int xPos = col*p.bucket_xsize, yPos = row*p.bucket_ysize;
+			const int xSize = std::min(p.bucket_xsize, p.xres - xPos), ySize = std::min(p.bucket_ysize, p.yres - yPos);
+			if(cb->on_bucket)
+			{
+				const float* ch = h->hChannels.as<float>() + (size_t(yPos)*p.xres + xPos)*9;
+				if(cb->on_bucket(cb->user, xPos, xPos + xSize, yPos, yPos + ySize, ch, p.xres*9))
+					return h->fail(AQH_ERR_CALLBACK, "on_bucket callback failed");
+			}
+			if(cb->on_data)
+				for(int d = 0; d < p.n_displays; ++d)
+				{
+					const int es = h->dispEntry[d];
+					bucketData.resize(size_t(xSize)*ySize*es);
+					for(int y = 0; y < ySize; ++y)
+						std::memcpy(&bucketData[size_t(y)*xSize*es],
+						            h->hDisplay[d].as<unsigned char>() + (size_t(yPos + y)*p.xres + xPos)*es, size_t(xSize)*es);
+					if(cb->on_data(cb->user, d, xPos, xPos + xSize, yPos, yPos + ySize, es, bucketData.data()))
+						return h->fail(AQH_ERR_CALLBACK, "on_data callback failed");
+				}
+			++done;
+			if(cb->on_progress) cb->on_progress(cb->user, (100.0f*done)/static_cast<float>(total));
+		}
+	if(cb->on_progress) cb->on_progress(cb->user, 100.0f);
+	return AQH_OK;
+}
+
+int aqh_frame_stats(const AqhHider* h, AqhFrameStats* out)
+{
+	if(!h || !out) return AQH_ERR_BAD_PARAMS;
+	*out = h->stats;
+	return AQH_OK;
+}
+
+int aqh_image_channels(const AqhHider* h, const float** data, int* width, int* height)
+{
+	if(!h || !data) return AQH_ERR_BAD_PARAMS;
+	if(!h->haveHostImage) return AQH_ERR_STATE;
+	*data = h->hChannels.as<float>();
+	if(width) *width = h->params.xres;
+	if(height) *height = h->params.yres;
+	return AQH_OK;
+}
+
+int aqh_image_display(const AqhHider* h, int display, const unsigned char** data, int* entrysize, int* type)
+{
+	if(!h || !data || display < 0 || display >= h->params.n_displays) return AQH_ERR_BAD_PARAMS;
+	if(!h->haveHostImage) return AQH_ERR_STATE;
+	*data = h->hDisplay[display].as<unsigned char>();
+	if(entrysize) *entrysize = h->dispEntry[display];
+	if(type) *type = h->dispType[display];
+	return AQH_OK;
+}
+
+int aqh_device_channels(const AqhHider* h, void** dev_ptr, size_t* bytes)
+{
+	if(!h || !dev_ptr) return AQH_ERR_BAD_PARAMS;
+	if(!h->rendered) return AQH_ERR_STATE;
+	*dev_ptr = h->dChannels.p;
+	if(bytes) *bytes = size_t(h->params.xres)*h->params.yres*9*4;
+	return AQH_OK;
+}
+
+int aqh_device_display(const AqhHider* h, int display, void** dev_ptr, size_t* bytes)
+{
+	if(!h || !dev_ptr || display < 0 || display >= h->params.n_displays) return AQH_ERR_BAD_PARAMS;
+	if(!h->rendered) return AQH_ERR_STATE;
+	*dev_ptr = h->dDisplay[display].p;
+	if(bytes) *bytes = size_t(h->params.xres)*h->params.yres*h->dispEntry[display];
+	return AQH_OK;
+}
+
+int aqh_num_strips(const AqhHider* h, int* n)
+{
+	if(!h || !n) return AQH_ERR_BAD_PARAMS;
+	*n = (int)h->strips.size();
+	return AQH_OK;
+}
+
+int aqh_strip(const AqhHider* h, int i, int* y0, int* y1)
+{
+	if(!h || i < 0 || i >= (int)h->strips.size()) return AQH_ERR_BAD_PARAMS;
+	if(y0) *y0 = h->strips[i].first;
+	if(y1) *y1 = h->strips[i].second;
+	return AQH_OK;
+}
+
+// ---- host-side leaves ----------------------------------------------------------------
+struct AqhRandom { Random r; };
+AqhRandom* aqh_random_create(uint32_t seed) { AqhRandom* r = new AqhRandom; r->r.reseed(seed); return r; }
+void aqh_random_destroy(AqhRandom* r) { delete r; }
+void aqh_random_reseed(AqhRandom* r, uint32_t seed) { r->r.reseed(seed); }
+uint32_t aqh_random_uint(AqhRandom* r) { return r->r.nextUint(); }
+float aqh_random_float(AqhRandom* r) { return r->r.nextFloat(); }
+uint32_t aqh_random_int(AqhRandom* r, uint32_t range) { return r->r.nextInt(range); }
+
+int aqh_sampler_tables(AqhRandom* r, int xs, int ys, int jitter, float* pos, float* v1d, int32_t* shuffled, int* ncache)
+{
+	if(!r || xs < 1 || ys < 1 || !pos || !v1d || !shuffled) return AQH_ERR_BAD_PARAMS;
+	SamplerTables t;
+	if(jitter) buildJitterTables(r->r, xs, ys, t); else buildGridTables(xs, ys, t);
+	std::memcpy(pos, t.pos.data(), t.pos.size()*4);
+	std::memcpy(v1d, t.val1d.data(), t.val1d.size()*4);
+	std::memcpy(shuffled, t.shuffled.data(), t.shuffled.size()*4);
+	if(ncache) *ncache = t.ncache;
+	return AQH_OK;
+}
+
+int aqh_replay_frame_rng(const AqhFrameParams* p, uint8_t* planes, float* dither, int* sx0, int* sy0, int* sw, int* sh)
+{
+	if(!p || p->xsamples < 1 || p->ysamples < 1 || p->bucket_xsize < 1 || p->bucket_ysize < 1) return AQH_ERR_BAD_PARAMS;
+	ReplayLayout L = replayLayout(*p);
+	if(sx0) *sx0 = L.sx0; if(sy0) *sy0 = L.sy0; if(sw) *sw = L.sw; if(sh) *sh = L.sh;
+	if(!planes) return AQH_OK;
+	Random rng(p->rng_seed);
+	rng.discard(p->rng_predraws);
+	SamplerTables jit;
+	buildJitterTables(rng, p->xsamples, p->ysamples, jit);
+	replayFrame(*p, L, rng, p->jitter != 0, planes, dither);
+	return AQH_OK;
+}
+
+int aqh_filter_table(const AqhFrameParams* p, float* table, int* n_entries)
+{
+	if(!p) return AQH_ERR_BAD_PARAMS;
+	std::vector<float> t;
+	buildFilterTable(*p, t);
+	if(table) std::memcpy(table, t.data(), t.size()*4);
+	if(n_entries) *n_entries = (int)t.size();
+	return AQH_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,133 @@
+// hider_device.h -- structures shared by the host driver (hider_api.cpp) and the
+// sm_100a kernels (hider_kernels.cu).
+#ifndef AQSIS_B200_HIDER_DEVICE_H
+#define AQSIS_B200_HIDER_DEVICE_H
+
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/aqsis_b200_hider.h"
+
+namespace aqh {
+
+// Per-grid record in HBM (32 B).
+struct GridRec
+{
+	uint32_t vbase;     // first vertex of the grid in the Ci/Oi/culled arrays
+	uint32_t pbase;     // first position of the grid in the P arrays (key-major inside the grid)
+	uint32_t nverts;    // (cu+1)*(cv+1)
+	uint32_t cu_cv;     // cu | cv << 16
+	uint32_t flags;     // AQH_GRID_*
+	uint32_t nkeys_koff;// nkeys | key offset << 8  (key offset indexes keyTimes / splitLines)
+	float lod0, lod1;
+};
+
+// info word stored in P4.w (as float bits) by the project kernel
+enum : uint32_t
+{
+	VINFO_GRID_MASK  = 0x0fffffffu,
+	VINFO_OPAQUE     = 1u << 28,   // Oi >= 1 in all channels at this vertex (or no Oi)
+	VINFO_MP_VALID   = 1u << 29    // a micropolygon starts at this vertex (iu<cu, iv<cv, not culled)
+};
+
+// Everything the kernels need about the frame; passed by value (<= 4 KB of kernel params).
+struct DevFrame
+{
+	// options
+	int xres, yres;
+	int cropX0, cropX1, cropY0, cropY1;
+	int xs, ys, n;
+	int shiftX, shiftY;            // m_DiscreteShiftX/Y
+	float xfwo2, yfwo2;            // ceil(filterwidth)*0.5f
+	float clipNear, clipFar;
+	float shutterOpen, shutterClose;
+	int useDof;
+	float dofMult, dofInvFocal, dofScaleX, dofScaleY;
+	float zthr[3];
+	float expGain, expGamma;
+	int jitter;                    // 0: pattern index is always 0 and ncache == 1
+	float camToRaster[16];
+	int anyMotion, anyTransparent, anyLod, anyTriangular, anyCamera;
+	// sample region and tiling
+	int sx0, sy0, sw, sh;          // global sample region [crop-shift, crop+shift)
+	int tileW, tileH, ntx, nty;    // tiles cover the sample region
+	int nActiveTiles;
+	// inputs
+	const float* Praw;             // n_pos*3
+	const float* Ci;               // n_verts*3 or null
+	const float* Oi;               // n_verts*3 or null
+	const uint8_t* culled;         // n_verts or null
+	const GridRec* grids;
+	const uint32_t* chunkGrid;     // grid index of the first position of each 256-position chunk (+1 sentinel)
+	const float* keyTimes;         // per grid nkeys floats at key offset
+	float4* splitLines;            // per (grid,key): Ax,Ay,Bx,By (written by the project kernel)
+	int64_t nPos, nVerts;
+	int nGrids;
+	// derived geometry
+	float4* P4;                    // n_pos: raster x, raster y, camera z, info bits
+	// frame tables
+	const float2* posTab;          // ncache*n
+	const float* val1d;            // ncache*n
+	const uint8_t* shufTab;        // ncache*n (n <= 256)
+	const uint8_t* patPlanes;      // 5 planes of sw*sh
+	const float* filterTab;        // (2*shiftX+1)*(2*shiftY+1)*n
+	const float4* dofBounds;       // n: minx, miny, maxx, maxy
+	const float* dither;           // n_displays * xres*yres
+	// tiles / bins
+	const int32_t* tileSlot;       // ntx*nty: index into the active tile list or -1
+	const uint32_t* activeTiles;   // nActiveTiles tile ids
+	uint32_t* binCount;            // nActiveTiles
+	uint32_t* binOffset;           // nActiveTiles+1
+	uint32_t* binEntries;
+	uint32_t* tileCursor;          // persistent-CTA work counter
+	uint32_t* tileFlags;           // per active tile: bit0 = has non-opaque MPs
+	// resolved samples: planes [k][s][y][x] over the sample region
+	float* planes;                 // 7 planes: R G B Or Og Ob Z
+	uint32_t* maskPlane;           // bits 0-14 x-tap inclusion, 15-29 y-tap inclusion, 31 valid
+	int64_t planeStride;           // n*sw*sh
+	// deep (transparent) hit pool, per persistent CTA
+	uint4* deepA;                  // next, depth bits, p, sample index
+	float2* deepUV;
+	uint32_t deepCapPerCta;
+	uint32_t* errorFlags;          // bit0: deep pool overflow
+	unsigned long long* counters;  // [0] MPs binned, [1] bin entries, [2] deep hits
+	// output
+	float* channels;               // xres*yres*9
+	const uint8_t* rowOwned;       // yres: 1 when this rank owns the pixel row
+};
+
+struct DevDisplay
+{
+	int nChannels;
+	int channel[AQH_MAX_DISPLAY_CHANNELS];
+	int type;
+	int entrySize;
+	float qZero, qOne, qMin, qMax, qDither;
+	unsigned char* out;            // xres*yres*entrySize
+};
+struct DevDisplays
+{
+	int n;
+	DevDisplay d[AQH_MAX_DISPLAYS];
+};
+
+struct LaunchCfg
+{
+	int smCount;
+	int hideThreads;       // threads per CTA of the hide kernel
+	int hideCtas;          // persistent CTAs
+	size_t hideSmemBytes;
+	int batchMPs;
+};
+
+// kernel launchers (hider_kernels.cu); all asynchronous on `st`.
+cudaError_t launchProject(const DevFrame& f, cudaStream_t st);
+cudaError_t launchBinCount(const DevFrame& f, cudaStream_t st);
+cudaError_t launchBinScan(const DevFrame& f, cudaStream_t st);
+cudaError_t launchBinFill(const DevFrame& f, cudaStream_t st);
+cudaError_t launchHide(const DevFrame& f, const LaunchCfg& cfg, cudaStream_t st);
+cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, cudaStream_t st);
+cudaError_t hideKernelConfig(const DevFrame& f, int smCount, LaunchCfg& cfg);
+int kernelsArchOk();   // 1 when the loaded kernel image can run on the current device
+
+} // namespace aqh
+#endif

@@ -1,0 +1,1442 @@
+// hider_kernels.cu -- sm_100a kernels of the REYES hider + pixel filter.
+//
+// Compile with -fmad=false: every float operation below must round exactly like the
+// reference's x86-64 build, which has no fused multiply-add (SURVEY.md section 7,
+// "bit-stable parity without FMA").  Divisions and square roots are the IEEE ones
+// (nvcc defaults -prec-div=true -prec-sqrt=true; never --use_fast_math).
+//
+// Kernels (DESIGN.md has the data layout and the roofline of each):
+//   k_project    Project_points: raw P -> raster x,y + camera z, vertex info bits, split lines
+//                (CqMicroPolyGrid::Split, libs/core/micropolygon.cpp:684-749)
+//   k_bin_*      Bust_grids + AddMPG: micropolygon bound -> tile lists
+//                (micropolygon.cpp:770-856, imagebuffer.cpp:514-591)
+//   k_hide       Prepare_bucket + Render_MPGs + Combine_samples for one tile per CTA
+//                (bucketprocessor.cpp:95-206, 1067-1569; imagepixel.cpp:144-359)
+//   k_filter     Filter_samples + ExposeBucket + quantise
+//                (bucketprocessor.cpp:584-707, 766-806; ddmanager.cpp:1022-1118)
+#include "hider_device.h"
+
+#include <cfloat>
+
+namespace aqh {
+
+// ------------------------------------------------------------------------------------
+// scalar helpers (include/aqsis/math/math.h:47-125)
+__device__ __forceinline__ float minA(float a, float b) { return (a < b) ? a : b; }
+__device__ __forceinline__ float maxA(float a, float b) { return (a < b) ? b : a; }
+__device__ __forceinline__ int lceilF(float x) { int i = (int)x; return i + ((x > 0.f && x != (float)i) ? 1 : 0); }
+__device__ __forceinline__ int lfloorF(float x) { int i = (int)x; return i - ((x < 0.f && x != (float)i) ? 1 : 0); }
+__device__ __forceinline__ int floorI(float x) { return (int)floorf(x); }
+
+// order-preserving float -> uint map for the packed (depth, submission order) keys
+__device__ __forceinline__ uint32_t depthKey(float d)
+{
+	uint32_t b = __float_as_uint(d + 0.0f);   // -0 -> +0
+	return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float keyDepth(uint32_t k)
+{
+	uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+	return __uint_as_float(b);
+}
+#define KEY_EMPTY_HI 0xff7fffffu            /* depthKey(FLT_MAX): occlZ of a cleared sample */
+#define KEY_EMPTY ((((unsigned long long)KEY_EMPTY_HI) << 32) | 0xffffffffull)
+
+struct B2 { float mnx, mny, mnz, mxx, mxy, mxz; };   // CqBound
+
+__device__ __forceinline__ B2 boundOf4(const float4& a, const float4& b, const float4& c, const float4& d)
+{
+	B2 r;
+	r.mnx = minA(a.x, minA(b.x, minA(c.x, d.x))); r.mny = minA(a.y, minA(b.y, minA(c.y, d.y)));
+	r.mnz = minA(a.z, minA(b.z, minA(c.z, d.z)));
+	r.mxx = maxA(a.x, maxA(b.x, maxA(c.x, d.x))); r.mxy = maxA(a.y, maxA(b.y, maxA(c.y, d.y)));
+	r.mxz = maxA(a.z, maxA(b.z, maxA(c.z, d.z)));
+	return r;
+}
+__device__ __forceinline__ void encapsulate(B2& a, const B2& b)
+{
+	a.mxx = maxA(a.mxx, b.mxx); a.mxy = maxA(a.mxy, b.mxy); a.mxz = maxA(a.mxz, b.mxz);
+	a.mnx = minA(a.mnx, b.mnx); a.mny = minA(a.mny, b.mny); a.mnz = minA(a.mnz, b.mnz);
+}
+
+// CqRenderer::GetCircleOfConfusion, renderer.h:401-406
+__device__ __forceinline__ float2 cocAt(const DevFrame& f, float depth)
+{
+	float c = f.dofMult * fabsf(1.0f / depth - f.dofInvFocal);
+	return make_float2(f.dofScaleX * c, f.dofScaleY * c);
+}
+// CqRenderer::MinCoCForBound, renderer.cpp:1602-1617
+__device__ __forceinline__ float minCoCForBound(const DevFrame& f, float z1, float z2)
+{
+	float focalDist = 1.0f / f.dofInvFocal;
+	if((z1 - focalDist)*(z2 - focalDist) < 0.f)
+		return 0.f;
+	float minBlur = minA(fabsf(1.0f/z1 - f.dofInvFocal), fabsf(1.0f/z2 - f.dofInvFocal));
+	return f.dofMult * minA(f.dofScaleX, f.dofScaleY) * minBlur;
+}
+
+__device__ __forceinline__ uint32_t infoOf(const float4& v) { return __float_as_uint(v.w); }
+
+// ------------------------------------------------------------------------------------
+// k_project: one thread per position.
+__global__ void __launch_bounds__(256) k_project(DevFrame f)
+{
+	const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+	if(i >= f.nPos) return;
+	// locate the grid: bounded binary search between the grids of this and the next chunk
+	uint32_t lo = f.chunkGrid[blockIdx.x], hi = f.chunkGrid[blockIdx.x + 1];
+	while(lo < hi)
+	{
+		uint32_t mid = (lo + hi + 1) >> 1;
+		if((int64_t)f.grids[mid].pbase <= i) lo = mid; else hi = mid - 1;
+	}
+	const GridRec g = f.grids[lo];
+	const uint32_t local = (uint32_t)(i - g.pbase);
+	const uint32_t key = local / g.nverts;
+	const uint32_t v = local - key*g.nverts;
+	float x = f.Praw[3*i], y = f.Praw[3*i+1], z = f.Praw[3*i+2];
+	if(g.flags & AQH_GRID_CAMERA_SPACE)
+	{
+		// CqMatrix::operator*(CqVector3D), include/aqsis/math/matrix.h:717-750
+		const float* m = f.camToRaster;
+		float h = (m[3]*x + m[7]*y + m[11]*z + m[15]);
+		float rx = (m[0]*x + m[4]*y + m[8]*z + m[12]);
+		float ry = (m[1]*x + m[5]*y + m[9]*z + m[13]);
+		if(h != 1.f)
+		{
+			float invh = 1.f/h;
+			rx = rx*invh; ry = ry*invh;
+		}
+		x = rx; y = ry;   // z keeps the camera depth (micropolygon.cpp:727-729)
+	}
+	uint32_t info = lo & VINFO_GRID_MASK;
+	if(key == 0)
+	{
+		const uint32_t cu = g.cu_cv & 0xffffu, cv = g.cu_cv >> 16;
+		const uint32_t iv = v / (cu + 1), iu = v - iv*(cu + 1);
+		const uint32_t vid = g.vbase + v;
+		bool opaque = true;
+		if(f.Oi)
+			opaque = (f.Oi[3*(size_t)vid] >= 1.0f) && (f.Oi[3*(size_t)vid+1] >= 1.0f) && (f.Oi[3*(size_t)vid+2] >= 1.0f);
+		bool valid = (iu < cu) && (iv < cv) && !(f.culled && f.culled[vid]);
+		if(opaque) info |= VINFO_OPAQUE;
+		if(valid) info |= VINFO_MP_VALID;
+	}
+	f.P4[i] = make_float4(x, y, z, __uint_as_float(info));
+}
+
+// Triangle split line per (grid, key): micropolygon.cpp:733-749.  One thread per grid.
+__global__ void __launch_bounds__(128) k_splitlines(DevFrame f)
+{
+	const int gi = blockIdx.x*128 + threadIdx.x;
+	if(gi >= f.nGrids) return;
+	const GridRec g = f.grids[gi];
+	const uint32_t cu = g.cu_cv & 0xffffu, cv = g.cu_cv >> 16;
+	const uint32_t nkeys = g.nkeys_koff & 0xffu, koff = g.nkeys_koff >> 8;
+	for(uint32_t k = 0; k < nkeys; ++k)
+	{
+		const float4* P = f.P4 + g.pbase + (size_t)k*g.nverts;
+		float4 v0 = P[0], v1 = P[cu], v2 = P[cv*(cu+1)];
+		float4 sl;
+		if(((v1.x - v0.x)*(v2.y - v0.y) - (v1.y - v0.y)*(v2.x - v0.x)) >= 0.f)
+			sl = make_float4(v1.x, v1.y, v2.x, v2.y);
+		else
+			sl = make_float4(v2.x, v2.y, v1.x, v1.y);
+		f.splitLines[koff + k] = sl;
+	}
+}
+
+// ------------------------------------------------------------------------------------
+// Binning.  The tile range of a micropolygon only has to be a SUPERSET of the tiles whose
+// samples it can touch (the hide kernel repeats the reference's exact tests), so the bound
+// is padded a little to stay conservative under the lerp rounding of the motion sub-bounds.
+struct TileRange { int tx0, tx1, ty0, ty1; };   // inclusive
+
+__device__ __forceinline__ bool mpTileRange(const DevFrame& f, int64_t p, const float4& a, TileRange& tr)
+{
+	const uint32_t info = infoOf(a);
+	if(!(info & VINFO_MP_VALID)) return false;
+	const GridRec g = f.grids[info & VINFO_GRID_MASK];
+	if((uint64_t)(p - g.pbase) >= g.nverts) return false;            // only key 0 starts micropolygons
+	const uint32_t cu = g.cu_cv & 0xffffu;
+	const uint32_t nkeys = g.nkeys_koff & 0xffu;
+	B2 B = boundOf4(a, f.P4[p+1], f.P4[p+cu+1], f.P4[p+cu+2]);
+	for(uint32_t k = 1; k < nkeys; ++k)
+	{
+		const float4* Pk = f.P4 + p + (size_t)k*g.nverts;
+		B2 kb = boundOf4(Pk[0], Pk[1], Pk[cu+1], Pk[cu+2]);
+		encapsulate(B, kb);
+	}
+	if(f.useDof)
+	{
+		// imagebuffer.cpp:519-531
+		float2 c1 = cocAt(f, B.mnz), c2 = cocAt(f, B.mxz);
+		float mcx = maxA(c1.x, c2.x), mcy = maxA(c1.y, c2.y);
+		B.mnx -= mcx; B.mny -= mcy; B.mxx += mcx; B.mxy += mcy;
+	}
+	const float pad = 1.0f/128.0f;
+	float x0 = B.mnx - pad - fabsf(B.mnx)*1e-6f, x1 = B.mxx + pad + fabsf(B.mxx)*1e-6f;
+	float y0 = B.mny - pad - fabsf(B.mny)*1e-6f, y1 = B.mxy + pad + fabsf(B.mxy)*1e-6f;
+	// pixel range [floor(min), ceil(max)) clamped to the sample region, in float to survive huge bounds
+	float fx0 = fmaxf(floorf(x0), (float)f.sx0), fx1 = fminf(ceilf(x1), (float)(f.sx0 + f.sw));
+	float fy0 = fmaxf(floorf(y0), (float)f.sy0), fy1 = fminf(ceilf(y1), (float)(f.sy0 + f.sh));
+	if(!(fx0 < fx1) || !(fy0 < fy1)) return false;
+	tr.tx0 = ((int)fx0 - f.sx0) / f.tileW; tr.tx1 = ((int)fx1 - 1 - f.sx0) / f.tileW;
+	tr.ty0 = ((int)fy0 - f.sy0) / f.tileH; tr.ty1 = ((int)fy1 - 1 - f.sy0) / f.tileH;
+	return true;
+}
+
+template<bool FILL>
+__global__ void __launch_bounds__(256) k_bin(DevFrame f)
+{
+	const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+	if(p >= f.nPos) return;
+	const float4 a = f.P4[p];
+	TileRange tr;
+	if(!mpTileRange(f, p, a, tr)) return;
+	unsigned long long nent = 0;
+	for(int ty = tr.ty0; ty <= tr.ty1; ++ty)
+		for(int tx = tr.tx0; tx <= tr.tx1; ++tx)
+		{
+			const int slot = f.tileSlot[ty*f.ntx + tx];
+			if(slot < 0) continue;
+			if(FILL)
+			{
+				uint32_t at = atomicAdd(&f.binCount[slot], 1u);
+				f.binEntries[f.binOffset[slot] + at] = (uint32_t)p;
+			}
+			else
+			{
+				atomicAdd(&f.binCount[slot], 1u);
+				++nent;
+			}
+		}
+	if(!FILL && nent)
+	{
+		atomicAdd(&f.counters[0], 1ull);
+		atomicAdd(&f.counters[1], nent);
+	}
+}
+
+// Exclusive scan of binCount -> binOffset (single CTA; the tile count is small), and reset
+// of binCount for the fill pass.
+__global__ void __launch_bounds__(1024) k_bin_scan(DevFrame f)
+{
+	__shared__ uint32_t s_part[1024];
+	const int n = f.nActiveTiles;
+	const int per = (n + 1023) / 1024;
+	const int beg = threadIdx.x * per, end = min(beg + per, n);
+	uint32_t sum = 0;
+	for(int i = beg; i < end; ++i) sum += f.binCount[i];
+	s_part[threadIdx.x] = sum;
+	__syncthreads();
+	// Hillis-Steele inclusive scan over the 1024 partials
+	for(int d = 1; d < 1024; d <<= 1)
+	{
+		uint32_t v = (threadIdx.x >= d) ? s_part[threadIdx.x - d] : 0;
+		__syncthreads();
+		s_part[threadIdx.x] += v;
+		__syncthreads();
+	}
+	uint32_t run = (threadIdx.x == 0) ? 0 : s_part[threadIdx.x - 1];
+	for(int i = beg; i < end; ++i)
+	{
+		uint32_t c = f.binCount[i];
+		f.binOffset[i] = run;
+		run += c;
+		f.binCount[i] = 0;
+	}
+	if(threadIdx.x == 1023) f.binOffset[n] = s_part[1023];
+	if(threadIdx.x == 0) *f.tileCursor = 0;
+}
+
+// ------------------------------------------------------------------------------------
+// Micropolygon hit-test pieces.
+
+// CqMicroPolygon::ComputeVertexOrder, micropolygon.cpp:1207-1284.  Vertices in natural
+// order P0=index, P1=index+1, P2=index+cu+1, P3=index+cu+2 (codes A=0, B=1, C=3, D=2).
+__device__ __forceinline__ float mag2d3(const float4& a, const float4& b)
+{
+	float dx = a.x-b.x, dy = a.y-b.y, dz = a.z-b.z;
+	return dx*dx + dy*dy + dz*dz;
+}
+#define DEGENERACY_MASK 0x8000000
+__device__ int computeVertexOrder(const float4 P[4])
+{
+	// IndexA..D -> natural slots 0,1,3,2
+	int iA = 0, iB = 1, iC = 3, iD = 2;
+	int CodeA = 0, CodeB = 1, CodeC = 3, CodeD = 2;
+	if((double)mag2d3(P[iA], P[iB]) < 1e-8)
+	{ iB = iC; CodeB = CodeC; iC = iD; CodeC = CodeD; iD = -1; CodeD = -1; }
+	else if((double)mag2d3(P[iB], P[iC]) < 1e-8)
+	{ iB = iC; CodeB = CodeC; iC = iD; CodeC = CodeD; iD = -1; CodeD = -1; }
+	else if((double)mag2d3(P[iC], P[iD]) < 1e-8)
+	{ iC = iD; CodeC = CodeD; iD = -1; CodeD = -1; }
+	else if((double)mag2d3(P[iD], P[iA]) < 1e-8)
+	{ iD = -1; CodeD = -1; }
+	const float4 vA = P[iA], vB = P[iB], vC = P[iC];
+	bool fFlip = ((vA.x - vB.x)*(vB.y - vC.y)) >= ((vA.y - vB.y)*(vB.x - vC.x));
+	int code;
+	if(!fFlip)
+		code = (CodeD == -1) ? ((CodeA & 3) | ((CodeC & 3) << 2) | ((CodeB & 3) << 4) | DEGENERACY_MASK)
+		                     : ((CodeA & 3) | ((CodeD & 3) << 2) | ((CodeC & 3) << 4) | ((CodeB & 3) << 6));
+	else
+		code = (CodeD == -1) ? ((CodeA & 3) | ((CodeB & 3) << 2) | ((CodeC & 3) << 4) | DEGENERACY_MASK)
+		                     : ((CodeA & 3) | ((CodeB & 3) << 2) | ((CodeC & 3) << 4) | ((CodeD & 3) << 6));
+	return code;
+}
+
+// The hit-test cache of one micropolygon at one instant: CqHitTestCache minus the DoF
+// members (micropolygon.h:520-551), filled by cachePointInPolyTest (micropolygon.cpp:1346-1392).
+struct HitCache
+{
+	float X[4], Y[4], XM[4], YM[4];
+	float Ax, Ay, Ex, Ey, Fx, Fy, Gx, Gy;
+	float z[4];
+	int linear;
+};
+
+__device__ __forceinline__ void cachePointInPolyTest(HitCache& c, const float px[4], const float py[4], const float pz[4], int code)
+{
+	c.z[0] = pz[0]; c.z[1] = pz[1]; c.z[2] = pz[2]; c.z[3] = pz[3];
+	// CqInvBilinear::setVertices(A,B,C,D), bilinear.h:260-275
+	c.Ax = px[0]; c.Ay = py[0];
+	c.Ex = px[1] - px[0]; c.Ey = py[1] - py[0];
+	c.Fx = px[2] - px[0]; c.Fy = py[2] - py[0];
+	c.Gx = -c.Ex - px[2] + px[3]; c.Gy = -c.Ey - py[2] + py[3];
+	float patchSize = maxA(maxA(fabsf(c.Fx), fabsf(c.Fy)), maxA(fabsf(c.Ex), fabsf(c.Ey)));
+	float irregularity = maxA(fabsf(c.Gx), fabsf(c.Gy));
+	c.linear = ((double)irregularity < 1e-2*(double)patchSize) ? 1 : 0;
+	const int i0 = (code >> 2) & 3, i1 = (code >> 4) & 3, i2 = (code >> 6) & 3, i3 = code & 3;
+	const float qx[4] = {px[i0], px[i1], px[i2], px[i3]};
+	const float qy[4] = {py[i0], py[i1], py[i2], py[i3]};
+	int j = 3;
+#pragma unroll
+	for(int i = 0; i < 4; ++i)
+	{
+		c.YM[i] = qx[i] - qx[j];
+		c.XM[i] = qy[i] - qy[j];
+		c.X[i] = qx[j];
+		c.Y[i] = qy[j];
+		j = i;
+	}
+	if(code & DEGENERACY_MASK)
+	{
+#pragma unroll
+		for(int i = 2; i < 4; ++i)
+		{
+			c.YM[i] = qx[3] - qx[1];
+			c.XM[i] = qy[3] - qy[1];
+			c.X[i] = qx[1];
+			c.Y[i] = qy[1];
+		}
+	}
+}
+
+// The four edge tests of CqMicroPolygon::fContains (micropolygon.cpp:1306-1335): edges 0,1
+// fail on <= 0, edges 2,3 on < 0.  The reference's m_LastFailedEdge only reorders the tests.
+__device__ __forceinline__ bool edgeTests(const float* X, const float* Y, const float* XM, const float* YM, float x, float y)
+{
+	float e0 = ((y - Y[0]) * YM[0]) - ((x - X[0]) * XM[0]);
+	float e1 = ((y - Y[1]) * YM[1]) - ((x - X[1]) * XM[1]);
+	float e2 = ((y - Y[2]) * YM[2]) - ((x - X[2]) * XM[2]);
+	float e3 = ((y - Y[3]) * YM[3]) - ((x - X[3]) * XM[3]);
+	return !(e0 <= 0.f) && !(e1 <= 0.f) && !(e2 < 0.f) && !(e3 < 0.f);
+}
+
+// CqInvBilinear::operator(), bilinear.h:277-311
+__device__ __forceinline__ float2 invBilinear(float Ax, float Ay, float Ex, float Ey, float Fx, float Fy,
+                                              float Gx, float Gy, int linear, float Px, float Py)
+{
+	float u = 0.5f, v = 0.5f;
+#pragma unroll
+	for(int it = 0; it < 2; ++it)
+	{
+		if(it == 1 && linear) break;
+		// bilinEval(uv) - P
+		float bx = (Ax + Ex*u + Fx*v + Gx*u*v) - Px;
+		float by = (Ay + Ey*u + Fy*v + Gy*u*v) - Py;
+		float M1x = Ex + Gx*v, M1y = Ey + Gy*v;
+		float M2x = Fx + Gx*u, M2y = Fy + Gy*u;
+		float det = M1x*M2y - M1y*M2x;
+		if(it == 0 || det != 0.f) det = 1.f/det;
+		float sx = det * (bx*M2y - by*M2x);
+		float sy = det * (-(bx*M1y - by*M1x));
+		u -= sx; v -= sy;
+	}
+	return make_float2(u, v);
+}
+// bilerp, bilinear.h:229-236
+__device__ __forceinline__ float bilerpZ(const float* z, float2 uv)
+{
+	float w0 = (1.f-uv.y)*(1.f-uv.x);
+	float w1 = (1.f-uv.y)*uv.x;
+	float w2 = uv.y*(1.f-uv.x);
+	float w3 = uv.y*uv.x;
+	return w0*z[0] + w1*z[1] + w2*z[2] + w3*z[3];
+}
+
+// CqMotionSpec::GetMotionObjectInterpolated on the split line (motion.h:176-228,
+// micropolygon.h:182-188) + the side test of micropolygon.cpp:1630-1654.
+__device__ bool triangleSplitReject(const DevFrame& f, const GridRec& g, float2 pos, float2 dofOff, float D, float time)
+{
+	const uint32_t nkeys = g.nkeys_koff & 0xffu, koff = g.nkeys_koff >> 8;
+	const float4* sl = f.splitLines + koff;
+	const float* times = f.keyTimes + koff;
+	float4 s;
+	if(nkeys == 1) s = sl[0];
+	else if(time >= times[nkeys-1]) s = sl[nkeys-1];
+	else if(time <= times[0]) s = sl[0];
+	else
+	{
+		uint32_t i = 0;
+		while(time >= times[i+1]) i += 1;
+		float Fr = (time - times[i]) / (times[i+1] - times[i]);
+		if(times[i] == time) s = sl[i];
+		else
+		{
+			float4 a = sl[i], b = sl[i+1];
+			s = make_float4(((1.0f - Fr)*a.x) + (Fr*b.x), ((1.0f - Fr)*a.y) + (Fr*b.y),
+			                ((1.0f - Fr)*a.z) + (Fr*b.z), ((1.0f - Fr)*a.w) + (Fr*b.w));
+		}
+	}
+	float Ax = s.x, Ay = s.y, Bx = s.z, By = s.w;
+	float hx = pos.x, hy = pos.y;
+	if(f.useDof)
+	{
+		float2 cm = cocAt(f, D);
+		hx += cm.x*dofOff.x; hy += cm.y*dofOff.y;
+	}
+	float v = (Ay - By)*hx + (Bx - Ax)*hy + (Ax*By - Bx*Ay);
+	return v <= 0.f;
+}
+
+// CqMicroPolygon::InterpolateOutputs + CacheOutputInterpCoeffs*, micropolygon.cpp:1443-1529
+__device__ __forceinline__ void shadeHit(const DevFrame& f, const GridRec& g, uint32_t p, float2 uv, float* col, float* opa)
+{
+	const uint32_t cu = g.cu_cv & 0xffffu;
+	const size_t v0 = (size_t)g.vbase + (p - g.pbase);
+	if(g.flags & AQH_GRID_SMOOTH)
+	{
+		const size_t vi[4] = {v0, v0 + 1, v0 + cu + 1, v0 + cu + 2};
+		float w[4];
+		w[0] = (1.f-uv.x)*(1.f-uv.y);
+		w[1] = uv.x*(1.f-uv.y);
+		w[2] = (1.f-uv.x)*uv.y;
+		w[3] = uv.x*uv.y;
+#pragma unroll
+		for(int k = 0; k < 3; ++k)
+		{
+			if(f.Ci)
+				col[k] = w[0]*f.Ci[3*vi[0]+k] + w[1]*f.Ci[3*vi[1]+k] + w[2]*f.Ci[3*vi[2]+k] + w[3]*f.Ci[3*vi[3]+k];
+			else
+				col[k] = w[0]*1.0f + w[1]*1.0f + w[2]*1.0f + w[3]*1.0f;
+			if(f.Oi)
+				opa[k] = w[0]*f.Oi[3*vi[0]+k] + w[1]*f.Oi[3*vi[1]+k] + w[2]*f.Oi[3*vi[2]+k] + w[3]*f.Oi[3*vi[3]+k];
+			else
+				opa[k] = w[0]*1.0f + w[1]*1.0f + w[2]*1.0f + w[3]*1.0f;
+		}
+	}
+	else
+	{
+#pragma unroll
+		for(int k = 0; k < 3; ++k)
+		{
+			col[k] = f.Ci ? f.Ci[3*v0+k] : 1.0f;
+			opa[k] = f.Oi ? f.Oi[3*v0+k] : 1.0f;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------
+// Shared-memory layout of the hide kernel (dynamic):
+//   u64 keys[ns] | float2 pos[ns] | [float time[ns]] | [float2 dof[ns]] | [u32 head[ns]] |
+//   StaticRec recs[batch] | u16 colIdx[tileW*xs] | u16 rowIdx[tileH*ys] | u8 shufPat[tileW*tileH]
+struct StaticRec   // 36 words
+{
+	float X[4], Y[4], XM[4], YM[4];
+	float bminx, bminy, bmaxx, bmaxy;
+	float Ax, Ay, Ex, Ey, Fx, Fy, Gx, Gy;
+	float z[4];
+	uint32_t zminKey;
+	uint32_t p;
+	uint32_t flags;     // grid id | REC_*
+	uint32_t rect;      // gx0 | gx1<<8 | gy0<<16 | gy1<<24  (tile sub-sample coordinates, <= 255)
+};
+enum : uint32_t { REC_LINEAR = 1u << 28, REC_RARE = 1u << 29 /* lod or triangular */ };
+
+struct TileCtx
+{
+	int tileX0, tileY0;        // global pixel of the tile origin
+	int rx0, ry0, rx1, ry1;    // tile ∩ sample region (global pixels)
+	int ns;                    // samples in the tile (tileW*tileH*n)
+};
+
+struct HideSmem
+{
+	unsigned long long* keys;
+	float2* pos;
+	float* time;
+	float2* dof;
+	uint32_t* head;
+	StaticRec* recs;
+	uint16_t* colIdx;
+	uint16_t* rowIdx;
+	uint8_t* shufPat;
+};
+
+__device__ __forceinline__ HideSmem carveSmem(const DevFrame& f, unsigned char* base, int batch)
+{
+	HideSmem s;
+	const int ns = f.tileW*f.tileH*f.n;
+	size_t o = 0;
+	s.keys = (unsigned long long*)(base + o); o += (size_t)ns*8;
+	s.pos = (float2*)(base + o); o += (size_t)ns*8;
+	s.dof = 0; s.time = 0; s.head = 0;
+	if(f.useDof) { s.dof = (float2*)(base + o); o += (size_t)ns*8; }
+	if(f.anyMotion) { s.time = (float*)(base + o); o += (size_t)ns*4; }
+	if(f.anyTransparent) { s.head = (uint32_t*)(base + o); o += (size_t)ns*4; }
+	o = (o + 15) & ~(size_t)15;
+	s.recs = (StaticRec*)(base + o); o += (size_t)batch*sizeof(StaticRec);
+	s.colIdx = (uint16_t*)(base + o); o += (size_t)f.tileW*f.xs*2;
+	s.rowIdx = (uint16_t*)(base + o); o += (size_t)f.tileH*f.ys*2;
+	s.shufPat = (uint8_t*)(base + o);
+	return s;
+}
+
+static size_t hideSmemBytes(const DevFrame& f, int batch)
+{
+	const size_t ns = (size_t)f.tileW*f.tileH*f.n;
+	size_t o = ns*16;
+	if(f.useDof) o += ns*8;
+	if(f.anyMotion) o += ns*4;
+	if(f.anyTransparent) o += ns*4;
+	o = (o + 15) & ~(size_t)15;
+	o += (size_t)batch*sizeof(StaticRec);
+	o += (size_t)f.tileW*f.xs*2 + (size_t)f.tileH*f.ys*2 + (size_t)f.tileW*f.tileH;
+	return (o + 15) & ~(size_t)15;
+}
+
+// Deposit a hit: opaque hits race for the per-sample (depth, order) minimum; transparent ones
+// are appended to the CTA's deep pool if they are in front of the final opaque depth.
+// StoreSample, bucketprocessor.cpp:1471-1569.
+__device__ __forceinline__ void storeOpaque(unsigned long long* key, float D, uint32_t p)
+{
+	if(!(D < FLT_MAX)) return;                       // occlZ(=FLT_MAX) <= D
+	unsigned long long nk = ((unsigned long long)depthKey(D) << 32) | p;
+	if(nk < *key)                                    // cheap pre-check; keys only ever decrease
+		atomicMin(key, nk);
+}
+
+struct DeepCtx
+{
+	uint4* A; float2* UV; uint32_t cap; uint32_t* count;   // count lives in shared memory
+};
+__device__ __forceinline__ void storeDeep(const DevFrame& f, const DeepCtx& dc, const HideSmem& s, int idx,
+                                          float D, uint32_t p, float2 uv)
+{
+	const uint32_t occl = (uint32_t)(s.keys[idx] >> 32);
+	if(!(depthKey(D) < occl)) return;                 // isCullable && occlZ <= D
+	uint32_t slot = atomicAdd(dc.count, 1u);
+	if(slot >= dc.cap) { atomicOr(f.errorFlags, 1u); return; }
+	uint32_t next = atomicExch(&s.head[idx], slot);
+	dc.A[slot] = make_uint4(next, __float_as_uint(D), p, (uint32_t)idx);
+	dc.UV[slot] = uv;
+}
+
+// ---- static micropolygons, no depth of field: RenderMPG_Static (bucketprocessor.cpp:1097-1218)
+__device__ void setupStaticRec(const DevFrame& f, const TileCtx& t, uint32_t p, bool wantOpaque, StaticRec& r)
+{
+	r.rect = 0;
+	r.p = p;
+	const float4 a = f.P4[p];
+	const uint32_t info = infoOf(a);
+	const uint32_t gi = info & VINFO_GRID_MASK;
+	const GridRec g = f.grids[gi];
+	const uint32_t cu = g.cu_cv & 0xffffu;
+	float4 P[4];
+	P[0] = a; P[1] = f.P4[p+1]; P[2] = f.P4[p+cu+1]; P[3] = f.P4[p+cu+2];
+	bool opaque = (info & VINFO_OPAQUE) != 0;
+	if(g.flags & AQH_GRID_SMOOTH)
+		opaque = opaque && (infoOf(P[1]) & VINFO_OPAQUE) && (infoOf(P[2]) & VINFO_OPAQUE) && (infoOf(P[3]) & VINFO_OPAQUE);
+	// MatteAlpha objects use the opaque slot too (bucketprocessor.cpp:1490-1491)
+	bool opaqueSlot = opaque || (g.flags & AQH_GRID_MATTE_ALPHA);
+	if(opaqueSlot != wantOpaque) return;
+	const B2 B = boundOf4(P[0], P[1], P[3], P[2]);
+	const float bminx = B.mnx, bmaxx = B.mxx, bminy = B.mny, bmaxy = B.mxy;
+	// pixel range clamped to (tile ∩ sample region); compare in float first so that huge
+	// bounds cannot overflow the int conversions.
+	if(!(bmaxx >= (float)t.rx0) || !(bmaxy >= (float)t.ry0) || !(bminx < (float)t.rx1) || !(bminy < (float)t.ry1)) return;
+	int eX = (bmaxx >= (float)t.rx1) ? t.rx1 : min(lceilF(bmaxx), t.rx1);
+	int eY = (bmaxy >= (float)t.ry1) ? t.ry1 : min(lceilF(bmaxy), t.ry1);
+	int sX = (bminx < (float)t.rx0) ? t.rx0 : max(floorI(bminx), t.rx0);
+	int sY = (bminy < (float)t.ry0) ? t.ry0 : max(floorI(bminy), t.ry0);
+	if(sX >= eX || sY >= eY) return;
+	const int xs = f.xs, ys = f.ys;
+	int im = (bminx < (float)sX) ? 0 : floorI((bminx - (float)sX) * (float)xs);
+	int in = (bminy < (float)sY) ? 0 : floorI((bminy - (float)sY) * (float)ys);
+	int em = (bmaxx > (float)eX) ? xs : lceilF((bmaxx - (float)(eX - 1)) * (float)xs);
+	int en = (bmaxy > (float)eY) ? ys : lceilF((bmaxy - (float)(eY - 1)) * (float)ys);
+	im = max(im, 0); in = max(in, 0); em = min(em, xs); en = min(en, ys);
+	int gx0 = (sX - t.tileX0)*xs + im, gx1 = (eX - 1 - t.tileX0)*xs + em;
+	int gy0 = (sY - t.tileY0)*ys + in, gy1 = (eY - 1 - t.tileY0)*ys + en;
+	if(gx1 <= gx0 || gy1 <= gy0) return;
+	const int code = computeVertexOrder(P);
+	HitCache c;
+	const float px[4] = {P[0].x, P[1].x, P[2].x, P[3].x};
+	const float py[4] = {P[0].y, P[1].y, P[2].y, P[3].y};
+	const float pz[4] = {P[0].z, P[1].z, P[2].z, P[3].z};
+	cachePointInPolyTest(c, px, py, pz, code);
+#pragma unroll
+	for(int i = 0; i < 4; ++i) { r.X[i] = c.X[i]; r.Y[i] = c.Y[i]; r.XM[i] = c.XM[i]; r.YM[i] = c.YM[i]; r.z[i] = c.z[i]; }
+	r.bminx = bminx; r.bminy = bminy; r.bmaxx = bmaxx; r.bmaxy = bmaxy;
+	r.Ax = c.Ax; r.Ay = c.Ay; r.Ex = c.Ex; r.Ey = c.Ey; r.Fx = c.Fx; r.Fy = c.Fy; r.Gx = c.Gx; r.Gy = c.Gy;
+	r.zminKey = depthKey(B.mnz);
+	uint32_t fl = gi;
+	if(c.linear) fl |= REC_LINEAR;
+	if((g.flags & AQH_GRID_TRIANGULAR) || g.lod0 >= 0.0f) fl |= REC_RARE;
+	r.flags = fl;
+	r.rect = (uint32_t)gx0 | ((uint32_t)gx1 << 8) | ((uint32_t)gy0 << 16) | ((uint32_t)gy1 << 24);
+}
+
+template<bool OPAQUE>
+__device__ __forceinline__ void sampleStaticRec(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc,
+                                                const StaticRec& r, int lane)
+{
+	const uint32_t rect = r.rect;
+	if(rect == 0) return;
+	const int gx0 = rect & 0xff, gx1 = (rect >> 8) & 0xff, gy0 = (rect >> 16) & 0xff, gy1 = rect >> 24;
+	const int W = gx1 - gx0, H = gy1 - gy0, total = W*H;
+	const float invW = 1.0f / (float)W;
+	const float bminx = r.bminx, bminy = r.bminy, bmaxx = r.bmaxx, bmaxy = r.bmaxy;
+	const uint32_t zminKey = r.zminKey;
+	for(int k = lane; k < total; k += 32)
+	{
+		int cy = (int)(((float)k + 0.5f) * invW);
+		int cx = k - cy*W;
+		if(cx < 0) { cy -= 1; cx += W; } else if(cx >= W) { cy += 1; cx -= W; }
+		const int idx = s.rowIdx[gy0 + cy] + s.colIdx[gx0 + cx];
+		const float2 pos = s.pos[idx];
+		// Bound.Contains2D, bound.h:144-151
+		if((pos.x < bminx || pos.x > bmaxx) || (pos.y < bminy || pos.y > bmaxy)) continue;
+		// occlusion cull against the current opaque depth (bucketprocessor.cpp:1179)
+		const uint32_t occl = (uint32_t)(s.keys[idx] >> 32);
+		if(zminKey > occl) continue;
+		if(!edgeTests(r.X, r.Y, r.XM, r.YM, pos.x, pos.y)) continue;
+		const float2 uv = invBilinear(r.Ax, r.Ay, r.Ex, r.Ey, r.Fx, r.Fy, r.Gx, r.Gy, (r.flags & REC_LINEAR) ? 1 : 0, pos.x, pos.y);
+		const float D = bilerpZ(r.z, uv);
+		if(r.flags & REC_RARE)
+		{
+			const GridRec g = f.grids[r.flags & VINFO_GRID_MASK];
+			if(g.lod0 >= 0.0f)
+			{
+				// sample level of detail = lods[i] of the pixel's lod pattern (imagepixel.cpp:356)
+				const int pixLocal = idx / f.n, i = idx - pixLocal*f.n;
+				const int gxp = t.tileX0 + pixLocal % f.tileW - f.sx0, gyp = t.tileY0 + pixLocal / f.tileW - f.sy0;
+				const int pat = f.patPlanes[(size_t)4*f.sw*f.sh + (size_t)gyp*f.sw + gxp];
+				const float lod = f.val1d[(size_t)pat*f.n + i];
+				if(g.lod0 > lod || lod >= g.lod1) continue;
+			}
+			if(g.flags & AQH_GRID_TRIANGULAR)
+				if(triangleSplitReject(f, g, pos, make_float2(0.f, 0.f), D, 0.0f)) continue;
+		}
+		if(OPAQUE)
+			storeOpaque(&s.keys[idx], D, r.p);
+		else
+			storeDeep(f, dc, s, idx, D, r.p, uv);
+	}
+}
+
+// ---- motion blur and/or depth of field: RenderMPG_MBOrDof (bucketprocessor.cpp:1221-1469).
+// One warp per micropolygon; the reference's loops over time sub-bounds are walked by the
+// whole warp, lanes spread over lens cells (DoF) or over (pixel, sample index) pairs (MB).
+struct MovingMP
+{
+	uint32_t p, nverts, cu, nkeys;
+	const float* times;
+	int code;
+	GridRec g;
+};
+
+__device__ __forceinline__ B2 keyBound(const DevFrame& f, const MovingMP& m, uint32_t k)
+{
+	const float4* Pk = f.P4 + m.p + (size_t)k*m.nverts;
+	return boundOf4(Pk[0], Pk[1], Pk[m.cu+1], Pk[m.cu+2]);
+}
+
+// Vertices of the micropolygon for one sample: CqMicroPolygon(Motion)::Sample,
+// micropolygon.cpp:1561-1589 and 1768-1873.  Returns false when the tight-bound test fails.
+__device__ bool samplePoints(const DevFrame& f, const MovingMP& m, bool moving, const B2& mpBound,
+                             float2 cocMin, float2 cocMax, float2 pos, float2 dofOff, float time,
+                             float px[4], float py[4], float pz[4], bool doBoundTest)
+{
+	B2 tight;
+	float Fraction = 0.0f;
+	bool Exact = true;
+	uint32_t iIndex = 0;
+	if(moving)
+	{
+		const float* times = m.times;
+		if(time > times[0])
+		{
+			if(time >= times[m.nkeys-1])
+				iIndex = m.nkeys - 1;
+			else
+			{
+				while(time >= times[iIndex+1]) iIndex += 1;
+				Fraction = (time - times[iIndex]) / (times[iIndex+1] - times[iIndex]);
+				Exact = (times[iIndex] == time);
+			}
+		}
+		if(doBoundTest)
+		{
+			if(Exact)
+				tight = keyBound(f, m, iIndex);
+			else
+			{
+				const B2 b1 = keyBound(f, m, iIndex), b2 = keyBound(f, m, iIndex+1);
+				tight.mnx = (1.f-Fraction)*b1.mnx + Fraction*b2.mnx; tight.mny = (1.f-Fraction)*b1.mny + Fraction*b2.mny;
+				tight.mnz = (1.f-Fraction)*b1.mnz + Fraction*b2.mnz;
+				tight.mxx = (1.f-Fraction)*b1.mxx + Fraction*b2.mxx; tight.mxy = (1.f-Fraction)*b1.mxy + Fraction*b2.mxy;
+				tight.mxz = (1.f-Fraction)*b1.mxz + Fraction*b2.mxz;
+			}
+		}
+	}
+	else
+		tight = mpBound;
+	if(doBoundTest)
+	{
+		if(f.useDof)
+		{
+			// dofSampleInBound, micropolygon.cpp:1531-1550
+			float mnx = pos.x + cocMin.x*dofOff.x, mny = pos.y + cocMin.y*dofOff.y;
+			float mxx = pos.x + cocMax.x*dofOff.x, mxy = pos.y + cocMax.y*dofOff.y;
+			if(dofOff.x < 0.f) { float tt = mnx; mnx = mxx; mxx = tt; }
+			if(dofOff.y < 0.f) { float tt = mny; mny = mxy; mxy = tt; }
+			if(mnx > tight.mxx || mny > tight.mxy || mxx < tight.mnx || mxy < tight.mny) return false;
+		}
+		else
+		{
+			if((pos.x < tight.mnx || pos.x > tight.mxx) || (pos.y < tight.mny || pos.y > tight.mxy)) return false;
+		}
+	}
+	const float4* K1 = f.P4 + m.p + (size_t)iIndex*m.nverts;
+	const uint32_t off[4] = {0, 1, m.cu+1, m.cu+2};
+	if(Exact)
+	{
+#pragma unroll
+		for(int i = 0; i < 4; ++i) { float4 v = K1[off[i]]; px[i] = v.x; py[i] = v.y; pz[i] = v.z; }
+	}
+	else
+	{
+		const float4* K2 = K1 + m.nverts;
+		const float F1 = 1.0f - Fraction;
+#pragma unroll
+		for(int i = 0; i < 4; ++i)
+		{
+			float4 a = K1[off[i]], b = K2[off[i]];
+			px[i] = (F1*a.x) + (Fraction*b.x);
+			py[i] = (F1*a.y) + (Fraction*b.y);
+			pz[i] = (F1*a.z) + (Fraction*b.z);
+		}
+	}
+	if(f.useDof)
+	{
+#pragma unroll
+		for(int i = 0; i < 4; ++i)
+		{
+			float2 cm = cocAt(f, pz[i]);
+			px[i] = px[i] - cm.x*dofOff.x;
+			py[i] = py[i] - cm.y*dofOff.y;
+		}
+	}
+	return true;
+}
+
+__device__ __forceinline__ float sampleLod(const DevFrame& f, const TileCtx& t, int idx)
+{
+	const int pixLocal = idx / f.n, i = idx - pixLocal*f.n;
+	const int gxp = t.tileX0 + pixLocal % f.tileW - f.sx0, gyp = t.tileY0 + pixLocal / f.tileW - f.sy0;
+	const int pat = f.patPlanes[(size_t)4*f.sw*f.sh + (size_t)gyp*f.sw + gxp];
+	return f.val1d[(size_t)pat*f.n + i];
+}
+
+// One candidate (micropolygon, sample) of the MB/DoF path, after the reference's gates.
+template<bool OPAQUE>
+__device__ __forceinline__ void testCandidateMBDof(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc,
+                                                   const MovingMP& m, bool moving, const B2& mpBound, float2 cocMin, float2 cocMax,
+                                                   int idx, float bzminKeyf /*unused*/, uint32_t zminKey,
+                                                   float bminx, float bminy, float bmaxx, float bmaxy, float time0, float time1)
+{
+	const float2 pos = s.pos[idx];
+	const float time = s.time ? s.time[idx] : f.shutterOpen;
+	if(moving && (time < time0 || time > time1)) return;
+	if((pos.x < bminx || pos.x > bmaxx) || (pos.y < bminy || pos.y > bmaxy)) return;
+	const uint32_t occl = (uint32_t)(s.keys[idx] >> 32);
+	if(zminKey > occl) return;
+	if(m.g.lod0 >= 0.0f)
+	{
+		float lod = sampleLod(f, t, idx);
+		if(m.g.lod0 > lod || lod >= m.g.lod1) return;
+	}
+	const float2 dofOff = s.dof ? s.dof[idx] : make_float2(0.f, 0.f);
+	float px[4], py[4], pz[4];
+	if(!samplePoints(f, m, moving, mpBound, cocMin, cocMax, pos, dofOff, time, px, py, pz, true)) return;
+	HitCache c;
+	cachePointInPolyTest(c, px, py, pz, m.code);
+	if(!edgeTests(c.X, c.Y, c.XM, c.YM, pos.x, pos.y)) return;
+	const float2 uv = invBilinear(c.Ax, c.Ay, c.Ex, c.Ey, c.Fx, c.Fy, c.Gx, c.Gy, c.linear, pos.x, pos.y);
+	const float D = bilerpZ(c.z, uv);
+	if(m.g.flags & AQH_GRID_TRIANGULAR)
+		if(triangleSplitReject(f, m.g, pos, dofOff, D, time)) return;
+	if(OPAQUE)
+		storeOpaque(&s.keys[idx], D, m.p);
+	else
+		storeDeep(f, dc, s, idx, D, m.p, uv);
+}
+
+// Returns false for a static micropolygon in a frame without depth of field: the reference
+// renders those with RenderMPG_Static even when other grids move (bucketprocessor.cpp:1087-1090).
+template<bool OPAQUE>
+__device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, uint32_t p, int lane)
+{
+	MovingMP m;
+	m.p = p;
+	const float4 a = f.P4[p];
+	const uint32_t info = infoOf(a);
+	m.g = f.grids[info & VINFO_GRID_MASK];
+	m.cu = m.g.cu_cv & 0xffffu;
+	m.nverts = m.g.nverts;
+	m.nkeys = m.g.nkeys_koff & 0xffu;
+	m.times = f.keyTimes + (m.g.nkeys_koff >> 8);
+	const bool moving = m.nkeys > 1;
+	if(!moving && !f.useDof) return false;
+	float4 P[4];
+	P[0] = a; P[1] = f.P4[p+1]; P[2] = f.P4[p+m.cu+1]; P[3] = f.P4[p+m.cu+2];
+	bool opaque = (info & VINFO_OPAQUE) != 0;
+	if(m.g.flags & AQH_GRID_SMOOTH)
+		opaque = opaque && (infoOf(P[1]) & VINFO_OPAQUE) && (infoOf(P[2]) & VINFO_OPAQUE) && (infoOf(P[3]) & VINFO_OPAQUE);
+	const bool opaqueSlot = opaque || (m.g.flags & AQH_GRID_MATTE_ALPHA);
+	if(opaqueSlot != OPAQUE) return true;
+	m.code = computeVertexOrder(P);
+	// m_Bound: union of the key bounds (AppendKey, micropolygon.cpp:1952-1967)
+	B2 mpBound = boundOf4(P[0], P[1], P[2], P[3]);
+	for(uint32_t k = 1; k < m.nkeys; ++k) { B2 kb = keyBound(f, m, k); encapsulate(mpBound, kb); }
+	// CacheHitTestValues (static :1406-1423, moving :1916-1938)
+	float2 cocMin = make_float2(0.f, 0.f), cocMax = make_float2(0.f, 0.f);
+	if(f.useDof)
+	{
+		if(!moving)
+		{
+			float2 c0 = cocAt(f, P[0].z), c1 = cocAt(f, P[1].z), c2 = cocAt(f, P[2].z), c3 = cocAt(f, P[3].z);
+			cocMin = make_float2(minA(minA(c0.x, c1.x), minA(c2.x, c3.x)), minA(minA(c0.y, c1.y), minA(c2.y, c3.y)));
+			cocMax = make_float2(maxA(maxA(c0.x, c1.x), maxA(c2.x, c3.x)), maxA(maxA(c0.y, c1.y), maxA(c2.y, c3.y)));
+		}
+		else
+		{
+			float2 c1 = cocAt(f, mpBound.mnz), c2 = cocAt(f, mpBound.mxz);
+			if(minCoCForBound(f, mpBound.mnz, mpBound.mxz) == 0.f) cocMin = make_float2(0.f, 0.f);
+			else cocMin = make_float2(minA(c1.x, c2.x), minA(c1.y, c2.y));
+			cocMax = make_float2(maxA(c1.x, c2.x), maxA(c1.y, c2.y));
+		}
+	}
+	const int n = f.n;
+	const float opentime = f.shutterOpen, closetime = f.shutterClose;
+	float timePerSample = 0.f;
+	bool fastShutter = false;
+	if(moving)
+	{
+		const float tol = 10.f*FLT_EPSILON;
+		float d = fabsf(closetime - opentime);
+		fastShutter = (d <= tol*fabsf(closetime)) || (d <= tol*fabsf(opentime));   // isClose, math.h:174-182
+		if(!fastShutter) timePerSample = (float)n / (closetime - opentime);
+	}
+	// BuildBoundList state (micropolygon.cpp:1689-1756), advanced one division per loop turn
+	int divisions = 1;
+	float dt = 0.f, timeAcc = 0.f;
+	int startKey = 0; uint32_t endKey = 1;
+	B2 runBound = mpBound;
+	if(moving)
+	{
+		const B2 kb0 = keyBound(f, m, 0);
+		float cx = kb0.mxx - kb0.mnx, cy = kb0.mxy - kb0.mny;
+		float polyLen2 = (cy == 0.f) ? cx*cx : ((cx == 0.f) ? cy*cy : cx*cx + cy*cy);
+		const float4 pl = f.P4[p + (size_t)(m.nkeys-1)*m.nverts];
+		float mx = P[0].x - pl.x, my = P[0].y - pl.y;
+		float moveDist2 = (my == 0.f) ? mx*mx : ((mx == 0.f) ? my*my : mx*mx + my*my);
+		int polyLengthsMoved = max(1, lfloorF(sqrtf(moveDist2/polyLen2)));
+		const int timeRanges = max(4, n);
+		divisions = min(polyLengthsMoved, timeRanges);
+		dt = (closetime - opentime) / (float)(unsigned)divisions;
+		timeAcc = opentime + dt;
+		runBound = kb0;
+	}
+	for(int bnum = 0; bnum < divisions; ++bnum)
+	{
+		B2 Bnd = mpBound;
+		float time0 = 0.f, time1 = 0.f;
+		if(moving)
+		{
+			const float* times = m.times;
+			while(timeAcc > times[endKey] && endKey < m.nkeys - 1) ++endKey;
+			const int endKey_1 = endKey - 1;
+			const B2 end0 = keyBound(f, m, endKey_1), end1 = keyBound(f, m, endKey);
+			const float end0Time = times[endKey_1], end1Time = times[endKey];
+			const float mix = (timeAcc - end0Time) / (end1Time - end0Time);
+			B2 mid = end0;
+			mid.mnx += mix * (end1.mnx - end0.mnx); mid.mny += mix * (end1.mny - end0.mny); mid.mnz += mix * (end1.mnz - end0.mnz);
+			mid.mxx += mix * (end1.mxx - end0.mxx); mid.mxy += mix * (end1.mxy - end0.mxy); mid.mxz += mix * (end1.mxz - end0.mxz);
+			encapsulate(runBound, mid);
+			while(startKey < endKey_1) { startKey++; B2 kb = keyBound(f, m, startKey); encapsulate(runBound, kb); }
+			Bnd = runBound;
+			time0 = timeAcc - dt;
+			const float nextAcc = timeAcc + dt;
+			time1 = (bnum != divisions - 1) ? (nextAcc - dt) : closetime;
+			runBound = mid;
+			timeAcc = nextAcc;
+		}
+		int indexT0 = 0, indexT1 = 0;
+		if(moving)
+		{
+			if(time1 < opentime || time0 > closetime) continue;
+			if(fastShutter) { indexT0 = 0; indexT1 = n; }
+			else
+			{
+				indexT0 = max(0, lfloorF((time0 - opentime) * timePerSample));
+				indexT1 = lceilF((time1 - opentime) * timePerSample);
+			}
+			if(indexT1 > n) indexT1 = n;
+			if(indexT0 >= n) continue;
+		}
+		if(Bnd.mnz > f.clipFar || Bnd.mxz < f.clipNear) continue;
+		const uint32_t zminKey = depthKey(Bnd.mnz);
+		if(f.useDof)
+		{
+			float2 c1 = cocAt(f, Bnd.mnz), c2 = cocAt(f, Bnd.mxz);
+			const float maxCocX = maxA(c1.x, c2.x), maxCocY = maxA(c1.y, c2.y);
+			for(int cell = lane; cell < n; cell += 32)
+			{
+				const float4 db = f.dofBounds[cell];
+				const float bminx = Bnd.mnx - db.z*maxCocX, bmaxx = Bnd.mxx - db.x*maxCocX;
+				const float bminy = Bnd.mny - db.w*maxCocY, bmaxy = Bnd.mxy - db.y*maxCocY;
+				if(!(bmaxx >= (float)t.rx0) || !(bmaxy >= (float)t.ry0) || !(bminx < (float)t.rx1) || !(bminy < (float)t.ry1)) continue;
+				int eX = (bmaxx >= (float)t.rx1) ? t.rx1 : min(lceilF(bmaxx), t.rx1);
+				int eY = (bmaxy >= (float)t.ry1) ? t.ry1 : min(lceilF(bmaxy), t.ry1);
+				int sX = (bminx < (float)t.rx0) ? t.rx0 : max(floorI(bminx), t.rx0);
+				int sY = (bminy < (float)t.ry0) ? t.ry0 : max(floorI(bminy), t.ry0);
+				for(int iY = sY; iY < eY; ++iY)
+					for(int iX = sX; iX < eX; ++iX)
+					{
+						const int pixLocal = (iY - t.tileY0)*f.tileW + (iX - t.tileX0);
+						// GetDofOffsetIndex(cell) = shuffledIndices[cell] of the pixel's shuffle pattern
+						const int index = f.shufTab[(size_t)s.shufPat[pixLocal]*n + cell];
+						testCandidateMBDof<OPAQUE>(f, t, s, dc, m, moving, mpBound, cocMin, cocMax, pixLocal*n + index,
+						                           0.f, zminKey, bminx, bminy, bmaxx, bmaxy, time0, time1);
+					}
+			}
+		}
+		else
+		{
+			const float bminx = Bnd.mnx, bmaxx = Bnd.mxx, bminy = Bnd.mny, bmaxy = Bnd.mxy;
+			if(!(bmaxx >= (float)t.rx0) || !(bmaxy >= (float)t.ry0) || !(bminx < (float)t.rx1) || !(bminy < (float)t.ry1)) continue;
+			int eX = (bmaxx >= (float)t.rx1) ? t.rx1 : min(lceilF(bmaxx), t.rx1);
+			int eY = (bmaxy >= (float)t.ry1) ? t.ry1 : min(lceilF(bmaxy), t.ry1);
+			int sX = (bminx < (float)t.rx0) ? t.rx0 : max(floorI(bminx), t.rx0);
+			int sY = (bminy < (float)t.ry0) ? t.ry0 : max(floorI(bminy), t.ry0);
+			if(sX >= eX || sY >= eY) continue;
+			// the reference's do-while visits at least one index per pixel
+			const int cnt = max(1, indexT1 - indexT0);
+			const int Wp = eX - sX, npix = Wp*(eY - sY), total = npix*cnt;
+			for(int k = lane; k < total; k += 32)
+			{
+				const int pi = k / cnt, j = k - pi*cnt;
+				const int iY = sY + pi / Wp, iX = sX + pi % Wp;
+				const int pixLocal = (iY - t.tileY0)*f.tileW + (iX - t.tileX0);
+				testCandidateMBDof<OPAQUE>(f, t, s, dc, m, moving, mpBound, cocMin, cocMax, pixLocal*n + indexT0 + j,
+				                           0.f, zminKey, bminx, bminy, bmaxx, bmaxy, time0, time1);
+			}
+		}
+	}
+	return true;
+}
+
+// ---- resolve one sample: colour/opacity of the winning opaque hit, composite of the deep
+// list (CqImagePixel::Combine, imagepixel.cpp:144-332; depth filter "min" only).
+__device__ void hitUV(const DevFrame& f, const GridRec& g, uint32_t p, float2 pos, float2 dofOff, float time, float2& uv)
+{
+	MovingMP m;
+	m.p = p; m.g = g; m.cu = g.cu_cv & 0xffffu; m.nverts = g.nverts; m.nkeys = g.nkeys_koff & 0xffu;
+	m.times = f.keyTimes + (g.nkeys_koff >> 8);
+	float px[4], py[4], pz[4];
+	B2 dummy;
+	samplePoints(f, m, m.nkeys > 1, dummy, make_float2(0.f, 0.f), make_float2(0.f, 0.f), pos, dofOff, time, px, py, pz, false);
+	HitCache c;
+	cachePointInPolyTest(c, px, py, pz, 0xE4 /* any valid code: only the uv part is used */);
+	uv = invBilinear(c.Ax, c.Ay, c.Ex, c.Ey, c.Fx, c.Fy, c.Gx, c.Gy, c.linear, pos.x, pos.y);
+}
+
+__device__ void resolveSample(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, int idx,
+                              float out[7], bool& valid)
+{
+	const unsigned long long key = s.keys[idx];
+	const uint32_t p = (uint32_t)key;
+	const bool haveOpaque = (p != 0xffffffffu);
+	const float2 pos = s.pos[idx];
+	float col[3] = {0.f, 0.f, 0.f}, opa[3] = {0.f, 0.f, 0.f};
+	float depth = 0.f;
+	bool opaqueMatte = false;
+	if(haveOpaque)
+	{
+		const float4 a = f.P4[p];
+		const GridRec g = f.grids[infoOf(a) & VINFO_GRID_MASK];
+		float2 uv;
+		const float2 dofOff = s.dof ? s.dof[idx] : make_float2(0.f, 0.f);
+		const float time = s.time ? s.time[idx] : 0.f;
+		hitUV(f, g, p, pos, dofOff, time, uv);
+		shadeHit(f, g, p, uv, col, opa);
+		depth = keyDepth((uint32_t)(key >> 32));
+		opaqueMatte = (g.flags & AQH_GRID_MATTE) != 0;
+	}
+	uint32_t head = s.head ? s.head[idx] : 0xffffffffu;
+	if(head == 0xffffffffu)
+	{
+		valid = haveOpaque;
+		if(opaqueMatte) { col[0] = col[1] = col[2] = 0.f; opa[0] = opa[1] = opa[2] = 0.f; }  // imagepixel.cpp:308-318
+		out[0] = col[0]; out[1] = col[1]; out[2] = col[2]; out[3] = opa[0]; out[4] = opa[1]; out[5] = opa[2]; out[6] = depth;
+		return;
+	}
+	// back-to-front over {opaque hit} ∪ deep list, i.e. descending (depth, order)
+	float sc[3] = {0.f, 0.f, 0.f}, so[3] = {0.f, 0.f, 0.f};
+	float opaqueDepth0 = haveOpaque ? depth : FLT_MAX;      // opaqueDepths[0] = occlZ
+	if(haveOpaque)
+	{
+		if(opaqueMatte)
+		{
+#pragma unroll
+			for(int k = 0; k < 3; ++k) { sc[k] = (1.f-opa[k])*sc[k] + opa[k]*0.0f; so[k] = (1.f-col[k])*so[k] + col[k]*0.0f; }
+		}
+		else
+		{
+#pragma unroll
+			for(int k = 0; k < 3; ++k)
+			{
+				sc[k] = (sc[k] * (1.0f - fminf(fmaxf(opa[k], 0.0f), 1.0f))) + col[k];
+				so[k] = ((1.0f - so[k]) * opa[k]) + so[k];
+			}
+		}
+		if(opa[0] >= f.zthr[0] && opa[1] >= f.zthr[1] && opa[2] >= f.zthr[2]) opaqueDepth0 = depth;
+	}
+	unsigned long long prev = ~0ull;
+	for(;;)
+	{
+		// farthest not yet composited entry: largest (depthKey, p) strictly below prev
+		unsigned long long best = 0; uint32_t bestSlot = 0xffffffffu;
+		for(uint32_t e = head; e != 0xffffffffu; )
+		{
+			const uint4 A = dc.A[e];
+			unsigned long long k = ((unsigned long long)depthKey(__uint_as_float(A.y)) << 32) | A.z;
+			if(k < prev && (bestSlot == 0xffffffffu || k > best)) { best = k; bestSlot = e; }
+			e = A.x;
+		}
+		if(bestSlot == 0xffffffffu) break;
+		prev = best;
+		const uint4 A = dc.A[bestSlot];
+		const float2 uv = dc.UV[bestSlot];
+		const float4 a = f.P4[A.z];
+		const GridRec g = f.grids[infoOf(a) & VINFO_GRID_MASK];
+		float c2[3], o2[3];
+		shadeHit(f, g, A.z, uv, c2, o2);
+		const float d2 = __uint_as_float(A.y);
+		if(g.flags & AQH_GRID_MATTE)
+		{
+#pragma unroll
+			for(int k = 0; k < 3; ++k) { sc[k] = (1.f-o2[k])*sc[k] + o2[k]*0.0f; so[k] = (1.f-c2[k])*so[k] + c2[k]*0.0f; }
+		}
+		else
+		{
+#pragma unroll
+			for(int k = 0; k < 3; ++k)
+			{
+				sc[k] = (sc[k] * (1.0f - fminf(fmaxf(o2[k], 0.0f), 1.0f))) + c2[k];
+				so[k] = ((1.0f - so[k]) * o2[k]) + so[k];
+			}
+		}
+		if(o2[0] >= f.zthr[0] && o2[1] >= f.zthr[1] && o2[2] >= f.zthr[2]) opaqueDepth0 = d2;
+	}
+	valid = true;
+	out[0] = sc[0]; out[1] = sc[1]; out[2] = sc[2]; out[3] = so[0]; out[4] = so[1]; out[5] = so[2];
+	out[6] = opaqueDepth0;
+}
+
+// ------------------------------------------------------------------------------------
+// k_hide: persistent CTAs pull tiles from a counter.
+template<bool MBDOF>
+__global__ void __launch_bounds__(256, 2) k_hide(DevFrame f, int batch)
+{
+	extern __shared__ __align__(16) unsigned char smemRaw[];
+	__shared__ uint32_t s_tile;
+	__shared__ uint32_t s_deepCount;
+	const HideSmem s = carveSmem(f, smemRaw, batch);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+	const int n = f.n, xs = f.xs;
+	DeepCtx dc;
+	dc.A = f.deepA + (size_t)blockIdx.x*f.deepCapPerCta;
+	dc.UV = f.deepUV + (size_t)blockIdx.x*f.deepCapPerCta;
+	dc.cap = f.deepCapPerCta;
+	dc.count = &s_deepCount;
+	// sub-sample -> sample index tables (pixel-major sample layout: idx = pixel*n + i)
+	for(int gx = tid; gx < f.tileW*xs; gx += blockDim.x) s.colIdx[gx] = (uint16_t)((gx / xs)*n + gx % xs);
+	for(int gy = tid; gy < f.tileH*f.ys; gy += blockDim.x) s.rowIdx[gy] = (uint16_t)((gy / f.ys)*f.tileW*n + (gy % f.ys)*xs);
+	for(;;)
+	{
+		__syncthreads();
+		if(tid == 0) { s_tile = atomicAdd(f.tileCursor, 1u); s_deepCount = 0; }
+		__syncthreads();
+		const uint32_t slot = s_tile;
+		if(slot >= (uint32_t)f.nActiveTiles) break;
+		const uint32_t tile = f.activeTiles[slot];
+		TileCtx t;
+		t.tileX0 = f.sx0 + (int)(tile % f.ntx)*f.tileW;
+		t.tileY0 = f.sy0 + (int)(tile / f.ntx)*f.tileH;
+		t.rx0 = t.tileX0; t.ry0 = t.tileY0;
+		t.rx1 = min(t.tileX0 + f.tileW, f.sx0 + f.sw);
+		t.ry1 = min(t.tileY0 + f.tileH, f.sy0 + f.sh);
+		t.ns = f.tileW*f.tileH*n;
+		// ---- Prepare_bucket: CqImagePixel::clear + setSamples (imagepixel.cpp:105-122, 334-359)
+		for(int idx = tid; idx < t.ns; idx += blockDim.x)
+		{
+			const int pixLocal = idx / n, i = idx - pixLocal*n;
+			const int X = t.tileX0 + pixLocal % f.tileW, Y = t.tileY0 + pixLocal / f.tileW;
+			s.keys[idx] = KEY_EMPTY;
+			if(s.head) s.head[idx] = 0xffffffffu;
+			if(X < t.rx1 && Y < t.ry1)
+			{
+				const size_t pp = (size_t)(Y - f.sy0)*f.sw + (X - f.sx0);
+				const size_t plane = (size_t)f.sw*f.sh;
+				const int patPos = f.patPlanes[plane + pp];
+				const float2 o = f.posTab[(size_t)patPos*n + i];
+				s.pos[idx] = make_float2((float)X + o.x, (float)Y + o.y);
+				if(s.time)
+				{
+					const int patT = f.patPlanes[3*plane + pp];
+					s.time[idx] = (f.shutterClose - f.shutterOpen) * f.val1d[(size_t)patT*n + i] + f.shutterOpen;
+				}
+				if(s.dof)
+				{
+					// samples[shuffled[i]].dofOffset = projectToCircle(-1 + 2*dofOffsets[i])
+					const int patS = f.patPlanes[pp], patD = f.patPlanes[2*plane + pp];
+					const int j = f.shufTab[(size_t)patS*n + i];
+					const float2 d = f.posTab[(size_t)patD*n + i];
+					const float vx = -1.f + 2.f*d.x, vy = -1.f + 2.f*d.y;
+					float m2 = (vy == 0.f) ? vx*vx : ((vx == 0.f) ? vy*vy : vx*vx + vy*vy);
+					float r = sqrtf(m2);
+					float2 o2 = make_float2(0.f, 0.f);
+					if(r != 0.f)
+					{
+						float adj = maxA(fabsf(vx), fabsf(vy)) / r;
+						o2 = make_float2(adj*vx, adj*vy);
+					}
+					s.dof[pixLocal*n + j] = o2;
+					if(i == 0) s.shufPat[pixLocal] = (uint8_t)patS;
+				}
+			}
+			else
+				s.pos[idx] = make_float2(-1e30f, -1e30f);
+		}
+		__syncthreads();
+		const uint32_t binBeg = f.binOffset[slot], binEnd = f.binOffset[slot+1];
+		const uint32_t tflags = f.tileFlags[slot];
+		// ---- Render_MPGs: opaque pass, then (if the tile saw non-opaque micropolygons) deep pass
+		for(int pass = 0; pass < 2; ++pass)
+		{
+			if(pass == 1 && !(f.anyTransparent && (tflags & 1u))) break;
+			if(MBDOF)
+			{
+				for(uint32_t e = binBeg + warp; e < binEnd; e += nwarps)
+				{
+					const uint32_t p = f.binEntries[e];
+					const bool handled = (pass == 0) ? renderMBOrDof<true>(f, t, s, dc, p, lane)
+					                                 : renderMBOrDof<false>(f, t, s, dc, p, lane);
+					if(!handled)
+					{
+						// static micropolygon, no depth of field: the per-warp record slot
+						if(lane == 0) setupStaticRec(f, t, p, pass == 0, s.recs[warp]);
+						__syncwarp();
+						if(pass == 0) sampleStaticRec<true>(f, t, s, dc, s.recs[warp], lane);
+						else sampleStaticRec<false>(f, t, s, dc, s.recs[warp], lane);
+						__syncwarp();
+					}
+				}
+			}
+			else
+			{
+				for(uint32_t b0 = binBeg; b0 < binEnd; b0 += batch)
+				{
+					const int cnt = min((uint32_t)batch, binEnd - b0);
+					for(int j = tid; j < cnt; j += blockDim.x)
+						setupStaticRec(f, t, f.binEntries[b0 + j], pass == 0, s.recs[j]);
+					__syncthreads();
+					for(int j = warp; j < cnt; j += nwarps)
+					{
+						if(pass == 0) sampleStaticRec<true>(f, t, s, dc, s.recs[j], lane);
+						else sampleStaticRec<false>(f, t, s, dc, s.recs[j], lane);
+					}
+					__syncthreads();
+				}
+			}
+			__syncthreads();
+		}
+		if(tid == 0 && s_deepCount) atomicAdd(&f.counters[2], (unsigned long long)min(s_deepCount, dc.cap));
+		// ---- Combine_samples + hand the resolved samples to the filter stage.
+		// Planes are [k][i][y][x]: consecutive threads take consecutive x of one sample index.
+		const int tw = t.rx1 - t.rx0, th = t.ry1 - t.ry0;
+		const int nOut = tw*th*n;
+		for(int o = tid; o < nOut; o += blockDim.x)
+		{
+			const int lx = o % tw, r2 = o / tw, ly = r2 % th, i = r2 / th;
+			const int idx = (ly*f.tileW + lx)*n + i;
+			float out[7]; bool valid;
+			resolveSample(f, t, s, dc, idx, out, valid);
+			const int X = t.rx0 + lx, Y = t.ry0 + ly;
+			const size_t at = ((size_t)i*f.sh + (size_t)(Y - f.sy0))*f.sw + (size_t)(X - f.sx0);
+			// per-tap inclusion bits (bucketprocessor.cpp:609-612), evaluated with the true pixel
+			// coordinates: this sample belongs to filter tap (fx,fy) of output pixel (X-fx, Y-fy).
+			const float2 pos = s.pos[idx];
+			uint32_t mask = valid ? 0x80000000u : 0u;
+			for(int fx = -f.shiftX; fx <= f.shiftX; ++fx)
+			{
+				float vx = pos.x - ((float)(X - fx) + 0.5f);
+				if(vx >= -f.xfwo2 && vx <= f.xfwo2) mask |= 1u << (fx + f.shiftX);
+			}
+			for(int fy = -f.shiftY; fy <= f.shiftY; ++fy)
+			{
+				float vy = pos.y - ((float)(Y - fy) + 0.5f);
+				if(vy >= -f.yfwo2 && vy <= f.yfwo2) mask |= 1u << (15 + fy + f.shiftY);
+			}
+			f.maskPlane[at] = mask;
+			if(valid)
+			{
+#pragma unroll
+				for(int k = 0; k < 7; ++k) f.planes[(size_t)k*f.planeStride + at] = out[k];
+			}
+		}
+	}
+}
+
+// Mark tiles whose bins contain non-opaque micropolygons (drives the deep pass).
+__global__ void __launch_bounds__(256) k_tile_flags(DevFrame f)
+{
+	const int slot = blockIdx.x;
+	__shared__ uint32_t s_any;
+	if(threadIdx.x == 0) s_any = 0;
+	__syncthreads();
+	uint32_t any = 0;
+	for(uint32_t e = f.binOffset[slot] + threadIdx.x; e < f.binOffset[slot+1] && !any; e += 256)
+	{
+		const uint32_t p = f.binEntries[e];
+		const float4 a = f.P4[p];
+		const uint32_t info = infoOf(a);
+		const GridRec g = f.grids[info & VINFO_GRID_MASK];
+		const uint32_t cu = g.cu_cv & 0xffffu;
+		bool opaque = (info & VINFO_OPAQUE) != 0;
+		if(g.flags & AQH_GRID_SMOOTH)
+			opaque = opaque && (infoOf(f.P4[p+1]) & VINFO_OPAQUE) && (infoOf(f.P4[p+cu+1]) & VINFO_OPAQUE) && (infoOf(f.P4[p+cu+2]) & VINFO_OPAQUE);
+		if(!(opaque || (g.flags & AQH_GRID_MATTE_ALPHA))) any = 1;
+	}
+	if(any) s_any = 1;
+	__syncthreads();
+	if(threadIdx.x == 0) f.tileFlags[slot] = s_any;
+}
+
+// ------------------------------------------------------------------------------------
+// k_filter: one thread per output pixel, taps in the reference's fy, fx, sy, sx order so the
+// float sums round identically (bucketprocessor.cpp:584-664); then coverage/alpha (:695-707),
+// ExposeBucket (:766-806) and FormatBucketForDisplay (ddmanager.cpp:1046-1113).
+__device__ __forceinline__ double clampD(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__global__ void __launch_bounds__(256) k_filter(DevFrame f, DevDisplays disp)
+{
+	extern __shared__ float s_filt[];
+	const int taps = (2*f.shiftX+1)*(2*f.shiftY+1)*f.n;
+	for(int i = threadIdx.x + threadIdx.y*blockDim.x; i < taps; i += blockDim.x*blockDim.y) s_filt[i] = f.filterTab[i];
+	__syncthreads();
+	const int x = f.cropX0 + blockIdx.x*blockDim.x + threadIdx.x;
+	const int y = f.cropY0 + blockIdx.y*blockDim.y + threadIdx.y;
+	if(x >= f.cropX1 || y >= f.cropY1) return;
+	if(f.rowOwned && !f.rowOwned[y]) return;
+	const int n = f.n, xmax = f.shiftX, ymax = f.shiftY;
+	float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+	float gTot = 0.f;
+	int SampleCount = 0;
+	for(int fy = -ymax; fy <= ymax; ++fy)
+		for(int fx = -xmax; fx <= xmax; ++fx)
+		{
+			const float* g = s_filt + ((fy + ymax)*(2*xmax+1) + fx + xmax)*n;
+			const uint32_t need = (1u << (fx + xmax)) | (1u << (15 + fy + ymax));
+			size_t at = (size_t)(y + fy - f.sy0)*f.sw + (size_t)(x + fx - f.sx0);
+			const size_t step = (size_t)f.sw*f.sh;
+			for(int sIdx = 0; sIdx < n; ++sIdx, at += step)
+			{
+				const uint32_t m = f.maskPlane[at];
+				if((m & need) == need)
+				{
+					const float w = g[sIdx];
+					gTot += w;
+					if(m & 0x80000000u)
+					{
+#pragma unroll
+						for(int k = 0; k < 7; ++k)
+							acc[k] += f.planes[(size_t)k*f.planeStride + at] * w;
+						SampleCount++;
+					}
+				}
+			}
+		}
+	float out[9];
+	float coverage;
+	if(SampleCount == 0)
+	{
+#pragma unroll
+		for(int k = 0; k < 9; ++k) out[k] = 0.f;
+		out[AQH_CH_Z] = FLT_MAX;
+		coverage = 0.f;
+	}
+	else
+	{
+		const float oneOverGTot = 1.0f / gTot;
+#pragma unroll
+		for(int k = 0; k < 6; ++k) out[k] = acc[k] * oneOverGTot;
+		out[AQH_CH_Z] = acc[6] * oneOverGTot;
+		coverage = (SampleCount >= n) ? 1.0f : (float)SampleCount / (float)n;
+	}
+	const float a = (out[3] + out[4] + out[5]) / 3.0f;
+	out[AQH_CH_ALPHA] = a * coverage;
+	out[AQH_CH_COVERAGE] = coverage;
+	if(!(f.expGain == 1.0f && f.expGamma == 1.0f))
+	{
+		const float oneovergamma = 1.0f / f.expGamma;
+#pragma unroll
+		for(int k = 0; k < 3; ++k)
+		{
+			if(f.expGain != 1.0f) out[k] *= f.expGain;
+			if(f.expGamma != 1.0f) out[k] = (float)pow((double)out[k], (double)oneovergamma);
+		}
+	}
+	float* dst = f.channels + ((size_t)y*f.xres + x)*9;
+#pragma unroll
+	for(int k = 0; k < 9; ++k) dst[k] = out[k];
+	// quantise
+	for(int d = 0; d < disp.n; ++d)
+	{
+		const DevDisplay& dd = disp.d[d];
+		const double s = (double)f.dither[((size_t)d*f.yres + y)*f.xres + x];
+		unsigned char* pd = dd.out + ((size_t)y*f.xres + x)*dd.entrySize;
+		for(int c = 0; c < dd.nChannels; ++c)
+		{
+			double value = (double)out[dd.channel[c]];
+			if(dd.qOne != 0.f)
+			{
+				double v = (double)dd.qZero + value * (double)(dd.qOne - dd.qZero) + ((double)dd.qDither * s);
+				// lround(x) = lfloor(x - 0.5) + 1, math.h:47-70
+				double xm = v - 0.5;
+				long long li = (long long)xm;
+				li = li - ((xm < 0.0 && xm != (double)li) ? 1 : 0);
+				value = (double)(li + 1);
+				value = clampD(value, (double)dd.qMin, (double)dd.qMax);
+			}
+			switch(dd.type)
+			{
+				case AQH_FLOAT32: { float v = (float)value; memcpy(pd, &v, 4); pd += 4; break; }
+				case AQH_UNSIGNED32: { value = clampD(value, 0.0, 4294967295.0); uint32_t v = (uint32_t)value; memcpy(pd, &v, 4); pd += 4; break; }
+				case AQH_SIGNED32: { value = clampD(value, -2147483648.0, 2147483647.0); int32_t v = (int32_t)value; memcpy(pd, &v, 4); pd += 4; break; }
+				case AQH_UNSIGNED16: { uint16_t v = (uint16_t)(int)value; memcpy(pd, &v, 2); pd += 2; break; }
+				case AQH_SIGNED16: { int16_t v = (int16_t)(int)value; memcpy(pd, &v, 2); pd += 2; break; }
+				case AQH_UNSIGNED8: { *pd++ = (unsigned char)(int)value; break; }
+				case AQH_SIGNED8: { *pd++ = (unsigned char)(signed char)(int)value; break; }
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------
+// launchers
+cudaError_t launchProject(const DevFrame& f, cudaStream_t st)
+{
+	if(f.nPos == 0) return cudaSuccess;
+	const unsigned blocks = (unsigned)((f.nPos + 255) / 256);
+	k_project<<<blocks, 256, 0, st>>>(f);
+	k_splitlines<<<(f.nGrids + 127)/128, 128, 0, st>>>(f);
+	return cudaGetLastError();
+}
+cudaError_t launchBinCount(const DevFrame& f, cudaStream_t st)
+{
+	if(f.nPos == 0) return cudaSuccess;
+	k_bin<false><<<(unsigned)((f.nPos + 255)/256), 256, 0, st>>>(f);
+	return cudaGetLastError();
+}
+cudaError_t launchBinScan(const DevFrame& f, cudaStream_t st)
+{
+	k_bin_scan<<<1, 1024, 0, st>>>(f);
+	return cudaGetLastError();
+}
+cudaError_t launchBinFill(const DevFrame& f, cudaStream_t st)
+{
+	if(f.nPos)
+		k_bin<true><<<(unsigned)((f.nPos + 255)/256), 256, 0, st>>>(f);
+	if(f.nActiveTiles)
+		k_tile_flags<<<f.nActiveTiles, 256, 0, st>>>(f);
+	return cudaGetLastError();
+}
+
+cudaError_t hideKernelConfig(const DevFrame& f, int smCount, LaunchCfg& cfg)
+{
+	cfg.smCount = smCount;
+	cfg.hideThreads = 256;
+	const bool mbdof = f.useDof || f.anyMotion;
+	cfg.batchMPs = mbdof ? 8 : 256;   // MB/DoF: one record slot per warp
+	cfg.hideSmemBytes = hideSmemBytes(f, cfg.batchMPs);
+	if(cfg.hideSmemBytes > 227*1024) return cudaErrorInvalidValue;
+	cudaError_t e;
+	if(mbdof) e = cudaFuncSetAttribute(k_hide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.hideSmemBytes);
+	else e = cudaFuncSetAttribute(k_hide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.hideSmemBytes);
+	if(e != cudaSuccess) return e;
+	int perSm = 0;
+	if(mbdof) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_hide<true>, cfg.hideThreads, cfg.hideSmemBytes);
+	else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_hide<false>, cfg.hideThreads, cfg.hideSmemBytes);
+	if(e != cudaSuccess) return e;
+	if(perSm < 1) perSm = 1;
+	cfg.hideCtas = smCount * perSm;
+	return cudaSuccess;
+}
+
+cudaError_t launchHide(const DevFrame& f, const LaunchCfg& cfg, cudaStream_t st)
+{
+	if(f.nActiveTiles == 0) return cudaSuccess;
+	const bool mbdof = f.useDof || f.anyMotion;
+	if(mbdof) k_hide<true><<<cfg.hideCtas, cfg.hideThreads, cfg.hideSmemBytes, st>>>(f, cfg.batchMPs);
+	else k_hide<false><<<cfg.hideCtas, cfg.hideThreads, cfg.hideSmemBytes, st>>>(f, cfg.batchMPs);
+	return cudaGetLastError();
+}
+
+cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, cudaStream_t st)
+{
+	const int w = f.cropX1 - f.cropX0, h = f.cropY1 - f.cropY0;
+	if(w <= 0 || h <= 0) return cudaSuccess;
+	dim3 block(32, 8), grid((w + 31)/32, (h + 7)/8);
+	const size_t smem = (size_t)(2*f.shiftX+1)*(2*f.shiftY+1)*f.n*sizeof(float);
+	if(smem > 48*1024)
+	{
+		cudaError_t e = cudaFuncSetAttribute(k_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if(e != cudaSuccess) return e;
+	}
+	k_filter<<<grid, block, smem, st>>>(f, disp);
+	return cudaGetLastError();
+}
+
+int kernelsArchOk()
+{
+	cudaFuncAttributes a;
+	return cudaFuncGetAttributes(&a, k_project) == cudaSuccess ? 1 : 0;
+}
+
+} // namespace aqh

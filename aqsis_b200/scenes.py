@@ -1,0 +1,168 @@
+"""Synthetic shaded grids of the shapes BASELINE.json names.
+
+The renderer front end (RIB, dicing, aqsl shaders) is outside the hot path and not buildable
+here, so the inputs of the hider -- shaded micropolygon grids (P, Ci, Oi) -- are generated
+directly: P already in the hybrid raster-x,y / camera-z space CqMicroPolyGrid::Split produces,
+"plastic" emulated by a smooth Lambert-like colour field.  Seed 20261017.
+"""
+import math
+
+import numpy as np
+
+from . import _abi as abi
+from .hider import GridArrays, default_params
+
+SEED = 20261017
+
+
+def _grids(rng, centers, size_px, cu, cv, zmin, zmax, warp=0.12, noise=0.02, opacity=None, rot=True):
+    """G grids of (cu+1)x(cv+1) vertices around `centers`, each about `size_px` pixels wide."""
+    G = centers.shape[0]
+    u = np.linspace(0.0, 1.0, cu + 1, dtype=np.float32)
+    v = np.linspace(0.0, 1.0, cv + 1, dtype=np.float32)
+    uu, vv = np.meshgrid(u, v)                       # (cv+1, cu+1): vertex index = iv*(cu+1)+iu
+    uu = uu.reshape(1, -1)
+    vv = vv.reshape(1, -1)
+    sx = (size_px * rng.uniform(0.85, 1.15, (G, 1))).astype(np.float32)
+    sy = (size_px * rng.uniform(0.85, 1.15, (G, 1))).astype(np.float32)
+    lx = (uu - 0.5) * sx
+    ly = (vv - 0.5) * sy
+    # bilinear corner warp: makes the micropolygons non-rectangular (second Newton step path)
+    w = (rng.uniform(-warp, warp, (G, 4, 2)) * size_px).astype(np.float32)
+    b00, b10, b01, b11 = (1 - uu) * (1 - vv), uu * (1 - vv), (1 - uu) * vv, uu * vv
+    lx = lx + b00 * w[:, 0:1, 0] + b10 * w[:, 1:2, 0] + b01 * w[:, 2:3, 0] + b11 * w[:, 3:4, 0]
+    ly = ly + b00 * w[:, 0:1, 1] + b10 * w[:, 1:2, 1] + b01 * w[:, 2:3, 1] + b11 * w[:, 3:4, 1]
+    if rot:
+        th = rng.uniform(0, 2 * math.pi, (G, 1)).astype(np.float32)
+        c, s = np.cos(th), np.sin(th)
+        lx, ly = c * lx - s * ly, s * lx + c * ly
+    nv = (cu + 1) * (cv + 1)
+    P = np.empty((G, nv, 3), dtype=np.float32)
+    P[:, :, 0] = centers[:, 0:1] + lx + rng.normal(0, noise, (G, nv)).astype(np.float32)
+    P[:, :, 1] = centers[:, 1:2] + ly + rng.normal(0, noise, (G, nv)).astype(np.float32)
+    z0 = rng.uniform(zmin, zmax, (G, 1)).astype(np.float32)
+    slope = (rng.uniform(-0.05, 0.05, (G, 2)) * z0).astype(np.float32)
+    P[:, :, 2] = z0 + slope[:, 0:1] * uu + slope[:, 1:2] * vv
+    # "plastic": base colour times a smooth diffuse term plus a small highlight
+    base = rng.uniform(0.15, 1.0, (G, 1, 3)).astype(np.float32)
+    ph = rng.uniform(0, 2 * math.pi, (G, 2)).astype(np.float32)
+    diff = 0.35 + 0.65 * (0.5 + 0.5 * np.sin(4.0 * uu + ph[:, 0:1]) * np.cos(3.0 * vv + ph[:, 1:2]))
+    spec = 0.25 * np.clip(1.0 - 6.0 * ((uu - 0.4) ** 2 + (vv - 0.6) ** 2), 0, 1) ** 4
+    Ci = (base * diff[:, :, None] + spec[:, :, None]).astype(np.float32)
+    if opacity is None:
+        Oi = np.ones((G, nv, 3), dtype=np.float32)
+    else:
+        Oi = np.broadcast_to(np.asarray(opacity, dtype=np.float32).reshape(-1, 1, 1), (G, nv, 3)).copy()
+        Ci = Ci * Oi                                   # premultiplied, as shaders hand Ci over
+    return P, Ci, Oi
+
+
+def _pack(P, Ci, Oi, cu, cv, flags=abi.GRID_SMOOTH, P2=None, key_times=None):
+    G = P.shape[0]
+    if P2 is not None:
+        Pk = np.stack([P, P2], axis=1).reshape(-1, 3)     # per grid: key-major
+        nkeys = np.full(G, 2, dtype=np.int32)
+        kt = np.tile(np.asarray(key_times, dtype=np.float32), G)
+    else:
+        Pk = P.reshape(-1, 3)
+        nkeys = None
+        kt = None
+    return GridArrays(cu=np.full(G, cu, dtype=np.int32), cv=np.full(G, cv, dtype=np.int32),
+                      flags=np.full(G, flags, dtype=np.uint32), P=np.ascontiguousarray(Pk),
+                      Ci=np.ascontiguousarray(Ci.reshape(-1, 3)), Oi=np.ascontiguousarray(Oi.reshape(-1, 3)),
+                      nkeys=nkeys, key_times=kt)
+
+
+def concat(blocks):
+    """Concatenate GridArrays (all static or all with nkeys given)."""
+    any_keys = any(b.nkeys is not None for b in blocks)
+    nk, kt = None, None
+    if any_keys:
+        nk = np.concatenate([b.nkeys if b.nkeys is not None else np.ones(b.n_grids, np.int32) for b in blocks])
+        kt = np.concatenate([b.key_times if b.key_times is not None else np.zeros(b.n_grids, np.float32) for b in blocks])
+    return GridArrays(cu=np.concatenate([b.cu for b in blocks]), cv=np.concatenate([b.cv for b in blocks]),
+                      flags=np.concatenate([b.flags for b in blocks]), P=np.concatenate([b.P for b in blocks]),
+                      Ci=np.concatenate([b.Ci for b in blocks]), Oi=np.concatenate([b.Oi for b in blocks]),
+                      nkeys=nk, key_times=kt)
+
+
+_RGBA8 = ("rgba", 1, 255.0, 0.0, 255.0, 0.5)     # Quantize "rgba" 255 0 255 0.5, file-driver channel order
+
+
+def config1(scale=1.0, seed=SEED):
+    """640x480, PixelSamples 4 4, gaussian 2x2, 10k bilinear patches diced 8x8 (~8x8 px each)."""
+    xres, yres = max(16, int(640 * scale)), max(16, int(480 * scale))
+    rng = np.random.default_rng(seed)
+    G = max(4, int(10000 * scale * scale))
+    centers = np.stack([rng.uniform(-4, xres + 4, G), rng.uniform(-4, yres + 4, G)], axis=1).astype(np.float32)
+    P, Ci, Oi = _grids(rng, centers, 8.0, 8, 8, 5.0, 50.0)
+    params = default_params(resolution=(xres, yres), samples=(4, 4), filter=("gaussian", 2.0, 2.0), displays=[_RGBA8])
+    return params, _pack(P, Ci, Oi, 8, 8)
+
+
+def config2(scale=1.0, seed=SEED + 1, filter=("catmull-rom", 3.0, 3.0), samples=(8, 8)):
+    """1920x1080, PixelSamples 8 8, ShadingRate 1, ~20M micropolygons, opaque, catmull-rom 3x3."""
+    xres, yres = max(16, int(1920 * scale)), max(16, int(1080 * scale))
+    rng = np.random.default_rng(seed)
+    G = max(4, int(78125 * scale * scale))
+    centers = np.stack([rng.uniform(-8, xres + 8, G), rng.uniform(-8, yres + 8, G)], axis=1).astype(np.float32)
+    P, Ci, Oi = _grids(rng, centers, 16.0, 16, 16, 2.0, 100.0)
+    params = default_params(resolution=(xres, yres), samples=samples, filter=filter, displays=[_RGBA8])
+    return params, _pack(P, Ci, Oi, 16, 16)
+
+
+def config3(scale=1.0, seed=SEED + 1, motion_px=16.0, fstop=2.8, focallength=0.05, focaldistance=20.0):
+    """config2 geometry + Shutter 0 1 with 2 keys per grid (raster motion ~U(0,16) px) + depth of field."""
+    xres, yres = max(16, int(1920 * scale)), max(16, int(1080 * scale))
+    rng = np.random.default_rng(seed)
+    G = max(4, int(78125 * scale * scale))
+    centers = np.stack([rng.uniform(-8, xres + 8, G), rng.uniform(-8, yres + 8, G)], axis=1).astype(np.float32)
+    P, Ci, Oi = _grids(rng, centers, 16.0, 16, 16, 2.0, 100.0)
+    ang = rng.uniform(0, 2 * math.pi, (G, 1))
+    mag = rng.uniform(0, motion_px, (G, 1))
+    P2 = P.copy()
+    P2[:, :, 0] += (mag * np.cos(ang)).astype(np.float32)
+    P2[:, :, 1] += (mag * np.sin(ang)).astype(np.float32)
+    P2[:, :, 2] *= rng.uniform(0.97, 1.03, (G, 1)).astype(np.float32)
+    # DoF scale: raster pixels per camera unit at z=1 for fov 40 degrees (options.cpp:162-171)
+    s = 0.5 * yres / math.tan(math.radians(20.0))
+    params = default_params(resolution=(xres, yres), samples=(8, 8), filter=("catmull-rom", 3.0, 3.0),
+                            shutter=(0.0, 1.0), dof=(fstop, focallength, focaldistance, s, s), displays=[_RGBA8])
+    return params, _pack(P, Ci, Oi, 16, 16, P2=P2, key_times=(0.0, 1.0))
+
+
+def config4(scale=1.0, seed=SEED + 3, layers=4):
+    """3840x2160, PixelSamples 16 16, ShadingRate 0.25, semi-transparent layered surfaces."""
+    xres, yres = max(16, int(3840 * scale)), max(16, int(2160 * scale))
+    rng = np.random.default_rng(seed)
+    blocks = []
+    opac = [0.25, 0.5, 0.75]
+    gx, gy = (xres + 7) // 8 + 1, (yres + 7) // 8 + 1       # 16x16-MP grids of 8x8 px => MP area 0.25 px^2
+    for layer in range(layers):
+        cx, cy = np.meshgrid(np.arange(gx, dtype=np.float32) * 8.0, np.arange(gy, dtype=np.float32) * 8.0)
+        centers = np.stack([cx.ravel(), cy.ravel()], axis=1) + rng.uniform(-1.5, 1.5, (gx * gy, 2)).astype(np.float32)
+        z0 = 10.0 + 10.0 * layer
+        o = None if layer == layers - 1 else np.full(gx * gy, opac[layer % 3], dtype=np.float32)
+        P, Ci, Oi = _grids(rng, centers, 9.0, 16, 16, z0, z0 + 5.0, warp=0.05, noise=0.01, opacity=o, rot=False)
+        blocks.append(_pack(P, Ci, Oi, 16, 16))
+    params = default_params(resolution=(xres, yres), samples=(16, 16), filter=("gaussian", 2.0, 2.0), displays=[_RGBA8])
+    return params, concat(blocks)
+
+
+def config5_filters():
+    """The PixelFilter sweep of config 5: (name, width) pairs run on the config-2 scene."""
+    return [(name, float(w)) for name in ("box", "triangle", "gaussian", "catmull-rom", "sinc") for w in range(1, 7)]
+
+
+def algorithmic_bytes(params, grids: GridArrays):
+    """B_alg of SURVEY.md 8(d): V*(12K + 24) + W*H*(36 + E)."""
+    nv = (grids.cu.astype(np.int64) + 1) * (grids.cv.astype(np.int64) + 1)
+    nk = grids.nkeys.astype(np.int64) if grids.nkeys is not None else np.ones_like(nv)
+    vbytes = int((nv * (12 * nk + 24)).sum())
+    w = params.crop_xmax - params.crop_xmin
+    h = params.crop_ymax - params.crop_ymin
+    e = 0
+    from .hider import display_info
+    for d in range(params.n_displays):
+        e += display_info(params, d)[2]
+    return vbytes + w * h * (36 + e)

@@ -1,0 +1,283 @@
+/* aqsis_b200_hider.h -- C ABI of the B200-native REYES hider + pixel filter.
+ *
+ * This is the drop-in boundary for the post-shading hot path of aqsis
+ * (SURVEY.md section 8b).  The reference has no plugin seam around its hider:
+ * it is reached by direct C++ calls.  Every entry point below therefore names
+ * the reference interface it stands in for (paths relative to the aqsis tree):
+ *
+ *   aqh_begin_frame   <- CqImageBuffer::SetImage()            libs/core/imagebuffer.cpp:174-228
+ *                        SqOptionCache::cacheOptions()        libs/core/optioncache.cpp:50-117
+ *                        CqRenderer::SetDepthOfFieldData/...  libs/core/renderer.h:368-406
+ *                        CqMultiJitteredSampler ctor          libs/core/multijitter.h:90-101
+ *                        CqBucketProcessor::InitialiseFilterValues  bucketprocessor.cpp:811-856
+ *   aqh_add_grid      <- CqMicroPolyGridBase::Split(xmin,xmax,ymin,ymax)  libs/core/micropolygon.h:115
+ *                        (call site bucketprocessor.cpp:1036) which busts the grid and feeds
+ *                        CqImageBuffer::AddMPG(shared_ptr<CqMicroPolygon>&)  imagebuffer.h:91
+ *   aqh_add_grid_block<- the same, for many grids at once (host or device resident)
+ *   aqh_end_frame     <- CqImageBuffer::RenderImage()         libs/core/imagebuffer.cpp:605-779
+ *                        and, per bucket, IqDDManager::DisplayBucket(CqRegion, IqChannelBuffer*)
+ *                        libs/core/ddmanager/iddmanager.h:99 -> FormatBucketForDisplay
+ *                        ddmanager.cpp:1022-1118 -> DspyImageData  include/aqsis/ri/ndspy.h:186-192
+ *   AqhBucketFunc     <- IqDDManager::DisplayBucket            (float channel buffer per bucket)
+ *   AqhDataFunc       <- DspyImageDataMethod                   include/aqsis/ri/ndspy.h:157
+ *   AqhProgressFunc   <- RtProgressFunc                        include/aqsis/ri/ritypes.h:73
+ *   AqhFilterFunc     <- RtFilterFunc                          include/aqsis/ri/ritypes.h:56
+ *   aqh_*_filter      <- RiGaussianFilter & co                 libs/core/filters.cpp:71-348
+ *
+ * Conventions: plain C, plain pointers and sizes, no exceptions cross the ABI,
+ * every function returns an AqhStatus (0 = ok).  One calling thread per handle.
+ * All arithmetic on the path is IEEE binary32 evaluated without fused
+ * multiply-add, exactly as the reference's x86-64 build does.
+ */
+#ifndef AQSIS_B200_HIDER_H_INCLUDED
+#define AQSIS_B200_HIDER_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#  define AQH_EXPORT __attribute__((visibility("default")))
+#else
+#  define AQH_EXPORT
+#endif
+
+#define AQH_ABI_VERSION 1
+
+typedef enum AqhStatus
+{
+	AQH_OK = 0,
+	AQH_ERR_BAD_PARAMS = 1,     /* like PkDspyErrorBadParams */
+	AQH_ERR_NO_MEMORY = 2,      /* host or device allocation failed */
+	AQH_ERR_UNSUPPORTED = 3,    /* feature outside the implemented path (CSG, trim curves, ...) */
+	AQH_ERR_NO_DEVICE = 4,      /* no CUDA device / kernel image: there is NO cpu fallback */
+	AQH_ERR_CUDA = 5,           /* a CUDA call failed; see aqh_last_error */
+	AQH_ERR_STATE = 6,          /* call out of order (add_grid outside begin/end, ...) */
+	AQH_ERR_DEEP_OVERFLOW = 7,  /* transparent hit pool exhausted; raise deep_hits_per_sample */
+	AQH_ERR_CALLBACK = 8        /* a display callback returned non-zero */
+} AqhStatus;
+
+/* --- enums mirrored from the reference ---------------------------------- */
+
+/* EqDepthFilter, libs/core/optioncache.h:34-40 */
+enum { AQH_DEPTHFILTER_MIN = 0, AQH_DEPTHFILTER_MIDPOINT = 1, AQH_DEPTHFILTER_MAX = 2, AQH_DEPTHFILTER_AVERAGE = 3 };
+/* EqDisplayMode, include/aqsis/core/ioptions.h:50-56 */
+enum { AQH_DMODE_RGB = 1, AQH_DMODE_A = 2, AQH_DMODE_Z = 4 };
+/* PkDspy* data types, include/aqsis/ri/ndspy.h:70-76 */
+enum { AQH_FLOAT32 = 1, AQH_UNSIGNED32 = 2, AQH_SIGNED32 = 3, AQH_UNSIGNED16 = 4, AQH_SIGNED16 = 5,
+       AQH_UNSIGNED8 = 6, AQH_SIGNED8 = 7 };
+/* Slots of the per-pixel float channel buffer handed to DisplayBucket
+ * (addChannel order in CqBucketProcessor::FilterBucket, bucketprocessor.cpp:389-393). */
+enum { AQH_CH_CI_R = 0, AQH_CH_CI_G = 1, AQH_CH_CI_B = 2, AQH_CH_OI_R = 3, AQH_CH_OI_G = 4, AQH_CH_OI_B = 5,
+       AQH_CH_ALPHA = 6, AQH_CH_Z = 7, AQH_CH_COVERAGE = 8, AQH_NUM_CHANNELS = 9 };
+
+/* Grid flags (SqGridInfo, libs/core/micropolygon.h:57-63; fTriangular, usesCSG). */
+enum {
+	AQH_GRID_SMOOTH       = 1u << 0,  /* useSmoothShading: bilinear Ci/Oi, else corner 0 */
+	AQH_GRID_MATTE        = 1u << 1,  /* SqImageSample::Flag_Matte */
+	AQH_GRID_MATTE_ALPHA  = 1u << 2,  /* SqImageSample::Flag_MatteAlpha */
+	AQH_GRID_TRIANGULAR   = 1u << 3,  /* fTriangular(): reject hits beyond the split line */
+	AQH_GRID_CAMERA_SPACE = 1u << 4,  /* P is camera space: project with cam_to_raster keeping camera z
+	                                     (micropolygon.cpp:723-731); else P is already raster x,y + camera z */
+	AQH_GRID_USES_CSG     = 1u << 5   /* rejected with AQH_ERR_UNSUPPORTED */
+};
+
+enum { AQH_MAX_DISPLAYS = 8, AQH_MAX_DISPLAY_CHANNELS = 16 };
+
+/* RtFilterFunc (include/aqsis/ri/ritypes.h:56): only ever tabulated on the host
+ * (bucketprocessor.cpp:850), so a user filter works unchanged. */
+typedef float (*AqhFilterFunc)(float x, float y, float xwidth, float ywidth);
+
+/* One display request: channel selection + quantisation
+ * (CqDisplayRequest m_formats/m_bufferMap + m_Quantize*, ddmanager.cpp:455-480,1046-1113). */
+typedef struct AqhDisplayDesc
+{
+	int32_t n_channels;                          /* entries of channel[] used */
+	int32_t channel[AQH_MAX_DISPLAY_CHANNELS];   /* AQH_CH_* slot per output element, in driver order */
+	int32_t type;                                /* AQH_FLOAT32...; 0 = select from (one,min,max) like selectDataFormat */
+	float quantize_zero, quantize_one, quantize_min, quantize_max, quantize_dither;
+} AqhDisplayDesc;
+
+typedef struct AqhFrameParams
+{
+	int32_t abi_version;            /* AQH_ABI_VERSION */
+	int32_t xres, yres;             /* System:Resolution */
+	int32_t crop_xmin, crop_xmax, crop_ymin, crop_ymax; /* integer crop window, renderer.cpp:1619-1627 */
+	int32_t xsamples, ysamples;     /* PixelSamples */
+	float   filter_xwidth, filter_ywidth;
+	AqhFilterFunc filter_func;      /* NULL = gaussian */
+	int32_t bucket_xsize, bucket_ysize; /* limits:bucketsize, default 16 16; fixes RNG replay + callback order */
+	float   clip_near, clip_far;
+	float   shutter_open, shutter_close;
+	int32_t use_dof;                /* CqRenderer::UsingDepthOfField() */
+	float   dof_multiplier;         /* m_DofMultiplier         renderer.h:368-377 */
+	float   dof_one_over_focal_distance;
+	float   dof_scale_x, dof_scale_y; /* m_DepthOfFieldScale   options.cpp:162-171 */
+	int32_t depth_filter;           /* AQH_DEPTHFILTER_* (only MIN implemented) */
+	float   zthreshold[3];          /* limits:zthreshold, default 1 1 1 */
+	int32_t display_mode;           /* AQH_DMODE_* union over displays */
+	float   exposure_gain, exposure_gamma;
+	int32_t jitter;                 /* Hider "jitter": 1 = CqMultiJitteredSampler, 0 = CqGridSampler */
+	float   cam_to_raster[16];      /* row-major m[i][j] of CqMatrix, used with AQH_GRID_CAMERA_SPACE */
+	uint32_t rng_seed;              /* seed of the global CqRandom at WorldBegin: 545 (ri.cpp:660) */
+	uint32_t rng_predraws;          /* front-end draws made between the reseed and RenderImage() */
+	int32_t n_displays;
+	AqhDisplayDesc display[AQH_MAX_DISPLAYS];
+	/* --- device-side knobs (no reference analogue) --- */
+	int32_t rank, world_size;       /* image strips are dealt round-robin to ranks; 0,1 = whole image */
+	int32_t strip_rows;             /* strip height in pixel rows (multiple of the tile height); 0 = default */
+	int32_t deep_hits_per_sample;   /* average capacity of the transparent hit pool; 0 = default */
+	int32_t reserved[8];
+} AqhFrameParams;
+
+/* One shaded grid as CqMicroPolyGrid::Split sees it (micropolygon.cpp:641-892, motion :946-1156).
+ * Arrays are AoS xyz / rgb floats exactly like IqShaderData::GetPointPtr / GetColorPtr
+ * (include/aqsis/shadervm/ishaderdata.h:72-95); they are copied, the caller keeps ownership. */
+typedef struct AqhGridDesc
+{
+	int32_t cu, cv;                 /* uGridRes(), vGridRes(): (cu+1)*(cv+1) vertices, cu*cv micropolygons */
+	int32_t nkeys;                  /* 1 = static; >1 = CqMotionMicroPolyGrid key grids */
+	const float* key_times;         /* nkeys shutter times (ignored when nkeys == 1) */
+	const float* const* P;          /* nkeys pointers to (cu+1)*(cv+1)*3 floats */
+	const float* Ci;                /* (cu+1)*(cv+1)*3 floats, NULL = white (micropolygon.cpp:1472-1475) */
+	const float* Oi;                /* idem, NULL = opaque */
+	const uint8_t* culled;          /* (cu+1)*(cv+1) bytes, non-zero = m_CulledPolys.Value(iIndex); NULL = none */
+	uint32_t flags;                 /* AQH_GRID_* */
+	float lod_bounds[2];            /* SqGridInfo::lodBounds; lod_bounds[0] < 0 = no level of detail */
+} AqhGridDesc;
+
+/* Many grids, concatenated.  memory_space 0 = host pointers, 1 = device pointers
+ * (grids already resident in HBM: nothing is staged through the host). */
+typedef struct AqhGridBlock
+{
+	int64_t n_grids;
+	const int32_t* cu;              /* n_grids */
+	const int32_t* cv;              /* n_grids */
+	const int32_t* nkeys;           /* n_grids, NULL = all 1 */
+	const uint32_t* flags;          /* n_grids */
+	const float* lod_bounds;        /* 2*n_grids, NULL = none */
+	const float* key_times;         /* sum(nkeys) floats, grid-major; NULL when all static */
+	const float* P;                 /* sum(nkeys*nverts)*3 floats: per grid, key-major, AoS xyz */
+	const float* Ci;                /* sum(nverts)*3 floats, NULL = white */
+	const float* Oi;                /* sum(nverts)*3 floats, NULL = opaque */
+	const uint8_t* culled;          /* sum(nverts) bytes, NULL = none */
+	int32_t memory_space;           /* applies to P, Ci, Oi, culled; the per-grid tables are always host */
+	int32_t reserved[3];
+} AqhGridBlock;
+
+/* IqDDManager::DisplayBucket stand-in: region [xmin,xmax1) x [ymin,ymax1) of the bucket and its
+ * float channel buffer, AQH_NUM_CHANNELS interleaved floats per pixel, row stride in floats. */
+typedef int (*AqhBucketFunc)(void* user, int xmin, int xmax1, int ymin, int ymax1,
+                             const float* channels, int row_stride_floats);
+/* DspyImageDataMethod stand-in (ndspy.h:157), one call per bucket per display, reference bucket order. */
+typedef int (*AqhDataFunc)(void* user, int display, int xmin, int xmax1, int ymin, int ymax1,
+                           int entrysize, const unsigned char* data);
+typedef void (*AqhProgressFunc)(void* user, float percent_complete);
+
+typedef struct AqhCallbacks
+{
+	void* user;
+	AqhBucketFunc on_bucket;        /* may be NULL */
+	AqhDataFunc on_data;            /* may be NULL */
+	AqhProgressFunc on_progress;    /* may be NULL */
+} AqhCallbacks;
+
+/* Stage timings of the last frame in milliseconds, named after the reference's
+ * timers (libs/core/stats.h:70-110). Device stages are CUDA-event times. */
+typedef struct AqhFrameStats
+{
+	double prepare_ms;        /* host: RNG replay + tables (Prepare_bucket) */
+	double upload_ms;         /* H2D of grids + tables */
+	double project_bust_ms;   /* Project_points + Bust_grids (+ binning) */
+	double render_mpgs_ms;    /* Render_MPGs + Combine_samples */
+	double filter_ms;         /* Filter_samples (+ expose) */
+	double display_ms;        /* Display_bucket: quantise */
+	double download_ms;       /* D2H of the image(s) */
+	double device_total_ms;   /* first kernel to last kernel */
+	int64_t n_grids, n_vertices, n_micropolygons, n_bin_entries, n_samples, n_deep_hits;
+	int64_t gpu_launches;     /* kernels launched for the frame */
+	int64_t h2d_bytes, d2h_bytes;
+} AqhFrameStats;
+
+typedef struct AqhHider AqhHider;
+
+/* Create / destroy a hider bound to one CUDA device.  Fails with AQH_ERR_NO_DEVICE when
+ * there is no usable sm_100 device: the product has no CPU path. */
+AQH_EXPORT int aqh_create(AqhHider** out, int device);
+AQH_EXPORT int aqh_destroy(AqhHider* h);
+AQH_EXPORT int aqh_abi_version(void);
+AQH_EXPORT const char* aqh_last_error(const AqhHider* h);
+/* Use a caller-owned cudaStream_t (e.g. torch's current stream) for all device work. */
+AQH_EXPORT int aqh_set_stream(AqhHider* h, void* cuda_stream);
+
+AQH_EXPORT int aqh_frame_params_default(AqhFrameParams* p);   /* options.cpp:273-305 defaults */
+/* Fill the DoF members from RiDepthOfField values the way SetDepthOfFieldData does. */
+AQH_EXPORT int aqh_frame_params_set_dof(AqhFrameParams* p, float fstop, float focallength, float focaldistance,
+                                        float scale_x, float scale_y);
+/* "rgba"/"rgb"/"a"/"z"/"rgbaz" -> channel list in the core's a,r,g,b,z request order (ddmanager.cpp:455-480)
+ * or, with driver_order != 0, the r,g,b,a,z order the file/tiff driver negotiates (display.cpp:454-490). */
+AQH_EXPORT int aqh_display_from_mode(AqhDisplayDesc* d, const char* mode, int driver_order,
+                                     float one, float min, float max, float dither);
+
+AQH_EXPORT int aqh_begin_frame(AqhHider* h, const AqhFrameParams* p);
+AQH_EXPORT int aqh_add_grid(AqhHider* h, const AqhGridDesc* g);
+AQH_EXPORT int aqh_add_grid_block(AqhHider* h, const AqhGridBlock* b);
+/* Hide + filter + expose + quantise everything added since begin_frame, download, fire callbacks
+ * in reference bucket order. */
+AQH_EXPORT int aqh_end_frame(AqhHider* h, const AqhCallbacks* cb);
+/* The same device work without download or callbacks: results stay in HBM (see aqh_device_*). */
+AQH_EXPORT int aqh_render_device(AqhHider* h);
+AQH_EXPORT int aqh_frame_stats(const AqhHider* h, AqhFrameStats* out);
+
+/* Results of the last frame.  Host copies (valid after aqh_end_frame): full-resolution images,
+ * rows owned by other ranks are zero. */
+AQH_EXPORT int aqh_image_channels(const AqhHider* h, const float** data, int* width, int* height);
+AQH_EXPORT int aqh_image_display(const AqhHider* h, int display, const unsigned char** data,
+                                 int* entrysize, int* type);
+/* Device copies (valid after aqh_render_device / aqh_end_frame) for NCCL gathers by the caller. */
+AQH_EXPORT int aqh_device_channels(const AqhHider* h, void** dev_ptr, size_t* bytes);
+AQH_EXPORT int aqh_device_display(const AqhHider* h, int display, void** dev_ptr, size_t* bytes);
+/* Pixel rows [y0,y1) of strip i owned by this rank. */
+AQH_EXPORT int aqh_num_strips(const AqhHider* h, int* n);
+AQH_EXPORT int aqh_strip(const AqhHider* h, int i, int* y0, int* y1);
+
+/* Host-side pieces of the path, exported so the reference-side tests can pin them. */
+AQH_EXPORT float aqh_box_filter(float x, float y, float xw, float yw);
+AQH_EXPORT float aqh_triangle_filter(float x, float y, float xw, float yw);
+AQH_EXPORT float aqh_gaussian_filter(float x, float y, float xw, float yw);
+AQH_EXPORT float aqh_catmullrom_filter(float x, float y, float xw, float yw);
+AQH_EXPORT float aqh_sinc_filter(float x, float y, float xw, float yw);
+AQH_EXPORT float aqh_mitchell_filter(float x, float y, float xw, float yw);
+AQH_EXPORT float aqh_disk_filter(float x, float y, float xw, float yw);
+AQH_EXPORT float aqh_bessel_filter(float x, float y, float xw, float yw);
+AQH_EXPORT AqhFilterFunc aqh_filter_by_name(const char* name);
+
+/* CqRandom (libs/math/random.cpp:97-224): one MT19937 stream per handle-less state. */
+typedef struct AqhRandom AqhRandom;
+AQH_EXPORT AqhRandom* aqh_random_create(uint32_t seed);
+AQH_EXPORT void aqh_random_destroy(AqhRandom* r);
+AQH_EXPORT void aqh_random_reseed(AqhRandom* r, uint32_t seed);
+AQH_EXPORT uint32_t aqh_random_uint(AqhRandom* r);
+AQH_EXPORT float aqh_random_float(AqhRandom* r);
+AQH_EXPORT uint32_t aqh_random_int(AqhRandom* r, uint32_t range);
+
+/* Sampler tables (CqMultiJitteredSampler / CqGridSampler) built from a given RNG state:
+ * out arrays hold ncache*n entries; positions are x,y pairs.  ncache is 250 (jitter) or 1 (grid). */
+AQH_EXPORT int aqh_sampler_tables(AqhRandom* r, int xsamples, int ysamples, int jitter,
+                                  float* positions_xy, float* values_1d, int32_t* shuffled, int* ncache);
+/* The per-pixel RNG replay of a whole frame: for every pixel of the sample
+ * region [crop-shift, crop+shift) five pattern indices (shuffle, position, dof, time, lod) as
+ * uint8 planes of size sw*sh, plus one dither float per display per image pixel. */
+AQH_EXPORT int aqh_replay_frame_rng(const AqhFrameParams* p, uint8_t* pattern_planes /*5*sw*sh*/,
+                                    float* dither /*n_displays*xres*yres, may be NULL*/,
+                                    int* sx0, int* sy0, int* sw, int* sh);
+/* Filter weight table exactly as InitialiseFilterValues lays it out. */
+AQH_EXPORT int aqh_filter_table(const AqhFrameParams* p, float* table, int* n_entries);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AQSIS_B200_HIDER_H_INCLUDED */

@@ -1,0 +1,2011 @@
+// oracle_hider.cpp -- CPU ORACLE for the hide + filter path.  TEST INFRASTRUCTURE ONLY.
+//
+// A restatement, written from the reference's semantics, of the aqsis REYES hider:
+// bust/bound -> bucket binning -> stochastic sampling (static / motion blur / depth of
+// field) -> depth test + opacity compositing -> pixel filter -> exposure -> quantise.
+// Each function cites the reference file:line it follows (paths relative to the aqsis
+// tree).  The bucket loop, the per-bucket sample regions and the micropolygon order are
+// the reference's; all arithmetic is IEEE binary32 without FMA (build with
+// -ffp-contract=off, no -march) exactly like the reference's x86-64 Release build.
+//
+// Pinning: the reference has no golden data for this path, so the leaves
+// here (RNG, jitter tables, filters, inverse bilinear) are checked bit-for-bit against
+// the reference's own sources compiled in place (oracle/_ref, tests/test_oracle_leaves.py)
+// and against the KATs of libs/core/bilinear_test.cpp; the bucket-level stages above the
+// leaves (sampling loops, Combine, FilterBucket, quantise) cannot be compiled from the
+// reference here and are "parity unpinned by reference tests": they are a careful
+// restatement only.  The product never links or loads this file.
+#include "oracle_hider.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cfloat>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <thread>
+#include <vector>
+
+namespace {
+
+typedef float F;
+
+// ---------------------------------------------------------------------------------
+// include/aqsis/math/math.h:47-70
+template<typename T> inline long lfloor(T x) { return static_cast<long>(x) - (x < 0 && x != static_cast<long>(x)); }
+template<typename T> inline long lceil(T x) { return static_cast<long>(x) + (x > 0 && x != static_cast<long>(x)); }
+inline long lround_aq(double x) { return lfloor(x - 0.5) + 1; }
+inline F fmin_(F a, F b) { return (a < b) ? a : b; }   // Aqsis::min, math.h:110-114
+inline F fmax_(F a, F b) { return (a < b) ? b : a; }   // Aqsis::max, math.h:121-125
+inline F clampf(F x, F lo, F hi) { return x < lo ? lo : (x > hi ? hi : x); }
+inline F lerpf(F t, F x0, F x1) { return (1-t)*x0 + t*x1; }  // math.h:88-91
+inline bool isClose(F x1, F x2)                              // math.h:174-182
+{
+	F tol = 10*std::numeric_limits<F>::epsilon();
+	F d = std::fabs(x1-x2);
+	return d <= tol*std::fabs(x1) || d <= tol*std::fabs(x2);
+}
+
+// ---------------------------------------------------------------------------------
+// CqRandom: ONE process-global MT19937, libs/math/random.cpp:97-224.
+struct GlobalRandom
+{
+	unsigned long mt[624];
+	int mti;
+	GlobalRandom() : mti(625) {}
+	void init(unsigned long s)                       // init_genrand :102-117
+	{
+		mt[0] = s & 0xffffffffUL;
+		for(mti = 1; mti < 624; mti++)
+		{
+			mt[mti] = (1812433253UL * (mt[mti-1] ^ (mt[mti-1] >> 30)) + mti);
+			mt[mti] &= 0xffffffffUL;
+		}
+	}
+	unsigned long next()                             // genrand_int32 :120-160
+	{
+		static const unsigned long mag01[2] = {0x0UL, 0x9908b0dfUL};
+		unsigned long y;
+		if(mti >= 624)
+		{
+			int kk;
+			if(mti == 625)
+				init(5489UL);
+			for(kk = 0; kk < 624-397; kk++)
+			{
+				y = (mt[kk] & 0x80000000UL) | (mt[kk+1] & 0x7fffffffUL);
+				mt[kk] = mt[kk+397] ^ (y >> 1) ^ mag01[y & 0x1UL];
+			}
+			for(; kk < 623; kk++)
+			{
+				y = (mt[kk] & 0x80000000UL) | (mt[kk+1] & 0x7fffffffUL);
+				mt[kk] = mt[kk+(397-624)] ^ (y >> 1) ^ mag01[y & 0x1UL];
+			}
+			y = (mt[623] & 0x80000000UL) | (mt[0] & 0x7fffffffUL);
+			mt[623] = mt[396] ^ (y >> 1) ^ mag01[y & 0x1UL];
+			mti = 0;
+		}
+		y = mt[mti++];
+		y ^= (y >> 11);
+		y ^= (y << 7) & 0x9d2c5680UL;
+		y ^= (y << 15) & 0xefc60000UL;
+		y ^= (y >> 18);
+		return y & 0xffffffffUL;
+	}
+	F randomFloat() { return next()*(1.0/4294967424.0); }           // :194-206
+	F randomFloat(F range) { return range*randomFloat(); }          // :211-214
+	unsigned randomInt(unsigned range) { double n = randomFloat(range); return lfloor(n); } // :186-190
+};
+GlobalRandom g_rng;
+
+// ---------------------------------------------------------------------------------
+// IqSampler tables: CqMultiJitteredSampler (multijitter.cpp:83-222) / CqGridSampler (grid.cpp:37-63)
+struct Sampler
+{
+	int xs, ys, n, ncache;
+	bool jitter;
+	std::vector<F> pos;      // ncache*n*2
+	std::vector<F> v1d;      // ncache*n
+	std::vector<int> shuf;   // ncache*n
+};
+
+void multiJitterIndices(int* indices, int numX, int numY)         // multijitter.cpp:83-128
+{
+	for(int iy = 0; iy < numY; iy++)
+		for(int ix = 0; ix < numX; ix++)
+		{
+			int which = 2*(iy*numX + ix);
+			indices[which] = iy;
+			indices[which+1] = ix;
+		}
+	for(int iy = 0; iy < numY; iy++)
+	{
+		int ix = numX;
+		while(ix > 1)
+		{
+			int ix2 = g_rng.randomInt(ix);
+			--ix;
+			std::swap(indices[2*(iy*numX + ix) + 1], indices[2*(iy*numX + ix2) + 1]);
+		}
+	}
+	for(int ix = 0; ix < numX; ix++)
+	{
+		int iy = numY;
+		while(iy > 1)
+		{
+			int iy2 = g_rng.randomInt(iy);
+			--iy;
+			std::swap(indices[2*(iy*numX + ix)], indices[2*(iy2*numX + ix)]);
+		}
+	}
+}
+
+void setupJitterPattern(Sampler& s, int offset)                    // multijitter.cpp:130-202
+{
+	const int nSamples = s.n;
+	if(s.xs == 1 && s.ys == 1)
+	{
+		// The reference writes CqVector2D(RandomFloat(), RandomFloat()); g++ evaluates the
+		// arguments right to left, hence y first (pinned vs oracle/_ref).
+		F ry = g_rng.randomFloat();
+		F rx = g_rng.randomFloat();
+		s.pos[2*offset] = rx; s.pos[2*offset+1] = ry;
+		s.v1d[offset] = g_rng.randomFloat();
+	}
+	else
+	{
+		std::vector<int> indices(nSamples*2);
+		multiJitterIndices(&indices[0], s.xs, s.ys);
+		F subPixelHeight = 1.0f / s.ys;
+		F subPixelWidth = 1.0f / s.xs;
+		F subcellWidth = 1.0f / nSamples;
+		int which = 0;
+		for(int iy = 0; iy < s.ys; iy++)
+			for(int ix = 0; ix < s.xs; ix++)
+			{
+				int xindex = indices[2*which];
+				int yindex = indices[2*which+1];
+				F ry = g_rng.randomFloat();
+				F rx = g_rng.randomFloat();
+				s.pos[2*(offset+which)]   = (xindex+rx)*subcellWidth + ix*subPixelWidth;
+				s.pos[2*(offset+which)+1] = (yindex+ry)*subcellWidth + iy*subPixelHeight;
+				++which;
+			}
+	}
+	F sample1d = 0;
+	F delta1d = 1.0f / nSamples;
+	F random1d = g_rng.randomFloat(delta1d);
+	for(int i = 0; i < nSamples; i++)
+	{
+		F t = sample1d + random1d;
+		s.v1d[offset+i] = t;
+		sample1d += delta1d;
+	}
+	for(int i = 0; i < nSamples; ++i)
+		s.shuf[offset+i] = i;
+	int j = nSamples;
+	while(j > 1)
+	{
+		int j2 = g_rng.randomInt(j);
+		--j;
+		std::swap(s.shuf[offset+j], s.shuf[offset+j2]);
+	}
+}
+
+void buildJitterSampler(Sampler& s, int xs, int ys)               // multijitter.h:90-101
+{
+	s.xs = xs; s.ys = ys; s.n = xs*ys; s.ncache = 250; s.jitter = true;
+	s.pos.assign(size_t(250)*s.n*2, 0); s.v1d.assign(size_t(250)*s.n, 0); s.shuf.assign(size_t(250)*s.n, 0);
+	for(int i = 0; i < 250; ++i)
+		setupJitterPattern(s, i*s.n);
+	g_rng.init(19);
+}
+
+void buildGridSampler(Sampler& s, int xs, int ys)                 // grid.cpp:37-63
+{
+	s.xs = xs; s.ys = ys; s.n = xs*ys; s.ncache = 1; s.jitter = false;
+	s.pos.assign(size_t(s.n)*2, 0); s.v1d.assign(s.n, 0); s.shuf.assign(s.n, 0);
+	F xScale = 1.0/xs;
+	F yScale = 1.0/ys;
+	for(int j = 0; j < ys; j++)
+		for(int i = 0; i < xs; i++)
+		{
+			s.pos[2*(j*xs+i)] = xScale*(i+0.5);
+			s.pos[2*(j*xs+i)+1] = yScale*(j+0.5);
+		}
+	F dt = 1/s.n;            // integer division, as in the reference
+	F sample = dt*0.5;
+	for(int i = 0; i < s.n; ++i)
+	{
+		s.v1d[i] = sample;
+		sample += dt;
+	}
+	for(int i = 0; i < s.n; ++i)
+		s.shuf[i] = i;
+}
+
+// ---------------------------------------------------------------------------------
+// Pixel filters, libs/core/filters.cpp:71-348.  Math calls are the ::f(double) overloads.
+const F RI_PI_F = 3.14159265359f;
+F mitchell1(F x, F B, F C)
+{
+	x = fabsf(2.f * x);
+	if(x > 1.f)
+		return ((-B - 6*C) * x*x*x + (6*B + 30*C) * x*x + (-12*B - 48*C) * x + (8*B + 24*C)) * (1.f/6.f);
+	else
+		return ((12 - 9*B - 6*C) * x*x*x + (-18 + 12*B + 6*C) * x*x + (6 - 2*B)) * (1.f/6.f);
+}
+F filterEval(int which, F x, F y, F xwidth, F ywidth)
+{
+	switch(which)
+	{
+		case 0: // box :131-146
+		{
+			double a = (fabs((double)x) <= xwidth / 2.0 ? 1.0 : 0.0);
+			double b = (fabs((double)y) <= ywidth / 2.0 ? 1.0 : 0.0);
+			return (a < b) ? a : b;
+		}
+		case 1: // triangle :153-168
+		{
+			F hxw = xwidth / 2.0;
+			F hyw = ywidth / 2.0;
+			F absx = fabs((double)x);
+			F absy = fabs((double)y);
+			double a = (absx <= hxw ? (hxw - absx) / hxw : 0.0);
+			double b = (absy <= hyw ? (hyw - absy) / hyw : 0.0);
+			return (a < b) ? a : b;
+		}
+		case 2: // gaussian :71-113
+		{
+			x /= xwidth;
+			y /= ywidth;
+			return exp(-8.0 * (x * x + y * y));
+		}
+		case 3: // catmull-rom :175-243
+		{
+			F r2 = (x*x + y*y);
+			F r = sqrt((double)r2);
+			return (r >= 2.0) ? 0.0 : (r < 1.0) ? (3.0*r*r2 - 5.0*r2 + 2.0) : (-r*r2 + 5.0*r2 - 8.0*r + 4.0);
+		}
+		case 4: // windowed sinc :250-294
+		{
+			if(x != 0.0) { x *= RI_PI_F; x = cos(0.5 * x / xwidth) * sin((double)x) / x; } else x = 1.0;
+			if(y != 0.0) { y *= RI_PI_F; y = cos(0.5 * y / ywidth) * sin((double)y) / y; } else y = 1.0;
+			return x*y;
+		}
+		case 5: // mitchell :119-125, class :36-64
+		{
+			F B = 1/3.0f, C = 1/3.0f;
+			F invXWidth = 1.0f/xwidth, invYWidth = 1.0f/ywidth;
+			return mitchell1(x * invXWidth, B, C) * mitchell1(y * invYWidth, B, C);
+		}
+		case 6: // disk :301-319
+		{
+			double xx = x * x, yy = y * y;
+			xwidth *= 0.5; ywidth *= 0.5;
+			double d = (xx) / (xwidth * xwidth) + (yy) / (ywidth * ywidth);
+			return (d < 1.0) ? 1.0 : 0.0;
+		}
+		case 7: // bessel :326-346
+		{
+			double xx = x * x, yy = y * y;
+			xwidth *= 0.5; ywidth *= 0.5;
+			double w = (xx) / (xwidth * xwidth) + (yy) / (ywidth * ywidth);
+			if(w < 1.0)
+			{
+				double d = sqrt(xx + yy);
+				if(d != 0.0)
+				{
+					w = cos(0.5 * RI_PI_F * sqrt(w));
+					return w * 2*j1(RI_PI_F * d) / d;
+				}
+				return RI_PI_F;
+			}
+			return 0.0;
+		}
+	}
+	return 0;
+}
+// The product's filter entry points are plain function pointers; the oracle identifies the
+// standard ones by probing them at a fixed point so it can use ITS OWN restatement, and
+// otherwise (user filter) calls through the pointer, as the reference would.
+int identifyFilter(AqhFilterFunc f)
+{
+	if(!f) return 2;
+	const F px = 0.3f, py = 0.2f, pw = 3.f;
+	for(int k = 0; k < 8; ++k)
+	{
+		bool same = true;
+		const F probes[3][2] = {{0.3f,0.2f},{-0.9f,0.6f},{1.3f,-1.2f}};
+		for(int i = 0; i < 3 && same; ++i)
+			same = std::fabs(f(probes[i][0], probes[i][1], pw, pw) - filterEval(k, probes[i][0], probes[i][1], pw, pw)) <= 1e-6f;
+		if(same) return k;
+	}
+	(void)px; (void)py;
+	return -1;
+}
+
+// ---------------------------------------------------------------------------------
+// Small value types.
+struct V2 { F x, y; };
+struct V3 { F x, y, z; };
+struct Bound { V3 mn, mx; };   // CqBound, libs/core/bound.h
+inline bool contains2D(const Bound& b, V2 v)                      // bound.h:144-151 (inclusive)
+{
+	if((v.x < b.mn.x || v.x > b.mx.x) || (v.y < b.mn.y || v.y > b.mx.y)) return false;
+	return true;
+}
+inline bool intersects(const Bound& b, V2 mn, V2 mx)              // bound.h:153-160
+{
+	if(mn.x > b.mx.x || mn.y > b.mx.y || mx.x < b.mn.x || mx.y < b.mn.y) return false;
+	return true;
+}
+inline void encapsulate(Bound& a, const Bound& b)                 // bound.cpp:116-125
+{
+	a.mx.x = fmax_(a.mx.x, b.mx.x); a.mx.y = fmax_(a.mx.y, b.mx.y); a.mx.z = fmax_(a.mx.z, b.mx.z);
+	a.mn.x = fmin_(a.mn.x, b.mn.x); a.mn.y = fmin_(a.mn.y, b.mn.y); a.mn.z = fmin_(a.mn.z, b.mn.z);
+}
+inline F cross2(V2 a, V2 b) { return a.x*b.y - a.y*b.x; }        // vector2d.h:377-380
+inline F maxNorm(V2 v) { return fmax_(std::fabs(v.x), std::fabs(v.y)); }
+inline F mag2_2d(F x, F y)                                        // vector2d.h:132-138
+{
+	if(y == 0.0) return x*x;
+	else if(x == 0.0) return y*y;
+	else return x*x + y*y;
+}
+
+// CqImagePixel::projectToCircle, imagepixel.h:429-436
+V2 projectToCircle(V2 pos)
+{
+	F r = std::sqrt(mag2_2d(pos.x, pos.y));
+	if(r == 0.0) return V2{0, 0};
+	F adj = fmax_(fabs(pos.x), fabs(pos.y)) / r;
+	return V2{adj*pos.x, adj*pos.y};
+}
+
+// ---------------------------------------------------------------------------------
+// CqInvBilinear + bilerp, libs/core/bilinear.h:229-310.
+struct InvBilinear
+{
+	V2 A, E, Fv, G;
+	bool linear;
+	void setVertices(V2 a, V2 b, V2 c, V2 d)                      // :260-275
+	{
+		A = a;
+		E = V2{b.x - a.x, b.y - a.y};
+		Fv = V2{c.x - a.x, c.y - a.y};
+		G = V2{-E.x - c.x + d.x, -E.y - c.y + d.y};
+		linear = false;
+		F patchSize = fmax_(maxNorm(Fv), maxNorm(E));
+		F irregularity = maxNorm(G);
+		if(irregularity < 1e-2*patchSize)
+			linear = true;
+	}
+	V2 bilinEval(V2 uv) const                                     // :308-311
+	{
+		return V2{A.x + E.x*uv.x + Fv.x*uv.y + G.x*uv.x*uv.y, A.y + E.y*uv.x + Fv.y*uv.y + G.y*uv.x*uv.y};
+	}
+	template<bool unsafeInvert> static V2 solve(V2 M1, V2 M2, V2 b) // :298-305
+	{
+		F det = cross2(M1, M2);
+		if(unsafeInvert || det != 0) det = 1/det;
+		return V2{det * cross2(b, M2), det * (-cross2(b, M1))};
+	}
+	V2 operator()(V2 P) const                                     // :277-291
+	{
+		V2 uv{0.5, 0.5};
+		V2 e = bilinEval(uv);
+		V2 s = solve<true>(V2{E.x + G.x*uv.y, E.y + G.y*uv.y}, V2{Fv.x + G.x*uv.x, Fv.y + G.y*uv.x}, V2{e.x - P.x, e.y - P.y});
+		uv.x -= s.x; uv.y -= s.y;
+		if(!linear)
+		{
+			e = bilinEval(uv);
+			s = solve<false>(V2{E.x + G.x*uv.y, E.y + G.y*uv.y}, V2{Fv.x + G.x*uv.x, Fv.y + G.y*uv.x}, V2{e.x - P.x, e.y - P.y});
+			uv.x -= s.x; uv.y -= s.y;
+		}
+		return uv;
+	}
+};
+inline F bilerp(F A, F B, F C, F D, V2 uv)                        // :229-236
+{
+	F w0 = (1-uv.y)*(1-uv.x);
+	F w1 = (1-uv.y)*uv.x;
+	F w2 = uv.y*(1-uv.x);
+	F w3 = uv.y*uv.x;
+	return w0*A + w1*B + w2*C + w3*D;
+}
+
+// ---------------------------------------------------------------------------------
+// Frame context: SqOptionCache + the bits of CqRenderer the path reads.
+struct Frame
+{
+	AqhFrameParams p;
+	int xs, ys, n;
+	int shiftX, shiftY;                  // m_DiscreteShiftX/Y, bucketprocessor.cpp:36-37
+	int sx0, sy0, sw, sh;                // global sample region [crop-shift, crop+shift)
+	int bx0, by0, bx1, by1;              // m_bucketRegion, imagebuffer.cpp:191-195
+	Sampler sampler;
+	std::vector<F> filterValues;         // m_aFilterValues
+	std::vector<Bound> dofBounds;        // m_DofBounds
+	int filterKind;
+	// GetCircleOfConfusion, renderer.h:401-406
+	V2 coc(F depth) const
+	{
+		F c = p.dof_multiplier * fabs(1.0f / depth - p.dof_one_over_focal_distance);
+		return V2{p.dof_scale_x * c, p.dof_scale_y * c};
+	}
+	// MinCoCForBound, renderer.cpp:1602-1617
+	F minCoCForBound(const Bound& b) const
+	{
+		F z1 = b.mn.z, z2 = b.mx.z;
+		F focalDist = 1/p.dof_one_over_focal_distance;
+		if((z1 - focalDist)*(z2 - focalDist) < 0)
+			return 0;
+		F minBlur = fmin_(std::fabs(1/z1 - p.dof_one_over_focal_distance), std::fabs(1/z2 - p.dof_one_over_focal_distance));
+		return p.dof_multiplier * fmin_(p.dof_scale_x, p.dof_scale_y) * minBlur;
+	}
+};
+
+void setupLayout(Frame& f)
+{
+	const AqhFrameParams& p = f.p;
+	f.xs = p.xsamples; f.ys = p.ysamples; f.n = f.xs*f.ys;
+	f.shiftX = lfloor(p.filter_xwidth/2.0f);
+	f.shiftY = lfloor(p.filter_ywidth/2.0f);
+	f.sx0 = p.crop_xmin - f.shiftX; f.sy0 = p.crop_ymin - f.shiftY;
+	f.sw = p.crop_xmax + f.shiftX - f.sx0; f.sh = p.crop_ymax + f.shiftY - f.sy0;
+	f.bx0 = p.crop_xmin/p.bucket_xsize; f.by0 = p.crop_ymin/p.bucket_ysize;
+	f.bx1 = (p.crop_xmax-1)/p.bucket_xsize + 1; f.by1 = (p.crop_ymax-1)/p.bucket_ysize + 1;
+}
+
+// CqBucketProcessor::InitialiseFilterValues, bucketprocessor.cpp:811-856
+void initialiseFilterValues(Frame& f)
+{
+	const AqhFrameParams& p = f.p;
+	int numSubPixels = f.n;
+	int xmax = f.shiftX, ymax = f.shiftY;
+	f.filterValues.assign(size_t(2*xmax+1)*(2*ymax+1)*numSubPixels, 0.f);
+	F xfwo2 = std::ceil(p.filter_xwidth) * 0.5f;
+	F yfwo2 = std::ceil(p.filter_ywidth) * 0.5f;
+	f.filterKind = identifyFilter(p.filter_func);
+	for(int py = -ymax; py <= ymax; py++)
+		for(int px = -xmax; px <= xmax; px++)
+		{
+			int subPixelIndex = ((py + ymax)*(2*xmax+1) + px + xmax)*numSubPixels;
+			for(int sy = 0; sy < f.ys; sy++)
+				for(int sx = 0; sx < f.xs; sx++, ++subPixelIndex)
+				{
+					F fx = (sx + 0.5f) / f.xs + px - 0.5f;
+					F fy = (sy + 0.5f) / f.ys + py - 0.5f;
+					F w = 0;
+					if(fx >= -xfwo2 && fy >= -yfwo2 && fx <= xfwo2 && fy <= yfwo2)
+					{
+						if(f.filterKind >= 0)
+							w = filterEval(f.filterKind, fx, fy, std::ceil(p.filter_xwidth), std::ceil(p.filter_ywidth));
+						else
+							w = p.filter_func(fx, fy, std::ceil(p.filter_xwidth), std::ceil(p.filter_ywidth));
+					}
+					f.filterValues[subPixelIndex] = w;
+				}
+		}
+}
+
+// CqBucketProcessor::CalculateDofBounds, bucketprocessor.cpp:858-913
+void calculateDofBounds(int xs, int ys, std::vector<Bound>& out)
+{
+	out.resize(size_t(xs)*ys);
+	F dx = 2.0 / xs;
+	F dy = 2.0 / ys;
+	F minX = -1.0, minY = -1.0;
+	int which = 0;
+	for(int j = 0; j < ys; ++j)
+	{
+		for(int i = 0; i < xs; ++i)
+		{
+			V2 topLeft = projectToCircle(V2{minX, minY});
+			V2 topRight = projectToCircle(V2{minX + dx, minY});
+			V2 bottomLeft = projectToCircle(V2{minX, minY + dy});
+			V2 bottomRight = projectToCircle(V2{minX + dx, minY + dy});
+			if((topLeft.y > 0.0 && bottomLeft.y < 0.0) || (topLeft.y < 0.0 && bottomLeft.y > 0.0))
+			{
+				topLeft.x = minX; bottomLeft.x = minX; topRight.x = minX + dx; bottomRight.x = minX + dx;
+			}
+			if((topLeft.x > 0.0 && topRight.x < 0.0) || (topLeft.x < 0.0 && topRight.x > 0.0))
+			{
+				topLeft.y = minY; bottomLeft.y = minY + dy; topRight.y = minY; bottomRight.y = minY + dy;
+			}
+			Bound b;
+			b.mn = V3{topLeft.x, topLeft.y, 0}; b.mx = b.mn;
+			const V2 pts[3] = {topRight, bottomLeft, bottomRight};
+			for(int k = 0; k < 3; ++k)   // CqBound::Encapsulate(CqVector2D), bound.cpp:150-157
+			{
+				b.mx.x = fmax_(b.mx.x, pts[k].x); b.mx.y = fmax_(b.mx.y, pts[k].y);
+				b.mn.x = fmin_(b.mn.x, pts[k].x); b.mn.y = fmin_(b.mn.y, pts[k].y);
+			}
+			out[which++] = b;
+			minX += dx;
+		}
+		minX = -1.0;
+		minY += dy;
+	}
+}
+
+// ---------------------------------------------------------------------------------
+// Image-wide sample store.  The reference keeps (bucket + overlap) pixels and hands the
+// overlap to neighbours through cache segments (bucketprocessor.cpp:259-358, 1645-1694);
+// each pixel is still set up, sampled and combined exactly once, by the first bucket whose
+// sample region contains it.  Keeping the pixels in one image-wide array indexed over
+// [crop-shift, crop+shift) is the same thing without the pointer shuffling.
+enum { Flag_Matte = 1, Flag_MatteAlpha = 2, Flag_Valid = 4 };     // imagepixel.h:94-99
+struct Hit { F d[7]; int flags; };    // R G B Or Og Ob Depth (slots 7,8 are never written by StoreSample)
+struct SampleData                     // SqSampleData, imagepixel.h:122-151
+{
+	V2 position, dofOffset;
+	F time, detailLevel, occlZ;
+	Hit occludingHit;
+	std::vector<Hit> data;
+};
+struct Image
+{
+	std::vector<SampleData> samples;   // sw*sh*n
+	std::vector<int> dofOffsetIndices; // sw*sh*n
+};
+
+// CqImagePixel::clear + setSamples, imagepixel.cpp:105-122, 334-359
+void setSamples(const Frame& f, Image& img, int x, int y)
+{
+	const int n = f.n;
+	const Sampler& s = f.sampler;
+	size_t base = (size_t(y - f.sy0)*f.sw + (x - f.sx0))*n;
+	int iShuf = 0, iPos = 0, iDof = 0, iTime = 0, iLod = 0;
+	if(s.jitter)
+	{
+		iShuf = g_rng.randomInt(250);    // getShuffledIndices, multijitter.cpp:217-221
+		iPos = g_rng.randomInt(250);     // get2DSamples (positions)
+		iDof = g_rng.randomInt(250);     // get2DSamples (dofOffsets)
+		iTime = g_rng.randomInt(250);    // get1DSamples (times)
+		iLod = g_rng.randomInt(250);     // get1DSamples (lods)
+	}
+	const int* shuffledIndices = &s.shuf[size_t(iShuf)*n];
+	const F* positions = &s.pos[size_t(iPos)*n*2];
+	const F* dofOffsets = &s.pos[size_t(iDof)*n*2];
+	const F* times = &s.v1d[size_t(iTime)*n];
+	const F* lods = &s.v1d[size_t(iLod)*n];
+	F opentime = f.p.shutter_open, closetime = f.p.shutter_close;
+	V2 offset{F(x), F(y)};
+	for(int i = 0; i < n; ++i)
+	{
+		SampleData& sd = img.samples[base+i];
+		sd.occludingHit.flags = 0;
+		sd.occlZ = FLT_MAX;
+		sd.data.clear();
+		img.dofOffsetIndices[base+i] = shuffledIndices[i];
+	}
+	for(int i = 0; i < n; ++i)
+	{
+		SampleData& sd = img.samples[base+i];
+		sd.position = V2{offset.x + positions[2*i], offset.y + positions[2*i+1]};
+		sd.time = (closetime - opentime) * times[i] + opentime;
+		sd.detailLevel = lods[i];
+		img.samples[base + img.dofOffsetIndices[base+i]].dofOffset =
+			projectToCircle(V2{-1 + 2*dofOffsets[2*i], -1 + 2*dofOffsets[2*i+1]});
+	}
+}
+
+// ---------------------------------------------------------------------------------
+// Grids as CqMicroPolyGrid::Split leaves them: P in raster x,y + camera z, per key.
+struct GridView
+{
+	int cu, cv, nkeys, nverts;
+	unsigned flags;
+	const F* times;                    // nkeys (null when static)
+	std::vector<const F*> P;           // per key, AoS xyz (points into `projected` or the caller's data)
+	const F* Ci; const F* Oi; const uint8_t* culled;
+	F lod[2];
+	std::vector<V3> split1, split2;    // SqTriangleSplitLine per key
+};
+
+struct Scene
+{
+	std::vector<GridView> grids;
+	std::vector<F> projected;          // storage for camera-space grids after projection
+};
+
+// CqMatrix::operator*(CqVector3D), include/aqsis/math/matrix.h:717-750, then keep camera z
+// (micropolygon.cpp:723-731).
+inline V3 projectPoint(const F* m, V3 v)
+{
+	F h = (m[0*4+3]*v.x + m[1*4+3]*v.y + m[2*4+3]*v.z + m[3*4+3]);
+	V3 r;
+	r.x = (m[0*4+0]*v.x + m[1*4+0]*v.y + m[2*4+0]*v.z + m[3*4+0]);
+	r.y = (m[0*4+1]*v.x + m[1*4+1]*v.y + m[2*4+1]*v.z + m[3*4+1]);
+	r.z = (m[0*4+2]*v.x + m[1*4+2]*v.y + m[2*4+2]*v.z + m[3*4+2]);
+	if(h != 1)
+	{
+		F invh = 1/h;
+		r.x = r.x*invh; r.y = r.y*invh; r.z = r.z*invh;
+	}
+	r.z = v.z;
+	return r;
+}
+
+void buildScene(const Frame& f, const AqhGridBlock& b, Scene& sc)
+{
+	sc.grids.resize(b.n_grids);
+	size_t totalPos = 0, camPos = 0;
+	for(int64_t g = 0; g < b.n_grids; ++g)
+	{
+		int nk = b.nkeys ? b.nkeys[g] : 1;
+		size_t nv = size_t(b.cu[g]+1)*(b.cv[g]+1);
+		totalPos += nv*nk;
+		if(b.flags[g] & AQH_GRID_CAMERA_SPACE) camPos += nv*nk;
+	}
+	sc.projected.resize(camPos*3);
+	size_t pOff = 0, vOff = 0, kOff = 0, prOff = 0;
+	for(int64_t g = 0; g < b.n_grids; ++g)
+	{
+		GridView& gv = sc.grids[g];
+		gv.cu = b.cu[g]; gv.cv = b.cv[g];
+		gv.nkeys = b.nkeys ? b.nkeys[g] : 1;
+		gv.nverts = (gv.cu+1)*(gv.cv+1);
+		gv.flags = b.flags[g];
+		gv.times = (b.key_times && gv.nkeys > 1) ? b.key_times + kOff : 0;
+		gv.Ci = b.Ci ? b.Ci + vOff*3 : 0;
+		gv.Oi = b.Oi ? b.Oi + vOff*3 : 0;
+		gv.culled = b.culled ? b.culled + vOff : 0;
+		gv.lod[0] = b.lod_bounds ? b.lod_bounds[2*g] : -1.f;
+		gv.lod[1] = b.lod_bounds ? b.lod_bounds[2*g+1] : -1.f;
+		gv.P.resize(gv.nkeys);
+		gv.split1.resize(gv.nkeys); gv.split2.resize(gv.nkeys);
+		for(int k = 0; k < gv.nkeys; ++k)
+		{
+			const F* src = b.P + (pOff + size_t(k)*gv.nverts)*3;
+			if(gv.flags & AQH_GRID_CAMERA_SPACE)
+			{
+				F* dst = &sc.projected[prOff*3];
+				for(int i = gv.nverts-1; i >= 0; i--)
+				{
+					V3 r = projectPoint(f.p.cam_to_raster, V3{src[3*i], src[3*i+1], src[3*i+2]});
+					dst[3*i] = r.x; dst[3*i+1] = r.y; dst[3*i+2] = r.z;
+				}
+				gv.P[k] = dst;
+				prOff += gv.nverts;
+			}
+			else
+				gv.P[k] = src;
+			// triangle split line, micropolygon.cpp:733-749 (per key :1035-1051)
+			const F* P = gv.P[k];
+			V3 v0{P[0], P[1], P[2]};
+			int i1 = gv.cu, i2 = gv.cv*(gv.cu+1);
+			V3 v1{P[3*i1], P[3*i1+1], P[3*i1+2]};
+			V3 v2{P[3*i2], P[3*i2+1], P[3*i2+2]};
+			if(((v1.x - v0.x)*(v2.y - v0.y) - (v1.y - v0.y)*(v2.x - v0.x)) >= 0)
+			{ gv.split1[k] = v1; gv.split2[k] = v2; }
+			else
+			{ gv.split1[k] = v2; gv.split2[k] = v1; }
+		}
+		pOff += size_t(gv.nverts)*gv.nkeys;
+		vOff += gv.nverts;
+		kOff += gv.nkeys;
+	}
+	(void)totalPos;
+}
+
+// ---------------------------------------------------------------------------------
+// One micropolygon, rebuilt on demand from (grid, index): CqMicroPolygon / CqMicroPolygonMotion.
+struct MPRef { int grid; int index; };
+
+const unsigned Degeneracy_Mask = 0x8000000;                       // micropolygon.h:791
+
+struct MicroPoly
+{
+	const GridView* g;
+	int index;
+	int indexCode;
+	Bound bound;                       // m_Bound (union over keys when moving)
+	bool moving;
+	// moving only
+	std::vector<V3> keyPts;            // nkeys*4: m_Point0..3 = verts index, +1, +cu+1, +cu+2
+	std::vector<Bound> keyBounds;
+	std::vector<Bound> boundList;      // CqBoundList
+	std::vector<F> boundTimes;
+};
+
+inline V3 vert(const F* P, int i) { return V3{P[3*i], P[3*i+1], P[3*i+2]}; }
+inline F mag2(V3 a, V3 b)
+{
+	F dx = a.x-b.x, dy = a.y-b.y, dz = a.z-b.z;
+	return dx*dx + dy*dy + dz*dz;                                   // vector3d.h:345-348
+}
+
+// CqMicroPolygon::ComputeVertexOrder, micropolygon.cpp:1207-1284
+int computeVertexOrder(const F* pP, int index, int cu)
+{
+	int IndexA = index, IndexB = index + 1, IndexC = index + cu + 2, IndexD = index + cu + 1;
+	short CodeA = 0, CodeB = 1, CodeC = 3, CodeD = 2;
+	if(mag2(vert(pP, IndexA), vert(pP, IndexB)) < 1e-8)
+	{
+		IndexB = IndexC; CodeB = CodeC; IndexC = IndexD; CodeC = CodeD; IndexD = -1; CodeD = -1;
+	}
+	else if(mag2(vert(pP, IndexB), vert(pP, IndexC)) < 1e-8)
+	{
+		IndexB = IndexC; CodeB = CodeC; IndexC = IndexD; CodeC = CodeD; IndexD = -1; CodeD = -1;
+	}
+	else if(mag2(vert(pP, IndexC), vert(pP, IndexD)) < 1e-8)
+	{
+		IndexC = IndexD; CodeC = CodeD; IndexD = -1; CodeD = -1;
+	}
+	else if(mag2(vert(pP, IndexD), vert(pP, IndexA)) < 1e-8)
+	{
+		IndexD = IndexC; CodeD = CodeC; IndexD = -1; CodeD = -1;
+	}
+	V3 vA2 = vert(pP, IndexA), vB2 = vert(pP, IndexB), vC2 = vert(pP, IndexC);
+	bool fFlip = ((vA2.x - vB2.x)*(vB2.y - vC2.y)) >= ((vA2.y - vB2.y)*(vB2.x - vC2.x));
+	int code;
+	if(!fFlip)
+		code = (CodeD == -1) ?
+			((CodeA & 0x3) | ((CodeC & 0x3) << 2) | ((CodeB & 0x3) << 4) | Degeneracy_Mask) :
+			((CodeA & 0x3) | ((CodeD & 0x3) << 2) | ((CodeC & 0x3) << 4) | ((CodeB & 0x3) << 6));
+	else
+		code = (CodeD == -1) ?
+			((CodeA & 0x3) | ((CodeB & 0x3) << 2) | ((CodeC & 0x3) << 4) | Degeneracy_Mask) :
+			((CodeA & 0x3) | ((CodeB & 0x3) << 2) | ((CodeC & 0x3) << 4) | ((CodeD & 0x3) << 6));
+	return code;
+}
+
+Bound boundOf4(V3 a, V3 b, V3 c, V3 d)
+{
+	// CqMovingMicroPolygonKey::GetBound, micropolygon.cpp:1974-1989.  The static
+	// CalculateBound (:1663-1673) nests the min/max differently; min and max are
+	// associative on non-NaN floats so one routine serves both.
+	Bound r;
+	r.mn.x = fmin_(a.x, fmin_(b.x, fmin_(c.x, d.x))); r.mn.y = fmin_(a.y, fmin_(b.y, fmin_(c.y, d.y)));
+	r.mn.z = fmin_(a.z, fmin_(b.z, fmin_(c.z, d.z)));
+	r.mx.x = fmax_(a.x, fmax_(b.x, fmax_(c.x, d.x))); r.mx.y = fmax_(a.y, fmax_(b.y, fmax_(c.y, d.y)));
+	r.mx.z = fmax_(a.z, fmax_(b.z, fmax_(c.z, d.z)));
+	return r;
+}
+
+void makeMicroPoly(const GridView& g, int index, MicroPoly& mp)
+{
+	mp.g = &g; mp.index = index;
+	const int cu = g.cu;
+	mp.indexCode = computeVertexOrder(g.P[0], index, cu);
+	mp.moving = g.nkeys > 1;
+	if(!mp.moving)
+	{
+		const F* P = g.P[0];
+		mp.bound = boundOf4(vert(P, index), vert(P, index+1), vert(P, index+cu+2), vert(P, index+cu+1));
+		return;
+	}
+	// AppendKey per key, micropolygon.cpp:1952-1967
+	mp.keyPts.resize(size_t(g.nkeys)*4);
+	mp.keyBounds.resize(g.nkeys);
+	for(int k = 0; k < g.nkeys; ++k)
+	{
+		const F* P = g.P[k];
+		V3* q = &mp.keyPts[size_t(k)*4];
+		q[0] = vert(P, index); q[1] = vert(P, index+1); q[2] = vert(P, index+cu+1); q[3] = vert(P, index+cu+2);
+		mp.keyBounds[k] = boundOf4(q[0], q[1], q[2], q[3]);
+		if(k == 0) mp.bound = mp.keyBounds[0];
+		else encapsulate(mp.bound, mp.keyBounds[k]);
+	}
+	mp.boundList.clear();
+}
+
+// CqMicroPolygonMotion::BuildBoundList, micropolygon.cpp:1689-1756
+void buildBoundList(const Frame& f, MicroPoly& mp, unsigned timeRanges)
+{
+	const GridView& g = *mp.g;
+	F opentime = f.p.shutter_open, closetime = f.p.shutter_close;
+	const Bound& kb0 = mp.keyBounds.front();
+	F polyLen2 = mag2_2d(kb0.mx.x - kb0.mn.x, kb0.mx.y - kb0.mn.y);
+	const V3& p0 = mp.keyPts[0];
+	const V3& pl = mp.keyPts[size_t(g.nkeys-1)*4];
+	F moveDist2 = mag2_2d(p0.x - pl.x, p0.y - pl.y);
+	int polyLengthsMoved = std::max<int>(1, lfloor(std::sqrt(moveDist2/polyLen2)));
+	unsigned divisions = std::min<int>(polyLengthsMoved, timeRanges);
+	F dt = (closetime - opentime) / divisions;
+	F time = opentime + dt;
+	int startKey = 0;
+	unsigned endKey = 1;
+	Bound bound = mp.keyBounds[startKey];
+	mp.boundList.resize(divisions);
+	mp.boundTimes.resize(divisions);
+	for(unsigned i = 0; i < divisions; i++)
+	{
+		while(time > g.times[endKey] && endKey < unsigned(g.nkeys) - 1)
+			++endKey;
+		int endKey_1 = endKey - 1;
+		const Bound& end0 = mp.keyBounds[endKey_1];
+		F end0Time = g.times[endKey_1];
+		const Bound& end1 = mp.keyBounds[endKey];
+		F end1Time = g.times[endKey];
+		F mix = (time - end0Time) / (end1Time - end0Time);
+		Bound mid(end0);
+		mid.mn.x += mix * (end1.mn.x - end0.mn.x); mid.mn.y += mix * (end1.mn.y - end0.mn.y); mid.mn.z += mix * (end1.mn.z - end0.mn.z);
+		mid.mx.x += mix * (end1.mx.x - end0.mx.x); mid.mx.y += mix * (end1.mx.y - end0.mx.y); mid.mx.z += mix * (end1.mx.z - end0.mx.z);
+		encapsulate(bound, mid);
+		while(startKey < endKey_1)
+		{
+			startKey++;
+			encapsulate(bound, mp.keyBounds[startKey]);
+		}
+		mp.boundList[i] = bound;
+		mp.boundTimes[i] = time - dt;
+		bound = mid;
+		time += dt;
+	}
+}
+
+// CqHitTestCache, micropolygon.h:520-551
+struct HitTestCache
+{
+	V3 P[4];
+	F z[4];
+	F YM[4], XM[4], X[4], Y[4];
+	int lastFailedEdge;
+	V2 cocMult[4], cocMultMin, cocMultMax;
+	InvBilinear xyToUV;
+};
+
+// CqMicroPolygon::cachePointInPolyTest, micropolygon.cpp:1346-1392
+void cachePointInPolyTest(const MicroPoly& mp, HitTestCache& c, const V3* pointsIn)
+{
+	c.z[0] = pointsIn[0].z; c.z[1] = pointsIn[1].z; c.z[2] = pointsIn[2].z; c.z[3] = pointsIn[3].z;
+	c.xyToUV.setVertices(V2{pointsIn[0].x, pointsIn[0].y}, V2{pointsIn[1].x, pointsIn[1].y},
+	                     V2{pointsIn[2].x, pointsIn[2].y}, V2{pointsIn[3].x, pointsIn[3].y});
+	const int code = mp.indexCode;
+	const V3 points[4] = { pointsIn[(code >> 2) & 0x3], pointsIn[(code >> 4) & 0x3],
+	                       pointsIn[(code >> 6) & 0x3], pointsIn[(code) & 0x3] };
+	int j = 3;
+	for(int i = 0; i < 4; ++i)
+	{
+		c.YM[i] = points[i].x - points[j].x;
+		c.XM[i] = points[i].y - points[j].y;
+		c.X[i] = points[j].x;
+		c.Y[i] = points[j].y;
+		j = i;
+	}
+	if(code & Degeneracy_Mask)
+	{
+		for(int i = 2; i < 4; ++i)
+		{
+			c.YM[i] = points[3].x - points[1].x;
+			c.XM[i] = points[3].y - points[1].y;
+			c.X[i] = points[1].x;
+			c.Y[i] = points[1].y;
+		}
+	}
+	c.lastFailedEdge = 0;
+}
+
+// CqMicroPolygon::fContains, micropolygon.cpp:1295-1342
+bool fContains(HitTestCache& c, V2 vecP, F& Depth, V2& uv)
+{
+	F x = vecP.x, y = vecP.y;
+	int e = c.lastFailedEdge;
+	for(int i = 0; i < 4; ++i)
+	{
+		if(e & 2)
+		{
+			if(((y - c.Y[e]) * c.YM[e]) - ((x - c.X[e]) * c.XM[e]) < 0)
+			{ c.lastFailedEdge = e; return false; }
+		}
+		else
+		{
+			if(((y - c.Y[e]) * c.YM[e]) - ((x - c.X[e]) * c.XM[e]) <= 0)
+			{ c.lastFailedEdge = e; return false; }
+		}
+		e = (e+1) & 3;
+	}
+	uv = c.xyToUV(vecP);
+	Depth = bilerp(c.z[0], c.z[1], c.z[2], c.z[3], uv);
+	return true;
+}
+
+// CqMicroPolygon::dofSampleInBound, micropolygon.cpp:1531-1550
+bool dofSampleInBound(const Bound& bound, const HitTestCache& c, const SampleData& s)
+{
+	V2 d = s.dofOffset, p = s.position;
+	V2 cocMin{p.x + c.cocMultMin.x*d.x, p.y + c.cocMultMin.y*d.y};
+	V2 cocMax{p.x + c.cocMultMax.x*d.x, p.y + c.cocMultMax.y*d.y};
+	if(d.x < 0) std::swap(cocMin.x, cocMax.x);
+	if(d.y < 0) std::swap(cocMin.y, cocMax.y);
+	return intersects(bound, cocMin, cocMax);
+}
+
+// CqMicroPolyGridBase::TriangleSplitPoints -> CqMotionSpec::GetMotionObjectInterpolated,
+// micropolygon.cpp:895-901, motion.h:176-228, micropolygon.h:182-188
+void triangleSplitPoints(const GridView& g, F time, V3& v1, V3& v2)
+{
+	int last = g.nkeys - 1;
+	if(g.nkeys == 1) { v1 = g.split1[0]; v2 = g.split2[0]; return; }
+	if(time >= g.times[last]) { v1 = g.split1[last]; v2 = g.split2[last]; return; }
+	if(time <= g.times[0]) { v1 = g.split1[0]; v2 = g.split2[0]; return; }
+	int i = 0;
+	while(time >= g.times[i+1]) i += 1;
+	F Fraction = (time - g.times[i]) / (g.times[i+1] - g.times[i]);
+	if(g.times[i] == time) { v1 = g.split1[i]; v2 = g.split2[i]; return; }
+	const V3& a1 = g.split1[i]; const V3& b1 = g.split1[i+1];
+	const V3& a2 = g.split2[i]; const V3& b2 = g.split2[i+1];
+	v1 = V3{((1.0f - Fraction)*a1.x) + (Fraction*b1.x), ((1.0f - Fraction)*a1.y) + (Fraction*b1.y), ((1.0f - Fraction)*a1.z) + (Fraction*b1.z)};
+	v2 = V3{((1.0f - Fraction)*a2.x) + (Fraction*b2.x), ((1.0f - Fraction)*a2.y) + (Fraction*b2.y), ((1.0f - Fraction)*a2.z) + (Fraction*b2.z)};
+}
+
+bool triangleSplitReject(const Frame& f, const GridView& g, const SampleData& s, F D, F time, bool usingDof)
+{
+	// micropolygon.cpp:1630-1654 and :1885-1909
+	V3 vA, vB;
+	triangleSplitPoints(g, time, vA, vB);
+	F Ax = vA.x, Ay = vA.y, Bx = vB.x, By = vB.y;
+	V2 hitPos = s.position;
+	if(usingDof)
+	{
+		V2 cocMult = f.coc(D);
+		hitPos.x += cocMult.x*s.dofOffset.x;
+		hitPos.y += cocMult.y*s.dofOffset.y;
+	}
+	F v = (Ay - By)*hitPos.x + (Bx - Ax)*hitPos.y + (Ax*By - Bx*Ay);
+	return v <= 0;
+}
+
+// CqMicroPolygon::Sample, micropolygon.cpp:1561-1660
+bool sampleStatic(const Frame& f, const MicroPoly& mp, HitTestCache& c, const SampleData& s, F& D, V2& uv, F time, bool usingDof)
+{
+	if(usingDof)
+	{
+		if(!dofSampleInBound(mp.bound, c, s))
+			return false;
+		V2 dofOffset = s.dofOffset;
+		V3 points[4];
+		for(int i = 0; i < 4; ++i)
+			points[i] = V3{c.P[i].x - c.cocMult[i].x*dofOffset.x, c.P[i].y - c.cocMult[i].y*dofOffset.y, c.P[i].z - 0.0f};
+		cachePointInPolyTest(mp, c, points);
+	}
+	if(fContains(c, s.position, D, uv))
+	{
+		if(mp.g->flags & AQH_GRID_TRIANGULAR)
+			if(triangleSplitReject(f, *mp.g, s, D, time, usingDof))
+				return false;
+		return true;
+	}
+	return false;
+}
+
+// CqMicroPolygonMotion::Sample, micropolygon.cpp:1768-1914
+bool sampleMoving(const Frame& f, const MicroPoly& mp, HitTestCache& c, const SampleData& s, F& D, V2& uv, F time, bool usingDof)
+{
+	const GridView& g = *mp.g;
+	const F* times = g.times;
+	const int nk = g.nkeys;
+	V3 points[4];
+	int iIndex = 0;
+	F Fraction = 0.0f;
+	bool Exact = true;
+	if(time > times[0])
+	{
+		if(time >= times[nk-1])
+			iIndex = nk - 1;
+		else
+		{
+			iIndex = 0;
+			while(time >= times[iIndex+1])
+				iIndex += 1;
+			Fraction = (time - times[iIndex]) / (times[iIndex+1] - times[iIndex]);
+			Exact = (times[iIndex] == time);
+		}
+	}
+	Bound tightBound;
+	if(Exact)
+		tightBound = mp.keyBounds[iIndex];
+	else
+	{
+		const Bound& b1 = mp.keyBounds[iIndex];
+		const Bound& b2 = mp.keyBounds[iIndex+1];
+		tightBound.mn = V3{(1-Fraction)*b1.mn.x + Fraction*b2.mn.x, (1-Fraction)*b1.mn.y + Fraction*b2.mn.y, (1-Fraction)*b1.mn.z + Fraction*b2.mn.z};
+		tightBound.mx = V3{(1-Fraction)*b1.mx.x + Fraction*b2.mx.x, (1-Fraction)*b1.mx.y + Fraction*b2.mx.y, (1-Fraction)*b1.mx.z + Fraction*b2.mx.z};
+	}
+	if(usingDof)
+	{
+		if(!dofSampleInBound(tightBound, c, s))
+			return false;
+	}
+	else
+	{
+		if(!contains2D(tightBound, s.position))
+			return false;
+	}
+	if(Exact)
+	{
+		const V3* k = &mp.keyPts[size_t(iIndex)*4];
+		points[0] = k[0]; points[1] = k[1]; points[2] = k[2]; points[3] = k[3];
+	}
+	else
+	{
+		F F1 = 1.0f - Fraction;
+		const V3* k1 = &mp.keyPts[size_t(iIndex)*4];
+		const V3* k2 = &mp.keyPts[size_t(iIndex+1)*4];
+		for(int i = 0; i < 4; ++i)
+			points[i] = V3{(F1*k1[i].x) + (Fraction*k2[i].x), (F1*k1[i].y) + (Fraction*k2[i].y), (F1*k1[i].z) + (Fraction*k2[i].z)};
+	}
+	if(usingDof)
+	{
+		V2 dofOffset = s.dofOffset;
+		for(int i = 0; i < 4; ++i)
+		{
+			V2 cm = f.coc(points[i].z);
+			points[i].x -= cm.x*dofOffset.x;
+			points[i].y -= cm.y*dofOffset.y;
+			points[i].z -= 0.0f;
+		}
+	}
+	cachePointInPolyTest(mp, c, points);
+	if(fContains(c, s.position, D, uv))
+	{
+		if(g.flags & AQH_GRID_TRIANGULAR)
+			if(triangleSplitReject(f, g, s, D, time, usingDof))
+				return false;
+		return true;
+	}
+	return false;
+}
+
+// SqMpgSampleInfo + CacheOutputInterpCoeffs*, micropolygon.cpp:1434-1529
+struct MpgSampleInfo
+{
+	F col[4][3], opa[4][3];
+	bool smoothInterpolation, isOpaque, isCullable;
+};
+void cacheOutputInterpCoeffs(const MicroPoly& mp, MpgSampleInfo& c)
+{
+	const GridView& g = *mp.g;
+	c.smoothInterpolation = (g.flags & AQH_GRID_SMOOTH) != 0;
+	const int idx[4] = {mp.index, mp.index+1, mp.index + g.cu + 1, mp.index + g.cu + 2};
+	const int nc = c.smoothInterpolation ? 4 : 1;
+	for(int i = 0; i < nc; ++i)
+		for(int k = 0; k < 3; ++k)
+		{
+			c.col[i][k] = g.Ci ? g.Ci[3*idx[i]+k] : 1.0f;
+			c.opa[i][k] = g.Oi ? g.Oi[3*idx[i]+k] : 1.0f;
+		}
+	c.isOpaque = true;
+	if(g.Oi)
+		for(int i = 0; i < nc; ++i)
+			c.isOpaque = c.isOpaque && (c.opa[i][0] >= 1.0f) && (c.opa[i][1] >= 1.0f) && (c.opa[i][2] >= 1.0f);
+}
+// CqMicroPolygon::InterpolateOutputs, micropolygon.cpp:1443-1462
+void interpolateOutputs(const MpgSampleInfo& c, V2 uv, F* outCol, F* outOpac)
+{
+	if(c.smoothInterpolation)
+	{
+		F w0 = (1-uv.x)*(1-uv.y);
+		F w1 = uv.x*(1-uv.y);
+		F w2 = (1-uv.x)*uv.y;
+		F w3 = uv.x*uv.y;
+		for(int k = 0; k < 3; ++k)
+		{
+			outCol[k] = w0*c.col[0][k] + w1*c.col[1][k] + w2*c.col[2][k] + w3*c.col[3][k];
+			outOpac[k] = w0*c.opa[0][k] + w1*c.opa[1][k] + w2*c.opa[2][k] + w3*c.opa[3][k];
+		}
+	}
+	else
+		for(int k = 0; k < 3; ++k) { outCol[k] = c.col[0][k]; outOpac[k] = c.opa[0][k]; }
+}
+
+// ---------------------------------------------------------------------------------
+struct Region { int xMin, yMin, xMax, yMax; };
+struct BucketCtx
+{
+	const Frame* f;
+	Image* img;
+	Region sampleRegion;
+	bool hasValidSamples;
+	int64_t splCount, splBoundHits, splHits, deepHits;
+	SampleData& sample(int x, int y, int i) { return img->samples[(size_t(y - f->sy0)*f->sw + (x - f->sx0))*f->n + i]; }
+	int dofOffsetIndex(int x, int y, int i) { return img->dofOffsetIndices[(size_t(y - f->sy0)*f->sw + (x - f->sx0))*f->n + i]; }
+};
+
+// CqBucketProcessor::StoreSample, bucketprocessor.cpp:1471-1569
+void storeSample(BucketCtx& b, const MicroPoly& mp, const MpgSampleInfo& info, SampleData& sampleData, F D, V2 uv)
+{
+	const Frame& f = *b.f;
+	bool isCullable = info.isCullable;
+	if(isCullable && sampleData.occlZ <= D)
+		return;
+	b.splHits++;
+	b.hasValidSamples = true;
+	int matteFlag = ((mp.g->flags & AQH_GRID_MATTE) ? Flag_Matte : 0) | ((mp.g->flags & AQH_GRID_MATTE_ALPHA) ? Flag_MatteAlpha : 0);
+	Hit* hit = 0;
+	if((info.isOpaque || (matteFlag & Flag_MatteAlpha)) && isCullable)
+	{
+		hit = &sampleData.occludingHit;
+		if((f.p.display_mode & AQH_DMODE_Z) && f.p.depth_filter == AQH_DEPTHFILTER_MIDPOINT)
+		{
+			F hitPrevZ = FLT_MAX;
+			if(hit->flags & Flag_Valid)
+				hitPrevZ = hit->d[6];
+			if(hitPrevZ < D)
+			{
+				sampleData.occlZ = D;
+				return;
+			}
+			else
+				sampleData.occlZ = hitPrevZ;
+		}
+		else
+			sampleData.occlZ = D;
+		hit->flags = Flag_Valid;
+	}
+	else
+	{
+		sampleData.data.push_back(Hit());
+		hit = &sampleData.data.back();
+		hit->flags = 0;
+		b.deepHits++;
+	}
+	F col[3], opa[3];
+	interpolateOutputs(info, uv, col, opa);
+	hit->d[0] = col[0]; hit->d[1] = col[1]; hit->d[2] = col[2];
+	hit->d[3] = opa[0]; hit->d[4] = opa[1]; hit->d[5] = opa[2];
+	hit->d[6] = D;
+	hit->flags |= matteFlag;
+}
+
+// CqBucketProcessor::RenderMPG_Static, bucketprocessor.cpp:1097-1218
+void renderMPGStatic(BucketCtx& b, const MicroPoly& mp, const MpgSampleInfo& info)
+{
+	const Frame& f = *b.f;
+	const F* LodBounds = mp.g->lod;
+	bool UsingLevelOfDetail = LodBounds[0] >= 0.0f;
+	bool isCullable = info.isCullable;
+	HitTestCache c;
+	{   // CacheHitTestValues(cache, false), micropolygon.cpp:1394-1432
+		const F* gridP = mp.g->P[0];
+		int cu = mp.g->cu;
+		c.P[0] = vert(gridP, mp.index); c.P[1] = vert(gridP, mp.index+1);
+		c.P[2] = vert(gridP, mp.index+cu+1); c.P[3] = vert(gridP, mp.index+cu+2);
+		cachePointInPolyTest(mp, c, c.P);
+	}
+	const Bound& Bnd = mp.bound;
+	F bminx = Bnd.mn.x, bmaxx = Bnd.mx.x, bminy = Bnd.mn.y, bmaxy = Bnd.mx.y;
+	int eX = lceil(bmaxx), eY = lceil(bmaxy);
+	if(eX > b.sampleRegion.xMax) eX = b.sampleRegion.xMax;
+	if(eY > b.sampleRegion.yMax) eY = b.sampleRegion.yMax;
+	int sX = static_cast<int>(std::floor(bminx)), sY = static_cast<int>(std::floor(bminy));
+	if(sY < b.sampleRegion.yMin) sY = b.sampleRegion.yMin;
+	if(sX < b.sampleRegion.xMin) sX = b.sampleRegion.xMin;
+	int iXSamples = f.xs, iYSamples = f.ys;
+	int im = (bminx < sX) ? 0 : static_cast<int>(std::floor((bminx - sX) * iXSamples));
+	int in = (bminy < sY) ? 0 : static_cast<int>(std::floor((bminy - sY) * iYSamples));
+	int em = (bmaxx > eX) ? iXSamples : lceil((bmaxx - (eX - 1)) * iXSamples);
+	int en = (bmaxy > eY) ? iYSamples : lceil((bmaxy - (eY - 1)) * iYSamples);
+	if(sX >= eX || sY >= eY)
+		return;
+	for(int iY = sY; iY < eY; ++iY)
+		for(int iX = sX; iX < eX; ++iX)
+		{
+			int n = (iY == sY) ? in : 0;
+			int end_n = (iY == (eY - 1)) ? en : iYSamples;
+			int start_m = (iX == sX) ? im : 0;
+			int end_m = (iX == (eX - 1)) ? em : iXSamples;
+			int index_start = n*iXSamples + start_m;
+			for(; n < end_n; n++)
+			{
+				int index = index_start;
+				for(int m = start_m; m < end_m; m++, index++)
+				{
+					SampleData& sampleData = b.sample(iX, iY, index);
+					const F time = 0.0;
+					b.splCount++;
+					if(!contains2D(Bnd, sampleData.position))
+						continue;
+					if(isCullable && Bnd.mn.z > sampleData.occlZ)
+						continue;
+					if(UsingLevelOfDetail)
+					{
+						F LevelOfDetail = sampleData.detailLevel;
+						if(LodBounds[0] > LevelOfDetail || LevelOfDetail >= LodBounds[1])
+							continue;
+					}
+					b.splBoundHits++;
+					F D; V2 uv;
+					if(sampleStatic(f, mp, c, sampleData, D, uv, time, false))
+						storeSample(b, mp, info, sampleData, D, uv);
+				}
+				index_start += iXSamples;
+			}
+		}
+}
+
+// CqBucketProcessor::RenderMPG_MBOrDof, bucketprocessor.cpp:1221-1469
+void renderMPGMBOrDof(BucketCtx& b, MicroPoly& mp, const MpgSampleInfo& info, bool IsMoving, bool UsingDof)
+{
+	const Frame& f = *b.f;
+	const F* LodBounds = mp.g->lod;
+	bool UsingLevelOfDetail = LodBounds[0] >= 0.0f;
+	bool isCullable = info.isCullable;
+	HitTestCache c;
+	c.lastFailedEdge = 0;
+	if(!IsMoving)
+	{   // CqMicroPolygon::CacheHitTestValues, micropolygon.cpp:1394-1432
+		const F* gridP = mp.g->P[0];
+		int cu = mp.g->cu;
+		c.P[0] = vert(gridP, mp.index); c.P[1] = vert(gridP, mp.index+1);
+		c.P[2] = vert(gridP, mp.index+cu+1); c.P[3] = vert(gridP, mp.index+cu+2);
+		if(UsingDof)
+		{
+			for(int i = 0; i < 4; ++i) c.cocMult[i] = f.coc(c.P[i].z);
+			c.cocMultMin = V2{fmin_(fmin_(c.cocMult[0].x, c.cocMult[1].x), fmin_(c.cocMult[2].x, c.cocMult[3].x)),
+			                  fmin_(fmin_(c.cocMult[0].y, c.cocMult[1].y), fmin_(c.cocMult[2].y, c.cocMult[3].y))};
+			c.cocMultMax = V2{fmax_(fmax_(c.cocMult[0].x, c.cocMult[1].x), fmax_(c.cocMult[2].x, c.cocMult[3].x)),
+			                  fmax_(fmax_(c.cocMult[0].y, c.cocMult[1].y), fmax_(c.cocMult[2].y, c.cocMult[3].y))};
+		}
+		else
+			cachePointInPolyTest(mp, c, c.P);
+	}
+	else if(UsingDof)
+	{   // CqMicroPolygonMotion::CacheHitTestValues, micropolygon.cpp:1916-1941
+		V2 coc1 = f.coc(mp.bound.mn.z);
+		V2 coc2 = f.coc(mp.bound.mx.z);
+		if(f.minCoCForBound(mp.bound) == 0)
+			c.cocMultMin = V2{0, 0};
+		else
+			c.cocMultMin = V2{fmin_(coc1.x, coc2.x), fmin_(coc1.y, coc2.y)};
+		c.cocMultMax = V2{fmax_(coc1.x, coc2.x), fmax_(coc1.y, coc2.y)};
+	}
+
+	int iXSamples = f.xs, iYSamples = f.ys;
+	F opentime = f.p.shutter_open, closetime = f.p.shutter_close;
+	F timePerSample = 0;
+	bool fastShutter = false;
+	int numSamples = iXSamples * iYSamples;
+	if(IsMoving)
+	{
+		fastShutter = isClose(closetime, opentime);
+		if(!fastShutter)
+			timePerSample = numSamples / (closetime - opentime);
+	}
+	const int timeRanges = std::max(4, f.xs * f.ys);
+	int bound_maxMB = 1;
+	if(IsMoving)
+	{
+		if(mp.boundList.empty())
+			buildBoundList(f, mp, timeRanges);
+		bound_maxMB = int(mp.boundList.size());
+	}
+	int bound_maxMB_1 = bound_maxMB - 1;
+	for(int bound_numMB = 0; bound_numMB < bound_maxMB; bound_numMB++)
+	{
+		F time0 = 0.0f, time1 = 0.0f;
+		const Bound& Bnd = IsMoving ? mp.boundList[bound_numMB] : mp.bound;
+		if(IsMoving) time0 = mp.boundTimes[bound_numMB];
+		int indexT0 = 0, indexT1 = 0;
+		if(IsMoving)
+		{
+			if(bound_numMB != bound_maxMB_1)
+				time1 = mp.boundTimes[bound_numMB + 1];
+			else
+				time1 = closetime;
+			if(time1 < opentime || time0 > closetime)
+				continue;
+			if(fastShutter)
+			{
+				indexT0 = 0;
+				indexT1 = numSamples;
+			}
+			else
+			{
+				indexT0 = std::max<int>(0, lfloor((time0 - opentime) * timePerSample));
+				indexT1 = lceil((time1 - opentime) * timePerSample);
+			}
+			// The reference indexes SampleData(index) unchecked; rounding can push these one
+			// past the end (undefined behaviour there).  The oracle clamps to the valid range.
+			if(indexT1 > numSamples) indexT1 = numSamples;
+			if(indexT0 >= numSamples) continue;
+		}
+		F maxCocX = 0, maxCocY = 0;
+		F bminx = Bnd.mn.x, bmaxx = Bnd.mx.x, bminy = Bnd.mn.y, bmaxy = Bnd.mx.y;
+		F bminz = Bnd.mn.z, bmaxz = Bnd.mx.z;
+		if(bminz > f.p.clip_far || bmaxz < f.p.clip_near)
+			continue;
+		F mpgbminx = bminx, mpgbmaxx = bmaxx, mpgbminy = bminy, mpgbmaxy = bmaxy;
+		int bound_maxDof = 1;
+		if(UsingDof)
+		{
+			V2 minZCoc = f.coc(Bnd.mn.z);
+			V2 maxZCoc = f.coc(Bnd.mx.z);
+			maxCocX = fmax_(minZCoc.x, maxZCoc.x);
+			maxCocY = fmax_(minZCoc.y, maxZCoc.y);
+			bound_maxDof = f.n;
+		}
+		for(int bound_numDof = 0; bound_numDof < bound_maxDof; bound_numDof++)
+		{
+			if(UsingDof)
+			{
+				const Bound& DofBound = f.dofBounds[bound_numDof];
+				F leftOffset = DofBound.mx.x * maxCocX;
+				F rightOffset = DofBound.mn.x * maxCocX;
+				F topOffset = DofBound.mx.y * maxCocY;
+				F bottomOffset = DofBound.mn.y * maxCocY;
+				bminx = mpgbminx - leftOffset;
+				bmaxx = mpgbmaxx - rightOffset;
+				bminy = mpgbminy - topOffset;
+				bmaxy = mpgbmaxy - bottomOffset;
+			}
+			int eX = lceil(bmaxx), eY = lceil(bmaxy);
+			if(eX > b.sampleRegion.xMax) eX = b.sampleRegion.xMax;
+			if(eY > b.sampleRegion.yMax) eY = b.sampleRegion.yMax;
+			int sX = static_cast<int>(std::floor(bminx)), sY = static_cast<int>(std::floor(bminy));
+			if(sY < b.sampleRegion.yMin) sY = b.sampleRegion.yMin;
+			if(sX < b.sampleRegion.xMin) sX = b.sampleRegion.xMin;
+			if(sX >= eX || sY >= eY)
+				continue;
+			for(int iY = sY; iY < eY; ++iY)
+				for(int iX = sX; iX < eX; ++iX)
+				{
+					int index;
+					if(UsingDof)
+						index = b.dofOffsetIndex(iX, iY, bound_numDof);
+					else
+						index = indexT0;
+					do
+					{
+						SampleData& sampleData = b.sample(iX, iY, index);
+						V2 vecP = sampleData.position;
+						const F time = sampleData.time;
+						index++;
+						b.splCount++;
+						if(IsMoving && (time < time0 || time > time1))
+							continue;
+						if(UsingDof)
+						{
+							Bound DofBound{V3{bminx, bminy, bminz}, V3{bmaxx, bmaxy, bmaxz}};
+							if(!contains2D(DofBound, vecP))
+								continue;
+						}
+						else
+						{
+							if(!contains2D(Bnd, vecP))
+								continue;
+						}
+						if(isCullable && Bnd.mn.z > sampleData.occlZ)
+							continue;
+						if(UsingLevelOfDetail)
+						{
+							F LevelOfDetail = sampleData.detailLevel;
+							if(LodBounds[0] > LevelOfDetail || LevelOfDetail >= LodBounds[1])
+								continue;
+						}
+						b.splBoundHits++;
+						F D; V2 uv;
+						bool SampleHit = IsMoving ? sampleMoving(f, mp, c, sampleData, D, uv, time, UsingDof)
+						                          : sampleStatic(f, mp, c, sampleData, D, uv, time, UsingDof);
+						if(SampleHit)
+							storeSample(b, mp, info, sampleData, D, uv);
+					} while(!UsingDof && index < indexT1);
+				}
+		}
+	}
+}
+
+// CqBucketProcessor::RenderMicroPoly, bucketprocessor.cpp:1067-1091
+void renderMicroPoly(BucketCtx& b, MicroPoly& mp)
+{
+	const Frame& f = *b.f;
+	bool UsingDof = f.p.use_dof != 0;
+	bool IsMoving = mp.moving;
+	MpgSampleInfo info;
+	info.isCullable = !((f.p.display_mode & AQH_DMODE_Z) &&
+	                    (f.p.depth_filter == AQH_DEPTHFILTER_MAX || f.p.depth_filter == AQH_DEPTHFILTER_AVERAGE));
+	cacheOutputInterpCoeffs(mp, info);
+	if(IsMoving || UsingDof)
+		renderMPGMBOrDof(b, mp, info, IsMoving, UsingDof);
+	else
+		renderMPGStatic(b, mp, info);
+}
+
+// CqImagePixel::Combine for one sample, imagepixel.cpp:144-332 (CSG resolve omitted: no CSG support)
+void combineSample(SampleData& sampleData, int depthfilter, const F* zThreshold)
+{
+	Hit& occlHit = sampleData.occludingHit;
+	if(!sampleData.data.empty())
+	{
+		if(occlHit.flags & Flag_Valid)
+			sampleData.data.push_back(occlHit);
+		// std::sort is unstable on equal depths; equal-depth layers are outside what parity
+		// tests exercise.  stable_sort keeps submission order on ties (the product's rule).
+		std::stable_sort(sampleData.data.begin(), sampleData.data.end(),
+		                 [](const Hit& a, const Hit& b) { return a.d[6] < b.d[6]; });
+		F samplecolor[3] = {0, 0, 0}, sampleopacity[3] = {0, 0, 0};
+		F opaqueDepths[2] = { sampleData.occlZ, FLT_MAX };
+		F maxOpaqueDepth = FLT_MAX;
+		for(std::vector<Hit>::reverse_iterator sample = sampleData.data.rbegin(); sample != sampleData.data.rend(); sample++)
+		{
+			F* sd = sample->d;
+			if(sample->flags & Flag_Matte)
+			{
+				for(int k = 0; k < 3; ++k)
+				{
+					samplecolor[k] = lerpf(sd[3+k], samplecolor[k], 0.0f);
+					sampleopacity[k] = lerpf(sd[k], sampleopacity[k], 0.0f);
+				}
+			}
+			else
+			{
+				for(int k = 0; k < 3; ++k)
+				{
+					samplecolor[k] = (samplecolor[k] * (1.0f - clampf(sd[3+k], 0.0f, 1.0f))) + sd[k];
+					sampleopacity[k] = ((1.0f - sampleopacity[k]) * sd[3+k]) + sampleopacity[k];
+				}
+			}
+			if(sd[3] >= zThreshold[0] && sd[4] >= zThreshold[1] && sd[5] >= zThreshold[2])
+			{
+				opaqueDepths[1] = opaqueDepths[0];
+				opaqueDepths[0] = sd[6];
+				if(!(maxOpaqueDepth < FLT_MAX))
+					maxOpaqueDepth = sd[6];
+			}
+		}
+		occlHit = *sampleData.data.begin();
+		F* occlData = occlHit.d;
+		for(int k = 0; k < 3; ++k) { occlData[k] = samplecolor[k]; occlData[3+k] = sampleopacity[k]; }
+		occlHit.flags |= Flag_Valid;
+		F& occlDepth = occlData[6];
+		if(depthfilter != AQH_DEPTHFILTER_MIN)
+		{
+			if(depthfilter == AQH_DEPTHFILTER_MIDPOINT)
+			{
+				if(sampleData.data.size() > 1)
+					occlDepth = ((opaqueDepths[0] + opaqueDepths[1]) * 0.5f);
+				else
+					occlDepth = FLT_MAX;
+			}
+			else if(depthfilter == AQH_DEPTHFILTER_MAX)
+				occlDepth = maxOpaqueDepth;
+			else if(depthfilter == AQH_DEPTHFILTER_AVERAGE)
+			{
+				F totDepth = 0.0f;
+				int totCount = 0;
+				for(std::vector<Hit>::iterator s2 = sampleData.data.begin(); s2 != sampleData.data.end(); s2++)
+					if(s2->d[3] >= zThreshold[0] || s2->d[4] >= zThreshold[1] || s2->d[5] >= zThreshold[2])
+					{
+						totDepth += s2->d[6];
+						totCount++;
+					}
+				totDepth /= totCount;
+				occlDepth = totDepth;
+			}
+		}
+		else
+			occlDepth = opaqueDepths[0];
+	}
+	else if(occlHit.flags & Flag_Valid)
+	{
+		F* occlData = occlHit.d;
+		if(occlHit.flags & Flag_Matte)
+			for(int k = 0; k < 6; ++k) occlData[k] = 0;
+		if(depthfilter == AQH_DEPTHFILTER_MIDPOINT)
+			occlData[6] = 0.5*(occlData[6] + sampleData.occlZ);
+	}
+}
+
+// ---------------------------------------------------------------------------------
+struct BucketInfo
+{
+	int col, row, xPos, yPos, xSize, ySize;
+	Region sampleRegion;
+	std::vector<MPRef> mps;            // CqBucket::micropolygons(), in AddMP order
+	bool hasValidSamples;
+};
+
+// CqBucketProcessor::FilterBucket (live non-separable branch) + alpha/coverage,
+// bucketprocessor.cpp:584-707, then ExposeBucket :766-806.
+void filterBucket(const Frame& f, Image& img, const BucketInfo& bk, bool hasValidSamples, F* channels /*image, 9/pixel*/)
+{
+	const AqhFrameParams& p = f.p;
+	const int xres = p.xres;
+	const int xmax = f.shiftX, ymax = f.shiftY;
+	F xfwo2 = std::ceil(p.filter_xwidth) * 0.5f;
+	F yfwo2 = std::ceil(p.filter_ywidth) * 0.5f;
+	int numSubPixels = f.n;
+	const int datasize = 7;  // slots 7,8 of a hit are never written and the channels they feed are overwritten below
+	// Pixels of a bucket that lie outside the crop window are filtered by the reference from
+	// never-initialised (stale) pixel storage; oracle and product define them as zero instead.
+	const int begy = std::max(bk.yPos, p.crop_ymin), begx = std::max(bk.xPos, p.crop_xmin);
+	int endy = std::min(bk.yPos + bk.ySize, p.crop_ymax), endx = std::min(bk.xPos + bk.xSize, p.crop_xmax);
+	for(int y = begy; y < endy; y++)
+	{
+		F ycent = y + 0.5f;
+		for(int x = begx; x < endx; x++)
+		{
+			F* out = channels + (size_t(y)*xres + x)*9;
+			F coverage = 0;
+			if(hasValidSamples)
+			{
+				F xcent = x + 0.5f;
+				F gTot = 0.0;
+				int SampleCount = 0;
+				F samples[7] = {0, 0, 0, 0, 0, 0, 0};
+				for(int fy = -ymax; fy <= ymax; fy++)
+					for(int fx = -xmax; fx <= xmax; fx++)
+					{
+						int index = ((fy + ymax)*(2*xmax+1) + fx + xmax) * numSubPixels;
+						int px = x + fx, py = y + fy;
+						// Pixels outside [crop-shift, crop+shift) never exist in the reference's
+						// data region of a bucket inside the crop window.
+						const SampleData* sd0 = &img.samples[(size_t(py - f.sy0)*f.sw + (px - f.sx0))*f.n];
+						int sampleIndex = 0;
+						for(int sy = 0; sy < f.ys; sy++)
+							for(int sx = 0; sx < f.xs; sx++)
+							{
+								const SampleData& sampleData = sd0[sampleIndex];
+								V2 vecS{sampleData.position.x - xcent, sampleData.position.y - ycent};
+								if(vecS.x >= -xfwo2 && vecS.y >= -yfwo2 && vecS.x <= xfwo2 && vecS.y <= yfwo2)
+								{
+									F g = f.filterValues[index + sampleIndex];
+									gTot += g;
+									const Hit& opv = sampleData.occludingHit;
+									if(opv.flags & Flag_Valid)
+									{
+										for(int k = 0; k < datasize; ++k)
+											samples[k] += opv.d[k] * g;
+										SampleCount++;
+									}
+								}
+								sampleIndex++;
+							}
+					}
+				if(SampleCount == 0)
+				{
+					for(int k = 0; k < 9; ++k) out[k] = 0.0f;
+					out[AQH_CH_Z] = FLT_MAX;
+					coverage = 0.0;
+				}
+				else
+				{
+					float oneOverGTot = 1.0 / gTot;
+					for(int k = 0; k < 6; ++k) out[k] = samples[k] * oneOverGTot;
+					out[AQH_CH_Z] = samples[6] * oneOverGTot;
+					if(SampleCount >= numSubPixels)
+						coverage = 1.0;
+					else
+						coverage = (F)SampleCount / (F)(numSubPixels);
+				}
+			}
+			else
+			{
+				for(int k = 0; k < 9; ++k) out[k] = 0.0f;
+				out[AQH_CH_Z] = FLT_MAX;
+				coverage = 0.0f;
+			}
+			F a = (out[3] + out[4] + out[5]) / 3.0f;
+			out[AQH_CH_ALPHA] = a * coverage;
+			out[AQH_CH_COVERAGE] = coverage;
+		}
+	}
+	// ExposeBucket
+	if(!hasValidSamples)
+		return;
+	F exposegain = p.exposure_gain, exposegamma = p.exposure_gamma;
+	if(exposegain == 1.0 && exposegamma == 1.0)
+		return;
+	F oneovergamma = 1.0f / exposegamma;
+	for(int y = begy; y < endy; y++)
+		for(int x = begx; x < endx; x++)
+		{
+			F* buffer = channels + (size_t(y)*xres + x)*9;
+			if(exposegain != 1.0)
+			{
+				buffer[0] *= exposegain; buffer[1] *= exposegain; buffer[2] *= exposegain;
+			}
+			if(exposegamma != 1.0)
+			{
+				buffer[0] = pow(buffer[0], oneovergamma);
+				buffer[1] = pow(buffer[1], oneovergamma);
+				buffer[2] = pow(buffer[2], oneovergamma);
+			}
+		}
+}
+
+// selectDataFormat, ddmanager.cpp:249-283
+int selectDataFormat(F oneVal, F minVal, F maxVal)
+{
+	if(oneVal == 0)
+		return AQH_FLOAT32;
+	if(minVal >= 0)
+	{
+		if(maxVal <= 255) return AQH_UNSIGNED8;
+		else if(maxVal <= 65535) return AQH_UNSIGNED16;
+		else return AQH_UNSIGNED32;
+	}
+	else
+	{
+		if(minVal >= -128 && maxVal <= 127) return AQH_SIGNED8;
+		else if(minVal >= -32768 && maxVal <= 32767) return AQH_SIGNED16;
+		else return AQH_SIGNED32;
+	}
+}
+int typeSize(int type)
+{
+	switch(type)
+	{
+		case AQH_FLOAT32: case AQH_UNSIGNED32: case AQH_SIGNED32: return 4;
+		case AQH_UNSIGNED16: case AQH_SIGNED16: return 2;
+		default: return 1;
+	}
+}
+
+// CqDisplayRequest::FormatBucketForDisplay, ddmanager.cpp:1022-1118
+void formatBucketForDisplay(const Frame& f, const BucketInfo& bk, const AqhDisplayDesc& d, const F* channels,
+                            const F* dither /*xres*yres for this display*/, unsigned char* out)
+{
+	const int xres = f.p.xres;
+	int type = d.type ? d.type : selectDataFormat(d.quantize_one, d.quantize_min, d.quantize_max);
+	int esize = typeSize(type) * d.n_channels;
+	for(int y = std::max(bk.yPos, f.p.crop_ymin); y < std::min(bk.yPos + bk.ySize, f.p.crop_ymax); ++y)
+		for(int x = std::max(bk.xPos, f.p.crop_xmin); x < std::min(bk.xPos + bk.xSize, f.p.crop_xmax); ++x)
+		{
+			double s = dither[size_t(y)*xres + x];
+			unsigned char* pdata = out + (size_t(y)*xres + x)*esize;
+			for(int c = 0; c < d.n_channels; ++c)
+			{
+				double value = channels[(size_t(y)*xres + x)*9 + d.channel[c]];
+				if(d.quantize_one != 0)
+				{
+					value = lround_aq(d.quantize_zero + value * (d.quantize_one - d.quantize_zero) + (d.quantize_dither * s));
+					double lo = d.quantize_min, hi = d.quantize_max;
+					value = value < lo ? lo : (value > hi ? hi : value);
+				}
+				switch(type)
+				{
+					case AQH_FLOAT32: { float v = value; std::memcpy(pdata, &v, 4); pdata += 4; break; }
+					case AQH_UNSIGNED32:
+					{
+						value = value < 0 ? 0 : (value > 4294967295.0 ? 4294967295.0 : value);
+						uint32_t v = static_cast<uint32_t>(value); std::memcpy(pdata, &v, 4); pdata += 4; break;
+					}
+					case AQH_SIGNED32:
+					{
+						value = value < -2147483648.0 ? -2147483648.0 : (value > 2147483647.0 ? 2147483647.0 : value);
+						int32_t v = static_cast<int32_t>(value); std::memcpy(pdata, &v, 4); pdata += 4; break;
+					}
+					case AQH_UNSIGNED16: { uint16_t v = static_cast<uint16_t>(value); std::memcpy(pdata, &v, 2); pdata += 2; break; }
+					case AQH_SIGNED16: { int16_t v = static_cast<int16_t>(value); std::memcpy(pdata, &v, 2); pdata += 2; break; }
+					case AQH_UNSIGNED8: { *pdata++ = static_cast<uint8_t>(value); break; }
+					case AQH_SIGNED8: { *pdata++ = static_cast<unsigned char>(static_cast<int8_t>(value)); break; }
+				}
+			}
+		}
+}
+
+double nowSec()
+{
+	return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+template<class Fn> void parallelFor(int n, int nthreads, Fn fn)
+{
+	if(nthreads <= 1 || n <= 1)
+	{
+		for(int i = 0; i < n; ++i) fn(i);
+		return;
+	}
+	std::atomic<int> next(0);
+	std::vector<std::thread> th;
+	for(int t = 0; t < nthreads; ++t)
+		th.emplace_back([&]() { for(;;) { int i = next.fetch_add(1); if(i >= n) break; fn(i); } });
+	for(auto& t : th) t.join();
+}
+
+} // namespace
+
+// =====================================================================================
+extern "C" {
+
+int orc_display_entrysize(const AqhDisplayDesc* d, int* type_out)
+{
+	int type = d->type ? d->type : selectDataFormat(d->quantize_one, d->quantize_min, d->quantize_max);
+	if(type_out) *type_out = type;
+	return typeSize(type) * d->n_channels;
+}
+
+int orc_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* channelsOut,
+               unsigned char* const* displayOut, int nthreads, OrcStats* stats)
+{
+	if(!pp || !grids || grids->memory_space != 0) return AQH_ERR_BAD_PARAMS;
+	if(pp->crop_xmax <= pp->crop_xmin || pp->crop_ymax <= pp->crop_ymin) return AQH_ERR_BAD_PARAMS;
+	for(int64_t g = 0; g < grids->n_grids; ++g)
+		if(grids->flags[g] & AQH_GRID_USES_CSG) return AQH_ERR_UNSUPPORTED;
+	double t0 = nowSec();
+	Frame f;
+	f.p = *pp;
+	setupLayout(f);
+	const AqhFrameParams& p = f.p;
+
+	// ---- RiWorldBegin: CqRandom().Reseed(545) (ri.cpp:660); front-end draws; then RenderImage:
+	// the jittered sampler is always built (imagebuffer.cpp:694), the grid sampler is used
+	// iff Hider "jitter" 0 (:698-704).
+	g_rng.init(p.rng_seed);
+	for(uint32_t i = 0; i < p.rng_predraws; ++i) g_rng.next();
+	buildJitterSampler(f.sampler, f.xs, f.ys);
+	if(!p.jitter)
+		buildGridSampler(f.sampler, f.xs, f.ys);
+	initialiseFilterValues(f);
+	calculateDofBounds(f.xs, f.ys, f.dofBounds);
+
+	Image img;
+	img.samples.resize(size_t(f.sw)*f.sh*f.n);
+	img.dofOffsetIndices.resize(size_t(f.sw)*f.sh*f.n);
+
+	// ---- bucket table + the sequential RNG replay (preProcess per bucket, then the display's
+	// dither draws) in the reference's row-major bucket order, imagebuffer.cpp:708-733.
+	const int nbx = f.bx1 - f.bx0, nby = f.by1 - f.by0;
+	std::vector<BucketInfo> buckets(size_t(nbx)*nby);
+	std::vector<F> dither(size_t(std::max(1, p.n_displays))*p.xres*p.yres, 0.f);
+	for(int row = f.by0; row < f.by1; ++row)
+		for(int col = f.bx0; col < f.bx1; ++col)
+		{
+			BucketInfo& bk = buckets[size_t(row - f.by0)*nbx + (col - f.bx0)];
+			bk.col = col; bk.row = row;
+			bk.xPos = col*p.bucket_xsize; bk.yPos = row*p.bucket_ysize;
+			bk.xSize = std::min(p.bucket_xsize, p.xres - bk.xPos);
+			bk.ySize = std::min(p.bucket_ysize, p.yres - bk.yPos);
+			bk.hasValidSamples = false;
+			// CqBucketProcessor::preProcess, bucketprocessor.cpp:112-137
+			int sminx = bk.xPos - f.shiftX, sminy = bk.yPos - f.shiftY;
+			int smaxx = bk.xPos + bk.xSize + f.shiftX, smaxy = bk.yPos + bk.ySize + f.shiftY;
+			if(sminx < p.crop_xmin - f.shiftX) sminx = p.crop_xmin - f.shiftX;
+			if(sminy < p.crop_ymin - f.shiftY) sminy = p.crop_ymin - f.shiftY;
+			if(smaxx > p.crop_xmax + f.shiftX) smaxx = p.crop_xmax + f.shiftX;
+			if(smaxy > p.crop_ymax + f.shiftY) smaxy = p.crop_ymax + f.shiftY;
+			if(col > f.bx0) sminx += f.shiftX*2;   // left cache segment applied
+			if(row > f.by0) sminy += f.shiftY*2;   // top cache segment applied
+			bk.sampleRegion = Region{sminx, sminy, smaxx, smaxy};
+			for(int y = sminy; y < smaxy; ++y)
+				for(int x = sminx; x < smaxx; ++x)
+					setSamples(f, img, x, y);
+			for(int d = 0; d < p.n_displays; ++d)
+				for(int y = 0; y < bk.ySize; ++y)
+					for(int x = 0; x < bk.xSize; ++x)
+						dither[(size_t(d)*p.yres + bk.yPos + y)*p.xres + bk.xPos + x] = g_rng.randomFloat();
+		}
+	double t1 = nowSec();
+
+	// ---- Split + AddMPG for every grid in submission order, micropolygon.cpp:770-880,
+	// imagebuffer.cpp:514-591.
+	Scene sc;
+	buildScene(f, *grids, sc);
+	int64_t nMP = 0, nEntries = 0;
+	for(size_t gi = 0; gi < sc.grids.size(); ++gi)
+	{
+		const GridView& g = sc.grids[gi];
+		for(int iv = 0; iv < g.cv; iv++)
+			for(int iu = 0; iu < g.cu; iu++)
+			{
+				int iIndex = (iv*(g.cu + 1)) + iu;
+				if(g.culled && g.culled[iIndex])
+					continue;
+				Bound B;
+				{
+					const int cu = g.cu;
+					const F* P = g.P[0];
+					B = boundOf4(vert(P, iIndex), vert(P, iIndex+1), vert(P, iIndex+cu+1), vert(P, iIndex+cu+2));
+					for(int k = 1; k < g.nkeys; ++k)
+					{
+						const F* Pk = g.P[k];
+						Bound kb = boundOf4(vert(Pk, iIndex), vert(Pk, iIndex+1), vert(Pk, iIndex+cu+1), vert(Pk, iIndex+cu+2));
+						encapsulate(B, kb);
+					}
+				}
+				if(p.use_dof)
+				{
+					V2 c1 = f.coc(B.mn.z), c2 = f.coc(B.mx.z);
+					V2 maxCoC{fmax_(c1.x, c2.x), fmax_(c1.y, c2.y)};
+					B.mn.x -= maxCoC.x; B.mn.y -= maxCoC.y; B.mn.z -= 0.0f;
+					B.mx.x += maxCoC.x; B.mx.y += maxCoC.y; B.mx.z += 0.0f;
+				}
+				if(B.mx.x < p.crop_xmin - p.filter_xwidth / 2.0f || B.mx.y < p.crop_ymin - p.filter_ywidth / 2.0f ||
+				   B.mn.x > p.crop_xmax + p.filter_xwidth / 2.0f || B.mn.y > p.crop_ymax + p.filter_ywidth / 2.0f)
+					continue;
+				B.mn.x = B.mn.x - (lfloor(p.filter_xwidth / 2.0f));
+				B.mn.y = B.mn.y - (lfloor(p.filter_ywidth / 2.0f));
+				B.mx.x = B.mx.x + (lfloor(p.filter_xwidth / 2.0f));
+				B.mx.y = B.mx.y + (lfloor(p.filter_ywidth / 2.0f));
+				int iXBa = static_cast<int>(B.mn.x / p.bucket_xsize);
+				int iYBa = static_cast<int>(B.mn.y / p.bucket_ysize);
+				int iXBb = static_cast<int>(B.mx.x / p.bucket_xsize);
+				int iYBb = static_cast<int>(B.mx.y / p.bucket_ysize);
+				if((iXBb < f.bx0) || (iYBb < f.by0) || (iXBa >= f.bx1) || (iYBa >= f.by1))
+					continue;
+				if(iXBa < f.bx0) iXBa = f.bx0;
+				if(iYBa < f.by0) iYBa = f.by0;
+				if(iXBb >= f.bx1) iXBb = f.bx1 - 1;
+				if(iYBb >= f.by1) iYBb = f.by1 - 1;
+				++nMP;
+				for(int i = iXBa; i <= iXBb; i++)
+					for(int j = iYBa; j <= iYBb; j++)
+					{
+						buckets[size_t(j - f.by0)*nbx + (i - f.bx0)].mps.push_back(MPRef{int(gi), iIndex});
+						++nEntries;
+					}
+			}
+	}
+	double t2 = nowSec();
+
+	// ---- per bucket: RenderWaitingMPs + CombineElements over the bucket's sample region.
+	std::atomic<int64_t> splCount(0), splBoundHits(0), splHits(0), deepHits(0);
+	parallelFor(int(buckets.size()), nthreads, [&](int bi)
+	{
+		BucketInfo& bk = buckets[bi];
+		BucketCtx ctx;
+		ctx.f = &f; ctx.img = &img; ctx.sampleRegion = bk.sampleRegion; ctx.hasValidSamples = false;
+		ctx.splCount = ctx.splBoundHits = ctx.splHits = ctx.deepHits = 0;
+		MicroPoly mp;
+		for(size_t i = 0; i < bk.mps.size(); ++i)
+		{
+			makeMicroPoly(sc.grids[bk.mps[i].grid], bk.mps[i].index, mp);
+			renderMicroPoly(ctx, mp);
+		}
+		// CombineElements, bucketprocessor.cpp:365-375
+		for(int y = bk.sampleRegion.yMin; y < bk.sampleRegion.yMax; ++y)
+			for(int x = bk.sampleRegion.xMin; x < bk.sampleRegion.xMax; ++x)
+				for(int i = 0; i < f.n; ++i)
+					combineSample(ctx.sample(x, y, i), p.depth_filter, p.zthreshold);
+		bk.hasValidSamples = ctx.hasValidSamples;
+		splCount += ctx.splCount; splBoundHits += ctx.splBoundHits; splHits += ctx.splHits; deepHits += ctx.deepHits;
+	});
+	double t3 = nowSec();
+
+	// m_hasValidSamples of a bucket also becomes true when an adopted cache-segment pixel has
+	// valid samples (applyCacheSegment, bucketprocessor.cpp:1676): i.e. when any pixel of the
+	// bucket's DATA region that was sampled by an earlier bucket received a hit.
+	std::vector<uint8_t> pixelHasValid(size_t(f.sw)*f.sh, 0);
+	for(int y = 0; y < f.sh; ++y)
+		for(int x = 0; x < f.sw; ++x)
+		{
+			const SampleData* sd = &img.samples[(size_t(y)*f.sw + x)*f.n];
+			uint8_t v = 0;
+			for(int i = 0; i < f.n && !v; ++i)
+				v = (sd[i].occludingHit.flags & Flag_Valid) ? 1 : 0;
+			pixelHasValid[size_t(y)*f.sw + x] = v;
+		}
+	std::vector<F> localChannels;
+	F* channels = channelsOut;
+	if(!channels)
+	{
+		localChannels.assign(size_t(p.xres)*p.yres*9, 0.f);
+		channels = localChannels.data();
+	}
+	else
+		std::fill(channels, channels + size_t(p.xres)*p.yres*9, 0.f);
+	std::vector<int> esize(std::max(1, p.n_displays), 0);
+	for(int d = 0; d < p.n_displays; ++d)
+	{
+		esize[d] = orc_display_entrysize(&p.display[d], 0);
+		if(displayOut && displayOut[d])
+			std::memset(displayOut[d], 0, size_t(p.xres)*p.yres*esize[d]);
+	}
+	double tFilter = 0, tDisplay = 0;
+	parallelFor(int(buckets.size()), nthreads, [&](int bi)
+	{
+		BucketInfo& bk = buckets[bi];
+		bool valid = bk.hasValidSamples;
+		if(!valid)
+		{
+			// data region = display region +- shift, clamped to the sample region of the image
+			int x0 = std::max(bk.xPos - f.shiftX, f.sx0), x1 = std::min(bk.xPos + p.bucket_xsize + f.shiftX, f.sx0 + f.sw);
+			int y0 = std::max(bk.yPos - f.shiftY, f.sy0), y1 = std::min(bk.yPos + p.bucket_ysize + f.shiftY, f.sy0 + f.sh);
+			for(int y = y0; y < y1 && !valid; ++y)
+				for(int x = x0; x < x1 && !valid; ++x)
+				{
+					// only pixels this bucket did NOT sample itself arrive through cache segments
+					bool own = x >= bk.sampleRegion.xMin && x < bk.sampleRegion.xMax && y >= bk.sampleRegion.yMin && y < bk.sampleRegion.yMax;
+					if(!own && pixelHasValid[size_t(y - f.sy0)*f.sw + (x - f.sx0)])
+						valid = true;
+				}
+		}
+		double a = nowSec();
+		filterBucket(f, img, bk, valid, channels);
+		double b = nowSec();
+		for(int d = 0; d < p.n_displays; ++d)
+			if(displayOut && displayOut[d])
+				formatBucketForDisplay(f, bk, p.display[d], channels, &dither[size_t(d)*p.xres*p.yres], displayOut[d]);
+		double c = nowSec();
+		if(nthreads <= 1) { tFilter += b - a; tDisplay += c - b; }
+	});
+	double t4 = nowSec();
+	if(stats)
+	{
+		std::memset(stats, 0, sizeof(*stats));
+		stats->prepare_s = t1 - t0; stats->bust_s = t2 - t1; stats->render_s = t3 - t2;
+		stats->filter_s = (nthreads <= 1) ? tFilter : (t4 - t3); stats->display_s = tDisplay;
+		stats->total_s = t4 - t0;
+		stats->n_micropolygons = nMP; stats->n_bucket_entries = nEntries;
+		stats->n_samples = int64_t(f.sw)*f.sh*f.n;
+		stats->spl_count = splCount; stats->spl_bound_hits = splBoundHits; stats->spl_hits = splHits;
+		stats->n_deep_hits = deepHits;
+		stats->threads = std::max(1, nthreads);
+	}
+	return AQH_OK;
+}
+
+// ---- leaves -------------------------------------------------------------------------
+void orc_random_reseed(uint32_t seed) { g_rng.init(seed); }
+uint32_t orc_random_uint(void) { return g_rng.next(); }
+float orc_random_float(void) { return g_rng.randomFloat(); }
+uint32_t orc_random_int(uint32_t range) { return g_rng.randomInt(range); }
+
+int orc_sampler_tables(int xs, int ys, int jitter, float* pos_xy, float* val1d, int32_t* shuffled)
+{
+	Sampler s;
+	if(jitter) buildJitterSampler(s, xs, ys); else buildGridSampler(s, xs, ys);
+	std::memcpy(pos_xy, s.pos.data(), s.pos.size()*sizeof(float));
+	std::memcpy(val1d, s.v1d.data(), s.v1d.size()*sizeof(float));
+	for(size_t i = 0; i < s.shuf.size(); ++i) shuffled[i] = s.shuf[i];
+	return s.ncache;
+}
+float orc_filter(int which, float x, float y, float xw, float yw) { return filterEval(which, x, y, xw, yw); }
+void orc_invbilinear(const float* v, float px, float py, float* uv)
+{
+	InvBilinear inv;
+	inv.setVertices(V2{v[0], v[1]}, V2{v[2], v[3]}, V2{v[4], v[5]}, V2{v[6], v[7]});
+	V2 r = inv(V2{px, py});
+	uv[0] = r.x; uv[1] = r.y;
+}
+float orc_bilerp(float a, float b, float c, float d, float u, float v) { return bilerp(a, b, c, d, V2{u, v}); }
+int orc_filter_table(const AqhFrameParams* p, float* table)
+{
+	Frame f; f.p = *p; setupLayout(f);
+	initialiseFilterValues(f);
+	std::memcpy(table, f.filterValues.data(), f.filterValues.size()*sizeof(float));
+	return int(f.filterValues.size());
+}
+int orc_replay(const AqhFrameParams* pp, uint8_t* planes, float* dither, int* sx0, int* sy0, int* sw, int* sh)
+{
+	Frame f; f.p = *pp; setupLayout(f);
+	const AqhFrameParams& p = f.p;
+	*sx0 = f.sx0; *sy0 = f.sy0; *sw = f.sw; *sh = f.sh;
+	if(!planes) return AQH_OK;
+	g_rng.init(p.rng_seed);
+	for(uint32_t i = 0; i < p.rng_predraws; ++i) g_rng.next();
+	Sampler s;
+	buildJitterSampler(s, f.xs, f.ys);
+	size_t plane = size_t(f.sw)*f.sh;
+	std::memset(planes, 0, 5*plane);
+	for(int row = f.by0; row < f.by1; ++row)
+		for(int col = f.bx0; col < f.bx1; ++col)
+		{
+			int xPos = col*p.bucket_xsize, yPos = row*p.bucket_ysize;
+			int xSize = std::min(p.bucket_xsize, p.xres - xPos), ySize = std::min(p.bucket_ysize, p.yres - yPos);
+			int sminx = std::max(xPos - f.shiftX, p.crop_xmin - f.shiftX), sminy = std::max(yPos - f.shiftY, p.crop_ymin - f.shiftY);
+			int smaxx = std::min(xPos + xSize + f.shiftX, p.crop_xmax + f.shiftX), smaxy = std::min(yPos + ySize + f.shiftY, p.crop_ymax + f.shiftY);
+			if(col > f.bx0) sminx += 2*f.shiftX;
+			if(row > f.by0) sminy += 2*f.shiftY;
+			if(p.jitter)
+				for(int y = sminy; y < smaxy; ++y)
+					for(int x = sminx; x < smaxx; ++x)
+						for(int k = 0; k < 5; ++k)
+							planes[k*plane + size_t(y - f.sy0)*f.sw + (x - f.sx0)] = uint8_t(g_rng.randomInt(250));
+			for(int d = 0; d < p.n_displays; ++d)
+				for(int y = 0; y < ySize; ++y)
+					for(int x = 0; x < xSize; ++x)
+					{
+						float v = g_rng.randomFloat();
+						if(dither) dither[(size_t(d)*p.yres + yPos + y)*p.xres + xPos + x] = v;
+					}
+		}
+	return AQH_OK;
+}
+void orc_dof_bounds(int xs, int ys, float* out)
+{
+	std::vector<Bound> b;
+	calculateDofBounds(xs, ys, b);
+	for(size_t i = 0; i < b.size(); ++i)
+	{
+		out[4*i] = b[i].mn.x; out[4*i+1] = b[i].mn.y; out[4*i+2] = b[i].mx.x; out[4*i+3] = b[i].mx.y;
+	}
+}
+
+} // extern "C"

@@ -1,0 +1,33 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def native_lib():
+    """The product library, built in-tree if needed (nvcc cross-compiles without a GPU)."""
+    from aqsis_b200 import build
+    build.build()
+    from aqsis_b200 import hider
+    return hider.lib()
+
+
+@pytest.fixture(scope="session")
+def gpu_hider(native_lib):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from aqsis_b200 import Hider
+    h = Hider(0)
+    yield h
+    h.close()

@@ -1,0 +1,117 @@
+"""ctypes face of the CPU oracle (oracle/oracle_hider.h).  TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product (aqsis_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from aqsis_b200 import _abi as abi
+from aqsis_b200._abi import FrameParams, GridBlock, DisplayDesc, OrcStats
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_LIB = os.path.join(ORACLE_DIR, "_build", "liboracle_hider.so")
+REF_LIB = os.path.join(ORACLE_DIR, "_ref", "libaqsis_refleaf.so")
+_lib = None
+_ref = None
+
+
+def build_oracle():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR, "oracle"], check=True, capture_output=True)
+    return ORACLE_LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        src = os.path.join(ORACLE_DIR, "oracle_hider.cpp")
+        if not os.path.exists(ORACLE_LIB) or os.path.getmtime(ORACLE_LIB) < os.path.getmtime(src):
+            build_oracle()
+        L = C.CDLL(ORACLE_LIB)
+        vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+        L.orc_render.argtypes = [C.POINTER(FrameParams), C.POINTER(GridBlock), vp, C.POINTER(vp), ci, C.POINTER(OrcStats)]
+        L.orc_display_entrysize.argtypes = [C.POINTER(DisplayDesc), C.POINTER(ci)]
+        L.orc_random_reseed.argtypes = [C.c_uint32]
+        L.orc_random_reseed.restype = None
+        L.orc_random_uint.restype = C.c_uint32
+        L.orc_random_float.restype = cf
+        L.orc_random_int.argtypes = [C.c_uint32]
+        L.orc_random_int.restype = C.c_uint32
+        L.orc_sampler_tables.argtypes = [ci, ci, ci, vp, vp, vp]
+        L.orc_filter.argtypes = [ci, cf, cf, cf, cf]
+        L.orc_filter.restype = cf
+        L.orc_invbilinear.argtypes = [vp, cf, cf, vp]
+        L.orc_invbilinear.restype = None
+        L.orc_bilerp.argtypes = [cf] * 6
+        L.orc_bilerp.restype = cf
+        L.orc_filter_table.argtypes = [C.POINTER(FrameParams), vp]
+        L.orc_replay.argtypes = [C.POINTER(FrameParams), vp, vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]
+        L.orc_dof_bounds.argtypes = [ci, ci, vp]
+        L.orc_dof_bounds.restype = None
+        _lib = L
+    return _lib
+
+
+def ref():
+    """The reference's own leaf sources compiled in place (None when oracle/_ref is absent)."""
+    global _ref
+    if _ref is None:
+        if not os.path.exists(REF_LIB):
+            if os.path.isdir("/root/reference/libs/core"):
+                subprocess.run(["make", "-s", "-C", ORACLE_DIR, "ref"], check=True, capture_output=True)
+            if not os.path.exists(REF_LIB):
+                return None
+        L = C.CDLL(REF_LIB)
+        vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+        L.ref_random_reseed.argtypes = [C.c_uint]
+        L.ref_random_reseed.restype = None
+        L.ref_random_uint.restype = C.c_uint
+        L.ref_random_float.restype = cf
+        L.ref_random_int.argtypes = [C.c_uint]
+        L.ref_random_int.restype = C.c_uint
+        L.ref_sampler_create.argtypes = [ci, ci, ci]
+        L.ref_sampler_create.restype = vp
+        L.ref_sampler_destroy.argtypes = [vp]
+        L.ref_sampler_destroy.restype = None
+        L.ref_sampler_draw.argtypes = [vp] * 6
+        L.ref_sampler_draw.restype = None
+        L.ref_filter.argtypes = [ci, cf, cf, cf, cf]
+        L.ref_filter.restype = cf
+        L.ref_invbilinear.argtypes = [vp, cf, cf, vp]
+        L.ref_invbilinear.restype = None
+        L.ref_bilerp.argtypes = [cf] * 6
+        L.ref_bilerp.restype = cf
+        L.ref_lfloor.argtypes = [C.c_double]
+        L.ref_lfloor.restype = C.c_long
+        L.ref_lceil.argtypes = [C.c_double]
+        L.ref_lceil.restype = C.c_long
+        L.ref_lround.argtypes = [C.c_double]
+        L.ref_lround.restype = C.c_long
+        L.ref_bound_contains2d.argtypes = [vp, cf, cf]
+        L.ref_bound_intersects.argtypes = [vp, cf, cf, cf, cf]
+        _ref = L
+    return _ref
+
+
+def render(params: FrameParams, grids, nthreads=1):
+    """Run the oracle. Returns (channels[yres,xres,9], [display arrays], stats dict)."""
+    from aqsis_b200.hider import display_info
+    L = lib()
+    b = grids.as_struct()
+    assert b.memory_space == 0
+    ch = np.zeros((params.yres, params.xres, 9), dtype=np.float32)
+    outs, ptrs = [], (C.c_void_p * max(1, params.n_displays))()
+    for d in range(params.n_displays):
+        dt, nch, es = display_info(params, d)
+        a = np.zeros((params.yres, params.xres, nch), dtype=dt)
+        outs.append(a)
+        ptrs[d] = a.ctypes.data
+    st = OrcStats()
+    rc = L.orc_render(C.byref(params), C.byref(b), ch.ctypes.data, ptrs, int(nthreads), C.byref(st))
+    if rc:
+        raise RuntimeError(f"orc_render failed: {abi.STATUS_NAMES.get(rc, rc)}")
+    return ch, outs, st.as_dict()
