@@ -35,6 +35,7 @@ GRID_CAMERA_SPACE = 1 << 4
 GRID_USES_CSG = 1 << 5
 
 MAX_DISPLAYS = 8
+FILTER_REFERENCE_ORDER, FILTER_TILE_PARTIALS = 0, 1
 MAX_DISPLAY_CHANNELS = 16
 
 FilterFunc = C.CFUNCTYPE(C.c_float, C.c_float, C.c_float, C.c_float, C.c_float)
@@ -83,7 +84,8 @@ class FrameParams(C.Structure):
         ("rank", C.c_int32), ("world_size", C.c_int32),
         ("strip_rows", C.c_int32),
         ("deep_hits_per_sample", C.c_int32),
-        ("reserved", C.c_int32 * 8),
+        ("filter_mode", C.c_int32),
+        ("reserved", C.c_int32 * 7),
     ]
 
 

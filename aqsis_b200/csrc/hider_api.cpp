@@ -130,7 +130,7 @@ struct AqhHider
 	DevBuf dPraw, dCi, dOi, dCulled, dP4, dGrids, dChunk, dKeyTimes, dSplit;
 	DevBuf dPosTab, dVal1d, dShuf, dPat, dFilt, dDofB, dDither;
 	DevBuf dTileSlot, dActive, dBinCount, dBinOffset, dBinEntries, dMisc, dTileFlags;
-	DevBuf dPlanes, dMask, dDeepA, dDeepUV, dChannels, dRowOwned;
+	DevBuf dPlanes, dMask, dPartials, dDeepA, dDeepUV, dChannels, dRowOwned;
 	DevBuf dDisplay[AQH_MAX_DISPLAYS];
 	// tiling
 	int tileW = 0, tileH = 0, ntx = 0, nty = 0;
@@ -190,6 +190,10 @@ int validateParams(AqhHider* h, const AqhFrameParams& p)
 	}
 	if(p.depth_filter != AQH_DEPTHFILTER_MIN)
 		return h->fail(AQH_ERR_UNSUPPORTED, "only depthfilter \"min\" is implemented on the device");
+	if(p.filter_mode != AQH_FILTER_TILE_PARTIALS && p.filter_mode != AQH_FILTER_REFERENCE_ORDER)
+		return h->fail(AQH_ERR_BAD_PARAMS, "filter_mode");
+	if(p.filter_xwidth >= 16.f || p.filter_ywidth >= 16.f)
+		return h->fail(AQH_ERR_BAD_PARAMS, "filter widths must be below 16");
 	if(p.world_size < 0 || (p.world_size > 0 && (p.rank < 0 || p.rank >= p.world_size)))
 		return h->fail(AQH_ERR_BAD_PARAMS, "rank/world_size");
 	if(p.use_dof && !(p.dof_one_over_focal_distance != 0.f))
@@ -387,8 +391,14 @@ int renderFrame(AqhHider* h, bool download)
 	CU(h->dMisc.reserve(256), "cudaMalloc(counters)");
 	CU(h->dRowOwned.reserve(p.yres), "cudaMalloc(row ownership)");
 	const size_t planeStride = size_t(L.sw)*L.sh*(p.xsamples*p.ysamples);
-	CU(h->dPlanes.reserve(planeStride*7*4), "cudaMalloc(sample planes)");
-	CU(h->dMask.reserve(planeStride*4), "cudaMalloc(sample mask plane)");
+	const int ntaps = (2*L.shiftX+1)*(2*L.shiftY+1);
+	if(p.filter_mode == AQH_FILTER_REFERENCE_ORDER)
+	{
+		CU(h->dPlanes.reserve(planeStride*7*4), "cudaMalloc(sample planes)");
+		CU(h->dMask.reserve(planeStride*4), "cudaMalloc(sample mask plane)");
+	}
+	else
+		CU(h->dPartials.reserve(size_t(ntaps)*9*L.sw*L.sh*4), "cudaMalloc(tap partial sums)");
 	CU(h->dChannels.reserve(size_t(p.xres)*p.yres*9*4), "cudaMalloc(channel buffer)");
 	DevDisplays disp{};
 	disp.n = p.n_displays;
@@ -496,7 +506,7 @@ int renderFrame(AqhHider* h, bool download)
 	f.expGain = p.exposure_gain; f.expGamma = p.exposure_gamma;
 	f.jitter = p.jitter;
 	std::memcpy(f.camToRaster, p.cam_to_raster, sizeof f.camToRaster);
-	f.anyMotion = anyMotion; f.anyTransparent = (dOi != nullptr); f.anyLod = anyLod; f.anyTriangular = anyTri; f.anyCamera = anyCam;
+	f.anyMotion = anyMotion; f.anyTransparent = 0; f.anyLod = anyLod; f.anyTriangular = anyTri; f.anyCamera = anyCam;
 	f.sx0 = L.sx0; f.sy0 = L.sy0; f.sw = L.sw; f.sh = L.sh;
 	f.tileW = h->tileW; f.tileH = h->tileH; f.ntx = h->ntx; f.nty = h->nty; f.nActiveTiles = nActive;
 	f.Praw = dP; f.Ci = dCi; f.Oi = dOi; f.culled = dCulled;
@@ -514,19 +524,9 @@ int renderFrame(AqhHider* h, bool download)
 	f.errorFlags = h->dMisc.as<uint32_t>() + 1;
 	f.counters = reinterpret_cast<unsigned long long*>(h->dMisc.as<unsigned char>() + 16);
 	f.planes = h->dPlanes.as<float>(); f.maskPlane = h->dMask.as<uint32_t>(); f.planeStride = (int64_t)planeStride;
+	f.filterMode = p.filter_mode; f.partials = h->dPartials.as<float>(); f.ntaps = ntaps;
 	f.channels = h->dChannels.as<float>();
 	f.rowOwned = (std::max(1, p.world_size) > 1) ? h->dRowOwned.as<uint8_t>() : nullptr;
-
-	LaunchCfg cfg{};
-	CU(hideKernelConfig(f, h->smCount, cfg), "hide kernel configuration (shared memory / occupancy)");
-	if(f.anyTransparent)
-	{
-		const int per = p.deep_hits_per_sample > 0 ? p.deep_hits_per_sample : 8;
-		f.deepCapPerCta = uint32_t(per)*uint32_t(f.tileW*f.tileH*f.n);
-		CU(h->dDeepA.reserve(size_t(cfg.hideCtas)*f.deepCapPerCta*16), "cudaMalloc(deep hit pool)");
-		CU(h->dDeepUV.reserve(size_t(cfg.hideCtas)*f.deepCapPerCta*8), "cudaMalloc(deep hit pool)");
-		f.deepA = h->dDeepA.as<uint4>(); f.deepUV = h->dDeepUV.as<float2>();
-	}
 
 	// ---- device work
 	S.gpu_launches = 0;
@@ -540,16 +540,30 @@ int renderFrame(AqhHider* h, bool download)
 	CU(launchBinCount(f, st), "k_bin<count>"); S.gpu_launches += nPos ? 1 : 0;
 	CU(launchBinScan(f, st), "k_bin_scan"); S.gpu_launches += 1;
 	// the fill pass needs the total entry count to size the list
-	uint32_t totalEntries = 0;
+	uint32_t totalEntries = 0, devFlags = 0;
 	CU(cudaMemcpyAsync(&totalEntries, f.binOffset + nActive, 4, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(bin total)");
+	CU(cudaMemcpyAsync(&devFlags, f.errorFlags, 4, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(frame flags)");
 	CU(cudaStreamSynchronize(st), "bin count");
 	CU(h->dBinEntries.reserve(std::max<size_t>(totalEntries, 1)*4), "cudaMalloc(bin entries)");
 	f.binEntries = h->dBinEntries.as<uint32_t>();
+	// the project kernel reports whether any vertex is non-opaque: only then does the hide kernel
+	// carry deep-list heads in shared memory and a deep hit pool in HBM
+	f.anyTransparent = (devFlags & 2u) ? 1 : 0;
+	LaunchCfg cfg{};
+	CU(hideKernelConfig(f, h->smCount, cfg), "hide kernel configuration (shared memory / occupancy)");
+	if(f.anyTransparent)
+	{
+		const int per = p.deep_hits_per_sample > 0 ? p.deep_hits_per_sample : 8;
+		f.deepCapPerCta = uint32_t(per)*uint32_t(f.tileW*f.tileH*f.n);
+		CU(h->dDeepA.reserve(size_t(cfg.hideCtas)*f.deepCapPerCta*16), "cudaMalloc(deep hit pool)");
+		CU(h->dDeepUV.reserve(size_t(cfg.hideCtas)*f.deepCapPerCta*8), "cudaMalloc(deep hit pool)");
+		f.deepA = h->dDeepA.as<uint4>(); f.deepUV = h->dDeepUV.as<float2>();
+	}
 	CU(launchBinFill(f, st), "k_bin<fill>"); S.gpu_launches += (nPos ? 1 : 0) + (nActive ? 1 : 0);
 	CU(cudaEventRecord(h->ev[1], st), "cudaEventRecord");
 	CU(launchHide(f, cfg, st), "k_hide"); S.gpu_launches += nActive ? 1 : 0;
 	CU(cudaEventRecord(h->ev[2], st), "cudaEventRecord");
-	CU(launchFilter(f, disp, st), "k_filter"); S.gpu_launches += 1;
+	CU(launchFilter(f, disp, h->filterTab.data(), st), "k_filter"); S.gpu_launches += 1;
 	CU(cudaEventRecord(h->ev[3], st), "cudaEventRecord");
 
 	// ---- results
@@ -623,7 +637,7 @@ int aqh_destroy(AqhHider* h)
 	cudaStreamSynchronize(h->stream);
 	DevBuf* bufs[] = {&h->dPraw, &h->dCi, &h->dOi, &h->dCulled, &h->dP4, &h->dGrids, &h->dChunk, &h->dKeyTimes, &h->dSplit,
 	                  &h->dPosTab, &h->dVal1d, &h->dShuf, &h->dPat, &h->dFilt, &h->dDofB, &h->dDither, &h->dTileSlot, &h->dActive,
-	                  &h->dBinCount, &h->dBinOffset, &h->dBinEntries, &h->dMisc, &h->dTileFlags, &h->dPlanes, &h->dMask,
+	                  &h->dBinCount, &h->dBinOffset, &h->dBinEntries, &h->dMisc, &h->dTileFlags, &h->dPlanes, &h->dMask, &h->dPartials,
 	                  &h->dDeepA, &h->dDeepUV, &h->dChannels, &h->dRowOwned};
 	for(DevBuf* b : bufs) b->release();
 	for(int d = 0; d < AQH_MAX_DISPLAYS; ++d) { h->dDisplay[d].release(); h->hDisplay[d].release(); }
@@ -671,6 +685,7 @@ int aqh_frame_params_default(AqhFrameParams* p)
 	p->rng_predraws = 0;
 	p->n_displays = 0;
 	p->rank = 0; p->world_size = 1;
+	p->filter_mode = AQH_FILTER_REFERENCE_ORDER;
 	return AQH_OK;
 }
 

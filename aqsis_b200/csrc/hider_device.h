@@ -84,6 +84,11 @@ struct DevFrame
 	float* planes;                 // 7 planes: R G B Or Og Ob Z
 	uint32_t* maskPlane;           // bits 0-14 x-tap inclusion, 15-29 y-tap inclusion, 31 valid
 	int64_t planeStride;           // n*sw*sh
+	// tile-partials filter mode: per (tap, value, y, x) partial sums over a pixel's samples;
+	// values: 0 gTot, 1 hit count, 2..8 R G B Or Og Ob Z
+	int filterMode;                // AQH_FILTER_*
+	float* partials;               // ntaps*9 planes of sw*sh
+	int ntaps;                     // (2*shiftX+1)*(2*shiftY+1)
 	// deep (transparent) hit pool, per persistent CTA
 	uint4* deepA;                  // next, depth bits, p, sample index
 	float2* deepUV;
@@ -125,7 +130,7 @@ cudaError_t launchBinCount(const DevFrame& f, cudaStream_t st);
 cudaError_t launchBinScan(const DevFrame& f, cudaStream_t st);
 cudaError_t launchBinFill(const DevFrame& f, cudaStream_t st);
 cudaError_t launchHide(const DevFrame& f, const LaunchCfg& cfg, cudaStream_t st);
-cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, cudaStream_t st);
+cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, const float* hostFilterTab, cudaStream_t st);
 cudaError_t hideKernelConfig(const DevFrame& f, int smCount, LaunchCfg& cfg);
 int kernelsArchOk();   // 1 when the loaded kernel image can run on the current device
 

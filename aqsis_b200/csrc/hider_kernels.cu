@@ -121,6 +121,9 @@ __global__ void __launch_bounds__(256) k_project(DevFrame f)
 		bool valid = (iu < cu) && (iv < cv) && !(f.culled && f.culled[vid]);
 		if(opaque) info |= VINFO_OPAQUE;
 		if(valid) info |= VINFO_MP_VALID;
+		// frame-level "there is transparency" flag: read before the atomic so that only the first
+		// few non-opaque vertices pay for one
+		if(!opaque && !(*(volatile uint32_t*)f.errorFlags & 2u)) atomicOr(f.errorFlags, 2u);
 	}
 	f.P4[i] = make_float4(x, y, z, __uint_as_float(info));
 }
@@ -190,11 +193,15 @@ template<bool FILL>
 __global__ void __launch_bounds__(256) k_bin(DevFrame f)
 {
 	const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
-	if(p >= f.nPos) return;
-	const float4 a = f.P4[p];
 	TileRange tr;
-	if(!mpTileRange(f, p, a, tr)) return;
-	unsigned long long nent = 0;
+	bool live = p < f.nPos;
+	if(live)
+	{
+		const float4 a = f.P4[p];
+		live = mpTileRange(f, p, a, tr);
+	}
+	unsigned nent = 0;
+	if(live)
 	for(int ty = tr.ty0; ty <= tr.ty1; ++ty)
 		for(int tx = tr.tx0; tx <= tr.tx1; ++tx)
 		{
@@ -211,10 +218,16 @@ __global__ void __launch_bounds__(256) k_bin(DevFrame f)
 				++nent;
 			}
 		}
-	if(!FILL && nent)
+	if(!FILL)
 	{
-		atomicAdd(&f.counters[0], 1ull);
-		atomicAdd(&f.counters[1], nent);
+		// statistics: one atomic per warp, not per thread
+		unsigned nmp = __popc(__ballot_sync(0xffffffffu, nent != 0));
+		unsigned tot = __reduce_add_sync(0xffffffffu, nent);
+		if((threadIdx.x & 31) == 0 && tot)
+		{
+			atomicAdd(&f.counters[0], (unsigned long long)nmp);
+			atomicAdd(&f.counters[1], (unsigned long long)tot);
+		}
 	}
 }
 
@@ -449,9 +462,14 @@ __device__ __forceinline__ void shadeHit(const DevFrame& f, const GridRec& g, ui
 }
 
 // ------------------------------------------------------------------------------------
-// Shared-memory layout of the hide kernel (dynamic):
-//   u64 keys[ns] | float2 pos[ns] | [float time[ns]] | [float2 dof[ns]] | [u32 head[ns]] |
-//   StaticRec recs[batch] | u16 colIdx[tileW*xs] | u16 rowIdx[tileH*ys] | u8 shufPat[tileW*tileH]
+// Shared-memory layout of the hide kernel (dynamic).  The samples of a tile live in a padded
+// SUB-SAMPLE GRID: row gy = py*ys + sy, column gx = px*xs + sx, idx = gy*stride + gx with
+// stride = tileW*xs + SMEM_PAD, so that the candidate rectangle of a micropolygon is a plain 2-D
+// window (no per-candidate table lookups) and consecutive lanes touch consecutive banks.
+//   u64 keys[nsP] | f32 posx[nsP] | f32 posy[nsP] | [f32 time[nsP]] | [float2 dof[nsP]] | [u32 head[nsP]] |
+//   StaticRec recs[nwarps*RECS_PER_WARP] | u16 subOfs[n] | u8 shufPat[tileW*tileH]
+#define SMEM_PAD 8
+#define RECS_PER_WARP 16
 struct StaticRec   // 36 words
 {
 	float X[4], Y[4], XM[4], YM[4];
@@ -469,52 +487,62 @@ struct TileCtx
 {
 	int tileX0, tileY0;        // global pixel of the tile origin
 	int rx0, ry0, rx1, ry1;    // tile ∩ sample region (global pixels)
-	int ns;                    // samples in the tile (tileW*tileH*n)
 };
 
 struct HideSmem
 {
 	unsigned long long* keys;
-	float2* pos;
+	float* posx;
+	float* posy;
 	float* time;
 	float2* dof;
 	uint32_t* head;
 	StaticRec* recs;
-	uint16_t* colIdx;
-	uint16_t* rowIdx;
+	uint16_t* subOfs;          // sample index i -> (i / xs)*stride + i % xs
 	uint8_t* shufPat;
+	int stride, nsP;
 };
 
-__device__ __forceinline__ HideSmem carveSmem(const DevFrame& f, unsigned char* base, int batch)
+__host__ __device__ __forceinline__ int hideStride(const DevFrame& f) { return f.tileW*f.xs + SMEM_PAD; }
+
+__device__ __forceinline__ HideSmem carveSmem(const DevFrame& f, unsigned char* base, int nrecs)
 {
 	HideSmem s;
-	const int ns = f.tileW*f.tileH*f.n;
+	s.stride = hideStride(f);
+	s.nsP = f.tileH*f.ys*s.stride;
+	const size_t ns = (size_t)s.nsP;
 	size_t o = 0;
-	s.keys = (unsigned long long*)(base + o); o += (size_t)ns*8;
-	s.pos = (float2*)(base + o); o += (size_t)ns*8;
+	s.keys = (unsigned long long*)(base + o); o += ns*8;
+	s.posx = (float*)(base + o); o += ns*4;
+	s.posy = (float*)(base + o); o += ns*4;
 	s.dof = 0; s.time = 0; s.head = 0;
-	if(f.useDof) { s.dof = (float2*)(base + o); o += (size_t)ns*8; }
-	if(f.anyMotion) { s.time = (float*)(base + o); o += (size_t)ns*4; }
-	if(f.anyTransparent) { s.head = (uint32_t*)(base + o); o += (size_t)ns*4; }
+	if(f.useDof) { s.dof = (float2*)(base + o); o += ns*8; }
+	if(f.anyMotion) { s.time = (float*)(base + o); o += ns*4; }
+	if(f.anyTransparent) { s.head = (uint32_t*)(base + o); o += ns*4; }
 	o = (o + 15) & ~(size_t)15;
-	s.recs = (StaticRec*)(base + o); o += (size_t)batch*sizeof(StaticRec);
-	s.colIdx = (uint16_t*)(base + o); o += (size_t)f.tileW*f.xs*2;
-	s.rowIdx = (uint16_t*)(base + o); o += (size_t)f.tileH*f.ys*2;
+	s.recs = (StaticRec*)(base + o); o += (size_t)nrecs*sizeof(StaticRec);
+	s.subOfs = (uint16_t*)(base + o); o += (size_t)f.n*2;
 	s.shufPat = (uint8_t*)(base + o);
 	return s;
 }
 
-static size_t hideSmemBytes(const DevFrame& f, int batch)
+static size_t hideSmemBytes(const DevFrame& f, int nrecs)
 {
-	const size_t ns = (size_t)f.tileW*f.tileH*f.n;
+	const size_t ns = (size_t)f.tileH*f.ys*hideStride(f);
 	size_t o = ns*16;
 	if(f.useDof) o += ns*8;
 	if(f.anyMotion) o += ns*4;
 	if(f.anyTransparent) o += ns*4;
 	o = (o + 15) & ~(size_t)15;
-	o += (size_t)batch*sizeof(StaticRec);
-	o += (size_t)f.tileW*f.xs*2 + (size_t)f.tileH*f.ys*2 + (size_t)f.tileW*f.tileH;
+	o += (size_t)nrecs*sizeof(StaticRec);
+	o += (size_t)f.n*2 + (size_t)f.tileW*f.tileH;
 	return (o + 15) & ~(size_t)15;
+}
+
+// sample index of (pixel-local x, y, i) in the padded sub-sample grid
+__device__ __forceinline__ int sampleIdx(const DevFrame& f, const HideSmem& s, int plx, int ply, int i)
+{
+	return (ply*f.ys)*s.stride + plx*f.xs + s.subOfs[i];
 }
 
 // Deposit a hit: opaque hits race for the per-sample (depth, order) minimum; transparent ones
@@ -542,6 +570,17 @@ __device__ __forceinline__ void storeDeep(const DevFrame& f, const DeepCtx& dc, 
 	uint32_t next = atomicExch(&s.head[idx], slot);
 	dc.A[slot] = make_uint4(next, __float_as_uint(D), p, (uint32_t)idx);
 	dc.UV[slot] = uv;
+}
+
+// sample level of detail = lods[i] of the pixel's lod pattern (imagepixel.cpp:356)
+__device__ __forceinline__ float sampleLod(const DevFrame& f, const TileCtx& t, const HideSmem& s, int idx)
+{
+	const int gy = idx / s.stride, gx = idx - gy*s.stride;
+	const int plx = gx / f.xs, ply = gy / f.ys;
+	const int i = (gy - ply*f.ys)*f.xs + (gx - plx*f.xs);
+	const int gxp = t.tileX0 + plx - f.sx0, gyp = t.tileY0 + ply - f.sy0;
+	const int pat = f.patPlanes[(size_t)4*f.sw*f.sh + (size_t)gyp*f.sw + gxp];
+	return f.val1d[(size_t)pat*f.n + i];
 }
 
 // ---- static micropolygons, no depth of field: RenderMPG_Static (bucketprocessor.cpp:1097-1218)
@@ -606,39 +645,37 @@ __device__ __forceinline__ void sampleStaticRec(const DevFrame& f, const TileCtx
 	const uint32_t rect = r.rect;
 	if(rect == 0) return;
 	const int gx0 = rect & 0xff, gx1 = (rect >> 8) & 0xff, gy0 = (rect >> 16) & 0xff, gy1 = rect >> 24;
-	const int W = gx1 - gx0, H = gy1 - gy0, total = W*H;
-	const float invW = 1.0f / (float)W;
+	const int W = gx1 - gx0, total = W*(gy1 - gy0);
+	// lanes walk the window in row-major order, 32 candidates per step
+	const int dy = 32 / W, dx = 32 - dy*W;
+	int cy = lane / W, cx = lane - cy*W;
 	const float bminx = r.bminx, bminy = r.bminy, bmaxx = r.bmaxx, bmaxy = r.bmaxy;
 	const uint32_t zminKey = r.zminKey;
+	const int stride = s.stride;
 	for(int k = lane; k < total; k += 32)
 	{
-		int cy = (int)(((float)k + 0.5f) * invW);
-		int cx = k - cy*W;
-		if(cx < 0) { cy -= 1; cx += W; } else if(cx >= W) { cy += 1; cx -= W; }
-		const int idx = s.rowIdx[gy0 + cy] + s.colIdx[gx0 + cx];
-		const float2 pos = s.pos[idx];
+		const int idx = (gy0 + cy)*stride + gx0 + cx;
+		cx += dx; cy += dy;
+		if(cx >= W) { cx -= W; cy += 1; }
+		const float x = s.posx[idx], y = s.posy[idx];
 		// Bound.Contains2D, bound.h:144-151
-		if((pos.x < bminx || pos.x > bmaxx) || (pos.y < bminy || pos.y > bmaxy)) continue;
+		if((x < bminx || x > bmaxx) || (y < bminy || y > bmaxy)) continue;
 		// occlusion cull against the current opaque depth (bucketprocessor.cpp:1179)
 		const uint32_t occl = (uint32_t)(s.keys[idx] >> 32);
 		if(zminKey > occl) continue;
-		if(!edgeTests(r.X, r.Y, r.XM, r.YM, pos.x, pos.y)) continue;
-		const float2 uv = invBilinear(r.Ax, r.Ay, r.Ex, r.Ey, r.Fx, r.Fy, r.Gx, r.Gy, (r.flags & REC_LINEAR) ? 1 : 0, pos.x, pos.y);
+		if(!edgeTests(r.X, r.Y, r.XM, r.YM, x, y)) continue;
+		const float2 uv = invBilinear(r.Ax, r.Ay, r.Ex, r.Ey, r.Fx, r.Fy, r.Gx, r.Gy, (r.flags & REC_LINEAR) ? 1 : 0, x, y);
 		const float D = bilerpZ(r.z, uv);
 		if(r.flags & REC_RARE)
 		{
 			const GridRec g = f.grids[r.flags & VINFO_GRID_MASK];
 			if(g.lod0 >= 0.0f)
 			{
-				// sample level of detail = lods[i] of the pixel's lod pattern (imagepixel.cpp:356)
-				const int pixLocal = idx / f.n, i = idx - pixLocal*f.n;
-				const int gxp = t.tileX0 + pixLocal % f.tileW - f.sx0, gyp = t.tileY0 + pixLocal / f.tileW - f.sy0;
-				const int pat = f.patPlanes[(size_t)4*f.sw*f.sh + (size_t)gyp*f.sw + gxp];
-				const float lod = f.val1d[(size_t)pat*f.n + i];
+				const float lod = sampleLod(f, t, s, idx);
 				if(g.lod0 > lod || lod >= g.lod1) continue;
 			}
 			if(g.flags & AQH_GRID_TRIANGULAR)
-				if(triangleSplitReject(f, g, pos, make_float2(0.f, 0.f), D, 0.0f)) continue;
+				if(triangleSplitReject(f, g, make_float2(x, y), make_float2(0.f, 0.f), D, 0.0f)) continue;
 		}
 		if(OPAQUE)
 			storeOpaque(&s.keys[idx], D, r.p);
@@ -753,14 +790,6 @@ __device__ bool samplePoints(const DevFrame& f, const MovingMP& m, bool moving, 
 	return true;
 }
 
-__device__ __forceinline__ float sampleLod(const DevFrame& f, const TileCtx& t, int idx)
-{
-	const int pixLocal = idx / f.n, i = idx - pixLocal*f.n;
-	const int gxp = t.tileX0 + pixLocal % f.tileW - f.sx0, gyp = t.tileY0 + pixLocal / f.tileW - f.sy0;
-	const int pat = f.patPlanes[(size_t)4*f.sw*f.sh + (size_t)gyp*f.sw + gxp];
-	return f.val1d[(size_t)pat*f.n + i];
-}
-
 // One candidate (micropolygon, sample) of the MB/DoF path, after the reference's gates.
 template<bool OPAQUE>
 __device__ __forceinline__ void testCandidateMBDof(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc,
@@ -768,7 +797,7 @@ __device__ __forceinline__ void testCandidateMBDof(const DevFrame& f, const Tile
                                                    int idx, float bzminKeyf /*unused*/, uint32_t zminKey,
                                                    float bminx, float bminy, float bmaxx, float bmaxy, float time0, float time1)
 {
-	const float2 pos = s.pos[idx];
+	const float2 pos = make_float2(s.posx[idx], s.posy[idx]);
 	const float time = s.time ? s.time[idx] : f.shutterOpen;
 	if(moving && (time < time0 || time > time1)) return;
 	if((pos.x < bminx || pos.x > bmaxx) || (pos.y < bminy || pos.y > bmaxy)) return;
@@ -776,7 +805,7 @@ __device__ __forceinline__ void testCandidateMBDof(const DevFrame& f, const Tile
 	if(zminKey > occl) return;
 	if(m.g.lod0 >= 0.0f)
 	{
-		float lod = sampleLod(f, t, idx);
+		float lod = sampleLod(f, t, s, idx);
 		if(m.g.lod0 > lod || lod >= m.g.lod1) return;
 	}
 	const float2 dofOff = s.dof ? s.dof[idx] : make_float2(0.f, 0.f);
@@ -930,7 +959,8 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 						const int pixLocal = (iY - t.tileY0)*f.tileW + (iX - t.tileX0);
 						// GetDofOffsetIndex(cell) = shuffledIndices[cell] of the pixel's shuffle pattern
 						const int index = f.shufTab[(size_t)s.shufPat[pixLocal]*n + cell];
-						testCandidateMBDof<OPAQUE>(f, t, s, dc, m, moving, mpBound, cocMin, cocMax, pixLocal*n + index,
+						testCandidateMBDof<OPAQUE>(f, t, s, dc, m, moving, mpBound, cocMin, cocMax,
+						                           sampleIdx(f, s, iX - t.tileX0, iY - t.tileY0, index),
 						                           0.f, zminKey, bminx, bminy, bmaxx, bmaxy, time0, time1);
 					}
 			}
@@ -951,8 +981,8 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 			{
 				const int pi = k / cnt, j = k - pi*cnt;
 				const int iY = sY + pi / Wp, iX = sX + pi % Wp;
-				const int pixLocal = (iY - t.tileY0)*f.tileW + (iX - t.tileX0);
-				testCandidateMBDof<OPAQUE>(f, t, s, dc, m, moving, mpBound, cocMin, cocMax, pixLocal*n + indexT0 + j,
+				testCandidateMBDof<OPAQUE>(f, t, s, dc, m, moving, mpBound, cocMin, cocMax,
+				                           sampleIdx(f, s, iX - t.tileX0, iY - t.tileY0, indexT0 + j),
 				                           0.f, zminKey, bminx, bminy, bmaxx, bmaxy, time0, time1);
 			}
 		}
@@ -981,7 +1011,7 @@ __device__ void resolveSample(const DevFrame& f, const TileCtx& t, const HideSme
 	const unsigned long long key = s.keys[idx];
 	const uint32_t p = (uint32_t)key;
 	const bool haveOpaque = (p != 0xffffffffu);
-	const float2 pos = s.pos[idx];
+	const float2 pos = make_float2(s.posx[idx], s.posy[idx]);
 	float col[3] = {0.f, 0.f, 0.f}, opa[3] = {0.f, 0.f, 0.f};
 	float depth = 0.f;
 	bool opaqueMatte = false;
@@ -1068,29 +1098,53 @@ __device__ void resolveSample(const DevFrame& f, const TileCtx& t, const HideSme
 	out[6] = opaqueDepth0;
 }
 
+// Per-tap inclusion bits of one sample (bucketprocessor.cpp:609-612), evaluated with the true
+// pixel coordinates: the sample of pixel (X,Y) belongs to filter tap (fx,fy) of output pixel
+// (X-fx, Y-fy).  Bits 0-14: x taps, 15-29: y taps, 31: the sample holds a valid hit.
+__device__ __forceinline__ uint32_t tapMask(const DevFrame& f, float posx, float posy, int X, int Y, bool valid)
+{
+	uint32_t mask = valid ? 0x80000000u : 0u;
+	for(int fx = -f.shiftX; fx <= f.shiftX; ++fx)
+	{
+		float vx = posx - ((float)(X - fx) + 0.5f);
+		if(vx >= -f.xfwo2 && vx <= f.xfwo2) mask |= 1u << (fx + f.shiftX);
+	}
+	for(int fy = -f.shiftY; fy <= f.shiftY; ++fy)
+	{
+		float vy = posy - ((float)(Y - fy) + 0.5f);
+		if(vy >= -f.yfwo2 && vy <= f.yfwo2) mask |= 1u << (15 + fy + f.shiftY);
+	}
+	return mask;
+}
+
 // ------------------------------------------------------------------------------------
-// k_hide: persistent CTAs pull tiles from a counter.
-template<bool MBDOF>
-__global__ void __launch_bounds__(256, 2) k_hide(DevFrame f, int batch)
+// k_hide: persistent CTAs pull tiles from a counter.  Inside a tile every warp runs its own
+// pipeline -- grab RECS_PER_WARP micropolygons of the tile's bin, set them up (one lane each,
+// records in the warp's shared-memory slots), then sample them one after the other with all 32
+// lanes -- so there is no CTA-wide barrier inside the micropolygon loop.
+template<bool MBDOF, int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevFrame f)
 {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
 	__shared__ uint32_t s_tile;
 	__shared__ uint32_t s_deepCount;
-	const HideSmem s = carveSmem(f, smemRaw, batch);
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-	const int n = f.n, xs = f.xs;
+	__shared__ uint32_t s_next;
+	constexpr int NWARPS = THREADS/32;
+	const HideSmem s = carveSmem(f, smemRaw, NWARPS*RECS_PER_WARP);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int n = f.n, xs = f.xs, ys = f.ys;
+	const int rowLen = f.tileW*xs;
+	StaticRec* myRecs = s.recs + warp*RECS_PER_WARP;
 	DeepCtx dc;
 	dc.A = f.deepA + (size_t)blockIdx.x*f.deepCapPerCta;
 	dc.UV = f.deepUV + (size_t)blockIdx.x*f.deepCapPerCta;
 	dc.cap = f.deepCapPerCta;
 	dc.count = &s_deepCount;
-	// sub-sample -> sample index tables (pixel-major sample layout: idx = pixel*n + i)
-	for(int gx = tid; gx < f.tileW*xs; gx += blockDim.x) s.colIdx[gx] = (uint16_t)((gx / xs)*n + gx % xs);
-	for(int gy = tid; gy < f.tileH*f.ys; gy += blockDim.x) s.rowIdx[gy] = (uint16_t)((gy / f.ys)*f.tileW*n + (gy % f.ys)*xs);
+	for(int i = tid; i < n; i += THREADS) s.subOfs[i] = (uint16_t)((i / xs)*s.stride + i % xs);
 	for(;;)
 	{
 		__syncthreads();
-		if(tid == 0) { s_tile = atomicAdd(f.tileCursor, 1u); s_deepCount = 0; }
+		if(tid == 0) { s_tile = atomicAdd(f.tileCursor, 1u); s_deepCount = 0; s_next = 0; }
 		__syncthreads();
 		const uint32_t slot = s_tile;
 		if(slot >= (uint32_t)f.nActiveTiles) break;
@@ -1101,21 +1155,23 @@ __global__ void __launch_bounds__(256, 2) k_hide(DevFrame f, int batch)
 		t.rx0 = t.tileX0; t.ry0 = t.tileY0;
 		t.rx1 = min(t.tileX0 + f.tileW, f.sx0 + f.sw);
 		t.ry1 = min(t.tileY0 + f.tileH, f.sy0 + f.sh);
-		t.ns = f.tileW*f.tileH*n;
 		// ---- Prepare_bucket: CqImagePixel::clear + setSamples (imagepixel.cpp:105-122, 334-359)
-		for(int idx = tid; idx < t.ns; idx += blockDim.x)
+		for(int idx = tid; idx < s.nsP; idx += THREADS)
 		{
-			const int pixLocal = idx / n, i = idx - pixLocal*n;
-			const int X = t.tileX0 + pixLocal % f.tileW, Y = t.tileY0 + pixLocal / f.tileW;
+			const int gy = idx / s.stride, gx = idx - gy*s.stride;
+			const int plx = gx / xs, ply = gy / ys;
+			const int X = t.tileX0 + plx, Y = t.tileY0 + ply;
 			s.keys[idx] = KEY_EMPTY;
 			if(s.head) s.head[idx] = 0xffffffffu;
-			if(X < t.rx1 && Y < t.ry1)
+			if(gx < rowLen && X < t.rx1 && Y < t.ry1)
 			{
+				const int i = (gy - ply*ys)*xs + (gx - plx*xs);
 				const size_t pp = (size_t)(Y - f.sy0)*f.sw + (X - f.sx0);
 				const size_t plane = (size_t)f.sw*f.sh;
 				const int patPos = f.patPlanes[plane + pp];
 				const float2 o = f.posTab[(size_t)patPos*n + i];
-				s.pos[idx] = make_float2((float)X + o.x, (float)Y + o.y);
+				s.posx[idx] = (float)X + o.x;
+				s.posy[idx] = (float)Y + o.y;
 				if(s.time)
 				{
 					const int patT = f.patPlanes[3*plane + pp];
@@ -1136,88 +1192,153 @@ __global__ void __launch_bounds__(256, 2) k_hide(DevFrame f, int batch)
 						float adj = maxA(fabsf(vx), fabsf(vy)) / r;
 						o2 = make_float2(adj*vx, adj*vy);
 					}
-					s.dof[pixLocal*n + j] = o2;
-					if(i == 0) s.shufPat[pixLocal] = (uint8_t)patS;
+					s.dof[(ply*ys)*s.stride + plx*xs + (j / xs)*s.stride + j % xs] = o2;
+					if(i == 0) s.shufPat[ply*f.tileW + plx] = (uint8_t)patS;
 				}
 			}
 			else
-				s.pos[idx] = make_float2(-1e30f, -1e30f);
+			{
+				s.posx[idx] = -1e30f;
+				s.posy[idx] = -1e30f;
+			}
 		}
 		__syncthreads();
-		const uint32_t binBeg = f.binOffset[slot], binEnd = f.binOffset[slot+1];
+		const uint32_t binBeg = f.binOffset[slot], binCnt = f.binOffset[slot+1] - binBeg;
 		const uint32_t tflags = f.tileFlags[slot];
 		// ---- Render_MPGs: opaque pass, then (if the tile saw non-opaque micropolygons) deep pass
 		for(int pass = 0; pass < 2; ++pass)
 		{
-			if(pass == 1 && !(f.anyTransparent && (tflags & 1u))) break;
-			if(MBDOF)
+			if(pass == 1)
 			{
-				for(uint32_t e = binBeg + warp; e < binEnd; e += nwarps)
+				if(!(f.anyTransparent && (tflags & 1u))) break;
+				__syncthreads();
+				if(tid == 0) s_next = 0;
+				__syncthreads();
+			}
+			for(;;)
+			{
+				uint32_t base = 0;
+				if(lane == 0) base = atomicAdd(&s_next, (uint32_t)RECS_PER_WARP);
+				base = __shfl_sync(0xffffffffu, base, 0);
+				if(base >= binCnt) break;
+				const int cnt = min((uint32_t)RECS_PER_WARP, binCnt - base);
+				if(MBDOF)
 				{
-					const uint32_t p = f.binEntries[e];
-					const bool handled = (pass == 0) ? renderMBOrDof<true>(f, t, s, dc, p, lane)
-					                                 : renderMBOrDof<false>(f, t, s, dc, p, lane);
-					if(!handled)
+					for(int j = 0; j < cnt; ++j)
 					{
-						// static micropolygon, no depth of field: the per-warp record slot
-						if(lane == 0) setupStaticRec(f, t, p, pass == 0, s.recs[warp]);
-						__syncwarp();
-						if(pass == 0) sampleStaticRec<true>(f, t, s, dc, s.recs[warp], lane);
-						else sampleStaticRec<false>(f, t, s, dc, s.recs[warp], lane);
-						__syncwarp();
+						const uint32_t p = f.binEntries[binBeg + base + j];
+						const bool handled = (pass == 0) ? renderMBOrDof<true>(f, t, s, dc, p, lane)
+						                                 : renderMBOrDof<false>(f, t, s, dc, p, lane);
+						if(!handled)
+						{
+							// static micropolygon in a frame without depth of field
+							if(lane == 0) setupStaticRec(f, t, p, pass == 0, myRecs[0]);
+							__syncwarp();
+							if(pass == 0) sampleStaticRec<true>(f, t, s, dc, myRecs[0], lane);
+							else sampleStaticRec<false>(f, t, s, dc, myRecs[0], lane);
+							__syncwarp();
+						}
 					}
 				}
-			}
-			else
-			{
-				for(uint32_t b0 = binBeg; b0 < binEnd; b0 += batch)
+				else
 				{
-					const int cnt = min((uint32_t)batch, binEnd - b0);
-					for(int j = tid; j < cnt; j += blockDim.x)
-						setupStaticRec(f, t, f.binEntries[b0 + j], pass == 0, s.recs[j]);
-					__syncthreads();
-					for(int j = warp; j < cnt; j += nwarps)
+					if(lane < cnt) setupStaticRec(f, t, f.binEntries[binBeg + base + lane], pass == 0, myRecs[lane]);
+					__syncwarp();
+					for(int j = 0; j < cnt; ++j)
 					{
-						if(pass == 0) sampleStaticRec<true>(f, t, s, dc, s.recs[j], lane);
-						else sampleStaticRec<false>(f, t, s, dc, s.recs[j], lane);
+						if(pass == 0) sampleStaticRec<true>(f, t, s, dc, myRecs[j], lane);
+						else sampleStaticRec<false>(f, t, s, dc, myRecs[j], lane);
 					}
-					__syncthreads();
+					__syncwarp();
 				}
 			}
-			__syncthreads();
 		}
+		__syncthreads();
 		if(tid == 0 && s_deepCount) atomicAdd(&f.counters[2], (unsigned long long)min(s_deepCount, dc.cap));
 		// ---- Combine_samples + hand the resolved samples to the filter stage.
-		// Planes are [k][i][y][x]: consecutive threads take consecutive x of one sample index.
 		const int tw = t.rx1 - t.rx0, th = t.ry1 - t.ry0;
-		const int nOut = tw*th*n;
-		for(int o = tid; o < nOut; o += blockDim.x)
+		if(f.filterMode == AQH_FILTER_REFERENCE_ORDER)
 		{
-			const int lx = o % tw, r2 = o / tw, ly = r2 % th, i = r2 / th;
-			const int idx = (ly*f.tileW + lx)*n + i;
-			float out[7]; bool valid;
-			resolveSample(f, t, s, dc, idx, out, valid);
-			const int X = t.rx0 + lx, Y = t.ry0 + ly;
-			const size_t at = ((size_t)i*f.sh + (size_t)(Y - f.sy0))*f.sw + (size_t)(X - f.sx0);
-			// per-tap inclusion bits (bucketprocessor.cpp:609-612), evaluated with the true pixel
-			// coordinates: this sample belongs to filter tap (fx,fy) of output pixel (X-fx, Y-fy).
-			const float2 pos = s.pos[idx];
-			uint32_t mask = valid ? 0x80000000u : 0u;
-			for(int fx = -f.shiftX; fx <= f.shiftX; ++fx)
+			// Planes are [k][i][y][x]: consecutive threads take consecutive x of one sample index.
+			const int nOut = tw*th*n;
+			for(int o = tid; o < nOut; o += THREADS)
 			{
-				float vx = pos.x - ((float)(X - fx) + 0.5f);
-				if(vx >= -f.xfwo2 && vx <= f.xfwo2) mask |= 1u << (fx + f.shiftX);
-			}
-			for(int fy = -f.shiftY; fy <= f.shiftY; ++fy)
-			{
-				float vy = pos.y - ((float)(Y - fy) + 0.5f);
-				if(vy >= -f.yfwo2 && vy <= f.yfwo2) mask |= 1u << (15 + fy + f.shiftY);
-			}
-			f.maskPlane[at] = mask;
-			if(valid)
-			{
+				const int lx = o % tw, r2 = o / tw, ly = r2 % th, i = r2 / th;
+				const int idx = sampleIdx(f, s, lx, ly, i);
+				float out[7]; bool valid;
+				resolveSample(f, t, s, dc, idx, out, valid);
+				const int X = t.rx0 + lx, Y = t.ry0 + ly;
+				const size_t at = ((size_t)i*f.sh + (size_t)(Y - f.sy0))*f.sw + (size_t)(X - f.sx0);
+				f.maskPlane[at] = tapMask(f, s.posx[idx], s.posy[idx], X, Y, valid);
+				if(valid)
+				{
 #pragma unroll
-				for(int k = 0; k < 7; ++k) f.planes[(size_t)k*f.planeStride + at] = out[k];
+					for(int k = 0; k < 7; ++k) f.planes[(size_t)k*f.planeStride + at] = out[k];
+				}
+			}
+		}
+		else
+		{
+			// Tile-partials mode: one warp per pixel.  32 samples at a time are resolved (one per
+			// lane) into the warp's scratch; then lane (tap, group) runs over them in sample order and
+			// adds weight*value into its three of the nine per-(pixel,tap) sums
+			// (0 gTot, 1 hit count | R G B | Or Og Ob Z is split 3/3/3 over the groups).
+			float4* scratch = reinterpret_cast<float4*>(myRecs);     // 32 samples x 2 float4
+			const size_t planeSz = (size_t)f.sw*f.sh;
+			for(int pix = warp; pix < tw*th; pix += NWARPS)
+			{
+				const int lx = pix % tw, ly = pix / tw;
+				const int X = t.rx0 + lx, Y = t.ry0 + ly;
+				const size_t at = (size_t)(Y - f.sy0)*f.sw + (size_t)(X - f.sx0);
+				for(int c0 = 0; c0 < n; c0 += 32)
+				{
+					const int i = c0 + lane;
+					if(i < n)
+					{
+						const int idx = sampleIdx(f, s, lx, ly, i);
+						float out[7]; bool valid;
+						resolveSample(f, t, s, dc, idx, out, valid);
+						const uint32_t m = tapMask(f, s.posx[idx], s.posy[idx], X, Y, valid);
+						if(!valid) { out[0] = out[1] = out[2] = out[3] = out[4] = out[5] = out[6] = 0.f; }
+						scratch[2*lane] = make_float4(out[0], out[1], out[2], out[3]);
+						scratch[2*lane+1] = make_float4(out[4], out[5], out[6], __uint_as_float(m));
+					}
+					__syncwarp();
+					const int cn = min(32, n - c0);
+					for(int t0 = 0; t0 < f.ntaps; t0 += 10)
+					{
+						const int tap = t0 + lane/3, grp = lane - (lane/3)*3;
+						if(lane < 30 && tap < f.ntaps)
+						{
+							const int fy = tap / (2*f.shiftX+1), fx = tap - fy*(2*f.shiftX+1);
+							const uint32_t need = (1u << fx) | (1u << (15 + fy));
+							const float* g = f.filterTab + (size_t)tap*n + c0;
+							float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+							for(int j = 0; j < cn; ++j)
+							{
+								const float4 hi = scratch[2*j+1];
+								const uint32_t m = __float_as_uint(hi.w);
+								if((m & need) != need) continue;
+								const float w = g[j];
+								if(grp == 0)
+								{
+									a0 += w;
+									if(m & 0x80000000u) { a1 += 1.0f; a2 += scratch[2*j].x * w; }
+								}
+								else if(m & 0x80000000u)
+								{
+									const float4 lo = scratch[2*j];
+									if(grp == 1) { a0 += lo.y * w; a1 += lo.z * w; a2 += lo.w * w; }
+									else { a0 += hi.x * w; a1 += hi.y * w; a2 += hi.z * w; }
+								}
+							}
+							float* dst = f.partials + ((size_t)tap*9 + grp*3)*planeSz + at;
+							if(c0 == 0) { dst[0] = a0; dst[planeSz] = a1; dst[2*planeSz] = a2; }
+							else { dst[0] += a0; dst[planeSz] += a1; dst[2*planeSz] += a2; }
+						}
+					}
+					__syncwarp();
+				}
 			}
 		}
 	}
@@ -1254,6 +1375,79 @@ __global__ void __launch_bounds__(256) k_tile_flags(DevFrame f)
 // ExposeBucket (:766-806) and FormatBucketForDisplay (ddmanager.cpp:1046-1113).
 __device__ __forceinline__ double clampD(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// Everything after the sums: normalise, coverage/alpha (bucketprocessor.cpp:633-707),
+// ExposeBucket (:766-806), store the 9-float pixel and quantise per display
+// (FormatBucketForDisplay, ddmanager.cpp:1046-1113).
+__device__ __forceinline__ void finishPixel(const DevFrame& f, const DevDisplays& disp, int x, int y,
+                                            const float acc[7], float gTot, int SampleCount)
+{
+	const int n = f.n;
+	float out[9];
+	float coverage;
+	if(SampleCount == 0)
+	{
+#pragma unroll
+		for(int k = 0; k < 9; ++k) out[k] = 0.f;
+		out[AQH_CH_Z] = FLT_MAX;
+		coverage = 0.f;
+	}
+	else
+	{
+		const float oneOverGTot = 1.0f / gTot;
+#pragma unroll
+		for(int k = 0; k < 6; ++k) out[k] = acc[k] * oneOverGTot;
+		out[AQH_CH_Z] = acc[6] * oneOverGTot;
+		coverage = (SampleCount >= n) ? 1.0f : (float)SampleCount / (float)n;
+	}
+	const float a = (out[3] + out[4] + out[5]) / 3.0f;
+	out[AQH_CH_ALPHA] = a * coverage;
+	out[AQH_CH_COVERAGE] = coverage;
+	if(!(f.expGain == 1.0f && f.expGamma == 1.0f))
+	{
+		const float oneovergamma = 1.0f / f.expGamma;
+#pragma unroll
+		for(int k = 0; k < 3; ++k)
+		{
+			if(f.expGain != 1.0f) out[k] *= f.expGain;
+			if(f.expGamma != 1.0f) out[k] = (float)pow((double)out[k], (double)oneovergamma);
+		}
+	}
+	float* dst = f.channels + ((size_t)y*f.xres + x)*9;
+#pragma unroll
+	for(int k = 0; k < 9; ++k) dst[k] = out[k];
+	for(int d = 0; d < disp.n; ++d)
+	{
+		const DevDisplay& dd = disp.d[d];
+		const double s = (double)f.dither[((size_t)d*f.yres + y)*f.xres + x];
+		unsigned char* pd = dd.out + ((size_t)y*f.xres + x)*dd.entrySize;
+		for(int c = 0; c < dd.nChannels; ++c)
+		{
+			double value = (double)out[dd.channel[c]];
+			if(dd.qOne != 0.f)
+			{
+				double v = (double)dd.qZero + value * (double)(dd.qOne - dd.qZero) + ((double)dd.qDither * s);
+				// lround(x) = lfloor(x - 0.5) + 1, math.h:47-70
+				double xm = v - 0.5;
+				long long li = (long long)xm;
+				li = li - ((xm < 0.0 && xm != (double)li) ? 1 : 0);
+				value = (double)(li + 1);
+				value = clampD(value, (double)dd.qMin, (double)dd.qMax);
+			}
+			switch(dd.type)
+			{
+				case AQH_FLOAT32: { float v = (float)value; memcpy(pd, &v, 4); pd += 4; break; }
+				case AQH_UNSIGNED32: { value = clampD(value, 0.0, 4294967295.0); uint32_t v = (uint32_t)value; memcpy(pd, &v, 4); pd += 4; break; }
+				case AQH_SIGNED32: { value = clampD(value, -2147483648.0, 2147483647.0); int32_t v = (int32_t)value; memcpy(pd, &v, 4); pd += 4; break; }
+				case AQH_UNSIGNED16: { uint16_t v = (uint16_t)(int)value; memcpy(pd, &v, 2); pd += 2; break; }
+				case AQH_SIGNED16: { int16_t v = (int16_t)(int)value; memcpy(pd, &v, 2); pd += 2; break; }
+				case AQH_UNSIGNED8: { *pd++ = (unsigned char)(int)value; break; }
+				case AQH_SIGNED8: { *pd++ = (unsigned char)(signed char)(int)value; break; }
+			}
+		}
+	}
+}
+
+// Reference-order filter: one running sum per output pixel over the per-sample planes.
 __global__ void __launch_bounds__(256) k_filter(DevFrame f, DevDisplays disp)
 {
 	extern __shared__ float s_filt[];
@@ -1292,70 +1486,175 @@ __global__ void __launch_bounds__(256) k_filter(DevFrame f, DevDisplays disp)
 				}
 			}
 		}
-	float out[9];
-	float coverage;
-	if(SampleCount == 0)
+	finishPixel(f, disp, x, y, acc, gTot, SampleCount);
+}
+
+// Reference-order filter, shared-memory tiled.  A CTA owns OW x OH output pixels.  The per-sample
+// tap masks of the (OW+2xmax) x (OH+2ymax) halo tile stay in shared memory (16 bit each); the
+// seven value planes are streamed through a second tile ONE PLANE AT A TIME, so every resolved
+// sample is read from HBM (OW+2xmax)(OH+2ymax)/(OW*OH) times instead of (2xmax+1)(2ymax+1) times,
+// while each thread still adds its taps in exactly the reference's fy, fx, sy, sx order.
+// Weights come from constant memory (the index is warp-uniform).
+__constant__ float c_filt[49*256];
+
+__device__ __forceinline__ void cpAsync4(void* smemDst, const void* gsrc)
+{
+	const uint32_t d = (uint32_t)__cvta_generic_to_shared(smemDst);
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cpAsyncWaitAll()
+{
+	asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// Walks the elements tid, tid+nthreads, ... of an [n*HH rows][HW] halo tile without divisions.
+struct TileWalk
+{
+	int hx, hy, sI, dh, dr, HW, HH;
+	__device__ __forceinline__ TileWalk(int tid, int nthreads, int HW_, int HH_) : HW(HW_), HH(HH_)
 	{
-#pragma unroll
-		for(int k = 0; k < 9; ++k) out[k] = 0.f;
-		out[AQH_CH_Z] = FLT_MAX;
-		coverage = 0.f;
+		const int row = tid / HW_;
+		hx = tid - row*HW_;
+		sI = row / HH_; hy = row - sI*HH_;
+		dr = nthreads / HW_; dh = nthreads - dr*HW_;
 	}
-	else
+	__device__ __forceinline__ void next()
 	{
-		const float oneOverGTot = 1.0f / gTot;
-#pragma unroll
-		for(int k = 0; k < 6; ++k) out[k] = acc[k] * oneOverGTot;
-		out[AQH_CH_Z] = acc[6] * oneOverGTot;
-		coverage = (SampleCount >= n) ? 1.0f : (float)SampleCount / (float)n;
+		hx += dh; hy += dr;
+		if(hx >= HW) { hx -= HW; ++hy; }
+		while(hy >= HH) { hy -= HH; ++sI; }
 	}
-	const float a = (out[3] + out[4] + out[5]) / 3.0f;
-	out[AQH_CH_ALPHA] = a * coverage;
-	out[AQH_CH_COVERAGE] = coverage;
-	if(!(f.expGain == 1.0f && f.expGamma == 1.0f))
+};
+
+__global__ void __launch_bounds__(512) k_filter_tiled(DevFrame f, DevDisplays disp, int OW, int OH)
+{
+	extern __shared__ __align__(16) unsigned char fsm[];
+	const int n = f.n, xmax = f.shiftX, ymax = f.shiftY;
+	const int HW = OW + 2*xmax, HH = OH + 2*ymax, HHHW = HH*HW, tileN = n*HHHW;
+	const int nthreads = OW*OH, tid = threadIdx.x;
+	const int nw = (n + 31) >> 5;                       // 32-sample words per tap
+	float* planeT = reinterpret_cast<float*>(fsm);
+	uint32_t* useW = reinterpret_cast<uint32_t*>(fsm + (size_t)tileN*4);          // [tap*nw + w][thread]
+	uint16_t* maskT = reinterpret_cast<uint16_t*>(fsm + (size_t)tileN*4 + (size_t)f.ntaps*nw*nthreads*4);
+	const int tx = tid % OW, ty = tid / OW;
+	const int x0 = f.cropX0 + blockIdx.x*OW, y0 = f.cropY0 + blockIdx.y*OH;
+	const int x = x0 + tx, y = y0 + ty;
+	const bool live = x < f.cropX1 && y < f.cropY1 && !(f.rowOwned && !f.rowOwned[y]);
+	// mask tile (converted to 16 bits) + first value plane (asynchronous copies)
 	{
-		const float oneovergamma = 1.0f / f.expGamma;
-#pragma unroll
-		for(int k = 0; k < 3; ++k)
+		TileWalk w(tid, nthreads, HW, HH);
+		for(; w.sI < n; w.next())
 		{
-			if(f.expGain != 1.0f) out[k] *= f.expGain;
-			if(f.expGamma != 1.0f) out[k] = (float)pow((double)out[k], (double)oneovergamma);
+			const int gy = y0 - ymax + w.hy - f.sy0, gx = x0 - xmax + w.hx - f.sx0;
+			const int o = (w.sI*HH + w.hy)*HW + w.hx;
+			if(gy >= 0 && gy < f.sh && gx >= 0 && gx < f.sw)
+			{
+				const size_t src = ((size_t)w.sI*f.sh + gy)*f.sw + gx;
+				cpAsync4(&planeT[o], f.planes + src);
+				const uint32_t m = f.maskPlane[src];
+				maskT[o] = (uint16_t)((m & 0x7fu) | (((m >> 15) & 0x7fu) << 7) | ((m >> 31) << 15));
+			}
+			else { planeT[o] = 0.f; maskT[o] = 0; }
 		}
+		cpAsyncWaitAll();
 	}
-	float* dst = f.channels + ((size_t)y*f.xres + x)*9;
-#pragma unroll
-	for(int k = 0; k < 9; ++k) dst[k] = out[k];
-	// quantise
-	for(int d = 0; d < disp.n; ++d)
+	__syncthreads();
+	float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+	float gTot = 0.f;
+	int SampleCount = 0;
+	if(live)
 	{
-		const DevDisplay& dd = disp.d[d];
-		const double s = (double)f.dither[((size_t)d*f.yres + y)*f.xres + x];
-		unsigned char* pd = dd.out + ((size_t)y*f.xres + x)*dd.entrySize;
-		for(int c = 0; c < dd.nChannels; ++c)
-		{
-			double value = (double)out[dd.channel[c]];
-			if(dd.qOne != 0.f)
+		// plane 0 (red) together with the weight total, the hit count and the "use" bits
+		float a = 0.f;
+		int tap = 0;
+		for(int fy = 0; fy <= 2*ymax; ++fy)
+			for(int fx = 0; fx <= 2*xmax; ++fx, ++tap)
 			{
-				double v = (double)dd.qZero + value * (double)(dd.qOne - dd.qZero) + ((double)dd.qDither * s);
-				// lround(x) = lfloor(x - 0.5) + 1, math.h:47-70
-				double xm = v - 0.5;
-				long long li = (long long)xm;
-				li = li - ((xm < 0.0 && xm != (double)li) ? 1 : 0);
-				value = (double)(li + 1);
-				value = clampD(value, (double)dd.qMin, (double)dd.qMax);
+				const uint32_t need = (1u << fx) | (1u << (7 + fy));
+				int o = (ty + fy)*HW + tx + fx;
+				const float* w = c_filt + tap*n;
+				for(int w0 = 0; w0 < nw; ++w0)
+				{
+					uint32_t bits = 0;
+					const int sEnd = min(32, n - w0*32);
+					for(int b2 = 0; b2 < sEnd; ++b2, o += HHHW)
+					{
+						const uint32_t m = maskT[o];
+						if((m & need) == need)
+						{
+							const float g = w[w0*32 + b2];
+							gTot += g;
+							if(m & 0x8000u) { a += planeT[o] * g; SampleCount++; bits |= 1u << b2; }
+						}
+					}
+					useW[(tap*nw + w0)*nthreads + tid] = bits;
+				}
 			}
-			switch(dd.type)
-			{
-				case AQH_FLOAT32: { float v = (float)value; memcpy(pd, &v, 4); pd += 4; break; }
-				case AQH_UNSIGNED32: { value = clampD(value, 0.0, 4294967295.0); uint32_t v = (uint32_t)value; memcpy(pd, &v, 4); pd += 4; break; }
-				case AQH_SIGNED32: { value = clampD(value, -2147483648.0, 2147483647.0); int32_t v = (int32_t)value; memcpy(pd, &v, 4); pd += 4; break; }
-				case AQH_UNSIGNED16: { uint16_t v = (uint16_t)(int)value; memcpy(pd, &v, 2); pd += 2; break; }
-				case AQH_SIGNED16: { int16_t v = (int16_t)(int)value; memcpy(pd, &v, 2); pd += 2; break; }
-				case AQH_UNSIGNED8: { *pd++ = (unsigned char)(int)value; break; }
-				case AQH_SIGNED8: { *pd++ = (unsigned char)(signed char)(int)value; break; }
-			}
-		}
+		acc[0] = a;
 	}
+#pragma unroll 1
+	for(int k = 1; k < 7; ++k)
+	{
+		__syncthreads();
+		const float* plane = f.planes + (size_t)k*f.planeStride;
+		{
+			TileWalk w(tid, nthreads, HW, HH);
+			for(; w.sI < n; w.next())
+			{
+				const int gy = y0 - ymax + w.hy - f.sy0, gx = x0 - xmax + w.hx - f.sx0;
+				const int o = (w.sI*HH + w.hy)*HW + w.hx;
+				if(gy >= 0 && gy < f.sh && gx >= 0 && gx < f.sw)
+					cpAsync4(&planeT[o], plane + ((size_t)w.sI*f.sh + gy)*f.sw + gx);
+				else
+					planeT[o] = 0.f;
+			}
+			cpAsyncWaitAll();
+		}
+		__syncthreads();
+		if(!live) continue;
+		float a = 0.f;
+		int tap = 0;
+		for(int fy = 0; fy <= 2*ymax; ++fy)
+			for(int fx = 0; fx <= 2*xmax; ++fx, ++tap)
+			{
+				int o = (ty + fy)*HW + tx + fx;
+				const float* w = c_filt + tap*n;
+				for(int w0 = 0; w0 < nw; ++w0)
+				{
+					const uint32_t bits = useW[(tap*nw + w0)*nthreads + tid];
+					const int sEnd = min(32, n - w0*32);
+#pragma unroll 8
+					for(int b2 = 0; b2 < sEnd; ++b2, o += HHHW)
+						if((bits >> b2) & 1u) a += planeT[o] * w[w0*32 + b2];
+				}
+			}
+		acc[k] = a;
+	}
+	if(live) finishPixel(f, disp, x, y, acc, gTot, SampleCount);
+}
+
+// Tile-partials filter: sum the nine per-(pixel,tap) partial sums over the taps in fy, fx order.
+__global__ void __launch_bounds__(256) k_filter_partials(DevFrame f, DevDisplays disp)
+{
+	const int x = f.cropX0 + blockIdx.x*blockDim.x + threadIdx.x;
+	const int y = f.cropY0 + blockIdx.y*blockDim.y + threadIdx.y;
+	if(x >= f.cropX1 || y >= f.cropY1) return;
+	if(f.rowOwned && !f.rowOwned[y]) return;
+	const int xmax = f.shiftX, ymax = f.shiftY;
+	const size_t planeSz = (size_t)f.sw*f.sh;
+	float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+	float gTot = 0.f, cnt = 0.f;
+	int tap = 0;
+	for(int fy = -ymax; fy <= ymax; ++fy)
+		for(int fx = -xmax; fx <= xmax; ++fx, ++tap)
+		{
+			const float* src = f.partials + (size_t)tap*9*planeSz + (size_t)(y + fy - f.sy0)*f.sw + (size_t)(x + fx - f.sx0);
+			gTot += src[0];
+			cnt += src[planeSz];
+#pragma unroll
+			for(int k = 0; k < 7; ++k) acc[k] += src[(size_t)(2 + k)*planeSz];
+		}
+	finishPixel(f, disp, x, y, acc, gTot, (int)cnt);
 }
 
 // ------------------------------------------------------------------------------------
@@ -1388,42 +1687,88 @@ cudaError_t launchBinFill(const DevFrame& f, cudaStream_t st)
 	return cudaGetLastError();
 }
 
-cudaError_t hideKernelConfig(const DevFrame& f, int smCount, LaunchCfg& cfg)
+template<bool MBDOF, int THREADS>
+static cudaError_t configHide(const DevFrame& f, int smCount, LaunchCfg& cfg)
 {
-	cfg.smCount = smCount;
-	cfg.hideThreads = 256;
-	const bool mbdof = f.useDof || f.anyMotion;
-	cfg.batchMPs = mbdof ? 8 : 256;   // MB/DoF: one record slot per warp
+	cfg.hideThreads = THREADS;
+	cfg.batchMPs = (THREADS/32)*RECS_PER_WARP;
 	cfg.hideSmemBytes = hideSmemBytes(f, cfg.batchMPs);
 	if(cfg.hideSmemBytes > 227*1024) return cudaErrorInvalidValue;
-	cudaError_t e;
-	if(mbdof) e = cudaFuncSetAttribute(k_hide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.hideSmemBytes);
-	else e = cudaFuncSetAttribute(k_hide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.hideSmemBytes);
+	cudaError_t e = cudaFuncSetAttribute(k_hide<MBDOF, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.hideSmemBytes);
+	if(e != cudaSuccess) return e;
+	e = cudaFuncSetAttribute(k_hide<MBDOF, THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
 	if(e != cudaSuccess) return e;
 	int perSm = 0;
-	if(mbdof) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_hide<true>, cfg.hideThreads, cfg.hideSmemBytes);
-	else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_hide<false>, cfg.hideThreads, cfg.hideSmemBytes);
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_hide<MBDOF, THREADS>, THREADS, cfg.hideSmemBytes);
 	if(e != cudaSuccess) return e;
 	if(perSm < 1) perSm = 1;
 	cfg.hideCtas = smCount * perSm;
 	return cudaSuccess;
 }
 
+cudaError_t hideKernelConfig(const DevFrame& f, int smCount, LaunchCfg& cfg)
+{
+	cfg.smCount = smCount;
+	const bool mbdof = f.useDof || f.anyMotion;
+	return mbdof ? configHide<true, 256>(f, smCount, cfg) : configHide<false, 512>(f, smCount, cfg);
+}
+
 cudaError_t launchHide(const DevFrame& f, const LaunchCfg& cfg, cudaStream_t st)
 {
 	if(f.nActiveTiles == 0) return cudaSuccess;
 	const bool mbdof = f.useDof || f.anyMotion;
-	if(mbdof) k_hide<true><<<cfg.hideCtas, cfg.hideThreads, cfg.hideSmemBytes, st>>>(f, cfg.batchMPs);
-	else k_hide<false><<<cfg.hideCtas, cfg.hideThreads, cfg.hideSmemBytes, st>>>(f, cfg.batchMPs);
+	if(mbdof) k_hide<true, 256><<<cfg.hideCtas, 256, cfg.hideSmemBytes, st>>>(f);
+	else k_hide<false, 512><<<cfg.hideCtas, 512, cfg.hideSmemBytes, st>>>(f);
 	return cudaGetLastError();
 }
 
-cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, cudaStream_t st)
+static size_t filterTiledSmem(const DevFrame& f, int OW, int OH)
+{
+	const size_t tileN = (size_t)f.n*(OW + 2*f.shiftX)*(OH + 2*f.shiftY);
+	const size_t nw = (f.n + 31)/32;
+	return tileN*6 + (size_t)f.ntaps*nw*OW*OH*4 + 16;
+}
+
+cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, const float* hostFilterTab, cudaStream_t st)
 {
 	const int w = f.cropX1 - f.cropX0, h = f.cropY1 - f.cropY0;
 	if(w <= 0 || h <= 0) return cudaSuccess;
+	if(f.filterMode != AQH_FILTER_REFERENCE_ORDER)
+	{
+		dim3 block(32, 8), grid((w + 31)/32, (h + 7)/8);
+		k_filter_partials<<<grid, block, 0, st>>>(f, disp);
+		return cudaGetLastError();
+	}
+	const int ntapw = (2*f.shiftX+1)*(2*f.shiftY+1)*f.n;
+	// tiled kernel: masks as 7+7 tap bits (filter widths < 8), weights in 64 KB of constant memory
+	if(f.shiftX <= 3 && f.shiftY <= 3 && ntapw <= 49*256)
+	{
+		const size_t budget = 200*1024;
+		int OW = 32, OH = 0;
+		for(; OW >= 8 && OH < 1; OW >>= 1)
+		{
+			for(int oh = 16; oh >= 1; --oh)
+			{
+				if(OW*oh > 512) continue;
+				const size_t need = filterTiledSmem(f, OW, oh);
+				if(need <= budget) { OH = oh; break; }
+			}
+			if(OH >= 1) break;
+		}
+		if(OH >= 1 && OW*OH >= 32)
+		{
+			const size_t smem = filterTiledSmem(f, OW, OH);
+			cudaError_t e = cudaMemcpyToSymbolAsync(c_filt, hostFilterTab, (size_t)ntapw*4, 0, cudaMemcpyHostToDevice, st);
+			if(e != cudaSuccess) return e;
+			e = cudaFuncSetAttribute(k_filter_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if(e != cudaSuccess) return e;
+			dim3 grid((w + OW - 1)/OW, (h + OH - 1)/OH);
+			k_filter_tiled<<<grid, OW*OH, smem, st>>>(f, disp, OW, OH);
+			return cudaGetLastError();
+		}
+	}
 	dim3 block(32, 8), grid((w + 31)/32, (h + 7)/8);
-	const size_t smem = (size_t)(2*f.shiftX+1)*(2*f.shiftY+1)*f.n*sizeof(float);
+	const size_t smem = (size_t)ntapw*sizeof(float);
 	if(smem > 48*1024)
 	{
 		cudaError_t e = cudaFuncSetAttribute(k_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

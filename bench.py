@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py -- hide+filter throughput of the B200 hider on BASELINE.json's synthetic scenes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2] [--impl reference]
+
+A "step" is one pass of the hot path (project+bust, bin, sample, composite, filter, expose,
+quantise, and for N>1 the NCCL gather of the image) over one frame of synthetic shaded grids.
+`value` is measured with the grids already resident in HBM; `e2e` goes through the public
+C ABI with pinned HOST buffers (H2D of the grids and D2H of the image inside the timed region).
+N>1: one process per GPU under torchrun, image strips dealt round-robin (strong scaling of one
+frame), grids replicated to the ranks whose strips they touch, final image gathered to rank 0.
+
+--impl reference times the reference's own (CPU) algorithm for the same metric: the oracle
+port of the aqsis hider (the aqsis binary cannot be built in this image) on all
+host cores, each step a bounded, same-density sample of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    1: "config1: 640x480, PixelSamples 4 4, gaussian 2x2, 10k bilinear patches (0.64M micropolygons)",
+    2: "config2: 1920x1080, PixelSamples 8 8, ShadingRate 1, ~20M micropolygons, opaque, catmull-rom 3x3",
+    3: "config3: 1920x1080, PixelSamples 8 8, motion blur (shutter 0 1) + depth of field, ~20M micropolygons",
+    4: "config4: 3840x2160, PixelSamples 16 16, ShadingRate 0.25, 4 layers, semi-transparent, gaussian 2x2",
+}
+# same-density reduced copies of the workloads for the CPU legs (linear image scale)
+CPU_SAMPLE_SCALE = {1: 1.0, 2: 0.35, 3: 0.1, 4: 0.06}
+
+
+def make_scene(config, scale=1.0):
+    from aqsis_b200 import scenes
+    fn = {1: scenes.config1, 2: scenes.config2, 3: scenes.config3, 4: scenes.config4}[config]
+    return fn(scale=scale)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag.is_set():
+                    break
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag.set()
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], 0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # under load = samples within 25% of the top observed clock or all if few
+        med = float(np.median(sm)) if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def split_grids_for_rank(params, grids, rank, world, strip_rows):
+    """Keep the grids whose (motion/DoF/filter-expanded) y-range touches a strip owned by `rank`."""
+    from aqsis_b200 import GridArrays
+    if world == 1:
+        return grids
+    nv = (grids.cu.astype(np.int64) + 1) * (grids.cv.astype(np.int64) + 1)
+    nk = grids.nkeys.astype(np.int64) if grids.nkeys is not None else np.ones_like(nv)
+    pstart = np.concatenate([[0], np.cumsum(nv * nk)])
+    vstart = np.concatenate([[0], np.cumsum(nv)])
+    y = np.asarray(grids.P)[:, 1]
+    z = np.asarray(grids.P)[:, 2]
+    ymin = np.minimum.reduceat(y, pstart[:-1])
+    ymax = np.maximum.reduceat(y, pstart[:-1])
+    pad = np.floor(params.filter_ywidth / 2.0) + 1.0
+    if params.use_dof:
+        zmin = np.minimum.reduceat(z, pstart[:-1])
+        zmax = np.maximum.reduceat(z, pstart[:-1])
+        coc = lambda zz: params.dof_multiplier * np.abs(1.0 / zz - params.dof_one_over_focal_distance) * params.dof_scale_y
+        pad = pad + np.maximum(coc(zmin), coc(zmax))
+    lo = np.floor(ymin - pad).astype(np.int64)
+    hi = np.ceil(ymax + pad).astype(np.int64)
+    keep = np.zeros(grids.n_grids, dtype=bool)
+    y0 = params.crop_ymin
+    si = 0
+    while y0 < params.crop_ymax:
+        y1 = min(y0 + strip_rows, params.crop_ymax)
+        if si % world == rank:
+            keep |= (hi >= y0) & (lo < y1)
+        y0 = y1
+        si += 1
+    idx = np.nonzero(keep)[0]
+    pos_idx = np.concatenate([np.arange(pstart[g], pstart[g + 1]) for g in idx]) if len(idx) else np.zeros(0, np.int64)
+    vert_idx = np.concatenate([np.arange(vstart[g], vstart[g + 1]) for g in idx]) if len(idx) else np.zeros(0, np.int64)
+    kt = None
+    if grids.key_times is not None:
+        kstart = np.concatenate([[0], np.cumsum(nk)])
+        kt = np.concatenate([grids.key_times[kstart[g]:kstart[g + 1]] for g in idx]) if len(idx) else np.zeros(0, np.float32)
+    return GridArrays(cu=grids.cu[idx], cv=grids.cv[idx], flags=grids.flags[idx], P=np.asarray(grids.P)[pos_idx],
+                      Ci=None if grids.Ci is None else np.asarray(grids.Ci)[vert_idx],
+                      Oi=None if grids.Oi is None else np.asarray(grids.Oi)[vert_idx],
+                      nkeys=None if grids.nkeys is None else grids.nkeys[idx], key_times=kt,
+                      lod_bounds=None if grids.lod_bounds is None else grids.lod_bounds.reshape(-1, 2)[idx].ravel(),
+                      culled=None if grids.culled is None else np.asarray(grids.culled)[vert_idx])
+
+
+class _CudaArray:
+    """Expose a raw device pointer to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def run_reference(args):
+    """The reference arm: the CPU algorithm (oracle port) on all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    orc.build_oracle()
+    cores = os.cpu_count() or 1
+    scale = CPU_SAMPLE_SCALE[args.config]
+    params, grids = make_scene(args.config, scale)
+    nmp = grids.n_micropolygons
+    nsamp = params.xres * params.yres * params.xsamples * params.ysamples
+    for _ in range(args.warmup):
+        orc.render(params, grids, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, _, st = orc.render(params, grids, cores)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = nmp / dt / 1e6
+    sample = (f"{WORKLOADS[args.config].split(':')[0]} at linear scale {scale} ({params.xres}x{params.yres}, "
+              f"{grids.n_grids} grids, {nmp} micropolygons, same density and options), {cores} threads over buckets")
+    line = {
+        "impl": "reference", "metric": "hide+filter throughput", "value": value, "unit": "Mpolys/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "msamples_per_s": nsamp / dt / 1e6,
+        "config": {"workload": WORKLOADS[args.config], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mpolys/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mpolys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "oracle port of the aqsis CPU hider (oracle/oracle_hider.cpp); the aqsis binary is not buildable here",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def cpu_baseline(config, budget_s=20.0):
+    """Oracle on a bounded same-density sample of the workload; 1 thread (reference-faithful) and all cores."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    orc.build_oracle()
+    cores = os.cpu_count() or 1
+    scale = CPU_SAMPLE_SCALE[config]
+    params, grids = make_scene(config, scale)
+    nmp = grids.n_micropolygons
+    t0 = time.perf_counter()
+    orc.render(params, grids, cores)
+    t_all = time.perf_counter() - t0
+    out = {"value": nmp / t_all / 1e6, "unit": "Mpolys/s", "cores": cores, "kind": "port",
+           "sample": f"{WORKLOADS[config].split(':')[0]} at linear scale {scale}: {params.xres}x{params.yres}, "
+                     f"{nmp} micropolygons, same density/options; oracle/oracle_hider.cpp"}
+    if t_all * cores < budget_s:     # the faithful single-threaded bucket loop, if it fits the budget
+        t0 = time.perf_counter()
+        orc.render(params, grids, 1)
+        t1 = time.perf_counter() - t0
+        out["value_1thread"] = nmp / t1 / 1e6
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4])
+    ap.add_argument("--scale", type=float, default=1.0, help="linear image scale of the workload (1.0 = as named)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--strip-rows", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from aqsis_b200 import Hider, build, scenes
+    from aqsis_b200.hider import display_info
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hider has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+
+    params, grids = make_scene(args.config, args.scale)
+    params.rank, params.world_size, params.strip_rows = rank, world, args.strip_rows
+    n_mp_total = grids.n_micropolygons
+    n_samples_total = (params.crop_xmax - params.crop_xmin) * (params.crop_ymax - params.crop_ymin) * params.xsamples * params.ysamples
+    b_alg_total = scenes.algorithmic_bytes(params, grids)
+    mine = split_grids_for_rank(params, grids, rank, world, args.strip_rows)
+    b_alg_mine = scenes.algorithmic_bytes(params, mine) if world > 1 else b_alg_total
+    del grids
+
+    stream = torch.cuda.current_stream()
+    h = Hider(local_rank, stream=stream.cuda_stream)
+    dev_grids = mine.to_torch(device=dev)
+    pin_grids = mine.to_torch(pin=True)
+    h2d_bytes = sum(int(t.numel() * t.element_size()) for t in (pin_grids.P, pin_grids.Ci, pin_grids.Oi) if t is not None)
+
+    # ---- gather plumbing: rows owned by each rank, padded to equal size
+    h.begin_frame(params)
+    h.add_grid_block(dev_grids)
+    h.render_device()
+    strips = h.strips()
+    rows = np.concatenate([np.arange(a, b) for a, b in strips]) if strips else np.zeros(0, np.int64)
+    dtype_d, nch_d, es_d = display_info(params, 0) if params.n_displays else (np.dtype("uint8"), 0, 0)
+    if world > 1:
+        nrows = torch.tensor([len(rows)], device=dev)
+        allrows = [torch.zeros_like(nrows) for _ in range(world)]
+        dist.all_gather(allrows, nrows)
+        max_rows = int(max(int(t.item()) for t in allrows))
+        row_idx = torch.zeros(max_rows, dtype=torch.long, device=dev)
+        row_idx[:len(rows)] = torch.from_numpy(rows).to(dev)
+        gathered_rows = [torch.zeros(max_rows, dtype=torch.long, device=dev) for _ in range(world)]
+        dist.all_gather(gathered_rows, row_idx)
+        counts = [int(t.item()) for t in allrows]
+
+    def device_images():
+        pc, _ = h.device_channels()
+        ch = torch.as_tensor(_CudaArray(pc, (params.yres, params.xres * 9), "<f4"), device=dev)
+        dsp = None
+        if params.n_displays:
+            pd, _ = h.device_display(0)
+            dsp = torch.as_tensor(_CudaArray(pd, (params.yres, params.xres * es_d), "|u1"), device=dev)
+        return ch, dsp
+
+    final = {}
+
+    def gather_image():
+        """Final image to rank 0 over NCCL (the only collective of the path)."""
+        ch, dsp = device_images()
+        if world == 1:
+            final["channels"], final["display"] = ch, dsp
+            return
+        send_c = ch.index_select(0, row_idx)
+        send_d = dsp.index_select(0, row_idx) if dsp is not None else None
+        if rank == 0:
+            rc = [torch.empty_like(send_c) for _ in range(world)]
+            dist.gather(send_c, rc, dst=0)
+            full_c = torch.zeros_like(ch)
+            for r in range(world):
+                full_c.index_copy_(0, gathered_rows[r][:counts[r]], rc[r][:counts[r]])
+            final["channels"] = full_c
+            if send_d is not None:
+                rd = [torch.empty_like(send_d) for _ in range(world)]
+                dist.gather(send_d, rd, dst=0)
+                full_d = torch.zeros_like(dsp)
+                for r in range(world):
+                    full_d.index_copy_(0, gathered_rows[r][:counts[r]], rd[r][:counts[r]])
+                final["display"] = full_d
+        else:
+            dist.gather(send_c, None, dst=0)
+            if send_d is not None:
+                dist.gather(send_d, None, dst=0)
+
+    def step_resident():
+        h.render_device()
+        gather_image()
+
+    def step_e2e():
+        h.begin_frame(params)
+        h.add_grid_block(pin_grids)
+        h.end_frame()
+        gather_image()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage = {"project_bust_ms": 0.0, "render_mpgs_ms": 0.0, "filter_ms": 0.0, "launches": 0}
+        e0.record()
+        for _ in range(steps):
+            fn()
+            s = h.stats()
+            for k in ("project_bust_ms", "render_mpgs_ms", "filter_ms"):
+                stage[k] += s[k]
+            stage["launches"] += s["gpu_launches"]
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        for k in ("project_bust_ms", "render_mpgs_ms", "filter_ms"):
+            stage[k] /= steps
+        return ms, stage
+
+    # resident-input measurement
+    h.begin_frame(params)
+    h.add_grid_block(dev_grids)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, stage = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.finish() if sampler else None
+    stats = h.stats()
+
+    # the opt-in tile-partials filter mode (not bit-exact), for information
+    from aqsis_b200 import abi as _abi
+    params.filter_mode = _abi.FILTER_TILE_PARTIALS
+    h.begin_frame(params)
+    h.add_grid_block(dev_grids)
+    tiled_ms, tiled_stage = timed(step_resident, max(3, args.steps // 2), 2)
+    params.filter_mode = _abi.FILTER_REFERENCE_ORDER
+
+    e2e = None
+    if not args.no_e2e:
+        e_ms, _ = timed(step_e2e, max(3, args.steps // 2), 2)
+        s2 = h.stats()
+        e2e = {"value": n_mp_total / (e_ms * 1e-3) / 1e6, "unit": "Mpolys/s", "ms_per_step": e_ms,
+               "h2d_bytes_per_step": int(s2["h2d_bytes"]), "d2h_bytes_per_step": int(s2["d2h_bytes"])}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+        hide_ms = stage["render_mpgs_ms"]
+        # dominant kernel: k_hide.  Algorithmic bytes of one launch = the vertex data of the grids this
+        # rank hides, V*(12K+24) (sample state stays on chip and is not compulsory traffic).
+        nvb = b_alg_mine - (params.crop_xmax - params.crop_xmin) * (params.crop_ymax - params.crop_ymin) * (36 + es_d)
+        achieved = nvb / (hide_ms * 1e-3) / 1e9 if hide_ms > 0 else 0.0
+        frame_achieved = b_alg_total / (ms * 1e-3) / 1e9
+        line = {
+            "metric": "hide+filter throughput", "value": n_mp_total / (ms * 1e-3) / 1e6, "unit": "Mpolys/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "msamples_per_s": n_samples_total / (ms * 1e-3) / 1e6, "frame_ms": ms,
+            "config": {"workload": WORKLOADS[args.config] + ("" if args.scale == 1.0 else f" [scale {args.scale}]"),
+                       "micropolygons": n_mp_total, "samples": n_samples_total,
+                       "l2_policy": "inputs (>= 0.8 GB) and sample planes (>= 4 GB) exceed the 126 MB L2",
+                       "parallelism": f"{world} rank(s), {args.strip_rows}-row strips round-robin, NCCL gather"},
+            "stages_ms": {k: round(v, 4) for k, v in stage.items() if k.endswith("_ms")},
+            "gpu_launches": int(stage["launches"]),
+            "roofline": {"bound": "hbm", "kernel": "k_hide", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frame_achieved_gbs": frame_achieved, "frame_frac": frame_achieved / peak,
+                         "algorithmic_bytes_frame": int(b_alg_total)},
+            "filter_mode": "reference-order (bit-exact sums)",
+            "tile_partials_mode": {"ms_per_step": tiled_ms, "stages_ms": {k: round(v, 4) for k, v in tiled_stage.items() if k.endswith("_ms")}},
+            "clocks": clocks, "e2e": e2e,
+            "counters": {k: int(stats[k]) for k in ("n_grids", "n_vertices", "n_micropolygons", "n_bin_entries", "n_deep_hits")},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(args.config)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -87,6 +87,17 @@ enum {
 
 enum { AQH_MAX_DISPLAYS = 8, AQH_MAX_DISPLAY_CHANNELS = 16 };
 
+/* How the pixel filter sums are associated (the SET of samples and the weights are always the
+ * reference's: inclusion by jittered position, weight by sub-pixel cell centre).
+ *   REFERENCE_ORDER one running sum per output pixel in the reference's fy, fx, sy, sx order
+ *                   (bucketprocessor.cpp:597-629): bit-identical float results, at the price of
+ *                   writing every resolved sample to HBM once.  The default.
+ *   TILE_PARTIALS   per (source pixel, filter tap) partial sums over the pixel's samples, formed
+ *                   on chip by the hide kernel, then summed over the taps: deterministic, but the
+ *                   different association shows as rounding noise (~1e-6 relative for positive
+ *                   filters, up to ~1e-4 on dark pixels under negative-lobed filters). */
+enum { AQH_FILTER_REFERENCE_ORDER = 0, AQH_FILTER_TILE_PARTIALS = 1 };
+
 /* RtFilterFunc (include/aqsis/ri/ritypes.h:56): only ever tabulated on the host
  * (bucketprocessor.cpp:850), so a user filter works unchanged. */
 typedef float (*AqhFilterFunc)(float x, float y, float xwidth, float ywidth);
@@ -130,7 +141,8 @@ typedef struct AqhFrameParams
 	int32_t rank, world_size;       /* image strips are dealt round-robin to ranks; 0,1 = whole image */
 	int32_t strip_rows;             /* strip height in pixel rows (multiple of the tile height); 0 = default */
 	int32_t deep_hits_per_sample;   /* average capacity of the transparent hit pool; 0 = default */
-	int32_t reserved[8];
+	int32_t filter_mode;            /* AQH_FILTER_*; 0 = AQH_FILTER_REFERENCE_ORDER (bit-exact sums) */
+	int32_t reserved[7];
 } AqhFrameParams;
 
 /* One shaded grid as CqMicroPolyGrid::Split sees it (micropolygon.cpp:641-892, motion :946-1156).

@@ -22,7 +22,9 @@
 #include <cfloat>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <new>
 #include <limits>
 #include <thread>
 #include <vector>
@@ -548,25 +550,47 @@ struct SampleData                     // SqSampleData, imagepixel.h:122-151
 };
 struct Image
 {
-	std::vector<SampleData> samples;   // sw*sh*n
-	std::vector<int> dofOffsetIndices; // sw*sh*n
+	// Raw storage: each pixel's samples are constructed by the bucket that owns the pixel
+	// (setSamples) so that first-touch and construction are spread over the worker threads
+	// instead of serialising a multi-hundred-MB value-initialisation.
+	SampleData* samples;               // sw*sh*n
+	int* dofOffsetIndices;             // sw*sh*n
+	size_t count;
+	Image() : samples(0), dofOffsetIndices(0), count(0) {}
+	void allocate(size_t n)
+	{
+		count = n;
+		samples = static_cast<SampleData*>(std::malloc(n*sizeof(SampleData)));
+		dofOffsetIndices = static_cast<int*>(std::malloc(n*sizeof(int)));
+	}
+	~Image() { std::free(samples); std::free(dofOffsetIndices); }
 };
 
 // CqImagePixel::clear + setSamples, imagepixel.cpp:105-122, 334-359
-void setSamples(const Frame& f, Image& img, int x, int y)
+// The five table picks of one pixel, drawn in setSamples order (imagepixel.cpp:338-347) from the
+// global stream: getShuffledIndices, get2DSamples (positions), get2DSamples (dofOffsets),
+// get1DSamples (times), get1DSamples (lods); each is RandomInt(m_cacheSize) (multijitter.cpp:205-222).
+struct PixelPicks { uint8_t shuf, pos, dof, time, lod; };
+inline PixelPicks drawPixelPicks(bool jitter)
+{
+	PixelPicks k = {0, 0, 0, 0, 0};
+	if(jitter)
+	{
+		k.shuf = uint8_t(g_rng.randomInt(250));
+		k.pos = uint8_t(g_rng.randomInt(250));
+		k.dof = uint8_t(g_rng.randomInt(250));
+		k.time = uint8_t(g_rng.randomInt(250));
+		k.lod = uint8_t(g_rng.randomInt(250));
+	}
+	return k;
+}
+
+void setSamples(const Frame& f, Image& img, int x, int y, const PixelPicks& pk)
 {
 	const int n = f.n;
 	const Sampler& s = f.sampler;
 	size_t base = (size_t(y - f.sy0)*f.sw + (x - f.sx0))*n;
-	int iShuf = 0, iPos = 0, iDof = 0, iTime = 0, iLod = 0;
-	if(s.jitter)
-	{
-		iShuf = g_rng.randomInt(250);    // getShuffledIndices, multijitter.cpp:217-221
-		iPos = g_rng.randomInt(250);     // get2DSamples (positions)
-		iDof = g_rng.randomInt(250);     // get2DSamples (dofOffsets)
-		iTime = g_rng.randomInt(250);    // get1DSamples (times)
-		iLod = g_rng.randomInt(250);     // get1DSamples (lods)
-	}
+	const int iShuf = pk.shuf, iPos = pk.pos, iDof = pk.dof, iTime = pk.time, iLod = pk.lod;
 	const int* shuffledIndices = &s.shuf[size_t(iShuf)*n];
 	const F* positions = &s.pos[size_t(iPos)*n*2];
 	const F* dofOffsets = &s.pos[size_t(iDof)*n*2];
@@ -576,7 +600,7 @@ void setSamples(const Frame& f, Image& img, int x, int y)
 	V2 offset{F(x), F(y)};
 	for(int i = 0; i < n; ++i)
 	{
-		SampleData& sd = img.samples[base+i];
+		SampleData& sd = *new (&img.samples[base+i]) SampleData();
 		sd.occludingHit.flags = 0;
 		sd.occlZ = FLT_MAX;
 		sd.data.clear();
@@ -1736,8 +1760,11 @@ int orc_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* chann
 	calculateDofBounds(f.xs, f.ys, f.dofBounds);
 
 	Image img;
-	img.samples.resize(size_t(f.sw)*f.sh*f.n);
-	img.dofOffsetIndices.resize(size_t(f.sw)*f.sh*f.n);
+	img.allocate(size_t(f.sw)*f.sh*f.n);
+	if(!img.samples || !img.dofOffsetIndices) return AQH_ERR_NO_MEMORY;
+	// The table picks are drawn here, sequentially, in the reference's order; copying the picked
+	// tables into the pixels (the rest of setSamples) is done by the bucket that owns the pixel.
+	std::vector<PixelPicks> picks(size_t(f.sw)*f.sh);
 
 	// ---- bucket table + the sequential RNG replay (preProcess per bucket, then the display's
 	// dither draws) in the reference's row-major bucket order, imagebuffer.cpp:708-733.
@@ -1765,7 +1792,7 @@ int orc_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* chann
 			bk.sampleRegion = Region{sminx, sminy, smaxx, smaxy};
 			for(int y = sminy; y < smaxy; ++y)
 				for(int x = sminx; x < smaxx; ++x)
-					setSamples(f, img, x, y);
+					picks[size_t(y - f.sy0)*f.sw + (x - f.sx0)] = drawPixelPicks(f.sampler.jitter);
 			for(int d = 0; d < p.n_displays; ++d)
 				for(int y = 0; y < bk.ySize; ++y)
 					for(int x = 0; x < bk.xSize; ++x)
@@ -1842,6 +1869,9 @@ int orc_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* chann
 		BucketCtx ctx;
 		ctx.f = &f; ctx.img = &img; ctx.sampleRegion = bk.sampleRegion; ctx.hasValidSamples = false;
 		ctx.splCount = ctx.splBoundHits = ctx.splHits = ctx.deepHits = 0;
+		for(int y = bk.sampleRegion.yMin; y < bk.sampleRegion.yMax; ++y)
+			for(int x = bk.sampleRegion.xMin; x < bk.sampleRegion.xMax; ++x)
+				setSamples(f, img, x, y, picks[size_t(y - f.sy0)*f.sw + (x - f.sx0)]);
 		MicroPoly mp;
 		for(size_t i = 0; i < bk.mps.size(); ++i)
 		{
@@ -1916,6 +1946,11 @@ int orc_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* chann
 		if(nthreads <= 1) { tFilter += b - a; tDisplay += c - b; }
 	});
 	double t4 = nowSec();
+	parallelFor(f.sh, nthreads, [&](int row)
+	{
+		SampleData* sd = img.samples + size_t(row)*f.sw*f.n;
+		for(size_t i = 0; i < size_t(f.sw)*f.n; ++i) sd[i].~SampleData();
+	});
 	if(stats)
 	{
 		std::memset(stats, 0, sizeof(*stats));

@@ -38,10 +38,18 @@ def add_grids_one_by_one(h, grids):
         ko += nk
 
 
-def compare(ch_gpu, disp_gpu, ch_ref, disp_ref, float_rtol=FLOAT_RTOL, quant_atol=QUANT_ATOL):
-    """Returns a dict of error measures; raises AssertionError beyond tolerance."""
+def compare(ch_gpu, disp_gpu, ch_ref, disp_ref, float_rtol=FLOAT_RTOL, quant_atol=QUANT_ATOL, strict_special=True):
+    """Returns a dict of error measures; raises AssertionError beyond tolerance.
+
+    strict_special=False (tile-partials filter mode): where the reference's filtered depth is not
+    a finite ordinary number (sums involving FLT_MAX depths overflow, and how depends on the order
+    of the additions) the z channel is not compared."""
     a = ch_gpu.astype(np.float64)
     b = ch_ref.astype(np.float64)
+    if not strict_special:
+        bad = ~(np.isfinite(b[..., 7]) & (np.abs(b[..., 7]) < 1e30))
+        a = a.copy()
+        a[..., 7] = np.where(bad, b[..., 7], a[..., 7])
     finite = np.isfinite(a) & np.isfinite(b) & (np.abs(b) < 1e30)
     # relative error against max(|ref|, small floor) so that exact zeros compare absolutely
     denom = np.maximum(np.abs(b), 1e-3)
