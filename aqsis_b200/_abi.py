@@ -137,20 +137,6 @@ class FrameStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-class OrcStats(C.Structure):
-    """oracle/oracle_hider.h OrcStats (lives here so tests and bench share one definition)."""
-    _fields_ = [
-        ("prepare_s", C.c_double), ("bust_s", C.c_double), ("render_s", C.c_double), ("combine_s", C.c_double),
-        ("filter_s", C.c_double), ("display_s", C.c_double), ("total_s", C.c_double),
-        ("n_micropolygons", C.c_int64), ("n_bucket_entries", C.c_int64), ("n_samples", C.c_int64),
-        ("spl_count", C.c_int64), ("spl_bound_hits", C.c_int64), ("spl_hits", C.c_int64),
-        ("n_deep_hits", C.c_int64), ("threads", C.c_int32),
-    ]
-
-    def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
-
-
 TYPE_SIZES = {FLOAT32: 4, UNSIGNED32: 4, SIGNED32: 4, UNSIGNED16: 2, SIGNED16: 2, UNSIGNED8: 1, SIGNED8: 1}
 TYPE_NUMPY = {FLOAT32: "float32", UNSIGNED32: "uint32", SIGNED32: "int32", UNSIGNED16: "uint16",
               SIGNED16: "int16", UNSIGNED8: "uint8", SIGNED8: "int8"}

@@ -273,8 +273,25 @@ int uploadTables(AqhHider* h)
 	return AQH_OK;
 }
 
-// Strips of pixel rows dealt round-robin to the ranks; every rank also hides the `shift` rows
-// of halo samples its filter footprint needs.
+// Strips of pixel rows dealt round-robin to the ranks.  The strip height is a
+// multiple of 16 rows so that it is a multiple of every tile height chooseTile can pick.
+int stripRows(const AqhFrameParams& p)
+{
+	int strip = p.strip_rows > 0 ? p.strip_rows : 64;
+	return std::max(16, (strip/16)*16);
+}
+void computeStrips(const AqhFrameParams& p, int rank, std::vector<std::pair<int,int>>& strips)
+{
+	const int world = std::max(1, p.world_size);
+	const int strip = stripRows(p);
+	strips.clear();
+	int si = 0;
+	for(int y0 = p.crop_ymin; y0 < p.crop_ymax; y0 += strip, ++si)
+		if(si % world == (world > 1 ? rank : 0))
+			strips.push_back(std::make_pair(y0, std::min(y0 + strip, p.crop_ymax)));
+}
+
+// Every rank also hides the `shift` rows of halo samples its filter footprint needs.
 void buildTiling(AqhHider* h, bool mbdof)
 {
 	const AqhFrameParams& p = h->params;
@@ -282,20 +299,13 @@ void buildTiling(AqhHider* h, bool mbdof)
 	chooseTile(p, mbdof, h->tileW, h->tileH);
 	h->ntx = (L.sw + h->tileW - 1)/h->tileW;
 	h->nty = (L.sh + h->tileH - 1)/h->tileH;
-	const int world = std::max(1, p.world_size);
-	int strip = p.strip_rows > 0 ? p.strip_rows : 64;
-	strip = std::max(h->tileH, (strip/h->tileH)*h->tileH);
 	h->rowOwned.assign(p.yres, 0);
-	h->strips.clear();
+	computeStrips(p, p.rank, h->strips);
 	std::vector<uint8_t> rowNeeded(L.sh, 0);
-	int si = 0;
-	for(int y0 = p.crop_ymin; y0 < p.crop_ymax; y0 += strip, ++si)
+	for(const auto& s : h->strips)
 	{
-		if(si % world != (world > 1 ? p.rank : 0)) continue;
-		const int y1 = std::min(y0 + strip, p.crop_ymax);
-		h->strips.push_back(std::make_pair(y0, y1));
-		for(int y = y0; y < y1; ++y) h->rowOwned[y] = 1;
-		for(int y = y0 - L.shiftY; y < y1 + L.shiftY; ++y) rowNeeded[y - L.sy0] = 1;
+		for(int y = s.first; y < s.second; ++y) h->rowOwned[y] = 1;
+		for(int y = s.first - L.shiftY; y < s.second + L.shiftY; ++y) rowNeeded[y - L.sy0] = 1;
 	}
 	h->tileSlot.assign(size_t(h->ntx)*h->nty, -1);
 	h->activeTiles.clear();
@@ -913,6 +923,22 @@ int aqh_device_display(const AqhHider* h, int display, void** dev_ptr, size_t* b
 	if(!h->rendered) return AQH_ERR_STATE;
 	*dev_ptr = h->dDisplay[display].p;
 	if(bytes) *bytes = size_t(h->params.xres)*h->params.yres*h->dispEntry[display];
+	return AQH_OK;
+}
+
+int aqh_strip_layout(const AqhFrameParams* p, int rank, int* n_strips, int* y0, int* y1, int capacity)
+{
+	if(!p || !n_strips || p->crop_ymax <= p->crop_ymin) return AQH_ERR_BAD_PARAMS;
+	const int world = std::max(1, p->world_size);
+	if(rank < 0 || rank >= world) return AQH_ERR_BAD_PARAMS;
+	std::vector<std::pair<int,int>> strips;
+	computeStrips(*p, rank, strips);
+	*n_strips = (int)strips.size();
+	for(int i = 0; i < (int)strips.size() && i < capacity; ++i)
+	{
+		if(y0) y0[i] = strips[i].first;
+		if(y1) y1[i] = strips[i].second;
+	}
 	return AQH_OK;
 }
 

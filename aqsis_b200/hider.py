@@ -52,6 +52,7 @@ def lib():
     L.aqh_image_display.argtypes = [vp, ci, C.POINTER(C.POINTER(C.c_ubyte)), C.POINTER(ci), C.POINTER(ci)]
     L.aqh_device_channels.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.aqh_device_display.argtypes = [vp, ci, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.aqh_strip_layout.argtypes = [C.POINTER(FrameParams), ci, C.POINTER(ci), vp, vp, ci]
     L.aqh_num_strips.argtypes = [vp, C.POINTER(ci)]
     L.aqh_strip.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci)]
     for name in ("box", "triangle", "gaussian", "catmullrom", "sinc", "mitchell", "disk", "bessel"):

@@ -92,51 +92,6 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def split_grids_for_rank(params, grids, rank, world, strip_rows):
-    """Keep the grids whose (motion/DoF/filter-expanded) y-range touches a strip owned by `rank`."""
-    from aqsis_b200 import GridArrays
-    if world == 1:
-        return grids
-    nv = (grids.cu.astype(np.int64) + 1) * (grids.cv.astype(np.int64) + 1)
-    nk = grids.nkeys.astype(np.int64) if grids.nkeys is not None else np.ones_like(nv)
-    pstart = np.concatenate([[0], np.cumsum(nv * nk)])
-    vstart = np.concatenate([[0], np.cumsum(nv)])
-    y = np.asarray(grids.P)[:, 1]
-    z = np.asarray(grids.P)[:, 2]
-    ymin = np.minimum.reduceat(y, pstart[:-1])
-    ymax = np.maximum.reduceat(y, pstart[:-1])
-    pad = np.floor(params.filter_ywidth / 2.0) + 1.0
-    if params.use_dof:
-        zmin = np.minimum.reduceat(z, pstart[:-1])
-        zmax = np.maximum.reduceat(z, pstart[:-1])
-        coc = lambda zz: params.dof_multiplier * np.abs(1.0 / zz - params.dof_one_over_focal_distance) * params.dof_scale_y
-        pad = pad + np.maximum(coc(zmin), coc(zmax))
-    lo = np.floor(ymin - pad).astype(np.int64)
-    hi = np.ceil(ymax + pad).astype(np.int64)
-    keep = np.zeros(grids.n_grids, dtype=bool)
-    y0 = params.crop_ymin
-    si = 0
-    while y0 < params.crop_ymax:
-        y1 = min(y0 + strip_rows, params.crop_ymax)
-        if si % world == rank:
-            keep |= (hi >= y0) & (lo < y1)
-        y0 = y1
-        si += 1
-    idx = np.nonzero(keep)[0]
-    pos_idx = np.concatenate([np.arange(pstart[g], pstart[g + 1]) for g in idx]) if len(idx) else np.zeros(0, np.int64)
-    vert_idx = np.concatenate([np.arange(vstart[g], vstart[g + 1]) for g in idx]) if len(idx) else np.zeros(0, np.int64)
-    kt = None
-    if grids.key_times is not None:
-        kstart = np.concatenate([[0], np.cumsum(nk)])
-        kt = np.concatenate([grids.key_times[kstart[g]:kstart[g + 1]] for g in idx]) if len(idx) else np.zeros(0, np.float32)
-    return GridArrays(cu=grids.cu[idx], cv=grids.cv[idx], flags=grids.flags[idx], P=np.asarray(grids.P)[pos_idx],
-                      Ci=None if grids.Ci is None else np.asarray(grids.Ci)[vert_idx],
-                      Oi=None if grids.Oi is None else np.asarray(grids.Oi)[vert_idx],
-                      nkeys=None if grids.nkeys is None else grids.nkeys[idx], key_times=kt,
-                      lod_bounds=None if grids.lod_bounds is None else grids.lod_bounds.reshape(-1, 2)[idx].ravel(),
-                      culled=None if grids.culled is None else np.asarray(grids.culled)[vert_idx])
-
-
 class _CudaArray:
     """Expose a raw device pointer to torch through __cuda_array_interface__."""
 
@@ -221,7 +176,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from aqsis_b200 import Hider, build, scenes
+    from aqsis_b200 import Hider, build, scenes, sharding
     from aqsis_b200.hider import display_info
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -245,7 +200,7 @@ def main():
     n_mp_total = grids.n_micropolygons
     n_samples_total = (params.crop_xmax - params.crop_xmin) * (params.crop_ymax - params.crop_ymin) * params.xsamples * params.ysamples
     b_alg_total = scenes.algorithmic_bytes(params, grids)
-    mine = split_grids_for_rank(params, grids, rank, world, args.strip_rows)
+    mine = sharding.split_grids_for_rank(params, grids, rank, world)
     b_alg_mine = scenes.algorithmic_bytes(params, mine) if world > 1 else b_alg_total
     del grids
 
@@ -255,23 +210,13 @@ def main():
     pin_grids = mine.to_torch(pin=True)
     h2d_bytes = sum(int(t.numel() * t.element_size()) for t in (pin_grids.P, pin_grids.Ci, pin_grids.Oi) if t is not None)
 
-    # ---- gather plumbing: rows owned by each rank, padded to equal size
+    # ---- gather plumbing: rows owned by each rank (index tensors built once)
     h.begin_frame(params)
     h.add_grid_block(dev_grids)
     h.render_device()
-    strips = h.strips()
-    rows = np.concatenate([np.arange(a, b) for a, b in strips]) if strips else np.zeros(0, np.int64)
+    assert h.strips() == sharding.strips_for_rank(params, rank)
     dtype_d, nch_d, es_d = display_info(params, 0) if params.n_displays else (np.dtype("uint8"), 0, 0)
-    if world > 1:
-        nrows = torch.tensor([len(rows)], device=dev)
-        allrows = [torch.zeros_like(nrows) for _ in range(world)]
-        dist.all_gather(allrows, nrows)
-        max_rows = int(max(int(t.item()) for t in allrows))
-        row_idx = torch.zeros(max_rows, dtype=torch.long, device=dev)
-        row_idx[:len(rows)] = torch.from_numpy(rows).to(dev)
-        gathered_rows = [torch.zeros(max_rows, dtype=torch.long, device=dev) for _ in range(world)]
-        dist.all_gather(gathered_rows, row_idx)
-        counts = [int(t.item()) for t in allrows]
+    gather = sharding.ImageGather(params, rank, world, dev, dist if world > 1 else None)
 
     def device_images():
         pc, _ = h.device_channels()
@@ -287,29 +232,10 @@ def main():
     def gather_image():
         """Final image to rank 0 over NCCL (the only collective of the path)."""
         ch, dsp = device_images()
-        if world == 1:
-            final["channels"], final["display"] = ch, dsp
-            return
-        send_c = ch.index_select(0, row_idx)
-        send_d = dsp.index_select(0, row_idx) if dsp is not None else None
-        if rank == 0:
-            rc = [torch.empty_like(send_c) for _ in range(world)]
-            dist.gather(send_c, rc, dst=0)
-            full_c = torch.zeros_like(ch)
-            for r in range(world):
-                full_c.index_copy_(0, gathered_rows[r][:counts[r]], rc[r][:counts[r]])
-            final["channels"] = full_c
-            if send_d is not None:
-                rd = [torch.empty_like(send_d) for _ in range(world)]
-                dist.gather(send_d, rd, dst=0)
-                full_d = torch.zeros_like(dsp)
-                for r in range(world):
-                    full_d.index_copy_(0, gathered_rows[r][:counts[r]], rd[r][:counts[r]])
-                final["display"] = full_d
-        else:
-            dist.gather(send_c, None, dst=0)
-            if send_d is not None:
-                dist.gather(send_d, None, dst=0)
+        res = gather([ch] if dsp is None else [ch, dsp])
+        if res is not None:
+            final["channels"] = res[0]
+            final["display"] = res[1] if len(res) > 1 else None
 
     def step_resident():
         h.render_device()

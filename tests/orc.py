@@ -10,7 +10,21 @@ import subprocess
 import numpy as np
 
 from aqsis_b200 import _abi as abi
-from aqsis_b200._abi import FrameParams, GridBlock, DisplayDesc, OrcStats
+from aqsis_b200._abi import FrameParams, GridBlock, DisplayDesc
+
+class OrcStats(C.Structure):
+    """OrcStats of oracle/oracle_hider.h."""
+    _fields_ = [
+        ("prepare_s", C.c_double), ("bust_s", C.c_double), ("render_s", C.c_double), ("combine_s", C.c_double),
+        ("filter_s", C.c_double), ("display_s", C.c_double), ("total_s", C.c_double),
+        ("n_micropolygons", C.c_int64), ("n_bucket_entries", C.c_int64), ("n_samples", C.c_int64),
+        ("spl_count", C.c_int64), ("spl_bound_hits", C.c_int64), ("spl_hits", C.c_int64),
+        ("n_deep_hits", C.c_int64), ("threads", C.c_int32),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")

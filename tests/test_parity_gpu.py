@@ -103,3 +103,89 @@ def test_empty_frame(gpu_hider):
     ch, disp = gpu_hider.end_frame()
     assert np.all(ch[..., :7] == 0) and np.all(ch[..., abi.CH_Z] == np.float32(3.4028234663852886e38))
     assert disp[0].max() <= 1      # dither only
+
+
+# ---- the hand-derivable scenes of tests/test_oracle_render.py, through the CUDA path
+def _kat_scenes():
+    from test_oracle_render import one_grid, params_1spp
+    out = []
+    p = params_1spp()
+    out.append(("rectangle", p, one_grid([2.25, 6.75], [1.25, 4.75], z=7.0)))
+    for i, (xs, ys) in enumerate([([2.5, 4.5, 6.5], [1.25, 4.75]), ([2.25, 6.75], [1.5, 3.5, 5.5]), ([2.5, 4.5, 6.5], [1.5, 3.5, 5.5])]):
+        out.append((f"shared-edge-{i}", params_1spp(), one_grid(xs, ys, ci=(0.5, 0.5, 0.5), oi=(0.5, 0.5, 0.5))))
+    a = one_grid([1.25, 8.75], [1.25, 6.75], z=4.0, ci=(0, 0, 1))
+    b = one_grid([1.25, 8.75], [1.25, 6.75], z=4.0, ci=(1, 1, 0))
+    out.append(("depth-tie", params_1spp(), scenes.concat([a, b])))
+    back = one_grid([1.25, 8.75], [1.25, 6.75], z=9.0, ci=(0.0, 0.5, 1.0))
+    mid = one_grid([1.25, 8.75], [1.25, 6.75], z=6.0, ci=(0.125, 0.125, 0.0), oi=(0.25, 0.25, 0.25))
+    front = one_grid([1.25, 8.75], [1.25, 6.75], z=3.0, ci=(0.5, 0.0, 0.25), oi=(0.5, 0.5, 0.5))
+    out.append(("layers", params_1spp(), scenes.concat([mid, front, back])))
+    g = one_grid([1.25, 3.25, 5.25, 7.25], [1.25, 6.75], ci=(1, 1, 1))
+    g.culled = np.array([0, 1, 0, 0, 0, 0, 0, 0], np.uint8)
+    out.append(("culled", params_1spp(), g))
+    pe = params_1spp(exposure=(2.0, 2.0), displays=[("rgba", 1, 255.0, 0.0, 255.0, 0.0), ("rgb", 1, 1000.0, 10.0, 600.0, 0.0),
+                                                    ("rgbaz", 0, 0.0, 0.0, 0.0, 0.0)])
+    out.append(("exposure-displays", pe, one_grid([-2, 12], [-2, 10], ci=(0.02, 0.125, 0.5))))
+    return out
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_known_answer_scenes_bit_exact(gpu_hider, mode):
+    for name, p, g in _kat_scenes():
+        p.filter_mode = mode
+        ch_g, disp_g, _ = pu.run_product(gpu_hider, p, g)
+        import orc
+        ch_r, disp_r, _ = orc.render(p, g, 1)
+        assert np.array_equal(ch_g.view(np.uint32), ch_r.view(np.uint32)), name
+        for a, b in zip(disp_g, disp_r):
+            assert np.array_equal(a, b), name
+
+
+def test_bucket_callbacks_in_reference_order(gpu_hider):
+    """on_bucket / on_data fire once per bucket, row-major (imagebuffer.cpp:708-733), and tile the image."""
+    p, g = scenes.config1(scale=0.1)
+    gpu_hider.begin_frame(p)
+    gpu_hider.add_grid_block(g)
+    seen, data, prog = [], [], []
+    img = np.zeros((p.yres, p.xres, 9), np.float32)
+    q = np.zeros((p.yres, p.xres, 4), np.uint8)
+
+    def on_bucket(x0, x1, y0, y1, ch):
+        seen.append((y0, x0))
+        img[y0:y1, x0:x1] = ch
+
+    def on_data(d, x0, x1, y0, y1, es, buf):
+        assert d == 0 and es == 4
+        q[y0:y1, x0:x1] = buf.reshape(y1 - y0, x1 - x0, 4)
+        data.append((y0, x0))
+
+    ch, disp = gpu_hider.end_frame(on_bucket=on_bucket, on_data=on_data, on_progress=prog.append)
+    assert seen == sorted(seen) and seen == data and len(seen) == ((p.xres + 15) // 16) * ((p.yres + 15) // 16)
+    assert np.array_equal(img, ch) and np.array_equal(q, disp[0])
+    assert prog[-1] == 100.0 and all(b >= a for a, b in zip(prog, prog[1:]))
+
+
+def test_errors_are_statuses_not_crashes(gpu_hider):
+    from aqsis_b200 import HiderError
+    p = default_params(resolution=(32, 32))
+    p.xsamples = 0
+    with pytest.raises(HiderError) as e:
+        gpu_hider.begin_frame(p)
+    assert e.value.status == abi.AQH_ERR_BAD_PARAMS
+    p = default_params(resolution=(32, 32))
+    p.depth_filter = abi.DEPTHFILTER_MIDPOINT
+    with pytest.raises(HiderError) as e:
+        gpu_hider.begin_frame(p)
+    assert e.value.status == abi.AQH_ERR_UNSUPPORTED
+    p = default_params(resolution=(32, 32))
+    gpu_hider.begin_frame(p)
+    from test_oracle_render import one_grid
+    g = one_grid([1, 5], [1, 5])
+    g.flags[:] = abi.GRID_USES_CSG
+    with pytest.raises(HiderError) as e:
+        gpu_hider.add_grid_block(g)
+    assert e.value.status == abi.AQH_ERR_UNSUPPORTED
+    gpu_hider.end_frame()
+    with pytest.raises(HiderError) as e:
+        gpu_hider.add_grid_block(g)
+    assert e.value.status == abi.AQH_ERR_STATE

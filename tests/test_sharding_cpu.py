@@ -1,0 +1,121 @@
+"""The N>1 path on CPU: strip dealing, grid replication and the final gather over gloo (world_size 2 and 3).
+
+Each rank runs the ORACLE on only the grids sharding.split_grids_for_rank hands it and keeps only the
+pixel rows it owns; the rows gathered on rank 0 must equal a single-process oracle render of the whole
+frame bit for bit.  That proves (i) straddling grids are replicated to every rank that needs them,
+halo and depth-of-field growth included, (ii) the strips partition the image, (iii) the gather puts
+every row in place.  On the GPU box the same sharding module drives the CUDA hider over NCCL.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _scene(kind):
+    from aqsis_b200 import scenes
+    if kind == "static":
+        p, g = scenes.config1(scale=0.2)
+    elif kind == "mbdof":
+        p, g = scenes.config3(scale=0.05, motion_px=6.0)
+    else:
+        p, g = scenes.config4(scale=0.02)
+    p.strip_rows = 16
+    return p, g
+
+
+def _worker(rank, world, port, kind, outdir):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    import orc
+    from aqsis_b200 import sharding
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        p, g = _scene(kind)
+        p.rank, p.world_size = rank, world
+        mine = sharding.split_grids_for_rank(p, g, rank, world)
+        ch, disp, _ = orc.render(p, mine, 2)
+        rows = sharding.rows_for_rank(p, rank)
+        keep = np.zeros(p.yres, bool)
+        keep[rows] = True
+        ch[~keep] = 0
+        disp[0][~keep] = 0
+        gather = sharding.ImageGather(p, rank, world, torch.device("cpu"), dist)
+        res = gather([torch.from_numpy(ch.reshape(p.yres, -1)), torch.from_numpy(disp[0].reshape(p.yres, -1))])
+        frac = torch.tensor([mine.n_grids / g.n_grids])
+        fr = [torch.zeros(1) for _ in range(world)]
+        dist.all_gather(fr, frac)
+        if rank == 0:
+            np.savez(os.path.join(outdir, "gathered.npz"), ch=res[0].numpy(), disp=res[1].numpy(),
+                     frac=np.array([float(f) for f in fr]))
+        else:
+            assert res is None
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+@pytest.mark.parametrize("kind,world", [("static", 2), ("mbdof", 2), ("deep", 3)])
+def test_sharded_render_equals_single_process(tmp_path, kind, world):
+    import torch.multiprocessing as mp
+    import orc
+    orc.lib()                      # build the oracle once, before the ranks race for it
+    mp.spawn(_worker, args=(world, _free_port(), kind, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(os.path.join(tmp_path, "gathered.npz"))
+    p, g = _scene(kind)
+    ch, disp, _ = orc.render(p, g, 4)
+    assert np.array_equal(got["ch"].view(np.uint32), ch.reshape(p.yres, -1).view(np.uint32))
+    assert np.array_equal(got["disp"], disp[0].reshape(p.yres, -1))
+    # grids are replicated only where they straddle: the shares add up to a bit more than one frame
+    assert 1.0 <= got["frac"].sum() < 1.0 + 0.9 * world / 2, got["frac"]
+
+
+def test_strips_partition_the_crop_window(native_lib):
+    from aqsis_b200 import default_params, sharding
+    for yres, crop, strip, world in [(200, None, 0, 1), (200, None, 32, 3), (1080, None, 64, 8), (97, (0, 50, 7, 91), 16, 4),
+                                     (64, None, 40, 2)]:
+        kw = dict(resolution=(50, yres))
+        if crop:
+            kw["crop"] = crop
+        p = default_params(**kw)
+        p.world_size, p.strip_rows = world, strip
+        owner = -np.ones(yres, int)
+        for r in range(world):
+            for y0, y1 in sharding.strips_for_rank(p, r):
+                assert np.all(owner[y0:y1] == -1)
+                owner[y0:y1] = r
+                assert (y0 - p.crop_ymin) % 16 == 0
+        assert np.all(owner[p.crop_ymin:p.crop_ymax] >= 0)
+        assert np.all(owner[:p.crop_ymin] == -1) and np.all(owner[p.crop_ymax:] == -1)
+        if world > 1 and (p.crop_ymax - p.crop_ymin) >= 16 * world * max(1, strip // 16):
+            assert len(set(owner[p.crop_ymin:p.crop_ymax])) == world
+
+
+def test_split_keeps_grid_payload_intact(native_lib):
+    from aqsis_b200 import scenes, sharding
+    p, g = scenes.config3(scale=0.05)
+    p.world_size, p.strip_rows = 2, 16
+    parts = [sharding.split_grids_for_rank(p, g, r, 2) for r in range(2)]
+    for part in parts:
+        assert part.P.shape[0] == int(((part.cu + 1) * (part.cv + 1) * part.nkeys).sum())
+        assert part.Ci.shape[0] == part.n_verts and len(part.key_times) == int(part.nkeys.sum())
+    # a grid far from every strip of a rank must not be sent to it
+    lo, hi = sharding.grid_row_ranges(p, g)
+    for r, part in enumerate(parts):
+        touched = np.zeros(g.n_grids, bool)
+        for y0, y1 in sharding.strips_for_rank(p, r):
+            touched |= (hi >= y0) & (lo < y1)
+        assert part.n_grids == int(touched.sum())
