@@ -1,0 +1,472 @@
+// ref_hider.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Drives the REFERENCE's OWN hider, compiled in place from /root/reference by oracle/Makefile
+// (target `refhider`; nothing is copied into this repository, the output is
+// oracle/_ref/libaqsis_refhider.so).  These reference translation units run unmodified:
+//
+//   libs/core/imagebuffer.cpp      CqImageBuffer::SetImage / AddMPG / RenderImage (the bucket loop)
+//   libs/core/bucketprocessor.cpp  preProcess, RenderMicroPoly, RenderMPG_Static, RenderMPG_MBOrDof,
+//                                  StoreSample, CombineElements, FilterBucket, ExposeBucket, overlap caches
+//   libs/core/imagepixel.cpp       CqImagePixel::setSamples / Combine
+//   libs/core/micropolygon.cpp     CqMicroPolygon(+Motion): Initialise, ComputeVertexOrder, bounds, BuildBoundList,
+//                                  CacheHitTestValues, fContains, Sample, CacheOutputInterpCoeffs
+//   libs/core/occlusion.cpp bucket.cpp bound.cpp optioncache.cpp options.cpp parameters.cpp stats.cpp
+//   libs/core/multijitter.cpp grid.cpp filters.cpp csgtree.cpp threadscheduler.cpp
+//   libs/math/random.cpp matrix.cpp color.cpp   libs/util/sstring.cpp logging.cpp
+//
+// What this file supplies around them (and therefore what is NOT the reference's code):
+//   * the render context: a CqRenderer whose constructor and the few members the hider calls are
+//     defined here (renderer.cpp would drag in the RI front end, shader VM and texture system);
+//     every other virtual is a generated abort stub (oracle/gen_ref_stubs.py);
+//     CqRenderer::MinCoCForBound restates libs/core/renderer.cpp:1602-1617;
+//   * a grid class over the caller's P/Ci/Oi arrays (CqMicroPolyGridBase subclass) whose busting
+//     loop restates CqMicroPolyGrid::Split (micropolygon.cpp:770-856) -- the real Split needs
+//     surfaces, attributes and transforms from the geometry front end;
+//   * a display manager that captures each bucket's float channel buffer and quantises it like
+//     CqDisplayRequest::FormatBucketForDisplay (ddmanager.cpp:1022-1118), drawing the dither value
+//     from the reference's global CqRandom in the reference's order.
+// The product never links or loads this library; tests/ and bench.py's CPU legs do.
+#include <vector>
+#include <string>
+#include <aqsis/aqsis.h>
+#include <aqsis/math/random.h>
+#include <aqsis/math/math.h>
+#include <aqsis/math/region.h>
+#include <aqsis/ri/ri.h>
+#include <aqsis/util/file.h>
+#include <aqsis/util/logging.h>
+#include <aqsis/shadervm/ishaderdata.h>
+#include <aqsis/shadervm/ishaderexecenv.h>
+
+#include "renderer.h"
+#include "imagebuffer.h"
+#include "bucketprocessor.h"
+#include "micropolygon.h"
+#include "imagers.h"
+#include "options.h"
+#include "attributes.h"
+#include "stats.h"
+#include "iddmanager.h"
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <list>
+#include <vector>
+
+#include "oracle_hider.h"
+
+[[noreturn]] static void refStubAbort(const char* what)
+{
+	std::fprintf(stderr, "ref_hider: %s is outside the hide+filter path and was stubbed out\n", what);
+	std::abort();
+}
+
+namespace Aqsis {
+
+// ---------------------------------------------------------------------------------------
+// Symbols the hider sources reference but never reach on this path.
+CqRenderer* pCurrRenderer = 0;
+std::list<CqAttributes*> Attribute_stack;
+IqRenderer* QGetRenderContextI() { return pCurrRenderer; }
+boost::shared_ptr<IqShaderExecEnv> IqShaderExecEnv::create(IqRenderer*) { refStubAbort("IqShaderExecEnv::create"); }
+boostfs::path findFileNothrow(const std::string&, const std::string&) { return boostfs::path(); }
+CqImagersource::CqImagersource(const boost::shared_ptr<IqShader>&, bool) { refStubAbort("CqImagersource"); }
+CqImagersource::~CqImagersource() {}
+void CqImagersource::Initialise(const CqRegion&, IqChannelBuffer*) { refStubAbort("CqImagersource::Initialise"); }
+CqColor CqImagersource::Color(TqFloat, TqFloat) { refStubAbort("CqImagersource::Color"); }
+CqColor CqImagersource::Opacity(TqFloat, TqFloat) { refStubAbort("CqImagersource::Opacity"); }
+TqFloat CqImagersource::Alpha(TqFloat, TqFloat) { refStubAbort("CqImagersource::Alpha"); }
+
+// ---------------------------------------------------------------------------------------
+// The render context.
+CqRenderer::CqRenderer()
+	: m_pImageBuffer(0), m_pDDManager(0), m_Mode(RenderMode_Image), m_fSaveGPrims(false), m_fWorldBegin(false),
+	  m_DofMultiplier(0), m_OneOverFocalDistance(FLT_MAX), m_UsingDepthOfField(false), m_DepthOfFieldScale(1, 1),
+	  m_OutputDataOffset(9), m_OutputDataTotalSize(9), m_FrameNo(0), m_pErrorHandler(0), m_abortRender(false),
+	  m_pProgressHandler(0), m_pRaytracer(0),
+	  m_cropWindowXMin(0), m_cropWindowXMax(0), m_cropWindowYMin(0), m_cropWindowYMax(0)
+{
+	m_poptDefault = CqOptionsPtr(new CqOptions);
+}
+CqRenderer::~CqRenderer() {}
+// Private state is reachable only from members, so the frame set-up rides on Initialise().
+static struct RefSetup { const AqhFrameParams* p; CqImageBuffer* image; IqDDManager* dd; } g_refSetup;
+void CqRenderer::Initialise()
+{
+	const AqhFrameParams& p = *g_refSetup.p;
+	m_pImageBuffer = g_refSetup.image;
+	m_pDDManager = g_refSetup.dd;
+	// integer crop window as CqRenderer::initialiseCropWindow leaves it (renderer.cpp:1619-1627)
+	m_cropWindowXMin = p.crop_xmin; m_cropWindowXMax = p.crop_xmax;
+	m_cropWindowYMin = p.crop_ymin; m_cropWindowYMax = p.crop_ymax;
+	// lens constants as SetDepthOfFieldData derives them (renderer.h:368-377); the C ABI carries them derived
+	m_UsingDepthOfField = p.use_dof != 0;
+	m_DofMultiplier = p.dof_multiplier;
+	m_OneOverFocalDistance = p.dof_one_over_focal_distance;
+	m_DepthOfFieldScale = CqVector2D(p.dof_scale_x, p.dof_scale_y);
+}
+const IqOptionsPtr CqRenderer::poptCurrent() const { return m_poptDefault; }
+TqFloat CqRenderer::Time() const { return 0; }
+const TqInt* CqRenderer::GetIntegerOption(const char* n, const char* p) const { return m_poptDefault->GetIntegerOption(n, p); }
+const TqFloat* CqRenderer::GetFloatOption(const char* n, const char* p) const { return m_poptDefault->GetFloatOption(n, p); }
+// libs/core/renderer.cpp:1602-1617 (restated: renderer.cpp is not part of this build)
+const TqFloat CqRenderer::MinCoCForBound(const CqBound& bound) const
+{
+	TqFloat z1 = bound.vecMin().z();
+	TqFloat z2 = bound.vecMax().z();
+	TqFloat focalDist = 1/m_OneOverFocalDistance;
+	if((z1 - focalDist)*(z2 - focalDist) < 0)
+		return 0;
+	TqFloat minBlur = min(std::fabs(1/z1 - m_OneOverFocalDistance), std::fabs(1/z2 - m_OneOverFocalDistance));
+	return m_DofMultiplier * min(m_DepthOfFieldScale.x(), m_DepthOfFieldScale.y()) * minBlur;
+}
+// no arbitrary output variables on this path (StoreExtraData, bucketprocessor.cpp:1573-1643, is a "next" row)
+TqInt CqRenderer::RegisterOutputData(const char*) { return -1; }
+TqInt CqRenderer::OutputDataIndex(const char*) { return -1; }
+TqInt CqRenderer::OutputDataSamples(const char*) { return 0; }
+#include "renderer_stubs.inc"
+
+} // namespace Aqsis
+
+using namespace Aqsis;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------
+// A shader variable that is just a window onto the caller's AoS float array
+// (CqVector3D and CqColor are three packed floats).
+class RefShaderData : public IqShaderData
+{
+public:
+	explicit RefShaderData(float* data) : m_data(data) {}
+	virtual void GetPointPtr(const CqVector3D*& res) const { res = reinterpret_cast<const CqVector3D*>(m_data); }
+	virtual void GetPointPtr(CqVector3D*& res) { res = reinterpret_cast<CqVector3D*>(m_data); }
+	virtual void GetColorPtr(const CqColor*& res) const { res = reinterpret_cast<const CqColor*>(m_data); }
+	virtual void GetColorPtr(CqColor*& res) { res = reinterpret_cast<CqColor*>(m_data); }
+#include "shaderdata_stubs.inc"
+private:
+	float* m_data;
+};
+
+// ---------------------------------------------------------------------------------------
+// One shaded grid as the hider sees it.
+class RefGrid : public CqMicroPolyGridBase
+{
+public:
+	RefGrid(int cu, int cv, float* P, float* Ci, float* Oi, uint32_t flags, const float* lod)
+		: m_cu(cu), m_cv(cv), m_P(P), m_Ci(Ci), m_Oi(Oi)
+	{
+		m_lod[0] = lod ? lod[0] : -1.0f; m_lod[1] = lod ? lod[1] : -1.0f;
+		m_fTriangular = (flags & AQH_GRID_TRIANGULAR) != 0;
+		// CacheGridInfo, micropolygon.cpp:46-66
+		m_CurrentGridInfo.lodBounds = m_lod;
+		m_CurrentGridInfo.matteFlag = (flags & AQH_GRID_MATTE_ALPHA) ? SqImageSample::Flag_MatteAlpha
+		                              : ((flags & AQH_GRID_MATTE) ? SqImageSample::Flag_Matte : 0);
+		m_CurrentGridInfo.usesDataMap = false;
+		m_CurrentGridInfo.useSmoothShading = (flags & AQH_GRID_SMOOTH) != 0;
+	}
+	virtual void Split(long, long, long, long) {}
+	virtual void Shade(bool) {}
+	virtual void TransferOutputVariables() {}
+	virtual void DeleteVariables(bool) {}
+	virtual CqSurface* pSurface() const { return 0; }
+	virtual const IqConstAttributesPtr pAttributes() const { return IqConstAttributesPtr(); }
+	virtual bool usesCSG() const { return false; }
+	virtual boost::shared_ptr<CqCSGTreeNode> pCSGNode() const { return boost::shared_ptr<CqCSGTreeNode>(); }
+	virtual TqInt uGridRes() const { return m_cu; }
+	virtual TqInt vGridRes() const { return m_cv; }
+	virtual TqUint numMicroPolygons(TqInt cu, TqInt cv) const { return cu*cv; }
+	virtual TqUint numShadingPoints(TqInt cu, TqInt cv) const { return (cu+1)*(cv+1); }
+	virtual bool hasValidDerivatives() const { return true; }
+	virtual IqShaderData* pVar(TqInt index)
+	{
+		switch(index)
+		{
+			case EnvVars_P: return &m_P;
+			case EnvVars_Ci: return m_Ci.valid() ? &m_Ci : 0;
+			case EnvVars_Oi: return m_Oi.valid() ? &m_Oi : 0;
+			default: return 0;
+		}
+	}
+	virtual IqShaderData* FindStandardVar(const char*) { return 0; }
+	virtual boost::shared_ptr<IqShaderExecEnv> pShaderExecEnv() { return boost::shared_ptr<IqShaderExecEnv>(); }
+	void addSplitLine(TqFloat time, const CqVector3D& a, const CqVector3D& b)
+	{
+		SqTriangleSplitLine sl;
+		sl.m_TriangleSplitPoint1 = a; sl.m_TriangleSplitPoint2 = b;
+		m_TriangleSplitLine.AddTimeSlot(time, sl);
+	}
+private:
+	struct Var : RefShaderData
+	{
+		explicit Var(float* d) : RefShaderData(d), m_ok(d != 0) {}
+		bool valid() const { return m_ok; }
+		bool m_ok;
+	};
+	int m_cu, m_cv;
+	Var m_P, m_Ci, m_Oi;
+	float m_lod[2];
+};
+
+// ---------------------------------------------------------------------------------------
+// Display manager: captures buckets.  Quantisation restates FormatBucketForDisplay
+// (ddmanager.cpp:1022-1118) and draws its dither from the reference's global CqRandom.
+int typeSize(int type)
+{
+	switch(type)
+	{
+		case AQH_FLOAT32: case AQH_UNSIGNED32: case AQH_SIGNED32: return 4;
+		case AQH_UNSIGNED16: case AQH_SIGNED16: return 2;
+		default: return 1;
+	}
+}
+
+class RefDDManager : public IqDDManager
+{
+public:
+	RefDDManager(const AqhFrameParams& p, float* channels, unsigned char* const* displays)
+		: m_p(p), m_channels(channels), m_displays(displays)
+	{
+		for(int d = 0; d < p.n_displays; ++d)
+		{
+			// selectDataFormat, ddmanager.cpp:249-283
+			const AqhDisplayDesc& dd = p.display[d];
+			int type = dd.type;
+			if(type == 0)
+			{
+				if(dd.quantize_one == 0) type = AQH_FLOAT32;
+				else if(dd.quantize_min >= 0)
+					type = dd.quantize_max <= 255.0f ? AQH_UNSIGNED8 : (dd.quantize_max <= 65535.0f ? AQH_UNSIGNED16 : AQH_UNSIGNED32);
+				else if(dd.quantize_min >= -128.0f && dd.quantize_max <= 127.0f) type = AQH_SIGNED8;
+				else if(dd.quantize_min >= -32768.0f && dd.quantize_max <= 32767.0f) type = AQH_SIGNED16;
+				else type = AQH_SIGNED32;
+			}
+			m_type[d] = type;
+			m_entry[d] = typeSize(type)*dd.n_channels;
+		}
+	}
+	virtual TqInt Initialise() { return 0; }
+	virtual TqInt Shutdown() { return 0; }
+	virtual TqInt AddDisplay(const TqChar*, const TqChar*, const TqChar*, TqInt, TqInt, TqInt, std::map<std::string, void*>) { return 0; }
+	virtual TqInt ClearDisplays() { return 0; }
+	virtual TqInt OpenDisplays(TqInt, TqInt) { return 0; }
+	virtual TqInt CloseDisplays() { return 0; }
+	virtual bool fDisplayNeeds(const TqChar*) { return false; }
+	virtual TqInt Uses() { return 0; }
+	virtual TqInt numDisplayRequests() { return 0; }
+	virtual boost::shared_ptr<IqDisplayRequest> displayRequest(TqInt) { return boost::shared_ptr<IqDisplayRequest>(); }
+	virtual TqInt DisplayBucket(const CqRegion& DRegion, const IqChannelBuffer* pBuffer)
+	{
+		// CqDDManager::DisplayBucket, ddmanager.cpp:146-171: buckets outside the crop window are skipped
+		CqRenderer* rc = QGetRenderContext();
+		if(pBuffer->width() == 0 || pBuffer->height() == 0) return 0;
+		if(DRegion.xMax() <= rc->cropWindowXMin() || DRegion.yMax() <= rc->cropWindowYMin() ||
+		   DRegion.xMin() > rc->cropWindowXMax() || DRegion.yMin() > rc->cropWindowYMax())
+			return 0;
+		static const char* names[5] = {"Ci", "Oi", "a", "z", "coverage"};
+		int idx[5];
+		for(int i = 0; i < 5; ++i) idx[i] = pBuffer->getChannelIndex(names[i]);
+		const int w = pBuffer->width(), h = pBuffer->height();
+		std::vector<float> px(size_t(w)*h*9);
+		for(int y = 0; y < h; ++y)
+			for(int x = 0; x < w; ++x)
+			{
+				float* o = &px[(size_t(y)*w + x)*9];
+				const float* ci = (*pBuffer)(x, y, idx[0]);
+				const float* oi = (*pBuffer)(x, y, idx[1]);
+				o[0] = ci[0]; o[1] = ci[1]; o[2] = ci[2]; o[3] = oi[0]; o[4] = oi[1]; o[5] = oi[2];
+				o[6] = (*pBuffer)(x, y, idx[2])[0];
+				o[7] = (*pBuffer)(x, y, idx[3])[0];
+				o[8] = (*pBuffer)(x, y, idx[4])[0];
+				const int X = DRegion.xMin() + x, Y = DRegion.yMin() + y;
+				if(m_channels && X < m_p.xres && Y < m_p.yres)
+					std::memcpy(m_channels + (size_t(Y)*m_p.xres + X)*9, o, 36);
+			}
+		CqRandom random;
+		for(int d = 0; d < m_p.n_displays; ++d)
+		{
+			const AqhDisplayDesc& dd = m_p.display[d];
+			for(int y = 0; y < h; ++y)
+				for(int x = 0; x < w; ++x)
+				{
+					double s = random.RandomFloat();
+					const int X = DRegion.xMin() + x, Y = DRegion.yMin() + y;
+					unsigned char* pdata = (m_displays && m_displays[d]) ? m_displays[d] + (size_t(Y)*m_p.xres + X)*m_entry[d] : 0;
+					if(!pdata) continue;
+					for(int c = 0; c < dd.n_channels; ++c)
+					{
+						double value = px[(size_t(y)*w + x)*9 + dd.channel[c]];
+						if(dd.quantize_one != 0)
+						{
+							value = Aqsis::lround(dd.quantize_zero + value * (dd.quantize_one - dd.quantize_zero) + (dd.quantize_dither * s));
+							value = clamp<double>(value, dd.quantize_min, dd.quantize_max);
+						}
+						switch(m_type[d])
+						{
+							case AQH_FLOAT32: { float v = value; std::memcpy(pdata, &v, 4); pdata += 4; break; }
+							case AQH_UNSIGNED32: { value = clamp<double>(value, 0, std::numeric_limits<uint32_t>::max()); uint32_t v = static_cast<uint32_t>(value); std::memcpy(pdata, &v, 4); pdata += 4; break; }
+							case AQH_SIGNED32: { value = clamp<double>(value, std::numeric_limits<int32_t>::min(), std::numeric_limits<int32_t>::max()); int32_t v = static_cast<int32_t>(value); std::memcpy(pdata, &v, 4); pdata += 4; break; }
+							case AQH_UNSIGNED16: { uint16_t v = static_cast<uint16_t>(value); std::memcpy(pdata, &v, 2); pdata += 2; break; }
+							case AQH_SIGNED16: { int16_t v = static_cast<int16_t>(value); std::memcpy(pdata, &v, 2); pdata += 2; break; }
+							case AQH_UNSIGNED8: { *pdata++ = static_cast<unsigned char>(value); break; }
+							case AQH_SIGNED8: { *pdata++ = static_cast<unsigned char>(static_cast<signed char>(value)); break; }
+						}
+					}
+				}
+		}
+		return 0;
+	}
+private:
+	const AqhFrameParams& m_p;
+	float* m_channels;
+	unsigned char* const* m_displays;
+	int m_entry[AQH_MAX_DISPLAYS], m_type[AQH_MAX_DISPLAYS];
+};
+
+double nowS() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+template<class T> void setOpt(T* dst, std::initializer_list<T> v) { int i = 0; for(T x : v) dst[i++] = x; }
+
+} // namespace
+
+extern "C" {
+
+// Render one frame with the reference's own hider.  Same contract as orc_render (oracle_hider.h);
+// single-threaded like the reference.  Returns 0, or AQH_ERR_UNSUPPORTED for options the driver
+// above does not map.
+int ref_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* channels,
+               unsigned char* const* display_out, OrcStats* stats)
+{
+	if(!pp || !grids || grids->memory_space != 0) return AQH_ERR_BAD_PARAMS;
+	const AqhFrameParams& p = *pp;
+	if(p.depth_filter != AQH_DEPTHFILTER_MIN) return AQH_ERR_UNSUPPORTED;
+	const double t0 = nowS();
+
+	// ---- render context and options (what RiCxxCore::WorldBegin leaves behind, ri.cpp:577-666)
+	CqRenderer* rc = new CqRenderer;
+	pCurrRenderer = rc;
+	CqOptions& opt = *boost::static_pointer_cast<CqOptions>(boost::const_pointer_cast<IqOptions>(rc->poptCurrent()));
+	setOpt<TqInt>(opt.GetIntegerOptionWrite("System", "Resolution", 2), {p.xres, p.yres});
+	setOpt<TqInt>(opt.GetIntegerOptionWrite("System", "PixelSamples", 2), {p.xsamples, p.ysamples});
+	setOpt<TqFloat>(opt.GetFloatOptionWrite("System", "FilterWidth", 2), {p.filter_xwidth, p.filter_ywidth});
+	setOpt<TqFloat>(opt.GetFloatOptionWrite("System", "Clipping", 2), {p.clip_near, p.clip_far});
+	setOpt<TqFloat>(opt.GetFloatOptionWrite("System", "Shutter", 2), {p.shutter_open, p.shutter_close});
+	setOpt<TqFloat>(opt.GetFloatOptionWrite("System", "Exposure", 2), {p.exposure_gain, p.exposure_gamma});
+	setOpt<TqInt>(opt.GetIntegerOptionWrite("System", "DisplayMode", 1), {p.display_mode});
+	setOpt<TqInt>(opt.GetIntegerOptionWrite("limits", "bucketsize", 2), {p.bucket_xsize, p.bucket_ysize});
+	setOpt<TqInt>(opt.GetIntegerOptionWrite("Hider", "jitter", 1), {p.jitter});
+	opt.SetfuncFilter(p.filter_func ? reinterpret_cast<RtFilterFunc>(p.filter_func) : RiGaussianFilter);
+	CqImageBuffer* image = new CqImageBuffer;
+	RefDDManager dd(p, channels, display_out);
+	g_refSetup.p = &p; g_refSetup.image = image; g_refSetup.dd = &dd;
+	rc->Initialise();
+
+	// ---- the global random stream: Reseed at WorldBegin (ri.cpp:660), then any front-end draws
+	CqRandom rng;
+	rng.Reseed(p.rng_seed);
+	for(uint32_t i = 0; i < p.rng_predraws; ++i) rng.RandomInt();
+
+	image->SetImage();
+
+	// ---- bust every grid and hand the micropolygons to CqImageBuffer::AddMPG
+	const double t1 = nowS();
+	CqMatrix camToRaster;
+	for(int i = 0; i < 4; ++i) for(int j = 0; j < 4; ++j) camToRaster.SetElement(i, j, p.cam_to_raster[i*4+j]);
+	camToRaster.SetfIdentity(false);
+	std::vector<RefGrid*> keep;
+	std::vector<std::vector<float> > owned;       // projected copies of P (the caller's arrays are const)
+	size_t po = 0, vo = 0, ko = 0;
+	int64_t nmp = 0;
+	for(int64_t g = 0; g < grids->n_grids; ++g)
+	{
+		const int cu = grids->cu[g], cv = grids->cv[g];
+		const int nk = grids->nkeys ? grids->nkeys[g] : 1;
+		const uint32_t flags = grids->flags[g];
+		if(flags & AQH_GRID_USES_CSG) return AQH_ERR_UNSUPPORTED;
+		const size_t nv = size_t(cu+1)*(cv+1);
+		owned.push_back(std::vector<float>(grids->P + po*3, grids->P + (po + nv*nk)*3));
+		float* P = owned.back().data();
+		if(flags & AQH_GRID_CAMERA_SPACE)
+		{
+			// micropolygon.cpp:723-731: raster x,y from the camera-to-raster matrix, camera z kept
+			for(size_t i = 0; i < nv*nk; ++i)
+			{
+				CqVector3D pt(P[3*i], P[3*i+1], P[3*i+2]);
+				TqFloat zdepth = pt.z();
+				CqVector3D r = camToRaster * pt;
+				P[3*i] = r.x(); P[3*i+1] = r.y(); P[3*i+2] = zdepth;
+			}
+		}
+		owned.push_back(std::vector<float>());
+		float* Ci = 0; float* Oi = 0;
+		if(grids->Ci) { owned.push_back(std::vector<float>(grids->Ci + vo*3, grids->Ci + (vo+nv)*3)); Ci = owned.back().data(); }
+		if(grids->Oi) { owned.push_back(std::vector<float>(grids->Oi + vo*3, grids->Oi + (vo+nv)*3)); Oi = owned.back().data(); }
+		RefGrid* grid = new RefGrid(cu, cv, P, Ci, Oi, flags, grids->lod_bounds ? grids->lod_bounds + 2*g : 0);
+		ADDREF(grid);
+		keep.push_back(grid);
+		// triangle split line per key, micropolygon.cpp:733-749
+		for(int k = 0; k < nk; ++k)
+		{
+			const float* Pk = P + size_t(k)*nv*3;
+			CqVector3D v0(Pk[0], Pk[1], Pk[2]), v1(Pk[3*cu], Pk[3*cu+1], Pk[3*cu+2]);
+			const size_t c = size_t(cv)*(cu+1);
+			CqVector3D v2(Pk[3*c], Pk[3*c+1], Pk[3*c+2]);
+			const TqFloat time = nk > 1 ? grids->key_times[ko + k] : 0.0f;
+			if(((v1.x() - v0.x())*(v2.y() - v0.y()) - (v1.y() - v0.y())*(v2.x() - v0.x())) >= 0)
+				grid->addSplitLine(time, v1, v2);
+			else
+				grid->addSplitLine(time, v2, v1);
+		}
+		// micropolygon.cpp:770-856
+		for(int iv = 0; iv < cv; ++iv)
+			for(int iu = 0; iu < cu; ++iu)
+			{
+				const int iIndex = iv*(cu+1) + iu;
+				if(grids->culled && grids->culled[vo + iIndex]) continue;
+				++nmp;
+				if(nk > 1)
+				{
+					boost::shared_ptr<CqMicroPolygonMotion> pNew(new CqMicroPolygonMotion(grid, iIndex));
+					for(int k = 0; k < nk; ++k)
+					{
+						const CqVector3D* Pk = reinterpret_cast<const CqVector3D*>(P + size_t(k)*nv*3);
+						pNew->AppendKey(Pk[iIndex], Pk[iIndex+1], Pk[iIndex+cu+1], Pk[iIndex+cu+2], grids->key_times[ko + k]);
+					}
+					pNew->Initialise();
+					boost::shared_ptr<CqMicroPolygon> pTemp(pNew);
+					image->AddMPG(pTemp);
+				}
+				else
+				{
+					boost::shared_ptr<CqMicroPolygon> pNew(new CqMicroPolygon(grid, iIndex));
+					pNew->Initialise();
+					image->AddMPG(pNew);
+				}
+			}
+		po += nv*nk; vo += nv; ko += nk;
+	}
+	const double t2 = nowS();
+
+	// ---- the reference's bucket loop
+	image->RenderImage();
+	const double t3 = nowS();
+
+	if(stats)
+	{
+		std::memset(stats, 0, sizeof *stats);
+		stats->prepare_s = t1 - t0; stats->bust_s = t2 - t1; stats->render_s = t3 - t2; stats->total_s = t3 - t0;
+		stats->n_micropolygons = nmp;
+		stats->n_samples = int64_t(p.crop_xmax - p.crop_xmin)*(p.crop_ymax - p.crop_ymin)*p.xsamples*p.ysamples;
+		stats->threads = 1;
+	}
+	delete image;
+	for(RefGrid* g : keep) RELEASEREF(g);
+	pCurrRenderer = 0;
+	delete rc;
+	return AQH_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,5 @@
+// Minimal stand-in for a Boost header (Boost is not in this image): std:: equivalents, only what the
+// reference's hider sources need to compile in place.  TEST INFRASTRUCTURE ONLY (oracle/_ref).
+#pragma once
+#include <any>
+namespace boost { using std::any; using std::any_cast; typedef std::bad_any_cast bad_any_cast; }

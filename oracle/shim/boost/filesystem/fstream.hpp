@@ -1,0 +1,6 @@
+// Minimal stand-in for a Boost header (Boost is not in this image): std:: equivalents, only what the
+// reference's hider sources need to compile in place.  TEST INFRASTRUCTURE ONLY (oracle/_ref).
+#pragma once
+#include <boost/filesystem/path.hpp>
+#include <fstream>
+namespace boost { namespace fsx { typedef std::ifstream ifstream; typedef std::ofstream ofstream; } }

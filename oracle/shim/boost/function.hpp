@@ -1,0 +1,6 @@
+// Minimal stand-in for a Boost header (Boost is not in this image): std:: equivalents, only what the
+// reference's hider sources need to compile in place.  TEST INFRASTRUCTURE ONLY (oracle/_ref).
+#pragma once
+#include <functional>
+namespace boost { using std::function; }
+namespace boost { template<class R> using function0 = std::function<R()>; }

@@ -1,0 +1,4 @@
+// Minimal stand-in for a Boost header (Boost is not in this image): std:: equivalents, only what the
+// reference's hider sources need to compile in place.  TEST INFRASTRUCTURE ONLY (oracle/_ref).
+#pragma once
+#include <boost/shared_ptr.hpp>

@@ -30,8 +30,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_LIB = os.path.join(ORACLE_DIR, "_build", "liboracle_hider.so")
 REF_LIB = os.path.join(ORACLE_DIR, "_ref", "libaqsis_refleaf.so")
+REFHIDER_LIB = os.path.join(ORACLE_DIR, "_ref", "libaqsis_refhider.so")
 _lib = None
 _ref = None
+_refhider = None
 
 
 def build_oracle():
@@ -128,4 +130,39 @@ def render(params: FrameParams, grids, nthreads=1):
     rc = L.orc_render(C.byref(params), C.byref(b), ch.ctypes.data, ptrs, int(nthreads), C.byref(st))
     if rc:
         raise RuntimeError(f"orc_render failed: {abi.STATUS_NAMES.get(rc, rc)}")
+    return ch, outs, st.as_dict()
+
+
+def refhider():
+    """The reference's own hider compiled in place (oracle/ref_hider.cpp); None when oracle/_ref lacks it."""
+    global _refhider
+    if _refhider is None:
+        if os.path.isdir("/root/reference/libs/core"):     # build container: (re)build in place when stale
+            subprocess.run(["make", "-s", "-C", ORACLE_DIR, "refhider"], check=True, capture_output=True)
+        if not os.path.exists(REFHIDER_LIB):
+            return None
+        L = C.CDLL(REFHIDER_LIB)
+        L.ref_render.argtypes = [C.POINTER(FrameParams), C.POINTER(GridBlock), C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(OrcStats)]
+        _refhider = L
+    return _refhider
+
+
+def render_reference(params: FrameParams, grids):
+    """Run the reference's own hider (single-threaded, like aqsis).  Same returns as render()."""
+    from aqsis_b200.hider import display_info
+    L = refhider()
+    if L is None:
+        raise RuntimeError("oracle/_ref/libaqsis_refhider.so is not available")
+    b = grids.as_struct()
+    ch = np.zeros((params.yres, params.xres, 9), dtype=np.float32)
+    outs, ptrs = [], (C.c_void_p * max(1, params.n_displays))()
+    for d in range(params.n_displays):
+        dt, nch, es = display_info(params, d)
+        a = np.zeros((params.yres, params.xres, nch), dtype=dt)
+        outs.append(a)
+        ptrs[d] = a.ctypes.data
+    st = OrcStats()
+    rc = L.ref_render(C.byref(params), C.byref(b), ch.ctypes.data, ptrs, C.byref(st))
+    if rc:
+        raise RuntimeError(f"ref_render failed: {abi.STATUS_NAMES.get(rc, rc)}")
     return ch, outs, st.as_dict()
