@@ -110,7 +110,7 @@ struct AqhHider
 	AqhFrameParams params{};
 	ReplayLayout layout{};
 	// frame tables (host) and the key they were built for
-	std::string tableKey;
+	std::string tableKey, maskLayoutKey;
 	SamplerTables tables;
 	std::vector<uint8_t> patPlanes;
 	std::vector<float> dither, filterTab, dofBounds;
@@ -400,12 +400,21 @@ int renderFrame(AqhHider* h, bool download)
 	CU(h->dTileFlags.reserve(std::max<size_t>(nActive, 1)*4), "cudaMalloc(tile flags)");
 	CU(h->dMisc.reserve(256), "cudaMalloc(counters)");
 	CU(h->dRowOwned.reserve(p.yres), "cudaMalloc(row ownership)");
-	const size_t planeStride = size_t(L.sw)*L.sh*(p.xsamples*p.ysamples);
+	const int planeW = ((L.sw + 3) & ~3) + 44;       // see DevFrame::planeW
+	const size_t planeStride = size_t(planeW)*L.sh*(p.xsamples*p.ysamples);
 	const int ntaps = (2*L.shiftX+1)*(2*L.shiftY+1);
 	if(p.filter_mode == AQH_FILTER_REFERENCE_ORDER)
 	{
 		CU(h->dPlanes.reserve(planeStride*7*4), "cudaMalloc(sample planes)");
 		CU(h->dMask.reserve(planeStride*4), "cudaMalloc(sample mask plane)");
+		// the pad columns of the mask plane are never written: they must read as "no sample"
+		char lk[96];
+		std::snprintf(lk, sizeof lk, "%p %d %d %d", h->dMask.p, planeW, L.sh, p.xsamples*p.ysamples);
+		if(h->maskLayoutKey != lk)
+		{
+			CU(cudaMemsetAsync(h->dMask.p, 0, planeStride*4, st), "cudaMemsetAsync(sample mask plane)");
+			h->maskLayoutKey = lk;
+		}
 	}
 	else
 		CU(h->dPartials.reserve(size_t(ntaps)*9*L.sw*L.sh*4), "cudaMalloc(tap partial sums)");
@@ -533,7 +542,7 @@ int renderFrame(AqhHider* h, bool download)
 	f.tileCursor = h->dMisc.as<uint32_t>();
 	f.errorFlags = h->dMisc.as<uint32_t>() + 1;
 	f.counters = reinterpret_cast<unsigned long long*>(h->dMisc.as<unsigned char>() + 16);
-	f.planes = h->dPlanes.as<float>(); f.maskPlane = h->dMask.as<uint32_t>(); f.planeStride = (int64_t)planeStride;
+	f.planes = h->dPlanes.as<float>(); f.maskPlane = h->dMask.as<uint32_t>(); f.planeStride = (int64_t)planeStride; f.planeW = planeW;
 	f.filterMode = p.filter_mode; f.partials = h->dPartials.as<float>(); f.ntaps = ntaps;
 	f.channels = h->dChannels.as<float>();
 	f.rowOwned = (std::max(1, p.world_size) > 1) ? h->dRowOwned.as<uint8_t>() : nullptr;
@@ -551,11 +560,13 @@ int renderFrame(AqhHider* h, bool download)
 	CU(launchBinScan(f, st), "k_bin_scan"); S.gpu_launches += 1;
 	// the fill pass needs the total entry count to size the list
 	uint32_t totalEntries = 0, devFlags = 0;
+	unsigned long long maxBin = 0;
 	CU(cudaMemcpyAsync(&totalEntries, f.binOffset + nActive, 4, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(bin total)");
+	CU(cudaMemcpyAsync(&maxBin, f.counters + 3, 8, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(longest bin)");
 	CU(cudaMemcpyAsync(&devFlags, f.errorFlags, 4, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(frame flags)");
 	CU(cudaStreamSynchronize(st), "bin count");
-	CU(h->dBinEntries.reserve(std::max<size_t>(totalEntries, 1)*4), "cudaMalloc(bin entries)");
-	f.binEntries = h->dBinEntries.as<uint32_t>();
+	CU(h->dBinEntries.reserve(std::max<size_t>(totalEntries, 1)*8), "cudaMalloc(bin entries)");
+	f.binEntries = h->dBinEntries.as<unsigned long long>();
 	// the project kernel reports whether any vertex is non-opaque: only then does the hide kernel
 	// carry deep-list heads in shared memory and a deep hit pool in HBM
 	f.anyTransparent = (devFlags & 2u) ? 1 : 0;
@@ -569,7 +580,10 @@ int renderFrame(AqhHider* h, bool download)
 		CU(h->dDeepUV.reserve(size_t(cfg.hideCtas)*f.deepCapPerCta*8), "cudaMalloc(deep hit pool)");
 		f.deepA = h->dDeepA.as<uint4>(); f.deepUV = h->dDeepUV.as<float2>();
 	}
-	CU(launchBinFill(f, st), "k_bin<fill>"); S.gpu_launches += (nPos ? 1 : 0) + (nActive ? 1 : 0);
+	// bins are sorted front to back in runs of sortRun entries (a power of two covering the longest bin, capped)
+	f.sortRun = 64;
+	while(f.sortRun < (int)maxBin && f.sortRun < 8192) f.sortRun <<= 1;
+	CU(launchBinFill(f, st), "k_bin<fill>"); S.gpu_launches += (nPos ? 1 : 0) + (nActive ? 1 : 0) + ((nPos && nActive) ? 1 : 0);
 	CU(cudaEventRecord(h->ev[1], st), "cudaEventRecord");
 	CU(launchHide(f, cfg, st), "k_hide"); S.gpu_launches += nActive ? 1 : 0;
 	CU(cudaEventRecord(h->ev[2], st), "cudaEventRecord");
@@ -577,7 +591,7 @@ int renderFrame(AqhHider* h, bool download)
 	CU(cudaEventRecord(h->ev[3], st), "cudaEventRecord");
 
 	// ---- results
-	struct { uint32_t cursor, err; uint32_t pad[2]; unsigned long long ctr[3]; } misc;
+	struct { uint32_t cursor, err; uint32_t pad[2]; unsigned long long ctr[4]; } misc;
 	CU(cudaMemcpyAsync(&misc, h->dMisc.p, sizeof misc, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(counters)");
 	const double tDown0 = nowMs();
 	S.d2h_bytes = 0;

@@ -77,13 +77,16 @@ struct DevFrame
 	const uint32_t* activeTiles;   // nActiveTiles tile ids
 	uint32_t* binCount;            // nActiveTiles
 	uint32_t* binOffset;           // nActiveTiles+1
-	uint32_t* binEntries;
+	unsigned long long* binEntries; // per tile: (depthKey(zmin) << 32 | position index), sorted ascending
+	int sortRun;                   // bins are sorted ascending in runs of this many entries
 	uint32_t* tileCursor;          // persistent-CTA work counter
 	uint32_t* tileFlags;           // per active tile: bit0 = has non-opaque MPs
-	// resolved samples: planes [k][s][y][x] over the sample region
+	// resolved samples: planes [k][y][s][x] over the sample region, rows padded to planeW floats
+	// (a multiple of 4 with slack, so that the filter can stage aligned 16-byte pieces past the edge)
 	float* planes;                 // 7 planes: R G B Or Og Ob Z
 	uint32_t* maskPlane;           // bits 0-14 x-tap inclusion, 15-29 y-tap inclusion, 31 valid
-	int64_t planeStride;           // n*sw*sh
+	int64_t planeStride;           // sh*n*planeW
+	int planeW;
 	// tile-partials filter mode: per (tap, value, y, x) partial sums over a pixel's samples;
 	// values: 0 gTot, 1 hit count, 2..8 R G B Or Og Ob Z
 	int filterMode;                // AQH_FILTER_*
@@ -94,7 +97,7 @@ struct DevFrame
 	float2* deepUV;
 	uint32_t deepCapPerCta;
 	uint32_t* errorFlags;          // bit0: deep pool overflow
-	unsigned long long* counters;  // [0] MPs binned, [1] bin entries, [2] deep hits
+	unsigned long long* counters;  // [0] MPs binned, [1] bin entries, [2] deep hits, [3] longest bin
 	// output
 	float* channels;               // xres*yres*9
 	const uint8_t* rowOwned;       // yres: 1 when this rank owns the pixel row

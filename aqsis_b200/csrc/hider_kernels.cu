@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(128) k_splitlines(DevFrame f)
 // is padded a little to stay conservative under the lerp rounding of the motion sub-bounds.
 struct TileRange { int tx0, tx1, ty0, ty1; };   // inclusive
 
-__device__ __forceinline__ bool mpTileRange(const DevFrame& f, int64_t p, const float4& a, TileRange& tr)
+__device__ __forceinline__ bool mpTileRange(const DevFrame& f, int64_t p, const float4& a, TileRange& tr, uint32_t& zminKey)
 {
 	const uint32_t info = infoOf(a);
 	if(!(info & VINFO_MP_VALID)) return false;
@@ -170,6 +170,7 @@ __device__ __forceinline__ bool mpTileRange(const DevFrame& f, int64_t p, const 
 		B2 kb = boundOf4(Pk[0], Pk[1], Pk[cu+1], Pk[cu+2]);
 		encapsulate(B, kb);
 	}
+	zminKey = depthKey(B.mnz);
 	if(f.useDof)
 	{
 		// imagebuffer.cpp:519-531
@@ -194,11 +195,12 @@ __global__ void __launch_bounds__(256) k_bin(DevFrame f)
 {
 	const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
 	TileRange tr;
+	uint32_t zminKey = 0;
 	bool live = p < f.nPos;
 	if(live)
 	{
 		const float4 a = f.P4[p];
-		live = mpTileRange(f, p, a, tr);
+		live = mpTileRange(f, p, a, tr, zminKey);
 	}
 	unsigned nent = 0;
 	if(live)
@@ -210,7 +212,8 @@ __global__ void __launch_bounds__(256) k_bin(DevFrame f)
 			if(FILL)
 			{
 				uint32_t at = atomicAdd(&f.binCount[slot], 1u);
-				f.binEntries[f.binOffset[slot] + at] = (uint32_t)p;
+				// (nearest depth of the micropolygon, position index): sorted per tile by k_bin_sort
+				f.binEntries[f.binOffset[slot] + at] = ((unsigned long long)zminKey << 32) | (uint32_t)p;
 			}
 			else
 			{
@@ -239,8 +242,10 @@ __global__ void __launch_bounds__(1024) k_bin_scan(DevFrame f)
 	const int n = f.nActiveTiles;
 	const int per = (n + 1023) / 1024;
 	const int beg = threadIdx.x * per, end = min(beg + per, n);
-	uint32_t sum = 0;
-	for(int i = beg; i < end; ++i) sum += f.binCount[i];
+	uint32_t sum = 0, mx = 0;
+	for(int i = beg; i < end; ++i) { sum += f.binCount[i]; mx = max(mx, f.binCount[i]); }
+	mx = __reduce_max_sync(0xffffffffu, mx);
+	if((threadIdx.x & 31) == 0 && mx) atomicMax(&f.counters[3], (unsigned long long)mx);   // longest bin: sizes the sort
 	s_part[threadIdx.x] = sum;
 	__syncthreads();
 	// Hillis-Steele inclusive scan over the 1024 partials
@@ -261,6 +266,46 @@ __global__ void __launch_bounds__(1024) k_bin_scan(DevFrame f)
 	}
 	if(threadIdx.x == 1023) f.binOffset[n] = s_part[1023];
 	if(threadIdx.x == 0) *f.tileCursor = 0;
+}
+
+// Order every tile's bin front to back (ascending nearest depth, ties by submission order).
+// The hide kernel's results do not depend on the order -- every hit competes through an
+// order-independent (depth, submission) key -- but its SPEED does: with near micropolygons
+// first the reference's own occlusion cull (Bound.zmin > occlZ, bucketprocessor.cpp:1179)
+// rejects hidden ones before their edge tests.  This mirrors the reference, which renders a
+// bucket's surfaces nearest first (CqBucket::closest_surface, bucket.h).
+// One CTA per tile; bitonic sort of up to SORT_MAX entries in shared memory; longer bins are
+// sorted in SORT_MAX-sized runs.
+#define SORT_MAX 8192
+__global__ void __launch_bounds__(256) k_bin_sort(DevFrame f, int sortMax)
+{
+	extern __shared__ unsigned long long s_keys[];
+	const int slot = blockIdx.x;
+	const uint32_t beg = f.binOffset[slot], end = f.binOffset[slot+1];
+	for(uint32_t c0 = beg; c0 < end; c0 += sortMax)
+	{
+		const int cnt = (int)min((uint32_t)sortMax, end - c0);
+		if(cnt < 2) break;
+		int n = 32;
+		while(n < cnt) n <<= 1;
+		for(int i = threadIdx.x; i < n; i += 256) s_keys[i] = (i < cnt) ? f.binEntries[c0 + i] : ~0ull;
+		__syncthreads();
+		for(int k = 2; k <= n; k <<= 1)
+			for(int j = k >> 1; j > 0; j >>= 1)
+			{
+				for(int t = threadIdx.x; t < (n >> 1); t += 256)
+				{
+					const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));     // index with bit j clear
+					const int l = i | j;
+					const unsigned long long a = s_keys[i], b = s_keys[l];
+					const bool up = (i & k) == 0;
+					if((a > b) == up) { s_keys[i] = b; s_keys[l] = a; }
+				}
+				__syncthreads();
+			}
+		for(int i = threadIdx.x; i < cnt; i += 256) f.binEntries[c0 + i] = s_keys[i];
+		__syncthreads();
+	}
 }
 
 // ------------------------------------------------------------------------------------
@@ -467,7 +512,7 @@ __device__ __forceinline__ void shadeHit(const DevFrame& f, const GridRec& g, ui
 // stride = tileW*xs + SMEM_PAD, so that the candidate rectangle of a micropolygon is a plain 2-D
 // window (no per-candidate table lookups) and consecutive lanes touch consecutive banks.
 //   u64 keys[nsP] | f32 posx[nsP] | f32 posy[nsP] | [f32 time[nsP]] | [float2 dof[nsP]] | [u32 head[nsP]] |
-//   StaticRec recs[nwarps*RECS_PER_WARP] | u16 subOfs[n] | u8 shufPat[tileW*tileH]
+//   StaticRec recs[nwarps*RECS_PER_WARP] | u32 pixZ[tileW*tileH] | u16 subOfs[n] | u8 shufPat[tileW*tileH]
 #define SMEM_PAD 8
 #define RECS_PER_WARP 16
 struct StaticRec   // 36 words
@@ -500,6 +545,9 @@ struct HideSmem
 	StaticRec* recs;
 	uint16_t* subOfs;          // sample index i -> (i / xs)*stride + i % xs
 	uint8_t* shufPat;
+	uint32_t* pixZ;            // per pixel: upper bound of the depth keys of its samples (hierarchical z)
+	uint32_t* tileZ;           // max of pixZ over the tile: nothing behind it can be visible in the tile
+	uint32_t* dirty;           // set by every successful opaque store since the last refresh
 	int stride, nsP;
 };
 
@@ -521,6 +569,7 @@ __device__ __forceinline__ HideSmem carveSmem(const DevFrame& f, unsigned char* 
 	if(f.anyTransparent) { s.head = (uint32_t*)(base + o); o += ns*4; }
 	o = (o + 15) & ~(size_t)15;
 	s.recs = (StaticRec*)(base + o); o += (size_t)nrecs*sizeof(StaticRec);
+	s.pixZ = (uint32_t*)(base + o); o += (size_t)f.tileW*f.tileH*4;
 	s.subOfs = (uint16_t*)(base + o); o += (size_t)f.n*2;
 	s.shufPat = (uint8_t*)(base + o);
 	return s;
@@ -535,6 +584,7 @@ static size_t hideSmemBytes(const DevFrame& f, int nrecs)
 	if(f.anyTransparent) o += ns*4;
 	o = (o + 15) & ~(size_t)15;
 	o += (size_t)nrecs*sizeof(StaticRec);
+	o += (size_t)f.tileW*f.tileH*4;
 	o += (size_t)f.n*2 + (size_t)f.tileW*f.tileH;
 	return (o + 15) & ~(size_t)15;
 }
@@ -548,12 +598,15 @@ __device__ __forceinline__ int sampleIdx(const DevFrame& f, const HideSmem& s, i
 // Deposit a hit: opaque hits race for the per-sample (depth, order) minimum; transparent ones
 // are appended to the CTA's deep pool if they are in front of the final opaque depth.
 // StoreSample, bucketprocessor.cpp:1471-1569.
-__device__ __forceinline__ void storeOpaque(unsigned long long* key, float D, uint32_t p)
+__device__ __forceinline__ void storeOpaque(const HideSmem& s, unsigned long long* key, float D, uint32_t p)
 {
 	if(!(D < FLT_MAX)) return;                       // occlZ(=FLT_MAX) <= D
 	unsigned long long nk = ((unsigned long long)depthKey(D) << 32) | p;
 	if(nk < *key)                                    // cheap pre-check; keys only ever decrease
+	{
 		atomicMin(key, nk);
+		*(volatile uint32_t*)s.dirty = 1u;
+	}
 }
 
 struct DeepCtx
@@ -583,8 +636,40 @@ __device__ __forceinline__ float sampleLod(const DevFrame& f, const TileCtx& t, 
 	return f.val1d[(size_t)pat*f.n + i];
 }
 
+// ---- hierarchical z.  pixZ[pixel] >= the occlusion depth key of every sample of the pixel (the keys
+// only ever decrease, so a stale value is merely conservative).  A micropolygon whose nearest depth
+// lies behind pixZ of every pixel it can touch would fail the reference's per-sample cull
+// "Bound.zmin > occlZ" (bucketprocessor.cpp:1179, :1393) at each of its candidates, so it is
+// dropped before its set-up: same image, far fewer instructions for hidden geometry.
+__device__ __forceinline__ void refreshPixZ(const DevFrame& f, const TileCtx& t, const HideSmem& s, int lane)
+{
+	const int tw = t.rx1 - t.rx0, th = t.ry1 - t.ry0;
+	const uint32_t* hi = reinterpret_cast<const uint32_t*>(s.keys) + 1;
+	uint32_t tileMax = 0;
+	for(int ly = 0; ly < th; ++ly)
+		for(int lx = 0; lx < tw; ++lx)
+		{
+			const int base = (ly*f.ys)*s.stride + lx*f.xs;
+			uint32_t m = 0;
+			for(int i = lane; i < f.n; i += 32) m = max(m, hi[2*(base + s.subOfs[i])]);
+			m = __reduce_max_sync(0xffffffffu, m);
+			if(lane == 0) s.pixZ[ly*f.tileW + lx] = m;
+			tileMax = max(tileMax, m);
+		}
+	if(lane == 0) *(volatile uint32_t*)s.tileZ = tileMax;
+}
+// largest pixZ over the pixel rectangle [sX,eX) x [sY,eY) (global pixel coordinates inside the tile)
+__device__ __forceinline__ uint32_t pixZMax(const DevFrame& f, const TileCtx& t, const HideSmem& s, int sX, int eX, int sY, int eY)
+{
+	uint32_t m = 0;
+	for(int y = sY; y < eY; ++y)
+		for(int x = sX; x < eX; ++x)
+			m = max(m, s.pixZ[(y - t.tileY0)*f.tileW + (x - t.tileX0)]);
+	return m;
+}
+
 // ---- static micropolygons, no depth of field: RenderMPG_Static (bucketprocessor.cpp:1097-1218)
-__device__ void setupStaticRec(const DevFrame& f, const TileCtx& t, uint32_t p, bool wantOpaque, StaticRec& r)
+__device__ void setupStaticRec(const DevFrame& f, const TileCtx& t, const HideSmem& s, uint32_t p, bool wantOpaque, StaticRec& r)
 {
 	r.rect = 0;
 	r.p = p;
@@ -611,6 +696,7 @@ __device__ void setupStaticRec(const DevFrame& f, const TileCtx& t, uint32_t p, 
 	int sX = (bminx < (float)t.rx0) ? t.rx0 : max(floorI(bminx), t.rx0);
 	int sY = (bminy < (float)t.ry0) ? t.ry0 : max(floorI(bminy), t.ry0);
 	if(sX >= eX || sY >= eY) return;
+	if(depthKey(B.mnz) > pixZMax(f, t, s, sX, eX, sY, eY)) return;      // hidden behind every sample it could touch
 	const int xs = f.xs, ys = f.ys;
 	int im = (bminx < (float)sX) ? 0 : floorI((bminx - (float)sX) * (float)xs);
 	int in = (bminy < (float)sY) ? 0 : floorI((bminy - (float)sY) * (float)ys);
@@ -678,7 +764,7 @@ __device__ __forceinline__ void sampleStaticRec(const DevFrame& f, const TileCtx
 				if(triangleSplitReject(f, g, make_float2(x, y), make_float2(0.f, 0.f), D, 0.0f)) continue;
 		}
 		if(OPAQUE)
-			storeOpaque(&s.keys[idx], D, r.p);
+			storeOpaque(s, &s.keys[idx], D, r.p);
 		else
 			storeDeep(f, dc, s, idx, D, r.p, uv);
 	}
@@ -819,7 +905,7 @@ __device__ __forceinline__ void testCandidateMBDof(const DevFrame& f, const Tile
 	if(m.g.flags & AQH_GRID_TRIANGULAR)
 		if(triangleSplitReject(f, m.g, pos, dofOff, D, time)) return;
 	if(OPAQUE)
-		storeOpaque(&s.keys[idx], D, m.p);
+		storeOpaque(s, &s.keys[idx], D, m.p);
 	else
 		storeDeep(f, dc, s, idx, D, m.p, uv);
 }
@@ -953,6 +1039,7 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 				int eY = (bmaxy >= (float)t.ry1) ? t.ry1 : min(lceilF(bmaxy), t.ry1);
 				int sX = (bminx < (float)t.rx0) ? t.rx0 : max(floorI(bminx), t.rx0);
 				int sY = (bminy < (float)t.ry0) ? t.ry0 : max(floorI(bminy), t.ry0);
+				if(zminKey > pixZMax(f, t, s, sX, eX, sY, eY)) continue;
 				for(int iY = sY; iY < eY; ++iY)
 					for(int iX = sX; iX < eX; ++iX)
 					{
@@ -974,6 +1061,7 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 			int sX = (bminx < (float)t.rx0) ? t.rx0 : max(floorI(bminx), t.rx0);
 			int sY = (bminy < (float)t.ry0) ? t.ry0 : max(floorI(bminy), t.ry0);
 			if(sX >= eX || sY >= eY) continue;
+			if(zminKey > pixZMax(f, t, s, sX, eX, sY, eY)) continue;
 			// the reference's do-while visits at least one index per pixel
 			const int cnt = max(1, indexT1 - indexT0);
 			const int Wp = eX - sX, npix = Wp*(eY - sY), total = npix*cnt;
@@ -1129,8 +1217,10 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 	__shared__ uint32_t s_tile;
 	__shared__ uint32_t s_deepCount;
 	__shared__ uint32_t s_next;
+	__shared__ uint32_t s_tileZ, s_dirty;
 	constexpr int NWARPS = THREADS/32;
-	const HideSmem s = carveSmem(f, smemRaw, NWARPS*RECS_PER_WARP);
+	HideSmem s = carveSmem(f, smemRaw, NWARPS*RECS_PER_WARP);
+	s.tileZ = &s_tileZ; s.dirty = &s_dirty;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int n = f.n, xs = f.xs, ys = f.ys;
 	const int rowLen = f.tileW*xs;
@@ -1202,6 +1292,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 				s.posy[idx] = -1e30f;
 			}
 		}
+		for(int i = tid; i < f.tileW*f.tileH; i += THREADS) s.pixZ[i] = 0xffffffffu;
+		if(tid == 0) { s_tileZ = 0xffffffffu; s_dirty = 0; }
 		__syncthreads();
 		const uint32_t binBeg = f.binOffset[slot], binCnt = f.binOffset[slot+1] - binBeg;
 		const uint32_t tflags = f.tileFlags[slot];
@@ -1212,27 +1304,49 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 			{
 				if(!(f.anyTransparent && (tflags & 1u))) break;
 				__syncthreads();
-				if(tid == 0) s_next = 0;
+				if(tid == 0) { s_next = 0; s_dirty = 0; }
+				if(warp == 0) refreshPixZ(f, t, s, lane);        // the opaque depths are final now
 				__syncthreads();
 			}
 			for(;;)
 			{
 				uint32_t base = 0;
-				if(lane == 0) base = atomicAdd(&s_next, (uint32_t)RECS_PER_WARP);
+				// Small grabs keep few micropolygons in flight, so that the front-to-back order of the
+				// bin turns into culling early.  Once the first wave (one grab per warp) is under way the
+				// hierarchical z is refreshed whenever new hits have landed, and because the bin is sorted
+				// by nearest depth, the first micropolygon found behind the whole tile ends its sorted run.
+				constexpr uint32_t GRAB = MBDOF ? 2u : 8u;
+				if(lane == 0) base = atomicAdd(&s_next, GRAB);
 				base = __shfl_sync(0xffffffffu, base, 0);
 				if(base >= binCnt) break;
-				const int cnt = min((uint32_t)RECS_PER_WARP, binCnt - base);
+				const int cnt = min(GRAB, binCnt - base);
+				if(base >= GRAB*NWARPS && ((base / GRAB) & (MBDOF ? 0u : 3u)) == 0 && *(volatile uint32_t*)s.dirty)
+				{
+					if(lane == 0) *(volatile uint32_t*)s.dirty = 0;
+					__syncwarp();
+					refreshPixZ(f, t, s, lane);
+					__syncwarp();
+				}
+				{
+					const uint32_t zfirst = (uint32_t)(f.binEntries[binBeg + base] >> 32);
+					if(zfirst > *(volatile uint32_t*)s.tileZ)
+					{
+						const uint32_t runEnd = min(binCnt, (base / (uint32_t)f.sortRun + 1u)*(uint32_t)f.sortRun);
+						if(lane == 0) atomicMax(&s_next, runEnd);
+						continue;
+					}
+				}
 				if(MBDOF)
 				{
 					for(int j = 0; j < cnt; ++j)
 					{
-						const uint32_t p = f.binEntries[binBeg + base + j];
+						const uint32_t p = (uint32_t)f.binEntries[binBeg + base + j];
 						const bool handled = (pass == 0) ? renderMBOrDof<true>(f, t, s, dc, p, lane)
 						                                 : renderMBOrDof<false>(f, t, s, dc, p, lane);
 						if(!handled)
 						{
 							// static micropolygon in a frame without depth of field
-							if(lane == 0) setupStaticRec(f, t, p, pass == 0, myRecs[0]);
+							if(lane == 0) setupStaticRec(f, t, s, p, pass == 0, myRecs[0]);
 							__syncwarp();
 							if(pass == 0) sampleStaticRec<true>(f, t, s, dc, myRecs[0], lane);
 							else sampleStaticRec<false>(f, t, s, dc, myRecs[0], lane);
@@ -1242,7 +1356,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 				}
 				else
 				{
-					if(lane < cnt) setupStaticRec(f, t, f.binEntries[binBeg + base + lane], pass == 0, myRecs[lane]);
+					if(lane < cnt) setupStaticRec(f, t, s, (uint32_t)f.binEntries[binBeg + base + lane], pass == 0, myRecs[lane]);
 					__syncwarp();
 					for(int j = 0; j < cnt; ++j)
 					{
@@ -1259,7 +1373,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 		const int tw = t.rx1 - t.rx0, th = t.ry1 - t.ry0;
 		if(f.filterMode == AQH_FILTER_REFERENCE_ORDER)
 		{
-			// Planes are [k][i][y][x]: consecutive threads take consecutive x of one sample index.
+			// Planes are [k][y][i][x] (row width planeW): consecutive threads take consecutive x of one sample index.
 			const int nOut = tw*th*n;
 			for(int o = tid; o < nOut; o += THREADS)
 			{
@@ -1268,7 +1382,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 				float out[7]; bool valid;
 				resolveSample(f, t, s, dc, idx, out, valid);
 				const int X = t.rx0 + lx, Y = t.ry0 + ly;
-				const size_t at = ((size_t)i*f.sh + (size_t)(Y - f.sy0))*f.sw + (size_t)(X - f.sx0);
+				const size_t at = ((size_t)(Y - f.sy0)*n + (size_t)i)*f.planeW + (size_t)(X - f.sx0);
 				f.maskPlane[at] = tapMask(f, s.posx[idx], s.posy[idx], X, Y, valid);
 				if(valid)
 				{
@@ -1354,7 +1468,7 @@ __global__ void __launch_bounds__(256) k_tile_flags(DevFrame f)
 	uint32_t any = 0;
 	for(uint32_t e = f.binOffset[slot] + threadIdx.x; e < f.binOffset[slot+1] && !any; e += 256)
 	{
-		const uint32_t p = f.binEntries[e];
+		const uint32_t p = (uint32_t)f.binEntries[e];
 		const float4 a = f.P4[p];
 		const uint32_t info = infoOf(a);
 		const GridRec g = f.grids[info & VINFO_GRID_MASK];
@@ -1467,8 +1581,8 @@ __global__ void __launch_bounds__(256) k_filter(DevFrame f, DevDisplays disp)
 		{
 			const float* g = s_filt + ((fy + ymax)*(2*xmax+1) + fx + xmax)*n;
 			const uint32_t need = (1u << (fx + xmax)) | (1u << (15 + fy + ymax));
-			size_t at = (size_t)(y + fy - f.sy0)*f.sw + (size_t)(x + fx - f.sx0);
-			const size_t step = (size_t)f.sw*f.sh;
+			size_t at = (size_t)(y + fy - f.sy0)*n*f.planeW + (size_t)(x + fx - f.sx0);
+			const size_t step = (size_t)f.planeW;
 			for(int sIdx = 0; sIdx < n; ++sIdx, at += step)
 			{
 				const uint32_t m = f.maskPlane[at];
@@ -1489,148 +1603,116 @@ __global__ void __launch_bounds__(256) k_filter(DevFrame f, DevDisplays disp)
 	finishPixel(f, disp, x, y, acc, gTot, SampleCount);
 }
 
-// Reference-order filter, shared-memory tiled.  A CTA owns OW x OH output pixels.  The per-sample
-// tap masks of the (OW+2xmax) x (OH+2ymax) halo tile stay in shared memory (16 bit each); the
-// seven value planes are streamed through a second tile ONE PLANE AT A TIME, so every resolved
-// sample is read from HBM (OW+2xmax)(OH+2ymax)/(OW*OH) times instead of (2xmax+1)(2ymax+1) times,
-// while each thread still adds its taps in exactly the reference's fy, fx, sy, sx order.
-// Weights come from constant memory (the index is warp-uniform).
+// Reference-order filter, row staged and channel split.
+// A CTA owns W consecutive output pixels of ONE image row and has 8*W threads: thread (px, ch)
+// accumulates channel ch of pixel px -- ch 0..6 = R G B Or Og Ob Z, ch 7 = the weight total and the
+// hit count -- over the taps in exactly the reference's fy, fx, sy, sx order
+// (bucketprocessor.cpp:597-629), so every per-channel float sum is the reference's own sequence of
+// roundings.  For each fy the n*(W+2*xmax) resolved samples of source row y+fy are staged ONCE in
+// shared memory (16-byte cp.async, all eight planes) and reused for the 2*xmax+1 values of fx, so a
+// sample travels L2 -> SM (2*ymax+1)*(1+2*xmax/W) times instead of (2*xmax+1)(2*ymax+1) times; with
+// the CTAs of neighbouring rows scheduled back to back the re-reads hit L2, not HBM.
+// Weights come from constant memory (uniform index).  Excluded samples are skipped by predication,
+// never multiplied by zero, so stale plane contents under an unset mask are harmless.
 __constant__ float c_filt[49*256];
 
-__device__ __forceinline__ void cpAsync4(void* smemDst, const void* gsrc)
+__device__ __forceinline__ void cpAsync16(void* smemDst, const void* gsrc)
 {
 	const uint32_t d = (uint32_t)__cvta_generic_to_shared(smemDst);
-	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(d), "l"(gsrc) : "memory");
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cpAsyncWaitAll()
 {
 	asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-// Walks the elements tid, tid+nthreads, ... of an [n*HH rows][HW] halo tile without divisions.
-struct TileWalk
-{
-	int hx, hy, sI, dh, dr, HW, HH;
-	__device__ __forceinline__ TileWalk(int tid, int nthreads, int HW_, int HH_) : HW(HW_), HH(HH_)
-	{
-		const int row = tid / HW_;
-		hx = tid - row*HW_;
-		sI = row / HH_; hy = row - sI*HH_;
-		dr = nthreads / HW_; dh = nthreads - dr*HW_;
-	}
-	__device__ __forceinline__ void next()
-	{
-		hx += dh; hy += dr;
-		if(hx >= HW) { hx -= HW; ++hy; }
-		while(hy >= HH) { hy -= HH; ++sI; }
-	}
-};
-
-__global__ void __launch_bounds__(512) k_filter_tiled(DevFrame f, DevDisplays disp, int OW, int OH)
+template<int W>
+__global__ void __launch_bounds__(8*W) k_filter_rows(DevFrame f, DevDisplays disp)
 {
 	extern __shared__ __align__(16) unsigned char fsm[];
+	constexpr int THREADS = 8*W;
 	const int n = f.n, xmax = f.shiftX, ymax = f.shiftY;
-	const int HW = OW + 2*xmax, HH = OH + 2*ymax, HHHW = HH*HW, tileN = n*HHHW;
-	const int nthreads = OW*OH, tid = threadIdx.x;
-	const int nw = (n + 31) >> 5;                       // 32-sample words per tap
-	float* planeT = reinterpret_cast<float*>(fsm);
-	uint32_t* useW = reinterpret_cast<uint32_t*>(fsm + (size_t)tileN*4);          // [tap*nw + w][thread]
-	uint16_t* maskT = reinterpret_cast<uint16_t*>(fsm + (size_t)tileN*4 + (size_t)f.ntaps*nw*nthreads*4);
-	const int tx = tid % OW, ty = tid / OW;
-	const int x0 = f.cropX0 + blockIdx.x*OW, y0 = f.cropY0 + blockIdx.y*OH;
-	const int x = x0 + tx, y = y0 + ty;
-	const bool live = x < f.cropX1 && y < f.cropY1 && !(f.rowOwned && !f.rowOwned[y]);
-	// mask tile (converted to 16 bits) + first value plane (asynchronous copies)
+	const int CW = W + ((2*xmax + 3) & ~3);            // staged columns, a multiple of 4
+	const int planeSz = n*CW + 8;                        // +8 words: the eight planes start 8 banks apart
+	float* tile = reinterpret_cast<float*>(fsm);         // [8 planes][n][CW]
+	const int tid = threadIdx.x, px = tid % W, ch = tid / W;
+	const int x0 = f.cropX0 + blockIdx.x*W, y = f.cropY0 + blockIdx.y;
+	if(f.rowOwned && !f.rowOwned[y]) return;             // uniform over the CTA
+	const int x = x0 + px;
+	const bool live = x < f.cropX1;
+	const int col0 = x0 - f.cropX0;                      // first staged column of the sample region (x0 - sx0 - xmax)
+	const float* myPlane = tile + (size_t)(ch < 7 ? ch : 7)*planeSz;
+	const uint32_t* maskT = reinterpret_cast<const uint32_t*>(tile + (size_t)7*planeSz);
+	float acc = 0.f;
+	int count = 0;
+	int tap = 0;
+	for(int fy = 0; fy <= 2*ymax; ++fy)
 	{
-		TileWalk w(tid, nthreads, HW, HH);
-		for(; w.sI < n; w.next())
+		__syncthreads();                                 // everyone is done with the previous row
 		{
-			const int gy = y0 - ymax + w.hy - f.sy0, gx = x0 - xmax + w.hx - f.sx0;
-			const int o = (w.sI*HH + w.hy)*HW + w.hx;
-			if(gy >= 0 && gy < f.sh && gx >= 0 && gx < f.sw)
+			const int cw4 = CW >> 2, per = n*cw4;
+			const size_t rowBase = (size_t)(y + fy - ymax - f.sy0)*n*f.planeW + (size_t)col0;
+			for(int e = tid; e < 8*per; e += THREADS)
 			{
-				const size_t src = ((size_t)w.sI*f.sh + gy)*f.sw + gx;
-				cpAsync4(&planeT[o], f.planes + src);
-				const uint32_t m = f.maskPlane[src];
-				maskT[o] = (uint16_t)((m & 0x7fu) | (((m >> 15) & 0x7fu) << 7) | ((m >> 31) << 15));
-			}
-			else { planeT[o] = 0.f; maskT[o] = 0; }
-		}
-		cpAsyncWaitAll();
-	}
-	__syncthreads();
-	float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-	float gTot = 0.f;
-	int SampleCount = 0;
-	if(live)
-	{
-		// plane 0 (red) together with the weight total, the hit count and the "use" bits
-		float a = 0.f;
-		int tap = 0;
-		for(int fy = 0; fy <= 2*ymax; ++fy)
-			for(int fx = 0; fx <= 2*xmax; ++fx, ++tap)
-			{
-				const uint32_t need = (1u << fx) | (1u << (7 + fy));
-				int o = (ty + fy)*HW + tx + fx;
-				const float* w = c_filt + tap*n;
-				for(int w0 = 0; w0 < nw; ++w0)
-				{
-					uint32_t bits = 0;
-					const int sEnd = min(32, n - w0*32);
-					for(int b2 = 0; b2 < sEnd; ++b2, o += HHHW)
-					{
-						const uint32_t m = maskT[o];
-						if((m & need) == need)
-						{
-							const float g = w[w0*32 + b2];
-							gTot += g;
-							if(m & 0x8000u) { a += planeT[o] * g; SampleCount++; bits |= 1u << b2; }
-						}
-					}
-					useW[(tap*nw + w0)*nthreads + tid] = bits;
-				}
-			}
-		acc[0] = a;
-	}
-#pragma unroll 1
-	for(int k = 1; k < 7; ++k)
-	{
-		__syncthreads();
-		const float* plane = f.planes + (size_t)k*f.planeStride;
-		{
-			TileWalk w(tid, nthreads, HW, HH);
-			for(; w.sI < n; w.next())
-			{
-				const int gy = y0 - ymax + w.hy - f.sy0, gx = x0 - xmax + w.hx - f.sx0;
-				const int o = (w.sI*HH + w.hy)*HW + w.hx;
-				if(gy >= 0 && gy < f.sh && gx >= 0 && gx < f.sw)
-					cpAsync4(&planeT[o], plane + ((size_t)w.sI*f.sh + gy)*f.sw + gx);
-				else
-					planeT[o] = 0.f;
+				const int k = e / per, r = e - k*per, sI = r / cw4, c4 = r - sI*cw4;
+				const float* src = (k < 7 ? f.planes + (size_t)k*f.planeStride : reinterpret_cast<const float*>(f.maskPlane))
+				                   + rowBase + (size_t)sI*f.planeW + 4*c4;
+				cpAsync16(tile + (size_t)k*planeSz + sI*CW + 4*c4, src);
 			}
 			cpAsyncWaitAll();
 		}
 		__syncthreads();
-		if(!live) continue;
-		float a = 0.f;
-		int tap = 0;
-		for(int fy = 0; fy <= 2*ymax; ++fy)
-			for(int fx = 0; fx <= 2*xmax; ++fx, ++tap)
+		if(!live) { tap += 2*xmax + 1; continue; }
+		for(int fx = 0; fx <= 2*xmax; ++fx, ++tap)
+		{
+			const uint32_t need = (1u << fx) | (1u << (15 + fy));
+			const uint32_t needV = need | 0x80000000u;
+			const float* w = c_filt + tap*n;
+			const int o = px + fx;
+			if(ch < 7)
 			{
-				int o = (ty + fy)*HW + tx + fx;
-				const float* w = c_filt + tap*n;
-				for(int w0 = 0; w0 < nw; ++w0)
-				{
-					const uint32_t bits = useW[(tap*nw + w0)*nthreads + tid];
-					const int sEnd = min(32, n - w0*32);
 #pragma unroll 8
-					for(int b2 = 0; b2 < sEnd; ++b2, o += HHHW)
-						if((bits >> b2) & 1u) a += planeT[o] * w[w0*32 + b2];
+				for(int sI = 0; sI < n; ++sI)
+				{
+					const uint32_t m = maskT[sI*CW + o];
+					const float v = myPlane[sI*CW + o] * w[sI];
+					if((m & needV) == needV) acc += v;
 				}
 			}
-		acc[k] = a;
+			else
+			{
+#pragma unroll 8
+				for(int sI = 0; sI < n; ++sI)
+				{
+					const uint32_t m = maskT[sI*CW + o];
+					if((m & need) == need)
+					{
+						acc += w[sI];
+						count += (int)(m >> 31);
+					}
+				}
+			}
+		}
 	}
-	if(live) finishPixel(f, disp, x, y, acc, gTot, SampleCount);
+	// gather the eight sums of a pixel in one thread
+	__syncthreads();
+	float* sums = reinterpret_cast<float*>(fsm);         // [9][W]
+	sums[ch*W + px] = acc;
+	if(ch == 7) sums[8*W + px] = __int_as_float(count);
+	__syncthreads();
+	if(ch == 0 && live)
+	{
+		float a[7];
+#pragma unroll
+		for(int k = 0; k < 7; ++k) a[k] = sums[k*W + px];
+		finishPixel(f, disp, x, y, a, sums[7*W + px], __float_as_int(sums[8*W + px]));
+	}
+}
+
+static size_t filterRowsSmem(const DevFrame& f, int W)
+{
+	const int CW = W + ((2*f.shiftX + 3) & ~3);
+	return (size_t)8*((size_t)f.n*CW + 8)*4;
 }
 
 // Tile-partials filter: sum the nine per-(pixel,tap) partial sums over the taps in fy, fx order.
@@ -1683,7 +1765,18 @@ cudaError_t launchBinFill(const DevFrame& f, cudaStream_t st)
 	if(f.nPos)
 		k_bin<true><<<(unsigned)((f.nPos + 255)/256), 256, 0, st>>>(f);
 	if(f.nActiveTiles)
+	{
+		static bool attr = false;
+		if(!attr)
+		{
+			cudaError_t e = cudaFuncSetAttribute(k_bin_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_MAX*8);
+			if(e != cudaSuccess) return e;
+			attr = true;
+		}
+		if(f.sortRun > SORT_MAX) return cudaErrorInvalidValue;
+		if(f.nPos) k_bin_sort<<<f.nActiveTiles, 256, (size_t)f.sortRun*8, st>>>(f, f.sortRun);
 		k_tile_flags<<<f.nActiveTiles, 256, 0, st>>>(f);
+	}
 	return cudaGetLastError();
 }
 
@@ -1722,13 +1815,6 @@ cudaError_t launchHide(const DevFrame& f, const LaunchCfg& cfg, cudaStream_t st)
 	return cudaGetLastError();
 }
 
-static size_t filterTiledSmem(const DevFrame& f, int OW, int OH)
-{
-	const size_t tileN = (size_t)f.n*(OW + 2*f.shiftX)*(OH + 2*f.shiftY);
-	const size_t nw = (f.n + 31)/32;
-	return tileN*6 + (size_t)f.ntaps*nw*OW*OH*4 + 16;
-}
-
 cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, const float* hostFilterTab, cudaStream_t st)
 {
 	const int w = f.cropX1 - f.cropX0, h = f.cropY1 - f.cropY0;
@@ -1740,30 +1826,36 @@ cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, const float
 		return cudaGetLastError();
 	}
 	const int ntapw = (2*f.shiftX+1)*(2*f.shiftY+1)*f.n;
-	// tiled kernel: masks as 7+7 tap bits (filter widths < 8), weights in 64 KB of constant memory
-	if(f.shiftX <= 3 && f.shiftY <= 3 && ntapw <= 49*256)
+	// row-staged kernel: tap bits fit the mask word (shift <= 7 always), weights in 64 KB of constant memory
+	if(ntapw <= 49*256)
 	{
-		const size_t budget = 200*1024;
-		int OW = 32, OH = 0;
-		for(; OW >= 8 && OH < 1; OW >>= 1)
+		const size_t budget = 110*1024;      // two CTAs per SM
+		int W = 32;
+		while(W > 8 && filterRowsSmem(f, W) > budget) W >>= 1;
+		const size_t smem = filterRowsSmem(f, W);
+		if(smem <= 220*1024)
 		{
-			for(int oh = 16; oh >= 1; --oh)
-			{
-				if(OW*oh > 512) continue;
-				const size_t need = filterTiledSmem(f, OW, oh);
-				if(need <= budget) { OH = oh; break; }
-			}
-			if(OH >= 1) break;
-		}
-		if(OH >= 1 && OW*OH >= 32)
-		{
-			const size_t smem = filterTiledSmem(f, OW, OH);
 			cudaError_t e = cudaMemcpyToSymbolAsync(c_filt, hostFilterTab, (size_t)ntapw*4, 0, cudaMemcpyHostToDevice, st);
 			if(e != cudaSuccess) return e;
-			e = cudaFuncSetAttribute(k_filter_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-			if(e != cudaSuccess) return e;
-			dim3 grid((w + OW - 1)/OW, (h + OH - 1)/OH);
-			k_filter_tiled<<<grid, OW*OH, smem, st>>>(f, disp, OW, OH);
+			dim3 grid((w + W - 1)/W, h);
+			if(W == 32)
+			{
+				e = cudaFuncSetAttribute(k_filter_rows<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+				if(e != cudaSuccess) return e;
+				k_filter_rows<32><<<grid, 256, smem, st>>>(f, disp);
+			}
+			else if(W == 16)
+			{
+				e = cudaFuncSetAttribute(k_filter_rows<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+				if(e != cudaSuccess) return e;
+				k_filter_rows<16><<<grid, 128, smem, st>>>(f, disp);
+			}
+			else
+			{
+				e = cudaFuncSetAttribute(k_filter_rows<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+				if(e != cudaSuccess) return e;
+				k_filter_rows<8><<<grid, 64, smem, st>>>(f, disp);
+			}
 			return cudaGetLastError();
 		}
 	}

@@ -99,8 +99,10 @@ class ImageGather:
     def __init__(self, params, rank, world, device, dist=None):
         import torch
         self.rank, self.world, self.dist = rank, world, dist
+        if world == 1:
+            return
         self.rows = [torch.from_numpy(rows_for_rank(params, r)).to(device) for r in range(world)]
-        self.max_rows = max(int(r.numel()) for r in self.rows) if world > 1 else 0
+        self.max_rows = max(int(r.numel()) for r in self.rows)
         pad = torch.zeros(self.max_rows, dtype=torch.long, device=device)
         pad[:self.rows[rank].numel()] = self.rows[rank]
         self.send_idx = pad
