@@ -400,21 +400,12 @@ int renderFrame(AqhHider* h, bool download)
 	CU(h->dTileFlags.reserve(std::max<size_t>(nActive, 1)*4), "cudaMalloc(tile flags)");
 	CU(h->dMisc.reserve(256), "cudaMalloc(counters)");
 	CU(h->dRowOwned.reserve(p.yres), "cudaMalloc(row ownership)");
-	const int planeW = ((L.sw + 3) & ~3) + 44;       // see DevFrame::planeW
+	const int planeW = (L.sw + 3) & ~3;              // row pitch: a multiple of 16 bytes for the TMA tensor map
 	const size_t planeStride = size_t(planeW)*L.sh*(p.xsamples*p.ysamples);
 	const int ntaps = (2*L.shiftX+1)*(2*L.shiftY+1);
 	if(p.filter_mode == AQH_FILTER_REFERENCE_ORDER)
 	{
-		CU(h->dPlanes.reserve(planeStride*7*4), "cudaMalloc(sample planes)");
-		CU(h->dMask.reserve(planeStride*4), "cudaMalloc(sample mask plane)");
-		// the pad columns of the mask plane are never written: they must read as "no sample"
-		char lk[96];
-		std::snprintf(lk, sizeof lk, "%p %d %d %d", h->dMask.p, planeW, L.sh, p.xsamples*p.ysamples);
-		if(h->maskLayoutKey != lk)
-		{
-			CU(cudaMemsetAsync(h->dMask.p, 0, planeStride*4, st), "cudaMemsetAsync(sample mask plane)");
-			h->maskLayoutKey = lk;
-		}
+		CU(h->dPlanes.reserve(planeStride*8*4 + 256), "cudaMalloc(sample planes)");   // 7 value planes + the mask plane
 	}
 	else
 		CU(h->dPartials.reserve(size_t(ntaps)*9*L.sw*L.sh*4), "cudaMalloc(tap partial sums)");
@@ -542,7 +533,7 @@ int renderFrame(AqhHider* h, bool download)
 	f.tileCursor = h->dMisc.as<uint32_t>();
 	f.errorFlags = h->dMisc.as<uint32_t>() + 1;
 	f.counters = reinterpret_cast<unsigned long long*>(h->dMisc.as<unsigned char>() + 16);
-	f.planes = h->dPlanes.as<float>(); f.maskPlane = h->dMask.as<uint32_t>(); f.planeStride = (int64_t)planeStride; f.planeW = planeW;
+	f.planes = h->dPlanes.as<float>(); f.maskPlane = reinterpret_cast<uint32_t*>(h->dPlanes.as<float>() + 7*planeStride); f.planeStride = (int64_t)planeStride; f.planeW = planeW;
 	f.filterMode = p.filter_mode; f.partials = h->dPartials.as<float>(); f.ntaps = ntaps;
 	f.channels = h->dChannels.as<float>();
 	f.rowOwned = (std::max(1, p.world_size) > 1) ? h->dRowOwned.as<uint8_t>() : nullptr;

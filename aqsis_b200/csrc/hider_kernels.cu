@@ -15,6 +15,7 @@
 //   k_filter     Filter_samples + ExposeBucket + quantise
 //                (bucketprocessor.cpp:584-707, 766-806; ddmanager.cpp:1022-1118)
 #include "hider_device.h"
+#include <cuda.h>      // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include <cfloat>
 
@@ -1603,65 +1604,87 @@ __global__ void __launch_bounds__(256) k_filter(DevFrame f, DevDisplays disp)
 	finishPixel(f, disp, x, y, acc, gTot, SampleCount);
 }
 
-// Reference-order filter, row staged and channel split.
+// Reference-order filter, row staged by TMA and channel split.
 // A CTA owns W consecutive output pixels of ONE image row and has 8*W threads: thread (px, ch)
 // accumulates channel ch of pixel px -- ch 0..6 = R G B Or Og Ob Z, ch 7 = the weight total and the
 // hit count -- over the taps in exactly the reference's fy, fx, sy, sx order
 // (bucketprocessor.cpp:597-629), so every per-channel float sum is the reference's own sequence of
-// roundings.  For each fy the n*(W+2*xmax) resolved samples of source row y+fy are staged ONCE in
-// shared memory (16-byte cp.async, all eight planes) and reused for the 2*xmax+1 values of fx, so a
-// sample travels L2 -> SM (2*ymax+1)*(1+2*xmax/W) times instead of (2*xmax+1)(2*ymax+1) times; with
-// the CTAs of neighbouring rows scheduled back to back the re-reads hit L2, not HBM.
+// roundings.  For each fy the n x CW box of resolved samples of source row y+fy is brought into
+// shared memory by ONE cp.async.bulk.tensor (TMA) per plane -- eight per row, issued by one thread,
+// completion on an mbarrier -- and reused for the 2*xmax+1 values of fx, so a sample travels
+// L2 -> SM (2*ymax+1)*CW/W times instead of (2*xmax+1)(2*ymax+1) times; CTAs of neighbouring rows
+// run back to back, so the re-reads hit L2 and HBM sees every sample once.  The tensor map covers
+// all eight planes as one 2-D array [8*sh*n rows][sw columns, row pitch planeW]; columns past the
+// sample region are zero-filled by the TMA unit (mask 0 = "no sample").
 // Weights come from constant memory (uniform index).  Excluded samples are skipped by predication,
-// never multiplied by zero, so stale plane contents under an unset mask are harmless.
+// never multiplied by zero.
 __constant__ float c_filt[49*256];
 
-__device__ __forceinline__ void cpAsync16(void* smemDst, const void* gsrc)
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count)
 {
-	const uint32_t d = (uint32_t)__cvta_generic_to_shared(smemDst);
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smemAddr(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cpAsyncWaitAll()
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes)
 {
-	asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra DONE_%=;\n"
+		"bra WAIT_%=;\n"
+		"DONE_%=:\n"
+		"}\n" :: "r"(smemAddr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmaLoad2D(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
+{
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+	             :: "r"(smemAddr(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smemAddr(bar)) : "memory");
 }
 
 template<int W>
-__global__ void __launch_bounds__(8*W) k_filter_rows(DevFrame f, DevDisplays disp)
+__global__ void __launch_bounds__(8*W) k_filter_rows(DevFrame f, DevDisplays disp, const __grid_constant__ CUtensorMap tmap)
 {
-	extern __shared__ __align__(16) unsigned char fsm[];
-	constexpr int THREADS = 8*W;
+	extern __shared__ __align__(128) unsigned char fsm[];
+	__shared__ __align__(8) uint64_t s_bar;
 	const int n = f.n, xmax = f.shiftX, ymax = f.shiftY;
 	const int CW = W + ((2*xmax + 3) & ~3);            // staged columns, a multiple of 4
-	const int planeSz = n*CW + 8;                        // +8 words: the eight planes start 8 banks apart
+	const int planeSz = (n*CW + 31) & ~31;               // every plane starts 128-byte aligned
 	float* tile = reinterpret_cast<float*>(fsm);         // [8 planes][n][CW]
 	const int tid = threadIdx.x, px = tid % W, ch = tid / W;
 	const int x0 = f.cropX0 + blockIdx.x*W, y = f.cropY0 + blockIdx.y;
 	if(f.rowOwned && !f.rowOwned[y]) return;             // uniform over the CTA
 	const int x = x0 + px;
 	const bool live = x < f.cropX1;
-	const int col0 = x0 - f.cropX0;                      // first staged column of the sample region (x0 - sx0 - xmax)
+	const int col0 = x0 - f.cropX0;                      // first staged column of the sample region (x0 - xmax - sx0)
 	const float* myPlane = tile + (size_t)(ch < 7 ? ch : 7)*planeSz;
 	const uint32_t* maskT = reinterpret_cast<const uint32_t*>(tile + (size_t)7*planeSz);
+	if(tid == 0)
+	{
+		mbarInit(&s_bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
 	float acc = 0.f;
 	int count = 0;
 	int tap = 0;
 	for(int fy = 0; fy <= 2*ymax; ++fy)
 	{
-		__syncthreads();                                 // everyone is done with the previous row
+		__syncthreads();                                 // barrier initialised / everyone is done with the previous row
+		if(tid == 0)
 		{
-			const int cw4 = CW >> 2, per = n*cw4;
-			const size_t rowBase = (size_t)(y + fy - ymax - f.sy0)*n*f.planeW + (size_t)col0;
-			for(int e = tid; e < 8*per; e += THREADS)
-			{
-				const int k = e / per, r = e - k*per, sI = r / cw4, c4 = r - sI*cw4;
-				const float* src = (k < 7 ? f.planes + (size_t)k*f.planeStride : reinterpret_cast<const float*>(f.maskPlane))
-				                   + rowBase + (size_t)sI*f.planeW + 4*c4;
-				cpAsync16(tile + (size_t)k*planeSz + sI*CW + 4*c4, src);
-			}
-			cpAsyncWaitAll();
+			// order the CTA's generic-proxy reads of the tile before the async-proxy overwrite
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			mbarExpectTx(&s_bar, (uint32_t)(8*n*CW*4));
+			const int row = (y + fy - ymax - f.sy0)*n;
+			for(int k = 0; k < 8; ++k)
+				tmaLoad2D(tile + (size_t)k*planeSz, &tmap, col0, k*f.sh*n + row, &s_bar);
 		}
-		__syncthreads();
+		mbarWait(&s_bar, (uint32_t)(fy & 1));
 		if(!live) { tap += 2*xmax + 1; continue; }
 		for(int fx = 0; fx <= 2*xmax; ++fx, ++tap)
 		{
@@ -1674,9 +1697,9 @@ __global__ void __launch_bounds__(8*W) k_filter_rows(DevFrame f, DevDisplays dis
 #pragma unroll 8
 				for(int sI = 0; sI < n; ++sI)
 				{
-					const uint32_t m = maskT[sI*CW + o];
+					const uint32_t m = ~maskT[sI*CW + o];
 					const float v = myPlane[sI*CW + o] * w[sI];
-					if((m & needV) == needV) acc += v;
+					if(!(m & needV)) acc += v;
 				}
 			}
 			else
@@ -1684,11 +1707,11 @@ __global__ void __launch_bounds__(8*W) k_filter_rows(DevFrame f, DevDisplays dis
 #pragma unroll 8
 				for(int sI = 0; sI < n; ++sI)
 				{
-					const uint32_t m = maskT[sI*CW + o];
-					if((m & need) == need)
+					const uint32_t m = ~maskT[sI*CW + o];
+					if(!(m & need))
 					{
 						acc += w[sI];
-						count += (int)(m >> 31);
+						count += (int)((~m) >> 31);
 					}
 				}
 			}
@@ -1712,7 +1735,36 @@ __global__ void __launch_bounds__(8*W) k_filter_rows(DevFrame f, DevDisplays dis
 static size_t filterRowsSmem(const DevFrame& f, int W)
 {
 	const int CW = W + ((2*f.shiftX + 3) & ~3);
-	return (size_t)8*((size_t)f.n*CW + 8)*4;
+	const size_t tile = (size_t)8*(((size_t)f.n*CW + 31) & ~(size_t)31)*4;
+	const size_t sums = (size_t)9*W*4;               // the per-pixel gather at the end reuses the tile
+	return tile > sums ? tile : sums;
+}
+
+// The tensor map of the resolved-sample planes: 2-D [8*sh*n][sw] floats, row pitch planeW, box n x CW.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static cudaError_t encodeSampleMap(const DevFrame& f, int W, CUtensorMap* map)
+{
+	static EncodeTiledFn fn = nullptr;
+	if(!fn)
+	{
+		void* p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+		if(e != cudaSuccess) return e;
+		if(q != cudaDriverEntryPointSuccess || !p) return cudaErrorNotSupported;
+		fn = reinterpret_cast<EncodeTiledFn>(p);
+	}
+	const int CW = W + ((2*f.shiftX + 3) & ~3);
+	const cuuint64_t dims[2] = {(cuuint64_t)f.sw, (cuuint64_t)8*f.sh*f.n};
+	const cuuint64_t strides[1] = {(cuuint64_t)f.planeW*4};
+	const cuuint32_t box[2] = {(cuuint32_t)CW, (cuuint32_t)f.n};
+	const cuuint32_t estr[2] = {1, 1};
+	CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)f.planes, dims, strides, box, estr,
+	                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+	                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 // Tile-partials filter: sum the nine per-(pixel,tap) partial sums over the taps in fy, fx order.
@@ -1837,24 +1889,27 @@ cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, const float
 		{
 			cudaError_t e = cudaMemcpyToSymbolAsync(c_filt, hostFilterTab, (size_t)ntapw*4, 0, cudaMemcpyHostToDevice, st);
 			if(e != cudaSuccess) return e;
+			CUtensorMap tmap;
+			e = encodeSampleMap(f, W, &tmap);
+			if(e != cudaSuccess) return e;
 			dim3 grid((w + W - 1)/W, h);
 			if(W == 32)
 			{
 				e = cudaFuncSetAttribute(k_filter_rows<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 				if(e != cudaSuccess) return e;
-				k_filter_rows<32><<<grid, 256, smem, st>>>(f, disp);
+				k_filter_rows<32><<<grid, 256, smem, st>>>(f, disp, tmap);
 			}
 			else if(W == 16)
 			{
 				e = cudaFuncSetAttribute(k_filter_rows<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 				if(e != cudaSuccess) return e;
-				k_filter_rows<16><<<grid, 128, smem, st>>>(f, disp);
+				k_filter_rows<16><<<grid, 128, smem, st>>>(f, disp, tmap);
 			}
 			else
 			{
 				e = cudaFuncSetAttribute(k_filter_rows<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 				if(e != cudaSuccess) return e;
-				k_filter_rows<8><<<grid, 64, smem, st>>>(f, disp);
+				k_filter_rows<8><<<grid, 64, smem, st>>>(f, disp, tmap);
 			}
 			return cudaGetLastError();
 		}
