@@ -273,22 +273,36 @@ int uploadTables(AqhHider* h)
 	return AQH_OK;
 }
 
-// Strips of pixel rows dealt round-robin to the ranks.  The strip height is a
-// multiple of 16 rows so that it is a multiple of every tile height chooseTile can pick.
+// Strips of pixel rows dealt round-robin to the ranks.
+//   strip_rows > 0: fixed strip height (rounded down to a multiple of 16 rows, at least 16);
+//   strip_rows <= 0 (default): balanced -- world*k strips of near-equal height with
+//   k = max(1, rows / (64*world)), so that every rank owns the same number of strips (a fixed
+//   64-row strip leaves 1080 rows as 17 strips: 3 on one of 8 ranks, 2 on the others).
 int stripRows(const AqhFrameParams& p)
 {
-	int strip = p.strip_rows > 0 ? p.strip_rows : 64;
-	return std::max(16, (strip/16)*16);
+	return std::max(16, (p.strip_rows/16)*16);
 }
 void computeStrips(const AqhFrameParams& p, int rank, std::vector<std::pair<int,int>>& strips)
 {
 	const int world = std::max(1, p.world_size);
-	const int strip = stripRows(p);
+	const int me = world > 1 ? rank : 0;
 	strips.clear();
-	int si = 0;
-	for(int y0 = p.crop_ymin; y0 < p.crop_ymax; y0 += strip, ++si)
-		if(si % world == (world > 1 ? rank : 0))
-			strips.push_back(std::make_pair(y0, std::min(y0 + strip, p.crop_ymax)));
+	if(p.strip_rows > 0)
+	{
+		const int strip = stripRows(p);
+		int si = 0;
+		for(int y0 = p.crop_ymin; y0 < p.crop_ymax; y0 += strip, ++si)
+			if(si % world == me)
+				strips.push_back(std::make_pair(y0, std::min(y0 + strip, p.crop_ymax)));
+		return;
+	}
+	const int64_t rows = std::max(0, p.crop_ymax - p.crop_ymin);
+	const int64_t nstrips = (int64_t)world*std::max<int64_t>(1, rows/(64*(int64_t)world));
+	for(int64_t si = me; si < nstrips; si += world)
+	{
+		const int y0 = p.crop_ymin + (int)(si*rows/nstrips), y1 = p.crop_ymin + (int)((si + 1)*rows/nstrips);
+		if(y1 > y0) strips.push_back(std::make_pair(y0, y1));
+	}
 }
 
 // Every rank also hides the `shift` rows of halo samples its filter footprint needs.

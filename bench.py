@@ -194,7 +194,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4])
     ap.add_argument("--scale", type=float, default=1.0, help="linear image scale of the workload (1.0 = as named)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--strip-rows", type=int, default=64)
+    ap.add_argument("--strip-rows", type=int, default=0, help="strip height; 0 = balanced (world*k near-equal strips)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -352,7 +352,7 @@ def main():
             "config": {"workload": WORKLOADS[args.config] + ("" if args.scale == 1.0 else f" [scale {args.scale}]"),
                        "micropolygons": n_mp_total, "samples": n_samples_total,
                        "l2_policy": "inputs (>= 0.8 GB) and sample planes (>= 4 GB) exceed the 126 MB L2",
-                       "parallelism": f"{world} rank(s), {args.strip_rows}-row strips round-robin, NCCL gather"},
+                       "parallelism": f"{world} rank(s), {len(sharding.strips_for_rank(params, 0))} strip(s) of pixel rows per rank dealt round-robin, grids replicated to the ranks they touch, NCCL gather to rank 0"},
             "stages_ms": {k: round(v, 4) for k, v in stage.items() if k.endswith("_ms")},
             "gpu_launches": int(stage["launches"]),
             "roofline": {"bound": "hbm", "kernel": "k_hide", "achieved": achieved, "peak": peak, "unit": "GB/s",

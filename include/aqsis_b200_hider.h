@@ -139,7 +139,7 @@ typedef struct AqhFrameParams
 	AqhDisplayDesc display[AQH_MAX_DISPLAYS];
 	/* --- device-side knobs (no reference analogue) --- */
 	int32_t rank, world_size;       /* image strips are dealt round-robin to ranks; 0,1 = whole image */
-	int32_t strip_rows;             /* strip height in pixel rows (rounded down to a multiple of 16); 0 = 64 */
+	int32_t strip_rows;             /* strip height in pixel rows (rounded down to a multiple of 16); 0 = balanced: world*k near-equal strips */
 	int32_t deep_hits_per_sample;   /* average capacity of the transparent hit pool; 0 = default */
 	int32_t filter_mode;            /* AQH_FILTER_*; 0 = AQH_FILTER_REFERENCE_ORDER (bit-exact sums) */
 	int32_t reserved[7];
@@ -254,7 +254,8 @@ AQH_EXPORT int aqh_device_channels(const AqhHider* h, void** dev_ptr, size_t* by
 AQH_EXPORT int aqh_device_display(const AqhHider* h, int display, void** dev_ptr, size_t* bytes);
 /* Pixel rows [y0,y1) of strip i owned by this rank. */
 /* Device-less: the strips (pixel-row ranges) `rank` of p->world_size owns, round-robin in strips of
- * p->strip_rows rows rounded down to a multiple of 16 (default 64).  Writes min(*n_strips, capacity) entries. */
+ * p->strip_rows rows rounded down to a multiple of 16, or (strip_rows <= 0, the default) world*k near-equal
+ * strips with k = max(1, rows/(64*world)) so every rank owns k of them.  Writes min(*n_strips, capacity) entries. */
 AQH_EXPORT int aqh_strip_layout(const AqhFrameParams* p, int rank, int* n_strips, int* y0, int* y1, int capacity);
 AQH_EXPORT int aqh_num_strips(const AqhHider* h, int* n);
 AQH_EXPORT int aqh_strip(const AqhHider* h, int i, int* y0, int* y1);

@@ -86,7 +86,8 @@ def test_sharded_render_equals_single_process(tmp_path, kind, world):
 def test_strips_partition_the_crop_window(native_lib):
     from aqsis_b200 import default_params, sharding
     for yres, crop, strip, world in [(200, None, 0, 1), (200, None, 32, 3), (1080, None, 64, 8), (97, (0, 50, 7, 91), 16, 4),
-                                     (64, None, 40, 2)]:
+                                     (64, None, 40, 2), (1080, None, 0, 8), (2160, None, 0, 8),
+                                     (1080, None, 0, 2), (100, (0, 50, 3, 90), 0, 4), (5, None, 0, 8)]:
         kw = dict(resolution=(50, yres))
         if crop:
             kw["crop"] = crop
@@ -97,11 +98,17 @@ def test_strips_partition_the_crop_window(native_lib):
             for y0, y1 in sharding.strips_for_rank(p, r):
                 assert np.all(owner[y0:y1] == -1)
                 owner[y0:y1] = r
-                assert (y0 - p.crop_ymin) % 16 == 0
+                if strip > 0:
+                    assert (y0 - p.crop_ymin) % 16 == 0
         assert np.all(owner[p.crop_ymin:p.crop_ymax] >= 0)
         assert np.all(owner[:p.crop_ymin] == -1) and np.all(owner[p.crop_ymax:] == -1)
         if world > 1 and (p.crop_ymax - p.crop_ymin) >= 16 * world * max(1, strip // 16):
             assert len(set(owner[p.crop_ymin:p.crop_ymax])) == world
+        if strip == 0 and world > 1 and (p.crop_ymax - p.crop_ymin) >= world:
+            # balanced mode: every rank owns the same number of strips and row counts differ by < one strip's rounding
+            counts = [int((owner == r).sum()) for r in range(world)]
+            nstr = [len(sharding.strips_for_rank(p, r)) for r in range(world)]
+            assert len(set(nstr)) == 1 and max(counts) - min(counts) <= nstr[0]
 
 
 def test_split_keeps_grid_payload_intact(native_lib):
