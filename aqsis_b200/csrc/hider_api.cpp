@@ -127,7 +127,7 @@ struct AqhHider
 	PinnedBuf stP, stCi, stOi, stCulled;
 	size_t stPUsed = 0, stVUsed = 0;   // floats*3 units: positions / vertices staged
 	// device buffers
-	DevBuf dPraw, dCi, dOi, dCulled, dP4, dGrids, dChunk, dKeyTimes, dSplit;
+	DevBuf dPraw, dCi, dOi, dCulled, dP4, dCO, dGrids, dChunk, dKeyTimes, dSplit;
 	DevBuf dPosTab, dVal1d, dShuf, dPat, dFilt, dDofB, dDither;
 	DevBuf dTileSlot, dActive, dBinCount, dBinOffset, dBinEntries, dMisc, dTileFlags;
 	DevBuf dPlanes, dMask, dPartials, dDeepA, dDeepUV, dChannels, dRowOwned;
@@ -407,6 +407,7 @@ int renderFrame(AqhHider* h, bool download)
 	CU(h->dKeyTimes.reserve(std::max<size_t>(h->gkeyTimes.size(), 1)*4), "cudaMalloc(key times)");
 	CU(h->dSplit.reserve(std::max<size_t>(h->gkeyTimes.size(), 1)*16), "cudaMalloc(split lines)");
 	CU(h->dP4.reserve(std::max<size_t>(nPos, 1)*16 + 64), "cudaMalloc(P4)");
+	CU(h->dCO.reserve(std::max<size_t>(nVerts, 1)*32 + 64), "cudaMalloc(packed Ci/Oi)");
 	CU(h->dTileSlot.reserve(std::max<size_t>(h->tileSlot.size(), 1)*4), "cudaMalloc(tile slots)");
 	CU(h->dActive.reserve(std::max<size_t>(nActive, 1)*4), "cudaMalloc(active tiles)");
 	CU(h->dBinCount.reserve(std::max<size_t>(nActive, 1)*4), "cudaMalloc(bin counts)");
@@ -538,6 +539,7 @@ int renderFrame(AqhHider* h, bool download)
 	f.keyTimes = h->dKeyTimes.as<float>(); f.splitLines = h->dSplit.as<float4>();
 	f.nPos = h->nPos; f.nVerts = h->nVerts; f.nGrids = (int)nGrids;
 	f.P4 = h->dP4.as<float4>();
+	f.CO = h->dCO.as<float4>();
 	f.posTab = h->dPosTab.as<float2>(); f.val1d = h->dVal1d.as<float>(); f.shufTab = h->dShuf.as<uint8_t>();
 	f.patPlanes = h->dPat.as<uint8_t>(); f.filterTab = h->dFilt.as<float>(); f.dofBounds = h->dDofB.as<float4>();
 	f.dither = h->dDither.as<float>();

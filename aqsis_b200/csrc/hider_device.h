@@ -64,6 +64,7 @@ struct DevFrame
 	int nGrids;
 	// derived geometry
 	float4* P4;                    // n_pos: raster x, raster y, camera z, info bits
+	float4* CO;                    // n_verts x 2: (Ci.r, Ci.g, Ci.b, Oi.r), (Oi.g, Oi.b, -, -): 16-byte loads for the shading of hits
 	// frame tables
 	const float2* posTab;          // ncache*n
 	const float* val1d;            // ncache*n

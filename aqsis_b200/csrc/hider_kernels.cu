@@ -116,9 +116,13 @@ __global__ void __launch_bounds__(256) k_project(DevFrame f)
 		const uint32_t cu = g.cu_cv & 0xffffu, cv = g.cu_cv >> 16;
 		const uint32_t iv = v / (cu + 1), iu = v - iv*(cu + 1);
 		const uint32_t vid = g.vbase + v;
-		bool opaque = true;
-		if(f.Oi)
-			opaque = (f.Oi[3*(size_t)vid] >= 1.0f) && (f.Oi[3*(size_t)vid+1] >= 1.0f) && (f.Oi[3*(size_t)vid+2] >= 1.0f);
+		float ci0 = 1.0f, ci1 = 1.0f, ci2 = 1.0f, oi0 = 1.0f, oi1 = 1.0f, oi2 = 1.0f;
+		if(f.Ci) { ci0 = f.Ci[3*(size_t)vid]; ci1 = f.Ci[3*(size_t)vid+1]; ci2 = f.Ci[3*(size_t)vid+2]; }
+		if(f.Oi) { oi0 = f.Oi[3*(size_t)vid]; oi1 = f.Oi[3*(size_t)vid+1]; oi2 = f.Oi[3*(size_t)vid+2]; }
+		// packed copy for the hit shading (two 16-byte loads per corner instead of six scalar ones)
+		f.CO[2*(size_t)vid] = make_float4(ci0, ci1, ci2, oi0);
+		f.CO[2*(size_t)vid+1] = make_float4(oi1, oi2, 0.f, 0.f);
+		const bool opaque = (oi0 >= 1.0f) && (oi1 >= 1.0f) && (oi2 >= 1.0f);
 		bool valid = (iu < cu) && (iv < cv) && !(f.culled && f.culled[vid]);
 		if(opaque) info |= VINFO_OPAQUE;
 		if(valid) info |= VINFO_MP_VALID;
@@ -477,33 +481,27 @@ __device__ __forceinline__ void shadeHit(const DevFrame& f, const GridRec& g, ui
 	const size_t v0 = (size_t)g.vbase + (p - g.pbase);
 	if(g.flags & AQH_GRID_SMOOTH)
 	{
-		const size_t vi[4] = {v0, v0 + 1, v0 + cu + 1, v0 + cu + 2};
+		const float4 a0 = f.CO[2*v0], a1 = f.CO[2*v0+1];
+		const float4 b0 = f.CO[2*(v0+1)], b1 = f.CO[2*(v0+1)+1];
+		const float4 c0 = f.CO[2*(v0+cu+1)], c1 = f.CO[2*(v0+cu+1)+1];
+		const float4 d0 = f.CO[2*(v0+cu+2)], d1 = f.CO[2*(v0+cu+2)+1];
 		float w[4];
 		w[0] = (1.f-uv.x)*(1.f-uv.y);
 		w[1] = uv.x*(1.f-uv.y);
 		w[2] = (1.f-uv.x)*uv.y;
 		w[3] = uv.x*uv.y;
-#pragma unroll
-		for(int k = 0; k < 3; ++k)
-		{
-			if(f.Ci)
-				col[k] = w[0]*f.Ci[3*vi[0]+k] + w[1]*f.Ci[3*vi[1]+k] + w[2]*f.Ci[3*vi[2]+k] + w[3]*f.Ci[3*vi[3]+k];
-			else
-				col[k] = w[0]*1.0f + w[1]*1.0f + w[2]*1.0f + w[3]*1.0f;
-			if(f.Oi)
-				opa[k] = w[0]*f.Oi[3*vi[0]+k] + w[1]*f.Oi[3*vi[1]+k] + w[2]*f.Oi[3*vi[2]+k] + w[3]*f.Oi[3*vi[3]+k];
-			else
-				opa[k] = w[0]*1.0f + w[1]*1.0f + w[2]*1.0f + w[3]*1.0f;
-		}
+		col[0] = w[0]*a0.x + w[1]*b0.x + w[2]*c0.x + w[3]*d0.x;
+		col[1] = w[0]*a0.y + w[1]*b0.y + w[2]*c0.y + w[3]*d0.y;
+		col[2] = w[0]*a0.z + w[1]*b0.z + w[2]*c0.z + w[3]*d0.z;
+		opa[0] = w[0]*a0.w + w[1]*b0.w + w[2]*c0.w + w[3]*d0.w;
+		opa[1] = w[0]*a1.x + w[1]*b1.x + w[2]*c1.x + w[3]*d1.x;
+		opa[2] = w[0]*a1.y + w[1]*b1.y + w[2]*c1.y + w[3]*d1.y;
 	}
 	else
 	{
-#pragma unroll
-		for(int k = 0; k < 3; ++k)
-		{
-			col[k] = f.Ci ? f.Ci[3*v0+k] : 1.0f;
-			opa[k] = f.Oi ? f.Oi[3*v0+k] : 1.0f;
-		}
+		const float4 a0 = f.CO[2*v0], a1 = f.CO[2*v0+1];
+		col[0] = a0.x; col[1] = a0.y; col[2] = a0.z;
+		opa[0] = a0.w; opa[1] = a1.x; opa[2] = a1.y;
 	}
 }
 
@@ -515,7 +513,7 @@ __device__ __forceinline__ void shadeHit(const DevFrame& f, const GridRec& g, ui
 //   u64 keys[nsP] | f32 posx[nsP] | f32 posy[nsP] | [f32 time[nsP]] | [float2 dof[nsP]] | [u32 head[nsP]] |
 //   StaticRec recs[nwarps*RECS_PER_WARP] | u32 pixZ[tileW*tileH] | u16 subOfs[n] | u8 shufPat[tileW*tileH]
 #define SMEM_PAD 8
-#define RECS_PER_WARP 16
+#define RECS_PER_WARP 8
 struct StaticRec   // 36 words
 {
 	float X[4], Y[4], XM[4], YM[4];
@@ -614,12 +612,27 @@ struct DeepCtx
 {
 	uint4* A; float2* UV; uint32_t cap; uint32_t* count;   // count lives in shared memory
 };
+template<bool AGG>
 __device__ __forceinline__ void storeDeep(const DevFrame& f, const DeepCtx& dc, const HideSmem& s, int idx,
                                           float D, uint32_t p, float2 uv)
 {
 	const uint32_t occl = (uint32_t)(s.keys[idx] >> 32);
 	if(!(depthKey(D) < occl)) return;                 // isCullable && occlZ <= D
-	uint32_t slot = atomicAdd(dc.count, 1u);
+	uint32_t slot;
+	if(AGG)
+	{
+		// one pool allocation for the lanes that arrive here together (no convergence is assumed:
+		// the group is whatever __activemask() reports), instead of one shared-memory atomic per hit
+		const unsigned m = __activemask();
+		const int lane = threadIdx.x & 31;
+		const int leader = __ffs(m) - 1;
+		uint32_t base = 0;
+		if(lane == leader) base = atomicAdd(dc.count, (uint32_t)__popc(m));
+		base = __shfl_sync(m, base, leader);
+		slot = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+	}
+	else
+		slot = atomicAdd(dc.count, 1u);
 	if(slot >= dc.cap) { atomicOr(f.errorFlags, 1u); return; }
 	uint32_t next = atomicExch(&s.head[idx], slot);
 	dc.A[slot] = make_uint4(next, __float_as_uint(D), p, (uint32_t)idx);
@@ -725,7 +738,7 @@ __device__ void setupStaticRec(const DevFrame& f, const TileCtx& t, const HideSm
 	r.rect = (uint32_t)gx0 | ((uint32_t)gx1 << 8) | ((uint32_t)gy0 << 16) | ((uint32_t)gy1 << 24);
 }
 
-template<bool OPAQUE>
+template<bool OPAQUE, bool AGG>
 __device__ __forceinline__ void sampleStaticRec(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc,
                                                 const StaticRec& r, int lane)
 {
@@ -767,7 +780,7 @@ __device__ __forceinline__ void sampleStaticRec(const DevFrame& f, const TileCtx
 		if(OPAQUE)
 			storeOpaque(s, &s.keys[idx], D, r.p);
 		else
-			storeDeep(f, dc, s, idx, D, r.p, uv);
+			storeDeep<AGG>(f, dc, s, idx, D, r.p, uv);
 	}
 }
 
@@ -908,7 +921,7 @@ __device__ __forceinline__ void testCandidateMBDof(const DevFrame& f, const Tile
 	if(OPAQUE)
 		storeOpaque(s, &s.keys[idx], D, m.p);
 	else
-		storeDeep(f, dc, s, idx, D, m.p, uv);
+		storeDeep<false>(f, dc, s, idx, D, m.p, uv);
 }
 
 // Returns false for a static micropolygon in a frame without depth of field: the reference
@@ -1145,20 +1158,57 @@ __device__ void resolveSample(const DevFrame& f, const TileCtx& t, const HideSme
 		}
 		if(opa[0] >= f.zthr[0] && opa[1] >= f.zthr[1] && opa[2] >= f.zthr[2]) opaqueDepth0 = depth;
 	}
-	unsigned long long prev = ~0ull;
-	for(;;)
+	// One walk over the sample's list collects up to DEEP_SORT entries into a register-resident,
+	// descending (depth, submission) order -- the pointer chase through the pool is paid once;
+	// longer lists fall back to repeated selection of the farthest not yet composited entry.
+	constexpr int DEEP_SORT = 8;
+	unsigned long long ks[DEEP_SORT];
+	uint32_t sl[DEEP_SORT];
+#pragma unroll
+	for(int j = 0; j < DEEP_SORT; ++j) { ks[j] = 0ull; sl[j] = 0xffffffffu; }
+	int nList = 0;
+	for(uint32_t e = head; e != 0xffffffffu; )
 	{
-		// farthest not yet composited entry: largest (depthKey, p) strictly below prev
-		unsigned long long best = 0; uint32_t bestSlot = 0xffffffffu;
-		for(uint32_t e = head; e != 0xffffffffu; )
+		const uint4 A = dc.A[e];
+		unsigned long long k = ((unsigned long long)depthKey(__uint_as_float(A.y)) << 32) | A.z;
+		uint32_t ce = e;
+#pragma unroll
+		for(int j = 0; j < DEEP_SORT; ++j)
 		{
-			const uint4 A = dc.A[e];
-			unsigned long long k = ((unsigned long long)depthKey(__uint_as_float(A.y)) << 32) | A.z;
-			if(k < prev && (bestSlot == 0xffffffffu || k > best)) { best = k; bestSlot = e; }
-			e = A.x;
+			// strict '>' keeps equal keys (a hit stored twice on a time sub-bound boundary) both in the list
+			if(k > ks[j] || (sl[j] == 0xffffffffu && ce != 0xffffffffu))
+			{
+				const unsigned long long tk = ks[j]; const uint32_t ts = sl[j];
+				ks[j] = k; sl[j] = ce; k = tk; ce = ts;
+			}
 		}
-		if(bestSlot == 0xffffffffu) break;
-		prev = best;
+		++nList;
+		e = A.x;
+	}
+	unsigned long long prev = ~0ull;
+	for(int step = 0; ; ++step)
+	{
+		uint32_t bestSlot = 0xffffffffu;
+		if(nList <= DEEP_SORT)
+		{
+			if(step >= nList) break;
+#pragma unroll
+			for(int j = 0; j < DEEP_SORT; ++j) if(j == step) bestSlot = sl[j];
+		}
+		else
+		{
+			// farthest not yet composited entry: largest (depthKey, p) strictly below prev
+			unsigned long long best = 0;
+			for(uint32_t e = head; e != 0xffffffffu; )
+			{
+				const uint4 A = dc.A[e];
+				unsigned long long k = ((unsigned long long)depthKey(__uint_as_float(A.y)) << 32) | A.z;
+				if(k < prev && (bestSlot == 0xffffffffu || k > best)) { best = k; bestSlot = e; }
+				e = A.x;
+			}
+			if(bestSlot == 0xffffffffu) break;
+			prev = best;
+		}
 		const uint4 A = dc.A[bestSlot];
 		const float2 uv = dc.UV[bestSlot];
 		const float4 a = f.P4[A.z];
@@ -1349,8 +1399,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 							// static micropolygon in a frame without depth of field
 							if(lane == 0) setupStaticRec(f, t, s, p, pass == 0, myRecs[0]);
 							__syncwarp();
-							if(pass == 0) sampleStaticRec<true>(f, t, s, dc, myRecs[0], lane);
-							else sampleStaticRec<false>(f, t, s, dc, myRecs[0], lane);
+							if(pass == 0) sampleStaticRec<true, false>(f, t, s, dc, myRecs[0], lane);
+							else sampleStaticRec<false, false>(f, t, s, dc, myRecs[0], lane);
 							__syncwarp();
 						}
 					}
@@ -1361,8 +1411,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 					__syncwarp();
 					for(int j = 0; j < cnt; ++j)
 					{
-						if(pass == 0) sampleStaticRec<true>(f, t, s, dc, myRecs[j], lane);
-						else sampleStaticRec<false>(f, t, s, dc, myRecs[j], lane);
+						if(pass == 0) sampleStaticRec<true, true>(f, t, s, dc, myRecs[j], lane);
+						else sampleStaticRec<false, true>(f, t, s, dc, myRecs[j], lane);
 					}
 					__syncwarp();
 				}

@@ -15,7 +15,7 @@ from . import _abi as abi
 from ._abi import FrameParams, DisplayDesc, GridBlock, GridDesc, Callbacks, FrameStats
 
 _LIB = None
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libaqsis_b200_hider.so")
+_LIB_PATH = os.environ.get("AQSIS_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libaqsis_b200_hider.so")
 
 
 class HiderError(RuntimeError):
