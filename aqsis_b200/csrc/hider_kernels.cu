@@ -533,8 +533,10 @@ struct TileCtx
 	int rx0, ry0, rx1, ry1;    // tile ∩ sample region (global pixels)
 };
 
+struct MovScratch;
 struct HideSmem
 {
+	MovScratch* mov;           // per-warp scratch of the motion blur / depth of field path (MBDOF kernel only)
 	unsigned long long* keys;
 	float* posx;
 	float* posy;
@@ -552,7 +554,7 @@ struct HideSmem
 
 __host__ __device__ __forceinline__ int hideStride(const DevFrame& f) { return f.tileW*f.xs + SMEM_PAD; }
 
-__device__ __forceinline__ HideSmem carveSmem(const DevFrame& f, unsigned char* base, int nrecs)
+__device__ __forceinline__ HideSmem carveSmem(const DevFrame& f, unsigned char* base, int nrecs, size_t movBytes)
 {
 	HideSmem s;
 	s.stride = hideStride(f);
@@ -568,13 +570,14 @@ __device__ __forceinline__ HideSmem carveSmem(const DevFrame& f, unsigned char* 
 	if(f.anyTransparent) { s.head = (uint32_t*)(base + o); o += ns*4; }
 	o = (o + 15) & ~(size_t)15;
 	s.recs = (StaticRec*)(base + o); o += (size_t)nrecs*sizeof(StaticRec);
+	s.mov = (MovScratch*)(base + o); o += movBytes;
 	s.pixZ = (uint32_t*)(base + o); o += (size_t)f.tileW*f.tileH*4;
 	s.subOfs = (uint16_t*)(base + o); o += (size_t)f.n*2;
 	s.shufPat = (uint8_t*)(base + o);
 	return s;
 }
 
-static size_t hideSmemBytes(const DevFrame& f, int nrecs)
+static size_t hideSmemBytes(const DevFrame& f, int nrecs, size_t movBytes)
 {
 	const size_t ns = (size_t)f.tileH*f.ys*hideStride(f);
 	size_t o = ns*16;
@@ -582,7 +585,7 @@ static size_t hideSmemBytes(const DevFrame& f, int nrecs)
 	if(f.anyMotion) o += ns*4;
 	if(f.anyTransparent) o += ns*4;
 	o = (o + 15) & ~(size_t)15;
-	o += (size_t)nrecs*sizeof(StaticRec);
+	o += (size_t)nrecs*sizeof(StaticRec) + movBytes;
 	o += (size_t)f.tileW*f.tileH*4;
 	o += (size_t)f.n*2 + (size_t)f.tileW*f.tileH;
 	return (o + 15) & ~(size_t)15;
@@ -785,8 +788,13 @@ __device__ __forceinline__ void sampleStaticRec(const DevFrame& f, const TileCtx
 }
 
 // ---- motion blur and/or depth of field: RenderMPG_MBOrDof (bucketprocessor.cpp:1221-1469).
-// One warp per micropolygon; the reference's loops over time sub-bounds are walked by the
-// whole warp, lanes spread over lens cells (DoF) or over (pixel, sample index) pairs (MB).
+// One warp per micropolygon.  The key vertices and key bounds of the micropolygon are staged once in the
+// warp's shared-memory scratch.  The reference's loops -- time sub-bounds, then lens cells (DoF) or
+// (pixel, sample index) pairs (MB) -- are walked by the lanes with only the reference's CHEAP gates
+// (time window, shifted-bound test, occlusion cull) evaluated in place; survivors are pushed on the warp's
+// candidate queue, and the expensive part (vertex interpolation at the sample time, per-vertex circle of
+// confusion, edge set-up, edge tests, inverse bilinear) is run on full batches of 32 queued candidates,
+// one per lane, so that the heavy code exists once and runs with (almost) all lanes active.
 struct MovingMP
 {
 	uint32_t p, nverts, cu, nkeys;
@@ -795,17 +803,39 @@ struct MovingMP
 	GridRec g;
 };
 
-__device__ __forceinline__ B2 keyBound(const DevFrame& f, const MovingMP& m, uint32_t k)
+#define MOV_KMAX 4          /* keys staged in shared memory; further keys are read from HBM */
+#define MOV_QCAP 1056       /* 1024 pushes per enumeration round + the < 32 left by the previous one */
+struct MovScratch           // per warp, 16-byte aligned
 {
+	float4 kv[MOV_KMAX][4];         // key vertices in natural order (x, y, z, info)
+	float4 kb[MOV_KMAX][2];         // key bounds: (mnx, mny, mnz, mxx), (mxy, mxz, -, -)
+	uint32_t qcount, pad[3];
+	uint16_t q[MOV_QCAP];           // candidate sample indices
+};
+
+__device__ __forceinline__ float4 movVert(const DevFrame& f, const MovingMP& m, const MovScratch* ws, uint32_t k, int i)
+{
+	if(ws && k < MOV_KMAX) return ws->kv[k][i];
+	const float4* Pk = f.P4 + m.p + (size_t)k*m.nverts;
+	return Pk[(uint32_t)(i & 1) + (uint32_t)(i >> 1)*(m.cu + 1)];
+}
+__device__ __forceinline__ B2 keyBound(const DevFrame& f, const MovingMP& m, const MovScratch* ws, uint32_t k)
+{
+	if(ws && k < MOV_KMAX)
+	{
+		const float4 a = ws->kb[k][0], b = ws->kb[k][1];
+		B2 r; r.mnx = a.x; r.mny = a.y; r.mnz = a.z; r.mxx = a.w; r.mxy = b.x; r.mxz = b.y;
+		return r;
+	}
 	const float4* Pk = f.P4 + m.p + (size_t)k*m.nverts;
 	return boundOf4(Pk[0], Pk[1], Pk[m.cu+1], Pk[m.cu+2]);
 }
 
 // Vertices of the micropolygon for one sample: CqMicroPolygon(Motion)::Sample,
 // micropolygon.cpp:1561-1589 and 1768-1873.  Returns false when the tight-bound test fails.
-__device__ bool samplePoints(const DevFrame& f, const MovingMP& m, bool moving, const B2& mpBound,
-                             float2 cocMin, float2 cocMax, float2 pos, float2 dofOff, float time,
-                             float px[4], float py[4], float pz[4], bool doBoundTest)
+__device__ __forceinline__ bool samplePoints(const DevFrame& f, const MovingMP& m, const MovScratch* ws, bool moving, const B2& mpBound,
+                                             float2 cocMin, float2 cocMax, float2 pos, float2 dofOff, float time,
+                                             float px[4], float py[4], float pz[4], bool doBoundTest)
 {
 	B2 tight;
 	float Fraction = 0.0f;
@@ -828,10 +858,10 @@ __device__ bool samplePoints(const DevFrame& f, const MovingMP& m, bool moving, 
 		if(doBoundTest)
 		{
 			if(Exact)
-				tight = keyBound(f, m, iIndex);
+				tight = keyBound(f, m, ws, iIndex);
 			else
 			{
-				const B2 b1 = keyBound(f, m, iIndex), b2 = keyBound(f, m, iIndex+1);
+				const B2 b1 = keyBound(f, m, ws, iIndex), b2 = keyBound(f, m, ws, iIndex+1);
 				tight.mnx = (1.f-Fraction)*b1.mnx + Fraction*b2.mnx; tight.mny = (1.f-Fraction)*b1.mny + Fraction*b2.mny;
 				tight.mnz = (1.f-Fraction)*b1.mnz + Fraction*b2.mnz;
 				tight.mxx = (1.f-Fraction)*b1.mxx + Fraction*b2.mxx; tight.mxy = (1.f-Fraction)*b1.mxy + Fraction*b2.mxy;
@@ -857,21 +887,18 @@ __device__ bool samplePoints(const DevFrame& f, const MovingMP& m, bool moving, 
 			if((pos.x < tight.mnx || pos.x > tight.mxx) || (pos.y < tight.mny || pos.y > tight.mxy)) return false;
 		}
 	}
-	const float4* K1 = f.P4 + m.p + (size_t)iIndex*m.nverts;
-	const uint32_t off[4] = {0, 1, m.cu+1, m.cu+2};
 	if(Exact)
 	{
 #pragma unroll
-		for(int i = 0; i < 4; ++i) { float4 v = K1[off[i]]; px[i] = v.x; py[i] = v.y; pz[i] = v.z; }
+		for(int i = 0; i < 4; ++i) { const float4 v = movVert(f, m, ws, iIndex, i); px[i] = v.x; py[i] = v.y; pz[i] = v.z; }
 	}
 	else
 	{
-		const float4* K2 = K1 + m.nverts;
 		const float F1 = 1.0f - Fraction;
 #pragma unroll
 		for(int i = 0; i < 4; ++i)
 		{
-			float4 a = K1[off[i]], b = K2[off[i]];
+			const float4 a = movVert(f, m, ws, iIndex, i), b = movVert(f, m, ws, iIndex+1, i);
 			px[i] = (F1*a.x) + (Fraction*b.x);
 			py[i] = (F1*a.y) + (Fraction*b.y);
 			pz[i] = (F1*a.z) + (Fraction*b.z);
@@ -890,46 +917,77 @@ __device__ bool samplePoints(const DevFrame& f, const MovingMP& m, bool moving, 
 	return true;
 }
 
-// One candidate (micropolygon, sample) of the MB/DoF path, after the reference's gates.
-template<bool OPAQUE>
-__device__ __forceinline__ void testCandidateMBDof(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc,
-                                                   const MovingMP& m, bool moving, const B2& mpBound, float2 cocMin, float2 cocMax,
-                                                   int idx, float bzminKeyf /*unused*/, uint32_t zminKey,
-                                                   float bminx, float bminy, float bmaxx, float bmaxy, float time0, float time1)
+// Per-micropolygon constants of the heavy part.
+struct MovCtx
+{
+	MovingMP m;
+	B2 mpBound;
+	float2 cocMin, cocMax;
+	bool moving, opaquePass;
+};
+
+// One queued candidate (micropolygon, sample): everything of CqMicroPolygon(Motion)::Sample after the gates
+// that were evaluated at enumeration time.
+__device__ __forceinline__ void movCandidate(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc,
+                                             const MovCtx& c, const MovScratch* ws, int idx)
 {
 	const float2 pos = make_float2(s.posx[idx], s.posy[idx]);
 	const float time = s.time ? s.time[idx] : f.shutterOpen;
-	if(moving && (time < time0 || time > time1)) return;
-	if((pos.x < bminx || pos.x > bmaxx) || (pos.y < bminy || pos.y > bmaxy)) return;
-	const uint32_t occl = (uint32_t)(s.keys[idx] >> 32);
-	if(zminKey > occl) return;
-	if(m.g.lod0 >= 0.0f)
+	if(c.m.g.lod0 >= 0.0f)
 	{
 		float lod = sampleLod(f, t, s, idx);
-		if(m.g.lod0 > lod || lod >= m.g.lod1) return;
+		if(c.m.g.lod0 > lod || lod >= c.m.g.lod1) return;
 	}
 	const float2 dofOff = s.dof ? s.dof[idx] : make_float2(0.f, 0.f);
 	float px[4], py[4], pz[4];
-	if(!samplePoints(f, m, moving, mpBound, cocMin, cocMax, pos, dofOff, time, px, py, pz, true)) return;
-	HitCache c;
-	cachePointInPolyTest(c, px, py, pz, m.code);
-	if(!edgeTests(c.X, c.Y, c.XM, c.YM, pos.x, pos.y)) return;
-	const float2 uv = invBilinear(c.Ax, c.Ay, c.Ex, c.Ey, c.Fx, c.Fy, c.Gx, c.Gy, c.linear, pos.x, pos.y);
-	const float D = bilerpZ(c.z, uv);
-	if(m.g.flags & AQH_GRID_TRIANGULAR)
-		if(triangleSplitReject(f, m.g, pos, dofOff, D, time)) return;
-	if(OPAQUE)
-		storeOpaque(s, &s.keys[idx], D, m.p);
+	if(!samplePoints(f, c.m, ws, c.moving, c.mpBound, c.cocMin, c.cocMax, pos, dofOff, time, px, py, pz, true)) return;
+	HitCache hc;
+	cachePointInPolyTest(hc, px, py, pz, c.m.code);
+	if(!edgeTests(hc.X, hc.Y, hc.XM, hc.YM, pos.x, pos.y)) return;
+	const float2 uv = invBilinear(hc.Ax, hc.Ay, hc.Ex, hc.Ey, hc.Fx, hc.Fy, hc.Gx, hc.Gy, hc.linear, pos.x, pos.y);
+	const float D = bilerpZ(hc.z, uv);
+	if(c.m.g.flags & AQH_GRID_TRIANGULAR)
+		if(triangleSplitReject(f, c.m.g, pos, dofOff, D, time)) return;
+	if(c.opaquePass)
+		storeOpaque(s, &s.keys[idx], D, c.m.p);
 	else
-		storeDeep<false>(f, dc, s, idx, D, m.p, uv);
+		storeDeep<false>(f, dc, s, idx, D, c.m.p, uv);
+}
+
+// Queue a candidate that passed the cheap gates (called from divergent per-lane loops).
+__device__ __forceinline__ void movPush(const DevFrame& f, MovScratch* ws, int idx)
+{
+	const uint32_t slot = atomicAdd(&ws->qcount, 1u);
+	if(slot < MOV_QCAP) ws->q[slot] = (uint16_t)idx;
+	else atomicOr(f.errorFlags, 4u);          // cannot happen: rounds are sized to the queue
+}
+
+// Run the heavy part on batches of up to 32 queued candidates while at least `need` are waiting.
+// Called by the whole warp at a converged point.
+__device__ __forceinline__ void movDrain(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc,
+                                         const MovCtx& c, MovScratch* ws, int lane, uint32_t need)
+{
+	for(;;)
+	{
+		__syncwarp();
+		uint32_t cnt = *(volatile uint32_t*)&ws->qcount;
+		if(cnt > MOV_QCAP) cnt = MOV_QCAP;
+		if(cnt < need) break;
+		const uint32_t take = cnt < 32u ? cnt : 32u, base = cnt - take;
+		__syncwarp();
+		if(lane == 0) *(volatile uint32_t*)&ws->qcount = base;
+		if((uint32_t)lane < take) movCandidate(f, t, s, dc, c, ws, (int)ws->q[base + lane]);
+	}
+	__syncwarp();
 }
 
 // Returns false for a static micropolygon in a frame without depth of field: the reference
 // renders those with RenderMPG_Static even when other grids move (bucketprocessor.cpp:1087-1090).
-template<bool OPAQUE>
-__device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, uint32_t p, int lane)
+__device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, MovScratch* ws,
+                              uint32_t p, int lane, bool opaquePass)
 {
-	MovingMP m;
+	MovCtx c;
+	MovingMP& m = c.m;
 	m.p = p;
 	const float4 a = f.P4[p];
 	const uint32_t info = infoOf(a);
@@ -940,17 +998,38 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 	m.times = f.keyTimes + (m.g.nkeys_koff >> 8);
 	const bool moving = m.nkeys > 1;
 	if(!moving && !f.useDof) return false;
+	c.moving = moving; c.opaquePass = opaquePass;
+	// ---- stage the key vertices and key bounds in the warp's scratch
+	__syncwarp();
+	{
+		const uint32_t nk = m.nkeys < MOV_KMAX ? m.nkeys : MOV_KMAX;
+		if((uint32_t)lane < 4u*nk)
+		{
+			const uint32_t k = (uint32_t)lane >> 2; const int i = lane & 3;
+			ws->kv[k][i] = f.P4[p + (size_t)k*m.nverts + (uint32_t)(i & 1) + (uint32_t)(i >> 1)*(m.cu + 1)];
+		}
+		if(lane == 0) ws->qcount = 0;
+		__syncwarp();
+		if((uint32_t)lane < nk)
+		{
+			const B2 b = boundOf4(ws->kv[lane][0], ws->kv[lane][1], ws->kv[lane][2], ws->kv[lane][3]);
+			ws->kb[lane][0] = make_float4(b.mnx, b.mny, b.mnz, b.mxx);
+			ws->kb[lane][1] = make_float4(b.mxy, b.mxz, 0.f, 0.f);
+		}
+		__syncwarp();
+	}
 	float4 P[4];
-	P[0] = a; P[1] = f.P4[p+1]; P[2] = f.P4[p+m.cu+1]; P[3] = f.P4[p+m.cu+2];
+	P[0] = ws->kv[0][0]; P[1] = ws->kv[0][1]; P[2] = ws->kv[0][2]; P[3] = ws->kv[0][3];
 	bool opaque = (info & VINFO_OPAQUE) != 0;
 	if(m.g.flags & AQH_GRID_SMOOTH)
 		opaque = opaque && (infoOf(P[1]) & VINFO_OPAQUE) && (infoOf(P[2]) & VINFO_OPAQUE) && (infoOf(P[3]) & VINFO_OPAQUE);
 	const bool opaqueSlot = opaque || (m.g.flags & AQH_GRID_MATTE_ALPHA);
-	if(opaqueSlot != OPAQUE) return true;
+	if(opaqueSlot != opaquePass) return true;
 	m.code = computeVertexOrder(P);
 	// m_Bound: union of the key bounds (AppendKey, micropolygon.cpp:1952-1967)
-	B2 mpBound = boundOf4(P[0], P[1], P[2], P[3]);
-	for(uint32_t k = 1; k < m.nkeys; ++k) { B2 kb = keyBound(f, m, k); encapsulate(mpBound, kb); }
+	B2 mpBound = keyBound(f, m, ws, 0);
+	for(uint32_t k = 1; k < m.nkeys; ++k) { B2 kb = keyBound(f, m, ws, k); encapsulate(mpBound, kb); }
+	c.mpBound = mpBound;
 	// CacheHitTestValues (static :1406-1423, moving :1916-1938)
 	float2 cocMin = make_float2(0.f, 0.f), cocMax = make_float2(0.f, 0.f);
 	if(f.useDof)
@@ -969,6 +1048,7 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 			cocMax = make_float2(maxA(c1.x, c2.x), maxA(c1.y, c2.y));
 		}
 	}
+	c.cocMin = cocMin; c.cocMax = cocMax;
 	const int n = f.n;
 	const float opentime = f.shutterOpen, closetime = f.shutterClose;
 	float timePerSample = 0.f;
@@ -987,10 +1067,10 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 	B2 runBound = mpBound;
 	if(moving)
 	{
-		const B2 kb0 = keyBound(f, m, 0);
+		const B2 kb0 = keyBound(f, m, ws, 0);
 		float cx = kb0.mxx - kb0.mnx, cy = kb0.mxy - kb0.mny;
 		float polyLen2 = (cy == 0.f) ? cx*cx : ((cx == 0.f) ? cy*cy : cx*cx + cy*cy);
-		const float4 pl = f.P4[p + (size_t)(m.nkeys-1)*m.nverts];
+		const float4 pl = movVert(f, m, ws, m.nkeys-1, 0);
 		float mx = P[0].x - pl.x, my = P[0].y - pl.y;
 		float moveDist2 = (my == 0.f) ? mx*mx : ((mx == 0.f) ? my*my : mx*mx + my*my);
 		int polyLengthsMoved = max(1, lfloorF(sqrtf(moveDist2/polyLen2)));
@@ -1000,6 +1080,9 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 		timeAcc = opentime + dt;
 		runBound = kb0;
 	}
+	// rows of tile pixels enumerated per round, so that one round queues at most 32 lanes x 32 pixels
+	const int tileRows = t.ry1 - t.ry0;
+	const int bandRows = (f.tileW >= 32) ? 1 : (32 / f.tileW);
 	for(int bnum = 0; bnum < divisions; ++bnum)
 	{
 		B2 Bnd = mpBound;
@@ -1009,14 +1092,14 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 			const float* times = m.times;
 			while(timeAcc > times[endKey] && endKey < m.nkeys - 1) ++endKey;
 			const int endKey_1 = endKey - 1;
-			const B2 end0 = keyBound(f, m, endKey_1), end1 = keyBound(f, m, endKey);
+			const B2 end0 = keyBound(f, m, ws, endKey_1), end1 = keyBound(f, m, ws, endKey);
 			const float end0Time = times[endKey_1], end1Time = times[endKey];
 			const float mix = (timeAcc - end0Time) / (end1Time - end0Time);
 			B2 mid = end0;
 			mid.mnx += mix * (end1.mnx - end0.mnx); mid.mny += mix * (end1.mny - end0.mny); mid.mnz += mix * (end1.mnz - end0.mnz);
 			mid.mxx += mix * (end1.mxx - end0.mxx); mid.mxy += mix * (end1.mxy - end0.mxy); mid.mxz += mix * (end1.mxz - end0.mxz);
 			encapsulate(runBound, mid);
-			while(startKey < endKey_1) { startKey++; B2 kb = keyBound(f, m, startKey); encapsulate(runBound, kb); }
+			while(startKey < endKey_1) { startKey++; B2 kb = keyBound(f, m, ws, startKey); encapsulate(runBound, kb); }
 			Bnd = runBound;
 			time0 = timeAcc - dt;
 			const float nextAcc = timeAcc + dt;
@@ -1043,27 +1126,51 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 		{
 			float2 c1 = cocAt(f, Bnd.mnz), c2 = cocAt(f, Bnd.mxz);
 			const float maxCocX = maxA(c1.x, c2.x), maxCocY = maxA(c1.y, c2.y);
-			for(int cell = lane; cell < n; cell += 32)
+			// quick reject of the whole division: the union of the lens-cell boxes misses the tile
+			// (dofBounds lie in [-1,1], so every cell box is inside Bnd grown by maxCoc)
+			if(!(Bnd.mxx + maxCocX >= (float)t.rx0) || !(Bnd.mxy + maxCocY >= (float)t.ry0) ||
+			   !(Bnd.mnx - maxCocX < (float)t.rx1) || !(Bnd.mny - maxCocY < (float)t.ry1)) continue;
+			for(int band0 = 0; band0 < tileRows; band0 += bandRows)
 			{
-				const float4 db = f.dofBounds[cell];
-				const float bminx = Bnd.mnx - db.z*maxCocX, bmaxx = Bnd.mxx - db.x*maxCocX;
-				const float bminy = Bnd.mny - db.w*maxCocY, bmaxy = Bnd.mxy - db.y*maxCocY;
-				if(!(bmaxx >= (float)t.rx0) || !(bmaxy >= (float)t.ry0) || !(bminx < (float)t.rx1) || !(bminy < (float)t.ry1)) continue;
-				int eX = (bmaxx >= (float)t.rx1) ? t.rx1 : min(lceilF(bmaxx), t.rx1);
-				int eY = (bmaxy >= (float)t.ry1) ? t.ry1 : min(lceilF(bmaxy), t.ry1);
-				int sX = (bminx < (float)t.rx0) ? t.rx0 : max(floorI(bminx), t.rx0);
-				int sY = (bminy < (float)t.ry0) ? t.ry0 : max(floorI(bminy), t.ry0);
-				if(zminKey > pixZMax(f, t, s, sX, eX, sY, eY)) continue;
-				for(int iY = sY; iY < eY; ++iY)
-					for(int iX = sX; iX < eX; ++iX)
+				const int by0 = t.ry0 + band0, by1 = min(t.ry1, by0 + bandRows);
+				for(int c0 = 0; c0 < n; c0 += 32)
+				{
+					const int cell = c0 + lane;
+					if(cell < n)
 					{
-						const int pixLocal = (iY - t.tileY0)*f.tileW + (iX - t.tileX0);
-						// GetDofOffsetIndex(cell) = shuffledIndices[cell] of the pixel's shuffle pattern
-						const int index = f.shufTab[(size_t)s.shufPat[pixLocal]*n + cell];
-						testCandidateMBDof<OPAQUE>(f, t, s, dc, m, moving, mpBound, cocMin, cocMax,
-						                           sampleIdx(f, s, iX - t.tileX0, iY - t.tileY0, index),
-						                           0.f, zminKey, bminx, bminy, bmaxx, bmaxy, time0, time1);
+						const float4 db = f.dofBounds[cell];
+						const float bminx = Bnd.mnx - db.z*maxCocX, bmaxx = Bnd.mxx - db.x*maxCocX;
+						const float bminy = Bnd.mny - db.w*maxCocY, bmaxy = Bnd.mxy - db.y*maxCocY;
+						if((bmaxx >= (float)t.rx0) && (bmaxy >= (float)t.ry0) && (bminx < (float)t.rx1) && (bminy < (float)t.ry1))
+						{
+							int eX = (bmaxx >= (float)t.rx1) ? t.rx1 : min(lceilF(bmaxx), t.rx1);
+							int eY = (bmaxy >= (float)t.ry1) ? t.ry1 : min(lceilF(bmaxy), t.ry1);
+							int sX = (bminx < (float)t.rx0) ? t.rx0 : max(floorI(bminx), t.rx0);
+							int sY = (bminy < (float)t.ry0) ? t.ry0 : max(floorI(bminy), t.ry0);
+							sY = max(sY, by0); eY = min(eY, by1);
+							for(int iY = sY; iY < eY; ++iY)
+								for(int iX = sX; iX < eX; ++iX)
+								{
+									const int pixLocal = (iY - t.tileY0)*f.tileW + (iX - t.tileX0);
+									// hierarchical z, per pixel: every sample of the pixel would fail "Bound.zmin > occlZ"
+									if(zminKey > s.pixZ[pixLocal]) continue;
+									// GetDofOffsetIndex(cell) = shuffledIndices[cell] of the pixel's shuffle pattern
+									const int index = f.shufTab[(size_t)s.shufPat[pixLocal]*n + cell];
+									const int idx = sampleIdx(f, s, iX - t.tileX0, iY - t.tileY0, index);
+									if(moving)
+									{
+										const float time = s.time[idx];
+										if(time < time0 || time > time1) continue;
+									}
+									const float x = s.posx[idx], y = s.posy[idx];
+									if((x < bminx || x > bmaxx) || (y < bminy || y > bmaxy)) continue;
+									if(zminKey > (uint32_t)(s.keys[idx] >> 32)) continue;
+									movPush(f, ws, idx);
+								}
+						}
 					}
+					movDrain(f, t, s, dc, c, ws, lane, 32u);
+				}
 			}
 		}
 		else
@@ -1075,20 +1182,31 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 			int sX = (bminx < (float)t.rx0) ? t.rx0 : max(floorI(bminx), t.rx0);
 			int sY = (bminy < (float)t.ry0) ? t.ry0 : max(floorI(bminy), t.ry0);
 			if(sX >= eX || sY >= eY) continue;
-			if(zminKey > pixZMax(f, t, s, sX, eX, sY, eY)) continue;
 			// the reference's do-while visits at least one index per pixel
 			const int cnt = max(1, indexT1 - indexT0);
 			const int Wp = eX - sX, npix = Wp*(eY - sY), total = npix*cnt;
-			for(int k = lane; k < total; k += 32)
+			for(int k0 = 0; k0 < total; k0 += 1024)
 			{
-				const int pi = k / cnt, j = k - pi*cnt;
-				const int iY = sY + pi / Wp, iX = sX + pi % Wp;
-				testCandidateMBDof<OPAQUE>(f, t, s, dc, m, moving, mpBound, cocMin, cocMax,
-				                           sampleIdx(f, s, iX - t.tileX0, iY - t.tileY0, indexT0 + j),
-				                           0.f, zminKey, bminx, bminy, bmaxx, bmaxy, time0, time1);
+				const int kEnd = min(total, k0 + 1024);
+				for(int k = k0 + lane; k < kEnd; k += 32)
+				{
+					const int pi = k / cnt, j = k - pi*cnt;
+					const int iY = sY + pi / Wp, iX = sX + pi % Wp;
+					const int pixLocal = (iY - t.tileY0)*f.tileW + (iX - t.tileX0);
+					if(zminKey > s.pixZ[pixLocal]) continue;
+					const int idx = sampleIdx(f, s, iX - t.tileX0, iY - t.tileY0, indexT0 + j);
+					const float time = s.time ? s.time[idx] : f.shutterOpen;
+					if(moving && (time < time0 || time > time1)) continue;
+					const float x = s.posx[idx], y = s.posy[idx];
+					if((x < bminx || x > bmaxx) || (y < bminy || y > bmaxy)) continue;
+					if(zminKey > (uint32_t)(s.keys[idx] >> 32)) continue;
+					movPush(f, ws, idx);
+				}
+				movDrain(f, t, s, dc, c, ws, lane, 32u);
 			}
 		}
 	}
+	movDrain(f, t, s, dc, c, ws, lane, 1u);
 	return true;
 }
 
@@ -1101,7 +1219,7 @@ __device__ void hitUV(const DevFrame& f, const GridRec& g, uint32_t p, float2 po
 	m.times = f.keyTimes + (g.nkeys_koff >> 8);
 	float px[4], py[4], pz[4];
 	B2 dummy;
-	samplePoints(f, m, m.nkeys > 1, dummy, make_float2(0.f, 0.f), make_float2(0.f, 0.f), pos, dofOff, time, px, py, pz, false);
+	samplePoints(f, m, nullptr, m.nkeys > 1, dummy, make_float2(0.f, 0.f), make_float2(0.f, 0.f), pos, dofOff, time, px, py, pz, false);
 	HitCache c;
 	cachePointInPolyTest(c, px, py, pz, 0xE4 /* any valid code: only the uv part is used */);
 	uv = invBilinear(c.Ax, c.Ay, c.Ex, c.Ey, c.Fx, c.Fy, c.Gx, c.Gy, c.linear, pos.x, pos.y);
@@ -1261,7 +1379,7 @@ __device__ __forceinline__ uint32_t tapMask(const DevFrame& f, float posx, float
 // pipeline -- grab RECS_PER_WARP micropolygons of the tile's bin, set them up (one lane each,
 // records in the warp's shared-memory slots), then sample them one after the other with all 32
 // lanes -- so there is no CTA-wide barrier inside the micropolygon loop.
-template<bool MBDOF, int THREADS>
+template<bool MBDOF, int THREADS, bool PARTIALS>
 __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevFrame f)
 {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -1270,7 +1388,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 	__shared__ uint32_t s_next;
 	__shared__ uint32_t s_tileZ, s_dirty;
 	constexpr int NWARPS = THREADS/32;
-	HideSmem s = carveSmem(f, smemRaw, NWARPS*RECS_PER_WARP);
+	HideSmem s = carveSmem(f, smemRaw, NWARPS*RECS_PER_WARP, MBDOF ? NWARPS*sizeof(MovScratch) : 0);
+	MovScratch* ws = MBDOF ? reinterpret_cast<MovScratch*>(reinterpret_cast<unsigned char*>(s.mov) + (size_t)(threadIdx.x >> 5)*sizeof(MovScratch)) : nullptr;
 	s.tileZ = &s_tileZ; s.dirty = &s_dirty;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int n = f.n, xs = f.xs, ys = f.ys;
@@ -1392,8 +1511,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 					for(int j = 0; j < cnt; ++j)
 					{
 						const uint32_t p = (uint32_t)f.binEntries[binBeg + base + j];
-						const bool handled = (pass == 0) ? renderMBOrDof<true>(f, t, s, dc, p, lane)
-						                                 : renderMBOrDof<false>(f, t, s, dc, p, lane);
+						const bool handled = renderMBOrDof(f, t, s, dc, ws, p, lane, pass == 0);
 						if(!handled)
 						{
 							// static micropolygon in a frame without depth of field
@@ -1422,7 +1540,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 		if(tid == 0 && s_deepCount) atomicAdd(&f.counters[2], (unsigned long long)min(s_deepCount, dc.cap));
 		// ---- Combine_samples + hand the resolved samples to the filter stage.
 		const int tw = t.rx1 - t.rx0, th = t.ry1 - t.ry0;
-		if(f.filterMode == AQH_FILTER_REFERENCE_ORDER)
+		if(!PARTIALS)
 		{
 			// Planes are [k][y][i][x] (row width planeW): consecutive threads take consecutive x of one sample index.
 			const int nOut = tw*th*n;
@@ -1882,19 +2000,19 @@ cudaError_t launchBinFill(const DevFrame& f, cudaStream_t st)
 	return cudaGetLastError();
 }
 
-template<bool MBDOF, int THREADS>
+template<bool MBDOF, int THREADS, bool PARTIALS>
 static cudaError_t configHide(const DevFrame& f, int smCount, LaunchCfg& cfg)
 {
 	cfg.hideThreads = THREADS;
 	cfg.batchMPs = (THREADS/32)*RECS_PER_WARP;
-	cfg.hideSmemBytes = hideSmemBytes(f, cfg.batchMPs);
+	cfg.hideSmemBytes = hideSmemBytes(f, cfg.batchMPs, MBDOF ? (THREADS/32)*sizeof(MovScratch) : 0);
 	if(cfg.hideSmemBytes > 227*1024) return cudaErrorInvalidValue;
-	cudaError_t e = cudaFuncSetAttribute(k_hide<MBDOF, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.hideSmemBytes);
+	cudaError_t e = cudaFuncSetAttribute(k_hide<MBDOF, THREADS, PARTIALS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.hideSmemBytes);
 	if(e != cudaSuccess) return e;
-	e = cudaFuncSetAttribute(k_hide<MBDOF, THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+	e = cudaFuncSetAttribute(k_hide<MBDOF, THREADS, PARTIALS>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
 	if(e != cudaSuccess) return e;
 	int perSm = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_hide<MBDOF, THREADS>, THREADS, cfg.hideSmemBytes);
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_hide<MBDOF, THREADS, PARTIALS>, THREADS, cfg.hideSmemBytes);
 	if(e != cudaSuccess) return e;
 	if(perSm < 1) perSm = 1;
 	cfg.hideCtas = smCount * perSm;
@@ -1905,15 +2023,26 @@ cudaError_t hideKernelConfig(const DevFrame& f, int smCount, LaunchCfg& cfg)
 {
 	cfg.smCount = smCount;
 	const bool mbdof = f.useDof || f.anyMotion;
-	return mbdof ? configHide<true, 256>(f, smCount, cfg) : configHide<false, 512>(f, smCount, cfg);
+	const bool partials = f.filterMode != AQH_FILTER_REFERENCE_ORDER;
+	if(mbdof) return partials ? configHide<true, 256, true>(f, smCount, cfg) : configHide<true, 256, false>(f, smCount, cfg);
+	return partials ? configHide<false, 512, true>(f, smCount, cfg) : configHide<false, 512, false>(f, smCount, cfg);
 }
 
 cudaError_t launchHide(const DevFrame& f, const LaunchCfg& cfg, cudaStream_t st)
 {
 	if(f.nActiveTiles == 0) return cudaSuccess;
 	const bool mbdof = f.useDof || f.anyMotion;
-	if(mbdof) k_hide<true, 256><<<cfg.hideCtas, 256, cfg.hideSmemBytes, st>>>(f);
-	else k_hide<false, 512><<<cfg.hideCtas, 512, cfg.hideSmemBytes, st>>>(f);
+	const bool partials = f.filterMode != AQH_FILTER_REFERENCE_ORDER;
+	if(mbdof)
+	{
+		if(partials) k_hide<true, 256, true><<<cfg.hideCtas, 256, cfg.hideSmemBytes, st>>>(f);
+		else k_hide<true, 256, false><<<cfg.hideCtas, 256, cfg.hideSmemBytes, st>>>(f);
+	}
+	else
+	{
+		if(partials) k_hide<false, 512, true><<<cfg.hideCtas, 512, cfg.hideSmemBytes, st>>>(f);
+		else k_hide<false, 512, false><<<cfg.hideCtas, 512, cfg.hideSmemBytes, st>>>(f);
+	}
 	return cudaGetLastError();
 }
 
