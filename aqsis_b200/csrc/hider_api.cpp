@@ -415,8 +415,12 @@ int renderFrame(AqhHider* h, bool download)
 	CU(h->dTileFlags.reserve(std::max<size_t>(nActive, 1)*4), "cudaMalloc(tile flags)");
 	CU(h->dMisc.reserve(256), "cudaMalloc(counters)");
 	CU(h->dRowOwned.reserve(p.yres), "cudaMalloc(row ownership)");
-	const int planeW = (L.sw + 3) & ~3;              // row pitch: a multiple of 16 bytes for the TMA tensor map
-	const size_t planeStride = size_t(planeW)*L.sh*(p.xsamples*p.ysamples);
+	// resolved-sample planes [k][y][chunk][x][planeSC] (hider_device.h)
+	const int nSamp = p.xsamples*p.ysamples;
+	const int planeSC = std::min((nSamp + 3) & ~3, 64);
+	const int planeChunks = (nSamp + planeSC - 1)/planeSC;
+	const int planeW = ((L.sw + 31) & ~31) + 16;     // the filter stages spans of up to 32+14 pixels starting at multiples of 32
+	const size_t planeStride = size_t(planeW)*L.sh*planeChunks*planeSC;
 	const int ntaps = (2*L.shiftX+1)*(2*L.shiftY+1);
 	if(p.filter_mode == AQH_FILTER_REFERENCE_ORDER)
 	{
@@ -549,7 +553,7 @@ int renderFrame(AqhHider* h, bool download)
 	f.tileCursor = h->dMisc.as<uint32_t>();
 	f.errorFlags = h->dMisc.as<uint32_t>() + 1;
 	f.counters = reinterpret_cast<unsigned long long*>(h->dMisc.as<unsigned char>() + 16);
-	f.planes = h->dPlanes.as<float>(); f.maskPlane = reinterpret_cast<uint32_t*>(h->dPlanes.as<float>() + 7*planeStride); f.planeStride = (int64_t)planeStride; f.planeW = planeW;
+	f.planes = h->dPlanes.as<float>(); f.maskPlane = reinterpret_cast<uint32_t*>(h->dPlanes.as<float>() + 7*planeStride); f.planeStride = (int64_t)planeStride; f.planeW = planeW; f.planeSC = planeSC; f.planeChunks = planeChunks;
 	f.filterMode = p.filter_mode; f.partials = h->dPartials.as<float>(); f.ntaps = ntaps;
 	f.channels = h->dChannels.as<float>();
 	f.rowOwned = (std::max(1, p.world_size) > 1) ? h->dRowOwned.as<uint8_t>() : nullptr;

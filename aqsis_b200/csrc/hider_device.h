@@ -82,12 +82,14 @@ struct DevFrame
 	int sortRun;                   // bins are sorted ascending in runs of this many entries
 	uint32_t* tileCursor;          // persistent-CTA work counter
 	uint32_t* tileFlags;           // per active tile: bit0 = has non-opaque MPs
-	// resolved samples: planes [k][y][s][x] over the sample region, rows padded to planeW floats
-	// (a multiple of 4 with slack, so that the filter can stage aligned 16-byte pieces past the edge)
+	// resolved samples: planes [k][y][chunk][x][planeSC] over the sample region: the samples of a pixel are
+	// split in planeChunks chunks of planeSC (<= 64, a multiple of 4) slots, pixel rows padded to planeW pixels
+	// with slack, so that one (row, chunk) of a span of pixels is ONE contiguous, 16-byte aligned piece for the
+	// filter's bulk copies.  Slots past n hold mask 0.
 	float* planes;                 // 7 planes: R G B Or Og Ob Z
 	uint32_t* maskPlane;           // bits 0-14 x-tap inclusion, 15-29 y-tap inclusion, 31 valid
-	int64_t planeStride;           // sh*n*planeW
-	int planeW;
+	int64_t planeStride;           // sh*planeChunks*planeW*planeSC
+	int planeW, planeSC, planeChunks;
 	// tile-partials filter mode: per (tap, value, y, x) partial sums over a pixel's samples;
 	// values: 0 gTot, 1 hit count, 2..8 R G B Or Og Ob Z
 	int filterMode;                // AQH_FILTER_*

@@ -15,7 +15,6 @@
 //   k_filter     Filter_samples + ExposeBucket + quantise
 //                (bucketprocessor.cpp:584-707, 766-806; ddmanager.cpp:1022-1118)
 #include "hider_device.h"
-#include <cuda.h>      // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include <cfloat>
 
@@ -1542,16 +1541,19 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 		const int tw = t.rx1 - t.rx0, th = t.ry1 - t.ry0;
 		if(!PARTIALS)
 		{
-			// Planes are [k][y][i][x] (row width planeW): consecutive threads take consecutive x of one sample index.
-			const int nOut = tw*th*n;
+			// Planes are [k][y][chunk][x][slot]: consecutive threads take consecutive sample slots of one pixel.
+			const int SC = f.planeSC, nCh = f.planeChunks, nSlots = SC*nCh;
+			const int nOut = tw*th*nSlots;
 			for(int o = tid; o < nOut; o += THREADS)
 			{
-				const int lx = o % tw, r2 = o / tw, ly = r2 % th, i = r2 / th;
+				const int i = o % nSlots, pix = o / nSlots, lx = pix % tw, ly = pix / tw;
+				const int c = i / SC, j = i - c*SC;
+				const int X = t.rx0 + lx, Y = t.ry0 + ly;
+				const size_t at = (((size_t)(Y - f.sy0)*nCh + c)*f.planeW + (size_t)(X - f.sx0))*SC + j;
+				if(i >= n) { f.maskPlane[at] = 0u; continue; }       // padding slot: never included
 				const int idx = sampleIdx(f, s, lx, ly, i);
 				float out[7]; bool valid;
 				resolveSample(f, t, s, dc, idx, out, valid);
-				const int X = t.rx0 + lx, Y = t.ry0 + ly;
-				const size_t at = ((size_t)(Y - f.sy0)*n + (size_t)i)*f.planeW + (size_t)(X - f.sx0);
 				f.maskPlane[at] = tapMask(f, s.posx[idx], s.posy[idx], X, Y, valid);
 				if(valid)
 				{
@@ -1750,10 +1752,11 @@ __global__ void __launch_bounds__(256) k_filter(DevFrame f, DevDisplays disp)
 		{
 			const float* g = s_filt + ((fy + ymax)*(2*xmax+1) + fx + xmax)*n;
 			const uint32_t need = (1u << (fx + xmax)) | (1u << (15 + fy + ymax));
-			size_t at = (size_t)(y + fy - f.sy0)*n*f.planeW + (size_t)(x + fx - f.sx0);
-			const size_t step = (size_t)f.planeW;
-			for(int sIdx = 0; sIdx < n; ++sIdx, at += step)
+			const int SC = f.planeSC, nCh = f.planeChunks;
+			for(int sIdx = 0; sIdx < n; ++sIdx)
 			{
+				const int c = sIdx / SC;
+				const size_t at = (((size_t)(y + fy - f.sy0)*nCh + c)*f.planeW + (size_t)(x + fx - f.sx0))*SC + (sIdx - c*SC);
 				const uint32_t m = f.maskPlane[at];
 				if((m & need) == need)
 				{
@@ -1772,21 +1775,24 @@ __global__ void __launch_bounds__(256) k_filter(DevFrame f, DevDisplays disp)
 	finishPixel(f, disp, x, y, acc, gTot, SampleCount);
 }
 
-// Reference-order filter, row staged by TMA and channel split.
+// Reference-order filter, pixel spans staged by bulk copies and channel split.
 // A CTA owns W consecutive output pixels of ONE image row and has 8*W threads: thread (px, ch)
-// accumulates channel ch of pixel px -- ch 0..6 = R G B Or Og Ob Z, ch 7 = the weight total and the
-// hit count -- over the taps in exactly the reference's fy, fx, sy, sx order
-// (bucketprocessor.cpp:597-629), so every per-channel float sum is the reference's own sequence of
-// roundings.  For each fy the n x CW box of resolved samples of source row y+fy is brought into
-// shared memory by ONE cp.async.bulk.tensor (TMA) per plane -- eight per row, issued by one thread,
-// completion on an mbarrier -- and reused for the 2*xmax+1 values of fx, so a sample travels
-// L2 -> SM (2*ymax+1)*CW/W times instead of (2*xmax+1)(2*ymax+1) times; CTAs of neighbouring rows
-// run back to back, so the re-reads hit L2 and HBM sees every sample once.  The tensor map covers
-// all eight planes as one 2-D array [8*sh*n rows][sw columns, row pitch planeW]; columns past the
-// sample region are zero-filled by the TMA unit (mask 0 = "no sample").
+// accumulates channel ch of pixel px -- ch 0..6 = R G B Or Og Ob Z, ch 7 = the weight total -- over the
+// taps in exactly the reference's fy, fx, sy, sx order (bucketprocessor.cpp:597-629), so every
+// per-channel float sum is the reference's own sequence of roundings.
+// The resolved samples lie in HBM as [plane][row][chunk][pixel][slot] (hider_device.h), so the samples of a
+// span of pixels of one source row (and one chunk of <= 64 slots) are ONE contiguous piece per plane: a
+// stage is eight cp.async.bulk copies (TMA engine, completion on an mbarrier) issued by one thread.
+//   n <= 64 : one stage per fy holds the W + 2*xmax pixels all fx taps need (each sample travels
+//             L2 -> SM (2*ymax+1)*(W+2*xmax)/W times);
+//   n  > 64 : the tile would not fit, so a stage is one (fy, fx, chunk) of exactly W pixels.
+// In shared memory the planes are skewed by 16 bytes each, and the eight channel threads of a pixel sit in
+// adjacent lanes: a quarter warp's 16-byte loads of four consecutive samples fall into eight different bank
+// groups (values) or on one address (mask), i.e. no bank conflicts.  The weight total is "channel 7" with
+// a value of 1.0 (1.0f*w == w exactly) so that all eight lanes run the same instructions.
 // Weights come from constant memory (uniform index).  Excluded samples are skipped by predication,
 // never multiplied by zero.
-__constant__ float c_filt[49*256];
+__constant__ float c_filt[49*256 + 64];
 
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count)
@@ -1809,87 +1815,102 @@ __device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity)
 		"DONE_%=:\n"
 		"}\n" :: "r"(smemAddr(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tmaLoad2D(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
+__device__ __forceinline__ void bulkLoad(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
 {
-	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-	             :: "r"(smemAddr(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smemAddr(bar)) : "memory");
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(smemAddr(dst)), "l"(src), "r"(bytes), "r"(smemAddr(bar)) : "memory");
 }
 
-template<int W>
-__global__ void __launch_bounds__(8*W) k_filter_rows(DevFrame f, DevDisplays disp, const __grid_constant__ CUtensorMap tmap)
+#define FILTER_W 32
+__host__ __device__ __forceinline__ int filterSpan(const DevFrame& f)      // staged pixels per stage
 {
+	return (f.planeChunks == 1) ? FILTER_W + ((2*f.shiftX + 3) & ~3) : FILTER_W;
+}
+__host__ __device__ __forceinline__ int filterPlaneFloats(const DevFrame& f)
+{
+	return ((filterSpan(f)*f.planeSC + 31) & ~31) + 4;     // + 4: the 16-byte skew between planes
+}
+
+__global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(DevFrame f, DevDisplays disp)
+{
+	constexpr int W = FILTER_W;
 	extern __shared__ __align__(128) unsigned char fsm[];
 	__shared__ __align__(8) uint64_t s_bar;
 	const int n = f.n, xmax = f.shiftX, ymax = f.shiftY;
-	const int CW = W + ((2*xmax + 3) & ~3);            // staged columns, a multiple of 4
-	const int planeSz = (n*CW + 31) & ~31;               // every plane starts 128-byte aligned
-	float* tile = reinterpret_cast<float*>(fsm);         // [8 planes][n][CW]
-	const int tid = threadIdx.x, px = tid % W, ch = tid / W;
+	const int SC = f.planeSC, nCh = f.planeChunks;
+	const bool halo = (nCh == 1);
+	const int span = filterSpan(f);
+	const int planeS = filterPlaneFloats(f);
+	float* tile = reinterpret_cast<float*>(fsm);         // [8 planes][span][SC], planes skewed
+	const int tid = threadIdx.x, ch = tid & 7, px = tid >> 3;
 	const int x0 = f.cropX0 + blockIdx.x*W, y = f.cropY0 + blockIdx.y;
 	if(f.rowOwned && !f.rowOwned[y]) return;             // uniform over the CTA
 	const int x = x0 + px;
 	const bool live = x < f.cropX1;
-	const int col0 = x0 - f.cropX0;                      // first staged column of the sample region (x0 - xmax - sx0)
-	const float* myPlane = tile + (size_t)(ch < 7 ? ch : 7)*planeSz;
-	const uint32_t* maskT = reinterpret_cast<const uint32_t*>(tile + (size_t)7*planeSz);
+	// the value plane of this thread; channel 7 reads four 1.0f with a zero stride
+	float* ones = tile + (size_t)8*planeS;
+	const float* vbase = (ch < 7) ? tile + (size_t)ch*planeS : ones;
+	const int vmul = (ch < 7) ? 1 : 0;
+	const uint32_t* mbase = reinterpret_cast<const uint32_t*>(tile + (size_t)7*planeS);
 	if(tid == 0)
 	{
 		mbarInit(&s_bar, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
+	if(tid < 4) ones[tid] = 1.0f;
 	float acc = 0.f;
 	int count = 0;
-	int tap = 0;
+	uint32_t phase = 0;
+	const uint32_t bytes = (uint32_t)(span*SC*4);
+	const int nStageFx = halo ? 1 : (2*xmax + 1);
 	for(int fy = 0; fy <= 2*ymax; ++fy)
 	{
-		__syncthreads();                                 // barrier initialised / everyone is done with the previous row
-		if(tid == 0)
-		{
-			// order the CTA's generic-proxy reads of the tile before the async-proxy overwrite
-			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-			mbarExpectTx(&s_bar, (uint32_t)(8*n*CW*4));
-			const int row = (y + fy - ymax - f.sy0)*n;
-			for(int k = 0; k < 8; ++k)
-				tmaLoad2D(tile + (size_t)k*planeSz, &tmap, col0, k*f.sh*n + row, &s_bar);
-		}
-		mbarWait(&s_bar, (uint32_t)(fy & 1));
-		if(!live) { tap += 2*xmax + 1; continue; }
-		for(int fx = 0; fx <= 2*xmax; ++fx, ++tap)
-		{
-			const uint32_t need = (1u << fx) | (1u << (15 + fy));
-			const uint32_t needV = need | 0x80000000u;
-			const float* w = c_filt + tap*n;
-			const int o = px + fx;
-			if(ch < 7)
+		const size_t srow = (size_t)(y + fy - ymax - f.sy0);
+		for(int sfx = 0; sfx < nStageFx; ++sfx)
+			for(int c = 0; c < nCh; ++c)
 			{
-#pragma unroll 8
-				for(int sI = 0; sI < n; ++sI)
+				__syncthreads();                         // barrier initialised / everyone is done with the previous stage
+				if(tid == 0)
 				{
-					const uint32_t m = ~maskT[sI*CW + o];
-					const float v = myPlane[sI*CW + o] * w[sI];
-					if(!(m & needV)) acc += v;
+					// order the CTA's generic-proxy reads of the tile before the async-proxy overwrite
+					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+					mbarExpectTx(&s_bar, 8u*bytes);
+					// first staged pixel column of the sample region: x0 - xmax - sx0 (+ fx when every fx is staged on its own)
+					const size_t col = (size_t)(x0 - f.cropX0) + (size_t)sfx;
+					const float* src = f.planes + ((srow*nCh + c)*f.planeW + col)*SC;
+					for(int k = 0; k < 8; ++k)
+						bulkLoad(tile + (size_t)k*planeS, src + (size_t)k*f.planeStride, bytes, &s_bar);
 				}
-			}
-			else
-			{
-#pragma unroll 8
-				for(int sI = 0; sI < n; ++sI)
+				mbarWait(&s_bar, phase);
+				phase ^= 1u;
+				if(!live) continue;
+				const int fx0 = halo ? 0 : sfx, fx1 = halo ? 2*xmax : sfx;
+				for(int fx = fx0; fx <= fx1; ++fx)
 				{
-					const uint32_t m = ~maskT[sI*CW + o];
-					if(!(m & need))
+					const int tap = fy*(2*xmax + 1) + fx;
+					const uint32_t need = (1u << fx) | (1u << (15 + fy)) | ((ch < 7) ? 0x80000000u : 0u);
+					const float* w = c_filt + tap*n + c*SC;
+					const int o = (halo ? px + fx : px)*SC;
+					const float4* vp = reinterpret_cast<const float4*>(vbase + o*vmul);
+					const uint4* mp = reinterpret_cast<const uint4*>(mbase + o);
+#pragma unroll 4
+					for(int s4 = 0; s4 < SC/4; ++s4)
 					{
-						acc += w[sI];
-						count += (int)((~m) >> 31);
+						const uint4 m = mp[s4];
+						const float4 v = vp[s4*vmul];
+						if((m.x & need) == need) { acc += v.x * w[4*s4+0]; ++count; }
+						if((m.y & need) == need) { acc += v.y * w[4*s4+1]; ++count; }
+						if((m.z & need) == need) { acc += v.z * w[4*s4+2]; ++count; }
+						if((m.w & need) == need) { acc += v.w * w[4*s4+3]; ++count; }
 					}
 				}
 			}
-		}
 	}
 	// gather the eight sums of a pixel in one thread
 	__syncthreads();
 	float* sums = reinterpret_cast<float*>(fsm);         // [9][W]
 	sums[ch*W + px] = acc;
-	if(ch == 7) sums[8*W + px] = __int_as_float(count);
+	if(ch == 0) sums[8*W + px] = __int_as_float(count);  // channel 0 counted the valid samples of the footprint
 	__syncthreads();
 	if(ch == 0 && live)
 	{
@@ -1900,39 +1921,11 @@ __global__ void __launch_bounds__(8*W) k_filter_rows(DevFrame f, DevDisplays dis
 	}
 }
 
-static size_t filterRowsSmem(const DevFrame& f, int W)
+static size_t filterSpansSmem(const DevFrame& f)
 {
-	const int CW = W + ((2*f.shiftX + 3) & ~3);
-	const size_t tile = (size_t)8*(((size_t)f.n*CW + 31) & ~(size_t)31)*4;
-	const size_t sums = (size_t)9*W*4;               // the per-pixel gather at the end reuses the tile
+	const size_t tile = ((size_t)8*filterPlaneFloats(f) + 4)*4;
+	const size_t sums = (size_t)9*FILTER_W*4;
 	return tile > sums ? tile : sums;
-}
-
-// The tensor map of the resolved-sample planes: 2-D [8*sh*n][sw] floats, row pitch planeW, box n x CW.
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static cudaError_t encodeSampleMap(const DevFrame& f, int W, CUtensorMap* map)
-{
-	static EncodeTiledFn fn = nullptr;
-	if(!fn)
-	{
-		void* p = nullptr;
-		cudaDriverEntryPointQueryResult q;
-		cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
-		if(e != cudaSuccess) return e;
-		if(q != cudaDriverEntryPointSuccess || !p) return cudaErrorNotSupported;
-		fn = reinterpret_cast<EncodeTiledFn>(p);
-	}
-	const int CW = W + ((2*f.shiftX + 3) & ~3);
-	const cuuint64_t dims[2] = {(cuuint64_t)f.sw, (cuuint64_t)8*f.sh*f.n};
-	const cuuint64_t strides[1] = {(cuuint64_t)f.planeW*4};
-	const cuuint32_t box[2] = {(cuuint32_t)CW, (cuuint32_t)f.n};
-	const cuuint32_t estr[2] = {1, 1};
-	CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)f.planes, dims, strides, box, estr,
-	                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-	                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-	return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 // Tile-partials filter: sum the nine per-(pixel,tap) partial sums over the taps in fy, fx order.
@@ -2057,39 +2050,18 @@ cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, const float
 		return cudaGetLastError();
 	}
 	const int ntapw = (2*f.shiftX+1)*(2*f.shiftY+1)*f.n;
-	// row-staged kernel: tap bits fit the mask word (shift <= 7 always), weights in 64 KB of constant memory
+	// span-staged kernel: tap bits fit the mask word (shift <= 7 always), weights in 64 KB of constant memory
 	if(ntapw <= 49*256)
 	{
-		const size_t budget = 110*1024;      // two CTAs per SM
-		int W = 32;
-		while(W > 8 && filterRowsSmem(f, W) > budget) W >>= 1;
-		const size_t smem = filterRowsSmem(f, W);
-		if(smem <= 220*1024)
+		const size_t smem = filterSpansSmem(f);
+		if(smem <= 113*1024)
 		{
 			cudaError_t e = cudaMemcpyToSymbolAsync(c_filt, hostFilterTab, (size_t)ntapw*4, 0, cudaMemcpyHostToDevice, st);
 			if(e != cudaSuccess) return e;
-			CUtensorMap tmap;
-			e = encodeSampleMap(f, W, &tmap);
+			e = cudaFuncSetAttribute(k_filter_spans, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			if(e != cudaSuccess) return e;
-			dim3 grid((w + W - 1)/W, h);
-			if(W == 32)
-			{
-				e = cudaFuncSetAttribute(k_filter_rows<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-				if(e != cudaSuccess) return e;
-				k_filter_rows<32><<<grid, 256, smem, st>>>(f, disp, tmap);
-			}
-			else if(W == 16)
-			{
-				e = cudaFuncSetAttribute(k_filter_rows<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-				if(e != cudaSuccess) return e;
-				k_filter_rows<16><<<grid, 128, smem, st>>>(f, disp, tmap);
-			}
-			else
-			{
-				e = cudaFuncSetAttribute(k_filter_rows<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-				if(e != cudaSuccess) return e;
-				k_filter_rows<8><<<grid, 64, smem, st>>>(f, disp, tmap);
-			}
+			dim3 grid((w + FILTER_W - 1)/FILTER_W, h);
+			k_filter_spans<<<grid, 8*FILTER_W, smem, st>>>(f, disp);
 			return cudaGetLastError();
 		}
 	}
