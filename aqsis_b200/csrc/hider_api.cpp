@@ -553,7 +553,8 @@ int renderFrame(AqhHider* h, bool download)
 	f.tileCursor = h->dMisc.as<uint32_t>();
 	f.errorFlags = h->dMisc.as<uint32_t>() + 1;
 	f.counters = reinterpret_cast<unsigned long long*>(h->dMisc.as<unsigned char>() + 16);
-	f.planes = h->dPlanes.as<float>(); f.maskPlane = reinterpret_cast<uint32_t*>(h->dPlanes.as<float>() + 7*planeStride); f.planeStride = (int64_t)planeStride; f.planeW = planeW; f.planeSC = planeSC; f.planeChunks = planeChunks;
+	f.planes = h->dPlanes.as<float>(); f.maskPlane = reinterpret_cast<unsigned char*>(h->dPlanes.as<float>() + 7*planeStride);
+	{ const int mbits = 2*L.shiftX + 2*L.shiftY + 3; f.maskBytes = mbits <= 8 ? 1 : (mbits <= 16 ? 2 : 4); } f.planeStride = (int64_t)planeStride; f.planeW = planeW; f.planeSC = planeSC; f.planeChunks = planeChunks;
 	f.filterMode = p.filter_mode; f.partials = h->dPartials.as<float>(); f.ntaps = ntaps;
 	f.channels = h->dChannels.as<float>();
 	f.rowOwned = (std::max(1, p.world_size) > 1) ? h->dRowOwned.as<uint8_t>() : nullptr;

@@ -87,7 +87,9 @@ struct DevFrame
 	// with slack, so that one (row, chunk) of a span of pixels is ONE contiguous, 16-byte aligned piece for the
 	// filter's bulk copies.  Slots past n hold mask 0.
 	float* planes;                 // 7 planes: R G B Or Og Ob Z
-	uint32_t* maskPlane;           // bits 0-14 x-tap inclusion, 15-29 y-tap inclusion, 31 valid
+	unsigned char* maskPlane;      // per slot one compact word of maskBytes (1, 2 or 4) bytes: bits [0, 2*shiftX] x-tap inclusion,
+	                               // the next 2*shiftY+1 bits y-tap inclusion, then one bit "holds a valid hit"
+	int maskBytes;
 	int64_t planeStride;           // sh*planeChunks*planeW*planeSC
 	int planeW, planeSC, planeChunks;
 	// tile-partials filter mode: per (tap, value, y, x) partial sums over a pixel's samples;

@@ -1373,6 +1373,25 @@ __device__ __forceinline__ uint32_t tapMask(const DevFrame& f, float posx, float
 	return mask;
 }
 
+// The compact per-slot word of the sample planes (hider_device.h): x-tap bits, y-tap bits, valid bit.
+__device__ __forceinline__ uint32_t packMask(const DevFrame& f, uint32_t m)
+{
+	const int nx = 2*f.shiftX + 1, ny = 2*f.shiftY + 1;
+	return (m & ((1u << nx) - 1u)) | (((m >> 15) & ((1u << ny) - 1u)) << nx) | ((m >> 31) << (nx + ny));
+}
+__device__ __forceinline__ void storeMask(const DevFrame& f, size_t at, uint32_t compact)
+{
+	if(f.maskBytes == 1) f.maskPlane[at] = (unsigned char)compact;
+	else if(f.maskBytes == 2) reinterpret_cast<uint16_t*>(f.maskPlane)[at] = (uint16_t)compact;
+	else reinterpret_cast<uint32_t*>(f.maskPlane)[at] = compact;
+}
+__device__ __forceinline__ uint32_t loadMask(const DevFrame& f, size_t at)
+{
+	if(f.maskBytes == 1) return f.maskPlane[at];
+	if(f.maskBytes == 2) return reinterpret_cast<const uint16_t*>(f.maskPlane)[at];
+	return reinterpret_cast<const uint32_t*>(f.maskPlane)[at];
+}
+
 // ------------------------------------------------------------------------------------
 // k_hide: persistent CTAs pull tiles from a counter.  Inside a tile every warp runs its own
 // pipeline -- grab RECS_PER_WARP micropolygons of the tile's bin, set them up (one lane each,
@@ -1550,11 +1569,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 				const int c = i / SC, j = i - c*SC;
 				const int X = t.rx0 + lx, Y = t.ry0 + ly;
 				const size_t at = (((size_t)(Y - f.sy0)*nCh + c)*f.planeW + (size_t)(X - f.sx0))*SC + j;
-				if(i >= n) { f.maskPlane[at] = 0u; continue; }       // padding slot: never included
+				if(i >= n) { storeMask(f, at, 0u); continue; }       // padding slot: never included
 				const int idx = sampleIdx(f, s, lx, ly, i);
 				float out[7]; bool valid;
 				resolveSample(f, t, s, dc, idx, out, valid);
-				f.maskPlane[at] = tapMask(f, s.posx[idx], s.posy[idx], X, Y, valid);
+				storeMask(f, at, packMask(f, tapMask(f, s.posx[idx], s.posy[idx], X, Y, valid)));
 				if(valid)
 				{
 #pragma unroll
@@ -1751,18 +1770,19 @@ __global__ void __launch_bounds__(256) k_filter(DevFrame f, DevDisplays disp)
 		for(int fx = -xmax; fx <= xmax; ++fx)
 		{
 			const float* g = s_filt + ((fy + ymax)*(2*xmax+1) + fx + xmax)*n;
-			const uint32_t need = (1u << (fx + xmax)) | (1u << (15 + fy + ymax));
+			const uint32_t need = (1u << (fx + xmax)) | (1u << (2*xmax + 1 + fy + ymax));
+			const uint32_t validBit = 1u << (2*xmax + 2*ymax + 2);
 			const int SC = f.planeSC, nCh = f.planeChunks;
 			for(int sIdx = 0; sIdx < n; ++sIdx)
 			{
 				const int c = sIdx / SC;
 				const size_t at = (((size_t)(y + fy - f.sy0)*nCh + c)*f.planeW + (size_t)(x + fx - f.sx0))*SC + (sIdx - c*SC);
-				const uint32_t m = f.maskPlane[at];
+				const uint32_t m = loadMask(f, at);
 				if((m & need) == need)
 				{
 					const float w = g[sIdx];
 					gTot += w;
-					if(m & 0x80000000u)
+					if(m & validBit)
 					{
 #pragma unroll
 						for(int k = 0; k < 7; ++k)
@@ -1822,6 +1842,7 @@ __device__ __forceinline__ void bulkLoad(void* dst, const void* src, uint32_t by
 }
 
 #define FILTER_W 32
+#define FILTER_ONES 128       /* floats of 1.0 read by channel 7 ("the weight total is the sum of 1.0*w") */
 __host__ __device__ __forceinline__ int filterSpan(const DevFrame& f)      // staged pixels per stage
 {
 	return (f.planeChunks == 1) ? FILTER_W + ((2*f.shiftX + 3) & ~3) : FILTER_W;
@@ -1831,6 +1852,9 @@ __host__ __device__ __forceinline__ int filterPlaneFloats(const DevFrame& f)
 	return ((filterSpan(f)*f.planeSC + 31) & ~31) + 4;     // + 4: the 16-byte skew between planes
 }
 
+// MB = bytes per mask word (1, 2 or 4).  Four consecutive slots are tested per step:
+// one 32-bit shared load for byte masks, one 64-bit load for 16-bit masks, one 128-bit load for 32-bit masks.
+template<int MB>
 __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(DevFrame f, DevDisplays disp)
 {
 	constexpr int W = FILTER_W;
@@ -1841,28 +1865,26 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(DevFrame f, DevDisp
 	const bool halo = (nCh == 1);
 	const int span = filterSpan(f);
 	const int planeS = filterPlaneFloats(f);
-	float* tile = reinterpret_cast<float*>(fsm);         // [8 planes][span][SC], planes skewed
+	float* tile = reinterpret_cast<float*>(fsm);         // [7 value planes][span][SC], planes skewed; ones; mask words
 	const int tid = threadIdx.x, ch = tid & 7, px = tid >> 3;
 	const int x0 = f.cropX0 + blockIdx.x*W, y = f.cropY0 + blockIdx.y;
 	if(f.rowOwned && !f.rowOwned[y]) return;             // uniform over the CTA
-	const int x = x0 + px;
-	const bool live = x < f.cropX1;
-	// the value plane of this thread; channel 7 reads four 1.0f with a zero stride
-	float* ones = tile + (size_t)8*planeS;
-	const float* vbase = (ch < 7) ? tile + (size_t)ch*planeS : ones;
-	const int vmul = (ch < 7) ? 1 : 0;
-	const uint32_t* mbase = reinterpret_cast<const uint32_t*>(tile + (size_t)7*planeS);
+	const bool live = (x0 + px) < f.cropX1;
+	// channel 7 reads 1.0f from a region laid out so that its banks continue the skew of the seven planes
+	float* ones = tile + (size_t)7*planeS;
+	const unsigned char* mbase = reinterpret_cast<const unsigned char*>(ones + FILTER_ONES);
 	if(tid == 0)
 	{
 		mbarInit(&s_bar, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
-	if(tid < 4) ones[tid] = 1.0f;
+	if(tid < FILTER_ONES) ones[tid] = 1.0f;
 	float acc = 0.f;
 	int count = 0;
 	uint32_t phase = 0;
-	const uint32_t bytes = (uint32_t)(span*SC*4);
+	const uint32_t vbytes = (uint32_t)(span*SC*4), mbytes = (uint32_t)(span*SC*MB);
 	const int nStageFx = halo ? 1 : (2*xmax + 1);
+	const uint32_t validBit = (ch < 7) ? (1u << (2*xmax + 2*ymax + 2)) : 0u;
 	for(int fy = 0; fy <= 2*ymax; ++fy)
 	{
 		const size_t srow = (size_t)(y + fy - ymax - f.sy0);
@@ -1874,12 +1896,13 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(DevFrame f, DevDisp
 				{
 					// order the CTA's generic-proxy reads of the tile before the async-proxy overwrite
 					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-					mbarExpectTx(&s_bar, 8u*bytes);
+					mbarExpectTx(&s_bar, 7u*vbytes + mbytes);
 					// first staged pixel column of the sample region: x0 - xmax - sx0 (+ fx when every fx is staged on its own)
 					const size_t col = (size_t)(x0 - f.cropX0) + (size_t)sfx;
-					const float* src = f.planes + ((srow*nCh + c)*f.planeW + col)*SC;
-					for(int k = 0; k < 8; ++k)
-						bulkLoad(tile + (size_t)k*planeS, src + (size_t)k*f.planeStride, bytes, &s_bar);
+					const size_t at = ((srow*nCh + c)*f.planeW + col)*SC;
+					for(int k = 0; k < 7; ++k)
+						bulkLoad(tile + (size_t)k*planeS, f.planes + (size_t)k*f.planeStride + at, vbytes, &s_bar);
+					bulkLoad(const_cast<unsigned char*>(mbase), f.maskPlane + at*MB, mbytes, &s_bar);
 				}
 				mbarWait(&s_bar, phase);
 				phase ^= 1u;
@@ -1888,44 +1911,77 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(DevFrame f, DevDisp
 				for(int fx = fx0; fx <= fx1; ++fx)
 				{
 					const int tap = fy*(2*xmax + 1) + fx;
-					const uint32_t need = (1u << fx) | (1u << (15 + fy)) | ((ch < 7) ? 0x80000000u : 0u);
+					const uint32_t need = (1u << fx) | (1u << (2*xmax + 1 + fy)) | validBit;
 					const float* w = c_filt + tap*n + c*SC;
 					const int o = (halo ? px + fx : px)*SC;
-					const float4* vp = reinterpret_cast<const float4*>(vbase + o*vmul);
-					const uint4* mp = reinterpret_cast<const uint4*>(mbase + o);
-#pragma unroll 4
-					for(int s4 = 0; s4 < SC/4; ++s4)
+					const float4* vp = reinterpret_cast<const float4*>((ch < 7) ? tile + (size_t)ch*planeS + o : ones + (o & 31));
+					if(MB == 1)
 					{
-						const uint4 m = mp[s4];
-						const float4 v = vp[s4*vmul];
-						if((m.x & need) == need) { acc += v.x * w[4*s4+0]; ++count; }
-						if((m.y & need) == need) { acc += v.y * w[4*s4+1]; ++count; }
-						if((m.z & need) == need) { acc += v.z * w[4*s4+2]; ++count; }
-						if((m.w & need) == need) { acc += v.w * w[4*s4+3]; ++count; }
+						const uint32_t* mp = reinterpret_cast<const uint32_t*>(mbase + o);
+						const uint32_t n0 = need, n1 = need << 8, n2 = need << 16, n3 = need << 24;
+#pragma unroll 4
+						for(int s4 = 0; s4 < SC/4; ++s4)
+						{
+							const uint32_t m = mp[s4];
+							const float4 v = vp[s4];
+							if((m & n0) == n0) { acc += v.x * w[4*s4+0]; ++count; }
+							if((m & n1) == n1) { acc += v.y * w[4*s4+1]; ++count; }
+							if((m & n2) == n2) { acc += v.z * w[4*s4+2]; ++count; }
+							if((m & n3) == n3) { acc += v.w * w[4*s4+3]; ++count; }
+						}
+					}
+					else if(MB == 2)
+					{
+						const uint2* mp = reinterpret_cast<const uint2*>(mbase + (size_t)o*2);
+						const uint32_t n0 = need, n1 = need << 16;
+#pragma unroll 4
+						for(int s4 = 0; s4 < SC/4; ++s4)
+						{
+							const uint2 m = mp[s4];
+							const float4 v = vp[s4];
+							if((m.x & n0) == n0) { acc += v.x * w[4*s4+0]; ++count; }
+							if((m.x & n1) == n1) { acc += v.y * w[4*s4+1]; ++count; }
+							if((m.y & n0) == n0) { acc += v.z * w[4*s4+2]; ++count; }
+							if((m.y & n1) == n1) { acc += v.w * w[4*s4+3]; ++count; }
+						}
+					}
+					else
+					{
+						const uint4* mp = reinterpret_cast<const uint4*>(mbase + (size_t)o*4);
+#pragma unroll 4
+						for(int s4 = 0; s4 < SC/4; ++s4)
+						{
+							const uint4 m = mp[s4];
+							const float4 v = vp[s4];
+							if((m.x & need) == need) { acc += v.x * w[4*s4+0]; ++count; }
+							if((m.y & need) == need) { acc += v.y * w[4*s4+1]; ++count; }
+							if((m.z & need) == need) { acc += v.z * w[4*s4+2]; ++count; }
+							if((m.w & need) == need) { acc += v.w * w[4*s4+3]; ++count; }
+						}
 					}
 				}
 			}
 	}
-	// gather the eight sums of a pixel in one thread
+	// gather the eight sums of a pixel; the first warp finishes the W pixels (one lane each)
 	__syncthreads();
 	float* sums = reinterpret_cast<float*>(fsm);         // [9][W]
 	sums[ch*W + px] = acc;
 	if(ch == 0) sums[8*W + px] = __int_as_float(count);  // channel 0 counted the valid samples of the footprint
 	__syncthreads();
-	if(ch == 0 && live)
+	if(tid < W && (x0 + tid) < f.cropX1)
 	{
 		float a[7];
 #pragma unroll
-		for(int k = 0; k < 7; ++k) a[k] = sums[k*W + px];
-		finishPixel(f, disp, x, y, a, sums[7*W + px], __float_as_int(sums[8*W + px]));
+		for(int k = 0; k < 7; ++k) a[k] = sums[k*W + tid];
+		finishPixel(f, disp, x0 + tid, y, a, sums[7*W + tid], __float_as_int(sums[8*W + tid]));
 	}
 }
 
 static size_t filterSpansSmem(const DevFrame& f)
 {
-	const size_t tile = ((size_t)8*filterPlaneFloats(f) + 4)*4;
+	const size_t tile = ((size_t)7*filterPlaneFloats(f) + FILTER_ONES)*4 + (size_t)filterSpan(f)*f.planeSC*f.maskBytes;
 	const size_t sums = (size_t)9*FILTER_W*4;
-	return tile > sums ? tile : sums;
+	return ((tile > sums ? tile : sums) + 15) & ~(size_t)15;
 }
 
 // Tile-partials filter: sum the nine per-(pixel,tap) partial sums over the taps in fy, fx order.
@@ -2058,10 +2114,25 @@ cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, const float
 		{
 			cudaError_t e = cudaMemcpyToSymbolAsync(c_filt, hostFilterTab, (size_t)ntapw*4, 0, cudaMemcpyHostToDevice, st);
 			if(e != cudaSuccess) return e;
-			e = cudaFuncSetAttribute(k_filter_spans, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-			if(e != cudaSuccess) return e;
 			dim3 grid((w + FILTER_W - 1)/FILTER_W, h);
-			k_filter_spans<<<grid, 8*FILTER_W, smem, st>>>(f, disp);
+			if(f.maskBytes == 1)
+			{
+				e = cudaFuncSetAttribute(k_filter_spans<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+				if(e != cudaSuccess) return e;
+				k_filter_spans<1><<<grid, 8*FILTER_W, smem, st>>>(f, disp);
+			}
+			else if(f.maskBytes == 2)
+			{
+				e = cudaFuncSetAttribute(k_filter_spans<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+				if(e != cudaSuccess) return e;
+				k_filter_spans<2><<<grid, 8*FILTER_W, smem, st>>>(f, disp);
+			}
+			else
+			{
+				e = cudaFuncSetAttribute(k_filter_spans<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+				if(e != cudaSuccess) return e;
+				k_filter_spans<4><<<grid, 8*FILTER_W, smem, st>>>(f, disp);
+			}
 			return cudaGetLastError();
 		}
 	}
