@@ -440,11 +440,10 @@ __device__ __forceinline__ float bilerpZ(const float* z, float2 uv)
 
 // CqMotionSpec::GetMotionObjectInterpolated on the split line (motion.h:176-228,
 // micropolygon.h:182-188) + the side test of micropolygon.cpp:1630-1654.
-__device__ bool triangleSplitReject(const DevFrame& f, const GridRec& g, float2 pos, float2 dofOff, float D, float time)
+__device__ __noinline__ bool triangleSplitRejectImpl(const float4* sl, const float* times, uint32_t nkeys,
+                                                     float posx, float posy, float dofx, float dofy, float D, float time,
+                                                     int useDof, float dofMult, float dofInvFocal, float dofScaleX, float dofScaleY)
 {
-	const uint32_t nkeys = g.nkeys_koff & 0xffu, koff = g.nkeys_koff >> 8;
-	const float4* sl = f.splitLines + koff;
-	const float* times = f.keyTimes + koff;
 	float4 s;
 	if(nkeys == 1) s = sl[0];
 	else if(time >= times[nkeys-1]) s = sl[nkeys-1];
@@ -463,14 +462,22 @@ __device__ bool triangleSplitReject(const DevFrame& f, const GridRec& g, float2 
 		}
 	}
 	float Ax = s.x, Ay = s.y, Bx = s.z, By = s.w;
-	float hx = pos.x, hy = pos.y;
-	if(f.useDof)
+	float hx = posx, hy = posy;
+	if(useDof)
 	{
-		float2 cm = cocAt(f, D);
-		hx += cm.x*dofOff.x; hy += cm.y*dofOff.y;
+		// GetCircleOfConfusion(D), renderer.h:401-406
+		float c = dofMult * fabsf(1.0f / D - dofInvFocal);
+		hx += (dofScaleX * c)*dofx; hy += (dofScaleY * c)*dofy;
 	}
 	float v = (Ay - By)*hx + (Bx - Ax)*hy + (Ax*By - Bx*Ay);
 	return v <= 0.f;
+}
+// Rare (polygon grids only): kept out of line so that the sampling loops stay small in the instruction cache.
+__device__ __forceinline__ bool triangleSplitReject(const DevFrame& f, const GridRec& g, float2 pos, float2 dofOff, float D, float time)
+{
+	const uint32_t nkeys = g.nkeys_koff & 0xffu, koff = g.nkeys_koff >> 8;
+	return triangleSplitRejectImpl(f.splitLines + koff, f.keyTimes + koff, nkeys, pos.x, pos.y, dofOff.x, dofOff.y, D, time,
+	                               f.useDof, f.dofMult, f.dofInvFocal, f.dofScaleX, f.dofScaleY);
 }
 
 // CqMicroPolygon::InterpolateOutputs + CacheOutputInterpCoeffs*, micropolygon.cpp:1443-1529
@@ -642,14 +649,20 @@ __device__ __forceinline__ void storeDeep(const DevFrame& f, const DeepCtx& dc, 
 }
 
 // sample level of detail = lods[i] of the pixel's lod pattern (imagepixel.cpp:356)
+__device__ __noinline__ float sampleLodImpl(const uint8_t* lodPlane, const float* val1d, int idx, int stride, int xs, int ys, int n,
+                                            int px0, int py0, int sw)
+{
+	const int gy = idx / stride, gx = idx - gy*stride;
+	const int plx = gx / xs, ply = gy / ys;
+	const int i = (gy - ply*ys)*xs + (gx - plx*xs);
+	const int pat = lodPlane[(size_t)(py0 + ply)*sw + (px0 + plx)];
+	return val1d[(size_t)pat*n + i];
+}
+// Rare (level-of-detail ranges only): out of line.
 __device__ __forceinline__ float sampleLod(const DevFrame& f, const TileCtx& t, const HideSmem& s, int idx)
 {
-	const int gy = idx / s.stride, gx = idx - gy*s.stride;
-	const int plx = gx / f.xs, ply = gy / f.ys;
-	const int i = (gy - ply*f.ys)*f.xs + (gx - plx*f.xs);
-	const int gxp = t.tileX0 + plx - f.sx0, gyp = t.tileY0 + ply - f.sy0;
-	const int pat = f.patPlanes[(size_t)4*f.sw*f.sh + (size_t)gyp*f.sw + gxp];
-	return f.val1d[(size_t)pat*f.n + i];
+	return sampleLodImpl(f.patPlanes + (size_t)4*f.sw*f.sh, f.val1d, idx, s.stride, f.xs, f.ys, f.n,
+	                     t.tileX0 - f.sx0, t.tileY0 - f.sy0, f.sw);
 }
 
 // ---- hierarchical z.  pixZ[pixel] >= the occlusion depth key of every sample of the pixel (the keys
@@ -812,11 +825,19 @@ struct MovScratch           // per warp, 16-byte aligned
 	uint16_t q[MOV_QCAP];           // candidate sample indices
 };
 
+// keys past MOV_KMAX (and the resolve stage) read HBM: out of line, the staged case is the hot one
+__device__ __noinline__ float4 movVertGlobal(const float4* Pk, uint32_t cu, int i)
+{
+	return Pk[(uint32_t)(i & 1) + (uint32_t)(i >> 1)*(cu + 1)];
+}
+__device__ __noinline__ B2 keyBoundGlobal(const float4* Pk, uint32_t cu)
+{
+	return boundOf4(Pk[0], Pk[1], Pk[cu+1], Pk[cu+2]);
+}
 __device__ __forceinline__ float4 movVert(const DevFrame& f, const MovingMP& m, const MovScratch* ws, uint32_t k, int i)
 {
 	if(ws && k < MOV_KMAX) return ws->kv[k][i];
-	const float4* Pk = f.P4 + m.p + (size_t)k*m.nverts;
-	return Pk[(uint32_t)(i & 1) + (uint32_t)(i >> 1)*(m.cu + 1)];
+	return movVertGlobal(f.P4 + m.p + (size_t)k*m.nverts, m.cu, i);
 }
 __device__ __forceinline__ B2 keyBound(const DevFrame& f, const MovingMP& m, const MovScratch* ws, uint32_t k)
 {
@@ -826,8 +847,7 @@ __device__ __forceinline__ B2 keyBound(const DevFrame& f, const MovingMP& m, con
 		B2 r; r.mnx = a.x; r.mny = a.y; r.mnz = a.z; r.mxx = a.w; r.mxy = b.x; r.mxz = b.y;
 		return r;
 	}
-	const float4* Pk = f.P4 + m.p + (size_t)k*m.nverts;
-	return boundOf4(Pk[0], Pk[1], Pk[m.cu+1], Pk[m.cu+2]);
+	return keyBoundGlobal(f.P4 + m.p + (size_t)k*m.nverts, m.cu);
 }
 
 // Vertices of the micropolygon for one sample: CqMicroPolygon(Motion)::Sample,
@@ -1082,111 +1102,135 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 	// rows of tile pixels enumerated per round, so that one round queues at most 32 lanes x 32 pixels
 	const int tileRows = t.ry1 - t.ry0;
 	const int bandRows = (f.tileW >= 32) ? 1 : (32 / f.tileW);
-	for(int bnum = 0; bnum < divisions; ++bnum)
+	const int cellRounds = (n + 31) >> 5;
+	// The reference's loops (time sub-bounds, then lens cells or sample-index windows) are flattened into
+	// ROUNDS -- one round queues at most 1024 candidates -- driven by ONE loop with ONE drain call, so that
+	// the heavy per-candidate code exists once in the instruction stream.
+	int bnum = -1, round = 0, nRounds = 0;
+	// state of the current division
+	B2 Bnd = mpBound;
+	float time0 = 0.f, time1 = 0.f;
+	int indexT0 = 0, indexT1 = 0;
+	uint32_t zminKey = 0;
+	float maxCocX = 0.f, maxCocY = 0.f;
+	int sX = 0, eX = 0, sY = 0, eY = 0, cnt = 1, total = 0;        // MB-only: pixel window and index window
+	for(;;)
 	{
-		B2 Bnd = mpBound;
-		float time0 = 0.f, time1 = 0.f;
-		if(moving)
+		bool last = false;
+		if(round >= nRounds)
 		{
-			const float* times = m.times;
-			while(timeAcc > times[endKey] && endKey < m.nkeys - 1) ++endKey;
-			const int endKey_1 = endKey - 1;
-			const B2 end0 = keyBound(f, m, ws, endKey_1), end1 = keyBound(f, m, ws, endKey);
-			const float end0Time = times[endKey_1], end1Time = times[endKey];
-			const float mix = (timeAcc - end0Time) / (end1Time - end0Time);
-			B2 mid = end0;
-			mid.mnx += mix * (end1.mnx - end0.mnx); mid.mny += mix * (end1.mny - end0.mny); mid.mnz += mix * (end1.mnz - end0.mnz);
-			mid.mxx += mix * (end1.mxx - end0.mxx); mid.mxy += mix * (end1.mxy - end0.mxy); mid.mxz += mix * (end1.mxz - end0.mxz);
-			encapsulate(runBound, mid);
-			while(startKey < endKey_1) { startKey++; B2 kb = keyBound(f, m, ws, startKey); encapsulate(runBound, kb); }
-			Bnd = runBound;
-			time0 = timeAcc - dt;
-			const float nextAcc = timeAcc + dt;
-			time1 = (bnum != divisions - 1) ? (nextAcc - dt) : closetime;
-			runBound = mid;
-			timeAcc = nextAcc;
-		}
-		int indexT0 = 0, indexT1 = 0;
-		if(moving)
-		{
-			if(time1 < opentime || time0 > closetime) continue;
-			if(fastShutter) { indexT0 = 0; indexT1 = n; }
-			else
+			// advance to the next division that has anything to enumerate
+			bool found = false;
+			while(++bnum < divisions)
 			{
-				indexT0 = max(0, lfloorF((time0 - opentime) * timePerSample));
-				indexT1 = lceilF((time1 - opentime) * timePerSample);
-			}
-			if(indexT1 > n) indexT1 = n;
-			if(indexT0 >= n) continue;
-		}
-		if(Bnd.mnz > f.clipFar || Bnd.mxz < f.clipNear) continue;
-		const uint32_t zminKey = depthKey(Bnd.mnz);
-		if(f.useDof)
-		{
-			float2 c1 = cocAt(f, Bnd.mnz), c2 = cocAt(f, Bnd.mxz);
-			const float maxCocX = maxA(c1.x, c2.x), maxCocY = maxA(c1.y, c2.y);
-			// quick reject of the whole division: the union of the lens-cell boxes misses the tile
-			// (dofBounds lie in [-1,1], so every cell box is inside Bnd grown by maxCoc)
-			if(!(Bnd.mxx + maxCocX >= (float)t.rx0) || !(Bnd.mxy + maxCocY >= (float)t.ry0) ||
-			   !(Bnd.mnx - maxCocX < (float)t.rx1) || !(Bnd.mny - maxCocY < (float)t.ry1)) continue;
-			for(int band0 = 0; band0 < tileRows; band0 += bandRows)
-			{
-				const int by0 = t.ry0 + band0, by1 = min(t.ry1, by0 + bandRows);
-				for(int c0 = 0; c0 < n; c0 += 32)
+				Bnd = mpBound;
+				if(moving)
 				{
-					const int cell = c0 + lane;
-					if(cell < n)
+					const float* times = m.times;
+					while(timeAcc > times[endKey] && endKey < m.nkeys - 1) ++endKey;
+					const int endKey_1 = endKey - 1;
+					const B2 end0 = keyBound(f, m, ws, endKey_1), end1 = keyBound(f, m, ws, endKey);
+					const float end0Time = times[endKey_1], end1Time = times[endKey];
+					const float mix = (timeAcc - end0Time) / (end1Time - end0Time);
+					B2 mid = end0;
+					mid.mnx += mix * (end1.mnx - end0.mnx); mid.mny += mix * (end1.mny - end0.mny); mid.mnz += mix * (end1.mnz - end0.mnz);
+					mid.mxx += mix * (end1.mxx - end0.mxx); mid.mxy += mix * (end1.mxy - end0.mxy); mid.mxz += mix * (end1.mxz - end0.mxz);
+					encapsulate(runBound, mid);
+					while(startKey < endKey_1) { startKey++; B2 kb = keyBound(f, m, ws, startKey); encapsulate(runBound, kb); }
+					Bnd = runBound;
+					time0 = timeAcc - dt;
+					const float nextAcc = timeAcc + dt;
+					time1 = (bnum != divisions - 1) ? (nextAcc - dt) : closetime;
+					runBound = mid;
+					timeAcc = nextAcc;
+					if(time1 < opentime || time0 > closetime) continue;
+					if(fastShutter) { indexT0 = 0; indexT1 = n; }
+					else
 					{
-						const float4 db = f.dofBounds[cell];
-						const float bminx = Bnd.mnx - db.z*maxCocX, bmaxx = Bnd.mxx - db.x*maxCocX;
-						const float bminy = Bnd.mny - db.w*maxCocY, bmaxy = Bnd.mxy - db.y*maxCocY;
-						if((bmaxx >= (float)t.rx0) && (bmaxy >= (float)t.ry0) && (bminx < (float)t.rx1) && (bminy < (float)t.ry1))
-						{
-							int eX = (bmaxx >= (float)t.rx1) ? t.rx1 : min(lceilF(bmaxx), t.rx1);
-							int eY = (bmaxy >= (float)t.ry1) ? t.ry1 : min(lceilF(bmaxy), t.ry1);
-							int sX = (bminx < (float)t.rx0) ? t.rx0 : max(floorI(bminx), t.rx0);
-							int sY = (bminy < (float)t.ry0) ? t.ry0 : max(floorI(bminy), t.ry0);
-							sY = max(sY, by0); eY = min(eY, by1);
-							for(int iY = sY; iY < eY; ++iY)
-								for(int iX = sX; iX < eX; ++iX)
-								{
-									const int pixLocal = (iY - t.tileY0)*f.tileW + (iX - t.tileX0);
-									// hierarchical z, per pixel: every sample of the pixel would fail "Bound.zmin > occlZ"
-									if(zminKey > s.pixZ[pixLocal]) continue;
-									// GetDofOffsetIndex(cell) = shuffledIndices[cell] of the pixel's shuffle pattern
-									const int index = f.shufTab[(size_t)s.shufPat[pixLocal]*n + cell];
-									const int idx = sampleIdx(f, s, iX - t.tileX0, iY - t.tileY0, index);
-									if(moving)
-									{
-										const float time = s.time[idx];
-										if(time < time0 || time > time1) continue;
-									}
-									const float x = s.posx[idx], y = s.posy[idx];
-									if((x < bminx || x > bmaxx) || (y < bminy || y > bmaxy)) continue;
-									if(zminKey > (uint32_t)(s.keys[idx] >> 32)) continue;
-									movPush(f, ws, idx);
-								}
-						}
+						indexT0 = max(0, lfloorF((time0 - opentime) * timePerSample));
+						indexT1 = lceilF((time1 - opentime) * timePerSample);
 					}
-					movDrain(f, t, s, dc, c, ws, lane, 32u);
+					if(indexT1 > n) indexT1 = n;
+					if(indexT0 >= n) continue;
+				}
+				if(Bnd.mnz > f.clipFar || Bnd.mxz < f.clipNear) continue;
+				zminKey = depthKey(Bnd.mnz);
+				if(f.useDof)
+				{
+					float2 c1 = cocAt(f, Bnd.mnz), c2 = cocAt(f, Bnd.mxz);
+					maxCocX = maxA(c1.x, c2.x); maxCocY = maxA(c1.y, c2.y);
+					// quick reject of the whole division: the union of the lens-cell boxes misses the tile
+					// (dofBounds lie in [-1,1], so every cell box is inside Bnd grown by maxCoc)
+					if(!(Bnd.mxx + maxCocX >= (float)t.rx0) || !(Bnd.mxy + maxCocY >= (float)t.ry0) ||
+					   !(Bnd.mnx - maxCocX < (float)t.rx1) || !(Bnd.mny - maxCocY < (float)t.ry1)) continue;
+					nRounds = ((tileRows + bandRows - 1)/bandRows)*cellRounds;
+				}
+				else
+				{
+					const float bminx = Bnd.mnx, bmaxx = Bnd.mxx, bminy = Bnd.mny, bmaxy = Bnd.mxy;
+					if(!(bmaxx >= (float)t.rx0) || !(bmaxy >= (float)t.ry0) || !(bminx < (float)t.rx1) || !(bminy < (float)t.ry1)) continue;
+					eX = (bmaxx >= (float)t.rx1) ? t.rx1 : min(lceilF(bmaxx), t.rx1);
+					eY = (bmaxy >= (float)t.ry1) ? t.ry1 : min(lceilF(bmaxy), t.ry1);
+					sX = (bminx < (float)t.rx0) ? t.rx0 : max(floorI(bminx), t.rx0);
+					sY = (bminy < (float)t.ry0) ? t.ry0 : max(floorI(bminy), t.ry0);
+					if(sX >= eX || sY >= eY) continue;
+					// the reference's do-while visits at least one index per pixel
+					cnt = max(1, indexT1 - indexT0);
+					total = (eX - sX)*(eY - sY)*cnt;
+					nRounds = (total + 1023) >> 10;
+				}
+				round = 0;
+				found = true;
+				break;
+			}
+			if(!found) last = true;
+		}
+		if(!last)
+		{
+			if(f.useDof)
+			{
+				const int band0 = (round / cellRounds)*bandRows, c0 = (round % cellRounds) << 5;
+				const int by0 = t.ry0 + band0, by1 = min(t.ry1, by0 + bandRows);
+				const int cell = c0 + lane;
+				if(cell < n)
+				{
+					const float4 db = f.dofBounds[cell];
+					const float bminx = Bnd.mnx - db.z*maxCocX, bmaxx = Bnd.mxx - db.x*maxCocX;
+					const float bminy = Bnd.mny - db.w*maxCocY, bmaxy = Bnd.mxy - db.y*maxCocY;
+					if((bmaxx >= (float)t.rx0) && (bmaxy >= (float)t.ry0) && (bminx < (float)t.rx1) && (bminy < (float)t.ry1))
+					{
+						const int ceX = (bmaxx >= (float)t.rx1) ? t.rx1 : min(lceilF(bmaxx), t.rx1);
+						int ceY = (bmaxy >= (float)t.ry1) ? t.ry1 : min(lceilF(bmaxy), t.ry1);
+						const int csX = (bminx < (float)t.rx0) ? t.rx0 : max(floorI(bminx), t.rx0);
+						int csY = (bminy < (float)t.ry0) ? t.ry0 : max(floorI(bminy), t.ry0);
+						csY = max(csY, by0); ceY = min(ceY, by1);
+						for(int iY = csY; iY < ceY; ++iY)
+							for(int iX = csX; iX < ceX; ++iX)
+							{
+								const int pixLocal = (iY - t.tileY0)*f.tileW + (iX - t.tileX0);
+								// hierarchical z, per pixel: every sample of the pixel would fail "Bound.zmin > occlZ"
+								if(zminKey > s.pixZ[pixLocal]) continue;
+								// GetDofOffsetIndex(cell) = shuffledIndices[cell] of the pixel's shuffle pattern
+								const int index = f.shufTab[(size_t)s.shufPat[pixLocal]*n + cell];
+								const int idx = sampleIdx(f, s, iX - t.tileX0, iY - t.tileY0, index);
+								if(moving)
+								{
+									const float time = s.time[idx];
+									if(time < time0 || time > time1) continue;
+								}
+								const float x = s.posx[idx], y = s.posy[idx];
+								if((x < bminx || x > bmaxx) || (y < bminy || y > bmaxy)) continue;
+								if(zminKey > (uint32_t)(s.keys[idx] >> 32)) continue;
+								movPush(f, ws, idx);
+							}
+					}
 				}
 			}
-		}
-		else
-		{
-			const float bminx = Bnd.mnx, bmaxx = Bnd.mxx, bminy = Bnd.mny, bmaxy = Bnd.mxy;
-			if(!(bmaxx >= (float)t.rx0) || !(bmaxy >= (float)t.ry0) || !(bminx < (float)t.rx1) || !(bminy < (float)t.ry1)) continue;
-			int eX = (bmaxx >= (float)t.rx1) ? t.rx1 : min(lceilF(bmaxx), t.rx1);
-			int eY = (bmaxy >= (float)t.ry1) ? t.ry1 : min(lceilF(bmaxy), t.ry1);
-			int sX = (bminx < (float)t.rx0) ? t.rx0 : max(floorI(bminx), t.rx0);
-			int sY = (bminy < (float)t.ry0) ? t.ry0 : max(floorI(bminy), t.ry0);
-			if(sX >= eX || sY >= eY) continue;
-			// the reference's do-while visits at least one index per pixel
-			const int cnt = max(1, indexT1 - indexT0);
-			const int Wp = eX - sX, npix = Wp*(eY - sY), total = npix*cnt;
-			for(int k0 = 0; k0 < total; k0 += 1024)
+			else
 			{
-				const int kEnd = min(total, k0 + 1024);
+				const float bminx = Bnd.mnx, bmaxx = Bnd.mxx, bminy = Bnd.mny, bmaxy = Bnd.mxy;
+				const int Wp = eX - sX;
+				const int k0 = round << 10, kEnd = min(total, k0 + 1024);
 				for(int k = k0 + lane; k < kEnd; k += 32)
 				{
 					const int pi = k / cnt, j = k - pi*cnt;
@@ -1201,11 +1245,12 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 					if(zminKey > (uint32_t)(s.keys[idx] >> 32)) continue;
 					movPush(f, ws, idx);
 				}
-				movDrain(f, t, s, dc, c, ws, lane, 32u);
 			}
+			++round;
 		}
+		movDrain(f, t, s, dc, c, ws, lane, last ? 1u : 32u);
+		if(last) break;
 	}
-	movDrain(f, t, s, dc, c, ws, lane, 1u);
 	return true;
 }
 
@@ -1486,8 +1531,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 		const uint32_t binBeg = f.binOffset[slot], binCnt = f.binOffset[slot+1] - binBeg;
 		const uint32_t tflags = f.tileFlags[slot];
 		// ---- Render_MPGs: opaque pass, then (if the tile saw non-opaque micropolygons) deep pass
+#pragma unroll 1
 		for(int pass = 0; pass < 2; ++pass)
 		{
+			// keep ONE copy of the pass body in the instruction stream (the compiler would otherwise peel the loop)
+			asm volatile("" : "+r"(pass));
 			if(pass == 1)
 			{
 				if(!(f.anyTransparent && (tflags & 1u))) break;
@@ -1526,6 +1574,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 				}
 				if(MBDOF)
 				{
+#pragma unroll 1
 					for(int j = 0; j < cnt; ++j)
 					{
 						const uint32_t p = (uint32_t)f.binEntries[binBeg + base + j];
