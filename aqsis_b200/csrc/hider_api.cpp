@@ -349,8 +349,17 @@ int appendGridTables(AqhHider* h, int cu, int cv, int nkeys, uint32_t flags, con
 }
 
 // Everything on the device for the frame.  download: copy the image(s) back to pinned host memory.
+// AQH_TRACE=1: host wall-clock checkpoints of one frame on stderr
+struct FrameTrace
+{
+	bool on; double t0, last;
+	FrameTrace() : on(std::getenv("AQH_TRACE") != nullptr), t0(nowMs()), last(t0) {}
+	void mark(const char* what) { if(!on) return; const double t = nowMs(); std::fprintf(stderr, "[aqh] %-22s +%8.3f ms  (%8.3f)\n", what, t - last, t - t0); last = t; }
+};
+
 int renderFrame(AqhHider* h, bool download)
 {
+	FrameTrace tr;
 	if(!h->inFrame) return h->fail(AQH_ERR_STATE, "no frame in progress");
 	const AqhFrameParams& p = h->params;
 	const ReplayLayout& L = h->layout;
@@ -360,6 +369,7 @@ int renderFrame(AqhHider* h, bool download)
 	if(h->nPos >= (int64_t)0xfffffff0u) return h->fail(AQH_ERR_BAD_PARAMS, "more than 2^32 grid positions in one frame");
 	if(nGrids > (int64_t)VINFO_GRID_MASK) return h->fail(AQH_ERR_BAD_PARAMS, "more than 2^28 grids in one frame");
 
+	tr.mark("entry");
 	const double tUp0 = nowMs();
 	S.h2d_bytes = 0;
 	int rc = uploadTables(h);
@@ -396,8 +406,10 @@ int renderFrame(AqhHider* h, bool download)
 			chunk[c] = (uint32_t)g;
 		}
 	}
+	tr.mark("grid records");
 	const bool mbdof = anyMotion || p.use_dof;
 	buildTiling(h, mbdof);
+	tr.mark("tiling");
 	const int nActive = (int)h->activeTiles.size();
 
 	// ---- device allocations
@@ -446,6 +458,7 @@ int renderFrame(AqhHider* h, bool download)
 		h->dispType[d] = o.type; h->dispEntry[d] = o.entrySize;
 	}
 
+	tr.mark("allocations");
 	// ---- grids into HBM
 	const float* dP = nullptr; const float* dCi = nullptr; const float* dOi = nullptr; const uint8_t* dCulled = nullptr;
 	const bool zeroCopy = h->segments.size() == 1 && h->segments[0].memorySpace == 1;
@@ -518,6 +531,7 @@ int renderFrame(AqhHider* h, bool download)
 	S.h2d_bytes += (int64_t)(recs.size()*sizeof(GridRec) + chunk.size()*4 + h->gkeyTimes.size()*4 + h->tileSlot.size()*4 + size_t(nActive)*4 + p.yres);
 	CU(cudaStreamSynchronize(st), "cudaStreamSynchronize(upload)");
 	S.upload_ms = nowMs() - tUp0;
+	tr.mark("upload done");
 
 	// ---- frame descriptor
 	DevFrame f{};
@@ -576,7 +590,9 @@ int renderFrame(AqhHider* h, bool download)
 	CU(cudaMemcpyAsync(&totalEntries, f.binOffset + nActive, 4, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(bin total)");
 	CU(cudaMemcpyAsync(&maxBin, f.counters + 3, 8, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(longest bin)");
 	CU(cudaMemcpyAsync(&devFlags, f.errorFlags, 4, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(frame flags)");
+	tr.mark("launched project+count");
 	CU(cudaStreamSynchronize(st), "bin count");
+	tr.mark("bin count sync");
 	CU(h->dBinEntries.reserve(std::max<size_t>(totalEntries, 1)*8), "cudaMalloc(bin entries)");
 	f.binEntries = h->dBinEntries.as<unsigned long long>();
 	// the project kernel reports whether any vertex is non-opaque: only then does the hide kernel
@@ -599,12 +615,14 @@ int renderFrame(AqhHider* h, bool download)
 	CU(cudaEventRecord(h->ev[1], st), "cudaEventRecord");
 	CU(launchHide(f, cfg, st), "k_hide"); S.gpu_launches += nActive ? 1 : 0;
 	CU(cudaEventRecord(h->ev[2], st), "cudaEventRecord");
+	tr.mark("launched hide");
 	CU(launchFilter(f, disp, h->filterTab.data(), st), "k_filter"); S.gpu_launches += 1;
 	CU(cudaEventRecord(h->ev[3], st), "cudaEventRecord");
 
 	// ---- results
 	struct { uint32_t cursor, err; uint32_t pad[2]; unsigned long long ctr[4]; } misc;
 	CU(cudaMemcpyAsync(&misc, h->dMisc.p, sizeof misc, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(counters)");
+	tr.mark("launched filter");
 	const double tDown0 = nowMs();
 	S.d2h_bytes = 0;
 	if(download)
@@ -623,6 +641,7 @@ int renderFrame(AqhHider* h, bool download)
 	}
 	CU(cudaStreamSynchronize(st), "cudaStreamSynchronize(frame)");
 	S.download_ms = download ? nowMs() - tDown0 : 0.0;
+	tr.mark("frame sync");
 	h->haveHostImage = download;
 	float ms = 0;
 	cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); S.project_bust_ms = ms;
@@ -633,6 +652,7 @@ int renderFrame(AqhHider* h, bool download)
 	S.n_micropolygons = (int64_t)misc.ctr[0]; S.n_bin_entries = (int64_t)misc.ctr[1]; S.n_deep_hits = (int64_t)misc.ctr[2];
 	S.n_samples = int64_t(L.sw)*L.sh*f.n;
 	h->rendered = true;
+	tr.mark("stats");
 	if(misc.err & 1u)
 		return h->fail(AQH_ERR_DEEP_OVERFLOW, "transparent hit pool exhausted: raise AqhFrameParams::deep_hits_per_sample");
 	return AQH_OK;
@@ -867,8 +887,11 @@ int aqh_render_device(AqhHider* h)
 int aqh_end_frame(AqhHider* h, const AqhCallbacks* cb)
 {
 	if(!h) return AQH_ERR_BAD_PARAMS;
+	FrameTrace tr;
 	if(cudaSetDevice(h->device) != cudaSuccess) return h->fail(AQH_ERR_NO_DEVICE, "cudaSetDevice failed");
+	tr.mark("end_frame: set device");
 	int rc = renderFrame(h, true);
+	tr.mark("end_frame: rendered");
 	h->inFrame = false;
 	if(rc) return rc;
 	if(!cb || (!cb->on_bucket && !cb->on_data && !cb->on_progress)) return AQH_OK;

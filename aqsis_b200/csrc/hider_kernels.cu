@@ -227,13 +227,19 @@ __global__ void __launch_bounds__(256) k_bin(DevFrame f)
 		}
 	if(!FILL)
 	{
-		// statistics: one atomic per warp, not per thread
+		// statistics: one pair of global atomics per CTA (every warp of the frame hitting the same two
+		// words serialises in L2)
+		__shared__ unsigned s_nmp, s_tot;
+		if(threadIdx.x == 0) { s_nmp = 0; s_tot = 0; }
+		__syncthreads();
 		unsigned nmp = __popc(__ballot_sync(0xffffffffu, nent != 0));
 		unsigned tot = __reduce_add_sync(0xffffffffu, nent);
-		if((threadIdx.x & 31) == 0 && tot)
+		if((threadIdx.x & 31) == 0 && tot) { atomicAdd(&s_nmp, nmp); atomicAdd(&s_tot, tot); }
+		__syncthreads();
+		if(threadIdx.x == 0 && s_tot)
 		{
-			atomicAdd(&f.counters[0], (unsigned long long)nmp);
-			atomicAdd(&f.counters[1], (unsigned long long)tot);
+			atomicAdd(&f.counters[0], (unsigned long long)s_nmp);
+			atomicAdd(&f.counters[1], (unsigned long long)s_tot);
 		}
 	}
 }

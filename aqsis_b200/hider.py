@@ -295,7 +295,9 @@ class Hider:
     def render_device(self):
         self._check(self._L.aqh_render_device(self._h))
 
-    def end_frame(self, on_bucket=None, on_data=None, on_progress=None):
+    def end_frame(self, on_bucket=None, on_data=None, on_progress=None, fetch=True):
+        """aqh_end_frame.  fetch=True returns numpy COPIES of the images (convenience for tests);
+        fetch=False leaves them in the library's pinned host buffers (see images(copy=False))."""
         cb = Callbacks()
         keep = []
         if on_bucket:
@@ -317,20 +319,25 @@ class Hider:
             keep.append(cb.on_progress)
         self._check(self._L.aqh_end_frame(self._h, C.byref(cb) if keep else None))
         self._block_keep = []
-        return self.images()
+        return self.images() if fetch else None
 
-    def images(self):
-        """(channels[yres,xres,9] float32, [display arrays]) of the last aqh_end_frame (copies)."""
+    def images(self, copy=True):
+        """(channels[yres,xres,9] float32, [display arrays]) of the last aqh_end_frame: copies, or with
+        copy=False views of the library's pinned host buffers (valid until the next frame)."""
         ptr = C.POINTER(C.c_float)()
         w, h = C.c_int(), C.c_int()
         self._check(self._L.aqh_image_channels(self._h, C.byref(ptr), C.byref(w), C.byref(h)))
-        channels = np.ctypeslib.as_array(ptr, shape=(h.value, w.value, 9)).copy()
+        channels = np.ctypeslib.as_array(ptr, shape=(h.value, w.value, 9))
+        if copy:
+            channels = channels.copy()
         displays = []
         for d in range(self.params.n_displays):
             bp = C.POINTER(C.c_ubyte)()
             es, ty = C.c_int(), C.c_int()
             self._check(self._L.aqh_image_display(self._h, d, C.byref(bp), C.byref(es), C.byref(ty)))
-            raw = np.ctypeslib.as_array(bp, shape=(h.value * w.value * es.value,)).copy()
+            raw = np.ctypeslib.as_array(bp, shape=(h.value * w.value * es.value,))
+            if copy:
+                raw = raw.copy()
             dt = np.dtype(abi.TYPE_NUMPY[ty.value])
             displays.append(raw.view(dt).reshape(h.value, w.value, es.value // dt.itemsize))
         return channels, displays
