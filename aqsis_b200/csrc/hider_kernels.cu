@@ -1262,8 +1262,20 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 
 // ---- resolve one sample: colour/opacity of the winning opaque hit, composite of the deep
 // list (CqImagePixel::Combine, imagepixel.cpp:144-332; depth filter "min" only).
-__device__ void hitUV(const DevFrame& f, const GridRec& g, uint32_t p, float2 pos, float2 dofOff, float time, float2& uv)
+template<bool MBDOF>
+__device__ __forceinline__ void hitUV(const DevFrame& f, const GridRec& g, uint32_t p, float2 pos, float2 dofOff, float time, float2& uv)
 {
+	if(!MBDOF)
+	{
+		// no motion and no depth of field anywhere in the frame: the vertices are those of the grid
+		const uint32_t cu = g.cu_cv & 0xffffu;
+		const float4 P0 = f.P4[p], P1 = f.P4[p+1], P2 = f.P4[p+cu+1], P3 = f.P4[p+cu+2];
+		const float qx[4] = {P0.x, P1.x, P2.x, P3.x}, qy[4] = {P0.y, P1.y, P2.y, P3.y}, qz[4] = {P0.z, P1.z, P2.z, P3.z};
+		HitCache c;
+		cachePointInPolyTest(c, qx, qy, qz, 0xE4 /* any valid code: only the uv part is used */);
+		uv = invBilinear(c.Ax, c.Ay, c.Ex, c.Ey, c.Fx, c.Fy, c.Gx, c.Gy, c.linear, pos.x, pos.y);
+		return;
+	}
 	MovingMP m;
 	m.p = p; m.g = g; m.cu = g.cu_cv & 0xffffu; m.nverts = g.nverts; m.nkeys = g.nkeys_koff & 0xffu;
 	m.times = f.keyTimes + (g.nkeys_koff >> 8);
@@ -1275,6 +1287,7 @@ __device__ void hitUV(const DevFrame& f, const GridRec& g, uint32_t p, float2 po
 	uv = invBilinear(c.Ax, c.Ay, c.Ex, c.Ey, c.Fx, c.Fy, c.Gx, c.Gy, c.linear, pos.x, pos.y);
 }
 
+template<bool MBDOF>
 __device__ void resolveSample(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, int idx,
                               float out[7], bool& valid)
 {
@@ -1292,7 +1305,7 @@ __device__ void resolveSample(const DevFrame& f, const TileCtx& t, const HideSme
 		float2 uv;
 		const float2 dofOff = s.dof ? s.dof[idx] : make_float2(0.f, 0.f);
 		const float time = s.time ? s.time[idx] : 0.f;
-		hitUV(f, g, p, pos, dofOff, time, uv);
+		hitUV<MBDOF>(f, g, p, pos, dofOff, time, uv);
 		shadeHit(f, g, p, uv, col, opa);
 		depth = keyDepth((uint32_t)(key >> 32));
 		opaqueMatte = (g.flags & AQH_GRID_MATTE) != 0;
@@ -1485,31 +1498,38 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 		t.rx1 = min(t.tileX0 + f.tileW, f.sx0 + f.sw);
 		t.ry1 = min(t.tileY0 + f.tileH, f.sy0 + f.sh);
 		// ---- Prepare_bucket: CqImagePixel::clear + setSamples (imagepixel.cpp:105-122, 334-359)
+		// every slot (padding included) starts empty and far outside any bound ...
 		for(int idx = tid; idx < s.nsP; idx += THREADS)
 		{
-			const int gy = idx / s.stride, gx = idx - gy*s.stride;
-			const int plx = gx / xs, ply = gy / ys;
-			const int X = t.tileX0 + plx, Y = t.tileY0 + ply;
 			s.keys[idx] = KEY_EMPTY;
 			if(s.head) s.head[idx] = 0xffffffffu;
-			if(gx < rowLen && X < t.rx1 && Y < t.ry1)
+			s.posx[idx] = -1e30f;
+			s.posy[idx] = -1e30f;
+		}
+		__syncthreads();
+		// ... then one warp per pixel of the tile, lanes over its samples (no per-sample index arithmetic)
+		for(int pix = warp; pix < f.tileW*f.tileH; pix += NWARPS)
+		{
+			const int ply = pix / f.tileW, plx = pix - ply*f.tileW;
+			const int X = t.tileX0 + plx, Y = t.tileY0 + ply;
+			if(X >= t.rx1 || Y >= t.ry1) continue;
+			const size_t pp = (size_t)(Y - f.sy0)*f.sw + (X - f.sx0);
+			const size_t plane = (size_t)f.sw*f.sh;
+			const int patPos = f.patPlanes[plane + pp];
+			const int patT = s.time ? f.patPlanes[3*plane + pp] : 0;
+			const int patS = s.dof ? f.patPlanes[pp] : 0, patD = s.dof ? f.patPlanes[2*plane + pp] : 0;
+			const int base = (ply*ys)*s.stride + plx*xs;
+			for(int i = lane; i < n; i += 32)
 			{
-				const int i = (gy - ply*ys)*xs + (gx - plx*xs);
-				const size_t pp = (size_t)(Y - f.sy0)*f.sw + (X - f.sx0);
-				const size_t plane = (size_t)f.sw*f.sh;
-				const int patPos = f.patPlanes[plane + pp];
+				const int idx = base + s.subOfs[i];
 				const float2 o = f.posTab[(size_t)patPos*n + i];
 				s.posx[idx] = (float)X + o.x;
 				s.posy[idx] = (float)Y + o.y;
 				if(s.time)
-				{
-					const int patT = f.patPlanes[3*plane + pp];
 					s.time[idx] = (f.shutterClose - f.shutterOpen) * f.val1d[(size_t)patT*n + i] + f.shutterOpen;
-				}
 				if(s.dof)
 				{
 					// samples[shuffled[i]].dofOffset = projectToCircle(-1 + 2*dofOffsets[i])
-					const int patS = f.patPlanes[pp], patD = f.patPlanes[2*plane + pp];
 					const int j = f.shufTab[(size_t)patS*n + i];
 					const float2 d = f.posTab[(size_t)patD*n + i];
 					const float vx = -1.f + 2.f*d.x, vy = -1.f + 2.f*d.y;
@@ -1521,15 +1541,10 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 						float adj = maxA(fabsf(vx), fabsf(vy)) / r;
 						o2 = make_float2(adj*vx, adj*vy);
 					}
-					s.dof[(ply*ys)*s.stride + plx*xs + (j / xs)*s.stride + j % xs] = o2;
-					if(i == 0) s.shufPat[ply*f.tileW + plx] = (uint8_t)patS;
+					s.dof[base + s.subOfs[j]] = o2;
 				}
 			}
-			else
-			{
-				s.posx[idx] = -1e30f;
-				s.posy[idx] = -1e30f;
-			}
+			if(lane == 0 && s.dof) s.shufPat[pix] = (uint8_t)patS;
 		}
 		for(int i = tid; i < f.tileW*f.tileH; i += THREADS) s.pixZ[i] = 0xffffffffu;
 		if(tid == 0) { s_tileZ = 0xffffffffu; s_dirty = 0; }
@@ -1537,11 +1552,12 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 		const uint32_t binBeg = f.binOffset[slot], binCnt = f.binOffset[slot+1] - binBeg;
 		const uint32_t tflags = f.tileFlags[slot];
 		// ---- Render_MPGs: opaque pass, then (if the tile saw non-opaque micropolygons) deep pass
-#pragma unroll 1
+		// MBDOF kernel: keep ONE copy of the (large) pass body in the instruction stream; the compiler would
+		// otherwise peel the loop.  The static kernel is small enough to profit from the specialised copies.
+#pragma unroll (MBDOF ? 1 : 2)
 		for(int pass = 0; pass < 2; ++pass)
 		{
-			// keep ONE copy of the pass body in the instruction stream (the compiler would otherwise peel the loop)
-			asm volatile("" : "+r"(pass));
+			if(MBDOF) asm volatile("" : "+r"(pass));
 			if(pass == 1)
 			{
 				if(!(f.anyTransparent && (tflags & 1u))) break;
@@ -1615,24 +1631,27 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 		const int tw = t.rx1 - t.rx0, th = t.ry1 - t.ry0;
 		if(!PARTIALS)
 		{
-			// Planes are [k][y][chunk][x][slot]: consecutive threads take consecutive sample slots of one pixel.
+			// Planes are [k][y][chunk][x][slot]: one warp per pixel, lanes over its sample slots.
 			const int SC = f.planeSC, nCh = f.planeChunks, nSlots = SC*nCh;
-			const int nOut = tw*th*nSlots;
-			for(int o = tid; o < nOut; o += THREADS)
+			for(int pix = warp; pix < tw*th; pix += NWARPS)
 			{
-				const int i = o % nSlots, pix = o / nSlots, lx = pix % tw, ly = pix / tw;
-				const int c = i / SC, j = i - c*SC;
+				const int ly = pix / tw, lx = pix - ly*tw;
 				const int X = t.rx0 + lx, Y = t.ry0 + ly;
-				const size_t at = (((size_t)(Y - f.sy0)*nCh + c)*f.planeW + (size_t)(X - f.sx0))*SC + j;
-				if(i >= n) { storeMask(f, at, 0u); continue; }       // padding slot: never included
-				const int idx = sampleIdx(f, s, lx, ly, i);
-				float out[7]; bool valid;
-				resolveSample(f, t, s, dc, idx, out, valid);
-				storeMask(f, at, packMask(f, tapMask(f, s.posx[idx], s.posy[idx], X, Y, valid)));
-				if(valid)
+				const size_t rowAt = (size_t)(Y - f.sy0)*nCh*f.planeW + (size_t)(X - f.sx0);
+				for(int i = lane; i < nSlots; i += 32)
 				{
+					const int c = i / SC, j = i - c*SC;
+					const size_t at = (rowAt + (size_t)c*f.planeW)*SC + j;
+					if(i >= n) { storeMask(f, at, 0u); continue; }       // padding slot: never included
+					const int idx = sampleIdx(f, s, lx, ly, i);
+					float out[7]; bool valid;
+					resolveSample<MBDOF>(f, t, s, dc, idx, out, valid);
+					storeMask(f, at, packMask(f, tapMask(f, s.posx[idx], s.posy[idx], X, Y, valid)));
+					if(valid)
+					{
 #pragma unroll
-					for(int k = 0; k < 7; ++k) f.planes[(size_t)k*f.planeStride + at] = out[k];
+						for(int k = 0; k < 7; ++k) f.planes[(size_t)k*f.planeStride + at] = out[k];
+					}
 				}
 			}
 		}
@@ -1656,7 +1675,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 					{
 						const int idx = sampleIdx(f, s, lx, ly, i);
 						float out[7]; bool valid;
-						resolveSample(f, t, s, dc, idx, out, valid);
+						resolveSample<MBDOF>(f, t, s, dc, idx, out, valid);
 						const uint32_t m = tapMask(f, s.posx[idx], s.posy[idx], X, Y, valid);
 						if(!valid) { out[0] = out[1] = out[2] = out[3] = out[4] = out[5] = out[6] = 0.f; }
 						scratch[2*lane] = make_float4(out[0], out[1], out[2], out[3]);
