@@ -188,8 +188,8 @@ int validateParams(AqhHider* h, const AqhFrameParams& p)
 			if(dd.channel[c] < 0 || dd.channel[c] >= AQH_NUM_CHANNELS) return h->fail(AQH_ERR_BAD_PARAMS, "display channel index");
 		if(dd.type < 0 || dd.type > AQH_SIGNED8) return h->fail(AQH_ERR_BAD_PARAMS, "display data type");
 	}
-	if(p.depth_filter != AQH_DEPTHFILTER_MIN)
-		return h->fail(AQH_ERR_UNSUPPORTED, "only depthfilter \"min\" is implemented on the device");
+	if(p.depth_filter < AQH_DEPTHFILTER_MIN || p.depth_filter > AQH_DEPTHFILTER_AVERAGE)
+		return h->fail(AQH_ERR_BAD_PARAMS, "depth_filter");
 	if(p.filter_mode != AQH_FILTER_TILE_PARTIALS && p.filter_mode != AQH_FILTER_REFERENCE_ORDER)
 		return h->fail(AQH_ERR_BAD_PARAMS, "filter_mode");
 	if(p.filter_xwidth >= 16.f || p.filter_ywidth >= 16.f)
@@ -546,6 +546,12 @@ int renderFrame(AqhHider* h, bool download)
 	f.dofMult = p.dof_multiplier; f.dofInvFocal = p.dof_one_over_focal_distance;
 	f.dofScaleX = p.dof_scale_x; f.dofScaleY = p.dof_scale_y;
 	for(int k = 0; k < 3; ++k) f.zthr[k] = p.zthreshold[k];
+	f.depthFilter = p.depth_filter;
+	{
+		const bool dz = (p.display_mode & AQH_DMODE_Z) != 0;
+		f.cullable = !(dz && (p.depth_filter == AQH_DEPTHFILTER_MAX || p.depth_filter == AQH_DEPTHFILTER_AVERAGE)) ? 1 : 0;
+		f.midpointZ = (dz && p.depth_filter == AQH_DEPTHFILTER_MIDPOINT) ? 1 : 0;
+	}
 	f.expGain = p.exposure_gain; f.expGamma = p.exposure_gamma;
 	f.jitter = p.jitter;
 	std::memcpy(f.camToRaster, p.cam_to_raster, sizeof f.camToRaster);
@@ -597,7 +603,7 @@ int renderFrame(AqhHider* h, bool download)
 	f.binEntries = h->dBinEntries.as<unsigned long long>();
 	// the project kernel reports whether any vertex is non-opaque: only then does the hide kernel
 	// carry deep-list heads in shared memory and a deep hit pool in HBM
-	f.anyTransparent = (devFlags & 2u) ? 1 : 0;
+	f.anyTransparent = ((devFlags & 2u) || !f.cullable) ? 1 : 0;
 	LaunchCfg cfg{};
 	CU(hideKernelConfig(f, h->smCount, cfg), "hide kernel configuration (shared memory / occupancy)");
 	if(f.anyTransparent)

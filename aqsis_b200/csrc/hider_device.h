@@ -43,6 +43,9 @@ struct DevFrame
 	int useDof;
 	float dofMult, dofInvFocal, dofScaleX, dofScaleY;
 	float zthr[3];
+	int depthFilter;               // AQH_DEPTHFILTER_*
+	int cullable;                  // 0: display mode has z and the depth filter is max/average -> every hit joins the sample's list (bucketprocessor.cpp:1074-1079)
+	int midpointZ;                 // display mode has z and the depth filter is midpoint -> occlZ is the SECOND nearest opaque depth
 	float expGain, expGamma;
 	int jitter;                    // 0: pattern index is always 0 and ncache == 1
 	float camToRaster[16];

@@ -549,7 +549,8 @@ struct MovScratch;
 struct HideSmem
 {
 	MovScratch* mov;           // per-warp scratch of the motion blur / depth of field path (MBDOF kernel only)
-	unsigned long long* keys;
+	unsigned long long* keys;  // per sample (occlusion depth key << 32 | position index of the hit that set it)
+	unsigned long long* near;  // nearest opaque hit; == keys unless f.midpointZ (then keys holds the second nearest)
 	float* posx;
 	float* posy;
 	float* time;
@@ -576,11 +577,12 @@ __device__ __forceinline__ HideSmem carveSmem(const DevFrame& f, unsigned char* 
 	s.keys = (unsigned long long*)(base + o); o += ns*8;
 	s.posx = (float*)(base + o); o += ns*4;
 	s.posy = (float*)(base + o); o += ns*4;
-	s.dof = 0; s.time = 0; s.head = 0;
+	s.dof = 0; s.time = 0; s.head = 0; s.near = s.keys;
 	if(f.useDof) { s.dof = (float2*)(base + o); o += ns*8; }
 	if(f.anyMotion) { s.time = (float*)(base + o); o += ns*4; }
 	if(f.anyTransparent) { s.head = (uint32_t*)(base + o); o += ns*4; }
 	o = (o + 15) & ~(size_t)15;
+	if(f.midpointZ) { s.near = (unsigned long long*)(base + o); o += ns*8; }
 	s.recs = (StaticRec*)(base + o); o += (size_t)nrecs*sizeof(StaticRec);
 	s.mov = (MovScratch*)(base + o); o += movBytes;
 	s.pixZ = (uint32_t*)(base + o); o += (size_t)f.tileW*f.tileH*4;
@@ -597,6 +599,7 @@ static size_t hideSmemBytes(const DevFrame& f, int nrecs, size_t movBytes)
 	if(f.anyMotion) o += ns*4;
 	if(f.anyTransparent) o += ns*4;
 	o = (o + 15) & ~(size_t)15;
+	if(f.midpointZ) o += ns*8;
 	o += (size_t)nrecs*sizeof(StaticRec) + movBytes;
 	o += (size_t)f.tileW*f.tileH*4;
 	o += (size_t)f.n*2 + (size_t)f.tileW*f.tileH;
@@ -618,7 +621,17 @@ __device__ __forceinline__ void storeOpaque(const HideSmem& s, unsigned long lon
 	unsigned long long nk = ((unsigned long long)depthKey(D) << 32) | p;
 	if(nk < *key)                                    // cheap pre-check; keys only ever decrease
 	{
-		atomicMin(key, nk);
+		if(s.near != s.keys)
+		{
+			// midpoint depth filter with a z display (bucketprocessor.cpp:1502-1529): the sample keeps the
+			// nearest hit and occlZ = the second nearest depth.  Order independent: the value that loses
+			// the race for "nearest" is offered to "second nearest".
+			unsigned long long* nearKey = s.near + (key - s.keys);
+			const unsigned long long old = atomicMin(nearKey, nk);
+			atomicMin(key, old > nk ? old : nk);
+		}
+		else
+			atomicMin(key, nk);
 		*(volatile uint32_t*)s.dirty = 1u;
 	}
 }
@@ -719,7 +732,7 @@ __device__ void setupStaticRec(const DevFrame& f, const TileCtx& t, const HideSm
 	if(g.flags & AQH_GRID_SMOOTH)
 		opaque = opaque && (infoOf(P[1]) & VINFO_OPAQUE) && (infoOf(P[2]) & VINFO_OPAQUE) && (infoOf(P[3]) & VINFO_OPAQUE);
 	// MatteAlpha objects use the opaque slot too (bucketprocessor.cpp:1490-1491)
-	bool opaqueSlot = opaque || (g.flags & AQH_GRID_MATTE_ALPHA);
+	bool opaqueSlot = (opaque || (g.flags & AQH_GRID_MATTE_ALPHA)) && f.cullable;
 	if(opaqueSlot != wantOpaque) return;
 	const B2 B = boundOf4(P[0], P[1], P[3], P[2]);
 	const float bminx = B.mnx, bmaxx = B.mxx, bminy = B.mny, bmaxy = B.mxy;
@@ -1048,7 +1061,7 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 	bool opaque = (info & VINFO_OPAQUE) != 0;
 	if(m.g.flags & AQH_GRID_SMOOTH)
 		opaque = opaque && (infoOf(P[1]) & VINFO_OPAQUE) && (infoOf(P[2]) & VINFO_OPAQUE) && (infoOf(P[3]) & VINFO_OPAQUE);
-	const bool opaqueSlot = opaque || (m.g.flags & AQH_GRID_MATTE_ALPHA);
+	const bool opaqueSlot = (opaque || (m.g.flags & AQH_GRID_MATTE_ALPHA)) && f.cullable;
 	if(opaqueSlot != opaquePass) return true;
 	m.code = computeVertexOrder(P);
 	// m_Bound: union of the key bounds (AppendKey, micropolygon.cpp:1952-1967)
@@ -1291,7 +1304,10 @@ template<bool MBDOF>
 __device__ void resolveSample(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, int idx,
                               float out[7], bool& valid)
 {
-	const unsigned long long key = s.keys[idx];
+	// s.near: nearest opaque hit; s.keys: the occlusion depth occlZ (the same array unless the midpoint depth
+	// filter keeps the SECOND nearest opaque depth there, bucketprocessor.cpp:1502-1529)
+	const unsigned long long key = s.near[idx];
+	const float occlZ = keyDepth((uint32_t)(s.keys[idx] >> 32));
 	const uint32_t p = (uint32_t)key;
 	const bool haveOpaque = (p != 0xffffffffu);
 	const float2 pos = make_float2(s.posx[idx], s.posy[idx]);
@@ -1313,109 +1329,148 @@ __device__ void resolveSample(const DevFrame& f, const TileCtx& t, const HideSme
 	uint32_t head = s.head ? s.head[idx] : 0xffffffffu;
 	if(head == 0xffffffffu)
 	{
+		// opaque-only sample: imagepixel.cpp:304-327
 		valid = haveOpaque;
-		if(opaqueMatte) { col[0] = col[1] = col[2] = 0.f; opa[0] = opa[1] = opa[2] = 0.f; }  // imagepixel.cpp:308-318
+		if(opaqueMatte) { col[0] = col[1] = col[2] = 0.f; opa[0] = opa[1] = opa[2] = 0.f; }
+		if(haveOpaque && f.depthFilter == AQH_DEPTHFILTER_MIDPOINT) depth = 0.5f*(depth + occlZ);
 		out[0] = col[0]; out[1] = col[1]; out[2] = col[2]; out[3] = opa[0]; out[4] = opa[1]; out[5] = opa[2]; out[6] = depth;
 		return;
 	}
-	// back-to-front over {opaque hit} ∪ deep list, i.e. descending (depth, order)
-	float sc[3] = {0.f, 0.f, 0.f}, so[3] = {0.f, 0.f, 0.f};
-	float opaqueDepth0 = haveOpaque ? depth : FLT_MAX;      // opaqueDepths[0] = occlZ
-	if(haveOpaque)
-	{
-		if(opaqueMatte)
-		{
-#pragma unroll
-			for(int k = 0; k < 3; ++k) { sc[k] = (1.f-opa[k])*sc[k] + opa[k]*0.0f; so[k] = (1.f-col[k])*so[k] + col[k]*0.0f; }
-		}
-		else
-		{
-#pragma unroll
-			for(int k = 0; k < 3; ++k)
-			{
-				sc[k] = (sc[k] * (1.0f - fminf(fmaxf(opa[k], 0.0f), 1.0f))) + col[k];
-				so[k] = ((1.0f - so[k]) * opa[k]) + so[k];
-			}
-		}
-		if(opa[0] >= f.zthr[0] && opa[1] >= f.zthr[1] && opa[2] >= f.zthr[2]) opaqueDepth0 = depth;
-	}
-	// One walk over the sample's list collects up to DEEP_SORT entries into a register-resident,
-	// descending (depth, submission) order -- the pointer chase through the pool is paid once;
-	// longer lists fall back to repeated selection of the farthest not yet composited entry.
+	// ---- CqImagePixel::Combine (imagepixel.cpp:144-300): the valid opaque hit joins the list, the list is
+	// ordered by depth and composited back to front.  One walk over the sample's list collects up to
+	// DEEP_SORT entries into a register-resident, descending (depth, submission) order -- the pointer chase
+	// through the pool is paid once; longer lists fall back to repeated selection.
 	constexpr int DEEP_SORT = 8;
+	constexpr uint32_t NIL = 0xffffffffu, OPQ = 0xfffffffeu;      // OPQ: "the entry is the opaque hit"
 	unsigned long long ks[DEEP_SORT];
 	uint32_t sl[DEEP_SORT];
 #pragma unroll
-	for(int j = 0; j < DEEP_SORT; ++j) { ks[j] = 0ull; sl[j] = 0xffffffffu; }
+	for(int j = 0; j < DEEP_SORT; ++j) { ks[j] = 0ull; sl[j] = NIL; }
 	int nList = 0;
-	for(uint32_t e = head; e != 0xffffffffu; )
 	{
-		const uint4 A = dc.A[e];
-		unsigned long long k = ((unsigned long long)depthKey(__uint_as_float(A.y)) << 32) | A.z;
-		uint32_t ce = e;
-#pragma unroll
-		for(int j = 0; j < DEEP_SORT; ++j)
+		uint32_t e = haveOpaque ? OPQ : head;
+		while(e != NIL)
 		{
-			// strict '>' keeps equal keys (a hit stored twice on a time sub-bound boundary) both in the list
-			if(k > ks[j] || (sl[j] == 0xffffffffu && ce != 0xffffffffu))
-			{
-				const unsigned long long tk = ks[j]; const uint32_t ts = sl[j];
-				ks[j] = k; sl[j] = ce; k = tk; ce = ts;
-			}
-		}
-		++nList;
-		e = A.x;
-	}
-	unsigned long long prev = ~0ull;
-	for(int step = 0; ; ++step)
-	{
-		uint32_t bestSlot = 0xffffffffu;
-		if(nList <= DEEP_SORT)
-		{
-			if(step >= nList) break;
-#pragma unroll
-			for(int j = 0; j < DEEP_SORT; ++j) if(j == step) bestSlot = sl[j];
-		}
-		else
-		{
-			// farthest not yet composited entry: largest (depthKey, p) strictly below prev
-			unsigned long long best = 0;
-			for(uint32_t e = head; e != 0xffffffffu; )
+			unsigned long long k; uint32_t nextE;
+			if(e == OPQ) { k = key; nextE = head; }
+			else
 			{
 				const uint4 A = dc.A[e];
-				unsigned long long k = ((unsigned long long)depthKey(__uint_as_float(A.y)) << 32) | A.z;
-				if(k < prev && (bestSlot == 0xffffffffu || k > best)) { best = k; bestSlot = e; }
-				e = A.x;
+				k = ((unsigned long long)depthKey(__uint_as_float(A.y)) << 32) | A.z;
+				nextE = A.x;
 			}
-			if(bestSlot == 0xffffffffu) break;
-			prev = best;
-		}
-		const uint4 A = dc.A[bestSlot];
-		const float2 uv = dc.UV[bestSlot];
-		const float4 a = f.P4[A.z];
-		const GridRec g = f.grids[infoOf(a) & VINFO_GRID_MASK];
-		float c2[3], o2[3];
-		shadeHit(f, g, A.z, uv, c2, o2);
-		const float d2 = __uint_as_float(A.y);
-		if(g.flags & AQH_GRID_MATTE)
-		{
+			uint32_t ce = e;
 #pragma unroll
-			for(int k = 0; k < 3; ++k) { sc[k] = (1.f-o2[k])*sc[k] + o2[k]*0.0f; so[k] = (1.f-c2[k])*so[k] + c2[k]*0.0f; }
-		}
-		else
-		{
-#pragma unroll
-			for(int k = 0; k < 3; ++k)
+			for(int j = 0; j < DEEP_SORT; ++j)
 			{
-				sc[k] = (sc[k] * (1.0f - fminf(fmaxf(o2[k], 0.0f), 1.0f))) + c2[k];
-				so[k] = ((1.0f - so[k]) * o2[k]) + so[k];
+				// strict '>' keeps equal keys (a hit stored twice on a time sub-bound boundary) both in the list
+				if(k > ks[j] || (sl[j] == NIL && ce != NIL))
+				{
+					const unsigned long long tk = ks[j]; const uint32_t ts = sl[j];
+					ks[j] = k; sl[j] = ce; k = tk; ce = ts;
+				}
+			}
+			++nList;
+			e = nextE;
+		}
+	}
+	float sc[3] = {0.f, 0.f, 0.f}, so[3] = {0.f, 0.f, 0.f};
+	float opaqueDepth0 = occlZ, opaqueDepth1 = FLT_MAX, maxOpaqueDepth = FLT_MAX;
+	float totDepth = 0.0f; int totCount = 0;
+	const bool average = f.depthFilter == AQH_DEPTHFILTER_AVERAGE;
+	// pass 0: back to front (descending) compositing; pass 1 (depth filter "average" only): front to back sum
+	// of the depths of the entries that reach the z threshold in ANY channel (imagepixel.cpp:279-296)
+	for(int pass = 0; pass < (average ? 2 : 1); ++pass)
+	{
+		unsigned long long prev = (pass == 0) ? ~0ull : 0ull;
+		for(int step = 0; ; ++step)
+		{
+			uint32_t bestSlot = NIL;
+			if(nList <= DEEP_SORT)
+			{
+				if(step >= nList) break;
+				const int want = (pass == 0) ? step : nList - 1 - step;
+#pragma unroll
+				for(int j = 0; j < DEEP_SORT; ++j) if(j == want) bestSlot = sl[j];
+			}
+			else
+			{
+				// next entry in (depthKey, p) order strictly beyond prev
+				unsigned long long best = 0;
+				uint32_t e = haveOpaque ? OPQ : head;
+				while(e != NIL)
+				{
+					unsigned long long k; uint32_t nextE;
+					if(e == OPQ) { k = key; nextE = head; }
+					else
+					{
+						const uint4 A = dc.A[e];
+						k = ((unsigned long long)depthKey(__uint_as_float(A.y)) << 32) | A.z;
+						nextE = A.x;
+					}
+					const bool beyond = (pass == 0) ? (k < prev) : (k > prev);
+					const bool better = (pass == 0) ? (k > best) : (k < best);
+					if(beyond && (bestSlot == NIL || better)) { best = k; bestSlot = e; }
+					e = nextE;
+				}
+				if(bestSlot == NIL) break;
+				prev = best;
+			}
+			float c2[3], o2[3], d2;
+			bool matte;
+			if(bestSlot == OPQ)
+			{
+#pragma unroll
+				for(int k = 0; k < 3; ++k) { c2[k] = col[k]; o2[k] = opa[k]; }
+				d2 = depth; matte = opaqueMatte;
+			}
+			else
+			{
+				const uint4 A = dc.A[bestSlot];
+				const float2 uv = dc.UV[bestSlot];
+				const float4 a = f.P4[A.z];
+				const GridRec g = f.grids[infoOf(a) & VINFO_GRID_MASK];
+				shadeHit(f, g, A.z, uv, c2, o2);
+				d2 = __uint_as_float(A.y);
+				matte = (g.flags & AQH_GRID_MATTE) != 0;
+			}
+			if(pass == 1)
+			{
+				// the nearest entry shares its data with the composited result in the reference (the hit is
+				// an index into the pixel's data pool): its test sees the composited opacity
+				const float* od = (step == 0) ? so : o2;
+				if(od[0] >= f.zthr[0] || od[1] >= f.zthr[1] || od[2] >= f.zthr[2]) { totDepth += d2; totCount++; }
+				continue;
+			}
+			if(matte)
+			{
+#pragma unroll
+				for(int k = 0; k < 3; ++k) { sc[k] = (1.f-o2[k])*sc[k] + o2[k]*0.0f; so[k] = (1.f-c2[k])*so[k] + c2[k]*0.0f; }
+			}
+			else
+			{
+#pragma unroll
+				for(int k = 0; k < 3; ++k)
+				{
+					sc[k] = (sc[k] * (1.0f - fminf(fmaxf(o2[k], 0.0f), 1.0f))) + c2[k];
+					so[k] = ((1.0f - so[k]) * o2[k]) + so[k];
+				}
+			}
+			if(o2[0] >= f.zthr[0] && o2[1] >= f.zthr[1] && o2[2] >= f.zthr[2])
+			{
+				opaqueDepth1 = opaqueDepth0;
+				opaqueDepth0 = d2;
+				if(!(maxOpaqueDepth < FLT_MAX)) maxOpaqueDepth = d2;
 			}
 		}
-		if(o2[0] >= f.zthr[0] && o2[1] >= f.zthr[1] && o2[2] >= f.zthr[2]) opaqueDepth0 = d2;
 	}
 	valid = true;
 	out[0] = sc[0]; out[1] = sc[1]; out[2] = sc[2]; out[3] = so[0]; out[4] = so[1]; out[5] = so[2];
-	out[6] = opaqueDepth0;
+	float zout = opaqueDepth0;
+	if(f.depthFilter == AQH_DEPTHFILTER_MIDPOINT) zout = (nList > 1) ? ((opaqueDepth0 + opaqueDepth1) * 0.5f) : FLT_MAX;
+	else if(f.depthFilter == AQH_DEPTHFILTER_MAX) zout = maxOpaqueDepth;
+	else if(average) zout = totDepth / (float)totCount;
+	out[6] = zout;
 }
 
 // Per-tap inclusion bits of one sample (bucketprocessor.cpp:609-612), evaluated with the true
@@ -1502,6 +1557,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 		for(int idx = tid; idx < s.nsP; idx += THREADS)
 		{
 			s.keys[idx] = KEY_EMPTY;
+			if(s.near != s.keys) s.near[idx] = KEY_EMPTY;
 			if(s.head) s.head[idx] = 0xffffffffu;
 			s.posx[idx] = -1e30f;
 			s.posy[idx] = -1e30f;
@@ -1740,7 +1796,7 @@ __global__ void __launch_bounds__(256) k_tile_flags(DevFrame f)
 		bool opaque = (info & VINFO_OPAQUE) != 0;
 		if(g.flags & AQH_GRID_SMOOTH)
 			opaque = opaque && (infoOf(f.P4[p+1]) & VINFO_OPAQUE) && (infoOf(f.P4[p+cu+1]) & VINFO_OPAQUE) && (infoOf(f.P4[p+cu+2]) & VINFO_OPAQUE);
-		if(!(opaque || (g.flags & AQH_GRID_MATTE_ALPHA))) any = 1;
+		if(!((opaque || (g.flags & AQH_GRID_MATTE_ALPHA)) && f.cullable)) any = 1;
 	}
 	if(any) s_any = 1;
 	__syncthreads();
@@ -1790,6 +1846,11 @@ __device__ __forceinline__ void finishPixel(const DevFrame& f, const DevDisplays
 			if(f.expGamma != 1.0f) out[k] = (float)pow((double)out[k], (double)oneovergamma);
 		}
 	}
+	// A NaN (0/0 of the "average" depth filter over no qualifying hit, inf - inf of filtered FLT_MAX depths with
+	// negative lobes) is the x86 default NaN 0xFFC00000 in the reference's build; the GPU's canonical NaN is
+	// 0x7FFFFFFF.  Same value class, made the same bits.
+#pragma unroll
+	for(int k = 0; k < 9; ++k) if(out[k] != out[k]) out[k] = __uint_as_float(0xffc00000u);
 	float* dst = f.channels + ((size_t)y*f.xres + x)*9;
 #pragma unroll
 	for(int k = 0; k < 9; ++k) dst[k] = out[k];

@@ -127,7 +127,7 @@ typedef struct AqhFrameParams
 	float   dof_multiplier;         /* m_DofMultiplier         renderer.h:368-377 */
 	float   dof_one_over_focal_distance;
 	float   dof_scale_x, dof_scale_y; /* m_DepthOfFieldScale   options.cpp:162-171 */
-	int32_t depth_filter;           /* AQH_DEPTHFILTER_* (only MIN implemented) */
+	int32_t depth_filter;           /* AQH_DEPTHFILTER_*: min, midpoint, max, average (imagepixel.cpp:264-327) */
 	float   zthreshold[3];          /* limits:zthreshold, default 1 1 1 */
 	int32_t display_mode;           /* AQH_DMODE_* union over displays */
 	float   exposure_gain, exposure_gamma;

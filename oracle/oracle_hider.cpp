@@ -1492,12 +1492,19 @@ void combineSample(SampleData& sampleData, int depthfilter, const F* zThreshold)
 			{
 				F totDepth = 0.0f;
 				int totCount = 0;
+				// In the reference a hit is (flags, index into the pixel's hit-data pool): "occlHit = *data.begin()"
+				// (imagepixel.cpp:251) copies the INDEX, so the composited colour/opacity written through occlData
+				// above also overwrite the nearest list entry -- its threshold test below sees the composited
+				// opacity, not its own (imagepixel.cpp:279-293).
 				for(std::vector<Hit>::iterator s2 = sampleData.data.begin(); s2 != sampleData.data.end(); s2++)
-					if(s2->d[3] >= zThreshold[0] || s2->d[4] >= zThreshold[1] || s2->d[5] >= zThreshold[2])
+				{
+					const F* od = (s2 == sampleData.data.begin()) ? occlData : s2->d;
+					if(od[3] >= zThreshold[0] || od[4] >= zThreshold[1] || od[5] >= zThreshold[2])
 					{
 						totDepth += s2->d[6];
 						totCount++;
 					}
+				}
 				totDepth /= totCount;
 				occlDepth = totDepth;
 			}

@@ -342,7 +342,6 @@ int ref_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* chann
 {
 	if(!pp || !grids || grids->memory_space != 0) return AQH_ERR_BAD_PARAMS;
 	const AqhFrameParams& p = *pp;
-	if(p.depth_filter != AQH_DEPTHFILTER_MIN) return AQH_ERR_UNSUPPORTED;
 	const double t0 = nowS();
 
 	// ---- render context and options (what RiCxxCore::WorldBegin leaves behind, ri.cpp:577-666)
@@ -358,6 +357,13 @@ int ref_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* chann
 	setOpt<TqInt>(opt.GetIntegerOptionWrite("System", "DisplayMode", 1), {p.display_mode});
 	setOpt<TqInt>(opt.GetIntegerOptionWrite("limits", "bucketsize", 2), {p.bucket_xsize, p.bucket_ysize});
 	setOpt<TqInt>(opt.GetIntegerOptionWrite("Hider", "jitter", 1), {p.jitter});
+	{
+		// Hider "depthfilter" and limits "zthreshold" (optioncache.cpp:95-116)
+		static const char* const names[4] = {"min", "midpoint", "max", "average"};
+		if(p.depth_filter < 0 || p.depth_filter > 3) return AQH_ERR_BAD_PARAMS;
+		opt.GetStringOptionWrite("Hider", "depthfilter", 1)[0] = names[p.depth_filter];
+		opt.GetColorOptionWrite("limits", "zthreshold", 1)[0] = CqColor(p.zthreshold[0], p.zthreshold[1], p.zthreshold[2]);
+	}
 	opt.SetfuncFilter(p.filter_func ? reinterpret_cast<RtFilterFunc>(p.filter_func) : RiGaussianFilter);
 	CqImageBuffer* image = new CqImageBuffer;
 	RefDDManager dd(p, channels, display_out);

@@ -55,7 +55,7 @@ def compare(ch_gpu, disp_gpu, ch_ref, disp_ref, float_rtol=FLOAT_RTOL, quant_ato
     denom = np.maximum(np.abs(b), 1e-3)
     rel = np.where(finite, np.abs(a - b) / denom, 0.0)
     # where the reference holds FLT_MAX / inf both must agree exactly
-    special_equal = np.array_equal(np.where(finite, 0, a), np.where(finite, 0, b))
+    special_equal = np.array_equal(np.where(finite, 0, a), np.where(finite, 0, b), equal_nan=True)
     out = {
         "float_max_rel": float(rel.max()) if rel.size else 0.0,
         "float_bit_exact_frac": float((ch_gpu.view(np.uint32) == ch_ref.view(np.uint32)).mean()),

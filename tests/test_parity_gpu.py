@@ -99,6 +99,20 @@ def test_odd_sample_counts(gpu_hider, samples):
     check(gpu_hider, p, g, TILED)
 
 
+@pytest.mark.parametrize("dmode", [abi.DMODE_RGB | abi.DMODE_A, abi.DMODE_RGB | abi.DMODE_A | abi.DMODE_Z], ids=["rgba", "rgbaz"])
+@pytest.mark.parametrize("dfilter", [abi.DEPTHFILTER_MIDPOINT, abi.DEPTHFILTER_MAX, abi.DEPTHFILTER_AVERAGE], ids=["midpoint", "max", "average"])
+def test_depth_filters(gpu_hider, dfilter, dmode):
+    """Hider "depthfilter" midpoint / max / average (imagepixel.cpp:264-327, bucketprocessor.cpp:1074-1079, 1502-1529):
+    opaque, deep-transparent and MB+DoF frames, bit-identical to the oracle (which is pinned to the reference's own
+    hider for the same cases in test_reference_hider.py)."""
+    for make in (lambda: scenes.config1(scale=0.15), lambda: scenes.config4(scale=0.015), lambda: scenes.config3(scale=0.04, motion_px=6.0)):
+        p, g = make()
+        p.depth_filter, p.display_mode = dfilter, dmode
+        p.deep_hits_per_sample = 24
+        # "average" over no qualifying hit is 0/0 in the reference: the NaN z must come out of both sides (same bits)
+        check(gpu_hider, p, g, EXACT)
+
+
 def test_empty_frame(gpu_hider):
     p = default_params(resolution=(40, 24), samples=(2, 2), displays=[("rgba", 1, 255.0, 0.0, 255.0, 0.5)])
     gpu_hider.begin_frame(p)
@@ -175,10 +189,10 @@ def test_errors_are_statuses_not_crashes(gpu_hider):
         gpu_hider.begin_frame(p)
     assert e.value.status == abi.AQH_ERR_BAD_PARAMS
     p = default_params(resolution=(32, 32))
-    p.depth_filter = abi.DEPTHFILTER_MIDPOINT
+    p.depth_filter = 7
     with pytest.raises(HiderError) as e:
         gpu_hider.begin_frame(p)
-    assert e.value.status == abi.AQH_ERR_UNSUPPORTED
+    assert e.value.status == abi.AQH_ERR_BAD_PARAMS
     p = default_params(resolution=(32, 32))
     gpu_hider.begin_frame(p)
     from test_oracle_render import one_grid
@@ -211,6 +225,10 @@ def _ref_cases():
     p, g = scenes.config1(scale=0.15)
     p.jitter = 0
     yield "jitter0", (p, g)
+    for df in (abi.DEPTHFILTER_MIDPOINT, abi.DEPTHFILTER_MAX, abi.DEPTHFILTER_AVERAGE):
+        p, g = scenes.config4(scale=0.012)
+        p.depth_filter, p.display_mode, p.deep_hits_per_sample = df, abi.DMODE_RGB | abi.DMODE_A | abi.DMODE_Z, 24
+        yield f"depthfilter{df}", (p, g)
 
 
 def test_cuda_path_equals_reference_hider(gpu_hider):

@@ -58,6 +58,14 @@ CASES = {
     "predraws": lambda: _mod(scenes.config1(scale=0.12), lambda p: _set(p, rng_predraws=1234, rng_seed=77)),
     "shutter-0.2-0.7": lambda: _mod(scenes.config3(scale=0.04, motion_px=6.0), lambda p: _set(p, shutter_open=0.2, shutter_close=0.7, use_dof=0)),
 }
+# depth filters (imagepixel.cpp:264-300, 319-327; StoreSample's midpoint rule bucketprocessor.cpp:1502-1529) with and
+# without a z display (DMode_Z turns max/average into "nothing is cullable", bucketprocessor.cpp:1074-1079)
+for _df, _dn in [(abi.DEPTHFILTER_MIDPOINT, "midpoint"), (abi.DEPTHFILTER_MAX, "max"), (abi.DEPTHFILTER_AVERAGE, "average")]:
+    for _dm, _mn in [(abi.DMODE_RGB | abi.DMODE_A, "rgba"), (abi.DMODE_RGB | abi.DMODE_A | abi.DMODE_Z, "rgbaz")]:
+        CASES[f"depthfilter-{_dn}-{_mn}-static"] = (lambda df=_df, dm=_dm: _mod(scenes.config1(scale=0.15), lambda p: _set(p, depth_filter=df, display_mode=dm)))
+        CASES[f"depthfilter-{_dn}-{_mn}-deep"] = (lambda df=_df, dm=_dm: _mod(scenes.config4(scale=0.015), lambda p: _set(p, depth_filter=df, display_mode=dm)))
+    CASES[f"depthfilter-{_dn}-rgbaz-mbdof"] = (lambda df=_df: _mod(scenes.config3(scale=0.04, motion_px=6.0),
+                                                                   lambda p: _set(p, depth_filter=df, display_mode=abi.DMODE_RGB | abi.DMODE_A | abi.DMODE_Z)))
 for _name, _w in [("box", 1.0), ("triangle", 2.0), ("gaussian", 3.0), ("catmull-rom", 4.0), ("sinc", 5.0), ("sinc", 6.0),
                   ("gaussian", 2.5), ("mitchell", 4.0), ("disk", 3.0), ("bessel", 4.0)]:
     CASES[f"filter-{_name}-{_w}"] = (lambda n=_name, w=_w: scenes.config2(scale=0.04, filter=(n, w, w), samples=(4, 4)))
