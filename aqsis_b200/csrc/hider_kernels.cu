@@ -550,7 +550,6 @@ struct HideSmem
 {
 	MovScratch* mov;           // per-warp scratch of the motion blur / depth of field path (MBDOF kernel only)
 	unsigned long long* keys;  // per sample (occlusion depth key << 32 | position index of the hit that set it)
-	unsigned long long* near;  // nearest opaque hit; == keys unless f.midpointZ (then keys holds the second nearest)
 	float* posx;
 	float* posy;
 	float* time;
@@ -574,15 +573,16 @@ __device__ __forceinline__ HideSmem carveSmem(const DevFrame& f, unsigned char* 
 	s.nsP = f.tileH*f.ys*s.stride;
 	const size_t ns = (size_t)s.nsP;
 	size_t o = 0;
-	s.keys = (unsigned long long*)(base + o); o += ns*8;
+	// f.midpointZ: a second array right behind the first -- keys[idx] = occlusion key (second nearest opaque
+	// depth), keys[nsP + idx] = nearest opaque hit (bucketprocessor.cpp:1502-1529); otherwise they are the same
+	s.keys = (unsigned long long*)(base + o); o += ns*8*(f.midpointZ ? 2 : 1);
 	s.posx = (float*)(base + o); o += ns*4;
 	s.posy = (float*)(base + o); o += ns*4;
-	s.dof = 0; s.time = 0; s.head = 0; s.near = s.keys;
+	s.dof = 0; s.time = 0; s.head = 0;
 	if(f.useDof) { s.dof = (float2*)(base + o); o += ns*8; }
 	if(f.anyMotion) { s.time = (float*)(base + o); o += ns*4; }
 	if(f.anyTransparent) { s.head = (uint32_t*)(base + o); o += ns*4; }
 	o = (o + 15) & ~(size_t)15;
-	if(f.midpointZ) { s.near = (unsigned long long*)(base + o); o += ns*8; }
 	s.recs = (StaticRec*)(base + o); o += (size_t)nrecs*sizeof(StaticRec);
 	s.mov = (MovScratch*)(base + o); o += movBytes;
 	s.pixZ = (uint32_t*)(base + o); o += (size_t)f.tileW*f.tileH*4;
@@ -594,12 +594,11 @@ __device__ __forceinline__ HideSmem carveSmem(const DevFrame& f, unsigned char* 
 static size_t hideSmemBytes(const DevFrame& f, int nrecs, size_t movBytes)
 {
 	const size_t ns = (size_t)f.tileH*f.ys*hideStride(f);
-	size_t o = ns*16;
+	size_t o = ns*16 + (f.midpointZ ? ns*8 : 0);
 	if(f.useDof) o += ns*8;
 	if(f.anyMotion) o += ns*4;
 	if(f.anyTransparent) o += ns*4;
 	o = (o + 15) & ~(size_t)15;
-	if(f.midpointZ) o += ns*8;
 	o += (size_t)nrecs*sizeof(StaticRec) + movBytes;
 	o += (size_t)f.tileW*f.tileH*4;
 	o += (size_t)f.n*2 + (size_t)f.tileW*f.tileH;
@@ -615,18 +614,18 @@ __device__ __forceinline__ int sampleIdx(const DevFrame& f, const HideSmem& s, i
 // Deposit a hit: opaque hits race for the per-sample (depth, order) minimum; transparent ones
 // are appended to the CTA's deep pool if they are in front of the final opaque depth.
 // StoreSample, bucketprocessor.cpp:1471-1569.
-__device__ __forceinline__ void storeOpaque(const HideSmem& s, unsigned long long* key, float D, uint32_t p)
+__device__ __forceinline__ void storeOpaque(const DevFrame& f, const HideSmem& s, unsigned long long* key, float D, uint32_t p)
 {
 	if(!(D < FLT_MAX)) return;                       // occlZ(=FLT_MAX) <= D
 	unsigned long long nk = ((unsigned long long)depthKey(D) << 32) | p;
 	if(nk < *key)                                    // cheap pre-check; keys only ever decrease
 	{
-		if(s.near != s.keys)
+		if(f.midpointZ)
 		{
 			// midpoint depth filter with a z display (bucketprocessor.cpp:1502-1529): the sample keeps the
 			// nearest hit and occlZ = the second nearest depth.  Order independent: the value that loses
 			// the race for "nearest" is offered to "second nearest".
-			unsigned long long* nearKey = s.near + (key - s.keys);
+			unsigned long long* nearKey = key + s.nsP;
 			const unsigned long long old = atomicMin(nearKey, nk);
 			atomicMin(key, old > nk ? old : nk);
 		}
@@ -812,7 +811,7 @@ __device__ __forceinline__ void sampleStaticRec(const DevFrame& f, const TileCtx
 				if(triangleSplitReject(f, g, make_float2(x, y), make_float2(0.f, 0.f), D, 0.0f)) continue;
 		}
 		if(OPAQUE)
-			storeOpaque(s, &s.keys[idx], D, r.p);
+			storeOpaque(f, s, &s.keys[idx], D, r.p);
 		else
 			storeDeep<AGG>(f, dc, s, idx, D, r.p, uv);
 	}
@@ -987,7 +986,7 @@ __device__ __forceinline__ void movCandidate(const DevFrame& f, const TileCtx& t
 	if(c.m.g.flags & AQH_GRID_TRIANGULAR)
 		if(triangleSplitReject(f, c.m.g, pos, dofOff, D, time)) return;
 	if(c.opaquePass)
-		storeOpaque(s, &s.keys[idx], D, c.m.p);
+		storeOpaque(f, s, &s.keys[idx], D, c.m.p);
 	else
 		storeDeep<false>(f, dc, s, idx, D, c.m.p, uv);
 }
@@ -1300,13 +1299,145 @@ __device__ __forceinline__ void hitUV(const DevFrame& f, const GridRec& g, uint3
 	uv = invBilinear(c.Ax, c.Ay, c.Ex, c.Ey, c.Fx, c.Fy, c.Gx, c.Gy, c.linear, pos.x, pos.y);
 }
 
+// Fast path: depth filter "min" (imagepixel.cpp:144-262, 301-318).
 template<bool MBDOF>
-__device__ void resolveSample(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, int idx,
+__device__ __forceinline__ void resolveSampleMin(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, int idx,
                               float out[7], bool& valid)
 {
-	// s.near: nearest opaque hit; s.keys: the occlusion depth occlZ (the same array unless the midpoint depth
+	const unsigned long long key = s.keys[idx];
+	const uint32_t p = (uint32_t)key;
+	const bool haveOpaque = (p != 0xffffffffu);
+	const float2 pos = make_float2(s.posx[idx], s.posy[idx]);
+	float col[3] = {0.f, 0.f, 0.f}, opa[3] = {0.f, 0.f, 0.f};
+	float depth = 0.f;
+	bool opaqueMatte = false;
+	if(haveOpaque)
+	{
+		const float4 a = f.P4[p];
+		const GridRec g = f.grids[infoOf(a) & VINFO_GRID_MASK];
+		float2 uv;
+		const float2 dofOff = s.dof ? s.dof[idx] : make_float2(0.f, 0.f);
+		const float time = s.time ? s.time[idx] : 0.f;
+		hitUV<MBDOF>(f, g, p, pos, dofOff, time, uv);
+		shadeHit(f, g, p, uv, col, opa);
+		depth = keyDepth((uint32_t)(key >> 32));
+		opaqueMatte = (g.flags & AQH_GRID_MATTE) != 0;
+	}
+	uint32_t head = s.head ? s.head[idx] : 0xffffffffu;
+	if(head == 0xffffffffu)
+	{
+		valid = haveOpaque;
+		if(opaqueMatte) { col[0] = col[1] = col[2] = 0.f; opa[0] = opa[1] = opa[2] = 0.f; }  // imagepixel.cpp:308-318
+		out[0] = col[0]; out[1] = col[1]; out[2] = col[2]; out[3] = opa[0]; out[4] = opa[1]; out[5] = opa[2]; out[6] = depth;
+		return;
+	}
+	// back-to-front over {opaque hit} ∪ deep list, i.e. descending (depth, order)
+	float sc[3] = {0.f, 0.f, 0.f}, so[3] = {0.f, 0.f, 0.f};
+	float opaqueDepth0 = haveOpaque ? depth : FLT_MAX;      // opaqueDepths[0] = occlZ
+	if(haveOpaque)
+	{
+		if(opaqueMatte)
+		{
+#pragma unroll
+			for(int k = 0; k < 3; ++k) { sc[k] = (1.f-opa[k])*sc[k] + opa[k]*0.0f; so[k] = (1.f-col[k])*so[k] + col[k]*0.0f; }
+		}
+		else
+		{
+#pragma unroll
+			for(int k = 0; k < 3; ++k)
+			{
+				sc[k] = (sc[k] * (1.0f - fminf(fmaxf(opa[k], 0.0f), 1.0f))) + col[k];
+				so[k] = ((1.0f - so[k]) * opa[k]) + so[k];
+			}
+		}
+		if(opa[0] >= f.zthr[0] && opa[1] >= f.zthr[1] && opa[2] >= f.zthr[2]) opaqueDepth0 = depth;
+	}
+	// One walk over the sample's list collects up to DEEP_SORT entries into a register-resident,
+	// descending (depth, submission) order -- the pointer chase through the pool is paid once;
+	// longer lists fall back to repeated selection of the farthest not yet composited entry.
+	constexpr int DEEP_SORT = 8;
+	unsigned long long ks[DEEP_SORT];
+	uint32_t sl[DEEP_SORT];
+#pragma unroll
+	for(int j = 0; j < DEEP_SORT; ++j) { ks[j] = 0ull; sl[j] = 0xffffffffu; }
+	int nList = 0;
+	for(uint32_t e = head; e != 0xffffffffu; )
+	{
+		const uint4 A = dc.A[e];
+		unsigned long long k = ((unsigned long long)depthKey(__uint_as_float(A.y)) << 32) | A.z;
+		uint32_t ce = e;
+#pragma unroll
+		for(int j = 0; j < DEEP_SORT; ++j)
+		{
+			// strict '>' keeps equal keys (a hit stored twice on a time sub-bound boundary) both in the list
+			if(k > ks[j] || (sl[j] == 0xffffffffu && ce != 0xffffffffu))
+			{
+				const unsigned long long tk = ks[j]; const uint32_t ts = sl[j];
+				ks[j] = k; sl[j] = ce; k = tk; ce = ts;
+			}
+		}
+		++nList;
+		e = A.x;
+	}
+	unsigned long long prev = ~0ull;
+	for(int step = 0; ; ++step)
+	{
+		uint32_t bestSlot = 0xffffffffu;
+		if(nList <= DEEP_SORT)
+		{
+			if(step >= nList) break;
+#pragma unroll
+			for(int j = 0; j < DEEP_SORT; ++j) if(j == step) bestSlot = sl[j];
+		}
+		else
+		{
+			// farthest not yet composited entry: largest (depthKey, p) strictly below prev
+			unsigned long long best = 0;
+			for(uint32_t e = head; e != 0xffffffffu; )
+			{
+				const uint4 A = dc.A[e];
+				unsigned long long k = ((unsigned long long)depthKey(__uint_as_float(A.y)) << 32) | A.z;
+				if(k < prev && (bestSlot == 0xffffffffu || k > best)) { best = k; bestSlot = e; }
+				e = A.x;
+			}
+			if(bestSlot == 0xffffffffu) break;
+			prev = best;
+		}
+		const uint4 A = dc.A[bestSlot];
+		const float2 uv = dc.UV[bestSlot];
+		const float4 a = f.P4[A.z];
+		const GridRec g = f.grids[infoOf(a) & VINFO_GRID_MASK];
+		float c2[3], o2[3];
+		shadeHit(f, g, A.z, uv, c2, o2);
+		const float d2 = __uint_as_float(A.y);
+		if(g.flags & AQH_GRID_MATTE)
+		{
+#pragma unroll
+			for(int k = 0; k < 3; ++k) { sc[k] = (1.f-o2[k])*sc[k] + o2[k]*0.0f; so[k] = (1.f-c2[k])*so[k] + c2[k]*0.0f; }
+		}
+		else
+		{
+#pragma unroll
+			for(int k = 0; k < 3; ++k)
+			{
+				sc[k] = (sc[k] * (1.0f - fminf(fmaxf(o2[k], 0.0f), 1.0f))) + c2[k];
+				so[k] = ((1.0f - so[k]) * o2[k]) + so[k];
+			}
+		}
+		if(o2[0] >= f.zthr[0] && o2[1] >= f.zthr[1] && o2[2] >= f.zthr[2]) opaqueDepth0 = d2;
+	}
+	valid = true;
+	out[0] = sc[0]; out[1] = sc[1]; out[2] = sc[2]; out[3] = so[0]; out[4] = so[1]; out[5] = so[2];
+	out[6] = opaqueDepth0;
+}
+
+template<bool MBDOF>
+__device__ void resolveSampleGeneral(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, int idx,
+                              float out[7], bool& valid)
+{
+	// keys[nsP + idx]: nearest opaque hit; keys[idx]: the occlusion depth occlZ (the same array unless the midpoint depth
 	// filter keeps the SECOND nearest opaque depth there, bucketprocessor.cpp:1502-1529)
-	const unsigned long long key = s.near[idx];
+	const unsigned long long key = s.keys[idx + (f.midpointZ ? s.nsP : 0)];
 	const float occlZ = keyDepth((uint32_t)(s.keys[idx] >> 32));
 	const uint32_t p = (uint32_t)key;
 	const bool haveOpaque = (p != 0xffffffffu);
@@ -1473,6 +1604,16 @@ __device__ void resolveSample(const DevFrame& f, const TileCtx& t, const HideSme
 	out[6] = zout;
 }
 
+// Depth filter "min" without the midpoint bookkeeping is the common case and keeps its own lean code; every
+// other depth filter goes through the general restatement of CqImagePixel::Combine above.
+template<bool MBDOF, bool DFGEN>
+__device__ __forceinline__ void resolveSample(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, int idx,
+                                              float out[7], bool& valid)
+{
+	if(!DFGEN) resolveSampleMin<MBDOF>(f, t, s, dc, idx, out, valid);
+	else resolveSampleGeneral<MBDOF>(f, t, s, dc, idx, out, valid);
+}
+
 // Per-tap inclusion bits of one sample (bucketprocessor.cpp:609-612), evaluated with the true
 // pixel coordinates: the sample of pixel (X,Y) belongs to filter tap (fx,fy) of output pixel
 // (X-fx, Y-fy).  Bits 0-14: x taps, 15-29: y taps, 31: the sample holds a valid hit.
@@ -1516,7 +1657,8 @@ __device__ __forceinline__ uint32_t loadMask(const DevFrame& f, size_t at)
 // pipeline -- grab RECS_PER_WARP micropolygons of the tile's bin, set them up (one lane each,
 // records in the warp's shared-memory slots), then sample them one after the other with all 32
 // lanes -- so there is no CTA-wide barrier inside the micropolygon loop.
-template<bool MBDOF, int THREADS, bool PARTIALS>
+// DFGEN: a depth filter other than "min" (kept out of the common kernels: its bookkeeping costs registers)
+template<bool MBDOF, int THREADS, bool PARTIALS, bool DFGEN>
 __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevFrame f)
 {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -1557,7 +1699,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 		for(int idx = tid; idx < s.nsP; idx += THREADS)
 		{
 			s.keys[idx] = KEY_EMPTY;
-			if(s.near != s.keys) s.near[idx] = KEY_EMPTY;
+			if(f.midpointZ) s.keys[s.nsP + idx] = KEY_EMPTY;
 			if(s.head) s.head[idx] = 0xffffffffu;
 			s.posx[idx] = -1e30f;
 			s.posy[idx] = -1e30f;
@@ -1636,10 +1778,15 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 				const int cnt = min(GRAB, binCnt - base);
 				if(base >= GRAB*NWARPS && ((base / GRAB) & (MBDOF ? 0u : 3u)) == 0 && *(volatile uint32_t*)s.dirty)
 				{
-					if(lane == 0) *(volatile uint32_t*)s.dirty = 0;
-					__syncwarp();
-					refreshPixZ(f, t, s, lane);
-					__syncwarp();
+					// exactly one warp takes the refresh (the others would only repeat it)
+					uint32_t mine = 0;
+					if(lane == 0) mine = atomicExch(s.dirty, 0u);
+					mine = __shfl_sync(0xffffffffu, mine, 0);
+					if(mine)
+					{
+						refreshPixZ(f, t, s, lane);
+						__syncwarp();
+					}
 				}
 				{
 					const uint32_t zfirst = (uint32_t)(f.binEntries[binBeg + base] >> 32);
@@ -1701,7 +1848,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 					if(i >= n) { storeMask(f, at, 0u); continue; }       // padding slot: never included
 					const int idx = sampleIdx(f, s, lx, ly, i);
 					float out[7]; bool valid;
-					resolveSample<MBDOF>(f, t, s, dc, idx, out, valid);
+					resolveSample<MBDOF, DFGEN>(f, t, s, dc, idx, out, valid);
 					storeMask(f, at, packMask(f, tapMask(f, s.posx[idx], s.posy[idx], X, Y, valid)));
 					if(valid)
 					{
@@ -1731,7 +1878,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 					{
 						const int idx = sampleIdx(f, s, lx, ly, i);
 						float out[7]; bool valid;
-						resolveSample<MBDOF>(f, t, s, dc, idx, out, valid);
+						resolveSample<MBDOF, DFGEN>(f, t, s, dc, idx, out, valid);
 						const uint32_t m = tapMask(f, s.posx[idx], s.posy[idx], X, Y, valid);
 						if(!valid) { out[0] = out[1] = out[2] = out[3] = out[4] = out[5] = out[6] = 0.f; }
 						scratch[2*lane] = make_float4(out[0], out[1], out[2], out[3]);
@@ -2184,19 +2331,19 @@ cudaError_t launchBinFill(const DevFrame& f, cudaStream_t st)
 	return cudaGetLastError();
 }
 
-template<bool MBDOF, int THREADS, bool PARTIALS>
+template<bool MBDOF, int THREADS, bool PARTIALS, bool DFGEN>
 static cudaError_t configHide(const DevFrame& f, int smCount, LaunchCfg& cfg)
 {
 	cfg.hideThreads = THREADS;
 	cfg.batchMPs = (THREADS/32)*RECS_PER_WARP;
 	cfg.hideSmemBytes = hideSmemBytes(f, cfg.batchMPs, MBDOF ? (THREADS/32)*sizeof(MovScratch) : 0);
 	if(cfg.hideSmemBytes > 227*1024) return cudaErrorInvalidValue;
-	cudaError_t e = cudaFuncSetAttribute(k_hide<MBDOF, THREADS, PARTIALS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.hideSmemBytes);
+	cudaError_t e = cudaFuncSetAttribute(k_hide<MBDOF, THREADS, PARTIALS, DFGEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.hideSmemBytes);
 	if(e != cudaSuccess) return e;
-	e = cudaFuncSetAttribute(k_hide<MBDOF, THREADS, PARTIALS>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+	e = cudaFuncSetAttribute(k_hide<MBDOF, THREADS, PARTIALS, DFGEN>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
 	if(e != cudaSuccess) return e;
 	int perSm = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_hide<MBDOF, THREADS, PARTIALS>, THREADS, cfg.hideSmemBytes);
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_hide<MBDOF, THREADS, PARTIALS, DFGEN>, THREADS, cfg.hideSmemBytes);
 	if(e != cudaSuccess) return e;
 	if(perSm < 1) perSm = 1;
 	cfg.hideCtas = smCount * perSm;
@@ -2208,8 +2355,11 @@ cudaError_t hideKernelConfig(const DevFrame& f, int smCount, LaunchCfg& cfg)
 	cfg.smCount = smCount;
 	const bool mbdof = f.useDof || f.anyMotion;
 	const bool partials = f.filterMode != AQH_FILTER_REFERENCE_ORDER;
-	if(mbdof) return partials ? configHide<true, 256, true>(f, smCount, cfg) : configHide<true, 256, false>(f, smCount, cfg);
-	return partials ? configHide<false, 512, true>(f, smCount, cfg) : configHide<false, 512, false>(f, smCount, cfg);
+	const bool dfgen = f.depthFilter != AQH_DEPTHFILTER_MIN;
+#define AQH_CFG(MB, TH) (partials ? (dfgen ? configHide<MB, TH, true, true>(f, smCount, cfg) : configHide<MB, TH, true, false>(f, smCount, cfg)) \
+                                  : (dfgen ? configHide<MB, TH, false, true>(f, smCount, cfg) : configHide<MB, TH, false, false>(f, smCount, cfg)))
+	return mbdof ? AQH_CFG(true, 256) : AQH_CFG(false, 512);
+#undef AQH_CFG
 }
 
 cudaError_t launchHide(const DevFrame& f, const LaunchCfg& cfg, cudaStream_t st)
@@ -2217,16 +2367,13 @@ cudaError_t launchHide(const DevFrame& f, const LaunchCfg& cfg, cudaStream_t st)
 	if(f.nActiveTiles == 0) return cudaSuccess;
 	const bool mbdof = f.useDof || f.anyMotion;
 	const bool partials = f.filterMode != AQH_FILTER_REFERENCE_ORDER;
-	if(mbdof)
-	{
-		if(partials) k_hide<true, 256, true><<<cfg.hideCtas, 256, cfg.hideSmemBytes, st>>>(f);
-		else k_hide<true, 256, false><<<cfg.hideCtas, 256, cfg.hideSmemBytes, st>>>(f);
-	}
-	else
-	{
-		if(partials) k_hide<false, 512, true><<<cfg.hideCtas, 512, cfg.hideSmemBytes, st>>>(f);
-		else k_hide<false, 512, false><<<cfg.hideCtas, 512, cfg.hideSmemBytes, st>>>(f);
-	}
+	const bool dfgen = f.depthFilter != AQH_DEPTHFILTER_MIN;
+#define AQH_LAUNCH(MB, TH, PA, DF) k_hide<MB, TH, PA, DF><<<cfg.hideCtas, TH, cfg.hideSmemBytes, st>>>(f)
+#define AQH_LAUNCH2(MB, TH) do { if(partials) { if(dfgen) AQH_LAUNCH(MB, TH, true, true); else AQH_LAUNCH(MB, TH, true, false); } \
+                                 else { if(dfgen) AQH_LAUNCH(MB, TH, false, true); else AQH_LAUNCH(MB, TH, false, false); } } while(0)
+	if(mbdof) AQH_LAUNCH2(true, 256); else AQH_LAUNCH2(false, 512);
+#undef AQH_LAUNCH2
+#undef AQH_LAUNCH
 	return cudaGetLastError();
 }
 
