@@ -144,6 +144,9 @@ struct AqhHider
 	int dispType[AQH_MAX_DISPLAYS] = {0}, dispEntry[AQH_MAX_DISPLAYS] = {0};
 	bool haveHostImage = false;
 	cudaEvent_t ev[8] = {nullptr};
+	// pipelined upload: host grids travel in chunks on copyStream while the main stream projects/bins the previous chunk
+	cudaStream_t copyStream = nullptr;
+	std::vector<cudaEvent_t> chunkEv;
 	AqhFrameStats stats{};
 
 	int fail(int status, const std::string& msg) { lastError = msg; return status; }
@@ -461,6 +464,16 @@ int renderFrame(AqhHider* h, bool download)
 	tr.mark("allocations");
 	// ---- grids into HBM
 	const float* dP = nullptr; const float* dCi = nullptr; const float* dOi = nullptr; const uint8_t* dCulled = nullptr;
+	// Pipelined upload (large frames handed over in host memory): the bulk arrays go up in chunks of whole grids
+	// on a second stream; each chunk is projected and bin-counted while the next one is on the bus.
+	struct UploadChunk { const float* P; const float* Ci; const float* Oi; const uint8_t* culled; int64_t p0, p1, v0, v1; };
+	std::vector<UploadChunk> plan;
+	// AQH_PIPELINE_MIN_POS: smallest frame (grid positions) that takes this route (default 2^20; tests force 1; a huge value disables it)
+	size_t pipeMin = size_t(1) << 20;
+	if(const char* e = std::getenv("AQH_PIPELINE_MIN_POS")) pipeMin = (size_t)std::strtoull(e, nullptr, 10);
+	bool pipelined = h->copyStream != nullptr && nPos >= std::max<size_t>(pipeMin, 1);
+	for(const Segment& s : h->segments)
+		if(s.memorySpace != 0 || (h->anyCi && !s.Ci) || (h->anyOi && !s.Oi)) pipelined = false;
 	const bool zeroCopy = h->segments.size() == 1 && h->segments[0].memorySpace == 1;
 	if(zeroCopy)
 	{
@@ -478,6 +491,7 @@ int renderFrame(AqhHider* h, bool download)
 		size_t po = 0, vo = 0;
 		for(const Segment& s : h->segments)
 		{
+			if(pipelined) break;
 			const float* sP = s.P; const float* sCi = s.Ci; const float* sOi = s.Oi; const uint8_t* sCu = s.culled;
 			if(s.staged)
 			{
@@ -514,6 +528,39 @@ int renderFrame(AqhHider* h, bool download)
 				if(!s.memorySpace) S.h2d_bytes += s.nVerts;
 			}
 			po += s.nPos; vo += s.nVerts;
+		}
+		if(pipelined)
+		{
+			const int64_t target = std::max<int64_t>(int64_t(nPos)/12, pipeMin < 4096 ? 64 : (int64_t(1) << 19));     // ~12 chunks per frame
+			int64_t g = 0, ppos = 0, vpos = 0;
+			for(const Segment& sg : h->segments)
+			{
+				const float* sP = sg.P; const float* sCi = sg.Ci; const float* sOi = sg.Oi; const uint8_t* sCu = sg.culled;
+				if(sg.staged)
+				{
+					sP = h->stP.as<float>() + (size_t)(uintptr_t)sg.P;
+					sCi = h->stCi.as<float>() + (size_t)(uintptr_t)sg.Ci;
+					sOi = h->stOi.as<float>() + (size_t)(uintptr_t)sg.Oi;
+					sCu = sg.culled ? h->stCulled.as<uint8_t>() + ((size_t)(uintptr_t)sg.culled - 1) : nullptr;
+				}
+				const int64_t segP0 = ppos, segV0 = vpos, gEnd = g + sg.nGrids;
+				while(g < gEnd)
+				{
+					UploadChunk c{};
+					c.p0 = ppos; c.v0 = vpos;
+					while(g < gEnd && ppos - c.p0 < target)
+					{
+						const int64_t nv = int64_t(h->gcu[g]+1)*(h->gcv[g]+1);
+						ppos += nv*h->gnkeys[g]; vpos += nv; ++g;
+					}
+					c.p1 = ppos; c.v1 = vpos;
+					c.P = sP + (c.p0 - segP0)*3;
+					c.Ci = sCi ? sCi + (c.v0 - segV0)*3 : nullptr;
+					c.Oi = sOi ? sOi + (c.v0 - segV0)*3 : nullptr;
+					c.culled = sCu ? sCu + (c.v0 - segV0) : nullptr;
+					plan.push_back(c);
+				}
+			}
 		}
 		dP = h->dPraw.as<float>();
 		dCi = h->anyCi ? h->dCi.as<float>() : nullptr;
@@ -587,8 +634,35 @@ int renderFrame(AqhHider* h, bool download)
 	CU(cudaMemsetAsync(h->dChannels.p, 0, size_t(p.xres)*p.yres*9*4, st), "cudaMemsetAsync");
 	for(int d = 0; d < p.n_displays; ++d)
 		CU(cudaMemsetAsync(h->dDisplay[d].p, 0, size_t(p.xres)*p.yres*disp.d[d].entrySize, st), "cudaMemsetAsync");
-	CU(launchProject(f, st), "k_project"); S.gpu_launches += nPos ? 2 : 0;
-	CU(launchBinCount(f, st), "k_bin<count>"); S.gpu_launches += nPos ? 1 : 0;
+	if(pipelined && !plan.empty())
+	{
+		while(h->chunkEv.size() < plan.size() + 1)
+		{
+			cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+			h->chunkEv.push_back(e);
+		}
+		// the copies must not overtake the memsets / table uploads queued above
+		CU(cudaEventRecord(h->chunkEv[plan.size()], st), "cudaEventRecord");
+		CU(cudaStreamWaitEvent(h->copyStream, h->chunkEv[plan.size()], 0), "cudaStreamWaitEvent");
+		for(size_t c = 0; c < plan.size(); ++c)
+		{
+			const UploadChunk& u = plan[c];
+			CU(cudaMemcpyAsync(h->dPraw.as<float>() + u.p0*3, u.P, size_t(u.p1 - u.p0)*12, cudaMemcpyHostToDevice, h->copyStream), "cudaMemcpyAsync(P)");
+			S.h2d_bytes += (u.p1 - u.p0)*12;
+			if(u.Ci) { CU(cudaMemcpyAsync(h->dCi.as<float>() + u.v0*3, u.Ci, size_t(u.v1 - u.v0)*12, cudaMemcpyHostToDevice, h->copyStream), "cudaMemcpyAsync(Ci)"); S.h2d_bytes += (u.v1 - u.v0)*12; }
+			if(u.Oi) { CU(cudaMemcpyAsync(h->dOi.as<float>() + u.v0*3, u.Oi, size_t(u.v1 - u.v0)*12, cudaMemcpyHostToDevice, h->copyStream), "cudaMemcpyAsync(Oi)"); S.h2d_bytes += (u.v1 - u.v0)*12; }
+			if(u.culled) { CU(cudaMemcpyAsync(h->dCulled.as<uint8_t>() + u.v0, u.culled, size_t(u.v1 - u.v0), cudaMemcpyHostToDevice, h->copyStream), "cudaMemcpyAsync(culled)"); S.h2d_bytes += (u.v1 - u.v0); }
+			CU(cudaEventRecord(h->chunkEv[c], h->copyStream), "cudaEventRecord");
+			CU(cudaStreamWaitEvent(st, h->chunkEv[c], 0), "cudaStreamWaitEvent");
+			CU(launchProjectCount(f, u.p0, u.p1, st), "k_project / k_bin<count>"); S.gpu_launches += 2;
+		}
+		CU(launchSplitLines(f, st), "k_splitlines"); S.gpu_launches += 1;
+	}
+	else
+	{
+		CU(launchProjectCount(f, 0, f.nPos, st), "k_project / k_bin<count>"); S.gpu_launches += nPos ? 2 : 0;
+		CU(launchSplitLines(f, st), "k_splitlines"); S.gpu_launches += nGrids ? 1 : 0;
+	}
 	CU(launchBinScan(f, st), "k_bin_scan"); S.gpu_launches += 1;
 	// the fill pass needs the total entry count to size the list
 	uint32_t totalEntries = 0, devFlags = 0;
@@ -688,6 +762,7 @@ int aqh_create(AqhHider** out, int device)
 	if(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return AQH_ERR_CUDA; }
 	h->ownStream = true;
 	for(int i = 0; i < 8; ++i) cudaEventCreate(&h->ev[i]);
+	if(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking) != cudaSuccess) h->copyStream = nullptr;
 	*out = h;
 	return AQH_OK;
 }
@@ -705,6 +780,8 @@ int aqh_destroy(AqhHider* h)
 	for(int d = 0; d < AQH_MAX_DISPLAYS; ++d) { h->dDisplay[d].release(); h->hDisplay[d].release(); }
 	h->hChannels.release(); h->stP.release(); h->stCi.release(); h->stOi.release(); h->stCulled.release();
 	for(int i = 0; i < 8; ++i) if(h->ev[i]) cudaEventDestroy(h->ev[i]);
+	for(cudaEvent_t e : h->chunkEv) cudaEventDestroy(e);
+	if(h->copyStream) cudaStreamDestroy(h->copyStream);
 	if(h->ownStream && h->stream) cudaStreamDestroy(h->stream);
 	delete h;
 	return AQH_OK;

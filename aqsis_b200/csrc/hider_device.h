@@ -136,8 +136,8 @@ struct LaunchCfg
 };
 
 // kernel launchers (hider_kernels.cu); all asynchronous on `st`.
-cudaError_t launchProject(const DevFrame& f, cudaStream_t st);
-cudaError_t launchBinCount(const DevFrame& f, cudaStream_t st);
+cudaError_t launchProjectCount(const DevFrame& f, int64_t pA, int64_t pB, cudaStream_t st);
+cudaError_t launchSplitLines(const DevFrame& f, cudaStream_t st);
 cudaError_t launchBinScan(const DevFrame& f, cudaStream_t st);
 cudaError_t launchBinFill(const DevFrame& f, cudaStream_t st);
 cudaError_t launchHide(const DevFrame& f, const LaunchCfg& cfg, cudaStream_t st);

@@ -79,12 +79,12 @@ __device__ __forceinline__ uint32_t infoOf(const float4& v) { return __float_as_
 
 // ------------------------------------------------------------------------------------
 // k_project: one thread per position.
-__global__ void __launch_bounds__(256) k_project(DevFrame f)
+__global__ void __launch_bounds__(256) k_project(DevFrame f, int64_t pA, int64_t pB)
 {
-	const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-	if(i >= f.nPos) return;
-	// locate the grid: bounded binary search between the grids of this and the next chunk
-	uint32_t lo = f.chunkGrid[blockIdx.x], hi = f.chunkGrid[blockIdx.x + 1];
+	const int64_t i = pA + (int64_t)blockIdx.x * 256 + threadIdx.x;
+	if(i >= pB) return;
+	// locate the grid: bounded binary search between the grids of this and the next 256-position chunk
+	uint32_t lo = f.chunkGrid[i >> 8], hi = f.chunkGrid[(i >> 8) + 1];
 	while(lo < hi)
 	{
 		uint32_t mid = (lo + hi + 1) >> 1;
@@ -195,12 +195,12 @@ __device__ __forceinline__ bool mpTileRange(const DevFrame& f, int64_t p, const 
 }
 
 template<bool FILL>
-__global__ void __launch_bounds__(256) k_bin(DevFrame f)
+__global__ void __launch_bounds__(256) k_bin(DevFrame f, int64_t pA, int64_t pB)
 {
-	const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+	const int64_t p = pA + (int64_t)blockIdx.x * 256 + threadIdx.x;
 	TileRange tr;
 	uint32_t zminKey = 0;
-	bool live = p < f.nPos;
+	bool live = p < pB;
 	if(live)
 	{
 		const float4 a = f.P4[p];
@@ -2292,18 +2292,20 @@ __global__ void __launch_bounds__(256) k_filter_partials(DevFrame f, DevDisplays
 
 // ------------------------------------------------------------------------------------
 // launchers
-cudaError_t launchProject(const DevFrame& f, cudaStream_t st)
+// Project + count the bin entries of the positions [pA, pB) (whole grids): the two steps that only need
+// the grids uploaded so far, so that they can run while the next chunk of the frame is still on the bus.
+cudaError_t launchProjectCount(const DevFrame& f, int64_t pA, int64_t pB, cudaStream_t st)
 {
-	if(f.nPos == 0) return cudaSuccess;
-	const unsigned blocks = (unsigned)((f.nPos + 255) / 256);
-	k_project<<<blocks, 256, 0, st>>>(f);
-	k_splitlines<<<(f.nGrids + 127)/128, 128, 0, st>>>(f);
+	if(pB <= pA) return cudaSuccess;
+	const unsigned blocks = (unsigned)((pB - pA + 255) / 256);
+	k_project<<<blocks, 256, 0, st>>>(f, pA, pB);
+	k_bin<false><<<blocks, 256, 0, st>>>(f, pA, pB);
 	return cudaGetLastError();
 }
-cudaError_t launchBinCount(const DevFrame& f, cudaStream_t st)
+cudaError_t launchSplitLines(const DevFrame& f, cudaStream_t st)
 {
-	if(f.nPos == 0) return cudaSuccess;
-	k_bin<false><<<(unsigned)((f.nPos + 255)/256), 256, 0, st>>>(f);
+	if(f.nGrids == 0) return cudaSuccess;
+	k_splitlines<<<(f.nGrids + 127)/128, 128, 0, st>>>(f);
 	return cudaGetLastError();
 }
 cudaError_t launchBinScan(const DevFrame& f, cudaStream_t st)
@@ -2314,7 +2316,7 @@ cudaError_t launchBinScan(const DevFrame& f, cudaStream_t st)
 cudaError_t launchBinFill(const DevFrame& f, cudaStream_t st)
 {
 	if(f.nPos)
-		k_bin<true><<<(unsigned)((f.nPos + 255)/256), 256, 0, st>>>(f);
+		k_bin<true><<<(unsigned)((f.nPos + 255)/256), 256, 0, st>>>(f, 0, f.nPos);
 	if(f.nActiveTiles)
 	{
 		static bool attr = false;

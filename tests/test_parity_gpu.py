@@ -113,6 +113,23 @@ def test_depth_filters(gpu_hider, dfilter, dmode):
         check(gpu_hider, p, g, EXACT)
 
 
+def test_pipelined_upload_is_the_same_image(gpu_hider, monkeypatch):
+    """Large host-memory frames are uploaded in chunks of whole grids on a second stream while the previous chunk is
+    projected and bin-counted (hider_api.cpp); forced here on small frames: same bits as the one-piece upload."""
+    for make in (lambda: scenes.config1(scale=0.2), lambda: scenes.config3(scale=0.04, motion_px=6.0), lambda: scenes.config4(scale=0.015)):
+        p, g = make()
+        rng = np.random.default_rng(11)
+        g.culled = (rng.uniform(size=g.n_verts) < 0.05).astype(np.uint8)
+        monkeypatch.setenv("AQH_PIPELINE_MIN_POS", str(1 << 40))
+        ch_a, disp_a, st_a = pu.run_product(gpu_hider, p, g)
+        monkeypatch.setenv("AQH_PIPELINE_MIN_POS", "1")
+        ch_b, disp_b, st_b = pu.run_product(gpu_hider, p, g)
+        assert st_b["gpu_launches"] > st_a["gpu_launches"]          # several project/count launches
+        assert np.array_equal(ch_a.view(np.uint32), ch_b.view(np.uint32)) and np.array_equal(disp_a[0], disp_b[0])
+        ch_c, disp_c, _ = pu.run_product(gpu_hider, p, g, use_block=False)   # staged aqh_add_grid route, pipelined too
+        assert np.array_equal(ch_a.view(np.uint32), ch_c.view(np.uint32))
+
+
 def test_empty_frame(gpu_hider):
     p = default_params(resolution=(40, 24), samples=(2, 2), displays=[("rgba", 1, 255.0, 0.0, 255.0, 0.5)])
     gpu_hider.begin_frame(p)
