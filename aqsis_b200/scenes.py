@@ -131,11 +131,17 @@ def config3(scale=1.0, seed=SEED + 1, motion_px=16.0, fstop=2.8, focallength=0.0
     return params, _pack(P, Ci, Oi, 16, 16, P2=P2, key_times=(0.0, 1.0))
 
 
-def config4(scale=1.0, seed=SEED + 3, layers=4):
-    """3840x2160, PixelSamples 16 16, ShadingRate 0.25, semi-transparent layered surfaces."""
+def config4(scale=1.0, seed=SEED + 3, layers=4, shard=None):
+    """3840x2160, PixelSamples 16 16, ShadingRate 0.25, semi-transparent layered surfaces.
+
+    shard: optional callable(params, block) -> block applied to every layer as it is generated (multi-GPU bench:
+    a rank keeps only the grids that touch its strips, so that N ranks on one box never hold N full 5.4 GB scenes).
+    The returned GridArrays then carries the totals of the WHOLE scene in .total_micropolygons / .total_vbytes."""
     xres, yres = max(16, int(3840 * scale)), max(16, int(2160 * scale))
     rng = np.random.default_rng(seed)
     blocks = []
+    total_mps = total_vbytes = 0
+    params = default_params(resolution=(xres, yres), samples=(16, 16), filter=("gaussian", 2.0, 2.0), displays=[_RGBA8])
     opac = [0.25, 0.5, 0.75]
     gx, gy = (xres + 7) // 8 + 1, (yres + 7) // 8 + 1       # 16x16-MP grids of 8x8 px => MP area 0.25 px^2
     for layer in range(layers):
@@ -144,9 +150,13 @@ def config4(scale=1.0, seed=SEED + 3, layers=4):
         z0 = 10.0 + 10.0 * layer
         o = None if layer == layers - 1 else np.full(gx * gy, opac[layer % 3], dtype=np.float32)
         P, Ci, Oi = _grids(rng, centers, 9.0, 16, 16, z0, z0 + 5.0, warp=0.05, noise=0.01, opacity=o, rot=False)
-        blocks.append(_pack(P, Ci, Oi, 16, 16))
-    params = default_params(resolution=(xres, yres), samples=(16, 16), filter=("gaussian", 2.0, 2.0), displays=[_RGBA8])
-    return params, concat(blocks)
+        b = _pack(P, Ci, Oi, 16, 16)
+        total_mps += b.n_micropolygons
+        total_vbytes += int(b.n_verts) * 36
+        blocks.append(shard(params, b) if shard else b)
+    out = concat(blocks)
+    out.total_micropolygons, out.total_vbytes = total_mps, total_vbytes
+    return params, out
 
 
 def config5_filters():

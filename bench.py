@@ -225,14 +225,26 @@ def main():
     if world > 1:
         dist.barrier()
 
-    params, grids = make_scene(args.config, args.scale)
-    params.rank, params.world_size, params.strip_rows = rank, world, args.strip_rows
-    n_mp_total = grids.n_micropolygons
+    if args.config == 4 and world > 1:
+        # the 5.4 GB scene is generated layer by layer and sharded on the fly: N ranks never hold N full copies
+        def shard(p, block):
+            p.rank, p.world_size, p.strip_rows = rank, world, args.strip_rows
+            return sharding.split_grids_for_rank(p, block, rank, world)
+        params, mine = scenes.config4(scale=args.scale, shard=shard)
+        params.rank, params.world_size, params.strip_rows = rank, world, args.strip_rows
+        n_mp_total = int(mine.total_micropolygons)
+        px_bytes = (params.crop_xmax - params.crop_xmin) * (params.crop_ymax - params.crop_ymin)
+        b_alg_total = int(mine.total_vbytes) + scenes.algorithmic_bytes(params, mine) - int(mine.n_verts) * 36
+        b_alg_mine = scenes.algorithmic_bytes(params, mine)
+    else:
+        params, grids = make_scene(args.config, args.scale)
+        params.rank, params.world_size, params.strip_rows = rank, world, args.strip_rows
+        n_mp_total = grids.n_micropolygons
+        b_alg_total = scenes.algorithmic_bytes(params, grids)
+        mine = sharding.split_grids_for_rank(params, grids, rank, world)
+        b_alg_mine = scenes.algorithmic_bytes(params, mine) if world > 1 else b_alg_total
+        del grids
     n_samples_total = (params.crop_xmax - params.crop_xmin) * (params.crop_ymax - params.crop_ymin) * params.xsamples * params.ysamples
-    b_alg_total = scenes.algorithmic_bytes(params, grids)
-    mine = sharding.split_grids_for_rank(params, grids, rank, world)
-    b_alg_mine = scenes.algorithmic_bytes(params, mine) if world > 1 else b_alg_total
-    del grids
 
     stream = torch.cuda.current_stream()
     h = Hider(local_rank, stream=stream.cuda_stream)
