@@ -1639,17 +1639,20 @@ __device__ __forceinline__ uint32_t packMask(const DevFrame& f, uint32_t m)
 	const int nx = 2*f.shiftX + 1, ny = 2*f.shiftY + 1;
 	return (m & ((1u << nx) - 1u)) | (((m >> 15) & ((1u << ny) - 1u)) << nx) | ((m >> 31) << (nx + ny));
 }
+// Stored INVERTED (a set bit = "not in this tap" / "no valid hit"), so that the filter's inclusion test is
+// a single AND-and-test-zero; padding slots hold all ones.
 __device__ __forceinline__ void storeMask(const DevFrame& f, size_t at, uint32_t compact)
 {
+	compact = ~compact;
 	if(f.maskBytes == 1) f.maskPlane[at] = (unsigned char)compact;
 	else if(f.maskBytes == 2) reinterpret_cast<uint16_t*>(f.maskPlane)[at] = (uint16_t)compact;
 	else reinterpret_cast<uint32_t*>(f.maskPlane)[at] = compact;
 }
 __device__ __forceinline__ uint32_t loadMask(const DevFrame& f, size_t at)
 {
-	if(f.maskBytes == 1) return f.maskPlane[at];
-	if(f.maskBytes == 2) return reinterpret_cast<const uint16_t*>(f.maskPlane)[at];
-	return reinterpret_cast<const uint32_t*>(f.maskPlane)[at];
+	if(f.maskBytes == 1) return (~(uint32_t)f.maskPlane[at]) & 0xffu;
+	if(f.maskBytes == 2) return (~(uint32_t)reinterpret_cast<const uint16_t*>(f.maskPlane)[at]) & 0xffffu;
+	return ~reinterpret_cast<const uint32_t*>(f.maskPlane)[at];
 }
 
 // ------------------------------------------------------------------------------------
@@ -1665,7 +1668,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 	__shared__ uint32_t s_tile;
 	__shared__ uint32_t s_deepCount;
 	__shared__ uint32_t s_next;
-	__shared__ uint32_t s_tileZ, s_dirty;
+	__shared__ uint32_t s_tileZ, s_dirty, s_lastRef;
 	constexpr int NWARPS = THREADS/32;
 	HideSmem s = carveSmem(f, smemRaw, NWARPS*RECS_PER_WARP, MBDOF ? NWARPS*sizeof(MovScratch) : 0);
 	MovScratch* ws = MBDOF ? reinterpret_cast<MovScratch*>(reinterpret_cast<unsigned char*>(s.mov) + (size_t)(threadIdx.x >> 5)*sizeof(MovScratch)) : nullptr;
@@ -1745,7 +1748,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 			if(lane == 0 && s.dof) s.shufPat[pix] = (uint8_t)patS;
 		}
 		for(int i = tid; i < f.tileW*f.tileH; i += THREADS) s.pixZ[i] = 0xffffffffu;
-		if(tid == 0) { s_tileZ = 0xffffffffu; s_dirty = 0; }
+		if(tid == 0) { s_tileZ = 0xffffffffu; s_dirty = 0; s_lastRef = 0; }
 		__syncthreads();
 		const uint32_t binBeg = f.binOffset[slot], binCnt = f.binOffset[slot+1] - binBeg;
 		const uint32_t tflags = f.tileFlags[slot];
@@ -1760,7 +1763,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 			{
 				if(!(f.anyTransparent && (tflags & 1u))) break;
 				__syncthreads();
-				if(tid == 0) { s_next = 0; s_dirty = 0; }
+				if(tid == 0) { s_next = 0; s_dirty = 0; s_lastRef = 0; }
 				if(warp == 0) refreshPixZ(f, t, s, lane);        // the opaque depths are final now
 				__syncthreads();
 			}
@@ -1776,16 +1779,23 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 				base = __shfl_sync(0xffffffffu, base, 0);
 				if(base >= binCnt) break;
 				const int cnt = min(GRAB, binCnt - base);
-				if(base >= GRAB*NWARPS && ((base / GRAB) & (MBDOF ? 0u : 3u)) == 0 && *(volatile uint32_t*)s.dirty)
+				// tile-wide pacing: one refresh per REFRESH_EVERY bin entries handed out (whichever warp crosses the
+				// mark takes it) -- 16 warps each refreshing on their own schedule spent 12 % of the kernel here
+				constexpr uint32_t REFRESH_EVERY = MBDOF ? 16u : 96u;
 				{
-					// exactly one warp takes the refresh (the others would only repeat it)
-					uint32_t mine = 0;
-					if(lane == 0) mine = atomicExch(s.dirty, 0u);
-					mine = __shfl_sync(0xffffffffu, mine, 0);
-					if(mine)
+					const uint32_t last = *(volatile uint32_t*)&s_lastRef;
+					if(base >= GRAB*NWARPS && base - last >= REFRESH_EVERY && *(volatile uint32_t*)s.dirty)
 					{
-						refreshPixZ(f, t, s, lane);
-						__syncwarp();
+						uint32_t mine = 0;
+						if(lane == 0) mine = (atomicCAS(&s_lastRef, last, base) == last) ? 1u : 0u;
+						mine = __shfl_sync(0xffffffffu, mine, 0);
+						if(mine)
+						{
+							if(lane == 0) *(volatile uint32_t*)s.dirty = 0;
+							__syncwarp();
+							refreshPixZ(f, t, s, lane);
+							__syncwarp();
+						}
 					}
 				}
 				{
@@ -2123,6 +2133,14 @@ __device__ __forceinline__ void bulkLoad(void* dst, const void* src, uint32_t by
 	             :: "r"(smemAddr(dst)), "l"(src), "r"(bytes), "r"(smemAddr(bar)) : "memory");
 }
 
+// ld.shared.v4: the compiler splits a float4 load from a runtime-strided shared address into two 8-byte
+// loads, which puts two pixels in one wavefront and makes the skewed planes collide.
+__device__ __forceinline__ float4 lds128(const float* p)
+{
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smemAddr(p)));
+	return v;
+}
 #define FILTER_W 32
 #define FILTER_ONES 128       /* floats of 1.0 read by channel 7 ("the weight total is the sum of 1.0*w") */
 __host__ __device__ __forceinline__ int filterSpan(const DevFrame& f)      // staged pixels per stage
@@ -2196,7 +2214,7 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(DevFrame f, DevDisp
 					const uint32_t need = (1u << fx) | (1u << (2*xmax + 1 + fy)) | validBit;
 					const float* w = c_filt + tap*n + c*SC;
 					const int o = (halo ? px + fx : px)*SC;
-					const float4* vp = reinterpret_cast<const float4*>((ch < 7) ? tile + (size_t)ch*planeS + o : ones + (o & 31));
+					const float* vp = (ch < 7) ? tile + (size_t)ch*planeS + o : ones + (o & 31);
 					if(MB == 1)
 					{
 						const uint32_t* mp = reinterpret_cast<const uint32_t*>(mbase + o);
@@ -2205,11 +2223,11 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(DevFrame f, DevDisp
 						for(int s4 = 0; s4 < SC/4; ++s4)
 						{
 							const uint32_t m = mp[s4];
-							const float4 v = vp[s4];
-							if((m & n0) == n0) { acc += v.x * w[4*s4+0]; ++count; }
-							if((m & n1) == n1) { acc += v.y * w[4*s4+1]; ++count; }
-							if((m & n2) == n2) { acc += v.z * w[4*s4+2]; ++count; }
-							if((m & n3) == n3) { acc += v.w * w[4*s4+3]; ++count; }
+							const float4 v = lds128(vp + 4*s4);
+							if((m & n0) == 0u) { acc += v.x * w[4*s4+0]; ++count; }
+							if((m & n1) == 0u) { acc += v.y * w[4*s4+1]; ++count; }
+							if((m & n2) == 0u) { acc += v.z * w[4*s4+2]; ++count; }
+							if((m & n3) == 0u) { acc += v.w * w[4*s4+3]; ++count; }
 						}
 					}
 					else if(MB == 2)
@@ -2220,11 +2238,11 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(DevFrame f, DevDisp
 						for(int s4 = 0; s4 < SC/4; ++s4)
 						{
 							const uint2 m = mp[s4];
-							const float4 v = vp[s4];
-							if((m.x & n0) == n0) { acc += v.x * w[4*s4+0]; ++count; }
-							if((m.x & n1) == n1) { acc += v.y * w[4*s4+1]; ++count; }
-							if((m.y & n0) == n0) { acc += v.z * w[4*s4+2]; ++count; }
-							if((m.y & n1) == n1) { acc += v.w * w[4*s4+3]; ++count; }
+							const float4 v = lds128(vp + 4*s4);
+							if((m.x & n0) == 0u) { acc += v.x * w[4*s4+0]; ++count; }
+							if((m.x & n1) == 0u) { acc += v.y * w[4*s4+1]; ++count; }
+							if((m.y & n0) == 0u) { acc += v.z * w[4*s4+2]; ++count; }
+							if((m.y & n1) == 0u) { acc += v.w * w[4*s4+3]; ++count; }
 						}
 					}
 					else
@@ -2234,11 +2252,11 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(DevFrame f, DevDisp
 						for(int s4 = 0; s4 < SC/4; ++s4)
 						{
 							const uint4 m = mp[s4];
-							const float4 v = vp[s4];
-							if((m.x & need) == need) { acc += v.x * w[4*s4+0]; ++count; }
-							if((m.y & need) == need) { acc += v.y * w[4*s4+1]; ++count; }
-							if((m.z & need) == need) { acc += v.z * w[4*s4+2]; ++count; }
-							if((m.w & need) == need) { acc += v.w * w[4*s4+3]; ++count; }
+							const float4 v = lds128(vp + 4*s4);
+							if((m.x & need) == 0u) { acc += v.x * w[4*s4+0]; ++count; }
+							if((m.y & need) == 0u) { acc += v.y * w[4*s4+1]; ++count; }
+							if((m.z & need) == 0u) { acc += v.z * w[4*s4+2]; ++count; }
+							if((m.w & need) == 0u) { acc += v.w * w[4*s4+3]; ++count; }
 						}
 					}
 				}
