@@ -1798,8 +1798,10 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 						}
 					}
 				}
+				// the grab's entries in one coalesced load (one lane each); the first one also decides the early out
+				const unsigned long long ent = (lane < cnt) ? f.binEntries[binBeg + base + lane] : 0ull;
 				{
-					const uint32_t zfirst = (uint32_t)(f.binEntries[binBeg + base] >> 32);
+					const uint32_t zfirst = __shfl_sync(0xffffffffu, (uint32_t)(ent >> 32), 0);
 					if(zfirst > *(volatile uint32_t*)s.tileZ)
 					{
 						const uint32_t runEnd = min(binCnt, (base / (uint32_t)f.sortRun + 1u)*(uint32_t)f.sortRun);
@@ -1812,7 +1814,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 #pragma unroll 1
 					for(int j = 0; j < cnt; ++j)
 					{
-						const uint32_t p = (uint32_t)f.binEntries[binBeg + base + j];
+						const uint32_t p = __shfl_sync(0xffffffffu, (uint32_t)ent, j);
 						const bool handled = renderMBOrDof(f, t, s, dc, ws, p, lane, pass == 0);
 						if(!handled)
 						{
@@ -1827,7 +1829,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 				}
 				else
 				{
-					if(lane < cnt) setupStaticRec(f, t, s, (uint32_t)f.binEntries[binBeg + base + lane], pass == 0, myRecs[lane]);
+					if(lane < cnt) setupStaticRec(f, t, s, (uint32_t)ent, pass == 0, myRecs[lane]);
 					__syncwarp();
 					for(int j = 0; j < cnt; ++j)
 					{
