@@ -126,3 +126,20 @@ def test_split_keeps_grid_payload_intact(native_lib):
         for y0, y1 in sharding.strips_for_rank(p, r):
             touched |= (hi >= y0) & (lo < y1)
         assert part.n_grids == int(touched.sum())
+
+
+def test_config4_streaming_shard_equals_post_hoc_shard():
+    """bench.py shards the 5.4 GB config-4 scene layer by layer while generating it (N ranks never hold N full
+    copies): same grids, in the same order, as sharding the finished scene."""
+    from aqsis_b200 import scenes, sharding
+    for rank in (0, 1, 2):
+        def shard(p, block, rank=rank):
+            p.rank, p.world_size = rank, 3
+            return sharding.split_grids_for_rank(p, block, rank, 3)
+        p_s, g_s = scenes.config4(scale=0.04, shard=shard)
+        p_f, g_f = scenes.config4(scale=0.04)
+        p_f.rank, p_f.world_size = rank, 3
+        m = sharding.split_grids_for_rank(p_f, g_f, rank, 3)
+        assert g_s.total_micropolygons == g_f.n_micropolygons
+        assert np.array_equal(np.asarray(g_s.P), np.asarray(m.P)) and np.array_equal(np.asarray(g_s.Oi), np.asarray(m.Oi))
+        assert np.array_equal(g_s.cu, m.cu) and g_s.n_micropolygons == m.n_micropolygons
