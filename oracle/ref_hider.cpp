@@ -35,6 +35,7 @@
 #include <aqsis/ri/ri.h>
 #include <aqsis/util/file.h>
 #include <aqsis/util/logging.h>
+#include <aqsis/util/logging_streambufs.h>
 #include <aqsis/shadervm/ishaderdata.h>
 #include <aqsis/shadervm/ishaderexecenv.h>
 
@@ -342,6 +343,9 @@ int ref_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* chann
 {
 	if(!pp || !grids || grids->memory_space != 0) return AQH_ERR_BAD_PARAMS;
 	const AqhFrameParams& p = *pp;
+	// like aqsis' own main(): only warnings and worse reach std::cerr (tools/aqsis/aqsis.cpp installs the same filter)
+	static Aqsis::filter_by_level_buf* quiet = new Aqsis::filter_by_level_buf(Aqsis::WARNING, std::cerr);
+	(void)quiet;
 	const double t0 = nowS();
 
 	// ---- render context and options (what RiCxxCore::WorldBegin leaves behind, ri.cpp:577-666)
