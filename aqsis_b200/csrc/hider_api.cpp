@@ -138,6 +138,7 @@ struct AqhHider
 	std::vector<uint32_t> activeTiles;
 	std::vector<uint8_t> rowOwned;
 	std::vector<std::pair<int,int>> strips;
+	std::string stripKey, hostStripKey;   // image geometry + row ownership of the device images / of what the host images hold
 	// outputs (host)
 	PinnedBuf hChannels;
 	PinnedBuf hDisplay[AQH_MAX_DISPLAYS];
@@ -318,6 +319,11 @@ void buildTiling(AqhHider* h, bool mbdof)
 	h->nty = (L.sh + h->tileH - 1)/h->tileH;
 	h->rowOwned.assign(p.yres, 0);
 	computeStrips(p, p.rank, h->strips);
+	{
+		char key[160];
+		std::snprintf(key, sizeof key, "%d %d %d %d %d %d", p.xres, p.yres, p.rank, p.world_size, p.strip_rows, p.n_displays);
+		h->stripKey = key;
+	}
 	std::vector<uint8_t> rowNeeded(L.sh, 0);
 	for(const auto& s : h->strips)
 	{
@@ -707,17 +713,35 @@ int renderFrame(AqhHider* h, bool download)
 	S.d2h_bytes = 0;
 	if(download)
 	{
-		const size_t chBytes = size_t(p.xres)*p.yres*9*4;
+		// Only the pixel rows this rank owns travel back (all of them on a single rank); the rest of the host
+		// images stays zero, like the device images.
+		const size_t chRow = size_t(p.xres)*9*4, chBytes = chRow*p.yres;
+		const bool sharded = std::max(1, p.world_size) > 1;
+		const bool firstCh = h->hChannels.cap < chBytes;
 		if(!h->hChannels.reserve(chBytes)) return h->fail(AQH_ERR_NO_MEMORY, "cudaHostAlloc(channel image)");
-		CU(cudaMemcpyAsync(h->hChannels.p, h->dChannels.p, chBytes, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(channels)");
-		S.d2h_bytes += (int64_t)chBytes;
+		if(sharded && (firstCh || h->hostStripKey != h->stripKey)) std::memset(h->hChannels.p, 0, chBytes);
+		std::vector<std::pair<int,int>> rows;
+		if(sharded) rows = h->strips; else rows.push_back(std::make_pair(0, p.yres));
+		for(const auto& r : rows)
+		{
+			CU(cudaMemcpyAsync(h->hChannels.as<unsigned char>() + chRow*r.first, h->dChannels.as<unsigned char>() + chRow*r.first,
+			                   chRow*size_t(r.second - r.first), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(channels)");
+			S.d2h_bytes += (int64_t)(chRow*size_t(r.second - r.first));
+		}
 		for(int d = 0; d < p.n_displays; ++d)
 		{
-			const size_t b = size_t(p.xres)*p.yres*disp.d[d].entrySize;
+			const size_t dRow = size_t(p.xres)*disp.d[d].entrySize, b = dRow*p.yres;
+			const bool firstD = h->hDisplay[d].cap < b;
 			if(!h->hDisplay[d].reserve(b)) return h->fail(AQH_ERR_NO_MEMORY, "cudaHostAlloc(display image)");
-			CU(cudaMemcpyAsync(h->hDisplay[d].p, h->dDisplay[d].p, b, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(display)");
-			S.d2h_bytes += (int64_t)b;
+			if(sharded && (firstD || h->hostStripKey != h->stripKey)) std::memset(h->hDisplay[d].p, 0, b);
+			for(const auto& r : rows)
+			{
+				CU(cudaMemcpyAsync(h->hDisplay[d].as<unsigned char>() + dRow*r.first, h->dDisplay[d].as<unsigned char>() + dRow*r.first,
+				                   dRow*size_t(r.second - r.first), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(display)");
+				S.d2h_bytes += (int64_t)(dRow*size_t(r.second - r.first));
+			}
 		}
+		h->hostStripKey = h->stripKey;
 	}
 	CU(cudaStreamSynchronize(st), "cudaStreamSynchronize(frame)");
 	S.download_ms = download ? nowMs() - tDown0 : 0.0;
@@ -1064,6 +1088,7 @@ int aqh_strip_layout(const AqhFrameParams* p, int rank, int* n_strips, int* y0, 
 	const int world = std::max(1, p->world_size);
 	if(rank < 0 || rank >= world) return AQH_ERR_BAD_PARAMS;
 	std::vector<std::pair<int,int>> strips;
+	std::string stripKey, hostStripKey;   // image geometry + row ownership of the device images / of what the host images hold
 	computeStrips(*p, rank, strips);
 	*n_strips = (int)strips.size();
 	for(int i = 0; i < (int)strips.size() && i < capacity; ++i)
