@@ -132,6 +132,9 @@ struct AqhHider
 	DevBuf dTileSlot, dActive, dBinCount, dBinOffset, dBinEntries, dMisc, dTileFlags;
 	DevBuf dPlanes, dMask, dPartials, dDeepA, dDeepUV, dChannels, dRowOwned;
 	DevBuf dDisplay[AQH_MAX_DISPLAYS];
+	DevBuf dOccl;
+	PinnedBuf hOccl;
+	bool haveOccl = false;
 	// tiling
 	int tileW = 0, tileH = 0, ntx = 0, nty = 0;
 	std::vector<int32_t> tileSlot;
@@ -366,7 +369,7 @@ struct FrameTrace
 	void mark(const char* what) { if(!on) return; const double t = nowMs(); std::fprintf(stderr, "[aqh] %-22s +%8.3f ms  (%8.3f)\n", what, t - last, t - t0); last = t; }
 };
 
-int renderFrame(AqhHider* h, bool download)
+int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 {
 	FrameTrace tr;
 	if(!h->inFrame) return h->fail(AQH_ERR_STATE, "no frame in progress");
@@ -630,6 +633,12 @@ int renderFrame(AqhHider* h, bool download)
 	{ const int mbits = 2*L.shiftX + 2*L.shiftY + 3; f.maskBytes = mbits <= 8 ? 1 : (mbits <= 16 ? 2 : 4); } f.planeStride = (int64_t)planeStride; f.planeW = planeW; f.planeSC = planeSC; f.planeChunks = planeChunks;
 	f.filterMode = p.filter_mode; f.partials = h->dPartials.as<float>(); f.ntaps = ntaps;
 	f.channels = h->dChannels.as<float>();
+	f.occlImage = nullptr; f.zOnly = zOnly ? 1 : 0;
+	if(zOnly)
+	{
+		CU(h->dOccl.reserve(size_t(p.xres)*p.yres*4), "cudaMalloc(occlusion image)");
+		f.occlImage = h->dOccl.as<float>();
+	}
 	f.rowOwned = (std::max(1, p.world_size) > 1) ? h->dRowOwned.as<uint8_t>() : nullptr;
 
 	// ---- device work
@@ -699,10 +708,17 @@ int renderFrame(AqhHider* h, bool download)
 	while(f.sortRun < (int)maxBin && f.sortRun < 8192) f.sortRun <<= 1;
 	CU(launchBinFill(f, st), "k_bin<fill>"); S.gpu_launches += (nPos ? 1 : 0) + (nActive ? 1 : 0) + ((nPos && nActive) ? 1 : 0);
 	CU(cudaEventRecord(h->ev[1], st), "cudaEventRecord");
+	if(zOnly)
+	{
+		// every pixel starts uncovered (FLT_MAX); tiles this rank does not hide stay that way
+		std::vector<float> inf(size_t(p.xres)*p.yres, FLT_MAX);
+		CU(cudaMemcpyAsync(h->dOccl.p, inf.data(), inf.size()*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(occlusion image)");
+		CU(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+	}
 	CU(launchHide(f, cfg, st), "k_hide"); S.gpu_launches += nActive ? 1 : 0;
 	CU(cudaEventRecord(h->ev[2], st), "cudaEventRecord");
 	tr.mark("launched hide");
-	CU(launchFilter(f, disp, h->filterTab.data(), st), "k_filter"); S.gpu_launches += 1;
+	if(!zOnly) { CU(launchFilter(f, disp, h->filterTab.data(), st), "k_filter"); S.gpu_launches += 1; }
 	CU(cudaEventRecord(h->ev[3], st), "cudaEventRecord");
 
 	// ---- results
@@ -743,10 +759,18 @@ int renderFrame(AqhHider* h, bool download)
 		}
 		h->hostStripKey = h->stripKey;
 	}
+	if(zOnly)
+	{
+		const size_t ob = size_t(p.xres)*p.yres*4;
+		if(!h->hOccl.reserve(ob)) return h->fail(AQH_ERR_NO_MEMORY, "cudaHostAlloc(occlusion image)");
+		CU(cudaMemcpyAsync(h->hOccl.p, h->dOccl.p, ob, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(occlusion image)");
+		S.d2h_bytes += (int64_t)ob;
+	}
 	CU(cudaStreamSynchronize(st), "cudaStreamSynchronize(frame)");
 	S.download_ms = download ? nowMs() - tDown0 : 0.0;
 	tr.mark("frame sync");
 	h->haveHostImage = download;
+	if(zOnly) h->haveOccl = true;
 	float ms = 0;
 	cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); S.project_bust_ms = ms;
 	cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); S.render_mpgs_ms = ms;
@@ -802,6 +826,7 @@ int aqh_destroy(AqhHider* h)
 	                  &h->dDeepA, &h->dDeepUV, &h->dChannels, &h->dRowOwned};
 	for(DevBuf* b : bufs) b->release();
 	for(int d = 0; d < AQH_MAX_DISPLAYS; ++d) { h->dDisplay[d].release(); h->hDisplay[d].release(); }
+	h->dOccl.release(); h->hOccl.release();
 	h->hChannels.release(); h->stP.release(); h->stCi.release(); h->stOi.release(); h->stCulled.release();
 	for(int i = 0; i < 8; ++i) if(h->ev[i]) cudaEventDestroy(h->ev[i]);
 	for(cudaEvent_t e : h->chunkEv) cudaEventDestroy(e);
@@ -901,7 +926,7 @@ int aqh_begin_frame(AqhHider* h, const AqhFrameParams* p)
 	if(rc) return rc;
 	h->stats.prepare_ms = nowMs() - t0;
 	resetFrameGrids(h);
-	h->inFrame = true; h->rendered = false; h->haveHostImage = false;
+	h->inFrame = true; h->rendered = false; h->haveHostImage = false; h->haveOccl = false;
 	return AQH_OK;
 }
 
@@ -989,6 +1014,37 @@ int aqh_render_device(AqhHider* h)
 	if(!h) return AQH_ERR_BAD_PARAMS;
 	if(cudaSetDevice(h->device) != cudaSuccess) return h->fail(AQH_ERR_NO_DEVICE, "cudaSetDevice failed");
 	return renderFrame(h, false);
+}
+
+int aqh_flush(AqhHider* h)
+{
+	if(!h) return AQH_ERR_BAD_PARAMS;
+	if(!h->inFrame) return h->fail(AQH_ERR_STATE, "aqh_flush outside aqh_begin_frame/aqh_end_frame");
+	if(cudaSetDevice(h->device) != cudaSuccess) return h->fail(AQH_ERR_NO_DEVICE, "cudaSetDevice failed");
+	return renderFrame(h, false, true);
+}
+
+int aqh_can_cull(const AqhHider* h, const float bound[6], int* culled)
+{
+	if(!h || !bound || !culled) return AQH_ERR_BAD_PARAMS;
+	*culled = 0;
+	if(!h->inFrame || !h->haveOccl) return AQH_OK;
+	const AqhFrameParams& p = h->params;
+	// RenderSurface never asks the tree in this mode (bucketprocessor.cpp:945-948)
+	if((p.display_mode & AQH_DMODE_Z) && (p.depth_filter == AQH_DEPTHFILTER_MAX || p.depth_filter == AQH_DEPTHFILTER_AVERAGE))
+		return AQH_OK;
+	const float xmin = bound[0], ymin = bound[1], zmin = bound[2], xmax = bound[3], ymax = bound[4];
+	if(!(xmin <= xmax) || !(ymin <= ymax)) return AQH_ERR_BAD_PARAMS;
+	// pixels the bound touches, inside the crop window (canCull crops to the tree's bound, occlusion.cpp:164-168)
+	const float fx0 = std::max(std::floor(xmin), (float)p.crop_xmin), fx1 = std::min(std::floor(xmax) + 1.0f, (float)p.crop_xmax);
+	const float fy0 = std::max(std::floor(ymin), (float)p.crop_ymin), fy1 = std::min(std::floor(ymax) + 1.0f, (float)p.crop_ymax);
+	if(!(fx0 < fx1) || !(fy0 < fy1)) { *culled = 1; return AQH_OK; }      // nothing of it can reach a sample
+	const float* occl = h->hOccl.as<float>();
+	for(int y = (int)fy0; y < (int)fy1; ++y)
+		for(int x = (int)fx0; x < (int)fx1; ++x)
+			if(!(occl[size_t(y)*p.xres + x] < zmin)) return AQH_OK;
+	*culled = 1;
+	return AQH_OK;
 }
 
 int aqh_end_frame(AqhHider* h, const AqhCallbacks* cb)

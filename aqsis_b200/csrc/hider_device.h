@@ -108,6 +108,10 @@ struct DevFrame
 	unsigned long long* counters;  // [0] MPs binned, [1] bin entries, [2] deep hits, [3] longest bin
 	// output
 	float* channels;               // xres*yres*9
+	// occlusion feedback (aqh_flush): per image pixel the farthest occlusion depth over the pixel's samples
+	// (FLT_MAX while any sample is uncovered); with zOnly the tile stops there -- no resolve, no filter input
+	float* occlImage;              // xres*yres or null
+	int zOnly;
 	const uint8_t* rowOwned;       // yres: 1 when this rank owns the pixel row
 };
 

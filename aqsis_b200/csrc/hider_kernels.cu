@@ -1842,6 +1842,21 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 		}
 		__syncthreads();
 		if(tid == 0 && s_deepCount) atomicAdd(&f.counters[2], (unsigned long long)min(s_deepCount, dc.cap));
+		// ---- occlusion feedback for the front end (CqOcclusionTree, occlusion.cpp:54-225, at pixel granularity)
+		if(f.occlImage)
+		{
+			if(warp == 0) refreshPixZ(f, t, s, lane);
+			__syncthreads();
+			const int tw0 = t.rx1 - t.rx0, th0 = t.ry1 - t.ry0;
+			for(int pix = tid; pix < tw0*th0; pix += THREADS)
+			{
+				const int ly = pix / tw0, lx = pix - ly*tw0;
+				const int X = t.rx0 + lx, Y = t.ry0 + ly;
+				if(X >= 0 && X < f.xres && Y >= 0 && Y < f.yres)
+					f.occlImage[(size_t)Y*f.xres + X] = keyDepth(s.pixZ[ly*f.tileW + lx]);
+			}
+			if(f.zOnly) continue;          // the next tile's first barrier orders the reads of pixZ above
+		}
 		// ---- Combine_samples + hand the resolved samples to the filter stage.
 		const int tw = t.rx1 - t.rx0, th = t.ry1 - t.ry0;
 		if(!PARTIALS)

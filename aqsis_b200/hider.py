@@ -47,6 +47,8 @@ def lib():
     L.aqh_add_grid_block.argtypes = [vp, C.POINTER(GridBlock)]
     L.aqh_end_frame.argtypes = [vp, C.POINTER(Callbacks)]
     L.aqh_render_device.argtypes = [vp]
+    L.aqh_flush.argtypes = [vp]
+    L.aqh_can_cull.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     L.aqh_frame_stats.argtypes = [vp, C.POINTER(FrameStats)]
     L.aqh_image_channels.argtypes = [vp, C.POINTER(C.POINTER(C.c_float)), C.POINTER(ci), C.POINTER(ci)]
     L.aqh_image_display.argtypes = [vp, ci, C.POINTER(C.POINTER(C.c_ubyte)), C.POINTER(ci), C.POINTER(ci)]
@@ -291,6 +293,17 @@ class Hider:
         self._block_keep = getattr(self, "_block_keep", [])
         self._block_keep.append(grids)
         self._check(self._L.aqh_add_grid_block(self._h, C.byref(b)))
+
+    def flush(self):
+        """aqh_flush: hide what has been submitted so far and refresh the occlusion image (the frame stays open)."""
+        self._check(self._L.aqh_flush(self._h))
+
+    def can_cull(self, bound) -> bool:
+        """aqh_can_cull for a raster bound (xmin, ymin, zmin, xmax, ymax, zmax)."""
+        b = (C.c_float * 6)(*[float(x) for x in bound])
+        out = C.c_int()
+        self._check(self._L.aqh_can_cull(self._h, b, C.byref(out)))
+        return bool(out.value)
 
     def render_device(self):
         self._check(self._L.aqh_render_device(self._h))

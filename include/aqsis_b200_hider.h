@@ -242,6 +242,20 @@ AQH_EXPORT int aqh_add_grid_block(AqhHider* h, const AqhGridBlock* b);
 AQH_EXPORT int aqh_end_frame(AqhHider* h, const AqhCallbacks* cb);
 /* The same device work without download or callbacks: results stay in HBM (see aqh_device_*). */
 AQH_EXPORT int aqh_render_device(AqhHider* h);
+
+/* Occlusion feedback to the front end -- what CqOcclusionTree::canCull(const CqBound&) gives aqsis
+ * (libs/core/occlusion.h:128, occlusion.cpp:161-225; call site CqBucketProcessor::RenderSurface,
+ * bucketprocessor.cpp:945-958: a surface whose raster bound lies behind every sample it could touch is
+ * re-posted / dropped before it is diced and shaded).
+ * aqh_flush hides the grids submitted so far (the frame stays open: more grids may follow, aqh_end_frame
+ * renders all of them) and keeps, per image pixel, the farthest occlusion depth over the pixel's samples --
+ * FLT_MAX while any sample of the pixel is uncovered.  aqh_can_cull(bound = xmin, ymin, zmin, xmax, ymax, zmax in
+ * raster space, the bound aqsis passes) sets *culled = 1 when every pixel the bound touches (inside the crop
+ * window) is occluded nearer than zmin: pixel granularity instead of the reference's per-sample tree, i.e. never
+ * culls more than the reference would.  Before the first flush of a frame nothing is culled.  As in the reference
+ * nothing is culled when the display mode has z and the depth filter is max or average. */
+AQH_EXPORT int aqh_flush(AqhHider* h);
+AQH_EXPORT int aqh_can_cull(const AqhHider* h, const float bound[6], int* culled);
 AQH_EXPORT int aqh_frame_stats(const AqhHider* h, AqhFrameStats* out);
 
 /* Results of the last frame.  Host copies (valid after aqh_end_frame): full-resolution images,

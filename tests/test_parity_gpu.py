@@ -130,6 +130,46 @@ def test_pipelined_upload_is_the_same_image(gpu_hider, monkeypatch):
         assert np.array_equal(ch_a.view(np.uint32), ch_c.view(np.uint32))
 
 
+def test_occlusion_feedback_flush_and_can_cull(gpu_hider):
+    """aqh_flush / aqh_can_cull: what CqOcclusionTree::canCull gives the front end (occlusion.cpp:161-225)."""
+    from test_oracle_render import one_grid, params_1spp
+    p = params_1spp()                                             # 10 x 8 pixels, one sample each
+    front = one_grid([1.25, 8.75], [1.25, 6.75], z=5.0, ci=(1, 0, 0))      # covers pixels x 2..7, y 2..5 completely
+    back = one_grid([2.25, 7.75], [2.25, 5.75], z=9.0, ci=(0, 1, 0))       # hidden behind it
+    h = gpu_hider
+    h.begin_frame(p)
+    assert not h.can_cull((3.0, 3.0, 6.0, 5.0, 5.0, 7.0))       # nothing flushed yet: nothing is culled
+    h.add_grid_block(front)
+    h.flush()
+    assert h.can_cull((3.0, 3.0, 6.0, 5.0, 5.0, 7.0))           # behind the front sheet, inside its footprint
+    assert h.can_cull((2.0, 2.0, 5.5, 7.9, 5.9, 9.0))           # the whole covered block
+    assert not h.can_cull((3.0, 3.0, 4.0, 5.0, 5.0, 4.5))       # in front of it
+    assert not h.can_cull((3.0, 3.0, 6.0, 9.5, 5.0, 7.0))       # reaches pixels the sheet does not cover
+    assert h.can_cull((-30.0, -30.0, 1.0, -20.0, -20.0, 2.0))   # entirely outside the crop window: cannot reach a sample
+    # the frame is still open: the hidden sheet may be skipped or submitted, the image is the same either way
+    ch_a, disp_a = h.end_frame()
+    ch_b, disp_b, _ = pu.run_product(h, p, scenes.concat([front, back]))
+    ch_o, disp_o, _ = __import__("orc").render(p, scenes.concat([front, back]), 1)
+    assert np.array_equal(ch_a.view(np.uint32), ch_b.view(np.uint32)) and np.array_equal(ch_a.view(np.uint32), ch_o.view(np.uint32))
+    assert np.array_equal(disp_a[0], disp_b[0])
+    # a flush in the middle of a bigger frame does not change the final image
+    p2, g2 = scenes.config1(scale=0.2)
+    h.begin_frame(p2)
+    h.add_grid_block(g2)
+    h.flush()
+    ch_c, disp_c = h.end_frame()
+    ch_d, disp_d, _ = pu.run_product(h, p2, g2)
+    assert np.array_equal(ch_c.view(np.uint32), ch_d.view(np.uint32)) and np.array_equal(disp_c[0], disp_d[0])
+    # max / average depth filters with a z display: the reference never asks the tree
+    p3 = params_1spp()
+    p3.depth_filter, p3.display_mode = abi.DEPTHFILTER_MAX, abi.DMODE_RGB | abi.DMODE_A | abi.DMODE_Z
+    h.begin_frame(p3)
+    h.add_grid_block(front)
+    h.flush()
+    assert not h.can_cull((3.0, 3.0, 6.0, 5.0, 5.0, 7.0))
+    h.end_frame()
+
+
 def test_empty_frame(gpu_hider):
     p = default_params(resolution=(40, 24), samples=(2, 2), displays=[("rgba", 1, 255.0, 0.0, 255.0, 0.5)])
     gpu_hider.begin_frame(p)
