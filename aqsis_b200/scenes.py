@@ -131,6 +131,37 @@ def config3(scale=1.0, seed=SEED + 1, motion_px=16.0, fstop=2.8, focallength=0.0
     return params, _pack(P, Ci, Oi, 16, 16, P2=P2, key_times=(0.0, 1.0))
 
 
+def multikey(scale=0.05, nkeys=3, seed=SEED + 7, motion_px=10.0, dof=True, shutter=(0.0, 1.0)):
+    """config-3 style frame whose grids carry `nkeys` motion keys at non-uniform times on a curved path
+    (CqMicroPolygonMotion::AppendKey once per key, micropolygon.cpp:1952-1967; BuildBoundList walks the keys, :1689-1756)."""
+    xres, yres = max(16, int(1920 * scale)), max(16, int(1080 * scale))
+    rng = np.random.default_rng(seed)
+    G = max(4, int(78125 * scale * scale))
+    centers = np.stack([rng.uniform(-8, xres + 8, G), rng.uniform(-8, yres + 8, G)], axis=1).astype(np.float32)
+    P, Ci, Oi = _grids(rng, centers, 16.0, 16, 16, 2.0, 100.0)
+    ang = rng.uniform(0, 2 * math.pi, (G, 1))
+    mag = rng.uniform(0, motion_px, (G, 1))
+    t = np.linspace(0.0, 1.0, nkeys) ** 1.5                       # non-uniform key times in [0, 1]
+    times = (shutter[0] + (shutter[1] - shutter[0]) * t).astype(np.float32)
+    keys = []
+    for k in range(nkeys):
+        Pk = P.copy()
+        bend = math.sin(math.pi * t[k]) * 0.35                      # sideways bulge: the path is not a straight line
+        Pk[:, :, 0] += (mag * (t[k] * np.cos(ang) - bend * np.sin(ang))).astype(np.float32)
+        Pk[:, :, 1] += (mag * (t[k] * np.sin(ang) + bend * np.cos(ang))).astype(np.float32)
+        Pk[:, :, 2] *= np.float32(1.0 + 0.02 * t[k])
+        keys.append(Pk)
+    Pall = np.stack(keys, axis=1).reshape(-1, 3)                   # per grid: key-major
+    s_ = 0.5 * yres / math.tan(math.radians(20.0))
+    kw = {"dof": (2.8, 0.05, 20.0, s_, s_)} if dof else {}
+    params = default_params(resolution=(xres, yres), samples=(4, 4), filter=("gaussian", 2.0, 2.0), shutter=shutter,
+                            displays=[_RGBA8], **kw)
+    g = GridArrays(cu=np.full(G, 16, np.int32), cv=np.full(G, 16, np.int32), flags=np.full(G, abi.GRID_SMOOTH, np.uint32),
+                   P=np.ascontiguousarray(Pall.astype(np.float32)), Ci=np.ascontiguousarray(Ci.reshape(-1, 3)),
+                   Oi=np.ascontiguousarray(Oi.reshape(-1, 3)), nkeys=np.full(G, nkeys, np.int32), key_times=np.tile(times, G))
+    return params, g
+
+
 def config4(scale=1.0, seed=SEED + 3, layers=4, shard=None):
     """3840x2160, PixelSamples 16 16, ShadingRate 0.25, semi-transparent layered surfaces.
 

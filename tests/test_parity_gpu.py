@@ -61,6 +61,16 @@ def test_motion_only(gpu_hider, mode):
     check(gpu_hider, p, g, mode, exact_frac=0.99)
 
 
+@pytest.mark.parametrize("nkeys,dof", [(3, True), (3, False), (6, True), (6, False)])
+def test_several_motion_keys(gpu_hider, nkeys, dof):
+    """More than two keys per grid at non-uniform times on curved paths; six keys exceed the four the MB/DoF kernel
+    stages in shared memory, so the HBM path of the key accessors is exercised too."""
+    p, g = scenes.multikey(scale=0.04, nkeys=nkeys, dof=dof)
+    check(gpu_hider, p, g, EXACT)
+    p, g = scenes.multikey(scale=0.03, nkeys=nkeys, dof=dof, shutter=(0.25, 0.75))
+    check(gpu_hider, p, g, EXACT)
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_dof_only(gpu_hider, mode):
     p, g = scenes.config2(scale=0.05)

@@ -66,6 +66,11 @@ for _df, _dn in [(abi.DEPTHFILTER_MIDPOINT, "midpoint"), (abi.DEPTHFILTER_MAX, "
         CASES[f"depthfilter-{_dn}-{_mn}-deep"] = (lambda df=_df, dm=_dm: _mod(scenes.config4(scale=0.015), lambda p: _set(p, depth_filter=df, display_mode=dm)))
     CASES[f"depthfilter-{_dn}-rgbaz-mbdof"] = (lambda df=_df: _mod(scenes.config3(scale=0.04, motion_px=6.0),
                                                                    lambda p: _set(p, depth_filter=df, display_mode=abi.DMODE_RGB | abi.DMODE_A | abi.DMODE_Z)))
+# more than two motion keys, non-uniform key times, curved paths (AppendKey / BuildBoundList over several keys)
+for _nk in (3, 6):
+    CASES[f"motion-{_nk}keys-dof"] = (lambda nk=_nk: scenes.multikey(scale=0.04, nkeys=nk, dof=True))
+    CASES[f"motion-{_nk}keys"] = (lambda nk=_nk: scenes.multikey(scale=0.04, nkeys=nk, dof=False))
+CASES["motion-5keys-subshutter"] = lambda: scenes.multikey(scale=0.04, nkeys=5, dof=False, shutter=(0.25, 0.75))
 for _name, _w in [("box", 1.0), ("triangle", 2.0), ("gaussian", 3.0), ("catmull-rom", 4.0), ("sinc", 5.0), ("sinc", 6.0),
                   ("gaussian", 2.5), ("mitchell", 4.0), ("disk", 3.0), ("bessel", 4.0)]:
     CASES[f"filter-{_name}-{_w}"] = (lambda n=_name, w=_w: scenes.config2(scale=0.04, filter=(n, w, w), samples=(4, 4)))
