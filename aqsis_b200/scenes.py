@@ -131,6 +131,39 @@ def config3(scale=1.0, seed=SEED + 1, motion_px=16.0, fstop=2.8, focallength=0.0
     return params, _pack(P, Ci, Oi, 16, 16, P2=P2, key_times=(0.0, 1.0))
 
 
+def to_camera_space(params, grids, fov_deg=40.0):
+    """Re-express raster-space grids in camera space and set params.cam_to_raster to the perspective matrix that maps
+    them back (row-vector convention of CqMatrix, include/aqsis/math/matrix.h:717-750): the device / the reference then
+    do the Project_points step themselves (micropolygon.cpp:723-731).  Camera depth is kept as z."""
+    xres, yres = params.xres, params.yres
+    fy = 0.5 * yres / math.tan(math.radians(fov_deg / 2.0))
+    fx, cx, cy = fy, 0.5 * xres, 0.5 * yres
+    m = np.zeros(16, np.float32)
+    m[0], m[5] = fx, fy            # x -> x', y -> y'
+    m[8], m[9] = cx, cy            # z row: x' += cx*z, y' += cy*z
+    m[11] = 1.0                    # h = z
+    for i in range(16):
+        params.cam_to_raster[i] = float(m[i])
+    P = np.asarray(grids.P, np.float32).copy()
+    z = P[:, 2].astype(np.float64)
+    P[:, 0] = ((P[:, 0].astype(np.float64) - cx) * z / fx).astype(np.float32)
+    P[:, 1] = ((P[:, 1].astype(np.float64) - cy) * z / fy).astype(np.float32)
+    grids.P = np.ascontiguousarray(P)
+    grids.flags = (grids.flags | np.uint32(abi.GRID_CAMERA_SPACE)).astype(np.uint32)
+    return params, grids
+
+
+def deep_stack(n_grids=150, seed=SEED + 11):
+    """A small frame under a tall stack of full-frame opaque grids: every tile's bin holds more entries than one
+    sorted run (8192), depth complexity = n_grids."""
+    xres, yres = 16, 16
+    rng = np.random.default_rng(seed)
+    centers = np.tile(np.float32([[8.0, 8.0]]), (n_grids, 1)) + rng.uniform(-1, 1, (n_grids, 2)).astype(np.float32)
+    P, Ci, Oi = _grids(rng, centers, 20.0, 16, 16, 2.0, 100.0)
+    params = default_params(resolution=(xres, yres), samples=(8, 8), filter=("catmull-rom", 3.0, 3.0), displays=[_RGBA8])
+    return params, _pack(P, Ci, Oi, 16, 16)
+
+
 def multikey(scale=0.05, nkeys=3, seed=SEED + 7, motion_px=10.0, dof=True, shutter=(0.0, 1.0)):
     """config-3 style frame whose grids carry `nkeys` motion keys at non-uniform times on a curved path
     (CqMicroPolygonMotion::AppendKey once per key, micropolygon.cpp:1952-1967; BuildBoundList walks the keys, :1689-1756)."""

@@ -53,7 +53,8 @@ def compare(ch_gpu, disp_gpu, ch_ref, disp_ref, float_rtol=FLOAT_RTOL, quant_ato
     finite = np.isfinite(a) & np.isfinite(b) & (np.abs(b) < 1e30)
     # relative error against max(|ref|, small floor) so that exact zeros compare absolutely
     denom = np.maximum(np.abs(b), 1e-3)
-    rel = np.where(finite, np.abs(a - b) / denom, 0.0)
+    with np.errstate(invalid="ignore", over="ignore"):          # inf - inf / FLT_MAX - x where the reference holds specials
+        rel = np.where(finite, np.abs(a - b) / denom, 0.0)
     # where the reference holds FLT_MAX / inf both must agree exactly
     special_equal = np.array_equal(np.where(finite, 0, a), np.where(finite, 0, b), equal_nan=True)
     out = {

@@ -180,6 +180,33 @@ def test_occlusion_feedback_flush_and_can_cull(gpu_hider):
     h.end_frame()
 
 
+def test_camera_space_grids_are_projected_on_the_device(gpu_hider):
+    """AQH_GRID_CAMERA_SPACE: k_project applies matCameraToRaster like CqMicroPolyGrid::Split (micropolygon.cpp:723-731)."""
+    for make in (lambda: scenes.config1(scale=0.15), lambda: scenes.config3(scale=0.04, motion_px=6.0)):
+        p, g = scenes.to_camera_space(*make())
+        check(gpu_hider, p, g, EXACT)
+
+
+def test_bins_longer_than_one_sorted_run(gpu_hider):
+    """150 full-frame opaque grids over a 16x16 image: > 8192 entries per tile (sorted in runs, early out per run)."""
+    p, g = scenes.deep_stack()
+    r = check(gpu_hider, p, g, EXACT)
+    assert r["gpu_stats"]["n_bin_entries"] > 4 * 8192
+
+
+def test_deep_pool_overflow_is_reported(gpu_hider):
+    from aqsis_b200 import HiderError
+    p, g = scenes.config4(scale=0.02)
+    p.deep_hits_per_sample = 1                 # three transparent layers need three slots per sample
+    gpu_hider.begin_frame(p)
+    gpu_hider.add_grid_block(g)
+    with pytest.raises(HiderError) as e:
+        gpu_hider.end_frame()
+    assert e.value.status == abi.AQH_ERR_DEEP_OVERFLOW
+    p.deep_hits_per_sample = 8
+    check(gpu_hider, p, g, EXACT)              # and the hider is usable afterwards
+
+
 def test_empty_frame(gpu_hider):
     p = default_params(resolution=(40, 24), samples=(2, 2), displays=[("rgba", 1, 255.0, 0.0, 255.0, 0.5)])
     gpu_hider.begin_frame(p)

@@ -71,6 +71,11 @@ for _nk in (3, 6):
     CASES[f"motion-{_nk}keys-dof"] = (lambda nk=_nk: scenes.multikey(scale=0.04, nkeys=nk, dof=True))
     CASES[f"motion-{_nk}keys"] = (lambda nk=_nk: scenes.multikey(scale=0.04, nkeys=nk, dof=False))
 CASES["motion-5keys-subshutter"] = lambda: scenes.multikey(scale=0.04, nkeys=5, dof=False, shutter=(0.25, 0.75))
+# Project_points on the hider's side of the seam (camera-space grids + matCameraToRaster, micropolygon.cpp:723-731;
+# the reference wrapper multiplies with aqsis' own CqMatrix), and bins longer than one sorted run
+CASES["camera-space-static"] = lambda: scenes.to_camera_space(*scenes.config1(scale=0.15))
+CASES["camera-space-mbdof"] = lambda: scenes.to_camera_space(*scenes.config3(scale=0.04, motion_px=6.0))
+CASES["deep-stack-150"] = lambda: scenes.deep_stack()
 for _name, _w in [("box", 1.0), ("triangle", 2.0), ("gaussian", 3.0), ("catmull-rom", 4.0), ("sinc", 5.0), ("sinc", 6.0),
                   ("gaussian", 2.5), ("mitchell", 4.0), ("disk", 3.0), ("bessel", 4.0)]:
     CASES[f"filter-{_name}-{_w}"] = (lambda n=_name, w=_w: scenes.config2(scale=0.04, filter=(n, w, w), samples=(4, 4)))
