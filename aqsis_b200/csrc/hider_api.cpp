@@ -706,7 +706,7 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 	// bins are sorted front to back in runs of sortRun entries (a power of two covering the longest bin, capped)
 	f.sortRun = 64;
 	while(f.sortRun < (int)maxBin && f.sortRun < 8192) f.sortRun <<= 1;
-	CU(launchBinFill(f, st), "k_bin<fill>"); S.gpu_launches += (nPos ? 1 : 0) + (nActive ? 1 : 0) + ((nPos && nActive) ? 1 : 0);
+	CU(launchBinFill(f, st), "k_bin<fill>"); S.gpu_launches += (nPos ? 1 : 0) + ((nActive && f.anyTransparent) ? 1 : 0) + ((nPos && nActive) ? 1 : 0);
 	CU(cudaEventRecord(h->ev[1], st), "cudaEventRecord");
 	if(zOnly)
 	{

@@ -2363,7 +2363,8 @@ cudaError_t launchBinFill(const DevFrame& f, cudaStream_t st)
 		}
 		if(f.sortRun > SORT_MAX) return cudaErrorInvalidValue;
 		if(f.nPos) k_bin_sort<<<f.nActiveTiles, 256, (size_t)f.sortRun*8, st>>>(f, f.sortRun);
-		k_tile_flags<<<f.nActiveTiles, 256, 0, st>>>(f);
+		// only the deep pass reads the flags: frames without a non-opaque vertex (and with cullable hits) skip the scan
+		if(f.anyTransparent) k_tile_flags<<<f.nActiveTiles, 256, 0, st>>>(f);
 	}
 	return cudaGetLastError();
 }
