@@ -166,3 +166,41 @@ def render_reference(params: FrameParams, grids):
     if rc:
         raise RuntimeError(f"ref_render failed: {abi.STATUS_NAMES.get(rc, rc)}")
     return ch, outs, st.as_dict()
+
+
+_pdiff = None
+
+
+def pdiff_lib():
+    """The reference's perceptual diff (thirdparty/pdiff) compiled in place (oracle/ref_pdiff.cpp); None when absent."""
+    global _pdiff
+    if _pdiff is None:
+        if os.path.isdir("/root/reference/thirdparty/pdiff"):
+            subprocess.run(["make", "-s", "-C", ORACLE_DIR, "pdiff"], check=True, capture_output=True)
+        path = os.path.join(ORACLE_DIR, "_ref", "libaqsis_pdiff.so")
+        if not os.path.exists(path):
+            _pdiff = False
+        else:
+            L = C.CDLL(path)
+            L.ref_pdiff.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                    C.c_uint, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+            L.ref_pdiff.restype = C.c_int
+            _pdiff = L
+    return _pdiff or None
+
+
+def pdiff(rgba_a, rgba_b, threshold_pixels=1, fov=45.0, gamma=2.2, luminance=100.0):
+    """Yee's perceptual metric as aqsis' regression tool runs it (defaults of CompareArgs.cpp), with the pixel
+    threshold at 1 = "zero pdiff-detected differences".  Returns (passed, failing pixels, binary identical)."""
+    L = pdiff_lib()
+    if L is None:
+        raise RuntimeError("oracle/_ref/libaqsis_pdiff.so is not available")
+    a = np.ascontiguousarray(rgba_a, dtype=np.uint8)
+    b = np.ascontiguousarray(rgba_b, dtype=np.uint8)
+    assert a.shape == b.shape and a.ndim == 3 and a.shape[2] == 4
+    failed, same = C.c_int(), C.c_int()
+    rc = L.ref_pdiff(a.ctypes.data, b.ctypes.data, a.shape[1], a.shape[0], fov, gamma, luminance, int(threshold_pixels),
+                     C.byref(failed), C.byref(same))
+    if rc < 0:
+        raise ValueError("ref_pdiff: bad arguments")
+    return bool(rc), int(failed.value), bool(same.value)

@@ -207,6 +207,26 @@ def test_deep_pool_overflow_is_reported(gpu_hider):
     check(gpu_hider, p, g, EXACT)              # and the hider is usable afterwards
 
 
+def test_zero_pdiff_differences(gpu_hider):
+    """Third criterion of the north star, measured with the reference's own pdiff (thirdparty/pdiff compiled in place):
+    the default mode is binary identical to aqsis' hider; the opt-in tile-partials mode, which rounds differently,
+    still shows zero perceptually different pixels."""
+    import orc
+    if orc.pdiff_lib() is None or orc.refhider() is None:
+        pytest.skip("oracle/_ref did not travel to this machine")
+    for make in (lambda: scenes.config2(scale=0.1), lambda: scenes.config3(scale=0.05, motion_px=6.0), lambda: scenes.config4(scale=0.02)):
+        p, g = make()
+        _, d_ref, _ = orc.render_reference(p, g)
+        p.filter_mode = EXACT
+        _, d_gpu, _ = pu.run_product(gpu_hider, p, g)
+        ok, failed, same = orc.pdiff(d_ref[0], d_gpu[0])
+        assert ok and failed == 0 and same
+        p.filter_mode = TILED
+        _, d_t, _ = pu.run_product(gpu_hider, p, g)
+        ok, failed, _ = orc.pdiff(d_ref[0], d_t[0])
+        assert ok and failed == 0
+
+
 def test_empty_frame(gpu_hider):
     p = default_params(resolution=(40, 24), samples=(2, 2), displays=[("rgba", 1, 255.0, 0.0, 255.0, 0.5)])
     gpu_hider.begin_frame(p)

@@ -144,3 +144,20 @@ def test_special_grids_match_reference():
             ch_r, d_r, _ = orc.render_reference(p, g)
             ch_o, d_o, _ = orc.render(p, g, 2)
             assert_identical(p, ch_r, d_r, ch_o, d_o, (flags, lod))
+
+
+def test_pdiff_reports_zero_differences_between_oracle_and_reference():
+    """BASELINE.json's third criterion, with the reference's own tool (thirdparty/pdiff compiled in place): the
+    quantised images are binary identical; and the tool does see a real difference (one bucket of pixels shifted)."""
+    if orc.pdiff_lib() is None:
+        pytest.skip("oracle/_ref/libaqsis_pdiff.so not built")
+    p, g = scenes.config2(scale=0.08)
+    _, d_r, _ = orc.render_reference(p, g)
+    _, d_o, _ = orc.render(p, g, 4)
+    ok, failed, same = orc.pdiff(d_r[0], d_o[0])
+    assert ok and failed == 0 and same
+    broken = d_o[0].copy()
+    broken[16:48, 16:48] = np.roll(broken[16:48, 16:48], 5, axis=1)
+    broken[60:70, 60:70] = 255 - broken[60:70, 60:70]
+    ok, failed, same = orc.pdiff(d_r[0], broken)
+    assert not ok and failed > 0 and not same
