@@ -181,13 +181,27 @@ FRAMES = {
     "config3_s0.04": lambda: scenes.config3(scale=0.04, motion_px=6.0),
     "config4_s0.015": lambda: scenes.config4(scale=0.015),
     "sweep_sinc5_s0.04": lambda: scenes.config2(scale=0.04, filter=("sinc", 5.0, 5.0), samples=(4, 4)),
+    "depthfilter_midpoint_rgbaz_deep": lambda: _with(scenes.config4(scale=0.015), depth_filter=abi.DEPTHFILTER_MIDPOINT, display_mode=7),
+    "depthfilter_max_rgbaz_deep": lambda: _with(scenes.config4(scale=0.015), depth_filter=abi.DEPTHFILTER_MAX, display_mode=7),
+    "depthfilter_average_rgbaz_mbdof": lambda: _with(scenes.config3(scale=0.04, motion_px=6.0), depth_filter=abi.DEPTHFILTER_AVERAGE, display_mode=7),
+    "motion_6keys_dof": lambda: scenes.multikey(scale=0.04, nkeys=6, dof=True),
+    "camera_space_static": lambda: scenes.to_camera_space(*scenes.config1(scale=0.15)),
+    "deep_stack_150": lambda: scenes.deep_stack(),
 }
+
+
+def _with(scene, **kw):
+    p, g = scene
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p, g
 
 
 @pytest.mark.parametrize("name", sorted(FRAMES))
 def test_oracle_frame_checksums(name):
-    """Regression pin of the oracle itself (written by `python tests/test_oracle_render.py`): the oracle
-    is the yardstick of every GPU parity test, so it must not drift silently."""
+    """Regression pin of the oracle itself (written by `python tests/test_oracle_render.py`, which refuses to write a
+    frame the reference's own hider does not reproduce bit for bit): the oracle is the yardstick of every GPU parity
+    test, so it must not drift silently -- also on machines where /root/reference and oracle/_ref are absent."""
     want = json.load(open(GOLDEN))
     p, g = FRAMES[name]()
     ch, disp, st = orc.render(p, g, 4)
@@ -200,7 +214,12 @@ if __name__ == "__main__":
     for name, fn in sorted(FRAMES.items()):
         p, g = fn()
         ch, disp, st = orc.render(p, g, 4)
+        # golden = output of the reference itself: only frames aqsis' own hider reproduces exactly are written
+        ch_r, disp_r, _ = orc.render_reference(p, g)
+        ys, xs = slice(p.crop_ymin, p.crop_ymax), slice(p.crop_xmin, p.crop_xmax)
+        assert np.array_equal(ch[ys, xs].view(np.uint32), ch_r[ys, xs].view(np.uint32)), name
+        assert all(np.array_equal(a[ys, xs], b[ys, xs]) for a, b in zip(disp, disp_r)), name
         out[name] = {"sha256": _digest(ch, disp), "spl_hits": int(st["spl_hits"]), "xres": p.xres, "yres": p.yres,
-                     "micropolygons": g.n_micropolygons}
+                     "micropolygons": g.n_micropolygons, "equals_reference_hider": True}
     json.dump(out, open(GOLDEN, "w"), indent=1, sort_keys=True)
     print(json.dumps(out, indent=1))
