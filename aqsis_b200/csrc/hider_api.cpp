@@ -65,6 +65,22 @@ struct PinnedBuf
 };
 
 // One contiguous run of grids as handed over by the caller.
+// A growable array in pinned host memory: what is uploaded from it can be copied asynchronously.
+template<class T> struct PinnedVec
+{
+	PinnedBuf b;
+	size_t n = 0;
+	bool ensure(size_t m)
+	{
+		if(m*sizeof(T) <= b.cap) return true;
+		return b.reserve(std::max(m*sizeof(T), size_t(1) << 16), true, n*sizeof(T));
+	}
+	bool push(const T& v) { if(!ensure(n + 1)) return false; b.as<T>()[n++] = v; return true; }
+	T* data() const { return b.as<T>(); }
+	void clear() { n = 0; }
+	void release() { b.release(); n = 0; }
+};
+
 struct Segment
 {
 	int64_t firstGrid = 0, nGrids = 0, nVerts = 0, nPos = 0;
@@ -121,6 +137,11 @@ struct AqhHider
 	std::vector<uint32_t> gflags;
 	std::vector<float> glod, gkeyTimes;
 	std::vector<Segment> segments;
+	// device-side grid table and the 256-position chunk index, built as the grids are submitted
+	PinnedVec<GridRec> recs;
+	PinnedVec<uint32_t> chunk;
+	uint64_t recVb = 0, recPb = 0, recKo = 0;
+	bool anyMotionG = false, anyLodG = false, anyTriG = false, anyCamG = false;
 	int64_t nVerts = 0, nPos = 0;
 	bool anyCi = false, anyOi = false, anyCulled = false, allCi = true, allOi = true;
 	// pinned staging for aqh_add_grid
@@ -169,6 +190,8 @@ void resetFrameGrids(AqhHider* h)
 {
 	h->gcu.clear(); h->gcv.clear(); h->gnkeys.clear(); h->gflags.clear(); h->glod.clear(); h->gkeyTimes.clear();
 	h->segments.clear();
+	h->recs.clear(); h->chunk.clear(); h->recVb = h->recPb = h->recKo = 0;
+	h->anyMotionG = h->anyLodG = h->anyTriG = h->anyCamG = false;
 	h->nVerts = h->nPos = 0;
 	h->anyCi = h->anyOi = h->anyCulled = false; h->allCi = h->allOi = true;
 	h->stPUsed = h->stVUsed = 0;
@@ -357,6 +380,28 @@ int appendGridTables(AqhHider* h, int cu, int cv, int nkeys, uint32_t flags, con
 	h->gcu.push_back(cu); h->gcv.push_back(cv); h->gnkeys.push_back(nkeys); h->gflags.push_back(flags);
 	h->glod.push_back(lod ? lod[0] : -1.f); h->glod.push_back(lod ? lod[1] : -1.f);
 	for(int k = 0; k < nkeys; ++k) h->gkeyTimes.push_back(nkeys > 1 ? times[k] : 0.f);
+	// the grid's device record and the chunk index entries of the positions it covers
+	GridRec r;
+	const uint32_t nv = uint32_t(cu + 1)*uint32_t(cv + 1);
+	r.vbase = (uint32_t)h->recVb; r.pbase = (uint32_t)h->recPb; r.nverts = nv;
+	r.cu_cv = uint32_t(cu) | (uint32_t(cv) << 16);
+	r.flags = flags;
+	r.nkeys_koff = uint32_t(nkeys) | (uint32_t(h->recKo) << 8);
+	r.lod0 = lod ? lod[0] : -1.f; r.lod1 = lod ? lod[1] : -1.f;
+	const uint32_t g = (uint32_t)h->recs.n;
+	if(!h->recs.push(r)) return h->fail(AQH_ERR_NO_MEMORY, "cudaHostAlloc(grid table)");
+	const uint64_t np = uint64_t(nv)*uint64_t(nkeys);
+	const uint64_t c0 = (h->recPb + 255)/256, c1 = (h->recPb + np - 1)/256;      // chunks whose first position lies in this grid
+	if(c1 + 1 >= c0 + 1 && c1 >= c0)
+	{
+		if(!h->chunk.ensure(c1 + 3)) return h->fail(AQH_ERR_NO_MEMORY, "cudaHostAlloc(chunk table)");
+		for(uint64_t c = c0; c <= c1; ++c) h->chunk.data()[c] = g;
+		h->chunk.n = std::max<size_t>(h->chunk.n, c1 + 1);
+	}
+	h->anyMotionG |= nkeys > 1; h->anyLodG |= r.lod0 >= 0.f;
+	h->anyTriG |= (flags & AQH_GRID_TRIANGULAR) != 0; h->anyCamG |= (flags & AQH_GRID_CAMERA_SPACE) != 0;
+	h->recVb += nv; h->recPb += np; h->recKo += (uint64_t)nkeys;
+	if(h->recKo >= (1u << 24)) return h->fail(AQH_ERR_BAD_PARAMS, "too many motion keys in one frame");
 	return AQH_OK;
 }
 
@@ -387,37 +432,14 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 	int rc = uploadTables(h);
 	if(rc) return rc;
 
-	// ---- host grid tables -> GridRec, chunk index, key times
-	bool anyMotion = false, anyLod = false, anyTri = false, anyCam = false;
-	std::vector<GridRec> recs(std::max<int64_t>(nGrids, 1));
-	{
-		uint64_t vb = 0, pb = 0, ko = 0;
-		for(int64_t g = 0; g < nGrids; ++g)
-		{
-			GridRec& r = recs[g];
-			const uint32_t nv = uint32_t(h->gcu[g]+1)*uint32_t(h->gcv[g]+1);
-			r.vbase = (uint32_t)vb; r.pbase = (uint32_t)pb; r.nverts = nv;
-			r.cu_cv = uint32_t(h->gcu[g]) | (uint32_t(h->gcv[g]) << 16);
-			r.flags = h->gflags[g];
-			r.nkeys_koff = uint32_t(h->gnkeys[g]) | (uint32_t(ko) << 8);
-			r.lod0 = h->glod[2*g]; r.lod1 = h->glod[2*g+1];
-			anyMotion |= h->gnkeys[g] > 1; anyLod |= r.lod0 >= 0.f;
-			anyTri |= (r.flags & AQH_GRID_TRIANGULAR) != 0; anyCam |= (r.flags & AQH_GRID_CAMERA_SPACE) != 0;
-			vb += nv; pb += uint64_t(nv)*h->gnkeys[g]; ko += h->gnkeys[g];
-			if(ko >= (1u << 24)) return h->fail(AQH_ERR_BAD_PARAMS, "too many motion keys in one frame");
-		}
-	}
+	// ---- grid records and chunk index were built at submission (appendGridTables); close the chunk index with
+	// two sentinels (k_project reads one entry past the chunk of a position)
+	const bool anyMotion = h->anyMotionG, anyLod = h->anyLodG, anyTri = h->anyTriG, anyCam = h->anyCamG;
 	const int64_t nChunks = (h->nPos + 255)/256;
-	std::vector<uint32_t> chunk(nChunks + 2, (uint32_t)std::max<int64_t>(nGrids - 1, 0));
-	{
-		int64_t g = 0;
-		for(int64_t c = 0; c < nChunks; ++c)
-		{
-			const uint64_t first = uint64_t(c)*256;
-			while(g + 1 < nGrids && recs[g+1].pbase <= first) ++g;
-			chunk[c] = (uint32_t)g;
-		}
-	}
+	if(!h->chunk.ensure((size_t)nChunks + 2)) return h->fail(AQH_ERR_NO_MEMORY, "cudaHostAlloc(chunk table)");
+	h->chunk.data()[nChunks] = h->chunk.data()[nChunks + 1] = (uint32_t)std::max<int64_t>(nGrids - 1, 0);
+	const GridRec* recs = h->recs.data();
+	const size_t nRecs = h->recs.n, nChunkEntries = (size_t)nChunks + 2;
 	tr.mark("grid records");
 	const bool mbdof = anyMotion || p.use_dof;
 	buildTiling(h, mbdof);
@@ -426,8 +448,8 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 
 	// ---- device allocations
 	const size_t nPos = (size_t)h->nPos, nVerts = (size_t)h->nVerts;
-	CU(h->dGrids.reserve(recs.size()*sizeof(GridRec)), "cudaMalloc(grid table)");
-	CU(h->dChunk.reserve(chunk.size()*4), "cudaMalloc(chunk table)");
+	CU(h->dGrids.reserve(std::max<size_t>(nRecs, 1)*sizeof(GridRec)), "cudaMalloc(grid table)");
+	CU(h->dChunk.reserve(nChunkEntries*4), "cudaMalloc(chunk table)");
 	CU(h->dKeyTimes.reserve(std::max<size_t>(h->gkeyTimes.size(), 1)*4), "cudaMalloc(key times)");
 	CU(h->dSplit.reserve(std::max<size_t>(h->gkeyTimes.size(), 1)*16), "cudaMalloc(split lines)");
 	CU(h->dP4.reserve(std::max<size_t>(nPos, 1)*16 + 64), "cudaMalloc(P4)");
@@ -576,16 +598,18 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 		dOi = h->anyOi ? h->dOi.as<float>() : nullptr;
 		dCulled = h->anyCulled ? h->dCulled.as<uint8_t>() : nullptr;
 	}
-	CU(cudaMemcpyAsync(h->dGrids.p, recs.data(), recs.size()*sizeof(GridRec), cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(grid table)");
-	CU(cudaMemcpyAsync(h->dChunk.p, chunk.data(), chunk.size()*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(chunk table)");
+	if(nRecs) CU(cudaMemcpyAsync(h->dGrids.p, recs, nRecs*sizeof(GridRec), cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(grid table)");
+	CU(cudaMemcpyAsync(h->dChunk.p, h->chunk.data(), nChunkEntries*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(chunk table)");
 	if(!h->gkeyTimes.empty())
 		CU(cudaMemcpyAsync(h->dKeyTimes.p, h->gkeyTimes.data(), h->gkeyTimes.size()*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(key times)");
 	CU(cudaMemcpyAsync(h->dTileSlot.p, h->tileSlot.data(), h->tileSlot.size()*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(tile slots)");
 	if(nActive)
 		CU(cudaMemcpyAsync(h->dActive.p, h->activeTiles.data(), size_t(nActive)*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(active tiles)");
 	CU(cudaMemcpyAsync(h->dRowOwned.p, h->rowOwned.data(), p.yres, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(row ownership)");
-	S.h2d_bytes += (int64_t)(recs.size()*sizeof(GridRec) + chunk.size()*4 + h->gkeyTimes.size()*4 + h->tileSlot.size()*4 + size_t(nActive)*4 + p.yres);
-	CU(cudaStreamSynchronize(st), "cudaStreamSynchronize(upload)");
+	S.h2d_bytes += (int64_t)(nRecs*sizeof(GridRec) + nChunkEntries*4 + h->gkeyTimes.size()*4 + h->tileSlot.size()*4 + size_t(nActive)*4 + p.yres);
+	// No host wait here unless the upload is being timed on its own: the tables come from pinned or staged memory
+	// and everything that follows is ordered behind the copies on the stream.
+	if(tr.on || !pipelined) CU(cudaStreamSynchronize(st), "cudaStreamSynchronize(upload)");
 	S.upload_ms = nowMs() - tUp0;
 	tr.mark("upload done");
 
@@ -826,7 +850,7 @@ int aqh_destroy(AqhHider* h)
 	                  &h->dDeepA, &h->dDeepUV, &h->dChannels, &h->dRowOwned};
 	for(DevBuf* b : bufs) b->release();
 	for(int d = 0; d < AQH_MAX_DISPLAYS; ++d) { h->dDisplay[d].release(); h->hDisplay[d].release(); }
-	h->dOccl.release(); h->hOccl.release();
+	h->dOccl.release(); h->hOccl.release(); h->recs.release(); h->chunk.release();
 	h->hChannels.release(); h->stP.release(); h->stCi.release(); h->stOi.release(); h->stCulled.release();
 	for(int i = 0; i < 8; ++i) if(h->ev[i]) cudaEventDestroy(h->ev[i]);
 	for(cudaEvent_t e : h->chunkEv) cudaEventDestroy(e);
