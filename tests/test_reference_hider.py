@@ -161,3 +161,13 @@ def test_pdiff_reports_zero_differences_between_oracle_and_reference():
     broken[60:70, 60:70] = 255 - broken[60:70, 60:70]
     ok, failed, same = orc.pdiff(d_r[0], broken)
     assert not ok and failed > 0 and not same
+
+
+@pytest.mark.parametrize("name,width", scenes.config5_filters())
+def test_config5_filter_sweep_oracle_equals_reference(name, width):
+    """BASELINE.json config 5: box, triangle, gaussian, catmull-rom, sinc at widths 1-6 -- every combination of the
+    sweep, on a small copy of the 1080p scene, bit for bit against aqsis' own FilterBucket."""
+    p, g = scenes.config2(scale=0.03, filter=(name, width, width), samples=(4, 4))
+    ch_r, d_r, _ = orc.render_reference(p, g)
+    ch_o, d_o, _ = orc.render(p, g, 2)
+    assert_identical(p, ch_r, d_r, ch_o, d_o, (name, width))
