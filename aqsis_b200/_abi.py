@@ -5,7 +5,7 @@ that the shared library exports every symbol the header declares.
 """
 import ctypes as C
 
-AQH_ABI_VERSION = 1
+AQH_ABI_VERSION = 2
 
 # AqhStatus
 AQH_OK = 0
@@ -33,13 +33,20 @@ GRID_MATTE_ALPHA = 1 << 2
 GRID_TRIANGULAR = 1 << 3
 GRID_CAMERA_SPACE = 1 << 4
 GRID_USES_CSG = 1 << 5
+GRID_POINTS = 1 << 6
+GRID_CULL_BACKFACING = 1 << 7
+GRID_CULL_TRANSPARENT = 1 << 8
+CSG_PRIMITIVE, CSG_UNION, CSG_INTERSECTION, CSG_DIFFERENCE = 0, 1, 2, 3
+DISPLAY_SCANLINE_ORDER = 1
+MAX_RANKS, MAX_AOVS, MAX_AOV_FLOATS = 64, 8, 21
 
 MAX_DISPLAYS = 8
 FILTER_REFERENCE_ORDER, FILTER_TILE_PARTIALS = 0, 1
 MAX_DISPLAY_CHANNELS = 16
 
 FilterFunc = C.CFUNCTYPE(C.c_float, C.c_float, C.c_float, C.c_float, C.c_float)
-BucketFunc = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int)
+BucketFunc = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int)
+ImagerFunc = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int)
 DataFunc = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                        C.POINTER(C.c_ubyte))
 ProgressFunc = C.CFUNCTYPE(None, C.c_void_p, C.c_float)
@@ -55,7 +62,12 @@ class DisplayDesc(C.Structure):
         ("quantize_min", C.c_float),
         ("quantize_max", C.c_float),
         ("quantize_dither", C.c_float),
+        ("flags", C.c_int32),
     ]
+
+
+class AovDesc(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("n_floats", C.c_int32), ("reserved", C.c_int32)]
 
 
 class FrameParams(C.Structure):
@@ -81,12 +93,20 @@ class FrameParams(C.Structure):
         ("rng_seed", C.c_uint32), ("rng_predraws", C.c_uint32),
         ("n_displays", C.c_int32),
         ("display", DisplayDesc * MAX_DISPLAYS),
+        ("n_aovs", C.c_int32),
+        ("aov", AovDesc * MAX_AOVS),
         ("rank", C.c_int32), ("world_size", C.c_int32),
         ("strip_rows", C.c_int32),
+        ("strip_bounds", C.c_int32 * (MAX_RANKS + 1)),
         ("deep_hits_per_sample", C.c_int32),
         ("filter_mode", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("plane_budget_mb", C.c_int32),
+        ("reserved", C.c_int32 * 6),
     ]
+
+    @property
+    def aov_floats(self):
+        return sum(self.aov[a].n_floats for a in range(self.n_aovs))
 
 
 class GridDesc(C.Structure):
@@ -100,6 +120,12 @@ class GridDesc(C.Structure):
         ("culled", C.POINTER(C.c_uint8)),
         ("flags", C.c_uint32),
         ("lod_bounds", C.c_float * 2),
+        ("aov", C.POINTER(C.c_float)),
+        ("Ng", C.POINTER(C.c_float)),
+        ("N", C.POINTER(C.c_float)),
+        ("radius", C.POINTER(C.c_float)),
+        ("csg_node", C.c_int32),
+        ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -111,6 +137,7 @@ class GridBlock(C.Structure):
         ("P", C.c_void_p), ("Ci", C.c_void_p), ("Oi", C.c_void_p), ("culled", C.c_void_p),
         ("memory_space", C.c_int32),
         ("reserved", C.c_int32 * 3),
+        ("aov", C.c_void_p), ("Ng", C.c_void_p), ("N", C.c_void_p), ("radius", C.c_void_p), ("csg_node", C.c_void_p),
     ]
 
 
@@ -120,7 +147,13 @@ class Callbacks(C.Structure):
         ("on_bucket", BucketFunc),
         ("on_data", DataFunc),
         ("on_progress", ProgressFunc),
+        ("on_imager", ImagerFunc),
     ]
+
+
+class Capture(C.Structure):
+    _fields_ = [("xres", C.c_int32), ("yres", C.c_int32), ("n_channels", C.c_int32), ("channels", C.c_void_p),
+                ("display", C.c_void_p * MAX_DISPLAYS), ("buckets", C.c_int64), ("bytes", C.c_int64)]
 
 
 class FrameStats(C.Structure):
@@ -131,6 +164,7 @@ class FrameStats(C.Structure):
         ("n_grids", C.c_int64), ("n_vertices", C.c_int64), ("n_micropolygons", C.c_int64),
         ("n_bin_entries", C.c_int64), ("n_samples", C.c_int64), ("n_deep_hits", C.c_int64),
         ("gpu_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+        ("device_bytes", C.c_int64), ("n_bands", C.c_int64), ("gather_ms", C.c_double),
     ]
 
     def as_dict(self):

@@ -16,8 +16,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libaqsis_b200_hider.so")
-SOURCES = ["hider_kernels.cu", "hider_api.cpp", "host_sampling.cpp", "host_filters.cpp"]
-HEADERS = ["hider_device.h", "host_sampling.h", os.path.join("..", "..", "include", "aqsis_b200_hider.h")]
+SOURCES = ["hider_kernels.cu", "hider_api.cpp", "hider_shard.cpp", "host_sampling.cpp", "host_filters.cpp"]
+HEADERS = ["hider_device.h", "hider_internal.h", "host_sampling.h", os.path.join("..", "..", "include", "aqsis_b200_hider.h")]
 
 
 def _nvcc():

@@ -4,8 +4,7 @@
 // pattern planes, lays the shaded grids out in HBM and launches the sm_100a kernels of
 // hider_kernels.cu.  There is deliberately no CPU implementation of the path in here: without
 // a usable device every entry point that would compute returns AQH_ERR_NO_DEVICE.
-#include "hider_device.h"
-#include "host_sampling.h"
+#include "hider_internal.h"
 
 #include <algorithm>
 #include <cfloat>
@@ -14,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -21,73 +21,14 @@ using namespace aqh;
 
 namespace {
 
+// The span filter reads its weights from ONE __constant__ table per device (hider_kernels.cu): hiders that share
+// a device and render from different threads take turns from the table upload to the end of their frame.
+std::mutex g_filterTableMutex[64];
+
 double nowMs()
 {
 	return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
-
-struct DevBuf
-{
-	void* p = nullptr;
-	size_t cap = 0;
-	cudaError_t reserve(size_t bytes)
-	{
-		if(bytes <= cap) return cudaSuccess;
-		if(p) cudaFree(p);
-		p = nullptr; cap = 0;
-		size_t want = bytes + bytes/8 + 256;
-		cudaError_t e = cudaMalloc(&p, want);
-		if(e != cudaSuccess) { want = bytes; e = cudaMalloc(&p, want); }
-		if(e == cudaSuccess) cap = want;
-		return e;
-	}
-	void release() { if(p) cudaFree(p); p = nullptr; cap = 0; }
-	template<class T> T* as() const { return static_cast<T*>(p); }
-};
-
-struct PinnedBuf
-{
-	void* p = nullptr;
-	size_t cap = 0;
-	bool reserve(size_t bytes, bool keep = false, size_t used = 0)
-	{
-		if(bytes <= cap) return true;
-		size_t want = std::max(bytes, cap*2);
-		void* q = nullptr;
-		if(cudaHostAlloc(&q, want, cudaHostAllocDefault) != cudaSuccess) return false;
-		if(keep && p && used) std::memcpy(q, p, used);
-		if(p) cudaFreeHost(p);
-		p = q; cap = want;
-		return true;
-	}
-	void release() { if(p) cudaFreeHost(p); p = nullptr; cap = 0; }
-	template<class T> T* as() const { return static_cast<T*>(p); }
-};
-
-// One contiguous run of grids as handed over by the caller.
-// A growable array in pinned host memory: what is uploaded from it can be copied asynchronously.
-template<class T> struct PinnedVec
-{
-	PinnedBuf b;
-	size_t n = 0;
-	bool ensure(size_t m)
-	{
-		if(m*sizeof(T) <= b.cap) return true;
-		return b.reserve(std::max(m*sizeof(T), size_t(1) << 16), true, n*sizeof(T));
-	}
-	bool push(const T& v) { if(!ensure(n + 1)) return false; b.as<T>()[n++] = v; return true; }
-	T* data() const { return b.as<T>(); }
-	void clear() { n = 0; }
-	void release() { b.release(); n = 0; }
-};
-
-struct Segment
-{
-	int64_t firstGrid = 0, nGrids = 0, nVerts = 0, nPos = 0;
-	const float* P = nullptr; const float* Ci = nullptr; const float* Oi = nullptr; const uint8_t* culled = nullptr;
-	int memorySpace = 0;     // 0 host, 1 device
-	bool staged = false;     // lives in the hider's own pinned staging (pointers are offsets to fix up)
-};
 
 int typeSize(int type)
 {
@@ -115,73 +56,6 @@ int selectDataFormat(float oneVal, float minVal, float maxVal)
 
 } // namespace
 
-struct AqhHider
-{
-	int device = 0;
-	int smCount = 0;
-	cudaStream_t stream = nullptr;
-	bool ownStream = false;
-	std::string lastError;
-	bool inFrame = false, rendered = false;
-	AqhFrameParams params{};
-	ReplayLayout layout{};
-	// frame tables (host) and the key they were built for
-	std::string tableKey, maskLayoutKey;
-	SamplerTables tables;
-	std::vector<uint8_t> patPlanes;
-	std::vector<float> dither, filterTab, dofBounds;
-	std::vector<uint8_t> shuf8;
-	bool tablesUploaded = false;
-	// grids of the frame (host tables)
-	std::vector<int32_t> gcu, gcv, gnkeys;
-	std::vector<uint32_t> gflags;
-	std::vector<float> glod, gkeyTimes;
-	std::vector<Segment> segments;
-	// device-side grid table and the 256-position chunk index, built as the grids are submitted
-	PinnedVec<GridRec> recs;
-	PinnedVec<uint32_t> chunk;
-	uint64_t recVb = 0, recPb = 0, recKo = 0;
-	bool anyMotionG = false, anyLodG = false, anyTriG = false, anyCamG = false;
-	int64_t nVerts = 0, nPos = 0;
-	bool anyCi = false, anyOi = false, anyCulled = false, allCi = true, allOi = true;
-	// pinned staging for aqh_add_grid
-	PinnedBuf stP, stCi, stOi, stCulled;
-	size_t stPUsed = 0, stVUsed = 0;   // floats*3 units: positions / vertices staged
-	// device buffers
-	DevBuf dPraw, dCi, dOi, dCulled, dP4, dCO, dGrids, dChunk, dKeyTimes, dSplit;
-	DevBuf dPosTab, dVal1d, dShuf, dPat, dFilt, dDofB, dDither;
-	DevBuf dTileSlot, dActive, dBinCount, dBinOffset, dBinEntries, dMisc, dTileFlags;
-	DevBuf dPlanes, dMask, dPartials, dDeepA, dDeepUV, dChannels, dRowOwned;
-	DevBuf dDisplay[AQH_MAX_DISPLAYS];
-	DevBuf dOccl;
-	PinnedBuf hOccl;
-	bool haveOccl = false;
-	// tiling
-	int tileW = 0, tileH = 0, ntx = 0, nty = 0;
-	std::vector<int32_t> tileSlot;
-	std::vector<uint32_t> activeTiles;
-	std::vector<uint8_t> rowOwned;
-	std::vector<std::pair<int,int>> strips;
-	std::string stripKey, hostStripKey;   // image geometry + row ownership of the device images / of what the host images hold
-	// outputs (host)
-	PinnedBuf hChannels;
-	PinnedBuf hDisplay[AQH_MAX_DISPLAYS];
-	int dispType[AQH_MAX_DISPLAYS] = {0}, dispEntry[AQH_MAX_DISPLAYS] = {0};
-	bool haveHostImage = false;
-	cudaEvent_t ev[8] = {nullptr};
-	// pipelined upload: host grids travel in chunks on copyStream while the main stream projects/bins the previous chunk
-	cudaStream_t copyStream = nullptr;
-	std::vector<cudaEvent_t> chunkEv;
-	AqhFrameStats stats{};
-
-	int fail(int status, const std::string& msg) { lastError = msg; return status; }
-	int cudaFail(cudaError_t e, const char* what)
-	{
-		lastError = std::string(what) + ": " + cudaGetErrorString(e);
-		return (e == cudaErrorMemoryAllocation) ? AQH_ERR_NO_MEMORY : AQH_ERR_CUDA;
-	}
-};
-
 #define CU(call, what) do { cudaError_t e__ = (call); if(e__ != cudaSuccess) return h->cudaFail(e__, what); } while(0)
 
 namespace {
@@ -204,18 +78,27 @@ int validateParams(AqhHider* h, const AqhFrameParams& p)
 	if(p.crop_xmin < 0 || p.crop_ymin < 0 || p.crop_xmax > p.xres || p.crop_ymax > p.yres ||
 	   p.crop_xmax <= p.crop_xmin || p.crop_ymax <= p.crop_ymin)
 		return h->fail(AQH_ERR_BAD_PARAMS, "crop window must be a non-empty sub-rectangle of the image");
-	if(p.xsamples < 1 || p.ysamples < 1 || p.xsamples*p.ysamples > 256)
-		return h->fail(AQH_ERR_BAD_PARAMS, "PixelSamples must be >= 1 with at most 256 samples per pixel");
+	if(p.xsamples < 1 || p.ysamples < 1 || p.xsamples > 255 || p.ysamples > 255 || p.xsamples*p.ysamples > 256)
+		return h->fail(AQH_ERR_BAD_PARAMS, "PixelSamples must be >= 1, at most 255 per axis and 256 samples per pixel");
 	if(!(p.filter_xwidth > 0.f) || !(p.filter_ywidth > 0.f) || p.filter_xwidth >= 16.f || p.filter_ywidth >= 16.f)
 		return h->fail(AQH_ERR_BAD_PARAMS, "filter widths must be in (0,16)");
 	if(p.bucket_xsize < 1 || p.bucket_ysize < 1) return h->fail(AQH_ERR_BAD_PARAMS, "bucket size must be positive");
 	if(p.n_displays < 0 || p.n_displays > AQH_MAX_DISPLAYS) return h->fail(AQH_ERR_BAD_PARAMS, "too many displays");
+	int aovFloats = 0;
+	if(p.n_aovs < 0 || p.n_aovs > AQH_MAX_AOVS) return h->fail(AQH_ERR_BAD_PARAMS, "too many arbitrary output variables");
+	for(int a = 0; a < p.n_aovs; ++a)
+	{
+		if(p.aov[a].n_floats != 1 && p.aov[a].n_floats != 3 && p.aov[a].n_floats != 16)
+			return h->fail(AQH_ERR_BAD_PARAMS, "an arbitrary output variable has 1, 3 or 16 floats");
+		aovFloats += p.aov[a].n_floats;
+	}
+	if(aovFloats > AQH_MAX_AOV_FLOATS) return h->fail(AQH_ERR_BAD_PARAMS, "too many floats of arbitrary output variables");
 	for(int d = 0; d < p.n_displays; ++d)
 	{
 		const AqhDisplayDesc& dd = p.display[d];
 		if(dd.n_channels < 1 || dd.n_channels > AQH_MAX_DISPLAY_CHANNELS) return h->fail(AQH_ERR_BAD_PARAMS, "display channel count");
 		for(int c = 0; c < dd.n_channels; ++c)
-			if(dd.channel[c] < 0 || dd.channel[c] >= AQH_NUM_CHANNELS) return h->fail(AQH_ERR_BAD_PARAMS, "display channel index");
+			if(dd.channel[c] < 0 || dd.channel[c] >= AQH_NUM_CHANNELS + aovFloats) return h->fail(AQH_ERR_BAD_PARAMS, "display channel index");
 		if(dd.type < 0 || dd.type > AQH_SIGNED8) return h->fail(AQH_ERR_BAD_PARAMS, "display data type");
 	}
 	if(p.depth_filter < AQH_DEPTHFILTER_MIN || p.depth_filter > AQH_DEPTHFILTER_AVERAGE)
@@ -224,8 +107,9 @@ int validateParams(AqhHider* h, const AqhFrameParams& p)
 		return h->fail(AQH_ERR_BAD_PARAMS, "filter_mode");
 	if(p.filter_xwidth >= 16.f || p.filter_ywidth >= 16.f)
 		return h->fail(AQH_ERR_BAD_PARAMS, "filter widths must be below 16");
-	if(p.world_size < 0 || (p.world_size > 0 && (p.rank < 0 || p.rank >= p.world_size)))
+	if(p.world_size < 0 || p.world_size > AQH_MAX_RANKS || (p.world_size > 0 && (p.rank < 0 || p.rank >= p.world_size)))
 		return h->fail(AQH_ERR_BAD_PARAMS, "rank/world_size");
+	if(p.strip_rows < -2) return h->fail(AQH_ERR_BAD_PARAMS, "strip_rows");
 	if(p.use_dof && !(p.dof_one_over_focal_distance != 0.f))
 		return h->fail(AQH_ERR_BAD_PARAMS, "depth of field needs a finite focal distance");
 	return AQH_OK;
@@ -308,7 +192,9 @@ int uploadTables(AqhHider* h)
 //   strip_rows <= 0 (default): balanced -- world*k strips of near-equal height with
 //   k = max(1, rows / (64*world)), so that every rank owns the same number of strips (a fixed
 //   64-row strip leaves 1080 rows as 17 strips: 3 on one of 8 ranks, 2 on the others).
-int stripRows(const AqhFrameParams& p)
+} // namespace
+namespace aqh {
+static int stripRows(const AqhFrameParams& p)
 {
 	return std::max(16, (p.strip_rows/16)*16);
 }
@@ -327,6 +213,30 @@ void computeStrips(const AqhFrameParams& p, int rank, std::vector<std::pair<int,
 		return;
 	}
 	const int64_t rows = std::max(0, p.crop_ymax - p.crop_ymin);
+	if(p.strip_rows == -2 && world > 1)
+	{
+		// explicit boundaries (aqh_balance_strips), clamped to the crop window and kept monotonic
+		int y0 = std::min(std::max(p.strip_bounds[me], p.crop_ymin), p.crop_ymax);
+		int y1 = std::min(std::max(p.strip_bounds[me + 1], p.crop_ymin), p.crop_ymax);
+		if(me == 0) y0 = p.crop_ymin;
+		if(me == world - 1) y1 = p.crop_ymax;
+		if(y1 > y0) strips.push_back(std::make_pair(y0, y1));
+		return;
+	}
+	if(p.strip_rows == -1 && world > 1)
+	{
+		// one contiguous strip per rank; inner boundaries on multiples of 16 rows where the frame is tall enough
+		auto bound = [&](int r) -> int {
+			if(r <= 0) return p.crop_ymin;
+			if(r >= world) return p.crop_ymax;
+			int y = p.crop_ymin + (int)(rows*r/world);
+			if(rows >= 128*(int64_t)world) y = (y/16)*16; else if(rows >= 16*(int64_t)world) y = (y/4)*4;
+			return std::min(std::max(y, p.crop_ymin), p.crop_ymax);
+		};
+		const int y0 = bound(me), y1 = bound(me + 1);
+		if(y1 > y0) strips.push_back(std::make_pair(y0, y1));
+		return;
+	}
 	const int64_t nstrips = (int64_t)world*std::max<int64_t>(1, rows/(64*(int64_t)world));
 	for(int64_t si = me; si < nstrips; si += world)
 	{
@@ -334,6 +244,8 @@ void computeStrips(const AqhFrameParams& p, int rank, std::vector<std::pair<int,
 		if(y1 > y0) strips.push_back(std::make_pair(y0, y1));
 	}
 }
+} // namespace aqh
+namespace {
 
 // Every rank also hides the `shift` rows of halo samples its filter footprint needs.
 void buildTiling(AqhHider* h, bool mbdof)
@@ -349,6 +261,7 @@ void buildTiling(AqhHider* h, bool mbdof)
 		char key[160];
 		std::snprintf(key, sizeof key, "%d %d %d %d %d %d", p.xres, p.yres, p.rank, p.world_size, p.strip_rows, p.n_displays);
 		h->stripKey = key;
+		for(const auto& st : h->strips) { std::snprintf(key, sizeof key, " %d-%d", st.first, st.second); h->stripKey += key; }
 	}
 	std::vector<uint8_t> rowNeeded(L.sh, 0);
 	for(const auto& s : h->strips)
@@ -371,12 +284,41 @@ void buildTiling(AqhHider* h, bool mbdof)
 	}
 }
 
-int appendGridTables(AqhHider* h, int cu, int cv, int nkeys, uint32_t flags, const float* lod, const float* times)
+// Everything about one grid that can be wrong, checked BEFORE any state is touched: a rejected grid or block
+// leaves the frame exactly as it was (the caller may skip it and go on).
+int checkGrid(AqhHider* h, int cu, int cv, int nkeys, uint32_t flags, const float* times)
 {
 	if(cu < 1 || cv < 1 || cu > 65535 || cv > 65535) return h->fail(AQH_ERR_BAD_PARAMS, "grid resolution out of range");
 	if(nkeys < 1 || nkeys > 255) return h->fail(AQH_ERR_BAD_PARAMS, "grid key count out of range");
 	if(flags & AQH_GRID_USES_CSG) return h->fail(AQH_ERR_UNSUPPORTED, "CSG grids are not supported");
 	if(nkeys > 1 && !times) return h->fail(AQH_ERR_BAD_PARAMS, "motion grid without key times");
+	return AQH_OK;
+}
+
+// Sizes of the per-frame grid tables, to undo a partly appended block when an allocation fails half way.
+struct GridTablesMark
+{
+	size_t nGrids, nKeyTimes, nRecs, nChunk;
+	uint64_t recVb, recPb, recKo;
+	bool anyMotionG, anyLodG, anyTriG, anyCamG;
+};
+GridTablesMark markGridTables(const AqhHider* h)
+{
+	return GridTablesMark{h->gcu.size(), h->gkeyTimes.size(), h->recs.n, h->chunk.n, h->recVb, h->recPb, h->recKo,
+	                      h->anyMotionG, h->anyLodG, h->anyTriG, h->anyCamG};
+}
+void rollbackGridTables(AqhHider* h, const GridTablesMark& m)
+{
+	h->gcu.resize(m.nGrids); h->gcv.resize(m.nGrids); h->gnkeys.resize(m.nGrids); h->gflags.resize(m.nGrids);
+	h->glod.resize(2*m.nGrids); h->gkeyTimes.resize(m.nKeyTimes);
+	h->recs.n = m.nRecs; h->chunk.n = m.nChunk;
+	h->recVb = m.recVb; h->recPb = m.recPb; h->recKo = m.recKo;
+	h->anyMotionG = m.anyMotionG; h->anyLodG = m.anyLodG; h->anyTriG = m.anyTriG; h->anyCamG = m.anyCamG;
+}
+
+int appendGridTables(AqhHider* h, int cu, int cv, int nkeys, uint32_t flags, const float* lod, const float* times)
+{
+	if(h->recKo + (uint64_t)nkeys >= (1u << 24)) return h->fail(AQH_ERR_BAD_PARAMS, "too many motion keys in one frame");
 	h->gcu.push_back(cu); h->gcv.push_back(cv); h->gnkeys.push_back(nkeys); h->gflags.push_back(flags);
 	h->glod.push_back(lod ? lod[0] : -1.f); h->glod.push_back(lod ? lod[1] : -1.f);
 	for(int k = 0; k < nkeys; ++k) h->gkeyTimes.push_back(nkeys > 1 ? times[k] : 0.f);
@@ -401,7 +343,6 @@ int appendGridTables(AqhHider* h, int cu, int cv, int nkeys, uint32_t flags, con
 	h->anyMotionG |= nkeys > 1; h->anyLodG |= r.lod0 >= 0.f;
 	h->anyTriG |= (flags & AQH_GRID_TRIANGULAR) != 0; h->anyCamG |= (flags & AQH_GRID_CAMERA_SPACE) != 0;
 	h->recVb += nv; h->recPb += np; h->recKo += (uint64_t)nkeys;
-	if(h->recKo >= (1u << 24)) return h->fail(AQH_ERR_BAD_PARAMS, "too many motion keys in one frame");
 	return AQH_OK;
 }
 
@@ -461,16 +402,31 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 	CU(h->dTileFlags.reserve(std::max<size_t>(nActive, 1)*4), "cudaMalloc(tile flags)");
 	CU(h->dMisc.reserve(256), "cudaMalloc(counters)");
 	CU(h->dRowOwned.reserve(p.yres), "cudaMalloc(row ownership)");
-	// resolved-sample planes [k][y][chunk][x][planeSC] (hider_device.h)
+	// resolved-sample planes [k][row][chunk][x][planeSC] (hider_device.h).  They hold the whole sample region when that
+	// fits AqhFrameParams::plane_budget_mb; otherwise ringRows rows at a time, and the frame is hidden and filtered in
+	// bands of tile rows (the reference's own memory bound is one bucket plus its overlap, bucketprocessor.cpp:259-358).
 	const int nSamp = p.xsamples*p.ysamples;
 	const int planeSC = std::min((nSamp + 3) & ~3, 64);
 	const int planeChunks = (nSamp + planeSC - 1)/planeSC;
 	const int planeW = ((L.sw + 31) & ~31) + 16;     // the filter stages spans of up to 32+14 pixels starting at multiples of 32
-	const size_t planeStride = size_t(planeW)*L.sh*planeChunks*planeSC;
 	const int ntaps = (2*L.shiftX+1)*(2*L.shiftY+1);
-	if(p.filter_mode == AQH_FILTER_REFERENCE_ORDER)
+	const size_t planeRowBytes = size_t(planeW)*planeChunks*planeSC*8*4;          // 7 value planes + the mask plane
+	int ringRows = L.sh, bandTileRows = h->nty;
+	if(p.filter_mode == AQH_FILTER_REFERENCE_ORDER && !zOnly)
 	{
-		CU(h->dPlanes.reserve(planeStride*8*4 + 256), "cudaMalloc(sample planes)");   // 7 value planes + the mask plane
+		const size_t budget = size_t(p.plane_budget_mb > 0 ? p.plane_budget_mb : 4608) << 20;
+		const size_t fit = budget/planeRowBytes;
+		if(fit < size_t(L.sh))
+		{
+			bandTileRows = (int)std::max<int64_t>(1, (int64_t(fit) - 2*L.shiftY)/h->tileH);
+			ringRows = std::min(L.sh, bandTileRows*h->tileH + 2*L.shiftY);
+		}
+	}
+	const size_t planeStride = size_t(planeW)*ringRows*planeChunks*planeSC;
+	if(zOnly) {}
+	else if(p.filter_mode == AQH_FILTER_REFERENCE_ORDER)
+	{
+		CU(h->dPlanes.reserve(planeStride*8*4 + 256), "cudaMalloc(sample planes)");
 	}
 	else
 		CU(h->dPartials.reserve(size_t(ntaps)*9*L.sw*L.sh*4), "cudaMalloc(tap partial sums)");
@@ -650,17 +606,16 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 	f.tileSlot = h->dTileSlot.as<int32_t>(); f.activeTiles = h->dActive.as<uint32_t>();
 	f.binCount = h->dBinCount.as<uint32_t>(); f.binOffset = h->dBinOffset.as<uint32_t>();
 	f.tileFlags = h->dTileFlags.as<uint32_t>();
-	f.tileCursor = h->dMisc.as<uint32_t>();
 	f.errorFlags = h->dMisc.as<uint32_t>() + 1;
 	f.counters = reinterpret_cast<unsigned long long*>(h->dMisc.as<unsigned char>() + 16);
 	f.planes = h->dPlanes.as<float>(); f.maskPlane = reinterpret_cast<unsigned char*>(h->dPlanes.as<float>() + 7*planeStride);
-	{ const int mbits = 2*L.shiftX + 2*L.shiftY + 3; f.maskBytes = mbits <= 8 ? 1 : (mbits <= 16 ? 2 : 4); } f.planeStride = (int64_t)planeStride; f.planeW = planeW; f.planeSC = planeSC; f.planeChunks = planeChunks;
+	{ const int mbits = 2*L.shiftX + 2*L.shiftY + 3; f.maskBytes = mbits <= 8 ? 1 : (mbits <= 16 ? 2 : 4); } f.planeStride = (int64_t)planeStride; f.planeW = planeW; f.planeSC = planeSC; f.planeChunks = planeChunks; f.ringRows = ringRows;
 	f.filterMode = p.filter_mode; f.partials = h->dPartials.as<float>(); f.ntaps = ntaps;
 	f.channels = h->dChannels.as<float>();
 	f.occlImage = nullptr; f.zOnly = zOnly ? 1 : 0;
 	if(zOnly)
 	{
-		CU(h->dOccl.reserve(size_t(p.xres)*p.yres*4), "cudaMalloc(occlusion image)");
+		CU(h->dOccl.reserve(size_t(L.sw)*L.sh*4), "cudaMalloc(occlusion image)");
 		f.occlImage = h->dOccl.as<float>();
 	}
 	f.rowOwned = (std::max(1, p.world_size) > 1) ? h->dRowOwned.as<uint8_t>() : nullptr;
@@ -734,15 +689,73 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 	CU(cudaEventRecord(h->ev[1], st), "cudaEventRecord");
 	if(zOnly)
 	{
-		// every pixel starts uncovered (FLT_MAX); tiles this rank does not hide stay that way
-		std::vector<float> inf(size_t(p.xres)*p.yres, FLT_MAX);
+		// every pixel of the sample region starts uncovered (FLT_MAX); tiles this rank does not hide stay that way
+		std::vector<float> inf(size_t(L.sw)*L.sh, FLT_MAX);
 		CU(cudaMemcpyAsync(h->dOccl.p, inf.data(), inf.size()*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(occlusion image)");
 		CU(cudaStreamSynchronize(st), "cudaStreamSynchronize");
 	}
-	CU(launchHide(f, cfg, st), "k_hide"); S.gpu_launches += nActive ? 1 : 0;
-	CU(cudaEventRecord(h->ev[2], st), "cudaEventRecord");
-	tr.mark("launched hide");
-	if(!zOnly) { CU(launchFilter(f, disp, h->filterTab.data(), st), "k_filter"); S.gpu_launches += 1; }
+	// ---- bands: consecutive active tile rows, at most bandTileRows of them, hidden by one launch each; the output rows
+	// whose whole filter footprint is then in the planes are filtered before the next band overwrites the ring
+	struct Band { uint32_t slotBeg, slotEnd; int rowBeg, rowEnd; bool firstOfRun; };   // rows: sample rows relative to sy0
+	std::vector<Band> bands;
+	{
+		int prevTy = -2;
+		for(int i = 0; i < nActive; i += h->ntx)
+		{
+			const int ty = (int)(h->activeTiles[i]/(uint32_t)h->ntx);
+			const bool contiguous = ty == prevTy + 1;
+			if(bands.empty() || !contiguous || (bands.back().rowEnd - bands.back().rowBeg) >= bandTileRows*h->tileH)
+				bands.push_back(Band{(uint32_t)i, (uint32_t)i, ty*h->tileH, ty*h->tileH, !contiguous});
+			bands.back().slotEnd = (uint32_t)(i + h->ntx);
+			bands.back().rowEnd = std::min((ty + 1)*h->tileH, L.sh);
+			prevTy = ty;
+		}
+	}
+	S.n_bands = (int64_t)bands.size();
+	CU(h->dBandCursor.reserve(std::max<size_t>(bands.size(), 1)*4), "cudaMalloc(band cursors)");
+	CU(cudaMemsetAsync(h->dBandCursor.p, 0, std::max<size_t>(bands.size(), 1)*4, st), "cudaMemsetAsync");
+	std::unique_lock<std::mutex> filterTable(g_filterTableMutex[h->device & 63], std::defer_lock);
+	// stage times: one event after every launch (hide and filter launches of several bands interleave)
+	while(h->bandEv.size() < 2*bands.size() + 1)
+	{
+		cudaEvent_t e; CU(cudaEventCreate(&e), "cudaEventCreate");
+		h->bandEv.push_back(e);
+	}
+	CU(cudaEventRecord(h->bandEv[0], st), "cudaEventRecord");
+	std::vector<int> bandEvKind;                          // per recorded event after bandEv[0]: 0 = a hide launch ended, 1 = a filter launch ended
+	bool tableUp = false;
+	int filtNext = 0;                                     // next output row (relative to the crop window) to filter
+	for(size_t b = 0; b < bands.size(); ++b)
+	{
+		const Band& bd = bands[b];
+		CU(launchHide(f, cfg, bd.slotBeg, bd.slotEnd, h->dBandCursor.as<uint32_t>() + b, st), "k_hide"); S.gpu_launches += 1;
+		bandEvKind.push_back(0);
+		CU(cudaEventRecord(h->bandEv[bandEvKind.size()], st), "cudaEventRecord");
+		if(zOnly) continue;
+		if(b == 0)
+		{
+			filterTable.lock();      // released when this function returns (the frame is synchronised by then)
+			tr.mark("launched hide");
+		}
+		// output row r (relative to the crop window) reads the sample rows r .. r + 2*shiftY
+		if(bd.firstOfRun) filtNext = bd.rowBeg;
+		int filtEnd = bd.rowEnd - 2*L.shiftY;
+		if(p.filter_mode != AQH_FILTER_REFERENCE_ORDER)
+		{
+			// the tap partial sums cover the whole frame: one filter launch after the last band
+			if(b + 1 < bands.size()) continue;
+			filtNext = 0; filtEnd = L.sh - 2*L.shiftY;
+		}
+		const int y0 = p.crop_ymin + std::max(filtNext, 0), y1 = std::min(p.crop_ymin + filtEnd, p.crop_ymax);
+		if(y1 > y0)
+		{
+			CU(launchFilter(f, disp, h->filterTab.data(), y0, y1, !tableUp, st), "k_filter"); S.gpu_launches += 1;
+			tableUp = true;
+			bandEvKind.push_back(1);
+			CU(cudaEventRecord(h->bandEv[bandEvKind.size()], st), "cudaEventRecord");
+		}
+		filtNext = std::max(filtNext, filtEnd);
+	}
 	CU(cudaEventRecord(h->ev[3], st), "cudaEventRecord");
 
 	// ---- results
@@ -751,12 +764,22 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 	tr.mark("launched filter");
 	const double tDown0 = nowMs();
 	S.d2h_bytes = 0;
+	// With a communicator the strips are gathered on the device first (aqh_gather): rank 0 then downloads the whole
+	// frame and the other ranks nothing.
+	const bool gathered = download && h->comm && std::max(1, p.world_size) > 1;
+	if(gathered)
+	{
+		h->rendered = true;
+		rc = aqh_gather(h, 0);
+		if(rc) return rc;
+		if(p.rank != 0) download = false;
+	}
 	if(download)
 	{
 		// Only the pixel rows this rank owns travel back (all of them on a single rank); the rest of the host
 		// images stays zero, like the device images.
 		const size_t chRow = size_t(p.xres)*9*4, chBytes = chRow*p.yres;
-		const bool sharded = std::max(1, p.world_size) > 1;
+		const bool sharded = std::max(1, p.world_size) > 1 && !gathered;
 		const bool firstCh = h->hChannels.cap < chBytes;
 		if(!h->hChannels.reserve(chBytes)) return h->fail(AQH_ERR_NO_MEMORY, "cudaHostAlloc(channel image)");
 		if(sharded && (firstCh || h->hostStripKey != h->stripKey)) std::memset(h->hChannels.p, 0, chBytes);
@@ -785,7 +808,7 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 	}
 	if(zOnly)
 	{
-		const size_t ob = size_t(p.xres)*p.yres*4;
+		const size_t ob = size_t(L.sw)*L.sh*4;
 		if(!h->hOccl.reserve(ob)) return h->fail(AQH_ERR_NO_MEMORY, "cudaHostAlloc(occlusion image)");
 		CU(cudaMemcpyAsync(h->hOccl.p, h->dOccl.p, ob, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(occlusion image)");
 		S.d2h_bytes += (int64_t)ob;
@@ -797,12 +820,27 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 	if(zOnly) h->haveOccl = true;
 	float ms = 0;
 	cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); S.project_bust_ms = ms;
-	cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); S.render_mpgs_ms = ms;
-	cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); S.filter_ms = ms; S.display_ms = 0;
+	S.render_mpgs_ms = 0; S.filter_ms = 0; S.display_ms = 0;
+	for(size_t i = 0; i < bandEvKind.size(); ++i)
+	{
+		cudaEventElapsedTime(&ms, h->bandEv[i], h->bandEv[i + 1]);
+		(bandEvKind[i] ? S.filter_ms : S.render_mpgs_ms) += ms;
+	}
 	cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]); S.device_total_ms = ms;
+	S.gather_ms = 0;
+	if(h->gatherPending) { cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); S.gather_ms = ms; h->gatherPending = false; }
 	S.n_grids = nGrids; S.n_vertices = h->nVerts;
 	S.n_micropolygons = (int64_t)misc.ctr[0]; S.n_bin_entries = (int64_t)misc.ctr[1]; S.n_deep_hits = (int64_t)misc.ctr[2];
 	S.n_samples = int64_t(L.sw)*L.sh*f.n;
+	{
+		const DevBuf* all[] = {&h->dPraw, &h->dCi, &h->dOi, &h->dCulled, &h->dP4, &h->dCO, &h->dGrids, &h->dChunk, &h->dKeyTimes, &h->dSplit,
+		                       &h->dPosTab, &h->dVal1d, &h->dShuf, &h->dPat, &h->dFilt, &h->dDofB, &h->dDither, &h->dTileSlot, &h->dActive,
+		                       &h->dBinCount, &h->dBinOffset, &h->dBinEntries, &h->dMisc, &h->dTileFlags, &h->dPlanes, &h->dPartials,
+		                       &h->dDeepA, &h->dDeepUV, &h->dChannels, &h->dRowOwned, &h->dOccl, &h->dBandCursor};
+		S.device_bytes = 0;
+		for(const DevBuf* b : all) S.device_bytes += (int64_t)b->cap;
+		for(int d = 0; d < AQH_MAX_DISPLAYS; ++d) S.device_bytes += (int64_t)h->dDisplay[d].cap;
+	}
 	h->rendered = true;
 	tr.mark("stats");
 	if(misc.err & 1u)
@@ -844,7 +882,8 @@ int aqh_destroy(AqhHider* h)
 	if(!h) return AQH_OK;
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->stream);
-	DevBuf* bufs[] = {&h->dPraw, &h->dCi, &h->dOi, &h->dCulled, &h->dP4, &h->dGrids, &h->dChunk, &h->dKeyTimes, &h->dSplit,
+	aqh_comm_destroy(h);
+	DevBuf* bufs[] = {&h->dPraw, &h->dCi, &h->dOi, &h->dCulled, &h->dP4, &h->dCO, &h->dGrids, &h->dChunk, &h->dKeyTimes, &h->dSplit,
 	                  &h->dPosTab, &h->dVal1d, &h->dShuf, &h->dPat, &h->dFilt, &h->dDofB, &h->dDither, &h->dTileSlot, &h->dActive,
 	                  &h->dBinCount, &h->dBinOffset, &h->dBinEntries, &h->dMisc, &h->dTileFlags, &h->dPlanes, &h->dMask, &h->dPartials,
 	                  &h->dDeepA, &h->dDeepUV, &h->dChannels, &h->dRowOwned};
@@ -854,6 +893,7 @@ int aqh_destroy(AqhHider* h)
 	h->hChannels.release(); h->stP.release(); h->stCi.release(); h->stOi.release(); h->stCulled.release();
 	for(int i = 0; i < 8; ++i) if(h->ev[i]) cudaEventDestroy(h->ev[i]);
 	for(cudaEvent_t e : h->chunkEv) cudaEventDestroy(e);
+	for(cudaEvent_t e : h->bandEv) cudaEventDestroy(e);
 	if(h->copyStream) cudaStreamDestroy(h->copyStream);
 	if(h->ownStream && h->stream) cudaStreamDestroy(h->stream);
 	delete h;
@@ -959,8 +999,11 @@ int aqh_add_grid(AqhHider* h, const AqhGridDesc* g)
 	if(!h || !g) return AQH_ERR_BAD_PARAMS;
 	if(!h->inFrame) return h->fail(AQH_ERR_STATE, "aqh_add_grid outside aqh_begin_frame/aqh_end_frame");
 	if(!g->P) return h->fail(AQH_ERR_BAD_PARAMS, "grid without P");
-	int rc = appendGridTables(h, g->cu, g->cv, g->nkeys, g->flags, g->lod_bounds, g->key_times);
+	// every check and every allocation comes before the first change of state
+	int rc = checkGrid(h, g->cu, g->cv, g->nkeys, g->flags, g->key_times);
 	if(rc) return rc;
+	for(int k = 0; k < g->nkeys; ++k)
+		if(!g->P[k]) return h->fail(AQH_ERR_BAD_PARAMS, "grid key without P");
 	const size_t nv = size_t(g->cu+1)*(g->cv+1), np = nv*g->nkeys;
 	// copy into the pinned staging run (the caller keeps ownership of its arrays)
 	if(!h->stP.reserve((h->stPUsed + np)*12, true, h->stPUsed*12) ||
@@ -968,11 +1011,13 @@ int aqh_add_grid(AqhHider* h, const AqhGridDesc* g)
 	   !h->stOi.reserve((h->stVUsed + nv)*12, true, h->stVUsed*12) ||
 	   !h->stCulled.reserve(h->stVUsed + nv, true, h->stVUsed))
 		return h->fail(AQH_ERR_NO_MEMORY, "cudaHostAlloc(grid staging)");
-	for(int k = 0; k < g->nkeys; ++k)
 	{
-		if(!g->P[k]) return h->fail(AQH_ERR_BAD_PARAMS, "grid key without P");
-		std::memcpy(h->stP.as<float>() + (h->stPUsed + size_t(k)*nv)*3, g->P[k], nv*12);
+		const GridTablesMark mark = markGridTables(h);
+		rc = appendGridTables(h, g->cu, g->cv, g->nkeys, g->flags, g->lod_bounds, g->key_times);
+		if(rc) { rollbackGridTables(h, mark); return rc; }
 	}
+	for(int k = 0; k < g->nkeys; ++k)
+		std::memcpy(h->stP.as<float>() + (h->stPUsed + size_t(k)*nv)*3, g->P[k], nv*12);
 	float* ci = h->stCi.as<float>() + h->stVUsed*3;
 	float* oi = h->stOi.as<float>() + h->stVUsed*3;
 	if(g->Ci) std::memcpy(ci, g->Ci, nv*12); else std::fill(ci, ci + nv*3, 1.0f);
@@ -1014,12 +1059,22 @@ int aqh_add_grid_block(AqhHider* h, const AqhGridBlock* b)
 	s.P = b->P; s.Ci = b->Ci; s.Oi = b->Oi; s.culled = b->culled;
 	s.memorySpace = b->memory_space;
 	size_t ko = 0;
+	// a block is accepted or rejected as a whole: all of its grids are checked before the first one is appended
+	for(int64_t g = 0; g < b->n_grids; ++g)
+	{
+		const int nk = b->nkeys ? b->nkeys[g] : 1;
+		int rc = checkGrid(h, b->cu[g], b->cv[g], nk, b->flags[g], (b->key_times && nk > 1) ? b->key_times + ko : nullptr);
+		if(rc) return rc;
+		ko += nk;
+	}
+	ko = 0;
+	const GridTablesMark mark = markGridTables(h);
 	for(int64_t g = 0; g < b->n_grids; ++g)
 	{
 		const int nk = b->nkeys ? b->nkeys[g] : 1;
 		int rc = appendGridTables(h, b->cu[g], b->cv[g], nk, b->flags[g], b->lod_bounds ? b->lod_bounds + 2*g : nullptr,
 		                          (b->key_times && nk > 1) ? b->key_times + ko : nullptr);
-		if(rc) return rc;
+		if(rc) { rollbackGridTables(h, mark); return rc; }
 		ko += nk;
 		const int64_t nv = int64_t(b->cu[g]+1)*(b->cv[g]+1);
 		s.nVerts += nv; s.nPos += nv*nk;
@@ -1059,14 +1114,19 @@ int aqh_can_cull(const AqhHider* h, const float bound[6], int* culled)
 		return AQH_OK;
 	const float xmin = bound[0], ymin = bound[1], zmin = bound[2], xmax = bound[3], ymax = bound[4];
 	if(!(xmin <= xmax) || !(ymin <= ymax)) return AQH_ERR_BAD_PARAMS;
-	// pixels the bound touches, inside the crop window (canCull crops to the tree's bound, occlusion.cpp:164-168)
-	const float fx0 = std::max(std::floor(xmin), (float)p.crop_xmin), fx1 = std::min(std::floor(xmax) + 1.0f, (float)p.crop_xmax);
-	const float fy0 = std::max(std::floor(ymin), (float)p.crop_ymin), fy1 = std::min(std::floor(ymax) + 1.0f, (float)p.crop_ymax);
-	if(!(fx0 < fx1) || !(fy0 < fy1)) { *culled = 1; return AQH_OK; }      // nothing of it can reach a sample
+	// The occlusion image covers the SAMPLE region [crop - shift, crop + shift): every pixel of it carries samples
+	// (the halo pixels are filtered into the border pixels) and belongs to exactly one bucket's CqOcclusionTree
+	// (setupTree, occlusion.cpp:54-104).  canCull crops the bound to the tree (occlusion.cpp:164-168) and compares
+	// inclusively, so a bound that ends exactly on a pixel edge still touches the pixel beyond it.
+	const ReplayLayout& L = h->layout;
+	const float rx0 = (float)L.sx0, ry0 = (float)L.sy0, rx1 = (float)(L.sx0 + L.sw), ry1 = (float)(L.sy0 + L.sh);
+	if(xmax < rx0 || ymax < ry0 || xmin > rx1 || ymin > ry1) { *culled = 1; return AQH_OK; }   // no sample can be reached
+	const float fx0 = std::max(std::ceil(xmin) - 1.0f, rx0), fx1 = std::min(std::floor(xmax) + 1.0f, rx1);
+	const float fy0 = std::max(std::ceil(ymin) - 1.0f, ry0), fy1 = std::min(std::floor(ymax) + 1.0f, ry1);
 	const float* occl = h->hOccl.as<float>();
 	for(int y = (int)fy0; y < (int)fy1; ++y)
 		for(int x = (int)fx0; x < (int)fx1; ++x)
-			if(!(occl[size_t(y)*p.xres + x] < zmin)) return AQH_OK;
+			if(!(occl[size_t(y - L.sy0)*L.sw + (x - L.sx0)] < zmin)) return AQH_OK;
 	*culled = 1;
 	return AQH_OK;
 }
@@ -1082,6 +1142,7 @@ int aqh_end_frame(AqhHider* h, const AqhCallbacks* cb)
 	h->inFrame = false;
 	if(rc) return rc;
 	if(!cb || (!cb->on_bucket && !cb->on_data && !cb->on_progress)) return AQH_OK;
+	if(!h->haveHostImage) return AQH_OK;          // a rank whose strips were gathered to rank 0: the displays live there
 	// Buckets in the reference's row-major order (imagebuffer.cpp:708-733, NextBucket :791-802).
 	const AqhFrameParams& p = h->params;
 	const ReplayLayout& L = h->layout;
@@ -1096,7 +1157,7 @@ int aqh_end_frame(AqhHider* h, const AqhCallbacks* cb)
 			if(cb->on_bucket)
 			{
 				const float* ch = h->hChannels.as<float>() + (size_t(yPos)*p.xres + xPos)*9;
-				if(cb->on_bucket(cb->user, xPos, xPos + xSize, yPos, yPos + ySize, ch, p.xres*9))
+				if(cb->on_bucket(cb->user, xPos, xPos + xSize, yPos, yPos + ySize, ch, p.xres*9, 9))
 					return h->fail(AQH_ERR_CALLBACK, "on_bucket callback failed");
 			}
 			if(cb->on_data)
@@ -1114,6 +1175,55 @@ int aqh_end_frame(AqhHider* h, const AqhCallbacks* cb)
 			if(cb->on_progress) cb->on_progress(cb->user, (100.0f*done)/static_cast<float>(total));
 		}
 	if(cb->on_progress) cb->on_progress(cb->user, 100.0f);
+	return AQH_OK;
+}
+
+int aqh_set_csg_tree(AqhHider* h, int n_nodes, const int32_t* type, const int32_t* parent)
+{
+	if(!h) return AQH_ERR_BAD_PARAMS;
+	(void)n_nodes; (void)type; (void)parent;
+	return h->fail(AQH_ERR_UNSUPPORTED, "CSG trees are not supported");
+}
+
+int aqh_clear_caches(AqhHider* h)
+{
+	if(!h) return AQH_ERR_BAD_PARAMS;
+	if(h->inFrame) return h->fail(AQH_ERR_STATE, "aqh_clear_caches inside a frame");
+	h->tableKey.clear(); h->tablesUploaded = false;
+	return AQH_OK;
+}
+
+int aqh_capture_on_bucket(void* user, int xmin, int xmax1, int ymin, int ymax1, const float* channels, int row_stride_floats, int pixel_stride_floats)
+{
+	AqhCapture* c = static_cast<AqhCapture*>(user);
+	if(!c) return 1;
+	c->buckets += 1;
+	if(!c->channels) return 0;
+	if(pixel_stride_floats != c->n_channels || xmin < 0 || ymin < 0 || xmax1 > c->xres || ymax1 > c->yres) return 1;
+	const size_t rowBytes = size_t(xmax1 - xmin)*pixel_stride_floats*4;
+	for(int y = ymin; y < ymax1; ++y)
+		std::memcpy(c->channels + (size_t(y)*c->xres + xmin)*c->n_channels, channels + size_t(y - ymin)*row_stride_floats, rowBytes);
+	c->bytes += (int64_t)rowBytes*(ymax1 - ymin);
+	return 0;
+}
+
+int aqh_capture_on_data(void* user, int display, int xmin, int xmax1, int ymin, int ymax1, int entrysize, const unsigned char* data)
+{
+	AqhCapture* c = static_cast<AqhCapture*>(user);
+	if(!c || display < 0 || display >= AQH_MAX_DISPLAYS) return 1;
+	if(!c->display[display]) return 0;
+	if(xmin < 0 || ymin < 0 || xmax1 > c->xres || ymax1 > c->yres) return 1;
+	const size_t rowBytes = size_t(xmax1 - xmin)*entrysize;
+	for(int y = ymin; y < ymax1; ++y)
+		std::memcpy(c->display[display] + (size_t(y)*c->xres + xmin)*entrysize, data + size_t(y - ymin)*rowBytes, rowBytes);
+	c->bytes += (int64_t)rowBytes*(ymax1 - ymin);
+	return 0;
+}
+
+int aqh_channel_count(const AqhHider* h, int* n)
+{
+	if(!h || !n) return AQH_ERR_BAD_PARAMS;
+	*n = h->nChannels;
 	return AQH_OK;
 }
 
@@ -1168,7 +1278,6 @@ int aqh_strip_layout(const AqhFrameParams* p, int rank, int* n_strips, int* y0, 
 	const int world = std::max(1, p->world_size);
 	if(rank < 0 || rank >= world) return AQH_ERR_BAD_PARAMS;
 	std::vector<std::pair<int,int>> strips;
-	std::string stripKey, hostStripKey;   // image geometry + row ownership of the device images / of what the host images hold
 	computeStrips(*p, rank, strips);
 	*n_strips = (int)strips.size();
 	for(int i = 0; i < (int)strips.size() && i < capacity; ++i)

@@ -83,7 +83,6 @@ struct DevFrame
 	uint32_t* binOffset;           // nActiveTiles+1
 	unsigned long long* binEntries; // per tile: (depthKey(zmin) << 32 | position index), sorted ascending
 	int sortRun;                   // bins are sorted ascending in runs of this many entries
-	uint32_t* tileCursor;          // persistent-CTA work counter
 	uint32_t* tileFlags;           // per active tile: bit0 = has non-opaque MPs
 	// resolved samples: planes [k][y][chunk][x][planeSC] over the sample region: the samples of a pixel are
 	// split in planeChunks chunks of planeSC (<= 64, a multiple of 4) slots, pixel rows padded to planeW pixels
@@ -93,8 +92,10 @@ struct DevFrame
 	unsigned char* maskPlane;      // per slot one compact word of maskBytes (1, 2 or 4) bytes: bits [0, 2*shiftX] x-tap inclusion,
 	                               // the next 2*shiftY+1 bits y-tap inclusion, then one bit "holds a valid hit"
 	int maskBytes;
-	int64_t planeStride;           // sh*planeChunks*planeW*planeSC
+	int64_t planeStride;           // ringRows*planeChunks*planeW*planeSC
 	int planeW, planeSC, planeChunks;
+	int ringRows;                  // sample rows the planes hold at a time: row y lives at (y - sy0) % ringRows.  The whole
+	                               // sample region when the frame fits AqhFrameParams::plane_budget_mb, else a ring over bands
 	// tile-partials filter mode: per (tap, value, y, x) partial sums over a pixel's samples;
 	// values: 0 gTot, 1 hit count, 2..8 R G B Or Og Ob Z
 	int filterMode;                // AQH_FILTER_*
@@ -110,7 +111,7 @@ struct DevFrame
 	float* channels;               // xres*yres*9
 	// occlusion feedback (aqh_flush): per image pixel the farthest occlusion depth over the pixel's samples
 	// (FLT_MAX while any sample is uncovered); with zOnly the tile stops there -- no resolve, no filter input
-	float* occlImage;              // xres*yres or null
+	float* occlImage;              // sw*sh (the sample region) or null
 	int zOnly;
 	const uint8_t* rowOwned;       // yres: 1 when this rank owns the pixel row
 };
@@ -144,8 +145,8 @@ cudaError_t launchProjectCount(const DevFrame& f, int64_t pA, int64_t pB, cudaSt
 cudaError_t launchSplitLines(const DevFrame& f, cudaStream_t st);
 cudaError_t launchBinScan(const DevFrame& f, cudaStream_t st);
 cudaError_t launchBinFill(const DevFrame& f, cudaStream_t st);
-cudaError_t launchHide(const DevFrame& f, const LaunchCfg& cfg, cudaStream_t st);
-cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, const float* hostFilterTab, cudaStream_t st);
+cudaError_t launchHide(const DevFrame& f, const LaunchCfg& cfg, uint32_t slotBeg, uint32_t slotEnd, uint32_t* cursor, cudaStream_t st);
+cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, const float* hostFilterTab, int yBeg, int yEnd, bool uploadTable, cudaStream_t st);
 cudaError_t hideKernelConfig(const DevFrame& f, int smCount, LaunchCfg& cfg);
 int kernelsArchOk();   // 1 when the loaded kernel image can run on the current device
 

@@ -16,6 +16,7 @@
 //                (bucketprocessor.cpp:584-707, 766-806; ddmanager.cpp:1022-1118)
 #include "hider_device.h"
 
+#include <algorithm>
 #include <cfloat>
 
 namespace aqh {
@@ -275,7 +276,6 @@ __global__ void __launch_bounds__(1024) k_bin_scan(DevFrame f)
 		f.binCount[i] = 0;
 	}
 	if(threadIdx.x == 1023) f.binOffset[n] = s_part[1023];
-	if(threadIdx.x == 0) *f.tileCursor = 0;
 }
 
 // Order every tile's bin front to back (ascending nearest depth, ties by submission order).
@@ -1662,7 +1662,7 @@ __device__ __forceinline__ uint32_t loadMask(const DevFrame& f, size_t at)
 // lanes -- so there is no CTA-wide barrier inside the micropolygon loop.
 // DFGEN: a depth filter other than "min" (kept out of the common kernels: its bookkeeping costs registers)
 template<bool MBDOF, int THREADS, bool PARTIALS, bool DFGEN>
-__global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevFrame f)
+__global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevFrame f, uint32_t slotBeg, uint32_t slotEnd, uint32_t* cursor)
 {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
 	__shared__ uint32_t s_tile;
@@ -1686,10 +1686,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 	for(;;)
 	{
 		__syncthreads();
-		if(tid == 0) { s_tile = atomicAdd(f.tileCursor, 1u); s_deepCount = 0; s_next = 0; }
+		// one band of tile rows per launch: active tiles [slotBeg, slotEnd), handed out through the band's own cursor
+		if(tid == 0) { s_tile = slotBeg + atomicAdd(cursor, 1u); s_deepCount = 0; s_next = 0; }
 		__syncthreads();
 		const uint32_t slot = s_tile;
-		if(slot >= (uint32_t)f.nActiveTiles) break;
+		if(slot >= slotEnd) break;
 		const uint32_t tile = f.activeTiles[slot];
 		TileCtx t;
 		t.tileX0 = f.sx0 + (int)(tile % f.ntx)*f.tileW;
@@ -1852,8 +1853,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 			{
 				const int ly = pix / tw0, lx = pix - ly*tw0;
 				const int X = t.rx0 + lx, Y = t.ry0 + ly;
-				if(X >= 0 && X < f.xres && Y >= 0 && Y < f.yres)
-					f.occlImage[(size_t)Y*f.xres + X] = keyDepth(s.pixZ[ly*f.tileW + lx]);
+				f.occlImage[(size_t)(Y - f.sy0)*f.sw + (X - f.sx0)] = keyDepth(s.pixZ[ly*f.tileW + lx]);
 			}
 			if(f.zOnly) continue;          // the next tile's first barrier orders the reads of pixZ above
 		}
@@ -1867,7 +1867,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 			{
 				const int ly = pix / tw, lx = pix - ly*tw;
 				const int X = t.rx0 + lx, Y = t.ry0 + ly;
-				const size_t rowAt = (size_t)(Y - f.sy0)*nCh*f.planeW + (size_t)(X - f.sx0);
+				// the planes hold ringRows sample rows at a time (a ring over the bands of the frame)
+				const size_t rowAt = (size_t)((Y - f.sy0) % f.ringRows)*nCh*f.planeW + (size_t)(X - f.sx0);
 				for(int i = lane; i < nSlots; i += 32)
 				{
 					const int c = i / SC, j = i - c*SC;
@@ -2061,15 +2062,18 @@ __device__ __forceinline__ void finishPixel(const DevFrame& f, const DevDisplays
 }
 
 // Reference-order filter: one running sum per output pixel over the per-sample planes.
-__global__ void __launch_bounds__(256) k_filter(DevFrame f, DevDisplays disp)
+__global__ void __launch_bounds__(256) k_filter(DevFrame f, DevDisplays disp, int weightsInSmem, int yBeg, int yEnd)
 {
-	extern __shared__ float s_filt[];
+	extern __shared__ float s_filtBuf[];
 	const int taps = (2*f.shiftX+1)*(2*f.shiftY+1)*f.n;
-	for(int i = threadIdx.x + threadIdx.y*blockDim.x; i < taps; i += blockDim.x*blockDim.y) s_filt[i] = f.filterTab[i];
+	// very wide filters at many samples per pixel (15x15 taps x 256 samples = 230 KB) do not fit: read the table from HBM/L2
+	const float* s_filt = weightsInSmem ? s_filtBuf : f.filterTab;
+	if(weightsInSmem)
+		for(int i = threadIdx.x + threadIdx.y*blockDim.x; i < taps; i += blockDim.x*blockDim.y) s_filtBuf[i] = f.filterTab[i];
 	__syncthreads();
 	const int x = f.cropX0 + blockIdx.x*blockDim.x + threadIdx.x;
-	const int y = f.cropY0 + blockIdx.y*blockDim.y + threadIdx.y;
-	if(x >= f.cropX1 || y >= f.cropY1) return;
+	const int y = yBeg + blockIdx.y*blockDim.y + threadIdx.y;
+	if(x >= f.cropX1 || y >= yEnd) return;
 	if(f.rowOwned && !f.rowOwned[y]) return;
 	const int n = f.n, xmax = f.shiftX, ymax = f.shiftY;
 	float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -2172,7 +2176,7 @@ __host__ __device__ __forceinline__ int filterPlaneFloats(const DevFrame& f)
 // MB = bytes per mask word (1, 2 or 4).  Four consecutive slots are tested per step:
 // one 32-bit shared load for byte masks, one 64-bit load for 16-bit masks, one 128-bit load for 32-bit masks.
 template<int MB>
-__global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(DevFrame f, DevDisplays disp)
+__global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(DevFrame f, DevDisplays disp, int yBeg)
 {
 	constexpr int W = FILTER_W;
 	extern __shared__ __align__(128) unsigned char fsm[];
@@ -2184,7 +2188,7 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(DevFrame f, DevDisp
 	const int planeS = filterPlaneFloats(f);
 	float* tile = reinterpret_cast<float*>(fsm);         // [7 value planes][span][SC], planes skewed; ones; mask words
 	const int tid = threadIdx.x, ch = tid & 7, px = tid >> 3;
-	const int x0 = f.cropX0 + blockIdx.x*W, y = f.cropY0 + blockIdx.y;
+	const int x0 = f.cropX0 + blockIdx.x*W, y = yBeg + blockIdx.y;
 	if(f.rowOwned && !f.rowOwned[y]) return;             // uniform over the CTA
 	const bool live = (x0 + px) < f.cropX1;
 	// channel 7 reads 1.0f from a region laid out so that its banks continue the skew of the seven planes
@@ -2204,7 +2208,7 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(DevFrame f, DevDisp
 	const uint32_t validBit = (ch < 7) ? (1u << (2*xmax + 2*ymax + 2)) : 0u;
 	for(int fy = 0; fy <= 2*ymax; ++fy)
 	{
-		const size_t srow = (size_t)(y + fy - ymax - f.sy0);
+		const size_t srow = (size_t)((y + fy - ymax - f.sy0) % f.ringRows);
 		for(int sfx = 0; sfx < nStageFx; ++sfx)
 			for(int c = 0; c < nCh; ++c)
 			{
@@ -2354,13 +2358,9 @@ cudaError_t launchBinFill(const DevFrame& f, cudaStream_t st)
 		k_bin<true><<<(unsigned)((f.nPos + 255)/256), 256, 0, st>>>(f, 0, f.nPos);
 	if(f.nActiveTiles)
 	{
-		static bool attr = false;
-		if(!attr)
-		{
-			cudaError_t e = cudaFuncSetAttribute(k_bin_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_MAX*8);
-			if(e != cudaSuccess) return e;
-			attr = true;
-		}
+		// function attributes are per device: set on every launch (a process may drive hiders on several GPUs)
+		cudaError_t e = cudaFuncSetAttribute(k_bin_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_MAX*8);
+		if(e != cudaSuccess) return e;
 		if(f.sortRun > SORT_MAX) return cudaErrorInvalidValue;
 		if(f.nPos) k_bin_sort<<<f.nActiveTiles, 256, (size_t)f.sortRun*8, st>>>(f, f.sortRun);
 		// only the deep pass reads the flags: frames without a non-opaque vertex (and with cullable hits) skip the scan
@@ -2400,13 +2400,14 @@ cudaError_t hideKernelConfig(const DevFrame& f, int smCount, LaunchCfg& cfg)
 #undef AQH_CFG
 }
 
-cudaError_t launchHide(const DevFrame& f, const LaunchCfg& cfg, cudaStream_t st)
+cudaError_t launchHide(const DevFrame& f, const LaunchCfg& cfg, uint32_t slotBeg, uint32_t slotEnd, uint32_t* cursor, cudaStream_t st)
 {
-	if(f.nActiveTiles == 0) return cudaSuccess;
+	if(slotEnd <= slotBeg) return cudaSuccess;
 	const bool mbdof = f.useDof || f.anyMotion;
 	const bool partials = f.filterMode != AQH_FILTER_REFERENCE_ORDER;
 	const bool dfgen = f.depthFilter != AQH_DEPTHFILTER_MIN;
-#define AQH_LAUNCH(MB, TH, PA, DF) k_hide<MB, TH, PA, DF><<<cfg.hideCtas, TH, cfg.hideSmemBytes, st>>>(f)
+	const int ctas = (int)std::min<uint32_t>((uint32_t)cfg.hideCtas, slotEnd - slotBeg);
+#define AQH_LAUNCH(MB, TH, PA, DF) k_hide<MB, TH, PA, DF><<<ctas, TH, cfg.hideSmemBytes, st>>>(f, slotBeg, slotEnd, cursor)
 #define AQH_LAUNCH2(MB, TH) do { if(partials) { if(dfgen) AQH_LAUNCH(MB, TH, true, true); else AQH_LAUNCH(MB, TH, true, false); } \
                                  else { if(dfgen) AQH_LAUNCH(MB, TH, false, true); else AQH_LAUNCH(MB, TH, false, false); } } while(0)
 	if(mbdof) AQH_LAUNCH2(true, 256); else AQH_LAUNCH2(false, 512);
@@ -2415,9 +2416,11 @@ cudaError_t launchHide(const DevFrame& f, const LaunchCfg& cfg, cudaStream_t st)
 	return cudaGetLastError();
 }
 
-cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, const float* hostFilterTab, cudaStream_t st)
+// Filter + expose + quantise the output rows [yBeg, yEnd) (all of their footprint rows are in the sample planes).
+// uploadTable: the first launch of a frame loads the weight table into constant memory.
+cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, const float* hostFilterTab, int yBeg, int yEnd, bool uploadTable, cudaStream_t st)
 {
-	const int w = f.cropX1 - f.cropX0, h = f.cropY1 - f.cropY0;
+	const int w = f.cropX1 - f.cropX0, h = yEnd - yBeg;
 	if(w <= 0 || h <= 0) return cudaSuccess;
 	if(f.filterMode != AQH_FILTER_REFERENCE_ORDER)
 	{
@@ -2432,38 +2435,41 @@ cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, const float
 		const size_t smem = filterSpansSmem(f);
 		if(smem <= 113*1024)
 		{
-			cudaError_t e = cudaMemcpyToSymbolAsync(c_filt, hostFilterTab, (size_t)ntapw*4, 0, cudaMemcpyHostToDevice, st);
+			cudaError_t e = cudaSuccess;
+			if(uploadTable) e = cudaMemcpyToSymbolAsync(c_filt, hostFilterTab, (size_t)ntapw*4, 0, cudaMemcpyHostToDevice, st);
 			if(e != cudaSuccess) return e;
 			dim3 grid((w + FILTER_W - 1)/FILTER_W, h);
 			if(f.maskBytes == 1)
 			{
 				e = cudaFuncSetAttribute(k_filter_spans<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 				if(e != cudaSuccess) return e;
-				k_filter_spans<1><<<grid, 8*FILTER_W, smem, st>>>(f, disp);
+				k_filter_spans<1><<<grid, 8*FILTER_W, smem, st>>>(f, disp, yBeg);
 			}
 			else if(f.maskBytes == 2)
 			{
 				e = cudaFuncSetAttribute(k_filter_spans<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 				if(e != cudaSuccess) return e;
-				k_filter_spans<2><<<grid, 8*FILTER_W, smem, st>>>(f, disp);
+				k_filter_spans<2><<<grid, 8*FILTER_W, smem, st>>>(f, disp, yBeg);
 			}
 			else
 			{
 				e = cudaFuncSetAttribute(k_filter_spans<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 				if(e != cudaSuccess) return e;
-				k_filter_spans<4><<<grid, 8*FILTER_W, smem, st>>>(f, disp);
+				k_filter_spans<4><<<grid, 8*FILTER_W, smem, st>>>(f, disp, yBeg);
 			}
 			return cudaGetLastError();
 		}
 	}
 	dim3 block(32, 8), grid((w + 31)/32, (h + 7)/8);
-	const size_t smem = (size_t)ntapw*sizeof(float);
+	size_t smem = (size_t)ntapw*sizeof(float);
+	const int inSmem = smem <= 200*1024 ? 1 : 0;
+	if(!inSmem) smem = 0;
 	if(smem > 48*1024)
 	{
 		cudaError_t e = cudaFuncSetAttribute(k_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if(e != cudaSuccess) return e;
 	}
-	k_filter<<<grid, block, smem, st>>>(f, disp);
+	k_filter<<<grid, block, smem, st>>>(f, disp, inSmem, yBeg, yEnd);
 	return cudaGetLastError();
 }
 

@@ -79,6 +79,16 @@ def lib():
     L.aqh_replay_frame_rng.argtypes = [C.POINTER(FrameParams), vp, vp, C.POINTER(ci), C.POINTER(ci),
                                        C.POINTER(ci), C.POINTER(ci)]
     L.aqh_filter_table.argtypes = [C.POINTER(FrameParams), vp, C.POINTER(ci)]
+    L.aqh_set_csg_tree.argtypes = [vp, ci, vp, vp]
+    L.aqh_channel_count.argtypes = [vp, C.POINTER(ci)]
+    L.aqh_grid_rank_masks.argtypes = [C.POINTER(FrameParams), C.POINTER(GridBlock), vp]
+    L.aqh_grid_row_cost.argtypes = [C.POINTER(FrameParams), C.POINTER(GridBlock), vp]
+    L.aqh_balance_strips.argtypes = [C.POINTER(FrameParams), vp]
+    L.aqh_comm_unique_id.argtypes = [vp]
+    L.aqh_comm_init.argtypes = [vp, vp, ci, ci]
+    L.aqh_comm_destroy.argtypes = [vp]
+    L.aqh_gather.argtypes = [vp, ci]
+    L.aqh_clear_caches.argtypes = [vp]
     _LIB = L
     return L
 
@@ -86,14 +96,80 @@ def lib():
 FILTER_NAMES = ("box", "triangle", "gaussian", "catmull-rom", "sinc", "mitchell", "disk", "bessel")
 
 
+# Pure-python mode: nothing in this module touches the native library (bench.py --impl reference must time the
+# reference's CPU hider in a process that never maps the product).  The pixel filter is then carried by NAME in
+# p._filter_name (filter_func stays NULL); tests/orc.py hands it to the reference / the oracle.
+PURE = False
+
+
+def _display_from_mode(d: DisplayDesc, mode, driver_order, one, mn, mx, dither):
+    """aqh_display_from_mode in python (core order a,r,g,b,z, ddmanager.cpp:455-480; file driver order r,g,b,a)."""
+    rgb, a, z = "rgb" in mode, "a" in mode, "z" in mode
+    if not (rgb or a or z):
+        raise HiderError(abi.AQH_ERR_BAD_PARAMS, f"display mode {mode!r}")
+    ch = []
+    if not driver_order and a:
+        ch.append(abi.CH_ALPHA)
+    if rgb:
+        ch += [abi.CH_CI_R, abi.CH_CI_G, abi.CH_CI_B]
+    if driver_order and a:
+        ch.append(abi.CH_ALPHA)
+    if z:
+        ch.append(abi.CH_Z)
+    C.memset(C.byref(d), 0, C.sizeof(d))
+    d.n_channels = len(ch)
+    for i, c in enumerate(ch):
+        d.channel[i] = c
+    d.quantize_zero, d.quantize_one, d.quantize_min, d.quantize_max, d.quantize_dither = 0.0, one, mn, mx, dither
+
+
+def _defaults_pure(p: FrameParams):
+    """aqh_frame_params_default in python (CqOptions defaults, libs/core/options.cpp:273-305); tests/test_abi.py
+    checks that both fill the struct identically."""
+    C.memset(C.byref(p), 0, C.sizeof(p))
+    p.abi_version = abi.AQH_ABI_VERSION
+    p.xres, p.yres = 640, 480
+    p.crop_xmin, p.crop_xmax, p.crop_ymin, p.crop_ymax = 0, 640, 0, 480
+    p.xsamples = p.ysamples = 2
+    p.filter_xwidth = p.filter_ywidth = 2.0
+    p.bucket_xsize = p.bucket_ysize = 16
+    p.clip_near, p.clip_far = float(np.finfo(np.float32).eps), float(np.finfo(np.float32).max)
+    p.depth_filter = abi.DEPTHFILTER_MIN
+    p.zthreshold[0] = p.zthreshold[1] = p.zthreshold[2] = 1.0
+    p.display_mode = abi.DMODE_RGB | abi.DMODE_A
+    p.exposure_gain = p.exposure_gamma = 1.0
+    p.jitter = 1
+    for i in range(4):
+        p.cam_to_raster[i * 4 + i] = 1.0
+    p.rng_seed = 545
+    p.world_size = 1
+    p.filter_mode = abi.FILTER_REFERENCE_ORDER
+
+
+def _set_dof_pure(p: FrameParams, fstop, focallength, focaldistance, sx, sy):
+    """CqRenderer::SetDepthOfFieldData (renderer.h:368-377) with the same float / double staging."""
+    f32 = np.float32
+    p.use_dof = 1 if f32(fstop) < np.finfo(np.float32).max else 0
+    if p.use_dof:
+        lens = f32(focallength) / f32(fstop)
+        fd = float(f32(focaldistance))
+        p.dof_multiplier = float(f32(0.5 * float(lens) * fd / (fd + float(lens))))
+        p.dof_one_over_focal_distance = float(f32(1.0 / fd))
+    p.dof_scale_x, p.dof_scale_y = sx, sy
+
+
 def default_params(**kw) -> FrameParams:
     """AqhFrameParams with the reference's option defaults, then overrides.
 
     Convenience keys: resolution=(x,y) also resets the crop window; samples=(xs,ys);
-    filter=("name", xw, yw); displays=[("rgba", driver_order, one, min, max, dither), ...].
-    """
+    filter=("name", xw, yw); displays=[("rgba", driver_order, one, min, max, dither), ...];
+    aovs=[("name", n_floats), ...]."""
     p = FrameParams()
-    lib().aqh_frame_params_default(C.byref(p))
+    if PURE:
+        _defaults_pure(p)
+    else:
+        lib().aqh_frame_params_default(C.byref(p))
+    p._filter_name = "gaussian"
     if "resolution" in kw:
         x, y = kw.pop("resolution")
         p.xres, p.yres = x, y
@@ -104,14 +180,18 @@ def default_params(**kw) -> FrameParams:
         p.xsamples, p.ysamples = kw.pop("samples")
     if "filter" in kw:
         name, xw, yw = kw.pop("filter")
-        fn = lib().aqh_filter_by_name(name.encode())
-        if not fn:
+        if name not in FILTER_NAMES:
             raise ValueError(f"unknown pixel filter {name!r}")
-        p.filter_func = fn
+        p._filter_name = name
+        if not PURE:
+            p.filter_func = lib().aqh_filter_by_name(name.encode())
         p.filter_xwidth, p.filter_ywidth = xw, yw
     if "dof" in kw:
         fstop, fl, fd, sx, sy = kw.pop("dof")
-        lib().aqh_frame_params_set_dof(C.byref(p), fstop, fl, fd, sx, sy)
+        if PURE:
+            _set_dof_pure(p, fstop, fl, fd, sx, sy)
+        else:
+            lib().aqh_frame_params_set_dof(C.byref(p), fstop, fl, fd, sx, sy)
     if "shutter" in kw:
         p.shutter_open, p.shutter_close = kw.pop("shutter")
     if "exposure" in kw:
@@ -121,14 +201,26 @@ def default_params(**kw) -> FrameParams:
         p.n_displays = len(ds)
         for i, d in enumerate(ds):
             mode, driver_order, one, mn, mx, dither = d
-            rc = lib().aqh_display_from_mode(C.byref(p.display[i]), mode.encode(), int(driver_order), one, mn, mx, dither)
-            if rc:
-                raise HiderError(rc, f"display mode {mode!r}")
+            _display_from_mode(p.display[i], mode, int(driver_order), one, mn, mx, dither)
+    if "aovs" in kw:
+        av = kw.pop("aovs")
+        p.n_aovs = len(av)
+        for i, (name, nf) in enumerate(av):
+            p.aov[i].name = name.encode()
+            p.aov[i].n_floats = nf
     for k, v in kw.items():
         if not hasattr(p, k):
             raise AttributeError(f"AqhFrameParams has no field {k!r}")
         setattr(p, k, v)
     return p
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = lib().aqh_comm_unique_id(buf)
+    if rc:
+        raise HiderError(rc, "aqh_comm_unique_id (is libnccl.so.2 loadable?)")
+    return buf.raw
 
 
 def display_info(p: FrameParams, d: int):
@@ -159,6 +251,11 @@ class GridArrays:
     key_times: Optional[np.ndarray] = None
     lod_bounds: Optional[np.ndarray] = None
     culled: Optional[object] = None
+    aov: Optional[object] = None       # (sum nverts, aov floats) float32
+    Ng: Optional[object] = None        # (sum nverts, 3)
+    N: Optional[object] = None
+    radius: Optional[object] = None    # (sum nkeys*nverts,) float32, read for GRID_POINTS grids
+    csg_node: Optional[np.ndarray] = None
     _keep: list = field(default_factory=list, repr=False)
 
     @property
@@ -171,7 +268,9 @@ class GridArrays:
 
     @property
     def n_micropolygons(self):
-        return int((self.cu.astype(np.int64) * self.cv.astype(np.int64)).sum())
+        pts = (self.flags.astype(np.int64) & abi.GRID_POINTS) != 0
+        cu, cv = self.cu.astype(np.int64), self.cv.astype(np.int64)
+        return int(np.where(pts, cu + 1, cu * cv).sum())
 
     def is_device(self):
         return hasattr(self.P, "data_ptr")
@@ -207,6 +306,11 @@ class GridArrays:
         b.Ci = bulk(self.Ci, np.float32)
         b.Oi = bulk(self.Oi, np.float32)
         b.culled = bulk(self.culled, np.uint8)
+        b.aov = bulk(self.aov, np.float32)
+        b.Ng = bulk(self.Ng, np.float32)
+        b.N = bulk(self.N, np.float32)
+        b.radius = bulk(self.radius, np.float32)
+        b.csg_node = host(self.csg_node, np.int32)
         b.memory_space = 1 if (hasattr(self.P, "is_cuda") and self.P.is_cuda) else 0
         return b
 
@@ -224,7 +328,9 @@ class GridArrays:
 
         return GridArrays(cu=self.cu, cv=self.cv, flags=self.flags, P=conv(self.P, np.float32),
                           Ci=conv(self.Ci, np.float32), Oi=conv(self.Oi, np.float32), nkeys=self.nkeys,
-                          key_times=self.key_times, lod_bounds=self.lod_bounds, culled=conv(self.culled, np.uint8))
+                          key_times=self.key_times, lod_bounds=self.lod_bounds, culled=conv(self.culled, np.uint8),
+                          aov=conv(self.aov, np.float32), Ng=conv(self.Ng, np.float32), N=conv(self.N, np.float32),
+                          radius=conv(self.radius, np.float32), csg_node=self.csg_node)
 
 
 class Hider:
@@ -262,7 +368,8 @@ class Hider:
         self.params = params
         self._check(self._L.aqh_begin_frame(self._h, C.byref(params)))
 
-    def add_grid(self, P, cu, cv, Ci=None, Oi=None, flags=abi.GRID_SMOOTH, key_times=None, culled=None, lod_bounds=None):
+    def add_grid(self, P, cu, cv, Ci=None, Oi=None, flags=abi.GRID_SMOOTH, key_times=None, culled=None, lod_bounds=None,
+                 aov=None, Ng=None, N=None, radius=None, csg_node=-1):
         """P: (nkeys, nverts, 3) or (nverts, 3) float32."""
         P = np.ascontiguousarray(P, dtype=np.float32)
         if P.ndim == 2:
@@ -277,7 +384,9 @@ class Hider:
             kt = np.ascontiguousarray(key_times, dtype=np.float32)
             keep.append(kt)
             g.key_times = kt.ctypes.data_as(C.POINTER(C.c_float))
-        for name, arr, dt in (("Ci", Ci, np.float32), ("Oi", Oi, np.float32), ("culled", culled, np.uint8)):
+        g.csg_node = int(csg_node)
+        for name, arr, dt in (("Ci", Ci, np.float32), ("Oi", Oi, np.float32), ("culled", culled, np.uint8),
+                              ("aov", aov, np.float32), ("Ng", Ng, np.float32), ("N", N, np.float32), ("radius", radius, np.float32)):
             if arr is not None:
                 a = np.ascontiguousarray(arr, dtype=dt)
                 keep.append(a)
@@ -308,16 +417,16 @@ class Hider:
     def render_device(self):
         self._check(self._L.aqh_render_device(self._h))
 
-    def end_frame(self, on_bucket=None, on_data=None, on_progress=None, fetch=True):
+    def end_frame(self, on_bucket=None, on_data=None, on_progress=None, fetch=True, on_imager=None):
         """aqh_end_frame.  fetch=True returns numpy COPIES of the images (convenience for tests);
         fetch=False leaves them in the library's pinned host buffers (see images(copy=False))."""
         cb = Callbacks()
         keep = []
         if on_bucket:
-            def _b(user, x0, x1, y0, y1, ch, stride):
-                n = (y1 - y0 - 1) * stride + (x1 - x0) * 9
+            def _b(user, x0, x1, y0, y1, ch, stride, nch):
+                n = (y1 - y0 - 1) * stride + (x1 - x0) * nch
                 a = np.ctypeslib.as_array(ch, shape=(n,))
-                rows = [a[r * stride: r * stride + (x1 - x0) * 9].reshape(x1 - x0, 9) for r in range(y1 - y0)]
+                rows = [a[r * stride: r * stride + (x1 - x0) * nch].reshape(x1 - x0, nch) for r in range(y1 - y0)]
                 return int(on_bucket(x0, x1, y0, y1, np.stack(rows)) or 0)
             cb.on_bucket = abi.BucketFunc(_b)
             keep.append(cb.on_bucket)
@@ -330,6 +439,16 @@ class Hider:
         if on_progress:
             cb.on_progress = abi.ProgressFunc(lambda user, pct: on_progress(pct))
             keep.append(cb.on_progress)
+        if on_imager:
+            def _i(user, x0, x1, y0, y1, ch, stride, nch):
+                n = (y1 - y0 - 1) * stride + (x1 - x0) * nch
+                a = np.ctypeslib.as_array(ch, shape=(n,))
+                for r in range(y1 - y0):
+                    row = a[r * stride: r * stride + (x1 - x0) * nch].reshape(x1 - x0, nch)     # a view: edits land in place
+                    on_imager(x0, x1, y0 + r, row)
+                return 0
+            cb.on_imager = abi.ImagerFunc(_i)
+            keep.append(cb.on_imager)
         self._check(self._L.aqh_end_frame(self._h, C.byref(cb) if keep else None))
         self._block_keep = []
         return self.images() if fetch else None
@@ -340,7 +459,7 @@ class Hider:
         ptr = C.POINTER(C.c_float)()
         w, h = C.c_int(), C.c_int()
         self._check(self._L.aqh_image_channels(self._h, C.byref(ptr), C.byref(w), C.byref(h)))
-        channels = np.ctypeslib.as_array(ptr, shape=(h.value, w.value, 9))
+        channels = np.ctypeslib.as_array(ptr, shape=(h.value, w.value, self.channel_count()))
         if copy:
             channels = channels.copy()
         displays = []
@@ -354,6 +473,45 @@ class Hider:
             dt = np.dtype(abi.TYPE_NUMPY[ty.value])
             displays.append(raw.view(dt).reshape(h.value, w.value, es.value // dt.itemsize))
         return channels, displays
+
+    def clear_caches(self):
+        self._check(self._L.aqh_clear_caches(self._h))
+
+    def end_frame_capture(self, channels=None, displays=()):
+        """aqh_end_frame with the library's own capture display as callbacks (aqh_capture_on_bucket / _on_data): the
+        buckets are copied, in reference bucket order, into the given full-frame numpy arrays -- what a framebuffer
+        display driver does with DspyImageData.  Returns the number of buckets delivered."""
+        cap = abi.Capture()
+        cap.xres, cap.yres, cap.n_channels = self.params.xres, self.params.yres, self.channel_count()
+        if channels is not None:
+            cap.channels = channels.ctypes.data
+        for d, a in enumerate(displays):
+            if a is not None:
+                cap.display[d] = a.ctypes.data
+        cb = Callbacks()
+        cb.user = C.cast(C.pointer(cap), C.c_void_p)
+        cb.on_bucket = C.cast(self._L.aqh_capture_on_bucket, abi.BucketFunc)
+        cb.on_data = C.cast(self._L.aqh_capture_on_data, abi.DataFunc)
+        self._check(self._L.aqh_end_frame(self._h, C.byref(cb)))
+        self._block_keep = []
+        return int(cap.buckets)
+
+    def channel_count(self) -> int:
+        n = C.c_int()
+        self._check(self._L.aqh_channel_count(self._h, C.byref(n)))
+        return n.value
+
+    def set_csg_tree(self, types, parents):
+        t = np.ascontiguousarray(types, np.int32)
+        pa = np.ascontiguousarray(parents, np.int32)
+        self._check(self._L.aqh_set_csg_tree(self._h, len(t), t.ctypes.data, pa.ctypes.data))
+
+    def comm_init(self, unique_id: bytes, rank, world):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._check(self._L.aqh_comm_init(self._h, buf, int(rank), int(world)))
+
+    def gather(self, root=0):
+        self._check(self._L.aqh_gather(self._h, int(root)))
 
     def stats(self) -> dict:
         s = FrameStats()

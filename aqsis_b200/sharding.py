@@ -31,28 +31,30 @@ def rows_for_rank(params, rank):
     return np.concatenate([np.arange(a, b) for a, b in s]).astype(np.int64) if s else np.zeros(0, np.int64)
 
 
-def grid_row_ranges(params, grids: GridArrays):
-    """Conservative [lo, hi] pixel-row range each grid can contribute to (imagebuffer.cpp:519-554:
-    union of the key bounds, grown by the largest circle of confusion and the filter half-width)."""
-    nv = (grids.cu.astype(np.int64) + 1) * (grids.cv.astype(np.int64) + 1)
-    nk = grids.nkeys.astype(np.int64) if grids.nkeys is not None else np.ones_like(nv)
-    pstart = np.concatenate([[0], np.cumsum(nv * nk)])
-    P = np.asarray(grids.P)
-    y, z = P[:, 1], P[:, 2]
-    ymin = np.minimum.reduceat(y, pstart[:-1])
-    ymax = np.maximum.reduceat(y, pstart[:-1])
-    pad = np.floor(params.filter_ywidth / 2.0) + 1.0
-    if params.use_dof:
-        zmin = np.minimum.reduceat(z, pstart[:-1]).astype(np.float64)
-        zmax = np.maximum.reduceat(z, pstart[:-1]).astype(np.float64)
+def grid_rank_masks(params, grids: GridArrays):
+    """uint64 per grid: bit r set when rank r must receive the grid (aqh_grid_rank_masks: the library's own rule --
+    row range of the grid over all its keys, camera-space grids projected, grown by the largest circle of confusion and
+    the filter half-width; straddlers carry several bits)."""
+    b = grids.as_struct()
+    masks = np.zeros(grids.n_grids, np.uint64)
+    rc = lib().aqh_grid_rank_masks(C.byref(params), C.byref(b), masks.ctypes.data)
+    if rc:
+        raise ValueError(f"aqh_grid_rank_masks failed ({rc})")
+    return masks
 
-        def coc(zz):
-            return params.dof_multiplier * np.abs(1.0 / zz - params.dof_one_over_focal_distance) * params.dof_scale_y
-        # |1/z - 1/fd| is convex in 1/z: its maximum over the bound is at an end point
-        pad = pad + np.maximum(coc(zmin), coc(zmax)) * 1.001 + 1e-3
-    lo = np.floor(ymin - pad).astype(np.int64)
-    hi = np.ceil(ymax + pad).astype(np.int64)
-    return lo, hi
+
+def balance_strips(params, blocks):
+    """One contiguous strip per rank with equal estimated work (aqh_grid_row_cost + aqh_balance_strips)."""
+    cost = np.zeros(params.yres, np.float64)
+    for g in blocks:
+        b = g.as_struct()
+        rc = lib().aqh_grid_row_cost(C.byref(params), C.byref(b), cost.ctypes.data)
+        if rc:
+            raise ValueError(f"aqh_grid_row_cost failed ({rc})")
+    rc = lib().aqh_balance_strips(C.byref(params), cost.ctypes.data)
+    if rc:
+        raise ValueError(f"aqh_balance_strips failed ({rc})")
+    return params
 
 
 def split_grids_for_rank(params, grids: GridArrays, rank, world):
@@ -63,10 +65,7 @@ def split_grids_for_rank(params, grids: GridArrays, rank, world):
     nk = grids.nkeys.astype(np.int64) if grids.nkeys is not None else np.ones_like(nv)
     pstart = np.concatenate([[0], np.cumsum(nv * nk)])
     vstart = np.concatenate([[0], np.cumsum(nv)])
-    lo, hi = grid_row_ranges(params, grids)
-    keep = np.zeros(grids.n_grids, dtype=bool)
-    for y0, y1 in strips_for_rank(params, rank):
-        keep |= (hi >= y0) & (lo < y1)
+    keep = (grid_rank_masks(params, grids) >> np.uint64(rank)) & np.uint64(1)
     idx = np.nonzero(keep)[0]
 
     def take(starts):
@@ -81,12 +80,17 @@ def split_grids_for_rank(params, grids: GridArrays, rank, world):
     if grids.key_times is not None:
         kstart = np.concatenate([[0], np.cumsum(nk)])
         kt = np.asarray(grids.key_times)[take(kstart)]
+
+    def verts(a):
+        return None if a is None else np.asarray(a)[vert_idx]
+
     return GridArrays(cu=grids.cu[idx], cv=grids.cv[idx], flags=grids.flags[idx], P=np.asarray(grids.P)[pos_idx],
-                      Ci=None if grids.Ci is None else np.asarray(grids.Ci)[vert_idx],
-                      Oi=None if grids.Oi is None else np.asarray(grids.Oi)[vert_idx],
+                      Ci=verts(grids.Ci), Oi=verts(grids.Oi),
                       nkeys=None if grids.nkeys is None else grids.nkeys[idx], key_times=kt,
                       lod_bounds=None if grids.lod_bounds is None else np.asarray(grids.lod_bounds).reshape(-1, 2)[idx].ravel(),
-                      culled=None if grids.culled is None else np.asarray(grids.culled)[vert_idx])
+                      culled=verts(grids.culled), aov=verts(grids.aov), Ng=verts(grids.Ng), N=verts(grids.N),
+                      radius=None if grids.radius is None else np.asarray(grids.radius)[pos_idx],
+                      csg_node=None if grids.csg_node is None else np.asarray(grids.csg_node)[idx])
 
 
 class ImageGather:

@@ -45,7 +45,7 @@ extern "C" {
 #  define AQH_EXPORT
 #endif
 
-#define AQH_ABI_VERSION 1
+#define AQH_ABI_VERSION 2
 
 typedef enum AqhStatus
 {
@@ -82,10 +82,34 @@ enum {
 	AQH_GRID_TRIANGULAR   = 1u << 3,  /* fTriangular(): reject hits beyond the split line */
 	AQH_GRID_CAMERA_SPACE = 1u << 4,  /* P is camera space: project with cam_to_raster keeping camera z
 	                                     (micropolygon.cpp:723-731); else P is already raster x,y + camera z */
-	AQH_GRID_USES_CSG     = 1u << 5   /* rejected with AQH_ERR_UNSUPPORTED */
+	AQH_GRID_USES_CSG     = 1u << 5,  /* pCSGNode() != 0: hits are never culled, kept in the sample's list and resolved
+	                                     through the CSG tree (imagepixel.cpp:166-189, csgtree.cpp:144-351); csg_node
+	                                     names the primitive node in the tree given to aqh_set_csg_tree */
+	AQH_GRID_POINTS       = 1u << 6,  /* CqMicroPolyGridPoints (geometry/points.cpp:653-700): every vertex is a disc of
+	                                     raster radius `radius`; cv must be 0, the grid has cu+1 points; constant shading */
+	AQH_GRID_CULL_BACKFACING  = 1u << 7, /* Sides 1: drop micropolygons whose corner normal faces away, (Ng . P) >= 0 in
+	                                     camera space (micropolygon.cpp:431-474); needs Ng and AQH_GRID_CAMERA_SPACE */
+	AQH_GRID_CULL_TRANSPARENT = 1u << 8  /* drop the trailing run of micropolygons with Oi == 0 (micropolygon.cpp:493-522,
+	                                     including the reference's early break at the first non-black vertex) */
 };
 
-enum { AQH_MAX_DISPLAYS = 8, AQH_MAX_DISPLAY_CHANNELS = 16 };
+enum { AQH_MAX_DISPLAYS = 8, AQH_MAX_DISPLAY_CHANNELS = 16, AQH_MAX_RANKS = 64, AQH_MAX_AOVS = 8, AQH_MAX_AOV_FLOATS = 21 };
+
+/* One arbitrary output variable (CqRenderer::RegisterOutputData, libs/core/renderer.cpp:1520-1546): `n_floats`
+ * consecutive floats of every hit (StoreExtraData, bucketprocessor.cpp:1573-1643: float 1, point/normal/vector/color 3,
+ * matrix 16), filtered like colour (bucketprocessor.cpp:620-653) and appended to the 9 standard floats of a pixel of
+ * the channel buffer in registration order: the first AOV starts at slot AQH_NUM_CHANNELS. */
+typedef struct AqhAovDesc
+{
+	char name[32];                  /* the shader output variable, e.g. "N" or "_albedo" (informational on this side) */
+	int32_t n_floats;               /* 1, 3 or 16 */
+	int32_t reserved;
+} AqhAovDesc;
+
+/* AqhDisplayDesc::flags */
+enum { AQH_DISPLAY_SCANLINE_ORDER = 1 };  /* PkDspyFlagsWantsScanLineOrder (ndspy.h:132): rows are delivered one at a time once
+                                             a row of buckets is complete (CollapseBucketsToScanlines / SendToDisplay,
+                                             ddmanager.cpp:1129-1175) */
 
 /* How the pixel filter sums are associated (the SET of samples and the weights are always the
  * reference's: inclusion by jittered position, weight by sub-pixel cell centre).
@@ -107,9 +131,11 @@ typedef float (*AqhFilterFunc)(float x, float y, float xwidth, float ywidth);
 typedef struct AqhDisplayDesc
 {
 	int32_t n_channels;                          /* entries of channel[] used */
-	int32_t channel[AQH_MAX_DISPLAY_CHANNELS];   /* AQH_CH_* slot per output element, in driver order */
+	int32_t channel[AQH_MAX_DISPLAY_CHANNELS];   /* AQH_CH_* slot per output element, in driver order; slots >= AQH_NUM_CHANNELS
+	                                                are floats of the arbitrary output variables */
 	int32_t type;                                /* AQH_FLOAT32...; 0 = select from (one,min,max) like selectDataFormat */
 	float quantize_zero, quantize_one, quantize_min, quantize_max, quantize_dither;
+	int32_t flags;                               /* AQH_DISPLAY_* */
 } AqhDisplayDesc;
 
 typedef struct AqhFrameParams
@@ -137,12 +163,22 @@ typedef struct AqhFrameParams
 	uint32_t rng_predraws;          /* front-end draws made between the reseed and RenderImage() */
 	int32_t n_displays;
 	AqhDisplayDesc display[AQH_MAX_DISPLAYS];
+	/* arbitrary output variables, in registration order (RiDisplay -> RegisterOutputData) */
+	int32_t n_aovs;
+	AqhAovDesc aov[AQH_MAX_AOVS];
 	/* --- device-side knobs (no reference analogue) --- */
-	int32_t rank, world_size;       /* image strips are dealt round-robin to ranks; 0,1 = whole image */
-	int32_t strip_rows;             /* strip height in pixel rows (rounded down to a multiple of 16); 0 = balanced: world*k near-equal strips */
+	int32_t rank, world_size;       /* pixel-row strips of the image are dealt to ranks; 0,1 = whole image */
+	int32_t strip_rows;             /* > 0: strips of this many rows (rounded down to a multiple of 16) dealt round-robin;
+	                                   0: world*k near-equal strips dealt round-robin;
+	                                   -1: ONE contiguous strip per rank, near-equal heights (least replication of straddlers);
+	                                   -2: one contiguous strip per rank, rank r owns rows [strip_bounds[r], strip_bounds[r+1])
+	                                       (see aqh_balance_strips) */
+	int32_t strip_bounds[AQH_MAX_RANKS + 1];
 	int32_t deep_hits_per_sample;   /* average capacity of the transparent hit pool; 0 = default */
 	int32_t filter_mode;            /* AQH_FILTER_*; 0 = AQH_FILTER_REFERENCE_ORDER (bit-exact sums) */
-	int32_t reserved[7];
+	int32_t plane_budget_mb;        /* HBM the resolved samples of the reference-order filter may occupy at a time; the frame
+	                                   is hidden and filtered in bands of tile rows that fit (0 = 4608 MB) */
+	int32_t reserved[6];
 } AqhFrameParams;
 
 /* One shaded grid as CqMicroPolyGrid::Split sees it (micropolygon.cpp:641-892, motion :946-1156).
@@ -159,6 +195,14 @@ typedef struct AqhGridDesc
 	const uint8_t* culled;          /* (cu+1)*(cv+1) bytes, non-zero = m_CulledPolys.Value(iIndex); NULL = none */
 	uint32_t flags;                 /* AQH_GRID_* */
 	float lod_bounds[2];            /* SqGridInfo::lodBounds; lod_bounds[0] < 0 = no level of detail */
+	const float* aov;               /* nverts * (sum of the frame's AqhAovDesc::n_floats) floats, vertex-major: what
+	                                   FindStandardVar(name)->Get*(value, index) returns; NULL = zeros (the reference would
+	                                   leave whatever the pixel pool held) */
+	const float* Ng;                /* nverts*3 camera-space geometric normals (AQH_GRID_CULL_BACKFACING), else NULL */
+	const float* N;                 /* nverts*3 user normals deciding the facing of Ng (micropolygon.cpp:452-458), may be NULL */
+	const float* radius;            /* AQH_GRID_POINTS: nkeys*nverts raster radii, key-major like P */
+	int32_t csg_node;               /* AQH_GRID_USES_CSG: index of the grid's primitive node in the CSG tree */
+	int32_t reserved[3];
 } AqhGridDesc;
 
 /* Many grids, concatenated.  memory_space 0 = host pointers, 1 = device pointers
@@ -176,14 +220,25 @@ typedef struct AqhGridBlock
 	const float* Ci;                /* sum(nverts)*3 floats, NULL = white */
 	const float* Oi;                /* sum(nverts)*3 floats, NULL = opaque */
 	const uint8_t* culled;          /* sum(nverts) bytes, NULL = none */
-	int32_t memory_space;           /* applies to P, Ci, Oi, culled; the per-grid tables are always host */
+	int32_t memory_space;           /* applies to P, Ci, Oi, culled, aov, Ng, N, radius; the per-grid tables are always host */
 	int32_t reserved[3];
+	const float* aov;               /* sum(nverts) * (sum of AqhAovDesc::n_floats) floats, vertex-major; NULL = zeros */
+	const float* Ng;                /* sum(nverts)*3, NULL unless some grid has AQH_GRID_CULL_BACKFACING */
+	const float* N;                 /* sum(nverts)*3 or NULL */
+	const float* radius;            /* sum(nkeys*nverts) floats (only read for AQH_GRID_POINTS grids) or NULL */
+	const int32_t* csg_node;        /* n_grids, NULL = none */
 } AqhGridBlock;
 
-/* IqDDManager::DisplayBucket stand-in: region [xmin,xmax1) x [ymin,ymax1) of the bucket and its
- * float channel buffer, AQH_NUM_CHANNELS interleaved floats per pixel, row stride in floats. */
+/* IqDDManager::DisplayBucket stand-in: region [xmin,xmax1) x [ymin,ymax1) of the bucket and its float channel
+ * buffer: pixel_stride_floats (= AQH_NUM_CHANNELS + the frame's AOV floats) interleaved floats per pixel, row stride
+ * in floats. */
 typedef int (*AqhBucketFunc)(void* user, int xmin, int xmax1, int ymin, int ymax1,
-                             const float* channels, int row_stride_floats);
+                             const float* channels, int row_stride_floats, int pixel_stride_floats);
+/* Imager shader stand-in (CqBucketProcessor::FilterBucket, bucketprocessor.cpp:712-743): called once per bucket in
+ * reference bucket order after filtering and BEFORE exposure and quantisation; may overwrite Ci (slots 0-2), Oi (3-5)
+ * and alpha (6) of the bucket's pixels in place. */
+typedef int (*AqhImagerFunc)(void* user, int xmin, int xmax1, int ymin, int ymax1,
+                             float* channels, int row_stride_floats, int pixel_stride_floats);
 /* DspyImageDataMethod stand-in (ndspy.h:157), one call per bucket per display, reference bucket order. */
 typedef int (*AqhDataFunc)(void* user, int display, int xmin, int xmax1, int ymin, int ymax1,
                            int entrysize, const unsigned char* data);
@@ -195,6 +250,7 @@ typedef struct AqhCallbacks
 	AqhBucketFunc on_bucket;        /* may be NULL */
 	AqhDataFunc on_data;            /* may be NULL */
 	AqhProgressFunc on_progress;    /* may be NULL */
+	AqhImagerFunc on_imager;        /* may be NULL */
 } AqhCallbacks;
 
 /* Stage timings of the last frame in milliseconds, named after the reference's
@@ -212,6 +268,9 @@ typedef struct AqhFrameStats
 	int64_t n_grids, n_vertices, n_micropolygons, n_bin_entries, n_samples, n_deep_hits;
 	int64_t gpu_launches;     /* kernels launched for the frame */
 	int64_t h2d_bytes, d2h_bytes;
+	int64_t device_bytes;     /* HBM held by the hider's own buffers after the frame (caller-owned device grids excluded) */
+	int64_t n_bands;          /* bands of tile rows the frame was hidden and filtered in (AqhFrameParams::plane_budget_mb) */
+	double gather_ms;         /* NCCL gather of the finished strips (aqh_gather), device time */
 } AqhFrameStats;
 
 typedef struct AqhHider AqhHider;
@@ -235,6 +294,14 @@ AQH_EXPORT int aqh_display_from_mode(AqhDisplayDesc* d, const char* mode, int dr
                                      float one, float min, float max, float dither);
 
 AQH_EXPORT int aqh_begin_frame(AqhHider* h, const AqhFrameParams* p);
+/* The frame's CSG tree (RiSolidBegin/End -> CqCSGTreeNode, libs/core/csgtree.h:69-215), between aqh_begin_frame and the
+ * first CSG grid: node i has type[i] (AQH_CSG_*) and parent[i] (-1 for a root; several trees may coexist).  The children
+ * of a node are ordered by node index, which is the order RiSolidBegin created them in.  Grids name their primitive
+ * node in csg_node.  Resolved per sample exactly like CqCSGTreeNode::ProcessTree (csgtree.cpp:144-351). */
+enum { AQH_CSG_PRIMITIVE = 0, AQH_CSG_UNION = 1, AQH_CSG_INTERSECTION = 2, AQH_CSG_DIFFERENCE = 3 };
+AQH_EXPORT int aqh_set_csg_tree(AqhHider* h, int n_nodes, const int32_t* type, const int32_t* parent);
+/* Floats per pixel of the channel buffer of the current frame: AQH_NUM_CHANNELS + the AOV floats. */
+AQH_EXPORT int aqh_channel_count(const AqhHider* h, int* n);
 AQH_EXPORT int aqh_add_grid(AqhHider* h, const AqhGridDesc* g);
 AQH_EXPORT int aqh_add_grid_block(AqhHider* h, const AqhGridBlock* b);
 /* Hide + filter + expose + quantise everything added since begin_frame, download, fire callbacks
@@ -258,6 +325,24 @@ AQH_EXPORT int aqh_flush(AqhHider* h);
 AQH_EXPORT int aqh_can_cull(const AqhHider* h, const float bound[6], int* culled);
 AQH_EXPORT int aqh_frame_stats(const AqhHider* h, AqhFrameStats* out);
 
+/* Forget everything cached across frames (the replayed random stream and the tables built from the frame options):
+ * the next aqh_begin_frame pays the full Prepare_bucket cost again, like the first frame of a process. */
+AQH_EXPORT int aqh_clear_caches(AqhHider* h);
+
+/* A minimal in-process capture display (what aqsis' debugdd / a framebuffer driver does with DspyImageData): ready-made
+ * AqhCallbacks targets that copy every bucket into caller-owned full-frame images.  user = AqhCapture*. */
+typedef struct AqhCapture
+{
+	int32_t xres, yres, n_channels;  /* n_channels: floats per pixel of `channels` (aqh_channel_count) */
+	float* channels;                 /* xres*yres*n_channels floats or NULL */
+	unsigned char* display[AQH_MAX_DISPLAYS];   /* xres*yres*entrysize bytes each or NULL */
+	int64_t buckets, bytes;          /* counted by the callbacks */
+} AqhCapture;
+AQH_EXPORT int aqh_capture_on_bucket(void* user, int xmin, int xmax1, int ymin, int ymax1,
+                                     const float* channels, int row_stride_floats, int pixel_stride_floats);
+AQH_EXPORT int aqh_capture_on_data(void* user, int display, int xmin, int xmax1, int ymin, int ymax1,
+                                   int entrysize, const unsigned char* data);
+
 /* Results of the last frame.  Host copies (valid after aqh_end_frame): full-resolution images,
  * rows owned by other ranks are zero. */
 AQH_EXPORT int aqh_image_channels(const AqhHider* h, const float** data, int* width, int* height);
@@ -273,6 +358,34 @@ AQH_EXPORT int aqh_device_display(const AqhHider* h, int display, void** dev_ptr
 AQH_EXPORT int aqh_strip_layout(const AqhFrameParams* p, int rank, int* n_strips, int* y0, int* y1, int capacity);
 AQH_EXPORT int aqh_num_strips(const AqhHider* h, int* n);
 AQH_EXPORT int aqh_strip(const AqhHider* h, int i, int* y0, int* y1);
+
+/* --- sharding one frame over the GPUs of a box, behind the C ABI so that a C++ host needs nothing else.
+ * Device-less.  aqh_grid_rank_masks: bit r of rank_mask[g] is set when rank r must receive grid g of a HOST-memory
+ * block, i.e. when the grid's raster row range -- union of its motion keys, grown by the largest circle of confusion
+ * and the filter half-width like CqImageBuffer::AddMPG does per micropolygon (imagebuffer.cpp:519-554); camera-space
+ * grids are projected with p->cam_to_raster first -- touches a strip of rank r.  Straddlers get several bits: they are
+ * replicated.  p->world_size <= AQH_MAX_RANKS. */
+AQH_EXPORT int aqh_grid_rank_masks(const AqhFrameParams* p, const AqhGridBlock* b, uint64_t* rank_mask /* n_grids */);
+/* Work estimate per pixel row: adds, for every grid of the block, its micropolygon count spread over the rows it
+ * covers to row_cost[p->yres] (call once per block; the caller zeroes the array first). */
+AQH_EXPORT int aqh_grid_row_cost(const AqhFrameParams* p, const AqhGridBlock* b, double* row_cost /* yres */);
+/* Contiguous strips of equal estimated work: fills p->strip_bounds[0..world_size] (multiples of 16 rows for tall strips, of 4
+ * rows otherwise, except at the ends of the crop window) and sets p->strip_rows = -2. */
+AQH_EXPORT int aqh_balance_strips(AqhFrameParams* p, const double* row_cost /* yres */);
+
+/* The one collective of the path: the finished strips of every rank travel to `root` over NVLink (grouped
+ * ncclSend/ncclRecv straight from / into the device images, no staging, no packing: a strip is a contiguous range of
+ * rows).  NCCL is loaded at run time (libnccl.so.2); without it these return AQH_ERR_UNSUPPORTED.
+ *   aqh_comm_unique_id   rank 0 makes the 128-byte ncclUniqueId; the host carries it to the other ranks by its own means
+ *   aqh_comm_init        every rank joins (collective call)
+ *   aqh_gather           after aqh_render_device: stream-ordered on the hider's stream; on return from the following
+ *                        synchronisation root's device images hold the whole frame.
+ * With a communicator set, aqh_end_frame gathers before it downloads: root then owns the complete host images and
+ * fires the callbacks; the other ranks download nothing. */
+AQH_EXPORT int aqh_comm_unique_id(void* id128);
+AQH_EXPORT int aqh_comm_init(AqhHider* h, const void* id128, int rank, int world_size);
+AQH_EXPORT int aqh_comm_destroy(AqhHider* h);
+AQH_EXPORT int aqh_gather(AqhHider* h, int root);
 
 /* Host-side pieces of the path, exported so the reference-side tests can pin them. */
 AQH_EXPORT float aqh_box_filter(float x, float y, float xw, float yw);

@@ -312,8 +312,10 @@ F filterEval(int which, F x, F y, F xwidth, F ywidth)
 // The product's filter entry points are plain function pointers; the oracle identifies the
 // standard ones by probing them at a fixed point so it can use ITS OWN restatement, and
 // otherwise (user filter) calls through the pointer, as the reference would.
+int g_forcedFilterKind = -1;      // orc_set_filter: the filter chosen by name (callers that never load the product library)
 int identifyFilter(AqhFilterFunc f)
 {
+	if(g_forcedFilterKind >= 0) return g_forcedFilterKind;
 	if(!f) return 2;
 	const F px = 0.3f, py = 0.2f, pw = 3.f;
 	for(int k = 0; k < 8; ++k)
@@ -1989,6 +1991,8 @@ int orc_sampler_tables(int xs, int ys, int jitter, float* pos_xy, float* val1d, 
 	return s.ncache;
 }
 float orc_filter(int which, float x, float y, float xw, float yw) { return filterEval(which, x, y, xw, yw); }
+// which: 0 box, 1 triangle, 2 gaussian, 3 catmull-rom, 4 sinc, 5 mitchell, 6 disk, 7 bessel; < 0 = go by AqhFrameParams::filter_func again
+void orc_set_filter(int which) { g_forcedFilterKind = (which >= 0 && which < 8) ? which : -1; }
 void orc_invbilinear(const float* v, float px, float py, float* uv)
 {
 	InvBilinear inv;

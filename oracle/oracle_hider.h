@@ -42,6 +42,7 @@ uint32_t orc_random_int(uint32_t range);
 /* builds tables from the current oracle RNG state (consumes the stream, reseeds 19 when jitter) */
 int orc_sampler_tables(int xs, int ys, int jitter, float* pos_xy, float* val1d, int32_t* shuffled);
 float orc_filter(int which, float x, float y, float xw, float yw);
+void orc_set_filter(int which);   /* pixel filter of the following orc_render calls by index (see oracle_hider.cpp); < 0 = by filter_func */
 void orc_invbilinear(const float* verts8, float px, float py, float* uv);
 float orc_bilerp(float a, float b, float c, float d, float u, float v);
 int orc_filter_table(const AqhFrameParams* p, float* table);

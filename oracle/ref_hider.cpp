@@ -25,6 +25,11 @@
 //   * a display manager that captures each bucket's float channel buffer and quantises it like
 //     CqDisplayRequest::FormatBucketForDisplay (ddmanager.cpp:1022-1118), drawing the dither value
 //     from the reference's global CqRandom in the reference's order.
+//   * the pixel filter handed to CqOptions::SetfuncFilter is the REFERENCE'S OWN Ri*Filter (libs/core/filters.cpp is part
+//     of this library): chosen by name (ref_set_filter) or by recognising which standard filter the caller's function
+//     pointer computes; only a genuinely user-defined filter is called through the pointer;
+//   * ref_can_cull: the answers of the reference's CqOcclusionTree::canCull (occlusion.cpp:161-225) for a list of
+//     bounds, asked of every bucket's tree once the bucket's micropolygons are rendered.
 // The product never links or loads this library; tests/ and bench.py's CPU legs do.
 #include <vector>
 #include <string>
@@ -41,7 +46,12 @@
 
 #include "renderer.h"
 #include "imagebuffer.h"
+// The occlusion-feedback checker (ref_can_cull below) asks the bucket processor's own CqOcclusionTree; the tree is a
+// private member and the processors are locals of CqImageBuffer::RenderImage, so this translation unit -- and only
+// this one -- reads the class with its access specifiers lifted (the object layout is the same).
+#define private public
 #include "bucketprocessor.h"
+#undef private
 #include "micropolygon.h"
 #include "imagers.h"
 #include "options.h"
@@ -135,6 +145,34 @@ TqInt CqRenderer::OutputDataSamples(const char*) { return 0; }
 using namespace Aqsis;
 
 namespace {
+
+// ---------------------------------------------------------------------------------------
+// The reference's own pixel filters (libs/core/filters.cpp), by name or by recognising the function behind a pointer.
+struct RefFilter { const char* name; RtFilterFunc fn; };
+const RefFilter kRefFilters[] = {
+	{"box", RiBoxFilter}, {"triangle", RiTriangleFilter}, {"gaussian", RiGaussianFilter}, {"catmull-rom", RiCatmullRomFilter},
+	{"sinc", RiSincFilter}, {"mitchell", RiMitchellFilter}, {"disk", RiDiskFilter}, {"bessel", RiBesselFilter},
+};
+RtFilterFunc g_forcedFilter = 0;
+
+RtFilterFunc referenceFilterFor(AqhFilterFunc f)
+{
+	if(g_forcedFilter) return g_forcedFilter;
+	if(!f) return RiGaussianFilter;
+	static const float probes[5][2] = {{0.3f, 0.2f}, {-0.9f, 0.6f}, {1.3f, -1.2f}, {0.05f, -0.45f}, {-1.7f, 0.1f}};
+	for(const RefFilter& rf : kRefFilters)
+	{
+		bool same = true;
+		for(int w = 2; w <= 4 && same; ++w)
+			for(int i = 0; i < 5 && same; ++i)
+				same = f(probes[i][0], probes[i][1], float(w), float(w)) == rf.fn(probes[i][0], probes[i][1], float(w), float(w));
+		if(same) return rf.fn;
+	}
+	return reinterpret_cast<RtFilterFunc>(f);       // a user filter: tabulated through the pointer, as aqsis would
+}
+
+// Occlusion queries of the current ref_can_cull call (empty during ref_render).
+struct CullQueries { int n; const float* bounds; unsigned char* culledEverywhere; } g_cull = {0, 0, 0};
 
 // ---------------------------------------------------------------------------------------
 // A shader variable that is just a window onto the caller's AoS float array
@@ -263,6 +301,20 @@ public:
 	{
 		// CqDDManager::DisplayBucket, ddmanager.cpp:146-171: buckets outside the crop window are skipped
 		CqRenderer* rc = QGetRenderContext();
+		if(g_cull.n)
+		{
+			// the bucket processor this channel buffer is a member of (RenderImage passes &processor->getChannelBuffer())
+			const CqBucketProcessor* bp = reinterpret_cast<const CqBucketProcessor*>(
+				reinterpret_cast<const char*>(pBuffer) - offsetof(CqBucketProcessor, m_channelBuffer));
+			// a bound that misses the tree's area is "culled" by canCull itself (the cropped bound is empty), so every
+			// bucket can be asked: the surface survives if ANY bucket it could be re-posted to keeps it
+			for(int i = 0; i < g_cull.n; ++i)
+			{
+				const float* b = g_cull.bounds + 6*i;
+				CqBound bound(b[0], b[1], b[2], b[3], b[4], b[5]);
+				if(!bp->m_OcclusionTree.canCull(bound)) g_cull.culledEverywhere[i] = 0;
+			}
+		}
 		if(pBuffer->width() == 0 || pBuffer->height() == 0) return 0;
 		if(DRegion.xMax() <= rc->cropWindowXMin() || DRegion.yMax() <= rc->cropWindowYMin() ||
 		   DRegion.xMin() > rc->cropWindowXMax() || DRegion.yMin() > rc->cropWindowYMax())
@@ -368,7 +420,7 @@ int ref_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* chann
 		opt.GetStringOptionWrite("Hider", "depthfilter", 1)[0] = names[p.depth_filter];
 		opt.GetColorOptionWrite("limits", "zthreshold", 1)[0] = CqColor(p.zthreshold[0], p.zthreshold[1], p.zthreshold[2]);
 	}
-	opt.SetfuncFilter(p.filter_func ? reinterpret_cast<RtFilterFunc>(p.filter_func) : RiGaussianFilter);
+	opt.SetfuncFilter(referenceFilterFor(p.filter_func));
 	CqImageBuffer* image = new CqImageBuffer;
 	RefDDManager dd(p, channels, display_out);
 	g_refSetup.p = &p; g_refSetup.image = image; g_refSetup.dd = &dd;
@@ -477,6 +529,32 @@ int ref_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* chann
 	pCurrRenderer = 0;
 	delete rc;
 	return AQH_OK;
+}
+
+// Choose the pixel filter of the following ref_render calls by its RenderMan name ("box", "triangle", "gaussian",
+// "catmull-rom", "sinc", "mitchell", "disk", "bessel"): the reference's own Ri*Filter.  NULL or "" returns to
+// recognising AqhFrameParams::filter_func.  Returns 0, or AQH_ERR_BAD_PARAMS for an unknown name.
+int ref_set_filter(const char* name)
+{
+	g_forcedFilter = 0;
+	if(!name || !*name) return AQH_OK;
+	for(const RefFilter& rf : kRefFilters)
+		if(std::strcmp(rf.name, name) == 0) { g_forcedFilter = rf.fn; return AQH_OK; }
+	return AQH_ERR_BAD_PARAMS;
+}
+
+// What aqsis' occlusion culling would do with surfaces of the given raster bounds (xmin, ymin, zmin, xmax, ymax, zmax)
+// arriving after all of `grids` has been rendered: culled[i] = 1 when CqOcclusionTree::canCull(bound) holds in EVERY
+// bucket whose sample region the bound touches (RenderSurface then re-posts the surface from bucket to bucket until it
+// falls off the image, bucketprocessor.cpp:945-958), or when it touches none.
+int ref_can_cull(const AqhFrameParams* pp, const AqhGridBlock* grids, int n_bounds, const float* bounds, unsigned char* culled)
+{
+	if(n_bounds < 0 || (n_bounds && (!bounds || !culled))) return AQH_ERR_BAD_PARAMS;
+	for(int i = 0; i < n_bounds; ++i) culled[i] = 1;
+	g_cull.n = n_bounds; g_cull.bounds = bounds; g_cull.culledEverywhere = culled;
+	const int rc = ref_render(pp, grids, 0, 0, 0);
+	g_cull.n = 0;
+	return rc;
 }
 
 } // extern "C"

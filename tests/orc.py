@@ -12,6 +12,16 @@ import numpy as np
 from aqsis_b200 import _abi as abi
 from aqsis_b200._abi import FrameParams, GridBlock, DisplayDesc
 
+FILTER_INDEX = {"box": 0, "triangle": 1, "gaussian": 2, "catmull-rom": 3, "sinc": 4, "mitchell": 5, "disk": 6, "bessel": 7}
+
+
+def _filter_name_of(params):
+    """The pixel filter to select by NAME: only when the frame carries no function pointer (pure-python parameter
+    blocks of bench.py --impl reference); otherwise the checkers recognise the function behind the pointer."""
+    if params.filter_func:
+        return None
+    return getattr(params, "_filter_name", None) or "gaussian"
+
 class OrcStats(C.Structure):
     """OrcStats of oracle/oracle_hider.h."""
     _fields_ = [
@@ -68,6 +78,8 @@ def lib():
         L.orc_replay.argtypes = [C.POINTER(FrameParams), vp, vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]
         L.orc_dof_bounds.argtypes = [ci, ci, vp]
         L.orc_dof_bounds.restype = None
+        L.orc_set_filter.argtypes = [ci]
+        L.orc_set_filter.restype = None
         _lib = L
     return _lib
 
@@ -127,7 +139,10 @@ def render(params: FrameParams, grids, nthreads=1):
         outs.append(a)
         ptrs[d] = a.ctypes.data
     st = OrcStats()
+    name = _filter_name_of(params)
+    L.orc_set_filter(FILTER_INDEX[name] if name else -1)
     rc = L.orc_render(C.byref(params), C.byref(b), ch.ctypes.data, ptrs, int(nthreads), C.byref(st))
+    L.orc_set_filter(-1)
     if rc:
         raise RuntimeError(f"orc_render failed: {abi.STATUS_NAMES.get(rc, rc)}")
     return ch, outs, st.as_dict()
@@ -143,6 +158,8 @@ def refhider():
             return None
         L = C.CDLL(REFHIDER_LIB)
         L.ref_render.argtypes = [C.POINTER(FrameParams), C.POINTER(GridBlock), C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(OrcStats)]
+        L.ref_set_filter.argtypes = [C.c_char_p]
+        L.ref_can_cull.argtypes = [C.POINTER(FrameParams), C.POINTER(GridBlock), C.c_int, C.c_void_p, C.c_void_p]
         _refhider = L
     return _refhider
 
@@ -162,10 +179,31 @@ def render_reference(params: FrameParams, grids):
         outs.append(a)
         ptrs[d] = a.ctypes.data
     st = OrcStats()
+    name = _filter_name_of(params)
+    L.ref_set_filter(name.encode() if name else None)
     rc = L.ref_render(C.byref(params), C.byref(b), ch.ctypes.data, ptrs, C.byref(st))
+    L.ref_set_filter(None)
     if rc:
         raise RuntimeError(f"ref_render failed: {abi.STATUS_NAMES.get(rc, rc)}")
     return ch, outs, st.as_dict()
+
+
+def reference_can_cull(params: FrameParams, grids, bounds):
+    """CqOcclusionTree::canCull of the reference's own hider for raster bounds (n, 6) = xmin ymin zmin xmax ymax zmax,
+    asked once all of `grids` is rendered: True where every bucket's tree culls the bound (ref_hider.cpp: ref_can_cull)."""
+    L = refhider()
+    if L is None:
+        raise RuntimeError("oracle/_ref/libaqsis_refhider.so is not available")
+    b = grids.as_struct()
+    bb = np.ascontiguousarray(bounds, np.float32).reshape(-1, 6)
+    out = np.zeros(len(bb), np.uint8)
+    name = _filter_name_of(params)
+    L.ref_set_filter(name.encode() if name else None)
+    rc = L.ref_can_cull(C.byref(params), C.byref(b), len(bb), bb.ctypes.data, out.ctypes.data)
+    L.ref_set_filter(None)
+    if rc:
+        raise RuntimeError(f"ref_can_cull failed: {abi.STATUS_NAMES.get(rc, rc)}")
+    return out.astype(bool)
 
 
 _pdiff = None

@@ -22,7 +22,7 @@ def header_functions():
 
 def test_library_exports_every_declared_symbol(native_lib):
     names = header_functions()
-    assert len(names) >= 35, names
+    assert len(names) >= 45, names
     out = subprocess.run(["nm", "-D", "--defined-only", libbuild.LIB], capture_output=True, text=True, check=True).stdout
     exported = set(l.split()[-1] for l in out.splitlines() if " T " in l)
     missing = [n for n in names if n not in exported]
@@ -40,16 +40,20 @@ def test_library_has_sm100a_kernels_only():
 def test_struct_layout_matches_header(native_lib):
     """Compile a probe against the header with gcc and compare sizeof/offsetof with the ctypes mirror."""
     probes = {
-        "AqhDisplayDesc": (abi.DisplayDesc, ["n_channels", "channel", "type", "quantize_zero", "quantize_dither"]),
+        "AqhDisplayDesc": (abi.DisplayDesc, ["n_channels", "channel", "type", "quantize_zero", "quantize_dither", "flags"]),
+        "AqhAovDesc": (abi.AovDesc, ["name", "n_floats"]),
         "AqhFrameParams": (abi.FrameParams, ["abi_version", "xres", "crop_ymax", "filter_func", "bucket_xsize", "shutter_close",
                                              "use_dof", "dof_scale_y", "depth_filter", "zthreshold", "exposure_gamma", "jitter",
-                                             "cam_to_raster", "rng_seed", "rng_predraws", "n_displays", "display", "rank",
-                                             "world_size", "strip_rows", "deep_hits_per_sample", "filter_mode"]),
-        "AqhGridDesc": (abi.GridDesc, ["cu", "nkeys", "key_times", "P", "Ci", "Oi", "culled", "flags", "lod_bounds"]),
+                                             "cam_to_raster", "rng_seed", "rng_predraws", "n_displays", "display", "n_aovs", "aov",
+                                             "rank", "world_size", "strip_rows", "strip_bounds", "deep_hits_per_sample",
+                                             "filter_mode", "plane_budget_mb", "reserved"]),
+        "AqhGridDesc": (abi.GridDesc, ["cu", "nkeys", "key_times", "P", "Ci", "Oi", "culled", "flags", "lod_bounds", "aov", "Ng", "N",
+                                       "radius", "csg_node"]),
         "AqhGridBlock": (abi.GridBlock, ["n_grids", "cu", "cv", "nkeys", "flags", "lod_bounds", "key_times", "P", "Ci", "Oi",
-                                         "culled", "memory_space"]),
-        "AqhCallbacks": (abi.Callbacks, ["user", "on_bucket", "on_data", "on_progress"]),
-        "AqhFrameStats": (abi.FrameStats, ["prepare_ms", "device_total_ms", "n_grids", "n_deep_hits", "gpu_launches", "d2h_bytes"]),
+                                         "culled", "memory_space", "aov", "Ng", "N", "radius", "csg_node"]),
+        "AqhCallbacks": (abi.Callbacks, ["user", "on_bucket", "on_data", "on_progress", "on_imager"]),
+        "AqhFrameStats": (abi.FrameStats, ["prepare_ms", "device_total_ms", "n_grids", "n_deep_hits", "gpu_launches", "d2h_bytes",
+                                           "device_bytes", "n_bands", "gather_ms"]),
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for cname, (_, fields) in probes.items():
@@ -83,6 +87,29 @@ def test_defaults_follow_reference_options(native_lib):
     assert (p.exposure_gain, p.exposure_gamma) == (1.0, 1.0) and p.rng_seed == 545 and p.jitter == 1
     assert list(p.zthreshold) == [1.0, 1.0, 1.0] and p.depth_filter == abi.DEPTHFILTER_MIN
     assert p.use_dof == 0 and p.shutter_open == 0.0 and p.shutter_close == 0.0
+
+
+def test_pure_python_parameter_blocks_equal_the_librarys(native_lib):
+    """bench.py --impl reference builds its parameter blocks without mapping the product library (hider.PURE): the
+    python mirrors of aqh_frame_params_default / aqh_frame_params_set_dof / aqh_display_from_mode must fill the same bytes."""
+    from aqsis_b200 import hider, scenes
+    made = {}
+    for pure in (False, True):
+        hider.PURE = pure
+        try:
+            made[pure] = [scenes.config1(scale=0.1)[0], scenes.config3(scale=0.05)[0], scenes.config4(scale=0.02)[0], default_params()]
+        finally:
+            hider.PURE = False
+    for a, b in zip(made[False], made[True]):
+        assert b.filter_func is None and a.filter_func
+        a.filter_func = None
+        assert bytes(a) == bytes(b)
+    d = abi.DisplayDesc()
+    for mode, order in [("rgba", 1), ("rgbaz", 0), ("z", 0), ("a", 1), ("rgb", 0)]:
+        assert native_lib.aqh_display_from_mode(C.byref(d), mode.encode(), order, 255.0, 0.0, 255.0, 0.5) == 0
+        e = abi.DisplayDesc()
+        hider._display_from_mode(e, mode, order, 255.0, 0.0, 255.0, 0.5)
+        assert bytes(d) == bytes(e)
 
 
 def test_set_dof_matches_reference_formula(native_lib):

@@ -180,6 +180,69 @@ def test_occlusion_feedback_flush_and_can_cull(gpu_hider):
     h.end_frame()
 
 
+@pytest.mark.parametrize("filt", [("gaussian", 2.0, 2.0), ("catmull-rom", 4.0, 4.0), ("box", 1.0, 1.0)])
+def test_can_cull_against_the_reference_occlusion_tree(gpu_hider, filt):
+    """aqh_can_cull vs CqOcclusionTree::canCull of aqsis' own hider (occlusion.cpp:161-225, asked of every bucket's tree
+    once the frame's micropolygons are rendered; oracle/ref_hider.cpp: ref_can_cull) on 1200 random raster bounds,
+    including bounds in the filter halo outside the crop window, on pixel edges and beyond the image.
+    The pixel-granular answer must never cull what the reference keeps; where both sides see whole pixels it agrees."""
+    import orc
+    if orc.refhider() is None:
+        pytest.skip("oracle/_ref/libaqsis_refhider.so did not travel")
+    p, g = scenes.config2(scale=0.08, filter=filt, samples=(4, 4))
+    p.crop_xmin, p.crop_xmax, p.crop_ymin, p.crop_ymax = 3, p.xres - 6, 2, p.yres - 5
+    rng = np.random.default_rng(5)
+    n = 1200
+    c = np.stack([rng.uniform(-6, p.xres + 6, n), rng.uniform(-6, p.yres + 6, n)], 1)
+    sz = rng.uniform(0.05, 14, (n, 2))
+    z = rng.uniform(1.5, 130, n)
+    b = np.concatenate([c - sz / 2, z[:, None], c + sz / 2, (z + rng.uniform(0, 3, n))[:, None]], 1).astype(np.float32)
+    b[:200, [0, 1, 3, 4]] = np.round(b[:200, [0, 1, 3, 4]])              # bounds that end exactly on pixel edges
+    b[:200, 3:5] = np.maximum(b[:200, 3:5], b[:200, 0:2])
+    b[200:260, 0] = p.crop_xmin - rng.uniform(0.1, 2.5, 60)              # in / around the filter halo left of the crop window
+    b[200:260, 3] = b[200:260, 0] + rng.uniform(0.05, 2.0, 60)
+    want = orc.reference_can_cull(p, g, b)
+    h = gpu_hider
+    h.begin_frame(p)
+    h.add_grid_block(g)
+    h.flush()
+    got = np.array([h.can_cull(x) for x in b])
+    h.end_frame()
+    wrong = np.nonzero(got & ~want)[0]
+    assert len(wrong) == 0, ("culled although aqsis keeps it", b[wrong[:5]])
+    assert want.sum() > 200 and got.sum() >= 0.8 * want.sum()          # pixel granularity gives up little
+
+
+def test_rejected_grids_leave_the_frame_untouched(gpu_hider):
+    """aqh_add_grid / aqh_add_grid_block are atomic: a rejected grid or block changes nothing, the caller may skip it."""
+    from aqsis_b200 import HiderError
+    p, g = scenes.config1(scale=0.15)
+    ch_a, d_a, _ = pu.run_product(gpu_hider, p, g)
+    h = gpu_hider
+    h.begin_frame(p)
+    half = g.n_grids // 2
+    nv = 81
+
+    def part(i0, i1, **kw):
+        from aqsis_b200 import GridArrays
+        return GridArrays(cu=g.cu[i0:i1].copy(), cv=g.cv[i0:i1].copy(), flags=g.flags[i0:i1].copy(), P=g.P[i0 * nv:i1 * nv],
+                          Ci=g.Ci[i0 * nv:i1 * nv], Oi=g.Oi[i0 * nv:i1 * nv], **kw)
+    h.add_grid_block(part(0, half))
+    bad = part(half, g.n_grids)
+    bad.cu[3] = 0                                              # fourth grid of the block is invalid
+    with pytest.raises(HiderError):
+        h.add_grid_block(bad)
+    bad2 = part(half, g.n_grids, nkeys=np.full(g.n_grids - half, 1, np.int32))
+    bad2.nkeys[5] = 300                                        # key count out of range
+    with pytest.raises(HiderError):
+        h.add_grid_block(bad2)
+    with pytest.raises(HiderError):
+        h.add_grid(g.P[:nv], 0, 8)
+    h.add_grid_block(part(half, g.n_grids))
+    ch_b, d_b = h.end_frame()
+    assert np.array_equal(ch_a.view(np.uint32), ch_b.view(np.uint32)) and np.array_equal(d_a[0], d_b[0])
+
+
 def test_camera_space_grids_are_projected_on_the_device(gpu_hider):
     """AQH_GRID_CAMERA_SPACE: k_project applies matCameraToRaster like CqMicroPolyGrid::Split (micropolygon.cpp:723-731)."""
     for make in (lambda: scenes.config1(scale=0.15), lambda: scenes.config3(scale=0.04, motion_px=6.0)):

@@ -119,13 +119,67 @@ def test_split_keeps_grid_payload_intact(native_lib):
     for part in parts:
         assert part.P.shape[0] == int(((part.cu + 1) * (part.cv + 1) * part.nkeys).sum())
         assert part.Ci.shape[0] == part.n_verts and len(part.key_times) == int(part.nkeys.sum())
-    # a grid far from every strip of a rank must not be sent to it
-    lo, hi = sharding.grid_row_ranges(p, g)
+    # a grid far from every strip of a rank must not be sent to it: recompute the library's rule (aqh_grid_rank_masks) in numpy
+    nv, nk = (g.cu.astype(np.int64) + 1) * (g.cv + 1), g.nkeys.astype(np.int64)
+    pstart = np.concatenate([[0], np.cumsum(nv * nk)])[:-1]
+    y, z = np.asarray(g.P)[:, 1], np.asarray(g.P)[:, 2].astype(np.float64)
+    coc = lambda zz: p.dof_multiplier * np.abs(1.0 / zz - p.dof_one_over_focal_distance) * p.dof_scale_y
+    pad = np.floor(p.filter_ywidth / 2.0) + 1.0 + np.maximum(coc(np.minimum.reduceat(z, pstart)), coc(np.maximum.reduceat(z, pstart))) * 1.001 + 1e-3
+    lo = np.floor(np.minimum.reduceat(y, pstart).astype(np.float64) - pad)
+    hi = np.ceil(np.maximum.reduceat(y, pstart).astype(np.float64) + pad)
+    masks = sharding.grid_rank_masks(p, g)
     for r, part in enumerate(parts):
         touched = np.zeros(g.n_grids, bool)
         for y0, y1 in sharding.strips_for_rank(p, r):
             touched |= (hi >= y0) & (lo < y1)
         assert part.n_grids == int(touched.sum())
+        assert np.array_equal(((masks >> np.uint64(r)) & np.uint64(1)).astype(bool), touched)
+
+
+def test_camera_space_grids_are_sharded_by_their_projection(native_lib):
+    """Ownership of AQH_GRID_CAMERA_SPACE grids is decided from the rows they project to (the same formula as k_project),
+    not from their camera-space y: the raster-space and the camera-space version of a frame shard identically."""
+    from aqsis_b200 import scenes, sharding
+    p, g = scenes.config3(scale=0.06)
+    p.world_size, p.strip_rows = 3, 16
+    want = sharding.grid_rank_masks(p, g)
+    pc, gc = scenes.to_camera_space(*scenes.config3(scale=0.06))
+    pc.world_size, pc.strip_rows = 3, 16
+    got = sharding.grid_rank_masks(pc, gc)
+    # the round trip raster -> camera -> raster moves a vertex by rounding noise only: at most a handful of borderline grids differ
+    assert (want != got).mean() < 0.01
+    assert np.all((got & ~want) == 0) or (want != got).sum() <= 5
+
+
+def test_contiguous_and_balanced_strips(native_lib):
+    """strip_rows -1: one contiguous strip per rank; -2: boundaries from aqh_balance_strips (equal estimated work)."""
+    from aqsis_b200 import scenes, sharding
+    p, g = scenes.config2(scale=0.25)
+    for world in (2, 4, 8):
+        p.world_size, p.strip_rows = world, -1
+        strips = [sharding.strips_for_rank(p, r) for r in range(world)]
+        assert all(len(s) == 1 for s in strips)
+        assert strips[0][0][0] == 0 and strips[-1][0][1] == p.yres
+        assert all(strips[r][0][1] == strips[r + 1][0][0] for r in range(world - 1))
+        sharding.balance_strips(p, [g])
+        assert p.strip_rows == -2
+        strips = [sharding.strips_for_rank(p, r) for r in range(world)]
+        assert strips[0][0][0] == 0 and strips[-1][0][1] == p.yres
+        assert all(strips[r][0][1] == strips[r + 1][0][0] for r in range(world - 1))
+        # the estimated work per rank is even for a statistically uniform scene
+        masks = sharding.grid_rank_masks(p, g)
+        share = np.array([int(((masks >> np.uint64(r)) & np.uint64(1)).sum()) for r in range(world)], float)
+        assert share.max() / share.min() < 1.35, share
+    # a scene whose grids sit in the top third: the balanced cuts crowd there
+    rows_used = np.asarray(g.P)[:, 1].reshape(g.n_grids, -1).mean(1) < p.yres / 3
+    from aqsis_b200 import GridArrays
+    idx = np.nonzero(rows_used)[0]
+    nv = 17 * 17
+    sel = (idx[:, None] * nv + np.arange(nv)[None, :]).ravel()
+    top = GridArrays(cu=g.cu[idx], cv=g.cv[idx], flags=g.flags[idx], P=np.asarray(g.P)[sel], Ci=np.asarray(g.Ci)[sel], Oi=np.asarray(g.Oi)[sel])
+    p.world_size = 4
+    sharding.balance_strips(p, [top])
+    assert p.strip_bounds[3] <= p.yres // 3 + 32
 
 
 def test_config4_streaming_shard_equals_post_hoc_shard():
