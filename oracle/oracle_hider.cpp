@@ -433,6 +433,7 @@ struct Frame
 	std::vector<F> filterValues;         // m_aFilterValues
 	std::vector<Bound> dofBounds;        // m_DofBounds
 	int filterKind;
+	int aovFloats, nch;                  // floats of the arbitrary output variables; channel buffer floats per pixel = 9 + aovFloats
 	// GetCircleOfConfusion, renderer.h:401-406
 	V2 coc(F depth) const
 	{
@@ -461,6 +462,10 @@ void setupLayout(Frame& f)
 	f.sw = p.crop_xmax + f.shiftX - f.sx0; f.sh = p.crop_ymax + f.shiftY - f.sy0;
 	f.bx0 = p.crop_xmin/p.bucket_xsize; f.by0 = p.crop_ymin/p.bucket_ysize;
 	f.bx1 = (p.crop_xmax-1)/p.bucket_xsize + 1; f.by1 = (p.crop_ymax-1)/p.bucket_ysize + 1;
+	// CqRenderer::RegisterOutputData, renderer.cpp:1520-1546: offsets in registration order behind the 9 standard floats
+	f.aovFloats = 0;
+	for(int a = 0; a < p.n_aovs; ++a) f.aovFloats += p.aov[a].n_floats;
+	f.nch = 9 + f.aovFloats;
 }
 
 // CqBucketProcessor::InitialiseFilterValues, bucketprocessor.cpp:811-856
@@ -542,7 +547,10 @@ void calculateDofBounds(int xs, int ys, std::vector<Bound>& out)
 // sample region contains it.  Keeping the pixels in one image-wide array indexed over
 // [crop-shift, crop+shift) is the same thing without the pointer shuffling.
 enum { Flag_Matte = 1, Flag_MatteAlpha = 2, Flag_Valid = 4 };     // imagepixel.h:94-99
-struct Hit { F d[7]; int flags; };    // R G B Or Og Ob Depth (slots 7,8 are never written by StoreSample)
+// R G B Or Og Ob Depth (slots 7,8 are never written by StoreSample); aov: the hit's arbitrary output variables
+// (StoreExtraData, bucketprocessor.cpp:1573-1643: the values at the micropolygon's own index, not interpolated) --
+// kept as a pointer into the grid's data instead of a copy; csg: index of the hit's CSG node or -1 (SqImageSample::csgNode)
+struct Hit { F d[7]; int flags; const F* aov; int csg; };
 struct SampleData                     // SqSampleData, imagepixel.h:122-151
 {
 	V2 position, dofOffset;
@@ -603,7 +611,7 @@ void setSamples(const Frame& f, Image& img, int x, int y, const PixelPicks& pk)
 	for(int i = 0; i < n; ++i)
 	{
 		SampleData& sd = *new (&img.samples[base+i]) SampleData();
-		sd.occludingHit.flags = 0;
+		sd.occludingHit.flags = 0; sd.occludingHit.aov = 0; sd.occludingHit.csg = -1;
 		sd.occlZ = FLT_MAX;
 		sd.data.clear();
 		img.dofOffsetIndices[base+i] = shuffledIndices[i];
@@ -630,6 +638,11 @@ struct GridView
 	const F* Ci; const F* Oi; const uint8_t* culled;
 	F lod[2];
 	std::vector<V3> split1, split2;    // SqTriangleSplitLine per key
+	const F* aov;                      // nverts * aovFloats or null
+	std::vector<const F*> radius;      // AQH_GRID_POINTS: per key, nverts raster radii
+	int csg;                           // primitive node of the grid in the frame's CSG tree or -1
+	std::vector<uint8_t> culledAll;    // caller's culled flags + backface / transparency culls (empty = use `culled`)
+	bool isCulled(int i) const { return culledAll.empty() ? (culled && culled[i]) : culledAll[i] != 0; }
 };
 
 struct Scene
@@ -680,6 +693,47 @@ void buildScene(const Frame& f, const AqhGridBlock& b, Scene& sc)
 		gv.Ci = b.Ci ? b.Ci + vOff*3 : 0;
 		gv.Oi = b.Oi ? b.Oi + vOff*3 : 0;
 		gv.culled = b.culled ? b.culled + vOff : 0;
+		gv.aov = (b.aov && f.aovFloats) ? b.aov + vOff*size_t(f.aovFloats) : 0;
+		gv.csg = ((gv.flags & AQH_GRID_USES_CSG) && b.csg_node) ? b.csg_node[g] : -1;
+		if(gv.flags & AQH_GRID_POINTS)
+		{
+			gv.radius.resize(gv.nkeys);
+			for(int k = 0; k < gv.nkeys; ++k) gv.radius[k] = b.radius + pOff + size_t(k)*gv.nverts;
+		}
+		// ---- culls CqMicroPolyGrid::Shade applies before the grid reaches the hider (micropolygon.cpp:431-474, 493-522)
+		if(gv.flags & (AQH_GRID_CULL_BACKFACING | AQH_GRID_CULL_TRANSPARENT))
+		{
+			gv.culledAll.assign(gv.nverts, 0);
+			if(gv.culled) for(int i = 0; i < gv.nverts; ++i) gv.culledAll[i] = gv.culled[i];
+			if((gv.flags & AQH_GRID_CULL_BACKFACING) && b.Ng && gv.csg < 0)
+			{
+				// camera-space P of the shaded key: ((s * Ng) . P) >= 0 faces away; s flips Ng to the side of a user normal
+				const F* Pc = b.P + pOff*3;
+				const F* Ng = b.Ng + vOff*3;
+				const F* N = b.N ? b.N + vOff*3 : 0;
+				for(int i = gv.nverts - 1; i >= 0; i--)
+				{
+					F s_ = 1.0f;
+					if(N)
+						s_ = ((N[3*i]*Ng[3*i] + N[3*i+1]*Ng[3*i+1] + N[3*i+2]*Ng[3*i+2]) < 0.0f) ? -1.0f : 1.0f;
+					const F nx = s_*Ng[3*i], ny = s_*Ng[3*i+1], nz = s_*Ng[3*i+2];
+					if((nx*Pc[3*i] + ny*Pc[3*i+1] + nz*Pc[3*i+2]) >= 0)
+						gv.culledAll[i] = 1;
+				}
+			}
+			const F* zt = f.p.zthreshold;
+			if((gv.flags & AQH_GRID_CULL_TRANSPARENT) && gv.Oi && !(zt[0] == 0 && zt[1] == 0 && zt[2] == 0))
+			{
+				// from the last shading point down, and only while Oi is black: the reference's loop breaks at the first other vertex
+				for(int i = gv.nverts - 1; i >= 0; i--)
+				{
+					if(gv.Oi[3*i] == 0 && gv.Oi[3*i+1] == 0 && gv.Oi[3*i+2] == 0)
+						gv.culledAll[i] = 1;
+					else
+						break;
+				}
+			}
+		}
 		gv.lod[0] = b.lod_bounds ? b.lod_bounds[2*g] : -1.f;
 		gv.lod[1] = b.lod_bounds ? b.lod_bounds[2*g+1] : -1.f;
 		gv.P.resize(gv.nkeys);
@@ -731,6 +785,7 @@ struct MicroPoly
 	int indexCode;
 	Bound bound;                       // m_Bound (union over keys when moving)
 	bool moving;
+	bool point; F radius;              // CqMicroPolygonPoints (geometry/points.h:327-371)
 	// moving only
 	std::vector<V3> keyPts;            // nkeys*4: m_Point0..3 = verts index, +1, +cu+1, +cu+2
 	std::vector<Bound> keyBounds;
@@ -797,6 +852,17 @@ void makeMicroPoly(const GridView& g, int index, MicroPoly& mp)
 {
 	mp.g = &g; mp.index = index;
 	const int cu = g.cu;
+	mp.point = (g.flags & AQH_GRID_POINTS) != 0;
+	if(mp.point)
+	{
+		// CqMicroPolygonPoints::Initialise, points.h:350-359: the bound is flat in z
+		mp.moving = false; mp.indexCode = 0;
+		mp.radius = g.radius[0][index];
+		const V3 pos = vert(g.P[0], index);
+		mp.bound.mn = V3{pos.x - mp.radius, pos.y - mp.radius, pos.z - 0};
+		mp.bound.mx = V3{pos.x + mp.radius, pos.y + mp.radius, pos.z + 0};
+		return;
+	}
 	mp.indexCode = computeVertexOrder(g.P[0], index, cu);
 	mp.moving = g.nkeys > 1;
 	if(!mp.moving)
@@ -980,6 +1046,20 @@ bool triangleSplitReject(const Frame& f, const GridView& g, const SampleData& s,
 // CqMicroPolygon::Sample, micropolygon.cpp:1561-1660
 bool sampleStatic(const Frame& f, const MicroPoly& mp, HitTestCache& c, const SampleData& s, F& D, V2& uv, F time, bool usingDof)
 {
+	if(mp.point)
+	{
+		// CqMicroPolygonPoints::Sample, geometry/points.cpp:653-664
+		V2 sampPos = s.position;
+		if(usingDof)
+			sampPos = V2{sampPos.x + s.dofOffset.x*c.cocMult[0].x, sampPos.y + s.dofOffset.y*c.cocMult[0].y};
+		if(mag2_2d(c.P[0].x - sampPos.x, c.P[0].y - sampPos.y) < mp.radius*mp.radius)
+		{
+			D = c.P[0].z;
+			uv = V2{0, 0};
+			return true;
+		}
+		return false;
+	}
 	if(usingDof)
 	{
 		if(!dofSampleInBound(mp.bound, c, s))
@@ -1087,7 +1167,7 @@ struct MpgSampleInfo
 void cacheOutputInterpCoeffs(const MicroPoly& mp, MpgSampleInfo& c)
 {
 	const GridView& g = *mp.g;
-	c.smoothInterpolation = (g.flags & AQH_GRID_SMOOTH) != 0;
+	c.smoothInterpolation = (g.flags & AQH_GRID_SMOOTH) != 0 && !mp.point;     // points: CacheOutputInterpCoeffsConstant
 	const int idx[4] = {mp.index, mp.index+1, mp.index + g.cu + 1, mp.index + g.cu + 2};
 	const int nc = c.smoothInterpolation ? 4 : 1;
 	for(int i = 0; i < nc; ++i)
@@ -1171,11 +1251,18 @@ void storeSample(BucketCtx& b, const MicroPoly& mp, const MpgSampleInfo& info, S
 		hit->flags = 0;
 		b.deepHits++;
 	}
+	hit->aov = 0; hit->csg = -1;
 	F col[3], opa[3];
 	interpolateOutputs(info, uv, col, opa);
 	hit->d[0] = col[0]; hit->d[1] = col[1]; hit->d[2] = col[2];
 	hit->d[3] = opa[0]; hit->d[4] = opa[1]; hit->d[5] = opa[2];
 	hit->d[6] = D;
+	// StoreExtraData (usesDataMap = the frame registered output variables, micropolygon.cpp:61-62): the values at the
+	// micropolygon's index.  A grid without the variables leaves the slots as they were in the reference's pixel pool
+	// (stale); here, as in the product, they read as zero.
+	if(f.aovFloats && mp.g->aov)
+		hit->aov = mp.g->aov + size_t(mp.index)*f.aovFloats;
+	hit->csg = mp.g->csg;
 	hit->flags |= matteFlag;
 }
 
@@ -1187,6 +1274,9 @@ void renderMPGStatic(BucketCtx& b, const MicroPoly& mp, const MpgSampleInfo& inf
 	bool UsingLevelOfDetail = LodBounds[0] >= 0.0f;
 	bool isCullable = info.isCullable;
 	HitTestCache c;
+	if(mp.point)
+		c.P[0] = vert(mp.g->P[0], mp.index);     // CqMicroPolygonPoints::CacheHitTestValues, points.cpp:666-671
+	else
 	{   // CacheHitTestValues(cache, false), micropolygon.cpp:1394-1432
 		const F* gridP = mp.g->P[0];
 		int cu = mp.g->cu;
@@ -1254,7 +1344,12 @@ void renderMPGMBOrDof(BucketCtx& b, MicroPoly& mp, const MpgSampleInfo& info, bo
 	bool isCullable = info.isCullable;
 	HitTestCache c;
 	c.lastFailedEdge = 0;
-	if(!IsMoving)
+	if(mp.point)
+	{   // CqMicroPolygonPoints::CacheHitTestValues, points.cpp:666-671
+		c.P[0] = vert(mp.g->P[0], mp.index);
+		if(UsingDof) c.cocMult[0] = f.coc(c.P[0].z);
+	}
+	else if(!IsMoving)
 	{   // CqMicroPolygon::CacheHitTestValues, micropolygon.cpp:1394-1432
 		const F* gridP = mp.g->P[0];
 		int cu = mp.g->cu;
@@ -1423,16 +1518,111 @@ void renderMicroPoly(BucketCtx& b, MicroPoly& mp)
 	bool UsingDof = f.p.use_dof != 0;
 	bool IsMoving = mp.moving;
 	MpgSampleInfo info;
-	info.isCullable = !((f.p.display_mode & AQH_DMODE_Z) &&
+	info.isCullable = !(mp.g->csg >= 0) && !((f.p.display_mode & AQH_DMODE_Z) &&
 	                    (f.p.depth_filter == AQH_DEPTHFILTER_MAX || f.p.depth_filter == AQH_DEPTHFILTER_AVERAGE));
 	cacheOutputInterpCoeffs(mp, info);
+	if(mp.point && IsMoving) return;            // CqMicroPolygonMotionPoints is outside the implemented path
 	if(IsMoving || UsingDof)
 		renderMPGMBOrDof(b, mp, info, IsMoving, UsingDof);
 	else
 		renderMPGStatic(b, mp, info);
 }
 
-// CqImagePixel::Combine for one sample, imagepixel.cpp:144-332 (CSG resolve omitted: no CSG support)
+// ---- CSG: CqCSGTreeNode::ProcessTree / ProcessSampleList / EvaluateState, csgtree.cpp:144-351 --------------------
+struct CsgTree
+{
+	std::vector<int> type, parent;
+	std::vector<std::vector<int> > children;     // in node-index order = the order RiSolidBegin created them
+};
+CsgTree g_csg;
+
+bool csgEvaluate(int type, const std::vector<char>& st)
+{
+	switch(type)
+	{
+		case AQH_CSG_UNION:
+			for(size_t i = 0; i < st.size(); ++i) if(st[i]) return true;
+			return false;
+		case AQH_CSG_INTERSECTION:
+			for(size_t i = 0; i < st.size(); ++i) if(!st[i]) return false;
+			return true;
+		case AQH_CSG_DIFFERENCE:
+			if(!st.empty() && st[0])
+			{
+				for(size_t i = 1; i < st.size(); ++i) if(st[i]) return false;
+				return true;
+			}
+			return false;
+	}
+	return false;
+}
+
+void csgProcessSampleList(int node, std::vector<Hit>& samples)
+{
+	const CsgTree& T = g_csg;
+	if(T.type[node] == AQH_CSG_PRIMITIVE)
+	{
+		// CqCSGNodePrimitive::ProcessSampleList: only reached when a primitive is the top of its tree
+		for(size_t i = 0; i < samples.size(); ++i) if(samples[i].csg == node) samples[i].csg = -1;
+		return;
+	}
+	const std::vector<int>& kids = T.children[node];
+	for(size_t k = 0; k < kids.size(); ++k)
+		if(T.type[kids[k]] != AQH_CSG_PRIMITIVE)
+			csgProcessSampleList(kids[k], samples);
+	std::vector<char> state(kids.size(), 0);
+	std::vector<int> childIndex(samples.size());
+	for(size_t j = 0; j < samples.size(); ++j)
+	{
+		childIndex[j] = -1;
+		if(samples[j].csg >= 0 && T.parent[samples[j].csg] == node)
+			for(size_t k = 0; k < kids.size(); ++k) if(kids[k] == samples[j].csg) childIndex[j] = int(k);
+	}
+	// (the reference's "camera starts inside a solid" loop tests Primitive && Union on the same node: it never fires)
+	bool current = csgEvaluate(T.type[node], state);
+	size_t i = 0;
+	for(size_t j = 0; i < samples.size(); ++j)
+	{
+		if(childIndex[j] >= 0)
+			state[childIndex[j]] = !state[childIndex[j]];
+		else
+		{
+			++i;
+			continue;
+		}
+		bool next = csgEvaluate(T.type[node], state);
+		if(next == current)
+			samples.erase(samples.begin() + i);
+		else
+		{
+			current = next;
+			samples[i].csg = (T.parent[node] >= 0) ? node : -1;
+			++i;
+		}
+	}
+}
+
+void csgResolve(std::vector<Hit>& samples)
+{
+	// imagepixel.cpp:166-189: as long as any sample belongs to a CSG node, run its whole tree over the list
+	bool processed;
+	do
+	{
+		processed = false;
+		for(size_t i = 0; i < samples.size(); ++i)
+			if(samples[i].csg >= 0)
+			{
+				int top = samples[i].csg;
+				while(g_csg.parent[top] >= 0) top = g_csg.parent[top];
+				csgProcessSampleList(top, samples);
+				processed = true;
+				break;
+			}
+	}
+	while(processed);
+}
+
+// CqImagePixel::Combine for one sample, imagepixel.cpp:144-332
 void combineSample(SampleData& sampleData, int depthfilter, const F* zThreshold)
 {
 	Hit& occlHit = sampleData.occludingHit;
@@ -1444,6 +1634,8 @@ void combineSample(SampleData& sampleData, int depthfilter, const F* zThreshold)
 		// tests exercise.  stable_sort keeps submission order on ties (the product's rule).
 		std::stable_sort(sampleData.data.begin(), sampleData.data.end(),
 		                 [](const Hit& a, const Hit& b) { return a.d[6] < b.d[6]; });
+		if(!g_csg.type.empty())
+			csgResolve(sampleData.data);
 		F samplecolor[3] = {0, 0, 0}, sampleopacity[3] = {0, 0, 0};
 		F opaqueDepths[2] = { sampleData.occlZ, FLT_MAX };
 		F maxOpaqueDepth = FLT_MAX;
@@ -1474,6 +1666,8 @@ void combineSample(SampleData& sampleData, int depthfilter, const F* zThreshold)
 					maxOpaqueDepth = sd[6];
 			}
 		}
+		if(sampleData.data.empty())
+			return;                                  // CSG removed every entry: the occluding hit (if any) stays as it is
 		occlHit = *sampleData.data.begin();
 		F* occlData = occlHit.d;
 		for(int k = 0; k < 3; ++k) { occlData[k] = samplecolor[k]; occlData[3+k] = sampleopacity[k]; }
@@ -1535,7 +1729,7 @@ struct BucketInfo
 
 // CqBucketProcessor::FilterBucket (live non-separable branch) + alpha/coverage,
 // bucketprocessor.cpp:584-707, then ExposeBucket :766-806.
-void filterBucket(const Frame& f, Image& img, const BucketInfo& bk, bool hasValidSamples, F* channels /*image, 9/pixel*/)
+void filterBucket(const Frame& f, Image& img, const BucketInfo& bk, bool hasValidSamples, F* channels /*image, f.nch floats per pixel*/)
 {
 	const AqhFrameParams& p = f.p;
 	const int xres = p.xres;
@@ -1553,8 +1747,10 @@ void filterBucket(const Frame& f, Image& img, const BucketInfo& bk, bool hasVali
 		F ycent = y + 0.5f;
 		for(int x = begx; x < endx; x++)
 		{
-			F* out = channels + (size_t(y)*xres + x)*9;
+			F* out = channels + (size_t(y)*xres + x)*f.nch;
 			F coverage = 0;
+			F aovSum[AQH_MAX_AOV_FLOATS];
+			for(int k = 0; k < f.aovFloats; ++k) { aovSum[k] = 0; out[9 + k] = 0.0f; }
 			if(hasValidSamples)
 			{
 				F xcent = x + 0.5f;
@@ -1584,6 +1780,9 @@ void filterBucket(const Frame& f, Image& img, const BucketInfo& bk, bool hasVali
 									{
 										for(int k = 0; k < datasize; ++k)
 											samples[k] += opv.d[k] * g;
+										// the extra floats of the hit are filtered like colour (bucketprocessor.cpp:620-629)
+										for(int k = 0; k < f.aovFloats; ++k)
+											aovSum[k] += (opv.aov ? opv.aov[k] : 0.0f) * g;
 										SampleCount++;
 									}
 								}
@@ -1601,6 +1800,7 @@ void filterBucket(const Frame& f, Image& img, const BucketInfo& bk, bool hasVali
 					float oneOverGTot = 1.0 / gTot;
 					for(int k = 0; k < 6; ++k) out[k] = samples[k] * oneOverGTot;
 					out[AQH_CH_Z] = samples[6] * oneOverGTot;
+					for(int k = 0; k < f.aovFloats; ++k) out[9 + k] = aovSum[k] * oneOverGTot;
 					if(SampleCount >= numSubPixels)
 						coverage = 1.0;
 					else
@@ -1628,7 +1828,7 @@ void filterBucket(const Frame& f, Image& img, const BucketInfo& bk, bool hasVali
 	for(int y = begy; y < endy; y++)
 		for(int x = begx; x < endx; x++)
 		{
-			F* buffer = channels + (size_t(y)*xres + x)*9;
+			F* buffer = channels + (size_t(y)*xres + x)*f.nch;
 			if(exposegain != 1.0)
 			{
 				buffer[0] *= exposegain; buffer[1] *= exposegain; buffer[2] *= exposegain;
@@ -1684,7 +1884,7 @@ void formatBucketForDisplay(const Frame& f, const BucketInfo& bk, const AqhDispl
 			unsigned char* pdata = out + (size_t(y)*xres + x)*esize;
 			for(int c = 0; c < d.n_channels; ++c)
 			{
-				double value = channels[(size_t(y)*xres + x)*9 + d.channel[c]];
+				double value = channels[(size_t(y)*xres + x)*f.nch + d.channel[c]];
 				if(d.quantize_one != 0)
 				{
 					value = lround_aq(d.quantize_zero + value * (d.quantize_one - d.quantize_zero) + (d.quantize_dither * s));
@@ -1750,7 +1950,11 @@ int orc_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* chann
 	if(!pp || !grids || grids->memory_space != 0) return AQH_ERR_BAD_PARAMS;
 	if(pp->crop_xmax <= pp->crop_xmin || pp->crop_ymax <= pp->crop_ymin) return AQH_ERR_BAD_PARAMS;
 	for(int64_t g = 0; g < grids->n_grids; ++g)
-		if(grids->flags[g] & AQH_GRID_USES_CSG) return AQH_ERR_UNSUPPORTED;
+	{
+		if((grids->flags[g] & AQH_GRID_USES_CSG) && (!grids->csg_node || grids->csg_node[g] < 0 || grids->csg_node[g] >= (int)g_csg.type.size()))
+			return AQH_ERR_BAD_PARAMS;
+		if((grids->flags[g] & AQH_GRID_POINTS) && (!grids->radius || grids->cv[g] != 0)) return AQH_ERR_BAD_PARAMS;
+	}
 	double t0 = nowSec();
 	Frame f;
 	f.p = *pp;
@@ -1817,13 +2021,23 @@ int orc_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* chann
 	for(size_t gi = 0; gi < sc.grids.size(); ++gi)
 	{
 		const GridView& g = sc.grids[gi];
-		for(int iv = 0; iv < g.cv; iv++)
-			for(int iu = 0; iu < g.cu; iu++)
+		const bool points = (g.flags & AQH_GRID_POINTS) != 0;      // CqMicroPolyGridPoints::Split: one micropolygon per point, no culled flags
+		for(int iv = 0; iv < (points ? 1 : g.cv); iv++)
+			for(int iu = 0; iu < (points ? g.nverts : g.cu); iu++)
 			{
-				int iIndex = (iv*(g.cu + 1)) + iu;
-				if(g.culled && g.culled[iIndex])
+				int iIndex = points ? iu : (iv*(g.cu + 1)) + iu;
+				if(!points && g.isCulled(iIndex))
 					continue;
+				if(points && g.nkeys > 1)
+					continue;                                         // moving points: outside the implemented path
 				Bound B;
+				if(points)
+				{
+					const V3 pos = vert(g.P[0], iIndex);
+					const F r = g.radius[0][iIndex];
+					B.mn = V3{pos.x - r, pos.y - r, pos.z - 0}; B.mx = V3{pos.x + r, pos.y + r, pos.z + 0};
+				}
+				else
 				{
 					const int cu = g.cu;
 					const F* P = g.P[0];
@@ -1914,11 +2128,11 @@ int orc_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* chann
 	F* channels = channelsOut;
 	if(!channels)
 	{
-		localChannels.assign(size_t(p.xres)*p.yres*9, 0.f);
+		localChannels.assign(size_t(p.xres)*p.yres*f.nch, 0.f);
 		channels = localChannels.data();
 	}
 	else
-		std::fill(channels, channels + size_t(p.xres)*p.yres*9, 0.f);
+		std::fill(channels, channels + size_t(p.xres)*p.yres*f.nch, 0.f);
 	std::vector<int> esize(std::max(1, p.n_displays), 0);
 	for(int d = 0; d < p.n_displays; ++d)
 	{
@@ -1993,6 +2207,21 @@ int orc_sampler_tables(int xs, int ys, int jitter, float* pos_xy, float* val1d, 
 float orc_filter(int which, float x, float y, float xw, float yw) { return filterEval(which, x, y, xw, yw); }
 // which: 0 box, 1 triangle, 2 gaussian, 3 catmull-rom, 4 sinc, 5 mitchell, 6 disk, 7 bessel; < 0 = go by AqhFrameParams::filter_func again
 void orc_set_filter(int which) { g_forcedFilterKind = (which >= 0 && which < 8) ? which : -1; }
+// The CSG tree of the following orc_render calls (what aqh_set_csg_tree gives the product); n_nodes = 0 clears it.
+int orc_set_csg_tree(int n_nodes, const int32_t* type, const int32_t* parent)
+{
+	g_csg = CsgTree();
+	if(n_nodes <= 0) return AQH_OK;
+	g_csg.type.assign(type, type + n_nodes);
+	g_csg.parent.assign(parent, parent + n_nodes);
+	g_csg.children.assign(n_nodes, std::vector<int>());
+	for(int i = 0; i < n_nodes; ++i)
+	{
+		if(parent[i] >= n_nodes || parent[i] == i || type[i] < 0 || type[i] > AQH_CSG_DIFFERENCE) { g_csg = CsgTree(); return AQH_ERR_BAD_PARAMS; }
+		if(parent[i] >= 0) g_csg.children[parent[i]].push_back(i);
+	}
+	return AQH_OK;
+}
 void orc_invbilinear(const float* v, float px, float py, float* uv)
 {
 	InvBilinear inv;

@@ -25,7 +25,7 @@ typedef struct OrcStats
 	int32_t threads;
 } OrcStats;
 
-/* Render one frame.  grids->memory_space must be 0.  channels: xres*yres*9 floats (may be NULL);
+/* Render one frame.  grids->memory_space must be 0.  channels: xres*yres*(9 + AOV floats) floats (may be NULL);
  * display_out[d]: xres*yres*entrysize(d) bytes (entries may be NULL).  nthreads <= 1 follows the
  * reference's single-threaded bucket loop literally; > 1 distributes buckets over threads
  * (identical results: pixels are owned by exactly one bucket). */
@@ -42,6 +42,7 @@ uint32_t orc_random_int(uint32_t range);
 /* builds tables from the current oracle RNG state (consumes the stream, reseeds 19 when jitter) */
 int orc_sampler_tables(int xs, int ys, int jitter, float* pos_xy, float* val1d, int32_t* shuffled);
 float orc_filter(int which, float x, float y, float xw, float yw);
+int orc_set_csg_tree(int n_nodes, const int32_t* type, const int32_t* parent);   /* CSG tree of the following orc_render calls; 0 nodes = none */
 void orc_set_filter(int which);   /* pixel filter of the following orc_render calls by index (see oracle_hider.cpp); < 0 = by filter_func */
 void orc_invbilinear(const float* verts8, float px, float py, float* uv);
 float orc_bilerp(float a, float b, float c, float d, float u, float v);
