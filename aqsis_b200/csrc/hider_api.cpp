@@ -68,6 +68,11 @@ void resetFrameGrids(AqhHider* h)
 	h->anyMotionG = h->anyLodG = h->anyTriG = h->anyCamG = false;
 	h->nVerts = h->nPos = 0;
 	h->anyCi = h->anyOi = h->anyCulled = false; h->allCi = h->allOi = true;
+	h->gcsg.clear(); h->csgType.clear(); h->csgParent.clear(); h->csgSlot.clear(); h->csgKids.clear(); h->csgOrder.clear();
+	h->hxAov.clear(); h->hxNg.clear(); h->hxN.clear(); h->hxRadius.clear();
+	h->anyAov = h->anyNg = h->anyN = h->anyRadius = h->anyCSG = h->anyPoints = false;
+	h->upPos = h->upVerts = h->upGrids = h->flushedPos = 0; h->upSegs = 0;
+	h->haveZ = h->sawTransparent = false; h->flushBinEntries = h->nFlushes = 0;
 	h->stPUsed = h->stVUsed = 0;
 }
 
@@ -286,11 +291,26 @@ void buildTiling(AqhHider* h, bool mbdof)
 
 // Everything about one grid that can be wrong, checked BEFORE any state is touched: a rejected grid or block
 // leaves the frame exactly as it was (the caller may skip it and go on).
-int checkGrid(AqhHider* h, int cu, int cv, int nkeys, uint32_t flags, const float* times)
+int checkGrid(AqhHider* h, int cu, int cv, int nkeys, uint32_t flags, const float* times, int csgNode, const float* radius, const float* Ng)
 {
-	if(cu < 1 || cv < 1 || cu > 65535 || cv > 65535) return h->fail(AQH_ERR_BAD_PARAMS, "grid resolution out of range");
+	if(flags & AQH_GRID_POINTS)
+	{
+		// CqMicroPolyGridPoints: cu + 1 points, no second dimension
+		if(cu < 0 || cu > 65535 || cv != 0) return h->fail(AQH_ERR_BAD_PARAMS, "a points grid has cu + 1 points and cv = 0");
+		if(!radius) return h->fail(AQH_ERR_BAD_PARAMS, "points grid without radii");
+		if(nkeys != 1) return h->fail(AQH_ERR_UNSUPPORTED, "moving points (CqMicroPolygonMotionPoints) are not supported");
+		if(flags & (AQH_GRID_TRIANGULAR | AQH_GRID_USES_CSG)) return h->fail(AQH_ERR_BAD_PARAMS, "points grids are neither triangular nor part of a solid");
+	}
+	else if(cu < 1 || cv < 1 || cu > 65535 || cv > 65535) return h->fail(AQH_ERR_BAD_PARAMS, "grid resolution out of range");
 	if(nkeys < 1 || nkeys > 255) return h->fail(AQH_ERR_BAD_PARAMS, "grid key count out of range");
-	if(flags & AQH_GRID_USES_CSG) return h->fail(AQH_ERR_UNSUPPORTED, "CSG grids are not supported");
+	if(flags & AQH_GRID_USES_CSG)
+	{
+		if(csgNode < 0 || csgNode >= (int)h->csgType.size())
+			return h->fail(AQH_ERR_BAD_PARAMS, "CSG grid without a node of the tree given to aqh_set_csg_tree");
+		if(h->csgType[csgNode] != AQH_CSG_PRIMITIVE) return h->fail(AQH_ERR_BAD_PARAMS, "a grid belongs to a primitive node of the CSG tree");
+	}
+	if((flags & AQH_GRID_CULL_BACKFACING) && (!Ng || !(flags & AQH_GRID_CAMERA_SPACE)))
+		return h->fail(AQH_ERR_BAD_PARAMS, "backface culling needs camera-space P and the geometric normals Ng");
 	if(nkeys > 1 && !times) return h->fail(AQH_ERR_BAD_PARAMS, "motion grid without key times");
 	return AQH_OK;
 }
@@ -300,26 +320,29 @@ struct GridTablesMark
 {
 	size_t nGrids, nKeyTimes, nRecs, nChunk;
 	uint64_t recVb, recPb, recKo;
-	bool anyMotionG, anyLodG, anyTriG, anyCamG;
+	bool anyMotionG, anyLodG, anyTriG, anyCamG, anyCSG, anyPoints;
 };
 GridTablesMark markGridTables(const AqhHider* h)
 {
 	return GridTablesMark{h->gcu.size(), h->gkeyTimes.size(), h->recs.n, h->chunk.n, h->recVb, h->recPb, h->recKo,
-	                      h->anyMotionG, h->anyLodG, h->anyTriG, h->anyCamG};
+	                      h->anyMotionG, h->anyLodG, h->anyTriG, h->anyCamG, h->anyCSG, h->anyPoints};
 }
 void rollbackGridTables(AqhHider* h, const GridTablesMark& m)
 {
 	h->gcu.resize(m.nGrids); h->gcv.resize(m.nGrids); h->gnkeys.resize(m.nGrids); h->gflags.resize(m.nGrids);
-	h->glod.resize(2*m.nGrids); h->gkeyTimes.resize(m.nKeyTimes);
+	h->glod.resize(2*m.nGrids); h->gkeyTimes.resize(m.nKeyTimes); h->gcsg.resize(m.nGrids);
 	h->recs.n = m.nRecs; h->chunk.n = m.nChunk;
 	h->recVb = m.recVb; h->recPb = m.recPb; h->recKo = m.recKo;
 	h->anyMotionG = m.anyMotionG; h->anyLodG = m.anyLodG; h->anyTriG = m.anyTriG; h->anyCamG = m.anyCamG;
+	h->anyCSG = m.anyCSG; h->anyPoints = m.anyPoints;
 }
 
-int appendGridTables(AqhHider* h, int cu, int cv, int nkeys, uint32_t flags, const float* lod, const float* times)
+int appendGridTables(AqhHider* h, int cu, int cv, int nkeys, uint32_t flags, const float* lod, const float* times, int csgNode)
 {
 	if(h->recKo + (uint64_t)nkeys >= (1u << 24)) return h->fail(AQH_ERR_BAD_PARAMS, "too many motion keys in one frame");
 	h->gcu.push_back(cu); h->gcv.push_back(cv); h->gnkeys.push_back(nkeys); h->gflags.push_back(flags);
+	h->gcsg.push_back((flags & AQH_GRID_USES_CSG) ? csgNode : -1);
+	h->anyCSG |= (flags & AQH_GRID_USES_CSG) != 0; h->anyPoints |= (flags & AQH_GRID_POINTS) != 0;
 	h->glod.push_back(lod ? lod[0] : -1.f); h->glod.push_back(lod ? lod[1] : -1.f);
 	for(int k = 0; k < nkeys; ++k) h->gkeyTimes.push_back(nkeys > 1 ? times[k] : 0.f);
 	// the grid's device record and the chunk index entries of the positions it covers
@@ -355,7 +378,7 @@ struct FrameTrace
 	void mark(const char* what) { if(!on) return; const double t = nowMs(); std::fprintf(stderr, "[aqh] %-22s +%8.3f ms  (%8.3f)\n", what, t - last, t - t0); last = t; }
 };
 
-int renderFrame(AqhHider* h, bool download, bool zOnly = false)
+int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbacks* imagerCb = nullptr)
 {
 	FrameTrace tr;
 	if(!h->inFrame) return h->fail(AQH_ERR_STATE, "no frame in progress");
@@ -387,14 +410,27 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 	tr.mark("tiling");
 	const int nActive = (int)h->activeTiles.size();
 
+	// ---- incremental flushes: a flush (zOnly) and every later call of the frame only upload and project what was
+	// submitted since the previous flush; projected positions (P4), packed shading (CO) and the per-sample occlusion keys
+	// persist in HBM in between
+	const bool incremental = zOnly || h->haveZ;
+	const size_t pos0 = incremental ? (size_t)h->upPos : 0, vert0 = incremental ? (size_t)h->upVerts : 0;
 	// ---- device allocations
 	const size_t nPos = (size_t)h->nPos, nVerts = (size_t)h->nVerts;
 	CU(h->dGrids.reserve(std::max<size_t>(nRecs, 1)*sizeof(GridRec)), "cudaMalloc(grid table)");
 	CU(h->dChunk.reserve(nChunkEntries*4), "cudaMalloc(chunk table)");
 	CU(h->dKeyTimes.reserve(std::max<size_t>(h->gkeyTimes.size(), 1)*4), "cudaMalloc(key times)");
 	CU(h->dSplit.reserve(std::max<size_t>(h->gkeyTimes.size(), 1)*16), "cudaMalloc(split lines)");
-	CU(h->dP4.reserve(std::max<size_t>(nPos, 1)*16 + 64), "cudaMalloc(P4)");
-	CU(h->dCO.reserve(std::max<size_t>(nVerts, 1)*32 + 64), "cudaMalloc(packed Ci/Oi)");
+	if(incremental)
+	{
+		CU(h->dP4.reserveKeep(std::max<size_t>(nPos, 1)*16 + 64, pos0*16, st), "cudaMalloc(P4)");
+		CU(h->dCO.reserveKeep(std::max<size_t>(nVerts, 1)*32 + 64, vert0*32, st), "cudaMalloc(packed Ci/Oi)");
+	}
+	else
+	{
+		CU(h->dP4.reserve(std::max<size_t>(nPos, 1)*16 + 64), "cudaMalloc(P4)");
+		CU(h->dCO.reserve(std::max<size_t>(nVerts, 1)*32 + 64), "cudaMalloc(packed Ci/Oi)");
+	}
 	CU(h->dTileSlot.reserve(std::max<size_t>(h->tileSlot.size(), 1)*4), "cudaMalloc(tile slots)");
 	CU(h->dActive.reserve(std::max<size_t>(nActive, 1)*4), "cudaMalloc(active tiles)");
 	CU(h->dBinCount.reserve(std::max<size_t>(nActive, 1)*4), "cudaMalloc(bin counts)");
@@ -410,7 +446,8 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 	const int planeChunks = (nSamp + planeSC - 1)/planeSC;
 	const int planeW = ((L.sw + 31) & ~31) + 16;     // the filter stages spans of up to 32+14 pixels starting at multiples of 32
 	const int ntaps = (2*L.shiftX+1)*(2*L.shiftY+1);
-	const size_t planeRowBytes = size_t(planeW)*planeChunks*planeSC*8*4;          // 7 value planes + the mask plane
+	const int nPlanes = 7 + h->aovFloats + 1;                                      // R G B Or Og Ob Z, the AOV floats, the mask plane
+	const size_t planeRowBytes = size_t(planeW)*planeChunks*planeSC*nPlanes*4;
 	int ringRows = L.sh, bandTileRows = h->nty;
 	if(p.filter_mode == AQH_FILTER_REFERENCE_ORDER && !zOnly)
 	{
@@ -426,11 +463,12 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 	if(zOnly) {}
 	else if(p.filter_mode == AQH_FILTER_REFERENCE_ORDER)
 	{
-		CU(h->dPlanes.reserve(planeStride*8*4 + 256), "cudaMalloc(sample planes)");
+		CU(h->dPlanes.reserve(planeStride*nPlanes*4 + 256), "cudaMalloc(sample planes)");
 	}
 	else
 		CU(h->dPartials.reserve(size_t(ntaps)*9*L.sw*L.sh*4), "cudaMalloc(tap partial sums)");
-	CU(h->dChannels.reserve(size_t(p.xres)*p.yres*9*4), "cudaMalloc(channel buffer)");
+	const int nch = h->nChannels;
+	CU(h->dChannels.reserve(size_t(p.xres)*p.yres*nch*4), "cudaMalloc(channel buffer)");
 	DevDisplays disp{};
 	disp.n = p.n_displays;
 	for(int d = 0; d < p.n_displays; ++d)
@@ -458,10 +496,10 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 	// AQH_PIPELINE_MIN_POS: smallest frame (grid positions) that takes this route (default 2^20; tests force 1; a huge value disables it)
 	size_t pipeMin = size_t(1) << 20;
 	if(const char* e = std::getenv("AQH_PIPELINE_MIN_POS")) pipeMin = (size_t)std::strtoull(e, nullptr, 10);
-	bool pipelined = h->copyStream != nullptr && nPos >= std::max<size_t>(pipeMin, 1);
+	bool pipelined = !incremental && h->copyStream != nullptr && nPos >= std::max<size_t>(pipeMin, 1);
 	for(const Segment& s : h->segments)
 		if(s.memorySpace != 0 || (h->anyCi && !s.Ci) || (h->anyOi && !s.Oi)) pipelined = false;
-	const bool zeroCopy = h->segments.size() == 1 && h->segments[0].memorySpace == 1;
+	const bool zeroCopy = !incremental && h->segments.size() == 1 && h->segments[0].memorySpace == 1;
 	if(zeroCopy)
 	{
 		const Segment& s = h->segments[0];
@@ -473,12 +511,14 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 		if(h->anyCi) CU(h->dCi.reserve(nVerts*12), "cudaMalloc(Ci)");
 		if(h->anyOi) CU(h->dOi.reserve(nVerts*12), "cudaMalloc(Oi)");
 		if(h->anyCulled) CU(h->dCulled.reserve(nVerts), "cudaMalloc(culled)");
-		if(h->anyCulled) CU(cudaMemsetAsync(h->dCulled.p, 0, nVerts, st), "cudaMemsetAsync(culled)");
+		if(h->anyCulled && nVerts > vert0) CU(cudaMemsetAsync(h->dCulled.as<uint8_t>() + vert0, 0, nVerts - vert0, st), "cudaMemsetAsync(culled)");
 		std::vector<float> ones;
-		size_t po = 0, vo = 0;
+		size_t po = 0, vo = 0, segIndex = 0;
 		for(const Segment& s : h->segments)
 		{
 			if(pipelined) break;
+			// the raw arrays are only read by k_project: segments an earlier flush projected need not travel again
+			if(incremental && segIndex++ < h->upSegs) { po += s.nPos; vo += s.nVerts; continue; }
 			const float* sP = s.P; const float* sCi = s.Ci; const float* sOi = s.Oi; const uint8_t* sCu = s.culled;
 			if(s.staged)
 			{
@@ -554,6 +594,70 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 		dOi = h->anyOi ? h->dOi.as<float>() : nullptr;
 		dCulled = h->anyCulled ? h->dCulled.as<uint8_t>() : nullptr;
 	}
+	// ---- the rarely used arrays: arbitrary output variables, normals for the backface cull, point radii, CSG tables.
+	// Plain copies on the main stream (they are ahead of every kernel that reads them).
+	const float* dAov = nullptr; const float* dNg = nullptr; const float* dNn = nullptr; const float* dRadius = nullptr;
+	{
+		struct Extra { bool any; DevBuf* buf; size_t perVertex, perPos; const float* Segment::* member; std::vector<float>* staged; const float** out; const char* what; };
+		const size_t A = (size_t)h->aovFloats;
+		Extra extras[] = {
+			{h->anyAov && A > 0, &h->dAov, A, 0, &Segment::aov, &h->hxAov, &dAov, "cudaMemcpyAsync(arbitrary output variables)"},
+			{h->anyNg, &h->dNg, 3, 0, &Segment::Ng, &h->hxNg, &dNg, "cudaMemcpyAsync(Ng)"},
+			{h->anyN, &h->dNn, 3, 0, &Segment::N, &h->hxN, &dNn, "cudaMemcpyAsync(N)"},
+			{h->anyRadius, &h->dRadius, 0, 1, &Segment::radius, &h->hxRadius, &dRadius, "cudaMemcpyAsync(point radii)"},
+		};
+		for(Extra& x : extras)
+		{
+			if(!x.any) continue;
+			if(zeroCopy && h->segments[0].*(x.member)) { *x.out = h->segments[0].*(x.member); continue; }
+			const size_t total = (x.perVertex ? nVerts*x.perVertex : nPos*x.perPos);
+			CU(x.buf->reserve(std::max<size_t>(total, 1)*4), "cudaMalloc(extra grid arrays)");
+			CU(cudaMemsetAsync(x.buf->p, 0, std::max<size_t>(total, 1)*4, st), "cudaMemsetAsync");
+			size_t po2 = 0, vo2 = 0;
+			for(const Segment& sg : h->segments)
+			{
+				const size_t off = x.perVertex ? vo2*x.perVertex : po2*x.perPos;
+				const size_t cnt = x.perVertex ? size_t(sg.nVerts)*x.perVertex : size_t(sg.nPos)*x.perPos;
+				const float* src = sg.*(x.member);
+				cudaMemcpyKind kind = sg.memorySpace ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+				if(sg.staged)
+				{
+					// grids handed over one by one: the frame-global host copy (it may be shorter than the frame when later grids lack the array)
+					src = nullptr; kind = cudaMemcpyHostToDevice;
+					if(x.staged->size() > off) { src = x.staged->data() + off; if(x.staged->size() < off + cnt) { x.staged->resize(off + cnt, 0.f); src = x.staged->data() + off; } }
+				}
+				if(src && cnt)
+				{
+					CU(cudaMemcpyAsync(x.buf->as<float>() + off, src, cnt*4, kind, st), x.what);
+					if(kind == cudaMemcpyHostToDevice) S.h2d_bytes += (int64_t)cnt*4;
+				}
+				po2 += (size_t)sg.nPos; vo2 += (size_t)sg.nVerts;
+			}
+			CU(cudaStreamSynchronize(st), "cudaStreamSynchronize(extra grid arrays)");      // pageable host memory: keep it simple
+			*x.out = x.buf->as<float>();
+		}
+	}
+	const bool anyCullT = std::find_if(h->gflags.begin(), h->gflags.end(), [](uint32_t fl) { return (fl & AQH_GRID_CULL_TRANSPARENT) != 0; }) != h->gflags.end();
+	if(anyCullT)
+	{
+		const size_t g0 = incremental ? (size_t)h->upGrids : 0;
+		CU(h->dGridTail.reserveKeep(std::max<size_t>(nRecs, 1)*4, g0*4, st), "cudaMalloc(grid tails)");
+		if(nRecs > g0) CU(cudaMemsetAsync(h->dGridTail.as<uint32_t>() + g0, 0, (nRecs - g0)*4, st), "cudaMemsetAsync");
+	}
+	const size_t nCsg = h->csgType.size(), nCsgOrder = h->csgOrder.size();
+	if(h->anyCSG)
+	{
+		CU(h->dGridCsg.reserve(std::max<size_t>(nRecs, 1)*4), "cudaMalloc(CSG nodes of the grids)");
+		CU(cudaMemcpyAsync(h->dGridCsg.p, h->gcsg.data(), nRecs*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(CSG nodes of the grids)");
+		CU(h->dCsgTab.reserve((4*nCsg + nCsgOrder + 1)*4), "cudaMalloc(CSG tree)");
+		int32_t* tab = h->dCsgTab.as<int32_t>();
+		CU(cudaMemcpyAsync(tab, h->csgType.data(), nCsg*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(CSG tree)");
+		CU(cudaMemcpyAsync(tab + nCsg, h->csgParent.data(), nCsg*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(CSG tree)");
+		CU(cudaMemcpyAsync(tab + 2*nCsg, h->csgSlot.data(), nCsg*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(CSG tree)");
+		CU(cudaMemcpyAsync(tab + 3*nCsg, h->csgKids.data(), nCsg*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(CSG tree)");
+		if(nCsgOrder) CU(cudaMemcpyAsync(tab + 4*nCsg, h->csgOrder.data(), nCsgOrder*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(CSG tree)");
+		CU(cudaStreamSynchronize(st), "cudaStreamSynchronize(CSG tree)");
+	}
 	if(nRecs) CU(cudaMemcpyAsync(h->dGrids.p, recs, nRecs*sizeof(GridRec), cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(grid table)");
 	CU(cudaMemcpyAsync(h->dChunk.p, h->chunk.data(), nChunkEntries*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(chunk table)");
 	if(!h->gkeyTimes.empty())
@@ -595,6 +699,22 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 	f.sx0 = L.sx0; f.sy0 = L.sy0; f.sw = L.sw; f.sh = L.sh;
 	f.tileW = h->tileW; f.tileH = h->tileH; f.ntx = h->ntx; f.nty = h->nty; f.nActiveTiles = nActive;
 	f.Praw = dP; f.Ci = dCi; f.Oi = dOi; f.culled = dCulled;
+	f.Ng = dNg; f.Nn = dNn; f.radius = dRadius; f.aov = dAov;
+	f.aovFloats = dAov ? h->aovFloats : 0; f.nch = nch;
+	f.gridTail = anyCullT ? h->dGridTail.as<uint32_t>() : nullptr;
+	f.cullTransparentOk = (anyCullT && !(p.zthreshold[0] == 0.f && p.zthreshold[1] == 0.f && p.zthreshold[2] == 0.f)) ? 1 : 0;
+	f.anyCSG = h->anyCSG ? 1 : 0; f.nCsgNodes = (int)nCsg; f.nCsgOrder = (int)nCsgOrder;
+	f.gridCsg = h->anyCSG ? h->dGridCsg.as<int32_t>() : nullptr;
+	if(h->anyCSG)
+	{
+		const int32_t* tab = h->dCsgTab.as<int32_t>();
+		f.csgType = tab; f.csgParent = tab + nCsg; f.csgSlot = tab + 2*nCsg; f.csgKids = tab + 3*nCsg; f.csgOrder = tab + 4*nCsg;
+	}
+	// the displays may show arbitrary output variables (filtered by later passes) and an imager may still change the
+	// pixels: then the filter only writes the float channel buffer and k_finish exposes / quantises afterwards
+	const bool imager = imagerCb && imagerCb->on_imager && download && !zOnly;
+	f.deferDisplay = (h->aovFloats > 0 || imager) ? 1 : 0;
+	f.deferExpose = imager ? 1 : 0;
 	f.grids = h->dGrids.as<GridRec>(); f.chunkGrid = h->dChunk.as<uint32_t>();
 	f.keyTimes = h->dKeyTimes.as<float>(); f.splitLines = h->dSplit.as<float4>();
 	f.nPos = h->nPos; f.nVerts = h->nVerts; f.nGrids = (int)nGrids;
@@ -608,15 +728,34 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 	f.tileFlags = h->dTileFlags.as<uint32_t>();
 	f.errorFlags = h->dMisc.as<uint32_t>() + 1;
 	f.counters = reinterpret_cast<unsigned long long*>(h->dMisc.as<unsigned char>() + 16);
-	f.planes = h->dPlanes.as<float>(); f.maskPlane = reinterpret_cast<unsigned char*>(h->dPlanes.as<float>() + 7*planeStride);
+	f.planes = h->dPlanes.as<float>(); f.maskPlane = reinterpret_cast<unsigned char*>(h->dPlanes.as<float>() + size_t(7 + h->aovFloats)*planeStride);
 	{ const int mbits = 2*L.shiftX + 2*L.shiftY + 3; f.maskBytes = mbits <= 8 ? 1 : (mbits <= 16 ? 2 : 4); } f.planeStride = (int64_t)planeStride; f.planeW = planeW; f.planeSC = planeSC; f.planeChunks = planeChunks; f.ringRows = ringRows;
 	f.filterMode = p.filter_mode; f.partials = h->dPartials.as<float>(); f.ntaps = ntaps;
 	f.channels = h->dChannels.as<float>();
 	f.occlImage = nullptr; f.zOnly = zOnly ? 1 : 0;
+	f.zKeys = nullptr; f.zKeys2 = nullptr; f.flushedPos = 0;
 	if(zOnly)
 	{
 		CU(h->dOccl.reserve(size_t(L.sw)*L.sh*4), "cudaMalloc(occlusion image)");
 		f.occlImage = h->dOccl.as<float>();
+	}
+	if(incremental)
+	{
+		const size_t nKeys = size_t(L.sw)*L.sh*size_t(p.xsamples*p.ysamples);
+		const bool mid = (p.display_mode & AQH_DMODE_Z) && p.depth_filter == AQH_DEPTHFILTER_MIDPOINT;
+		if(!h->haveZ)
+		{
+			CU(h->dZKeys.reserve(nKeys*8), "cudaMalloc(occlusion keys)");
+			CU(launchFillKeys(h->dZKeys.as<unsigned long long>(), nKeys, st), "k_fill_keys");
+			if(mid)
+			{
+				CU(h->dZKeys2.reserve(nKeys*8), "cudaMalloc(occlusion keys)");
+				CU(launchFillKeys(h->dZKeys2.as<unsigned long long>(), nKeys, st), "k_fill_keys");
+			}
+		}
+		f.zKeys = h->dZKeys.as<unsigned long long>();
+		f.zKeys2 = mid ? h->dZKeys2.as<unsigned long long>() : nullptr;
+		f.flushedPos = zOnly ? 0 : h->flushedPos;
 	}
 	f.rowOwned = (std::max(1, p.world_size) > 1) ? h->dRowOwned.as<uint8_t>() : nullptr;
 
@@ -625,7 +764,7 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 	CU(cudaEventRecord(h->ev[0], st), "cudaEventRecord");
 	CU(cudaMemsetAsync(h->dMisc.p, 0, 256, st), "cudaMemsetAsync");
 	CU(cudaMemsetAsync(h->dBinCount.p, 0, std::max<size_t>(nActive, 1)*4, st), "cudaMemsetAsync");
-	CU(cudaMemsetAsync(h->dChannels.p, 0, size_t(p.xres)*p.yres*9*4, st), "cudaMemsetAsync");
+	CU(cudaMemsetAsync(h->dChannels.p, 0, size_t(p.xres)*p.yres*nch*4, st), "cudaMemsetAsync");
 	for(int d = 0; d < p.n_displays; ++d)
 		CU(cudaMemsetAsync(h->dDisplay[d].p, 0, size_t(p.xres)*p.yres*disp.d[d].entrySize, st), "cudaMemsetAsync");
 	if(pipelined && !plan.empty())
@@ -652,6 +791,14 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 		}
 		CU(launchSplitLines(f, st), "k_splitlines"); S.gpu_launches += 1;
 	}
+	else if(incremental)
+	{
+		// only what arrived since the last flush is projected; a flush also bins only that, the final frame bins every
+		// position again (k_bin skips the opaque micropolygons the stored occlusion keys already contain)
+		CU(launchProject(f, (int64_t)pos0, f.nPos, st), "k_project"); S.gpu_launches += nPos > pos0 ? 1 : 0;
+		CU(launchSplitLines(f, st), "k_splitlines"); S.gpu_launches += nGrids ? 1 : 0;
+		CU(launchBinCount(f, zOnly ? (int64_t)pos0 : 0, f.nPos, st), "k_bin<count>"); S.gpu_launches += 1;
+	}
 	else
 	{
 		CU(launchProjectCount(f, 0, f.nPos, st), "k_project / k_bin<count>"); S.gpu_launches += nPos ? 2 : 0;
@@ -671,7 +818,8 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 	f.binEntries = h->dBinEntries.as<unsigned long long>();
 	// the project kernel reports whether any vertex is non-opaque: only then does the hide kernel
 	// carry deep-list heads in shared memory and a deep hit pool in HBM
-	f.anyTransparent = ((devFlags & 2u) || !f.cullable) ? 1 : 0;
+	if(devFlags & 2u) h->sawTransparent = true;          // k_project only saw what was new in this call
+	f.anyTransparent = (h->sawTransparent || !f.cullable || h->anyCSG) ? 1 : 0;
 	LaunchCfg cfg{};
 	CU(hideKernelConfig(f, h->smCount, cfg), "hide kernel configuration (shared memory / occupancy)");
 	if(f.anyTransparent)
@@ -685,9 +833,9 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 	// bins are sorted front to back in runs of sortRun entries (a power of two covering the longest bin, capped)
 	f.sortRun = 64;
 	while(f.sortRun < (int)maxBin && f.sortRun < 8192) f.sortRun <<= 1;
-	CU(launchBinFill(f, st), "k_bin<fill>"); S.gpu_launches += (nPos ? 1 : 0) + ((nActive && f.anyTransparent) ? 1 : 0) + ((nPos && nActive) ? 1 : 0);
+	CU(launchBinFill(f, (incremental && zOnly) ? (int64_t)pos0 : 0, f.nPos, st), "k_bin<fill>"); S.gpu_launches += (nPos ? 1 : 0) + ((nActive && f.anyTransparent) ? 1 : 0) + ((nPos && nActive) ? 1 : 0);
 	CU(cudaEventRecord(h->ev[1], st), "cudaEventRecord");
-	if(zOnly)
+	if(zOnly && !h->haveZ)
 	{
 		// every pixel of the sample region starts uncovered (FLT_MAX); tiles this rank does not hide stay that way
 		std::vector<float> inf(size_t(L.sw)*L.sh, FLT_MAX);
@@ -749,12 +897,44 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 		const int y0 = p.crop_ymin + std::max(filtNext, 0), y1 = std::min(p.crop_ymin + filtEnd, p.crop_ymax);
 		if(y1 > y0)
 		{
-			CU(launchFilter(f, disp, h->filterTab.data(), y0, y1, !tableUp, st), "k_filter"); S.gpu_launches += 1;
+			CU(launchFilter(f, disp, h->filterTab.data(), y0, y1, !tableUp, st), "k_filter"); S.gpu_launches += filterLaunchCount(f);
 			tableUp = true;
 			bandEvKind.push_back(1);
 			CU(cudaEventRecord(h->bandEv[bandEvKind.size()], st), "cudaEventRecord");
 		}
 		filtNext = std::max(filtNext, filtEnd);
+	}
+	if(f.deferDisplay && !zOnly)
+	{
+		if(imager)
+		{
+			// Imager shading (bucketprocessor.cpp:712-743) happens on the host, bucket by bucket in reference order, between
+			// filtering and exposure: the float channel buffer makes a round trip
+			const size_t chBytesAll = size_t(p.xres)*p.yres*nch*4;
+			if(!h->hChannels.reserve(chBytesAll)) return h->fail(AQH_ERR_NO_MEMORY, "cudaHostAlloc(channel image)");
+			CU(cudaMemcpyAsync(h->hChannels.p, h->dChannels.p, chBytesAll, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(channels)");
+			CU(cudaStreamSynchronize(st), "cudaStreamSynchronize(imager)");
+			S.d2h_bytes += (int64_t)chBytesAll;
+			for(int row = L.by0; row < L.by1; ++row)
+				for(int col = L.bx0; col < L.bx1; ++col)
+				{
+					const int xPos = col*p.bucket_xsize, yPos = row*p.bucket_ysize;
+					const int xSize = std::min(p.bucket_xsize, p.xres - xPos), ySize = std::min(p.bucket_ysize, p.yres - yPos);
+					// the bucket's display region, cropped like CqBucketProcessor::DisplayRegion
+					const int x0 = std::max(xPos, p.crop_xmin), x1 = std::min(xPos + xSize, p.crop_xmax);
+					const int y0 = std::max(yPos, p.crop_ymin), y1 = std::min(yPos + ySize, p.crop_ymax);
+					if(x1 <= x0 || y1 <= y0) continue;
+					bool mine = std::max(1, p.world_size) == 1;
+					for(int y = y0; y < y1 && !mine; ++y) mine = h->rowOwned[y] != 0;
+					if(!mine) continue;
+					float* ch = h->hChannels.as<float>() + (size_t(y0)*p.xres + x0)*nch;
+					if(imagerCb->on_imager(imagerCb->user, x0, x1, y0, y1, ch, p.xres*nch, nch))
+						return h->fail(AQH_ERR_CALLBACK, "on_imager callback failed");
+				}
+			CU(cudaMemcpyAsync(h->dChannels.p, h->hChannels.p, chBytesAll, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(channels)");
+			S.h2d_bytes += (int64_t)chBytesAll;
+		}
+		CU(launchFinish(f, disp, f.deferExpose, st), "k_finish"); S.gpu_launches += 1;
 	}
 	CU(cudaEventRecord(h->ev[3], st), "cudaEventRecord");
 
@@ -778,7 +958,7 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 	{
 		// Only the pixel rows this rank owns travel back (all of them on a single rank); the rest of the host
 		// images stays zero, like the device images.
-		const size_t chRow = size_t(p.xres)*9*4, chBytes = chRow*p.yres;
+		const size_t chRow = size_t(p.xres)*nch*4, chBytes = chRow*p.yres;
 		const bool sharded = std::max(1, p.world_size) > 1 && !gathered;
 		const bool firstCh = h->hChannels.cap < chBytes;
 		if(!h->hChannels.reserve(chBytes)) return h->fail(AQH_ERR_NO_MEMORY, "cudaHostAlloc(channel image)");
@@ -817,7 +997,19 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 	S.download_ms = download ? nowMs() - tDown0 : 0.0;
 	tr.mark("frame sync");
 	h->haveHostImage = download;
-	if(zOnly) h->haveOccl = true;
+	if(zOnly)
+	{
+		h->haveOccl = true;
+		// what this flush hid is in the occlusion keys now; later grids open a new staged run
+		h->haveZ = true; h->flushedPos = h->nPos; h->nFlushes += 1;
+		h->upPos = h->nPos; h->upVerts = h->nVerts; h->upGrids = nGrids; h->upSegs = h->segments.size();
+		if(!h->segments.empty()) h->segments.back().closed = true;
+	}
+	else if(incremental)
+	{
+		h->upPos = h->nPos; h->upVerts = h->nVerts; h->upGrids = nGrids; h->upSegs = h->segments.size();
+		if(!h->segments.empty()) h->segments.back().closed = true;
+	}
 	float ms = 0;
 	cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); S.project_bust_ms = ms;
 	S.render_mpgs_ms = 0; S.filter_ms = 0; S.display_ms = 0;
@@ -836,7 +1028,8 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 		const DevBuf* all[] = {&h->dPraw, &h->dCi, &h->dOi, &h->dCulled, &h->dP4, &h->dCO, &h->dGrids, &h->dChunk, &h->dKeyTimes, &h->dSplit,
 		                       &h->dPosTab, &h->dVal1d, &h->dShuf, &h->dPat, &h->dFilt, &h->dDofB, &h->dDither, &h->dTileSlot, &h->dActive,
 		                       &h->dBinCount, &h->dBinOffset, &h->dBinEntries, &h->dMisc, &h->dTileFlags, &h->dPlanes, &h->dPartials,
-		                       &h->dDeepA, &h->dDeepUV, &h->dChannels, &h->dRowOwned, &h->dOccl, &h->dBandCursor};
+		                       &h->dDeepA, &h->dDeepUV, &h->dChannels, &h->dRowOwned, &h->dOccl, &h->dBandCursor,
+		                       &h->dAov, &h->dNg, &h->dNn, &h->dRadius, &h->dGridTail, &h->dGridCsg, &h->dCsgTab, &h->dZKeys, &h->dZKeys2};
 		S.device_bytes = 0;
 		for(const DevBuf* b : all) S.device_bytes += (int64_t)b->cap;
 		for(int d = 0; d < AQH_MAX_DISPLAYS; ++d) S.device_bytes += (int64_t)h->dDisplay[d].cap;
@@ -845,6 +1038,8 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false)
 	tr.mark("stats");
 	if(misc.err & 1u)
 		return h->fail(AQH_ERR_DEEP_OVERFLOW, "transparent hit pool exhausted: raise AqhFrameParams::deep_hits_per_sample");
+	if(misc.err & 8u)
+		return h->fail(AQH_ERR_DEEP_OVERFLOW, "a sample of a CSG frame holds more than 48 hits");
 	return AQH_OK;
 }
 
@@ -886,7 +1081,8 @@ int aqh_destroy(AqhHider* h)
 	DevBuf* bufs[] = {&h->dPraw, &h->dCi, &h->dOi, &h->dCulled, &h->dP4, &h->dCO, &h->dGrids, &h->dChunk, &h->dKeyTimes, &h->dSplit,
 	                  &h->dPosTab, &h->dVal1d, &h->dShuf, &h->dPat, &h->dFilt, &h->dDofB, &h->dDither, &h->dTileSlot, &h->dActive,
 	                  &h->dBinCount, &h->dBinOffset, &h->dBinEntries, &h->dMisc, &h->dTileFlags, &h->dPlanes, &h->dMask, &h->dPartials,
-	                  &h->dDeepA, &h->dDeepUV, &h->dChannels, &h->dRowOwned};
+	                  &h->dDeepA, &h->dDeepUV, &h->dChannels, &h->dRowOwned, &h->dBandCursor,
+	                  &h->dAov, &h->dNg, &h->dNn, &h->dRadius, &h->dGridTail, &h->dGridCsg, &h->dCsgTab, &h->dZKeys, &h->dZKeys2};
 	for(DevBuf* b : bufs) b->release();
 	for(int d = 0; d < AQH_MAX_DISPLAYS; ++d) { h->dDisplay[d].release(); h->hDisplay[d].release(); }
 	h->dOccl.release(); h->hOccl.release(); h->recs.release(); h->chunk.release();
@@ -990,6 +1186,11 @@ int aqh_begin_frame(AqhHider* h, const AqhFrameParams* p)
 	if(rc) return rc;
 	h->stats.prepare_ms = nowMs() - t0;
 	resetFrameGrids(h);
+	h->aovFloats = 0;
+	for(int a = 0; a < h->params.n_aovs; ++a) h->aovFloats += h->params.aov[a].n_floats;
+	h->nChannels = AQH_NUM_CHANNELS + h->aovFloats;
+	if(h->aovFloats && h->params.filter_mode != AQH_FILTER_REFERENCE_ORDER)
+		return h->fail(AQH_ERR_UNSUPPORTED, "arbitrary output variables need the reference-order filter mode");
 	h->inFrame = true; h->rendered = false; h->haveHostImage = false; h->haveOccl = false;
 	return AQH_OK;
 }
@@ -1000,7 +1201,7 @@ int aqh_add_grid(AqhHider* h, const AqhGridDesc* g)
 	if(!h->inFrame) return h->fail(AQH_ERR_STATE, "aqh_add_grid outside aqh_begin_frame/aqh_end_frame");
 	if(!g->P) return h->fail(AQH_ERR_BAD_PARAMS, "grid without P");
 	// every check and every allocation comes before the first change of state
-	int rc = checkGrid(h, g->cu, g->cv, g->nkeys, g->flags, g->key_times);
+	int rc = checkGrid(h, g->cu, g->cv, g->nkeys, g->flags, g->key_times, g->csg_node, g->radius, g->Ng);
 	if(rc) return rc;
 	for(int k = 0; k < g->nkeys; ++k)
 		if(!g->P[k]) return h->fail(AQH_ERR_BAD_PARAMS, "grid key without P");
@@ -1013,8 +1214,17 @@ int aqh_add_grid(AqhHider* h, const AqhGridDesc* g)
 		return h->fail(AQH_ERR_NO_MEMORY, "cudaHostAlloc(grid staging)");
 	{
 		const GridTablesMark mark = markGridTables(h);
-		rc = appendGridTables(h, g->cu, g->cv, g->nkeys, g->flags, g->lod_bounds, g->key_times);
+		rc = appendGridTables(h, g->cu, g->cv, g->nkeys, g->flags, g->lod_bounds, g->key_times, g->csg_node);
 		if(rc) { rollbackGridTables(h, mark); return rc; }
+	}
+	// the rarely used arrays go to frame-global host copies indexed by the grid's vertex / position offsets
+	{
+		const size_t v0 = (size_t)h->nVerts, p0 = (size_t)h->nPos;
+		const size_t A = (size_t)h->aovFloats;
+		if(g->aov && A) { h->hxAov.resize((v0 + nv)*A, 0.f); std::memcpy(&h->hxAov[v0*A], g->aov, nv*A*4); h->anyAov = true; }
+		if(g->Ng) { h->hxNg.resize((v0 + nv)*3, 0.f); std::memcpy(&h->hxNg[v0*3], g->Ng, nv*12); h->anyNg = true; }
+		if(g->N) { h->hxN.resize((v0 + nv)*3, 0.f); std::memcpy(&h->hxN[v0*3], g->N, nv*12); h->anyN = true; }
+		if(g->radius && (g->flags & AQH_GRID_POINTS)) { h->hxRadius.resize(p0 + np, 0.f); std::memcpy(&h->hxRadius[p0], g->radius, np*4); h->anyRadius = true; }
 	}
 	for(int k = 0; k < g->nkeys; ++k)
 		std::memcpy(h->stP.as<float>() + (h->stPUsed + size_t(k)*nv)*3, g->P[k], nv*12);
@@ -1025,7 +1235,7 @@ int aqh_add_grid(AqhHider* h, const AqhGridDesc* g)
 	uint8_t* cu8 = h->stCulled.as<uint8_t>() + h->stVUsed;
 	if(g->culled) std::memcpy(cu8, g->culled, nv); else std::memset(cu8, 0, nv);
 	// extend the trailing staged segment or open a new one
-	if(h->segments.empty() || !h->segments.back().staged)
+	if(h->segments.empty() || !h->segments.back().staged || h->segments.back().closed)
 	{
 		Segment s;
 		s.firstGrid = (int64_t)h->gcu.size() - 1;
@@ -1057,13 +1267,15 @@ int aqh_add_grid_block(AqhHider* h, const AqhGridBlock* b)
 	s.firstGrid = (int64_t)h->gcu.size();
 	s.nGrids = b->n_grids;
 	s.P = b->P; s.Ci = b->Ci; s.Oi = b->Oi; s.culled = b->culled;
+	s.aov = h->aovFloats ? b->aov : nullptr; s.Ng = b->Ng; s.N = b->N; s.radius = b->radius;
 	s.memorySpace = b->memory_space;
 	size_t ko = 0;
 	// a block is accepted or rejected as a whole: all of its grids are checked before the first one is appended
 	for(int64_t g = 0; g < b->n_grids; ++g)
 	{
 		const int nk = b->nkeys ? b->nkeys[g] : 1;
-		int rc = checkGrid(h, b->cu[g], b->cv[g], nk, b->flags[g], (b->key_times && nk > 1) ? b->key_times + ko : nullptr);
+		int rc = checkGrid(h, b->cu[g], b->cv[g], nk, b->flags[g], (b->key_times && nk > 1) ? b->key_times + ko : nullptr,
+		                   b->csg_node ? b->csg_node[g] : -1, b->radius, b->Ng);
 		if(rc) return rc;
 		ko += nk;
 	}
@@ -1073,7 +1285,7 @@ int aqh_add_grid_block(AqhHider* h, const AqhGridBlock* b)
 	{
 		const int nk = b->nkeys ? b->nkeys[g] : 1;
 		int rc = appendGridTables(h, b->cu[g], b->cv[g], nk, b->flags[g], b->lod_bounds ? b->lod_bounds + 2*g : nullptr,
-		                          (b->key_times && nk > 1) ? b->key_times + ko : nullptr);
+		                          (b->key_times && nk > 1) ? b->key_times + ko : nullptr, b->csg_node ? b->csg_node[g] : -1);
 		if(rc) { rollbackGridTables(h, mark); return rc; }
 		ko += nk;
 		const int64_t nv = int64_t(b->cu[g]+1)*(b->cv[g]+1);
@@ -1085,6 +1297,10 @@ int aqh_add_grid_block(AqhHider* h, const AqhGridBlock* b)
 	if(b->Ci) h->anyCi = true;
 	if(b->Oi) h->anyOi = true;
 	if(b->culled) h->anyCulled = true;
+	if(s.aov) h->anyAov = true;
+	if(b->Ng) h->anyNg = true;
+	if(b->N) h->anyN = true;
+	if(b->radius) h->anyRadius = true;
 	return AQH_OK;
 }
 
@@ -1137,7 +1353,7 @@ int aqh_end_frame(AqhHider* h, const AqhCallbacks* cb)
 	FrameTrace tr;
 	if(cudaSetDevice(h->device) != cudaSuccess) return h->fail(AQH_ERR_NO_DEVICE, "cudaSetDevice failed");
 	tr.mark("end_frame: set device");
-	int rc = renderFrame(h, true);
+	int rc = renderFrame(h, true, false, cb);
 	tr.mark("end_frame: rendered");
 	h->inFrame = false;
 	if(rc) return rc;
@@ -1156,14 +1372,24 @@ int aqh_end_frame(AqhHider* h, const AqhCallbacks* cb)
 			const int xSize = std::min(p.bucket_xsize, p.xres - xPos), ySize = std::min(p.bucket_ysize, p.yres - yPos);
 			if(cb->on_bucket)
 			{
-				const float* ch = h->hChannels.as<float>() + (size_t(yPos)*p.xres + xPos)*9;
-				if(cb->on_bucket(cb->user, xPos, xPos + xSize, yPos, yPos + ySize, ch, p.xres*9, 9))
+				const float* ch = h->hChannels.as<float>() + (size_t(yPos)*p.xres + xPos)*h->nChannels;
+				if(cb->on_bucket(cb->user, xPos, xPos + xSize, yPos, yPos + ySize, ch, p.xres*h->nChannels, h->nChannels))
 					return h->fail(AQH_ERR_CALLBACK, "on_bucket callback failed");
 			}
 			if(cb->on_data)
 				for(int d = 0; d < p.n_displays; ++d)
 				{
 					const int es = h->dispEntry[d];
+					if(p.display[d].flags & AQH_DISPLAY_SCANLINE_ORDER)
+					{
+						// PkDspyFlagsWantsScanLineOrder: CollapseBucketsToScanlines gathers the buckets of a row; once the bucket
+						// at the right edge arrives SendToDisplay delivers the rows one at a time (ddmanager.cpp:1129-1175)
+						if(xPos + xSize < p.xres) continue;
+						for(int y = yPos; y < yPos + ySize; ++y)
+							if(cb->on_data(cb->user, d, 0, p.xres, y, y + 1, es, h->hDisplay[d].as<unsigned char>() + size_t(y)*p.xres*es))
+								return h->fail(AQH_ERR_CALLBACK, "on_data callback failed");
+						continue;
+					}
 					bucketData.resize(size_t(xSize)*ySize*es);
 					for(int y = 0; y < ySize; ++y)
 						std::memcpy(&bucketData[size_t(y)*xSize*es],
@@ -1181,8 +1407,51 @@ int aqh_end_frame(AqhHider* h, const AqhCallbacks* cb)
 int aqh_set_csg_tree(AqhHider* h, int n_nodes, const int32_t* type, const int32_t* parent)
 {
 	if(!h) return AQH_ERR_BAD_PARAMS;
-	(void)n_nodes; (void)type; (void)parent;
-	return h->fail(AQH_ERR_UNSUPPORTED, "CSG trees are not supported");
+	if(!h->inFrame) return h->fail(AQH_ERR_STATE, "aqh_set_csg_tree outside aqh_begin_frame/aqh_end_frame");
+	if(h->anyCSG) return h->fail(AQH_ERR_STATE, "the CSG tree must be set before the first CSG grid");
+	if(n_nodes < 0 || (n_nodes > 0 && (!type || !parent)) || n_nodes > 65536) return h->fail(AQH_ERR_BAD_PARAMS, "CSG tree");
+	std::vector<int32_t> ty(type, type + n_nodes), pa(parent, parent + n_nodes), slot(n_nodes, -1), kids(n_nodes, 0), order;
+	for(int i = 0; i < n_nodes; ++i)
+	{
+		if(ty[i] < AQH_CSG_PRIMITIVE || ty[i] > AQH_CSG_DIFFERENCE || pa[i] >= n_nodes || pa[i] == i || pa[i] < -1)
+			return h->fail(AQH_ERR_BAD_PARAMS, "CSG tree: node type or parent out of range");
+		if(pa[i] >= 0)
+		{
+			if(ty[pa[i]] == AQH_CSG_PRIMITIVE) return h->fail(AQH_ERR_BAD_PARAMS, "CSG tree: a primitive cannot have children");
+			slot[i] = kids[pa[i]]++;                   // children are ordered by node index (creation order)
+			if(kids[pa[i]] > 32) return h->fail(AQH_ERR_UNSUPPORTED, "CSG tree: more than 32 children of one node");
+		}
+	}
+	// children-before-parents order of the non-primitive nodes: the order CqCSGTreeNode::ProcessSampleList recurses in
+	// (depth first, children in order, the node itself last); also rejects cycles
+	std::vector<std::vector<int32_t> > children(n_nodes);
+	for(int i = 0; i < n_nodes; ++i) if(pa[i] >= 0) children[pa[i]].push_back(i);
+	std::vector<char> seen(n_nodes, 0);
+	for(int root = 0; root < n_nodes; ++root)
+	{
+		if(pa[root] >= 0) continue;
+		std::vector<std::pair<int32_t, size_t> > stack;
+		stack.push_back(std::make_pair((int32_t)root, size_t(0)));
+		seen[root] = 1;
+		while(!stack.empty())
+		{
+			const int32_t n = stack.back().first;
+			if(stack.back().second < children[n].size())
+			{
+				const int32_t c = children[n][stack.back().second++];
+				seen[c] = 1;
+				if(ty[c] != AQH_CSG_PRIMITIVE) stack.push_back(std::make_pair(c, size_t(0)));
+			}
+			else
+			{
+				if(ty[n] != AQH_CSG_PRIMITIVE) order.push_back(n);
+				stack.pop_back();
+			}
+		}
+	}
+	for(int i = 0; i < n_nodes; ++i) if(!seen[i]) return h->fail(AQH_ERR_BAD_PARAMS, "CSG tree: cycle");
+	h->csgType.swap(ty); h->csgParent.swap(pa); h->csgSlot.swap(slot); h->csgKids.swap(kids); h->csgOrder.swap(order);
+	return AQH_OK;
 }
 
 int aqh_clear_caches(AqhHider* h)
@@ -1259,7 +1528,7 @@ int aqh_device_channels(const AqhHider* h, void** dev_ptr, size_t* bytes)
 	if(!h || !dev_ptr) return AQH_ERR_BAD_PARAMS;
 	if(!h->rendered) return AQH_ERR_STATE;
 	*dev_ptr = h->dChannels.p;
-	if(bytes) *bytes = size_t(h->params.xres)*h->params.yres*9*4;
+	if(bytes) *bytes = size_t(h->params.xres)*h->params.yres*size_t(h->nChannels)*4;
 	return AQH_OK;
 }
 

@@ -26,7 +26,7 @@ enum : uint32_t
 {
 	VINFO_GRID_MASK  = 0x0fffffffu,
 	VINFO_OPAQUE     = 1u << 28,   // Oi >= 1 in all channels at this vertex (or no Oi)
-	VINFO_MP_VALID   = 1u << 29    // a micropolygon starts at this vertex (iu<cu, iv<cv, not culled)
+	VINFO_MP_VALID   = 1u << 29    // a micropolygon starts at this vertex (iu<cu, iv<cv, not culled; every vertex of a points grid)
 };
 
 // Everything the kernels need about the frame; passed by value (<= 4 KB of kernel params).
@@ -59,6 +59,25 @@ struct DevFrame
 	const float* Ci;               // n_verts*3 or null
 	const float* Oi;               // n_verts*3 or null
 	const uint8_t* culled;         // n_verts or null
+	const float* Ng;               // n_verts*3 camera-space geometric normals (AQH_GRID_CULL_BACKFACING) or null
+	const float* Nn;               // n_verts*3 user normals that decide the facing of Ng, or null
+	const float* radius;           // n_pos raster radii (AQH_GRID_POINTS) or null
+	const float* aov;              // n_verts*aovFloats arbitrary output variables, vertex-major, or null
+	int aovFloats, nch;            // floats per pixel of the channel buffer: 9 + aovFloats
+	uint32_t* gridTail;            // per grid: 1 + the last vertex whose Oi is not black (AQH_GRID_CULL_TRANSPARENT), 0 = none
+	// CSG (aqh_set_csg_tree): per grid its primitive node; per node type, parent, slot among the parent's children and
+	// child count; csgOrder lists the non-primitive nodes children-before-parents (the order ProcessSampleList recurses in)
+	int anyCSG, nCsgNodes, nCsgOrder;
+	const int32_t* gridCsg;        // nGrids or null
+	const int32_t* csgType; const int32_t* csgParent; const int32_t* csgSlot; const int32_t* csgKids; const int32_t* csgOrder;
+	int cullTransparentOk;         // limits:zthreshold is not black (micropolygon.cpp:496)
+	// incremental flushes: per-sample occlusion keys kept in HBM between aqh_flush calls ([row][pixel][sample] of the sample
+	// region; null when the frame was never flushed).  A flush hides only the opaque micropolygons at positions >= binFrom
+	// against them and writes them back; the final frame starts from them and skips the opaque micropolygons below flushedPos.
+	unsigned long long* zKeys; unsigned long long* zKeys2;
+	int64_t flushedPos;
+	int deferDisplay;              // the filter only writes the float channel buffer; k_finish exposes (deferExpose) and quantises
+	int deferExpose;
 	const GridRec* grids;
 	const uint32_t* chunkGrid;     // grid index of the first position of each 256-position chunk (+1 sentinel)
 	const float* keyTimes;         // per grid nkeys floats at key offset
@@ -144,9 +163,14 @@ struct LaunchCfg
 cudaError_t launchProjectCount(const DevFrame& f, int64_t pA, int64_t pB, cudaStream_t st);
 cudaError_t launchSplitLines(const DevFrame& f, cudaStream_t st);
 cudaError_t launchBinScan(const DevFrame& f, cudaStream_t st);
-cudaError_t launchBinFill(const DevFrame& f, cudaStream_t st);
+cudaError_t launchBinFill(const DevFrame& f, int64_t pA, int64_t pB, cudaStream_t st);
+cudaError_t launchBinCount(const DevFrame& f, int64_t pA, int64_t pB, cudaStream_t st);
+cudaError_t launchProject(const DevFrame& f, int64_t pA, int64_t pB, cudaStream_t st);
+cudaError_t launchFillKeys(unsigned long long* keys, size_t n, cudaStream_t st);      // every sample "empty" (occlZ = FLT_MAX, no hit)
 cudaError_t launchHide(const DevFrame& f, const LaunchCfg& cfg, uint32_t slotBeg, uint32_t slotEnd, uint32_t* cursor, cudaStream_t st);
 cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, const float* hostFilterTab, int yBeg, int yEnd, bool uploadTable, cudaStream_t st);
+cudaError_t launchFinish(const DevFrame& f, const DevDisplays& disp, int expose, cudaStream_t st);   // expose and/or quantise the channel buffer
+int filterLaunchCount(const DevFrame& f);     // kernel launches of one launchFilter call
 cudaError_t hideKernelConfig(const DevFrame& f, int smCount, LaunchCfg& cfg);
 int kernelsArchOk();   // 1 when the loaded kernel image can run on the current device
 

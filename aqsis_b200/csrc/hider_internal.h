@@ -29,6 +29,22 @@ struct DevBuf
 		if(e == cudaSuccess) cap = want;
 		return e;
 	}
+	// grow, keeping the first `keep` bytes (device-to-device copy on `st`; the old block is freed after the copy is queued:
+	// cudaFree synchronises)
+	cudaError_t reserveKeep(size_t bytes, size_t keep, cudaStream_t st)
+	{
+		if(bytes <= cap) return cudaSuccess;
+		void* q = nullptr;
+		size_t want = bytes + bytes/4 + 256;
+		cudaError_t e = cudaMalloc(&q, want);
+		if(e != cudaSuccess) { want = bytes; e = cudaMalloc(&q, want); }
+		if(e != cudaSuccess) return e;
+		if(p && keep) e = cudaMemcpyAsync(q, p, keep < cap ? keep : cap, cudaMemcpyDeviceToDevice, st);
+		if(e == cudaSuccess && p) { cudaStreamSynchronize(st); cudaFree(p); }
+		if(e != cudaSuccess) { cudaFree(q); return e; }
+		p = q; cap = want;
+		return cudaSuccess;
+	}
 	void release() { if(p) cudaFree(p); p = nullptr; cap = 0; }
 	template<class T> T* as() const { return static_cast<T*>(p); }
 };
@@ -72,8 +88,11 @@ struct Segment
 {
 	int64_t firstGrid = 0, nGrids = 0, nVerts = 0, nPos = 0;
 	const float* P = nullptr; const float* Ci = nullptr; const float* Oi = nullptr; const uint8_t* culled = nullptr;
+	// rarely used per-vertex / per-position arrays (block route: the caller's pointers; staged route: null, see AqhHider::hx*)
+	const float* aov = nullptr; const float* Ng = nullptr; const float* N = nullptr; const float* radius = nullptr;
 	int memorySpace = 0;     // 0 host, 1 device
 	bool staged = false;     // lives in the hider's own pinned staging (pointers are offsets to fix up)
+	bool closed = false;     // a flush consumed it: aqh_add_grid opens a new staged run
 };
 
 } // namespace aqh
@@ -102,6 +121,15 @@ struct AqhHider
 	std::vector<int32_t> gcu, gcv, gnkeys;
 	std::vector<uint32_t> gflags;
 	std::vector<float> glod, gkeyTimes;
+	std::vector<int32_t> gcsg;                      // per grid: its primitive node in the CSG tree or -1
+	// CSG tree of the frame (aqh_set_csg_tree): type, parent, slot among the parent's children, child count per node,
+	// and the non-primitive nodes children-before-parents
+	std::vector<int32_t> csgType, csgParent, csgSlot, csgKids, csgOrder;
+	// rarely used arrays of grids handed over one by one (aqh_add_grid): frame-global host copies, indexed like the
+	// device arrays (vertex / position offsets), grown on first use
+	std::vector<float> hxAov, hxNg, hxN, hxRadius;
+	bool anyAov = false, anyNg = false, anyN = false, anyRadius = false, anyCSG = false, anyPoints = false;
+	int aovFloats = 0;
 	std::vector<Segment> segments;
 	// device-side grid table and the 256-position chunk index, built as the grids are submitted
 	PinnedVec<GridRec> recs;
@@ -120,6 +148,15 @@ struct AqhHider
 	DevBuf dPlanes, dMask, dPartials, dDeepA, dDeepUV, dChannels, dRowOwned;
 	DevBuf dDisplay[AQH_MAX_DISPLAYS];
 	DevBuf dOccl, dBandCursor;
+	DevBuf dAov, dNg, dNn, dRadius, dGridTail, dGridCsg, dCsgTab;
+	// incremental flushes (aqh_flush): what is already on the device and projected, and the per-sample occlusion keys kept
+	// in HBM between flushes -- (depth key << 32 | position of the winning opaque hit) per sample of the sample region,
+	// [row][pixel][sample]; zKeys2: the nearest hit when the midpoint depth filter keeps the second nearest depth as occlZ
+	DevBuf dZKeys, dZKeys2;
+	int64_t upPos = 0, upVerts = 0, upGrids = 0, flushedPos = 0;
+	size_t upSegs = 0;
+	bool haveZ = false, sawTransparent = false;
+	int64_t flushBinEntries = 0, nFlushes = 0;
 	std::vector<cudaEvent_t> bandEv;    // one event after every hide / filter launch of a frame
 	PinnedBuf hOccl;
 	bool haveOccl = false;

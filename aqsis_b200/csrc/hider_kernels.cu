@@ -78,6 +78,25 @@ __device__ __forceinline__ float minCoCForBound(const DevFrame& f, float z1, flo
 
 __device__ __forceinline__ uint32_t infoOf(const float4& v) { return __float_as_uint(v.w); }
 
+// Does the micropolygon at position p use the sample's occluding slot?  isOpaque (all shading corners Oi >= 1: four
+// with smooth shading, the first otherwise -- points are always constant, micropolygon.cpp:1482,1518-1521) or MatteAlpha,
+// and cullable: not part of a CSG solid and the frame keeps no full hit lists for the depth filter
+// (bucketprocessor.cpp:1074-1079, 1490-1491).
+__device__ __forceinline__ bool mpCullable(const DevFrame& f, const GridRec& g)
+{
+	return f.cullable && !(g.flags & AQH_GRID_USES_CSG);
+}
+__device__ __forceinline__ bool mpOpaqueSlot(const DevFrame& f, const GridRec& g, uint32_t p, uint32_t info)
+{
+	bool opaque = (info & VINFO_OPAQUE) != 0;
+	if((g.flags & AQH_GRID_SMOOTH) && !(g.flags & AQH_GRID_POINTS))
+	{
+		const uint32_t cu = g.cu_cv & 0xffffu;
+		opaque = opaque && (infoOf(f.P4[p+1]) & VINFO_OPAQUE) && (infoOf(f.P4[p+cu+1]) & VINFO_OPAQUE) && (infoOf(f.P4[p+cu+2]) & VINFO_OPAQUE);
+	}
+	return (opaque || (g.flags & AQH_GRID_MATTE_ALPHA)) && mpCullable(f, g);
+}
+
 // ------------------------------------------------------------------------------------
 // k_project: one thread per position.
 __global__ void __launch_bounds__(256) k_project(DevFrame f, int64_t pA, int64_t pB)
@@ -123,7 +142,27 @@ __global__ void __launch_bounds__(256) k_project(DevFrame f, int64_t pA, int64_t
 		f.CO[2*(size_t)vid] = make_float4(ci0, ci1, ci2, oi0);
 		f.CO[2*(size_t)vid+1] = make_float4(oi1, oi2, 0.f, 0.f);
 		const bool opaque = (oi0 >= 1.0f) && (oi1 >= 1.0f) && (oi2 >= 1.0f);
-		bool valid = (iu < cu) && (iv < cv) && !(f.culled && f.culled[vid]);
+		// every vertex of a points grid is a micropolygon and CqMicroPolyGridPoints::Split ignores the culled flags
+		bool valid = (g.flags & AQH_GRID_POINTS) ? true : ((iu < cu) && (iv < cv) && !(f.culled && f.culled[vid]));
+		if((g.flags & AQH_GRID_CULL_BACKFACING) && f.Ng && !(g.flags & (AQH_GRID_USES_CSG | AQH_GRID_POINTS)))
+		{
+			// Sides 1 (micropolygon.cpp:431-474): ((s * Ng) . P) >= 0 with P in camera space; s turns Ng to the side of a user normal
+			const float px_ = f.Praw[3*i], py_ = f.Praw[3*i+1], pz_ = f.Praw[3*i+2];
+			const float gx = f.Ng[3*(size_t)vid], gy = f.Ng[3*(size_t)vid+1], gz = f.Ng[3*(size_t)vid+2];
+			float sgn = 1.0f;
+			if(f.Nn)
+			{
+				const float nx = f.Nn[3*(size_t)vid], ny = f.Nn[3*(size_t)vid+1], nz = f.Nn[3*(size_t)vid+2];
+				sgn = ((nx*gx + ny*gy + nz*gz) < 0.0f) ? -1.0f : 1.0f;
+			}
+			if((((sgn*gx)*px_) + ((sgn*gy)*py_) + ((sgn*gz)*pz_)) >= 0.f) valid = false;
+		}
+		if((g.flags & AQH_GRID_CULL_TRANSPARENT) && f.Oi && f.cullTransparentOk && !(g.flags & AQH_GRID_POINTS))
+		{
+			// fully transparent micropolygons are dropped from the last shading point down to the first one that is not
+			// black (micropolygon.cpp:493-522): remember the last non-black vertex, k_bin drops what lies behind it
+			if(!(oi0 == 0.f && oi1 == 0.f && oi2 == 0.f)) atomicMax(&f.gridTail[lo], v + 1u);
+		}
 		if(opaque) info |= VINFO_OPAQUE;
 		if(valid) info |= VINFO_MP_VALID;
 		// frame-level "there is transparency" flag: read before the atomic so that only the first
@@ -166,14 +205,30 @@ __device__ __forceinline__ bool mpTileRange(const DevFrame& f, int64_t p, const 
 	if(!(info & VINFO_MP_VALID)) return false;
 	const GridRec g = f.grids[info & VINFO_GRID_MASK];
 	if((uint64_t)(p - g.pbase) >= g.nverts) return false;            // only key 0 starts micropolygons
+	// incremental flushes: a flush (z only) hides just the micropolygons that can occlude; the final frame has the
+	// opaque ones of flushed grids in the stored occlusion keys already
+	if(f.zOnly && f.zKeys) { if(!mpOpaqueSlot(f, g, (uint32_t)p, info)) return false; }
+	else if(p < f.flushedPos) { if(mpOpaqueSlot(f, g, (uint32_t)p, info)) return false; }
 	const uint32_t cu = g.cu_cv & 0xffffu;
 	const uint32_t nkeys = g.nkeys_koff & 0xffu;
-	B2 B = boundOf4(a, f.P4[p+1], f.P4[p+cu+1], f.P4[p+cu+2]);
-	for(uint32_t k = 1; k < nkeys; ++k)
+	if((g.flags & AQH_GRID_CULL_TRANSPARENT) && f.Oi && f.cullTransparentOk && !(g.flags & AQH_GRID_POINTS))
+		if((uint32_t)(p - g.pbase) >= f.gridTail[info & VINFO_GRID_MASK]) return false;      // the trailing run of Oi == 0 vertices
+	B2 B;
+	if(g.flags & AQH_GRID_POINTS)
 	{
-		const float4* Pk = f.P4 + p + (size_t)k*g.nverts;
-		B2 kb = boundOf4(Pk[0], Pk[1], Pk[cu+1], Pk[cu+2]);
-		encapsulate(B, kb);
+		// CqMicroPolygonPoints::Initialise, geometry/points.h:350-359: position +- radius, flat in z
+		const float r = f.radius[p];
+		B.mnx = a.x - r; B.mny = a.y - r; B.mnz = a.z - 0.f; B.mxx = a.x + r; B.mxy = a.y + r; B.mxz = a.z + 0.f;
+	}
+	else
+	{
+		B = boundOf4(a, f.P4[p+1], f.P4[p+cu+1], f.P4[p+cu+2]);
+		for(uint32_t k = 1; k < nkeys; ++k)
+		{
+			const float4* Pk = f.P4 + p + (size_t)k*g.nverts;
+			B2 kb = boundOf4(Pk[0], Pk[1], Pk[cu+1], Pk[cu+2]);
+			encapsulate(B, kb);
+		}
 	}
 	zminKey = depthKey(B.mnz);
 	if(f.useDof)
@@ -491,7 +546,7 @@ __device__ __forceinline__ void shadeHit(const DevFrame& f, const GridRec& g, ui
 {
 	const uint32_t cu = g.cu_cv & 0xffffu;
 	const size_t v0 = (size_t)g.vbase + (p - g.pbase);
-	if(g.flags & AQH_GRID_SMOOTH)
+	if((g.flags & AQH_GRID_SMOOTH) && !(g.flags & AQH_GRID_POINTS))
 	{
 		const float4 a0 = f.CO[2*v0], a1 = f.CO[2*v0+1];
 		const float4 b0 = f.CO[2*(v0+1)], b1 = f.CO[2*(v0+1)+1];
@@ -537,7 +592,7 @@ struct StaticRec   // 36 words
 	uint32_t flags;     // grid id | REC_*
 	uint32_t rect;      // gx0 | gx1<<8 | gy0<<16 | gy1<<24  (tile sub-sample coordinates, <= 255)
 };
-enum : uint32_t { REC_LINEAR = 1u << 28, REC_RARE = 1u << 29 /* lod or triangular */ };
+enum : uint32_t { REC_LINEAR = 1u << 28, REC_RARE = 1u << 29 /* lod or triangular */, REC_POINT = 1u << 30 /* a disc: centre Ax,Ay radius Ex */ };
 
 struct TileCtx
 {
@@ -641,10 +696,10 @@ struct DeepCtx
 };
 template<bool AGG>
 __device__ __forceinline__ void storeDeep(const DevFrame& f, const DeepCtx& dc, const HideSmem& s, int idx,
-                                          float D, uint32_t p, float2 uv)
+                                          float D, uint32_t p, float2 uv, bool cullable = true)
 {
 	const uint32_t occl = (uint32_t)(s.keys[idx] >> 32);
-	if(!(depthKey(D) < occl)) return;                 // isCullable && occlZ <= D
+	if(cullable && !(depthKey(D) < occl)) return;     // isCullable && occlZ <= D
 	uint32_t slot;
 	if(AGG)
 	{
@@ -725,15 +780,24 @@ __device__ void setupStaticRec(const DevFrame& f, const TileCtx& t, const HideSm
 	const uint32_t gi = info & VINFO_GRID_MASK;
 	const GridRec g = f.grids[gi];
 	const uint32_t cu = g.cu_cv & 0xffffu;
+	const bool isPoint = (g.flags & AQH_GRID_POINTS) != 0;
+	if(mpOpaqueSlot(f, g, p, info) != wantOpaque) return;
+	const bool cullableMP = mpCullable(f, g);
 	float4 P[4];
-	P[0] = a; P[1] = f.P4[p+1]; P[2] = f.P4[p+cu+1]; P[3] = f.P4[p+cu+2];
-	bool opaque = (info & VINFO_OPAQUE) != 0;
-	if(g.flags & AQH_GRID_SMOOTH)
-		opaque = opaque && (infoOf(P[1]) & VINFO_OPAQUE) && (infoOf(P[2]) & VINFO_OPAQUE) && (infoOf(P[3]) & VINFO_OPAQUE);
-	// MatteAlpha objects use the opaque slot too (bucketprocessor.cpp:1490-1491)
-	bool opaqueSlot = (opaque || (g.flags & AQH_GRID_MATTE_ALPHA)) && f.cullable;
-	if(opaqueSlot != wantOpaque) return;
-	const B2 B = boundOf4(P[0], P[1], P[3], P[2]);
+	P[0] = a;
+	B2 B;
+	float pointR = 0.f;
+	if(isPoint)
+	{
+		pointR = f.radius[p];
+		P[1] = a; P[2] = a; P[3] = a;
+		B.mnx = a.x - pointR; B.mny = a.y - pointR; B.mnz = a.z - 0.f; B.mxx = a.x + pointR; B.mxy = a.y + pointR; B.mxz = a.z + 0.f;
+	}
+	else
+	{
+		P[1] = f.P4[p+1]; P[2] = f.P4[p+cu+1]; P[3] = f.P4[p+cu+2];
+		B = boundOf4(P[0], P[1], P[3], P[2]);
+	}
 	const float bminx = B.mnx, bmaxx = B.mxx, bminy = B.mny, bmaxy = B.mxy;
 	// pixel range clamped to (tile ∩ sample region); compare in float first so that huge
 	// bounds cannot overflow the int conversions.
@@ -743,7 +807,7 @@ __device__ void setupStaticRec(const DevFrame& f, const TileCtx& t, const HideSm
 	int sX = (bminx < (float)t.rx0) ? t.rx0 : max(floorI(bminx), t.rx0);
 	int sY = (bminy < (float)t.ry0) ? t.ry0 : max(floorI(bminy), t.ry0);
 	if(sX >= eX || sY >= eY) return;
-	if(depthKey(B.mnz) > pixZMax(f, t, s, sX, eX, sY, eY)) return;      // hidden behind every sample it could touch
+	if(cullableMP && depthKey(B.mnz) > pixZMax(f, t, s, sX, eX, sY, eY)) return;      // hidden behind every sample it could touch
 	const int xs = f.xs, ys = f.ys;
 	int im = (bminx < (float)sX) ? 0 : floorI((bminx - (float)sX) * (float)xs);
 	int in = (bminy < (float)sY) ? 0 : floorI((bminy - (float)sY) * (float)ys);
@@ -753,6 +817,16 @@ __device__ void setupStaticRec(const DevFrame& f, const TileCtx& t, const HideSm
 	int gx0 = (sX - t.tileX0)*xs + im, gx1 = (eX - 1 - t.tileX0)*xs + em;
 	int gy0 = (sY - t.tileY0)*ys + in, gy1 = (eY - 1 - t.tileY0)*ys + en;
 	if(gx1 <= gx0 || gy1 <= gy0) return;
+	if(isPoint)
+	{
+		r.bminx = bminx; r.bminy = bminy; r.bmaxx = bmaxx; r.bmaxy = bmaxy;
+		r.Ax = a.x; r.Ay = a.y; r.Ex = pointR;
+		r.z[0] = a.z;
+		r.zminKey = cullableMP ? depthKey(B.mnz) : 0u;
+		r.flags = gi | REC_POINT | ((g.lod0 >= 0.0f) ? REC_RARE : 0u);
+		r.rect = (uint32_t)gx0 | ((uint32_t)gx1 << 8) | ((uint32_t)gy0 << 16) | ((uint32_t)gy1 << 24);
+		return;
+	}
 	const int code = computeVertexOrder(P);
 	HitCache c;
 	const float px[4] = {P[0].x, P[1].x, P[2].x, P[3].x};
@@ -763,7 +837,7 @@ __device__ void setupStaticRec(const DevFrame& f, const TileCtx& t, const HideSm
 	for(int i = 0; i < 4; ++i) { r.X[i] = c.X[i]; r.Y[i] = c.Y[i]; r.XM[i] = c.XM[i]; r.YM[i] = c.YM[i]; r.z[i] = c.z[i]; }
 	r.bminx = bminx; r.bminy = bminy; r.bmaxx = bmaxx; r.bmaxy = bmaxy;
 	r.Ax = c.Ax; r.Ay = c.Ay; r.Ex = c.Ex; r.Ey = c.Ey; r.Fx = c.Fx; r.Fy = c.Fy; r.Gx = c.Gx; r.Gy = c.Gy;
-	r.zminKey = depthKey(B.mnz);
+	r.zminKey = cullableMP ? depthKey(B.mnz) : 0u;     // a non-cullable (CSG) micropolygon is never rejected by depth
 	uint32_t fl = gi;
 	if(c.linear) fl |= REC_LINEAR;
 	if((g.flags & AQH_GRID_TRIANGULAR) || g.lod0 >= 0.0f) fl |= REC_RARE;
@@ -796,9 +870,21 @@ __device__ __forceinline__ void sampleStaticRec(const DevFrame& f, const TileCtx
 		// occlusion cull against the current opaque depth (bucketprocessor.cpp:1179)
 		const uint32_t occl = (uint32_t)(s.keys[idx] >> 32);
 		if(zminKey > occl) continue;
-		if(!edgeTests(r.X, r.Y, r.XM, r.YM, x, y)) continue;
-		const float2 uv = invBilinear(r.Ax, r.Ay, r.Ex, r.Ey, r.Fx, r.Fy, r.Gx, r.Gy, (r.flags & REC_LINEAR) ? 1 : 0, x, y);
-		const float D = bilerpZ(r.z, uv);
+		float2 uv; float D;
+		if(r.flags & REC_POINT)
+		{
+			// CqMicroPolygonPoints::Sample, geometry/points.cpp:653-664
+			const float dx = r.Ax - x, dy = r.Ay - y;
+			if(!((dx*dx + dy*dy) < r.Ex*r.Ex)) continue;
+			uv = make_float2(0.f, 0.f);
+			D = r.z[0];
+		}
+		else
+		{
+			if(!edgeTests(r.X, r.Y, r.XM, r.YM, x, y)) continue;
+			uv = invBilinear(r.Ax, r.Ay, r.Ex, r.Ey, r.Fx, r.Fy, r.Gx, r.Gy, (r.flags & REC_LINEAR) ? 1 : 0, x, y);
+			D = bilerpZ(r.z, uv);
+		}
 		if(r.flags & REC_RARE)
 		{
 			const GridRec g = f.grids[r.flags & VINFO_GRID_MASK];
@@ -813,7 +899,7 @@ __device__ __forceinline__ void sampleStaticRec(const DevFrame& f, const TileCtx
 		if(OPAQUE)
 			storeOpaque(f, s, &s.keys[idx], D, r.p);
 		else
-			storeDeep<AGG>(f, dc, s, idx, D, r.p, uv);
+			storeDeep<AGG>(f, dc, s, idx, D, r.p, uv, zminKey != 0u);
 	}
 }
 
@@ -960,7 +1046,9 @@ struct MovCtx
 	MovingMP m;
 	B2 mpBound;
 	float2 cocMin, cocMax;
-	bool moving, opaquePass;
+	bool moving, opaquePass, cullable;
+	float pointR;            // > 0: a disc (CqMicroPolygonPoints), centre = the staged vertex
+	bool isPoint;
 };
 
 // One queued candidate (micropolygon, sample): everything of CqMicroPolygon(Motion)::Sample after the gates
@@ -976,6 +1064,19 @@ __device__ __forceinline__ void movCandidate(const DevFrame& f, const TileCtx& t
 		if(c.m.g.lod0 > lod || lod >= c.m.g.lod1) return;
 	}
 	const float2 dofOff = s.dof ? s.dof[idx] : make_float2(0.f, 0.f);
+	if(c.isPoint)
+	{
+		// CqMicroPolygonPoints::Sample under depth of field (geometry/points.cpp:653-664): the SAMPLE is moved by its lens
+		// offset times the point's circle of confusion
+		const float4 P0 = ws->kv[0][0];
+		const float2 cm = cocAt(f, P0.z);
+		const float sx = pos.x + dofOff.x*cm.x, sy = pos.y + dofOff.y*cm.y;
+		const float dx = P0.x - sx, dy = P0.y - sy;
+		if(!((dx*dx + dy*dy) < c.pointR*c.pointR)) return;
+		if(c.opaquePass) storeOpaque(f, s, &s.keys[idx], P0.z, c.m.p);
+		else storeDeep<false>(f, dc, s, idx, P0.z, c.m.p, make_float2(0.f, 0.f), c.cullable);
+		return;
+	}
 	float px[4], py[4], pz[4];
 	if(!samplePoints(f, c.m, ws, c.moving, c.mpBound, c.cocMin, c.cocMax, pos, dofOff, time, px, py, pz, true)) return;
 	HitCache hc;
@@ -988,7 +1089,7 @@ __device__ __forceinline__ void movCandidate(const DevFrame& f, const TileCtx& t
 	if(c.opaquePass)
 		storeOpaque(f, s, &s.keys[idx], D, c.m.p);
 	else
-		storeDeep<false>(f, dc, s, idx, D, c.m.p, uv);
+		storeDeep<false>(f, dc, s, idx, D, c.m.p, uv, c.cullable);
 }
 
 // Queue a candidate that passed the cheap gates (called from divergent per-lane loops).
@@ -1036,6 +1137,9 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 	const bool moving = m.nkeys > 1;
 	if(!moving && !f.useDof) return false;
 	c.moving = moving; c.opaquePass = opaquePass;
+	c.isPoint = (m.g.flags & AQH_GRID_POINTS) != 0;
+	c.pointR = c.isPoint ? f.radius[p] : 0.f;
+	c.cullable = mpCullable(f, m.g);
 	// ---- stage the key vertices and key bounds in the warp's scratch
 	__syncwarp();
 	{
@@ -1043,13 +1147,15 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 		if((uint32_t)lane < 4u*nk)
 		{
 			const uint32_t k = (uint32_t)lane >> 2; const int i = lane & 3;
-			ws->kv[k][i] = f.P4[p + (size_t)k*m.nverts + (uint32_t)(i & 1) + (uint32_t)(i >> 1)*(m.cu + 1)];
+			// a point has one vertex: all four slots hold it
+			ws->kv[k][i] = c.isPoint ? a : f.P4[p + (size_t)k*m.nverts + (uint32_t)(i & 1) + (uint32_t)(i >> 1)*(m.cu + 1)];
 		}
 		if(lane == 0) ws->qcount = 0;
 		__syncwarp();
 		if((uint32_t)lane < nk)
 		{
-			const B2 b = boundOf4(ws->kv[lane][0], ws->kv[lane][1], ws->kv[lane][2], ws->kv[lane][3]);
+			B2 b = boundOf4(ws->kv[lane][0], ws->kv[lane][1], ws->kv[lane][2], ws->kv[lane][3]);
+			if(c.isPoint) { b.mnx = a.x - c.pointR; b.mny = a.y - c.pointR; b.mxx = a.x + c.pointR; b.mxy = a.y + c.pointR; b.mnz = a.z - 0.f; b.mxz = a.z + 0.f; }
 			ws->kb[lane][0] = make_float4(b.mnx, b.mny, b.mnz, b.mxx);
 			ws->kb[lane][1] = make_float4(b.mxy, b.mxz, 0.f, 0.f);
 		}
@@ -1058,11 +1164,11 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 	float4 P[4];
 	P[0] = ws->kv[0][0]; P[1] = ws->kv[0][1]; P[2] = ws->kv[0][2]; P[3] = ws->kv[0][3];
 	bool opaque = (info & VINFO_OPAQUE) != 0;
-	if(m.g.flags & AQH_GRID_SMOOTH)
+	if((m.g.flags & AQH_GRID_SMOOTH) && !c.isPoint)
 		opaque = opaque && (infoOf(P[1]) & VINFO_OPAQUE) && (infoOf(P[2]) & VINFO_OPAQUE) && (infoOf(P[3]) & VINFO_OPAQUE);
-	const bool opaqueSlot = (opaque || (m.g.flags & AQH_GRID_MATTE_ALPHA)) && f.cullable;
+	const bool opaqueSlot = (opaque || (m.g.flags & AQH_GRID_MATTE_ALPHA)) && c.cullable;
 	if(opaqueSlot != opaquePass) return true;
-	m.code = computeVertexOrder(P);
+	m.code = c.isPoint ? 0xE4 : computeVertexOrder(P);
 	// m_Bound: union of the key bounds (AppendKey, micropolygon.cpp:1952-1967)
 	B2 mpBound = keyBound(f, m, ws, 0);
 	for(uint32_t k = 1; k < m.nkeys; ++k) { B2 kb = keyBound(f, m, ws, k); encapsulate(mpBound, kb); }
@@ -1172,7 +1278,7 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 					if(indexT0 >= n) continue;
 				}
 				if(Bnd.mnz > f.clipFar || Bnd.mxz < f.clipNear) continue;
-				zminKey = depthKey(Bnd.mnz);
+				zminKey = c.cullable ? depthKey(Bnd.mnz) : 0u;      // a CSG micropolygon is never rejected by depth
 				if(f.useDof)
 				{
 					float2 c1 = cocAt(f, Bnd.mnz), c2 = cocAt(f, Bnd.mxz);
@@ -1277,6 +1383,7 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 template<bool MBDOF>
 __device__ __forceinline__ void hitUV(const DevFrame& f, const GridRec& g, uint32_t p, float2 pos, float2 dofOff, float time, float2& uv)
 {
+	if(g.flags & AQH_GRID_POINTS) { uv = make_float2(0.f, 0.f); return; }     // a disc has no parametrisation: constant shading
 	if(!MBDOF)
 	{
 		// no motion and no depth of field anywhere in the frame: the vertices are those of the grid
@@ -1302,10 +1409,11 @@ __device__ __forceinline__ void hitUV(const DevFrame& f, const GridRec& g, uint3
 // Fast path: depth filter "min" (imagepixel.cpp:144-262, 301-318).
 template<bool MBDOF>
 __device__ __forceinline__ void resolveSampleMin(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, int idx,
-                              float out[7], bool& valid)
+                              float out[7], bool& valid, uint32_t& pNear)
 {
 	const unsigned long long key = s.keys[idx];
 	const uint32_t p = (uint32_t)key;
+	pNear = p;                       // the nearest entry hands its arbitrary output variables to the sample (imagepixel.cpp:249-251)
 	const bool haveOpaque = (p != 0xffffffffu);
 	const float2 pos = make_float2(s.posx[idx], s.posy[idx]);
 	float col[3] = {0.f, 0.f, 0.f}, opa[3] = {0.f, 0.f, 0.f};
@@ -1410,6 +1518,7 @@ __device__ __forceinline__ void resolveSampleMin(const DevFrame& f, const TileCt
 		float c2[3], o2[3];
 		shadeHit(f, g, A.z, uv, c2, o2);
 		const float d2 = __uint_as_float(A.y);
+		pNear = A.z;                 // composited back to front: the last entry is the nearest
 		if(g.flags & AQH_GRID_MATTE)
 		{
 #pragma unroll
@@ -1433,13 +1542,14 @@ __device__ __forceinline__ void resolveSampleMin(const DevFrame& f, const TileCt
 
 template<bool MBDOF>
 __device__ void resolveSampleGeneral(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, int idx,
-                              float out[7], bool& valid)
+                              float out[7], bool& valid, uint32_t& pNear)
 {
 	// keys[nsP + idx]: nearest opaque hit; keys[idx]: the occlusion depth occlZ (the same array unless the midpoint depth
 	// filter keeps the SECOND nearest opaque depth there, bucketprocessor.cpp:1502-1529)
 	const unsigned long long key = s.keys[idx + (f.midpointZ ? s.nsP : 0)];
 	const float occlZ = keyDepth((uint32_t)(s.keys[idx] >> 32));
 	const uint32_t p = (uint32_t)key;
+	pNear = p;
 	const bool haveOpaque = (p != 0xffffffffu);
 	const float2 pos = make_float2(s.posx[idx], s.posy[idx]);
 	float col[3] = {0.f, 0.f, 0.f}, opa[3] = {0.f, 0.f, 0.f};
@@ -1554,10 +1664,12 @@ __device__ void resolveSampleGeneral(const DevFrame& f, const TileCtx& t, const 
 #pragma unroll
 				for(int k = 0; k < 3; ++k) { c2[k] = col[k]; o2[k] = opa[k]; }
 				d2 = depth; matte = opaqueMatte;
+				if(pass == 0) pNear = p;
 			}
 			else
 			{
 				const uint4 A = dc.A[bestSlot];
+				if(pass == 0) pNear = A.z;
 				const float2 uv = dc.UV[bestSlot];
 				const float4 a = f.P4[A.z];
 				const GridRec g = f.grids[infoOf(a) & VINFO_GRID_MASK];
@@ -1604,14 +1716,186 @@ __device__ void resolveSampleGeneral(const DevFrame& f, const TileCtx& t, const 
 	out[6] = zout;
 }
 
+// ---- CSG: CqCSGTreeNode::ProcessTree / ProcessSampleList / EvaluateState (csgtree.cpp:144-351) on the sample's depth-sorted
+// list.  Samples with a list in a frame that has CSG grids take this path (rare: out of line, arrays in local memory).
+#define CSG_MAX_LIST 48
+__device__ __forceinline__ bool csgEvaluate(int type, uint32_t state, int nKids)
+{
+	const uint32_t all = nKids >= 32 ? 0xffffffffu : ((1u << nKids) - 1u);
+	if(type == AQH_CSG_UNION) return (state & all) != 0u;
+	if(type == AQH_CSG_INTERSECTION) return (state & all) == all;
+	if(type == AQH_CSG_DIFFERENCE) return (state & 1u) && !(state & all & ~1u);
+	return false;
+}
+template<bool MBDOF>
+__device__ __noinline__ void resolveSampleCSG(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, int idx,
+                                              float out[7], bool& valid, uint32_t& pNear)
+{
+	constexpr uint32_t NIL = 0xffffffffu, OPQ = 0xfffffffeu;
+	const unsigned long long key = s.keys[idx + (f.midpointZ ? s.nsP : 0)];
+	const float occlZ = keyDepth((uint32_t)(s.keys[idx] >> 32));
+	const uint32_t p = (uint32_t)key;
+	const bool haveOpaque = (p != NIL);
+	const float2 pos = make_float2(s.posx[idx], s.posy[idx]);
+	float col[3] = {0.f, 0.f, 0.f}, opa[3] = {0.f, 0.f, 0.f};
+	float depth = 0.f;
+	bool opaqueMatte = false;
+	if(haveOpaque)
+	{
+		const float4 a = f.P4[p];
+		const GridRec g = f.grids[infoOf(a) & VINFO_GRID_MASK];
+		float2 uv;
+		const float2 dofOff = s.dof ? s.dof[idx] : make_float2(0.f, 0.f);
+		const float time = s.time ? s.time[idx] : 0.f;
+		hitUV<MBDOF>(f, g, p, pos, dofOff, time, uv);
+		shadeHit(f, g, p, uv, col, opa);
+		depth = keyDepth((uint32_t)(key >> 32));
+		opaqueMatte = (g.flags & AQH_GRID_MATTE) != 0;
+	}
+	// the list in ascending (depth, submission) order, the valid opaque hit included (imagepixel.cpp:157-164)
+	unsigned long long ks[CSG_MAX_LIST];
+	uint32_t sl[CSG_MAX_LIST];
+	int nd[CSG_MAX_LIST];
+	int cnt = 0;
+	{
+		uint32_t e = haveOpaque ? OPQ : s.head[idx];
+		while(e != NIL)
+		{
+			unsigned long long k; uint32_t nextE; int node = -1;
+			if(e == OPQ) { k = key; nextE = s.head[idx]; }
+			else
+			{
+				const uint4 A = dc.A[e];
+				k = ((unsigned long long)depthKey(__uint_as_float(A.y)) << 32) | A.z;
+				nextE = A.x;
+				const uint32_t gi = infoOf(f.P4[A.z]) & VINFO_GRID_MASK;
+				if(f.grids[gi].flags & AQH_GRID_USES_CSG) node = f.gridCsg[gi];
+			}
+			if(cnt >= CSG_MAX_LIST) { atomicOr(f.errorFlags, 8u); break; }
+			int j = cnt++;
+			while(j > 0 && ks[j-1] > k) { ks[j] = ks[j-1]; sl[j] = sl[j-1]; nd[j] = nd[j-1]; --j; }
+			ks[j] = k; sl[j] = e; nd[j] = node;
+			e = nextE;
+		}
+	}
+	// as long as any entry belongs to a CSG node, run that node's whole tree over the list (imagepixel.cpp:166-189)
+	for(int guard = 0; guard < 64; ++guard)
+	{
+		int first = -1;
+		for(int j = 0; j < cnt && first < 0; ++j) if(nd[j] >= 0) first = j;
+		if(first < 0) break;
+		int root = nd[first];
+		while(f.csgParent[root] >= 0) root = f.csgParent[root];
+		if(f.csgType[root] == AQH_CSG_PRIMITIVE)
+		{
+			// CqCSGNodePrimitive::ProcessSampleList: a lone primitive just releases its samples
+			for(int j = 0; j < cnt; ++j) if(nd[j] == root) nd[j] = -1;
+			continue;
+		}
+		for(int oi = 0; oi < f.nCsgOrder; ++oi)
+		{
+			const int N = f.csgOrder[oi];
+			int r = N;
+			while(f.csgParent[r] >= 0) r = f.csgParent[r];
+			if(r != root) continue;
+			// ProcessSampleList of node N (its non-primitive children come earlier in csgOrder)
+			const int type = f.csgType[N], nKids = f.csgKids[N];
+			const int promoted = (f.csgParent[N] >= 0) ? N : -1;
+			uint32_t state = 0u;
+			bool current = csgEvaluate(type, state, nKids);
+			int w = 0;
+			for(int j = 0; j < cnt; ++j)
+			{
+				const int n = nd[j];
+				const int ci = (n >= 0 && f.csgParent[n] == N) ? f.csgSlot[n] : -1;
+				bool keep = true;
+				int newNode = n;
+				if(ci >= 0)
+				{
+					state ^= 1u << ci;
+					const bool next = csgEvaluate(type, state, nKids);
+					if(next == current) keep = false;          // the solid's state does not change here: the wall is not visible
+					else { current = next; newNode = promoted; }
+				}
+				if(keep) { ks[w] = ks[j]; sl[w] = sl[j]; nd[w] = newNode; ++w; }
+			}
+			cnt = w;
+		}
+	}
+	if(cnt == 0) { valid = false; pNear = NIL; return; }     // nothing left and no opaque hit: the sample stays empty
+	// ---- composite what is left back to front (imagepixel.cpp:191-300), exactly like resolveSampleGeneral
+	float sc[3] = {0.f, 0.f, 0.f}, so[3] = {0.f, 0.f, 0.f};
+	float opaqueDepth0 = occlZ, opaqueDepth1 = FLT_MAX, maxOpaqueDepth = FLT_MAX;
+	float totDepth = 0.0f; int totCount = 0;
+	const bool average = f.depthFilter == AQH_DEPTHFILTER_AVERAGE;
+	for(int pass = 0; pass < (average ? 2 : 1); ++pass)
+		for(int step = 0; step < cnt; ++step)
+		{
+			const int j = (pass == 0) ? cnt - 1 - step : step;
+			float c2[3], o2[3], d2;
+			bool matte;
+			if(sl[j] == OPQ)
+			{
+#pragma unroll
+				for(int k = 0; k < 3; ++k) { c2[k] = col[k]; o2[k] = opa[k]; }
+				d2 = depth; matte = opaqueMatte;
+			}
+			else
+			{
+				const uint4 A = dc.A[sl[j]];
+				const float2 uv = dc.UV[sl[j]];
+				const GridRec g = f.grids[infoOf(f.P4[A.z]) & VINFO_GRID_MASK];
+				shadeHit(f, g, A.z, uv, c2, o2);
+				d2 = __uint_as_float(A.y);
+				matte = (g.flags & AQH_GRID_MATTE) != 0;
+			}
+			if(pass == 1)
+			{
+				const float* od = (step == 0) ? so : o2;      // the nearest entry shares its data with the composited result
+				if(od[0] >= f.zthr[0] || od[1] >= f.zthr[1] || od[2] >= f.zthr[2]) { totDepth += d2; totCount++; }
+				continue;
+			}
+			if(matte)
+			{
+#pragma unroll
+				for(int k = 0; k < 3; ++k) { sc[k] = (1.f-o2[k])*sc[k] + o2[k]*0.0f; so[k] = (1.f-c2[k])*so[k] + c2[k]*0.0f; }
+			}
+			else
+			{
+#pragma unroll
+				for(int k = 0; k < 3; ++k)
+				{
+					sc[k] = (sc[k] * (1.0f - fminf(fmaxf(o2[k], 0.0f), 1.0f))) + c2[k];
+					so[k] = ((1.0f - so[k]) * o2[k]) + so[k];
+				}
+			}
+			if(o2[0] >= f.zthr[0] && o2[1] >= f.zthr[1] && o2[2] >= f.zthr[2])
+			{
+				opaqueDepth1 = opaqueDepth0;
+				opaqueDepth0 = d2;
+				if(!(maxOpaqueDepth < FLT_MAX)) maxOpaqueDepth = d2;
+			}
+		}
+	valid = true;
+	pNear = (sl[0] == OPQ) ? p : dc.A[sl[0]].z;
+	out[0] = sc[0]; out[1] = sc[1]; out[2] = sc[2]; out[3] = so[0]; out[4] = so[1]; out[5] = so[2];
+	float zout = opaqueDepth0;
+	if(f.depthFilter == AQH_DEPTHFILTER_MIDPOINT) zout = (cnt > 1) ? ((opaqueDepth0 + opaqueDepth1) * 0.5f) : FLT_MAX;
+	else if(f.depthFilter == AQH_DEPTHFILTER_MAX) zout = maxOpaqueDepth;
+	else if(average) zout = totDepth / (float)totCount;
+	out[6] = zout;
+}
+
 // Depth filter "min" without the midpoint bookkeeping is the common case and keeps its own lean code; every
-// other depth filter goes through the general restatement of CqImagePixel::Combine above.
+// other depth filter goes through the general restatement of CqImagePixel::Combine above; samples with a hit list in a
+// frame with CSG solids go through the CSG resolve.
 template<bool MBDOF, bool DFGEN>
 __device__ __forceinline__ void resolveSample(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, int idx,
-                                              float out[7], bool& valid)
+                                              float out[7], bool& valid, uint32_t& pNear)
 {
-	if(!DFGEN) resolveSampleMin<MBDOF>(f, t, s, dc, idx, out, valid);
-	else resolveSampleGeneral<MBDOF>(f, t, s, dc, idx, out, valid);
+	if(f.anyCSG && s.head && s.head[idx] != 0xffffffffu) { resolveSampleCSG<MBDOF>(f, t, s, dc, idx, out, valid, pNear); return; }
+	if(!DFGEN) resolveSampleMin<MBDOF>(f, t, s, dc, idx, out, valid, pNear);
+	else resolveSampleGeneral<MBDOF>(f, t, s, dc, idx, out, valid, pNear);
 }
 
 // Per-tap inclusion bits of one sample (bucketprocessor.cpp:609-612), evaluated with the true
@@ -1691,6 +1975,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 		__syncthreads();
 		const uint32_t slot = s_tile;
 		if(slot >= slotEnd) break;
+		// an incremental flush leaves tiles without new micropolygons as they are (their occlusion image is already there)
+		if(f.zOnly && f.zKeys && f.binOffset[slot+1] == f.binOffset[slot]) continue;
 		const uint32_t tile = f.activeTiles[slot];
 		TileCtx t;
 		t.tileX0 = f.sx0 + (int)(tile % f.ntx)*f.tileW;
@@ -1727,6 +2013,12 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 				const float2 o = f.posTab[(size_t)patPos*n + i];
 				s.posx[idx] = (float)X + o.x;
 				s.posy[idx] = (float)Y + o.y;
+				if(f.zKeys)
+				{
+					// the occlusion state earlier flushes of this frame left behind
+					s.keys[idx] = f.zKeys[pp*n + i];
+					if(f.midpointZ) s.keys[s.nsP + idx] = f.zKeys2[pp*n + i];
+				}
 				if(s.time)
 					s.time[idx] = (f.shutterClose - f.shutterOpen) * f.val1d[(size_t)patT*n + i] + f.shutterOpen;
 				if(s.dof)
@@ -1751,6 +2043,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 		for(int i = tid; i < f.tileW*f.tileH; i += THREADS) s.pixZ[i] = 0xffffffffu;
 		if(tid == 0) { s_tileZ = 0xffffffffu; s_dirty = 0; s_lastRef = 0; }
 		__syncthreads();
+		if(f.zKeys)
+		{
+			if(warp == 0) refreshPixZ(f, t, s, lane);        // start from the hierarchical z of the stored keys
+			__syncthreads();
+		}
 		const uint32_t binBeg = f.binOffset[slot], binCnt = f.binOffset[slot+1] - binBeg;
 		const uint32_t tflags = f.tileFlags[slot];
 		// ---- Render_MPGs: opaque pass, then (if the tile saw non-opaque micropolygons) deep pass
@@ -1762,7 +2059,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 			if(MBDOF) asm volatile("" : "+r"(pass));
 			if(pass == 1)
 			{
-				if(!(f.anyTransparent && (tflags & 1u))) break;
+				if(f.zOnly || !(f.anyTransparent && (tflags & 1u))) break;      // occlusion only needs the opaque pass
 				__syncthreads();
 				if(tid == 0) { s_next = 0; s_dirty = 0; s_lastRef = 0; }
 				if(warp == 0) refreshPixZ(f, t, s, lane);        // the opaque depths are final now
@@ -1803,7 +2100,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 				const unsigned long long ent = (lane < cnt) ? f.binEntries[binBeg + base + lane] : 0ull;
 				{
 					const uint32_t zfirst = __shfl_sync(0xffffffffu, (uint32_t)(ent >> 32), 0);
-					if(zfirst > *(volatile uint32_t*)s.tileZ)
+					// (CSG micropolygons are not cullable: with any in the frame the deep pass visits every entry)
+					if(!(pass == 1 && f.anyCSG) && zfirst > *(volatile uint32_t*)s.tileZ)
 					{
 						const uint32_t runEnd = min(binCnt, (base / (uint32_t)f.sortRun + 1u)*(uint32_t)f.sortRun);
 						if(lane == 0) atomicMax(&s_next, runEnd);
@@ -1855,6 +2153,21 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 				const int X = t.rx0 + lx, Y = t.ry0 + ly;
 				f.occlImage[(size_t)(Y - f.sy0)*f.sw + (X - f.sx0)] = keyDepth(s.pixZ[ly*f.tileW + lx]);
 			}
+			if(f.zOnly && f.zKeys)
+			{
+				// keep the per-sample occlusion keys for the next flush / the final frame: one warp per pixel
+				for(int pix = warp; pix < tw0*th0; pix += NWARPS)
+				{
+					const int ly = pix / tw0, lx = pix - ly*tw0;
+					const size_t pp = (size_t)(t.ry0 + ly - f.sy0)*f.sw + (size_t)(t.rx0 + lx - f.sx0);
+					const int base = (ly*ys)*s.stride + lx*xs;
+					for(int i = lane; i < n; i += 32)
+					{
+						f.zKeys[pp*n + i] = s.keys[base + s.subOfs[i]];
+						if(f.midpointZ) f.zKeys2[pp*n + i] = s.keys[s.nsP + base + s.subOfs[i]];
+					}
+				}
+			}
 			if(f.zOnly) continue;          // the next tile's first barrier orders the reads of pixZ above
 		}
 		// ---- Combine_samples + hand the resolved samples to the filter stage.
@@ -1875,13 +2188,21 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 					const size_t at = (rowAt + (size_t)c*f.planeW)*SC + j;
 					if(i >= n) { storeMask(f, at, 0u); continue; }       // padding slot: never included
 					const int idx = sampleIdx(f, s, lx, ly, i);
-					float out[7]; bool valid;
-					resolveSample<MBDOF, DFGEN>(f, t, s, dc, idx, out, valid);
+					float out[7]; bool valid; uint32_t pNear;
+					resolveSample<MBDOF, DFGEN>(f, t, s, dc, idx, out, valid, pNear);
 					storeMask(f, at, packMask(f, tapMask(f, s.posx[idx], s.posy[idx], X, Y, valid)));
 					if(valid)
 					{
 #pragma unroll
 						for(int k = 0; k < 7; ++k) f.planes[(size_t)k*f.planeStride + at] = out[k];
+						if(f.aovFloats)
+						{
+							// StoreExtraData (bucketprocessor.cpp:1573-1643): the values at the index of the micropolygon of the
+							// NEAREST hit, uninterpolated; planes 7.. are filtered like colour
+							const GridRec g = f.grids[infoOf(f.P4[pNear]) & VINFO_GRID_MASK];
+							const float* av = f.aov + ((size_t)g.vbase + (pNear - g.pbase))*f.aovFloats;
+							for(int k = 0; k < f.aovFloats; ++k) f.planes[(size_t)(7 + k)*f.planeStride + at] = av[k];
+						}
 					}
 				}
 			}
@@ -1905,8 +2226,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 					if(i < n)
 					{
 						const int idx = sampleIdx(f, s, lx, ly, i);
-						float out[7]; bool valid;
-						resolveSample<MBDOF, DFGEN>(f, t, s, dc, idx, out, valid);
+						float out[7]; bool valid; uint32_t pNear;
+						resolveSample<MBDOF, DFGEN>(f, t, s, dc, idx, out, valid, pNear);
 						const uint32_t m = tapMask(f, s.posx[idx], s.posy[idx], X, Y, valid);
 						if(!valid) { out[0] = out[1] = out[2] = out[3] = out[4] = out[5] = out[6] = 0.f; }
 						scratch[2*lane] = make_float4(out[0], out[1], out[2], out[3]);
@@ -1967,11 +2288,7 @@ __global__ void __launch_bounds__(256) k_tile_flags(DevFrame f)
 		const float4 a = f.P4[p];
 		const uint32_t info = infoOf(a);
 		const GridRec g = f.grids[info & VINFO_GRID_MASK];
-		const uint32_t cu = g.cu_cv & 0xffffu;
-		bool opaque = (info & VINFO_OPAQUE) != 0;
-		if(g.flags & AQH_GRID_SMOOTH)
-			opaque = opaque && (infoOf(f.P4[p+1]) & VINFO_OPAQUE) && (infoOf(f.P4[p+cu+1]) & VINFO_OPAQUE) && (infoOf(f.P4[p+cu+2]) & VINFO_OPAQUE);
-		if(!((opaque || (g.flags & AQH_GRID_MATTE_ALPHA)) && f.cullable)) any = 1;
+		if(!mpOpaqueSlot(f, g, p, info)) any = 1;
 	}
 	if(any) s_any = 1;
 	__syncthreads();
@@ -1984,51 +2301,9 @@ __global__ void __launch_bounds__(256) k_tile_flags(DevFrame f)
 // ExposeBucket (:766-806) and FormatBucketForDisplay (ddmanager.cpp:1046-1113).
 __device__ __forceinline__ double clampD(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-// Everything after the sums: normalise, coverage/alpha (bucketprocessor.cpp:633-707),
-// ExposeBucket (:766-806), store the 9-float pixel and quantise per display
-// (FormatBucketForDisplay, ddmanager.cpp:1046-1113).
-__device__ __forceinline__ void finishPixel(const DevFrame& f, const DevDisplays& disp, int x, int y,
-                                            const float acc[7], float gTot, int SampleCount)
+// FormatBucketForDisplay (ddmanager.cpp:1046-1113) for one pixel: px = the pixel's floats of the channel buffer.
+__device__ __forceinline__ void quantisePixel(const DevFrame& f, const DevDisplays& disp, int x, int y, const float* px)
 {
-	const int n = f.n;
-	float out[9];
-	float coverage;
-	if(SampleCount == 0)
-	{
-#pragma unroll
-		for(int k = 0; k < 9; ++k) out[k] = 0.f;
-		out[AQH_CH_Z] = FLT_MAX;
-		coverage = 0.f;
-	}
-	else
-	{
-		const float oneOverGTot = 1.0f / gTot;
-#pragma unroll
-		for(int k = 0; k < 6; ++k) out[k] = acc[k] * oneOverGTot;
-		out[AQH_CH_Z] = acc[6] * oneOverGTot;
-		coverage = (SampleCount >= n) ? 1.0f : (float)SampleCount / (float)n;
-	}
-	const float a = (out[3] + out[4] + out[5]) / 3.0f;
-	out[AQH_CH_ALPHA] = a * coverage;
-	out[AQH_CH_COVERAGE] = coverage;
-	if(!(f.expGain == 1.0f && f.expGamma == 1.0f))
-	{
-		const float oneovergamma = 1.0f / f.expGamma;
-#pragma unroll
-		for(int k = 0; k < 3; ++k)
-		{
-			if(f.expGain != 1.0f) out[k] *= f.expGain;
-			if(f.expGamma != 1.0f) out[k] = (float)pow((double)out[k], (double)oneovergamma);
-		}
-	}
-	// A NaN (0/0 of the "average" depth filter over no qualifying hit, inf - inf of filtered FLT_MAX depths with
-	// negative lobes) is the x86 default NaN 0xFFC00000 in the reference's build; the GPU's canonical NaN is
-	// 0x7FFFFFFF.  Same value class, made the same bits.
-#pragma unroll
-	for(int k = 0; k < 9; ++k) if(out[k] != out[k]) out[k] = __uint_as_float(0xffc00000u);
-	float* dst = f.channels + ((size_t)y*f.xres + x)*9;
-#pragma unroll
-	for(int k = 0; k < 9; ++k) dst[k] = out[k];
 	for(int d = 0; d < disp.n; ++d)
 	{
 		const DevDisplay& dd = disp.d[d];
@@ -2036,7 +2311,7 @@ __device__ __forceinline__ void finishPixel(const DevFrame& f, const DevDisplays
 		unsigned char* pd = dd.out + ((size_t)y*f.xres + x)*dd.entrySize;
 		for(int c = 0; c < dd.nChannels; ++c)
 		{
-			double value = (double)out[dd.channel[c]];
+			double value = (double)px[dd.channel[c]];
 			if(dd.qOne != 0.f)
 			{
 				double v = (double)dd.qZero + value * (double)(dd.qOne - dd.qZero) + ((double)dd.qDither * s);
@@ -2061,8 +2336,94 @@ __device__ __forceinline__ void finishPixel(const DevFrame& f, const DevDisplays
 	}
 }
 
+// ExposeBucket (bucketprocessor.cpp:766-806) on Ci of one pixel.
+__device__ __forceinline__ void exposePixel(const DevFrame& f, float* out)
+{
+	if(f.expGain == 1.0f && f.expGamma == 1.0f) return;
+	const float oneovergamma = 1.0f / f.expGamma;
+#pragma unroll
+	for(int k = 0; k < 3; ++k)
+	{
+		if(f.expGain != 1.0f) out[k] *= f.expGain;
+		if(f.expGamma != 1.0f) out[k] = (float)pow((double)out[k], (double)oneovergamma);
+	}
+}
+
+// Everything after the sums: normalise, coverage/alpha (bucketprocessor.cpp:633-707),
+// ExposeBucket (:766-806), store the 9 standard floats of the pixel and quantise per display
+// (FormatBucketForDisplay, ddmanager.cpp:1046-1113).  With f.deferDisplay the quantisation (and with f.deferExpose the
+// exposure) is left to k_finish: the displays may show arbitrary output variables, an imager may still change the pixel.
+__device__ __forceinline__ void finishPixel(const DevFrame& f, const DevDisplays& disp, int x, int y,
+                                            const float acc[7], float gTot, int SampleCount)
+{
+	const int n = f.n;
+	float out[9];
+	float coverage;
+	if(SampleCount == 0)
+	{
+#pragma unroll
+		for(int k = 0; k < 9; ++k) out[k] = 0.f;
+		out[AQH_CH_Z] = FLT_MAX;
+		coverage = 0.f;
+	}
+	else
+	{
+		const float oneOverGTot = 1.0f / gTot;
+#pragma unroll
+		for(int k = 0; k < 6; ++k) out[k] = acc[k] * oneOverGTot;
+		out[AQH_CH_Z] = acc[6] * oneOverGTot;
+		coverage = (SampleCount >= n) ? 1.0f : (float)SampleCount / (float)n;
+	}
+	const float a = (out[3] + out[4] + out[5]) / 3.0f;
+	out[AQH_CH_ALPHA] = a * coverage;
+	out[AQH_CH_COVERAGE] = coverage;
+	if(!f.deferExpose) exposePixel(f, out);
+	// A NaN (0/0 of the "average" depth filter over no qualifying hit, inf - inf of filtered FLT_MAX depths with
+	// negative lobes) is the x86 default NaN 0xFFC00000 in the reference's build; the GPU's canonical NaN is
+	// 0x7FFFFFFF.  Same value class, made the same bits.
+#pragma unroll
+	for(int k = 0; k < 9; ++k) if(out[k] != out[k]) out[k] = __uint_as_float(0xffc00000u);
+	float* dst = f.channels + ((size_t)y*f.xres + x)*f.nch;
+#pragma unroll
+	for(int k = 0; k < 9; ++k) dst[k] = out[k];
+	if(!f.deferDisplay) quantisePixel(f, disp, x, y, out);
+}
+
+// The filtered floats of an arbitrary-output-variable pass: values kBase-7 .. of the pixel's AOV block
+// (bucketprocessor.cpp:633-653: zero when no sample of the footprint holds a hit, else sum / gTot).
+__device__ __forceinline__ void finishAovPixel(const DevFrame& f, int x, int y, const float* acc, int nVal, int kBase, float gTot, int SampleCount)
+{
+	float* dst = f.channels + ((size_t)y*f.xres + x)*f.nch + 9 + (kBase - 7);
+	const float oneOverGTot = 1.0f / gTot;
+	for(int k = 0; k < nVal; ++k)
+	{
+		float v = (SampleCount == 0) ? 0.f : acc[k] * oneOverGTot;
+		if(v != v) v = __uint_as_float(0xffc00000u);
+		dst[k] = v;
+	}
+}
+
+// The deferred tail of the frame: exposure (when an imager ran in between) and the quantisation of every display, one
+// thread per pixel of the crop window.
+__global__ void __launch_bounds__(256) k_finish(DevFrame f, DevDisplays disp, int expose)
+{
+	const int x = f.cropX0 + blockIdx.x*blockDim.x + threadIdx.x;
+	const int y = f.cropY0 + blockIdx.y*blockDim.y + threadIdx.y;
+	if(x >= f.cropX1 || y >= f.cropY1) return;
+	if(f.rowOwned && !f.rowOwned[y]) return;
+	float* px = f.channels + ((size_t)y*f.xres + x)*f.nch;
+	if(expose)
+	{
+		float ci[3] = {px[0], px[1], px[2]};
+		exposePixel(f, ci);
+#pragma unroll
+		for(int k = 0; k < 3; ++k) { if(ci[k] != ci[k]) ci[k] = __uint_as_float(0xffc00000u); px[k] = ci[k]; }
+	}
+	quantisePixel(f, disp, x, y, px);
+}
+
 // Reference-order filter: one running sum per output pixel over the per-sample planes.
-__global__ void __launch_bounds__(256) k_filter(DevFrame f, DevDisplays disp, int weightsInSmem, int yBeg, int yEnd)
+__global__ void __launch_bounds__(256) k_filter(DevFrame f, DevDisplays disp, int weightsInSmem, int yBeg, int yEnd, int kBase, int nVal)
 {
 	extern __shared__ float s_filtBuf[];
 	const int taps = (2*f.shiftX+1)*(2*f.shiftY+1)*f.n;
@@ -2099,13 +2460,14 @@ __global__ void __launch_bounds__(256) k_filter(DevFrame f, DevDisplays disp, in
 					{
 #pragma unroll
 						for(int k = 0; k < 7; ++k)
-							acc[k] += f.planes[(size_t)k*f.planeStride + at] * w;
+							if(k < nVal) acc[k] += f.planes[(size_t)(kBase + k)*f.planeStride + at] * w;
 						SampleCount++;
 					}
 				}
 			}
 		}
-	finishPixel(f, disp, x, y, acc, gTot, SampleCount);
+	if(kBase == 0) finishPixel(f, disp, x, y, acc, gTot, SampleCount);
+	else finishAovPixel(f, x, y, acc, nVal, kBase, gTot, SampleCount);
 }
 
 // Reference-order filter, pixel spans staged by bulk copies and channel split.
@@ -2176,7 +2538,7 @@ __host__ __device__ __forceinline__ int filterPlaneFloats(const DevFrame& f)
 // MB = bytes per mask word (1, 2 or 4).  Four consecutive slots are tested per step:
 // one 32-bit shared load for byte masks, one 64-bit load for 16-bit masks, one 128-bit load for 32-bit masks.
 template<int MB>
-__global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(DevFrame f, DevDisplays disp, int yBeg)
+__global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(DevFrame f, DevDisplays disp, int yBeg, int kBase, int nVal)
 {
 	constexpr int W = FILTER_W;
 	extern __shared__ __align__(128) unsigned char fsm[];
@@ -2190,7 +2552,9 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(DevFrame f, DevDisp
 	const int tid = threadIdx.x, ch = tid & 7, px = tid >> 3;
 	const int x0 = f.cropX0 + blockIdx.x*W, y = yBeg + blockIdx.y;
 	if(f.rowOwned && !f.rowOwned[y]) return;             // uniform over the CTA
-	const bool live = (x0 + px) < f.cropX1;
+	// kBase / nVal: the planes this pass filters -- 0 / 7 for R G B Or Og Ob Z, then groups of up to seven AOV floats;
+	// channel threads beyond nVal idle, channel 7 always sums the weights
+	const bool live = (x0 + px) < f.cropX1 && (ch < nVal || ch == 7);
 	// channel 7 reads 1.0f from a region laid out so that its banks continue the skew of the seven planes
 	float* ones = tile + (size_t)7*planeS;
 	const unsigned char* mbase = reinterpret_cast<const unsigned char*>(ones + FILTER_ONES);
@@ -2217,12 +2581,12 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(DevFrame f, DevDisp
 				{
 					// order the CTA's generic-proxy reads of the tile before the async-proxy overwrite
 					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-					mbarExpectTx(&s_bar, 7u*vbytes + mbytes);
+					mbarExpectTx(&s_bar, (uint32_t)nVal*vbytes + mbytes);
 					// first staged pixel column of the sample region: x0 - xmax - sx0 (+ fx when every fx is staged on its own)
 					const size_t col = (size_t)(x0 - f.cropX0) + (size_t)sfx;
 					const size_t at = ((srow*nCh + c)*f.planeW + col)*SC;
-					for(int k = 0; k < 7; ++k)
-						bulkLoad(tile + (size_t)k*planeS, f.planes + (size_t)k*f.planeStride + at, vbytes, &s_bar);
+					for(int k = 0; k < nVal; ++k)
+						bulkLoad(tile + (size_t)k*planeS, f.planes + (size_t)(kBase + k)*f.planeStride + at, vbytes, &s_bar);
 					bulkLoad(const_cast<unsigned char*>(mbase), f.maskPlane + at*MB, mbytes, &s_bar);
 				}
 				mbarWait(&s_bar, phase);
@@ -2294,7 +2658,8 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(DevFrame f, DevDisp
 		float a[7];
 #pragma unroll
 		for(int k = 0; k < 7; ++k) a[k] = sums[k*W + tid];
-		finishPixel(f, disp, x0 + tid, y, a, sums[7*W + tid], __float_as_int(sums[8*W + tid]));
+		if(kBase == 0) finishPixel(f, disp, x0 + tid, y, a, sums[7*W + tid], __float_as_int(sums[8*W + tid]));
+		else finishAovPixel(f, x0 + tid, y, a, nVal, kBase, sums[7*W + tid], __float_as_int(sums[8*W + tid]));
 	}
 }
 
@@ -2352,17 +2717,39 @@ cudaError_t launchBinScan(const DevFrame& f, cudaStream_t st)
 	k_bin_scan<<<1, 1024, 0, st>>>(f);
 	return cudaGetLastError();
 }
-cudaError_t launchBinFill(const DevFrame& f, cudaStream_t st)
+__global__ void __launch_bounds__(256) k_fill_keys(unsigned long long* keys, size_t n)
 {
-	if(f.nPos)
-		k_bin<true><<<(unsigned)((f.nPos + 255)/256), 256, 0, st>>>(f, 0, f.nPos);
+	const size_t i = (size_t)blockIdx.x*256 + threadIdx.x;
+	if(i < n) keys[i] = KEY_EMPTY;
+}
+cudaError_t launchFillKeys(unsigned long long* keys, size_t n, cudaStream_t st)
+{
+	if(n) k_fill_keys<<<(unsigned)((n + 255)/256), 256, 0, st>>>(keys, n);
+	return cudaGetLastError();
+}
+cudaError_t launchProject(const DevFrame& f, int64_t pA, int64_t pB, cudaStream_t st)
+{
+	if(pB <= pA) return cudaSuccess;
+	k_project<<<(unsigned)((pB - pA + 255)/256), 256, 0, st>>>(f, pA, pB);
+	return cudaGetLastError();
+}
+cudaError_t launchBinCount(const DevFrame& f, int64_t pA, int64_t pB, cudaStream_t st)
+{
+	if(pB <= pA) return cudaSuccess;
+	k_bin<false><<<(unsigned)((pB - pA + 255)/256), 256, 0, st>>>(f, pA, pB);
+	return cudaGetLastError();
+}
+cudaError_t launchBinFill(const DevFrame& f, int64_t pA, int64_t pB, cudaStream_t st)
+{
+	if(pB > pA)
+		k_bin<true><<<(unsigned)((pB - pA + 255)/256), 256, 0, st>>>(f, pA, pB);
 	if(f.nActiveTiles)
 	{
 		// function attributes are per device: set on every launch (a process may drive hiders on several GPUs)
 		cudaError_t e = cudaFuncSetAttribute(k_bin_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_MAX*8);
 		if(e != cudaSuccess) return e;
 		if(f.sortRun > SORT_MAX) return cudaErrorInvalidValue;
-		if(f.nPos) k_bin_sort<<<f.nActiveTiles, 256, (size_t)f.sortRun*8, st>>>(f, f.sortRun);
+		if(pB > pA) k_bin_sort<<<f.nActiveTiles, 256, (size_t)f.sortRun*8, st>>>(f, f.sortRun);
 		// only the deep pass reads the flags: frames without a non-opaque vertex (and with cullable hits) skip the scan
 		if(f.anyTransparent) k_tile_flags<<<f.nActiveTiles, 256, 0, st>>>(f);
 	}
@@ -2417,7 +2804,12 @@ cudaError_t launchHide(const DevFrame& f, const LaunchCfg& cfg, uint32_t slotBeg
 }
 
 // Filter + expose + quantise the output rows [yBeg, yEnd) (all of their footprint rows are in the sample planes).
+// One pass for the seven standard planes, then one per group of up to seven AOV floats.
 // uploadTable: the first launch of a frame loads the weight table into constant memory.
+int filterLaunchCount(const DevFrame& f)
+{
+	return (f.filterMode != AQH_FILTER_REFERENCE_ORDER) ? 1 : 1 + (f.aovFloats + 6)/7;
+}
 cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, const float* hostFilterTab, int yBeg, int yEnd, bool uploadTable, cudaStream_t st)
 {
 	const int w = f.cropX1 - f.cropX0, h = yEnd - yBeg;
@@ -2429,47 +2821,61 @@ cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, const float
 		return cudaGetLastError();
 	}
 	const int ntapw = (2*f.shiftX+1)*(2*f.shiftY+1)*f.n;
-	// span-staged kernel: tap bits fit the mask word (shift <= 7 always), weights in 64 KB of constant memory
-	if(ntapw <= 49*256)
+	const size_t spanSmem = filterSpansSmem(f);
+	const bool spans = ntapw <= 49*256 && spanSmem <= 113*1024;     // tap bits fit the mask word (shift <= 7 always), weights in 64 KB of constant memory
+	cudaError_t e = cudaSuccess;
+	if(spans && uploadTable) e = cudaMemcpyToSymbolAsync(c_filt, hostFilterTab, (size_t)ntapw*4, 0, cudaMemcpyHostToDevice, st);
+	if(e != cudaSuccess) return e;
+	for(int kBase = 0; kBase < 7 + f.aovFloats; kBase += 7)
 	{
-		const size_t smem = filterSpansSmem(f);
-		if(smem <= 113*1024)
+		const int nVal = kBase == 0 ? 7 : std::min(7, 7 + f.aovFloats - kBase);
+		if(spans)
 		{
-			cudaError_t e = cudaSuccess;
-			if(uploadTable) e = cudaMemcpyToSymbolAsync(c_filt, hostFilterTab, (size_t)ntapw*4, 0, cudaMemcpyHostToDevice, st);
-			if(e != cudaSuccess) return e;
 			dim3 grid((w + FILTER_W - 1)/FILTER_W, h);
 			if(f.maskBytes == 1)
 			{
-				e = cudaFuncSetAttribute(k_filter_spans<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+				e = cudaFuncSetAttribute(k_filter_spans<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spanSmem);
 				if(e != cudaSuccess) return e;
-				k_filter_spans<1><<<grid, 8*FILTER_W, smem, st>>>(f, disp, yBeg);
+				k_filter_spans<1><<<grid, 8*FILTER_W, spanSmem, st>>>(f, disp, yBeg, kBase, nVal);
 			}
 			else if(f.maskBytes == 2)
 			{
-				e = cudaFuncSetAttribute(k_filter_spans<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+				e = cudaFuncSetAttribute(k_filter_spans<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spanSmem);
 				if(e != cudaSuccess) return e;
-				k_filter_spans<2><<<grid, 8*FILTER_W, smem, st>>>(f, disp, yBeg);
+				k_filter_spans<2><<<grid, 8*FILTER_W, spanSmem, st>>>(f, disp, yBeg, kBase, nVal);
 			}
 			else
 			{
-				e = cudaFuncSetAttribute(k_filter_spans<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+				e = cudaFuncSetAttribute(k_filter_spans<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spanSmem);
 				if(e != cudaSuccess) return e;
-				k_filter_spans<4><<<grid, 8*FILTER_W, smem, st>>>(f, disp, yBeg);
+				k_filter_spans<4><<<grid, 8*FILTER_W, spanSmem, st>>>(f, disp, yBeg, kBase, nVal);
 			}
-			return cudaGetLastError();
 		}
-	}
-	dim3 block(32, 8), grid((w + 31)/32, (h + 7)/8);
-	size_t smem = (size_t)ntapw*sizeof(float);
-	const int inSmem = smem <= 200*1024 ? 1 : 0;
-	if(!inSmem) smem = 0;
-	if(smem > 48*1024)
-	{
-		cudaError_t e = cudaFuncSetAttribute(k_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		else
+		{
+			dim3 block(32, 8), grid((w + 31)/32, (h + 7)/8);
+			size_t smem = (size_t)ntapw*sizeof(float);
+			const int inSmem = smem <= 200*1024 ? 1 : 0;
+			if(!inSmem) smem = 0;
+			if(smem > 48*1024)
+			{
+				e = cudaFuncSetAttribute(k_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+				if(e != cudaSuccess) return e;
+			}
+			k_filter<<<grid, block, smem, st>>>(f, disp, inSmem, yBeg, yEnd, kBase, nVal);
+		}
+		e = cudaGetLastError();
 		if(e != cudaSuccess) return e;
 	}
-	k_filter<<<grid, block, smem, st>>>(f, disp, inSmem, yBeg, yEnd);
+	return cudaSuccess;
+}
+
+cudaError_t launchFinish(const DevFrame& f, const DevDisplays& disp, int expose, cudaStream_t st)
+{
+	const int w = f.cropX1 - f.cropX0, h = f.cropY1 - f.cropY0;
+	if(w <= 0 || h <= 0) return cudaSuccess;
+	dim3 block(32, 8), grid((w + 31)/32, (h + 7)/8);
+	k_finish<<<grid, block, 0, st>>>(f, disp, expose);
 	return cudaGetLastError();
 }
 

@@ -367,6 +367,9 @@ class Hider:
     def begin_frame(self, params: FrameParams):
         self.params = params
         self._check(self._L.aqh_begin_frame(self._h, C.byref(params)))
+        csg = getattr(params, "_csg", None)          # (types, parents) attached by the scene generators
+        if csg:
+            self.set_csg_tree(csg[0], csg[1])
 
     def add_grid(self, P, cu, cv, Ci=None, Oi=None, flags=abi.GRID_SMOOTH, key_times=None, culled=None, lod_bounds=None,
                  aov=None, Ng=None, N=None, radius=None, csg_node=-1):

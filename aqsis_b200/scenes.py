@@ -223,6 +223,141 @@ def config4(scale=1.0, seed=SEED + 3, layers=4, shard=None):
     return params, out
 
 
+def with_aovs(params, grids, aovs=(("N", 3), ("_depthcue", 1), ("_albedo", 3)), seed=SEED + 21, partial=False):
+    """Attach arbitrary output variables (RiDisplay "+name" -> CqRenderer::RegisterOutputData, renderer.cpp:1520-1546) to a
+    frame: per-vertex values as the shaders would leave them in the grid (StoreExtraData copies the value at the
+    micropolygon's index, bucketprocessor.cpp:1573-1643), one extra float32 display showing them."""
+    rng = np.random.default_rng(seed)
+    params.n_aovs = len(aovs)
+    nf = 0
+    for i, (name, n) in enumerate(aovs):
+        params.aov[i].name = name.encode()
+        params.aov[i].n_floats = n
+        nf += n
+    nv = grids.n_verts
+    P = np.asarray(grids.P)
+    a = rng.uniform(-1.0, 1.0, (nv, nf)).astype(np.float32)
+    a[:, 0] = (np.asarray(grids.Ci)[:, 0] * 2.0 - 1.0)           # something image-like in the first slot
+    grids.aov = np.ascontiguousarray(a)
+    # a float display of the first AOVs next to the rgba8 one (quantize one = 0: unquantised, ddmanager.cpp:1065)
+    d = params.display[params.n_displays]
+    d.n_channels = min(nf, 4)
+    for c in range(d.n_channels):
+        d.channel[c] = abi.NUM_CHANNELS + c
+    d.type = 0
+    d.quantize_zero = d.quantize_one = d.quantize_min = d.quantize_max = 0.0
+    d.quantize_dither = 0.0
+    params.n_displays += 1
+    return params, grids
+
+
+def csg_scene(scale=0.1, seed=SEED + 31, op="difference", nested=False):
+    """Two (nested: three) solids built from grid "shells" and combined by a CSG tree (RiSolidBegin "difference" ...):
+    every solid is a front and a back sheet (entry and exit wall) at different depths, overlapping on screen, plus plain
+    opaque and transparent grids around them.  The tree rides on params._csg = (types, parents)."""
+    xres, yres = max(32, int(640 * scale)), max(32, int(480 * scale))
+    rng = np.random.default_rng(seed)
+    params = default_params(resolution=(xres, yres), samples=(3, 3), filter=("gaussian", 2.0, 2.0), displays=[_RGBA8])
+    opn = {"union": abi.CSG_UNION, "intersection": abi.CSG_INTERSECTION, "difference": abi.CSG_DIFFERENCE}[op]
+    if nested:
+        # node 0: op(node 1 = union(prim 2, prim 3), prim 4)
+        types = [opn, abi.CSG_UNION, abi.CSG_PRIMITIVE, abi.CSG_PRIMITIVE, abi.CSG_PRIMITIVE]
+        parents = [-1, 0, 1, 1, 0]
+        prims = [2, 3, 4]
+    else:
+        types = [opn, abi.CSG_PRIMITIVE, abi.CSG_PRIMITIVE]
+        parents = [-1, 0, 0]
+        prims = [1, 2]
+    blocks, csg = [], []
+    cx, cy = 0.5 * xres, 0.5 * yres
+    # a small opaque patch in front of everything, submitted FIRST: what is stored behind an opaque hit that already
+    # exists is dropped at store time by the reference (bucketprocessor.cpp:1475-1480) unless it belongs to a CSG solid
+    P, Ci, Oi = _grids(rng, np.float32([[cx - 0.3 * xres, cy - 0.2 * yres]]), 0.25 * min(xres, yres), 8, 8, 5.0, 5.2)
+    blocks.append(_pack(P, Ci, Oi, 8, 8)); csg.append(-1)
+    for k, node in enumerate(prims):
+        ox = (k - (len(prims) - 1) / 2.0) * 0.22 * xres
+        size = 0.55 * min(xres, yres)
+        for wall, z in enumerate((10.0 + 2.0 * k, 20.0 + 3.0 * k)):          # entry wall, exit wall
+            centers = np.float32([[cx + ox, cy + (k % 2) * 0.08 * yres]])
+            P, Ci, Oi = _grids(rng, centers, size, 16, 16, z, z + 0.5, warp=0.03, noise=0.0, rot=False)
+            blocks.append(_pack(P, Ci, Oi, 16, 16, flags=abi.GRID_SMOOTH | abi.GRID_USES_CSG))
+            csg.append(node)
+    # a plain opaque backdrop behind and a transparent sheet in the middle of the solids
+    P, Ci, Oi = _grids(rng, np.float32([[cx, cy]]), 1.3 * max(xres, yres), 16, 16, 40.0, 41.0, warp=0.0, noise=0.0, rot=False)
+    blocks.append(_pack(P, Ci, Oi, 16, 16)); csg.append(-1)
+    P, Ci, Oi = _grids(rng, np.float32([[cx, cy]]), 0.7 * max(xres, yres), 16, 16, 15.0, 15.5, warp=0.02, noise=0.0, opacity=[0.4])
+    blocks.append(_pack(P, Ci, Oi, 16, 16)); csg.append(-1)
+    g = concat(blocks)
+    g.csg_node = np.asarray(csg, np.int32)
+    params._csg = (np.asarray(types, np.int32), np.asarray(parents, np.int32))
+    return params, g
+
+
+def points_scene(scale=0.15, seed=SEED + 41, n_points=4000, dof=False, transparent=True, res=None):
+    """RiPoints as the hider sees them (CqMicroPolyGridPoints, geometry/points.cpp): grids of up to 256 points, every point a
+    disc of its own raster radius with constant colour / opacity; over a backdrop of ordinary grids."""
+    xres, yres = res if res else (max(32, int(640 * scale)), max(32, int(480 * scale)))
+    rng = np.random.default_rng(seed)
+    kw = {}
+    if dof:
+        s_ = 0.5 * yres / math.tan(math.radians(20.0))
+        kw["dof"] = (2.8, 0.05, 20.0, s_, s_)
+    params = default_params(resolution=(xres, yres), samples=(4, 4), filter=("gaussian", 2.0, 2.0), displays=[_RGBA8], **kw)
+    G = 12
+    centers = np.stack([rng.uniform(0, xres, G), rng.uniform(0, yres, G)], axis=1).astype(np.float32)
+    P, Ci, Oi = _grids(rng, centers, 24.0, 8, 8, 30.0, 60.0)
+    back = _pack(P, Ci, Oi, 8, 8)
+    per = 250
+    ng = (n_points + per - 1) // per
+    cu = np.full(ng, per - 1, np.int32)
+    npts = ng * per
+    Pp = np.stack([rng.uniform(-2, xres + 2, npts), rng.uniform(-2, yres + 2, npts), rng.uniform(5.0, 70.0, npts)], axis=1).astype(np.float32)
+    rad = rng.uniform(0.15, 2.5, npts).astype(np.float32)
+    Cip = rng.uniform(0.1, 1.0, (npts, 3)).astype(np.float32)
+    Oip = np.ones((npts, 3), np.float32)
+    if transparent:
+        t = rng.uniform(size=npts) < 0.4
+        Oip[t] = rng.uniform(0.2, 0.9, (int(t.sum()), 1)).astype(np.float32)
+        Cip[t] *= Oip[t]
+    pts = GridArrays(cu=cu, cv=np.zeros(ng, np.int32), flags=np.full(ng, abi.GRID_POINTS, np.uint32), P=Pp, Ci=Cip, Oi=Oip)
+    g = concat([back, pts])
+    r = np.zeros(g.P.shape[0], np.float32)
+    r[back.P.shape[0]:] = rad
+    g.radius = r
+    return params, g
+
+
+def cull_scene(scale=0.12, seed=SEED + 51):
+    """Camera-space grids with geometric normals for the culls CqMicroPolyGrid::Shade applies before busting
+    (micropolygon.cpp:431-474 backfacing, :493-522 fully transparent): half of the grids face away, some end in a run of
+    Oi = 0 vertices."""
+    p, g = to_camera_space(*config1(scale=scale, seed=seed))
+    rng = np.random.default_rng(seed + 1)
+    nv = 81
+    G = g.n_grids
+    Pc = np.asarray(g.P).reshape(G, nv, 3)
+    # normals: towards the camera (-P direction) for even grids, away for odd ones, jittered so that the sign varies inside a grid
+    Ng = -Pc / np.linalg.norm(Pc, axis=2, keepdims=True)
+    Ng = Ng + rng.normal(0, 0.8, Ng.shape)
+    Ng[1::2] *= -1.0
+    g.Ng = np.ascontiguousarray(Ng.reshape(-1, 3).astype(np.float32))
+    N = Ng.copy()
+    N[::3] *= -1.0                                                  # a user normal on the other side flips Ng's facing
+    g.N = np.ascontiguousarray(N.reshape(-1, 3).astype(np.float32))
+    Oi = np.asarray(g.Oi).reshape(G, nv, 3).copy()
+    Ci = np.asarray(g.Ci).reshape(G, nv, 3).copy()
+    tail = rng.integers(0, nv, G)
+    for i in range(0, G, 4):
+        Oi[i, tail[i]:] = 0.0                                       # trailing run of fully transparent vertices
+        Ci[i, tail[i]:] = 0.0
+        if tail[i] > 10:
+            Oi[i, 3] = 0.0                                          # an isolated one in the middle must survive (the loop breaks)
+    g.Oi = np.ascontiguousarray(Oi.reshape(-1, 3))
+    g.Ci = np.ascontiguousarray(Ci.reshape(-1, 3))
+    g.flags = (g.flags | np.uint32(abi.GRID_CULL_BACKFACING | abi.GRID_CULL_TRANSPARENT)).astype(np.uint32)
+    return p, g
+
+
 def config5_filters():
     """The PixelFilter sweep of config 5: (name, width) pairs run on the config-2 scene."""
     return [(name, float(w)) for name in ("box", "triangle", "gaussian", "catmull-rom", "sinc") for w in range(1, 7)]

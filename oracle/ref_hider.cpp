@@ -58,6 +58,7 @@
 #include "attributes.h"
 #include "stats.h"
 #include "iddmanager.h"
+#include "csgtree.h"
 
 #include <chrono>
 #include <cstdio>
@@ -118,6 +119,17 @@ void CqRenderer::Initialise()
 	m_DofMultiplier = p.dof_multiplier;
 	m_OneOverFocalDistance = p.dof_one_over_focal_distance;
 	m_DepthOfFieldScale = CqVector2D(p.dof_scale_x, p.dof_scale_y);
+	// what CqRenderer::RegisterOutputData leaves behind for every AOV of a RiDisplay (renderer.cpp:1520-1546; the token
+	// dictionary that derives the float count from the declaration is the front end's: the ABI carries the count)
+	for(int a = 0; a < p.n_aovs; ++a)
+	{
+		SqOutputDataEntry e;
+		e.m_Offset = m_OutputDataOffset;
+		e.m_NumSamples = p.aov[a].n_floats;
+		m_OutputDataOffset += e.m_NumSamples;
+		m_OutputDataTotalSize += e.m_NumSamples;
+		m_OutputDataEntries[std::string(p.aov[a].name)] = e;
+	}
 }
 const IqOptionsPtr CqRenderer::poptCurrent() const { return m_poptDefault; }
 TqFloat CqRenderer::Time() const { return 0; }
@@ -134,10 +146,18 @@ const TqFloat CqRenderer::MinCoCForBound(const CqBound& bound) const
 	TqFloat minBlur = min(std::fabs(1/z1 - m_OneOverFocalDistance), std::fabs(1/z2 - m_OneOverFocalDistance));
 	return m_DofMultiplier * min(m_DepthOfFieldScale.x(), m_DepthOfFieldScale.y()) * minBlur;
 }
-// no arbitrary output variables on this path (StoreExtraData, bucketprocessor.cpp:1573-1643, is a "next" row)
-TqInt CqRenderer::RegisterOutputData(const char*) { return -1; }
-TqInt CqRenderer::OutputDataIndex(const char*) { return -1; }
-TqInt CqRenderer::OutputDataSamples(const char*) { return 0; }
+// renderer.cpp:1549-1567 (restated: renderer.cpp is not part of this build); registration happens in Initialise() above
+TqInt CqRenderer::RegisterOutputData(const char* name) { return OutputDataIndex(name); }
+TqInt CqRenderer::OutputDataIndex(const char* name)
+{
+	std::map<std::string, SqOutputDataEntry>::const_iterator i = m_OutputDataEntries.find(name);
+	return i == m_OutputDataEntries.end() ? -1 : i->second.m_Offset;
+}
+TqInt CqRenderer::OutputDataSamples(const char* name)
+{
+	std::map<std::string, SqOutputDataEntry>::const_iterator i = m_OutputDataEntries.find(name);
+	return i == m_OutputDataEntries.end() ? 0 : i->second.m_NumSamples;
+}
 #include "renderer_stubs.inc"
 
 } // namespace Aqsis
@@ -190,6 +210,30 @@ private:
 	float* m_data;
 };
 
+// One arbitrary output variable of a grid: what FindStandardVar(name) hands StoreExtraData (bucketprocessor.cpp:1573-1643).
+// The caller's array is vertex-major with all AOV floats of a vertex side by side.
+class RefAovData : public RefShaderData
+{
+public:
+	RefAovData(const float* data, int stride, int offset, int nFloats)
+		: RefShaderData(0), m_aov(data), m_stride(stride), m_offset(offset), m_n(nFloats) {}
+	virtual EqVariableType Type() const { return m_n == 1 ? type_float : (m_n == 3 ? type_color : type_matrix); }
+	virtual void GetFloat(TqFloat& res, TqInt index = 0) const { res = at(index)[0]; }
+	virtual void GetColor(CqColor& res, TqInt index = 0) const { const float* v = at(index); res = CqColor(v[0], v[1], v[2]); }
+	virtual void GetPoint(CqVector3D& res, TqInt index = 0) const { const float* v = at(index); res = CqVector3D(v[0], v[1], v[2]); }
+	virtual void GetMatrix(CqMatrix& res, TqInt index = 0) const
+	{
+		TqFloat m[16];
+		for(int i = 0; i < 16; ++i) m[i] = at(index)[i];
+		res = CqMatrix(m);
+		res.SetfIdentity(false);
+	}
+private:
+	const float* at(TqInt index) const { return m_aov + size_t(index)*m_stride + m_offset; }
+	const float* m_aov;
+	int m_stride, m_offset, m_n;
+};
+
 // ---------------------------------------------------------------------------------------
 // One shaded grid as the hider sees it.
 class RefGrid : public CqMicroPolyGridBase
@@ -204,7 +248,7 @@ public:
 		m_CurrentGridInfo.lodBounds = m_lod;
 		m_CurrentGridInfo.matteFlag = (flags & AQH_GRID_MATTE_ALPHA) ? SqImageSample::Flag_MatteAlpha
 		                              : ((flags & AQH_GRID_MATTE) ? SqImageSample::Flag_Matte : 0);
-		m_CurrentGridInfo.usesDataMap = false;
+		m_CurrentGridInfo.usesDataMap = !(QGetRenderContext()->GetMapOfOutputDataEntries().empty());   // micropolygon.cpp:61-62
 		m_CurrentGridInfo.useSmoothShading = (flags & AQH_GRID_SMOOTH) != 0;
 	}
 	virtual void Split(long, long, long, long) {}
@@ -213,8 +257,14 @@ public:
 	virtual void DeleteVariables(bool) {}
 	virtual CqSurface* pSurface() const { return 0; }
 	virtual const IqConstAttributesPtr pAttributes() const { return IqConstAttributesPtr(); }
-	virtual bool usesCSG() const { return false; }
-	virtual boost::shared_ptr<CqCSGTreeNode> pCSGNode() const { return boost::shared_ptr<CqCSGTreeNode>(); }
+	virtual bool usesCSG() const { return m_csg.get() != 0; }
+	virtual boost::shared_ptr<CqCSGTreeNode> pCSGNode() const { return m_csg; }
+	void setCSGNode(const boost::shared_ptr<CqCSGTreeNode>& n) { m_csg = n; }
+	void addAov(const std::string& name, const float* data, int stride, int offset, int nFloats)
+	{
+		m_aovs.push_back(std::make_pair(name, new RefAovData(data, stride, offset, nFloats)));
+	}
+	virtual ~RefGrid() { for(size_t i = 0; i < m_aovs.size(); ++i) delete m_aovs[i].second; }
 	virtual TqInt uGridRes() const { return m_cu; }
 	virtual TqInt vGridRes() const { return m_cv; }
 	virtual TqUint numMicroPolygons(TqInt cu, TqInt cv) const { return cu*cv; }
@@ -230,7 +280,11 @@ public:
 			default: return 0;
 		}
 	}
-	virtual IqShaderData* FindStandardVar(const char*) { return 0; }
+	virtual IqShaderData* FindStandardVar(const char* name)
+	{
+		for(size_t i = 0; i < m_aovs.size(); ++i) if(m_aovs[i].first == name) return m_aovs[i].second;
+		return 0;
+	}
 	virtual boost::shared_ptr<IqShaderExecEnv> pShaderExecEnv() { return boost::shared_ptr<IqShaderExecEnv>(); }
 	void addSplitLine(TqFloat time, const CqVector3D& a, const CqVector3D& b)
 	{
@@ -248,7 +302,12 @@ private:
 	int m_cu, m_cv;
 	Var m_P, m_Ci, m_Oi;
 	float m_lod[2];
+	boost::shared_ptr<CqCSGTreeNode> m_csg;
+	std::vector<std::pair<std::string, RefAovData*> > m_aovs;
 };
+
+// The frame's CSG tree (ref_set_csg_tree): real CqCSGTreeNode objects, children attached in node-index order.
+std::vector<boost::shared_ptr<CqCSGTreeNode> > g_csgNodes;
 
 // ---------------------------------------------------------------------------------------
 // Display manager: captures buckets.  Quantisation restates FormatBucketForDisplay
@@ -323,20 +382,24 @@ public:
 		int idx[5];
 		for(int i = 0; i < 5; ++i) idx[i] = pBuffer->getChannelIndex(names[i]);
 		const int w = pBuffer->width(), h = pBuffer->height();
-		std::vector<float> px(size_t(w)*h*9);
+		int nch = 9, aovIdx[AQH_MAX_AOVS];
+		for(int a = 0; a < m_p.n_aovs; ++a) { aovIdx[a] = pBuffer->getChannelIndex(m_p.aov[a].name); nch += m_p.aov[a].n_floats; }
+		std::vector<float> px(size_t(w)*h*nch);
 		for(int y = 0; y < h; ++y)
 			for(int x = 0; x < w; ++x)
 			{
-				float* o = &px[(size_t(y)*w + x)*9];
+				float* o = &px[(size_t(y)*w + x)*nch];
 				const float* ci = (*pBuffer)(x, y, idx[0]);
 				const float* oi = (*pBuffer)(x, y, idx[1]);
 				o[0] = ci[0]; o[1] = ci[1]; o[2] = ci[2]; o[3] = oi[0]; o[4] = oi[1]; o[5] = oi[2];
 				o[6] = (*pBuffer)(x, y, idx[2])[0];
 				o[7] = (*pBuffer)(x, y, idx[3])[0];
 				o[8] = (*pBuffer)(x, y, idx[4])[0];
+				for(int a = 0, at = 9; a < m_p.n_aovs; at += m_p.aov[a].n_floats, ++a)
+					for(int k = 0; k < m_p.aov[a].n_floats; ++k) o[at + k] = (*pBuffer)(x, y, aovIdx[a])[k];
 				const int X = DRegion.xMin() + x, Y = DRegion.yMin() + y;
 				if(m_channels && X < m_p.xres && Y < m_p.yres)
-					std::memcpy(m_channels + (size_t(Y)*m_p.xres + X)*9, o, 36);
+					std::memcpy(m_channels + (size_t(Y)*m_p.xres + X)*nch, o, size_t(nch)*4);
 			}
 		CqRandom random;
 		for(int d = 0; d < m_p.n_displays; ++d)
@@ -351,7 +414,7 @@ public:
 					if(!pdata) continue;
 					for(int c = 0; c < dd.n_channels; ++c)
 					{
-						double value = px[(size_t(y)*w + x)*9 + dd.channel[c]];
+						double value = px[(size_t(y)*w + x)*nch + dd.channel[c]];
 						if(dd.quantize_one != 0)
 						{
 							value = Aqsis::lround(dd.quantize_zero + value * (dd.quantize_one - dd.quantize_zero) + (dd.quantize_dither * s));
@@ -442,12 +505,14 @@ int ref_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* chann
 	std::vector<std::vector<float> > owned;       // projected copies of P (the caller's arrays are const)
 	size_t po = 0, vo = 0, ko = 0;
 	int64_t nmp = 0;
+	int aovFloats = 0;
+	for(int a = 0; a < p.n_aovs; ++a) aovFloats += p.aov[a].n_floats;
 	for(int64_t g = 0; g < grids->n_grids; ++g)
 	{
 		const int cu = grids->cu[g], cv = grids->cv[g];
 		const int nk = grids->nkeys ? grids->nkeys[g] : 1;
 		const uint32_t flags = grids->flags[g];
-		if(flags & AQH_GRID_USES_CSG) return AQH_ERR_UNSUPPORTED;
+		if(flags & AQH_GRID_POINTS) return AQH_ERR_UNSUPPORTED;      // geometry/points.cpp needs the whole CqSurface family: restated in the oracle only
 		const size_t nv = size_t(cu+1)*(cv+1);
 		owned.push_back(std::vector<float>(grids->P + po*3, grids->P + (po + nv*nk)*3));
 		float* P = owned.back().data();
@@ -469,6 +534,49 @@ int ref_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* chann
 		RefGrid* grid = new RefGrid(cu, cv, P, Ci, Oi, flags, grids->lod_bounds ? grids->lod_bounds + 2*g : 0);
 		ADDREF(grid);
 		keep.push_back(grid);
+		if(flags & AQH_GRID_USES_CSG)
+		{
+			const int node = grids->csg_node ? grids->csg_node[g] : -1;
+			if(node < 0 || node >= (int)g_csgNodes.size()) return AQH_ERR_BAD_PARAMS;
+			grid->setCSGNode(g_csgNodes[node]);
+		}
+		if(aovFloats && grids->aov)
+			for(int a = 0, at = 0; a < p.n_aovs; at += p.aov[a].n_floats, ++a)
+				grid->addAov(p.aov[a].name, grids->aov + vo*aovFloats, aovFloats, at, p.aov[a].n_floats);
+		// the culls CqMicroPolyGrid::Shade applies before the grid reaches Split (micropolygon.cpp:431-474, 493-522),
+		// restated: Shade() itself needs the shader VM
+		std::vector<unsigned char> culledAll;
+		if(flags & (AQH_GRID_CULL_BACKFACING | AQH_GRID_CULL_TRANSPARENT))
+		{
+			culledAll.assign(nv, 0);
+			if(grids->culled) for(size_t i = 0; i < nv; ++i) culledAll[i] = grids->culled[vo + i];
+			if((flags & AQH_GRID_CULL_BACKFACING) && grids->Ng && !(flags & AQH_GRID_USES_CSG))
+			{
+				const CqVector3D* pP = reinterpret_cast<const CqVector3D*>(grids->P + po*3);     // camera space, the shaded key
+				const CqVector3D* pNg = reinterpret_cast<const CqVector3D*>(grids->Ng + vo*3);
+				const CqVector3D* pN = grids->N ? reinterpret_cast<const CqVector3D*>(grids->N + vo*3) : 0;
+				for(TqInt i = TqInt(nv) - 1; i >= 0; i--)
+				{
+					TqFloat s = 1.0f;
+					if(NULL != pN)
+						s = ((pN[i] * pNg[i]) < 0.0f) ? -1.0f : 1.0f;
+					if(((s * pNg[i]) * pP[i]) >= 0)
+						culledAll[i] = 1;
+				}
+			}
+			const CqColor zThr(p.zthreshold[0], p.zthreshold[1], p.zthreshold[2]);
+			if((flags & AQH_GRID_CULL_TRANSPARENT) && grids->Oi && !(zThr == gColBlack))
+			{
+				const CqColor* pOi = reinterpret_cast<const CqColor*>(grids->Oi + vo*3);
+				for(TqInt i = TqInt(nv) - 1; i >= 0; i--)
+				{
+					if(pOi[i] == gColBlack)
+						culledAll[i] = 1;
+					else
+						break;
+				}
+			}
+		}
 		// triangle split line per key, micropolygon.cpp:733-749
 		for(int k = 0; k < nk; ++k)
 		{
@@ -487,7 +595,7 @@ int ref_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* chann
 			for(int iu = 0; iu < cu; ++iu)
 			{
 				const int iIndex = iv*(cu+1) + iu;
-				if(grids->culled && grids->culled[vo + iIndex]) continue;
+				if(culledAll.empty() ? (grids->culled && grids->culled[vo + iIndex]) : culledAll[iIndex] != 0) continue;
 				++nmp;
 				if(nk > 1)
 				{
@@ -541,6 +649,25 @@ int ref_set_filter(const char* name)
 	for(const RefFilter& rf : kRefFilters)
 		if(std::strcmp(rf.name, name) == 0) { g_forcedFilter = rf.fn; return AQH_OK; }
 	return AQH_ERR_BAD_PARAMS;
+}
+
+// The CSG tree of the following ref_render calls, built from real CqCSGTreeNode objects (csgtree.cpp): type[i] is an
+// AQH_CSG_* value, parent[i] the parent node or -1; children are attached in node-index order.  0 nodes = none.
+int ref_set_csg_tree(int n_nodes, const int32_t* type, const int32_t* parent)
+{
+	g_csgNodes.clear();
+	CqCSGTreeNode::SetRequired(false);
+	if(n_nodes <= 0) return AQH_OK;
+	static const char* const names[4] = {"primitive", "union", "intersection", "difference"};
+	for(int i = 0; i < n_nodes; ++i)
+	{
+		if(type[i] < 0 || type[i] > 3 || parent[i] >= n_nodes || parent[i] == i) { g_csgNodes.clear(); return AQH_ERR_BAD_PARAMS; }
+		CqString t(names[type[i]]);
+		g_csgNodes.push_back(CqCSGTreeNode::CreateNode(t));
+	}
+	for(int i = 0; i < n_nodes; ++i)
+		if(parent[i] >= 0) g_csgNodes[parent[i]]->AddChild(g_csgNodes[i]);
+	return AQH_OK;
 }
 
 // What aqsis' occlusion culling would do with surfaces of the given raster bounds (xmin, ymin, zmin, xmax, ymax, zmax)

@@ -15,6 +15,17 @@ from aqsis_b200._abi import FrameParams, GridBlock, DisplayDesc
 FILTER_INDEX = {"box": 0, "triangle": 1, "gaussian": 2, "catmull-rom": 3, "sinc": 4, "mitchell": 5, "disk": 6, "bessel": 7}
 
 
+def _csg_arrays(params):
+    """(n, types, parents) of the frame's CSG tree: carried on the python parameter object as params._csg = (types, parents)
+    (the C struct has no room for it: the product takes it through aqh_set_csg_tree)."""
+    csg = getattr(params, "_csg", None)
+    if not csg:
+        return 0, None, None
+    t = np.ascontiguousarray(csg[0], np.int32)
+    pa = np.ascontiguousarray(csg[1], np.int32)
+    return len(t), t, pa
+
+
 def _filter_name_of(params):
     """The pixel filter to select by NAME: only when the frame carries no function pointer (pure-python parameter
     blocks of bench.py --impl reference); otherwise the checkers recognise the function behind the pointer."""
@@ -80,6 +91,7 @@ def lib():
         L.orc_dof_bounds.restype = None
         L.orc_set_filter.argtypes = [ci]
         L.orc_set_filter.restype = None
+        L.orc_set_csg_tree.argtypes = [ci, vp, vp]
         _lib = L
     return _lib
 
@@ -131,7 +143,7 @@ def render(params: FrameParams, grids, nthreads=1):
     L = lib()
     b = grids.as_struct()
     assert b.memory_space == 0
-    ch = np.zeros((params.yres, params.xres, 9), dtype=np.float32)
+    ch = np.zeros((params.yres, params.xres, 9 + params.aov_floats), dtype=np.float32)
     outs, ptrs = [], (C.c_void_p * max(1, params.n_displays))()
     for d in range(params.n_displays):
         dt, nch, es = display_info(params, d)
@@ -141,8 +153,11 @@ def render(params: FrameParams, grids, nthreads=1):
     st = OrcStats()
     name = _filter_name_of(params)
     L.orc_set_filter(FILTER_INDEX[name] if name else -1)
+    n, t, pa = _csg_arrays(params)
+    L.orc_set_csg_tree(n, t.ctypes.data if n else None, pa.ctypes.data if n else None)
     rc = L.orc_render(C.byref(params), C.byref(b), ch.ctypes.data, ptrs, int(nthreads), C.byref(st))
     L.orc_set_filter(-1)
+    L.orc_set_csg_tree(0, None, None)
     if rc:
         raise RuntimeError(f"orc_render failed: {abi.STATUS_NAMES.get(rc, rc)}")
     return ch, outs, st.as_dict()
@@ -159,6 +174,7 @@ def refhider():
         L = C.CDLL(REFHIDER_LIB)
         L.ref_render.argtypes = [C.POINTER(FrameParams), C.POINTER(GridBlock), C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(OrcStats)]
         L.ref_set_filter.argtypes = [C.c_char_p]
+        L.ref_set_csg_tree.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         L.ref_can_cull.argtypes = [C.POINTER(FrameParams), C.POINTER(GridBlock), C.c_int, C.c_void_p, C.c_void_p]
         _refhider = L
     return _refhider
@@ -171,7 +187,7 @@ def render_reference(params: FrameParams, grids):
     if L is None:
         raise RuntimeError("oracle/_ref/libaqsis_refhider.so is not available")
     b = grids.as_struct()
-    ch = np.zeros((params.yres, params.xres, 9), dtype=np.float32)
+    ch = np.zeros((params.yres, params.xres, 9 + params.aov_floats), dtype=np.float32)
     outs, ptrs = [], (C.c_void_p * max(1, params.n_displays))()
     for d in range(params.n_displays):
         dt, nch, es = display_info(params, d)
@@ -181,8 +197,11 @@ def render_reference(params: FrameParams, grids):
     st = OrcStats()
     name = _filter_name_of(params)
     L.ref_set_filter(name.encode() if name else None)
+    n, t, pa = _csg_arrays(params)
+    L.ref_set_csg_tree(n, t.ctypes.data if n else None, pa.ctypes.data if n else None)
     rc = L.ref_render(C.byref(params), C.byref(b), ch.ctypes.data, ptrs, C.byref(st))
     L.ref_set_filter(None)
+    L.ref_set_csg_tree(0, None, None)
     if rc:
         raise RuntimeError(f"ref_render failed: {abi.STATUS_NAMES.get(rc, rc)}")
     return ch, outs, st.as_dict()

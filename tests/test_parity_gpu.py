@@ -374,10 +374,14 @@ def test_errors_are_statuses_not_crashes(gpu_hider):
     gpu_hider.begin_frame(p)
     from test_oracle_render import one_grid
     g = one_grid([1, 5], [1, 5])
-    g.flags[:] = abi.GRID_USES_CSG
+    g.flags[:] = abi.GRID_USES_CSG                  # a CSG grid without a tree / node
     with pytest.raises(HiderError) as e:
         gpu_hider.add_grid_block(g)
-    assert e.value.status == abi.AQH_ERR_UNSUPPORTED
+    assert e.value.status == abi.AQH_ERR_BAD_PARAMS
+    g.flags[:] = abi.GRID_POINTS                    # points need cv = 0 and radii
+    with pytest.raises(HiderError) as e:
+        gpu_hider.add_grid_block(g)
+    assert e.value.status == abi.AQH_ERR_BAD_PARAMS
     gpu_hider.end_frame()
     with pytest.raises(HiderError) as e:
         gpu_hider.add_grid_block(g)

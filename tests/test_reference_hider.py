@@ -83,6 +83,23 @@ for _s in [(1, 1), (2, 3), (5, 5), (16, 16)]:
     CASES[f"samples-{_s[0]}x{_s[1]}"] = (lambda s=_s: scenes.config2(scale=0.03, samples=s, filter=("gaussian", 2.0, 2.0)))
 
 
+# arbitrary output variables through aqsis' own StoreExtraData / FilterBucket (bucketprocessor.cpp:1573-1643, 620-653)
+CASES["aov-static"] = lambda: scenes.with_aovs(*scenes.config1(scale=0.2))
+CASES["aov-deep"] = lambda: scenes.with_aovs(*scenes.config4(scale=0.02))
+CASES["aov-mbdof"] = lambda: scenes.with_aovs(*scenes.config3(scale=0.04, motion_px=6.0))
+CASES["aov-matrix"] = lambda: scenes.with_aovs(*scenes.config1(scale=0.12), aovs=(("N", 3), ("M", 16), ("s", 1), ("t", 1)))
+# CSG solids through aqsis' own CqCSGTreeNode objects (csgtree.cpp:144-351)
+for _op in ("difference", "union", "intersection"):
+    for _nested in (False, True):
+        CASES[f"csg-{_op}{'-nested' if _nested else ''}"] = (lambda op=_op, nested=_nested: scenes.csg_scene(op=op, nested=nested))
+CASES["csg-midpoint-rgbaz"] = lambda: _mod(scenes.csg_scene(op="difference", nested=True),
+                                            lambda p: _set(p, depth_filter=abi.DEPTHFILTER_MIDPOINT, display_mode=abi.DMODE_RGB | abi.DMODE_A | abi.DMODE_Z))
+CASES["csg-average-rgbaz"] = lambda: _mod(scenes.csg_scene(op="difference", nested=True),
+                                           lambda p: _set(p, depth_filter=abi.DEPTHFILTER_AVERAGE, display_mode=abi.DMODE_RGB | abi.DMODE_A | abi.DMODE_Z))
+# the backface / transparency culls of CqMicroPolyGrid::Shade (restated with aqsis' vector and colour classes in the wrapper)
+CASES["culls"] = lambda: scenes.cull_scene()
+
+
 def assert_identical(p, ch_r, d_r, ch_o, d_o, what):
     ys, xs = slice(p.crop_ymin, p.crop_ymax), slice(p.crop_xmin, p.crop_xmax)
     a, b = ch_r[ys, xs].view(np.uint32), ch_o[ys, xs].view(np.uint32)
