@@ -376,8 +376,11 @@ __global__ void __launch_bounds__(256) k_bin_sort(DevFrame f, int sortMax)
 // ------------------------------------------------------------------------------------
 // Micropolygon hit-test pieces.
 
-// CqMicroPolygon::ComputeVertexOrder, micropolygon.cpp:1207-1284.  Vertices in natural
-// order P0=index, P1=index+1, P2=index+cu+1, P3=index+cu+2 (codes A=0, B=1, C=3, D=2).
+// Vertex order of a micropolygon (what CqMicroPolygon::ComputeVertexOrder decides, micropolygon.cpp:1207-1284): which
+// corner to drop when an edge of the loop  slot 0 -> 1 -> 3 -> 2 -> 0  has collapsed (squared length, z included, below
+// 1e-8), and in which direction to walk the remaining corners so that the edge tests see a consistent winding.  Returns
+// the packed code the reference keeps in m_IndexCode: two bits per corner slot, first corner in bits 0-1, plus
+// DEGENERACY_MASK for triangles.
 __device__ __forceinline__ float mag2d3(const float4& a, const float4& b)
 {
 	float dx = a.x-b.x, dy = a.y-b.y, dz = a.z-b.z;
@@ -386,27 +389,23 @@ __device__ __forceinline__ float mag2d3(const float4& a, const float4& b)
 #define DEGENERACY_MASK 0x8000000
 __device__ int computeVertexOrder(const float4 P[4])
 {
-	// IndexA..D -> natural slots 0,1,3,2
-	int iA = 0, iB = 1, iC = 3, iD = 2;
-	int CodeA = 0, CodeB = 1, CodeC = 3, CodeD = 2;
-	if((double)mag2d3(P[iA], P[iB]) < 1e-8)
-	{ iB = iC; CodeB = CodeC; iC = iD; CodeC = CodeD; iD = -1; CodeD = -1; }
-	else if((double)mag2d3(P[iB], P[iC]) < 1e-8)
-	{ iB = iC; CodeB = CodeC; iC = iD; CodeC = CodeD; iD = -1; CodeD = -1; }
-	else if((double)mag2d3(P[iC], P[iD]) < 1e-8)
-	{ iC = iD; CodeC = CodeD; iD = -1; CodeD = -1; }
-	else if((double)mag2d3(P[iD], P[iA]) < 1e-8)
-	{ iD = -1; CodeD = -1; }
-	const float4 vA = P[iA], vB = P[iB], vC = P[iC];
-	bool fFlip = ((vA.x - vB.x)*(vB.y - vC.y)) >= ((vA.y - vB.y)*(vB.x - vC.x));
-	int code;
-	if(!fFlip)
-		code = (CodeD == -1) ? ((CodeA & 3) | ((CodeC & 3) << 2) | ((CodeB & 3) << 4) | DEGENERACY_MASK)
-		                     : ((CodeA & 3) | ((CodeD & 3) << 2) | ((CodeC & 3) << 4) | ((CodeB & 3) << 6));
-	else
-		code = (CodeD == -1) ? ((CodeA & 3) | ((CodeB & 3) << 2) | ((CodeC & 3) << 4) | DEGENERACY_MASK)
-		                     : ((CodeA & 3) | ((CodeB & 3) << 2) | ((CodeC & 3) << 4) | ((CodeD & 3) << 6));
-	return code;
+	// (double)m < 1e-8 for a float m  <=>  m <= the largest float below 1e-8 (no double arithmetic needed)
+	const float tiny = 9.99999993922529029e-9f;
+	// corner sequences, one nibble per position (0xF = none): the full loop, or the loop without the corner that
+	// coincides with its predecessor -- edges 0-1 and 1-3 both leave {0,3,2}, edge 3-2 leaves {0,1,2}, edge 2-0 leaves {0,1,3}
+	uint32_t seq = 0x2310u;
+	if(mag2d3(P[0], P[1]) <= tiny) seq = 0xF230u;
+	else if(mag2d3(P[1], P[3]) <= tiny) seq = 0xF230u;
+	else if(mag2d3(P[3], P[2]) <= tiny) seq = 0xF210u;
+	else if(mag2d3(P[2], P[0]) <= tiny) seq = 0xF310u;
+	const int s0 = seq & 3, s1 = (seq >> 4) & 3, s2 = (seq >> 8) & 3;
+	const bool triangle = (seq >> 12) == 0xFu;
+	const int s3 = (seq >> 12) & 3;
+	const float4 v0 = P[s0], v1 = P[s1], v2 = P[s2];
+	const bool forward = ((v0.x - v1.x)*(v1.y - v2.y)) >= ((v0.y - v1.y)*(v1.x - v2.x));
+	if(triangle)
+		return (forward ? (s0 | (s1 << 2) | (s2 << 4)) : (s0 | (s2 << 2) | (s1 << 4))) | DEGENERACY_MASK;
+	return forward ? (s0 | (s1 << 2) | (s2 << 4) | (s3 << 6)) : (s0 | (s3 << 2) | (s2 << 4) | (s1 << 6));
 }
 
 // The hit-test cache of one micropolygon at one instant: CqHitTestCache minus the DoF

@@ -5,7 +5,7 @@
 // then drives the device filter kernel.  Precision matters for bit parity of the table,
 // so each function states where the reference evaluates in double: its C math calls
 // resolve to the ::f(double) overloads (probed against the in-place compiled reference,
-// tests/test_host_sampling.py::test_filters_match_reference).
+// tests/test_oracle_leaves.py (filter values against tests/golden/ref_leaves.npz, generated from libs/core/filters.cpp)).
 #include "../../include/aqsis_b200_hider.h"
 
 #include <cmath>

@@ -36,86 +36,60 @@ void Random::refill()
 }
 
 // ---------------------------------------------------------------------------
-// CqMultiJitteredSampler::multiJitterIndices + setupJitterPattern,
-// libs/core/multijitter.cpp:83-202.
+// One cached pattern of n = xs*ys samples: multi-jittered 2-D positions, a stratified 1-D value per sample and a
+// permutation of the sample indices.  The ARITHMETIC and the order of the random draws are fixed by the reference
+// (CqMultiJitteredSampler, libs/core/multijitter.cpp:83-202) -- the stream is shared with everything else the renderer
+// draws, so one draw out of place changes every later pattern; the known-answer tests pin both.
+
+// Descending Fisher-Yates over `count` elements `stride` apart: for k = count .. 2 draw j in [0, k) and exchange
+// elements k-1 and j.  This is the one shuffle the reference uses everywhere (:104-127, :195-201).
+template<class T> static void shuffleDown(Random& rng, T* first, int count, int stride)
+{
+	for(int k = count; k > 1; --k)
+	{
+		const int j = static_cast<int>(rng.nextInt(static_cast<uint32_t>(k)));
+		std::swap(first[size_t(k - 1)*stride], first[size_t(j)*stride]);
+	}
+}
+
 static void jitterPattern(Random& rng, int xs, int ys, float* pos, float* val1d, int32_t* shuffled)
 {
 	const int n = xs*ys;
-	if(xs == 1 && ys == 1)
+	if(n == 1)
 	{
-		// CqVector2D(RandomFloat(), RandomFloat()): g++ evaluates the arguments right
-		// to left, so the y component takes the first draw (checked against the
-		// in-place compiled reference in tests/test_host_sampling.py).
-		float y = rng.nextFloat();
-		float x = rng.nextFloat();
+		// a 2-D point takes two draws, y first (the reference builds CqVector2D(RandomFloat(), RandomFloat()) and g++
+		// evaluates arguments right to left), then one draw for the 1-D value that the code below overwrites
+		const float y = rng.nextFloat(), x = rng.nextFloat();
 		pos[0] = x; pos[1] = y;
-		val1d[0] = rng.nextFloat();   // overwritten below, but the draw is consumed
+		(void)rng.nextFloat();
 	}
 	else
 	{
-		std::vector<int> idx(2*n);
+		// Sub-pixel (ix, iy) starts in sub-cell (iy, ix) of its own sub-pixel -- the canonical multi-jitter layout where
+		// the n x n fine grid has exactly one sample per fine row and per fine column.  Shuffling the fine-x cells among
+		// the sub-pixels of a row, then the fine-y cells among those of a column, keeps that property.
+		std::vector<int> fineX(n), fineY(n);
 		for(int iy = 0; iy < ys; ++iy)
-			for(int ix = 0; ix < xs; ++ix)
-			{
-				int which = 2*(iy*xs + ix);
-				idx[which] = iy;
-				idx[which+1] = ix;
-			}
-		// Fisher-Yates on the y sub-cell coordinate within each row of sub-pixels...
-		for(int iy = 0; iy < ys; ++iy)
+			for(int ix = 0; ix < xs; ++ix) { fineX[iy*xs + ix] = iy; fineY[iy*xs + ix] = ix; }
+		for(int iy = 0; iy < ys; ++iy) shuffleDown(rng, &fineY[iy*xs], xs, 1);      // along each row of sub-pixels
+		for(int ix = 0; ix < xs; ++ix) shuffleDown(rng, &fineX[ix], ys, xs);         // along each column
+		const float cellH = 1.0f / ys, cellW = 1.0f / xs, fine = 1.0f / n;
+		for(int i = 0; i < n; ++i)
 		{
-			int ix = xs;
-			while(ix > 1)
-			{
-				int ix2 = static_cast<int>(rng.nextInt(ix));
-				--ix;
-				std::swap(idx[2*(iy*xs + ix) + 1], idx[2*(iy*xs + ix2) + 1]);
-			}
+			const float jy = rng.nextFloat(), jx = rng.nextFloat();                  // y before x, as above
+			pos[2*i]     = (fineX[i] + jx)*fine + (i % xs)*cellW;
+			pos[2*i + 1] = (fineY[i] + jy)*fine + (i / xs)*cellH;
 		}
-		// ...and on the x sub-cell coordinate within each column.
-		for(int ix = 0; ix < xs; ++ix)
-		{
-			int iy = ys;
-			while(iy > 1)
-			{
-				int iy2 = static_cast<int>(rng.nextInt(iy));
-				--iy;
-				std::swap(idx[2*(iy*xs + ix)], idx[2*(iy2*xs + ix)]);
-			}
-		}
-		const float subPixelHeight = 1.0f / ys;
-		const float subPixelWidth = 1.0f / xs;
-		const float subcellWidth = 1.0f / n;
-		int which = 0;
-		for(int iy = 0; iy < ys; ++iy)
-			for(int ix = 0; ix < xs; ++ix)
-			{
-				int xindex = idx[2*which];
-				int yindex = idx[2*which+1];
-				float ry = rng.nextFloat();   // right-to-left argument evaluation: y first
-				float rx = rng.nextFloat();
-				pos[2*which]   = (xindex + rx)*subcellWidth + ix*subPixelWidth;
-				pos[2*which+1] = (yindex + ry)*subcellWidth + iy*subPixelHeight;
-				++which;
-			}
 	}
-	float sample1d = 0;
-	const float delta1d = 1.0f / n;
-	const float random1d = delta1d * rng.nextFloat();
-	for(int i = 0; i < n; ++i)
-	{
-		val1d[i] = sample1d + random1d;
-		sample1d += delta1d;
-	}
-	for(int i = 0; i < n; ++i)
-		shuffled[i] = i;
-	int j = n;
-	while(j > 1)
-	{
-		int j2 = static_cast<int>(rng.nextInt(j));
-		--j;
-		std::swap(shuffled[j], shuffled[j2]);
-	}
+	// stratified 1-D values (times, levels of detail): i/n plus ONE shared offset in [0, 1/n); the running sum is the
+	// reference's (:174-190), not i*step
+	const float step = 1.0f / n;
+	const float offset = step * rng.nextFloat();
+	float base = 0;
+	for(int i = 0; i < n; ++i) { val1d[i] = base + offset; base += step; }
+	// permutation of the sample indices (depth-of-field offsets are handed out through it)
+	for(int i = 0; i < n; ++i) shuffled[i] = i;
+	shuffleDown(rng, shuffled, n, 1);
 }
 
 void buildJitterTables(Random& rng, int xs, int ys, SamplerTables& out)
