@@ -37,13 +37,17 @@ def needs_build():
     return False
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, phase_timing=False):
+    """phase_timing: a DEVELOPMENT build whose k_hide counts warp cycles per phase (-DAQH_PHASE_TIMING, printed on stderr
+    after every frame); never the library that is benchmarked."""
+    if not force and not phase_timing and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-O3", "-cudart", "static", "-shared",
            "-o", LIB + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
+    if phase_timing:
+        cmd.insert(1, "-DAQH_PHASE_TIMING")
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -58,4 +62,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, phase_timing="--phase-timing" in sys.argv))

@@ -160,8 +160,16 @@ int buildTables(AqhHider* h)
 	replayFrame(p, L, rng, p.jitter != 0, h->patPlanes.data(), h->dither.data());
 	buildFilterTable(p, h->filterTab);
 	buildDofBounds(p.xsamples, p.ysamples, h->dofBounds);
-	h->shuf8.resize(h->tables.shuffled.size());
-	for(size_t i = 0; i < h->shuf8.size(); ++i) h->shuf8[i] = static_cast<uint8_t>(h->tables.shuffled[i]);
+	// the shuffle patterns as bytes, followed by their inverses (sample index -> lens cell)
+	{
+		const size_t N = h->tables.shuffled.size(), nS = size_t(p.xsamples)*p.ysamples;
+		h->shuf8.assign(2*N, 0);
+		for(size_t i = 0; i < N; ++i)
+		{
+			h->shuf8[i] = static_cast<uint8_t>(h->tables.shuffled[i]);
+			h->shuf8[N + (i/nS)*nS + size_t(h->tables.shuffled[i])] = static_cast<uint8_t>(i % nS);
+		}
+	}
 	h->tableKey = key;
 	h->tablesUploaded = false;
 	return AQH_OK;
@@ -720,7 +728,7 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 	f.nPos = h->nPos; f.nVerts = h->nVerts; f.nGrids = (int)nGrids;
 	f.P4 = h->dP4.as<float4>();
 	f.CO = h->dCO.as<float4>();
-	f.posTab = h->dPosTab.as<float2>(); f.val1d = h->dVal1d.as<float>(); f.shufTab = h->dShuf.as<uint8_t>();
+	f.posTab = h->dPosTab.as<float2>(); f.val1d = h->dVal1d.as<float>(); f.shufTab = h->dShuf.as<uint8_t>(); f.shufInvTab = f.shufTab + h->shuf8.size()/2;
 	f.patPlanes = h->dPat.as<uint8_t>(); f.filterTab = h->dFilt.as<float>(); f.dofBounds = h->dDofB.as<float4>();
 	f.dither = h->dDither.as<float>();
 	f.tileSlot = h->dTileSlot.as<int32_t>(); f.activeTiles = h->dActive.as<uint32_t>();
@@ -758,6 +766,11 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 		f.flushedPos = zOnly ? 0 : h->flushedPos;
 	}
 	f.rowOwned = (std::max(1, p.world_size) > 1) ? h->dRowOwned.as<uint8_t>() : nullptr;
+	if(const char* e = std::getenv("AQH_TUNE"))
+	{
+		int k = 0;
+		for(const char* q = e; *q && k < 8; ++k) { f.tune[k] = (int)std::strtol(q, const_cast<char**>(&q), 10); if(*q == ',') ++q; }
+	}
 
 	// ---- device work
 	S.gpu_launches = 0;
@@ -824,11 +837,17 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 	CU(hideKernelConfig(f, h->smCount, cfg), "hide kernel configuration (shared memory / occupancy)");
 	if(f.anyTransparent)
 	{
-		const int per = p.deep_hits_per_sample > 0 ? p.deep_hits_per_sample : 8;
-		f.deepCapPerCta = uint32_t(per)*uint32_t(f.tileW*f.tileH*f.n);
-		CU(h->dDeepA.reserve(size_t(cfg.hideCtas)*f.deepCapPerCta*16), "cudaMalloc(deep hit pool)");
-		CU(h->dDeepUV.reserve(size_t(cfg.hideCtas)*f.deepCapPerCta*8), "cudaMalloc(deep hit pool)");
-		f.deepA = h->dDeepA.as<uint4>(); f.deepUV = h->dDeepUV.as<float2>();
+		// every sample of a tile owns AQH_DEEP_INLINE in-line hit slots; the overflow pool behind them holds the rest of
+		// deep_hits_per_sample (an average over the tile's samples)
+		const int per = p.deep_hits_per_sample > 0 ? p.deep_hits_per_sample : 16;
+		const size_t tileSamples = size_t(f.tileW)*f.tileH*f.n;
+		const size_t nsP = size_t(f.tileH)*f.ys*(size_t(f.tileW)*f.xs + 8);          // padded sample slots of a tile (hideStride)
+		f.deepCapPerCta = (uint32_t)std::min<size_t>(size_t(std::max(per - AQH_DEEP_INLINE, 0))*tileSamples, (size_t(1) << 20) - 2);
+		const size_t perCta = AQH_DEEP_INLINE*nsP + f.deepCapPerCta;
+		CU(h->dDeepA.reserve(size_t(cfg.hideCtas)*perCta*8 + 16), "cudaMalloc(transparent hit pool)");
+		CU(h->dDeepB.reserve(size_t(cfg.hideCtas)*perCta*16 + 16), "cudaMalloc(transparent hit pool)");
+		CU(h->dDeepUV.reserve(size_t(cfg.hideCtas)*std::max<size_t>(f.deepCapPerCta, 1)*4), "cudaMalloc(transparent hit pool)");
+		f.deepA = h->dDeepA.as<uint2>(); f.deepB = h->dDeepB.as<uint4>(); f.deepNext = h->dDeepUV.as<uint32_t>();
 	}
 	// bins are sorted front to back in runs of sortRun entries (a power of two covering the longest bin, capped)
 	f.sortRun = 64;
@@ -939,7 +958,7 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 	CU(cudaEventRecord(h->ev[3], st), "cudaEventRecord");
 
 	// ---- results
-	struct { uint32_t cursor, err; uint32_t pad[2]; unsigned long long ctr[4]; } misc;
+	struct { uint32_t cursor, err; uint32_t pad[2]; unsigned long long ctr[18]; } misc;
 	CU(cudaMemcpyAsync(&misc, h->dMisc.p, sizeof misc, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(counters)");
 	tr.mark("launched filter");
 	const double tDown0 = nowMs();
@@ -1028,7 +1047,7 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 		const DevBuf* all[] = {&h->dPraw, &h->dCi, &h->dOi, &h->dCulled, &h->dP4, &h->dCO, &h->dGrids, &h->dChunk, &h->dKeyTimes, &h->dSplit,
 		                       &h->dPosTab, &h->dVal1d, &h->dShuf, &h->dPat, &h->dFilt, &h->dDofB, &h->dDither, &h->dTileSlot, &h->dActive,
 		                       &h->dBinCount, &h->dBinOffset, &h->dBinEntries, &h->dMisc, &h->dTileFlags, &h->dPlanes, &h->dPartials,
-		                       &h->dDeepA, &h->dDeepUV, &h->dChannels, &h->dRowOwned, &h->dOccl, &h->dBandCursor,
+		                       &h->dDeepA, &h->dDeepB, &h->dDeepUV, &h->dChannels, &h->dRowOwned, &h->dOccl, &h->dBandCursor,
 		                       &h->dAov, &h->dNg, &h->dNn, &h->dRadius, &h->dGridTail, &h->dGridCsg, &h->dCsgTab, &h->dZKeys, &h->dZKeys2};
 		S.device_bytes = 0;
 		for(const DevBuf* b : all) S.device_bytes += (int64_t)b->cap;
@@ -1036,6 +1055,16 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 	}
 	h->rendered = true;
 	tr.mark("stats");
+#ifdef AQH_PHASE_TIMING
+	{
+		// development build: warp-cycles worked / waited per phase of k_hide (hider_kernels.cu, PHASE_BARRIER)
+		static const char* names[7] = {"prepare", "opaque pass", "deep pass", "resolve", "tile fetch", "refresh", "occlusion image"};
+		double tot = 0;
+		for(int k = 0; k < 14; ++k) tot += (double)misc.ctr[4 + k];
+		for(int k = 0; k < 7 && tot > 0; ++k)
+			std::fprintf(stderr, "[aqh phase] %-16s work %6.2f %%  wait %6.2f %%\n", names[k], 100.0*misc.ctr[4 + 2*k]/tot, 100.0*misc.ctr[5 + 2*k]/tot);
+	}
+#endif
 	if(misc.err & 1u)
 		return h->fail(AQH_ERR_DEEP_OVERFLOW, "transparent hit pool exhausted: raise AqhFrameParams::deep_hits_per_sample");
 	if(misc.err & 8u)
@@ -1081,7 +1110,7 @@ int aqh_destroy(AqhHider* h)
 	DevBuf* bufs[] = {&h->dPraw, &h->dCi, &h->dOi, &h->dCulled, &h->dP4, &h->dCO, &h->dGrids, &h->dChunk, &h->dKeyTimes, &h->dSplit,
 	                  &h->dPosTab, &h->dVal1d, &h->dShuf, &h->dPat, &h->dFilt, &h->dDofB, &h->dDither, &h->dTileSlot, &h->dActive,
 	                  &h->dBinCount, &h->dBinOffset, &h->dBinEntries, &h->dMisc, &h->dTileFlags, &h->dPlanes, &h->dMask, &h->dPartials,
-	                  &h->dDeepA, &h->dDeepUV, &h->dChannels, &h->dRowOwned, &h->dBandCursor,
+	                  &h->dDeepA, &h->dDeepB, &h->dDeepUV, &h->dChannels, &h->dRowOwned, &h->dBandCursor,
 	                  &h->dAov, &h->dNg, &h->dNn, &h->dRadius, &h->dGridTail, &h->dGridCsg, &h->dCsgTab, &h->dZKeys, &h->dZKeys2};
 	for(DevBuf* b : bufs) b->release();
 	for(int d = 0; d < AQH_MAX_DISPLAYS; ++d) { h->dDisplay[d].release(); h->hDisplay[d].release(); }

@@ -9,6 +9,8 @@
 
 namespace aqh {
 
+#define AQH_DEEP_INLINE 8          /* in-line transparent hit slots per sample (hider_kernels.cu: DEEP_INLINE) */
+
 // Per-grid record in HBM (32 B).
 struct GridRec
 {
@@ -91,6 +93,7 @@ struct DevFrame
 	const float2* posTab;          // ncache*n
 	const float* val1d;            // ncache*n
 	const uint8_t* shufTab;        // ncache*n (n <= 256)
+	const uint8_t* shufInvTab;     // ncache*n: the inverse permutations (sample index -> lens cell)
 	const uint8_t* patPlanes;      // 5 planes of sw*sh
 	const float* filterTab;        // (2*shiftX+1)*(2*shiftY+1)*n
 	const float4* dofBounds;       // n: minx, miny, maxx, maxy
@@ -120,9 +123,11 @@ struct DevFrame
 	int filterMode;                // AQH_FILTER_*
 	float* partials;               // ntaps*9 planes of sw*sh
 	int ntaps;                     // (2*shiftX+1)*(2*shiftY+1)
-	// deep (transparent) hit pool, per persistent CTA
-	uint4* deepA;                  // next, depth bits, p, sample index
-	float2* deepUV;
+	// transparent hit pool, per persistent CTA: AQH_DEEP_INLINE in-line records per sample of the tile (rank-major), then
+	// deepCapPerCta overflow records; a hit is A = (depth bits, position index) and B = (u, v, first vertex, cu | shading flags)
+	uint2* deepA;
+	uint4* deepB;
+	uint32_t* deepNext;            // overflow chains: next overflow slot + 1
 	uint32_t deepCapPerCta;
 	uint32_t* errorFlags;          // bit0: deep pool overflow
 	unsigned long long* counters;  // [0] MPs binned, [1] bin entries, [2] deep hits, [3] longest bin
@@ -133,6 +138,7 @@ struct DevFrame
 	float* occlImage;              // sw*sh (the sample region) or null
 	int zOnly;
 	const uint8_t* rowOwned;       // yres: 1 when this rank owns the pixel row
+	int tune[8];                   // development knobs (environment AQH_TUNE="a,b,..."; 0 = the built-in default): [0] bin entries per grab, opaque pass; [1] deep pass; [2] entries between hierarchical-z refreshes
 };
 
 struct DevDisplay

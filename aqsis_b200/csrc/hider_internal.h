@@ -145,7 +145,7 @@ struct AqhHider
 	DevBuf dPraw, dCi, dOi, dCulled, dP4, dCO, dGrids, dChunk, dKeyTimes, dSplit;
 	DevBuf dPosTab, dVal1d, dShuf, dPat, dFilt, dDofB, dDither;
 	DevBuf dTileSlot, dActive, dBinCount, dBinOffset, dBinEntries, dMisc, dTileFlags;
-	DevBuf dPlanes, dMask, dPartials, dDeepA, dDeepUV, dChannels, dRowOwned;
+	DevBuf dPlanes, dMask, dPartials, dDeepA, dDeepB, dDeepUV, dChannels, dRowOwned;
 	DevBuf dDisplay[AQH_MAX_DISPLAYS];
 	DevBuf dOccl, dBandCursor;
 	DevBuf dAov, dNg, dNn, dRadius, dGridTail, dGridCsg, dCsgTab;

@@ -99,7 +99,7 @@ __device__ __forceinline__ bool mpOpaqueSlot(const DevFrame& f, const GridRec& g
 
 // ------------------------------------------------------------------------------------
 // k_project: one thread per position.
-__global__ void __launch_bounds__(256) k_project(DevFrame f, int64_t pA, int64_t pB)
+__global__ void __launch_bounds__(256) k_project(const __grid_constant__ DevFrame f, int64_t pA, int64_t pB)
 {
 	const int64_t i = pA + (int64_t)blockIdx.x * 256 + threadIdx.x;
 	if(i >= pB) return;
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256) k_project(DevFrame f, int64_t pA, int64_t
 }
 
 // Triangle split line per (grid, key): micropolygon.cpp:733-749.  One thread per grid.
-__global__ void __launch_bounds__(128) k_splitlines(DevFrame f)
+__global__ void __launch_bounds__(128) k_splitlines(const __grid_constant__ DevFrame f)
 {
 	const int gi = blockIdx.x*128 + threadIdx.x;
 	if(gi >= f.nGrids) return;
@@ -251,7 +251,7 @@ __device__ __forceinline__ bool mpTileRange(const DevFrame& f, int64_t p, const 
 }
 
 template<bool FILL>
-__global__ void __launch_bounds__(256) k_bin(DevFrame f, int64_t pA, int64_t pB)
+__global__ void __launch_bounds__(256) k_bin(const __grid_constant__ DevFrame f, int64_t pA, int64_t pB)
 {
 	const int64_t p = pA + (int64_t)blockIdx.x * 256 + threadIdx.x;
 	TileRange tr;
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(256) k_bin(DevFrame f, int64_t pA, int64_t pB)
 
 // Exclusive scan of binCount -> binOffset (single CTA; the tile count is small), and reset
 // of binCount for the fill pass.
-__global__ void __launch_bounds__(1024) k_bin_scan(DevFrame f)
+__global__ void __launch_bounds__(1024) k_bin_scan(const __grid_constant__ DevFrame f)
 {
 	__shared__ uint32_t s_part[1024];
 	const int n = f.nActiveTiles;
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(1024) k_bin_scan(DevFrame f)
 // One CTA per tile; bitonic sort of up to SORT_MAX entries in shared memory; longer bins are
 // sorted in SORT_MAX-sized runs.
 #define SORT_MAX 8192
-__global__ void __launch_bounds__(256) k_bin_sort(DevFrame f, int sortMax)
+__global__ void __launch_bounds__(256) k_bin_sort(const __grid_constant__ DevFrame f, int sortMax)
 {
 	extern __shared__ unsigned long long s_keys[];
 	const int slot = blockIdx.x;
@@ -387,7 +387,9 @@ __device__ __forceinline__ float mag2d3(const float4& a, const float4& b)
 	return dx*dx + dy*dy + dz*dz;
 }
 #define DEGENERACY_MASK 0x8000000
-__device__ int computeVertexOrder(const float4 P[4])
+// corner i of four values held in registers (a dynamically indexed array would live in local memory)
+__device__ __forceinline__ float pick4(const float v[4], int i) { return i == 0 ? v[0] : (i == 1 ? v[1] : (i == 2 ? v[2] : v[3])); }
+__device__ __forceinline__ int computeVertexOrder(const float4 P[4])
 {
 	// (double)m < 1e-8 for a float m  <=>  m <= the largest float below 1e-8 (no double arithmetic needed)
 	const float tiny = 9.99999993922529029e-9f;
@@ -401,8 +403,10 @@ __device__ int computeVertexOrder(const float4 P[4])
 	const int s0 = seq & 3, s1 = (seq >> 4) & 3, s2 = (seq >> 8) & 3;
 	const bool triangle = (seq >> 12) == 0xFu;
 	const int s3 = (seq >> 12) & 3;
-	const float4 v0 = P[s0], v1 = P[s1], v2 = P[s2];
-	const bool forward = ((v0.x - v1.x)*(v1.y - v2.y)) >= ((v0.y - v1.y)*(v1.x - v2.x));
+	const float X[4] = {P[0].x, P[1].x, P[2].x, P[3].x}, Y[4] = {P[0].y, P[1].y, P[2].y, P[3].y};
+	// the first corner of every sequence is corner 0
+	const float v0x = X[0], v0y = Y[0], v1x = pick4(X, s1), v1y = pick4(Y, s1), v2x = pick4(X, s2), v2y = pick4(Y, s2);
+	const bool forward = ((v0x - v1x)*(v1y - v2y)) >= ((v0y - v1y)*(v1x - v2x));
 	if(triangle)
 		return (forward ? (s0 | (s1 << 2) | (s2 << 4)) : (s0 | (s2 << 2) | (s1 << 4))) | DEGENERACY_MASK;
 	return forward ? (s0 | (s1 << 2) | (s2 << 4) | (s3 << 6)) : (s0 | (s3 << 2) | (s2 << 4) | (s1 << 6));
@@ -430,8 +434,8 @@ __device__ __forceinline__ void cachePointInPolyTest(HitCache& c, const float px
 	float irregularity = maxA(fabsf(c.Gx), fabsf(c.Gy));
 	c.linear = ((double)irregularity < 1e-2*(double)patchSize) ? 1 : 0;
 	const int i0 = (code >> 2) & 3, i1 = (code >> 4) & 3, i2 = (code >> 6) & 3, i3 = code & 3;
-	const float qx[4] = {px[i0], px[i1], px[i2], px[i3]};
-	const float qy[4] = {py[i0], py[i1], py[i2], py[i3]};
+	const float qx[4] = {pick4(px, i0), pick4(px, i1), pick4(px, i2), pick4(px, i3)};
+	const float qy[4] = {pick4(py, i0), pick4(py, i1), pick4(py, i2), pick4(py, i3)};
 	int j = 3;
 #pragma unroll
 	for(int i = 0; i < 4; ++i)
@@ -540,12 +544,11 @@ __device__ __forceinline__ bool triangleSplitReject(const DevFrame& f, const Gri
 	                               f.useDof, f.dofMult, f.dofInvFocal, f.dofScaleX, f.dofScaleY);
 }
 
-// CqMicroPolygon::InterpolateOutputs + CacheOutputInterpCoeffs*, micropolygon.cpp:1443-1529
-__device__ __forceinline__ void shadeHit(const DevFrame& f, const GridRec& g, uint32_t p, float2 uv, float* col, float* opa)
+// CqMicroPolygon::InterpolateOutputs + CacheOutputInterpCoeffs*, micropolygon.cpp:1443-1529.
+// v0: the micropolygon's first vertex in the Ci/Oi arrays; smooth: bilinear over the four corners, else the first corner.
+__device__ __forceinline__ void shadeAt(const DevFrame& f, size_t v0, uint32_t cu, bool smooth, float2 uv, float* col, float* opa)
 {
-	const uint32_t cu = g.cu_cv & 0xffffu;
-	const size_t v0 = (size_t)g.vbase + (p - g.pbase);
-	if((g.flags & AQH_GRID_SMOOTH) && !(g.flags & AQH_GRID_POINTS))
+	if(smooth)
 	{
 		const float4 a0 = f.CO[2*v0], a1 = f.CO[2*v0+1];
 		const float4 b0 = f.CO[2*(v0+1)], b1 = f.CO[2*(v0+1)+1];
@@ -570,6 +573,21 @@ __device__ __forceinline__ void shadeHit(const DevFrame& f, const GridRec& g, ui
 		opa[0] = a0.w; opa[1] = a1.x; opa[2] = a1.y;
 	}
 }
+__device__ __forceinline__ void shadeHit(const DevFrame& f, const GridRec& g, uint32_t p, float2 uv, float* col, float* opa)
+{
+	shadeAt(f, (size_t)g.vbase + (p - g.pbase), g.cu_cv & 0xffffu, (g.flags & AQH_GRID_SMOOTH) && !(g.flags & AQH_GRID_POINTS), uv, col, opa);
+}
+// What the resolve needs of a micropolygon's grid besides the position index, packed for the transparent hit records:
+// first vertex in the Ci/Oi arrays, and cu | smooth shading << 16 | matte << 17.
+#define HITF_SMOOTH (1u << 16)
+#define HITF_MATTE (1u << 17)
+__device__ __forceinline__ uint2 hitShadeInfo(const GridRec& g, uint32_t p)
+{
+	uint32_t fl = g.cu_cv & 0xffffu;
+	if((g.flags & AQH_GRID_SMOOTH) && !(g.flags & AQH_GRID_POINTS)) fl |= HITF_SMOOTH;
+	if(g.flags & AQH_GRID_MATTE) fl |= HITF_MATTE;
+	return make_uint2(g.vbase + (p - g.pbase), fl);
+}
 
 // ------------------------------------------------------------------------------------
 // Shared-memory layout of the hide kernel (dynamic).  The samples of a tile live in a padded
@@ -580,7 +598,7 @@ __device__ __forceinline__ void shadeHit(const DevFrame& f, const GridRec& g, ui
 //   StaticRec recs[nwarps*RECS_PER_WARP] | u32 pixZ[tileW*tileH] | u16 subOfs[n] | u8 shufPat[tileW*tileH]
 #define SMEM_PAD 8
 #define RECS_PER_WARP 8
-struct StaticRec   // 36 words
+struct StaticRec   // 40 words
 {
 	float X[4], Y[4], XM[4], YM[4];
 	float bminx, bminy, bmaxx, bmaxy;
@@ -590,6 +608,8 @@ struct StaticRec   // 36 words
 	uint32_t p;
 	uint32_t flags;     // grid id | REC_*
 	uint32_t rect;      // gx0 | gx1<<8 | gy0<<16 | gy1<<24  (tile sub-sample coordinates, <= 255)
+	uint32_t v0, shade; // hitShadeInfo(): what a transparent hit record carries for the resolve
+	uint32_t pad[2];
 };
 enum : uint32_t { REC_LINEAR = 1u << 28, REC_RARE = 1u << 29 /* lod or triangular */, REC_POINT = 1u << 30 /* a disc: centre Ax,Ay radius Ex */ };
 
@@ -689,35 +709,71 @@ __device__ __forceinline__ void storeOpaque(const DevFrame& f, const HideSmem& s
 	}
 }
 
+// Transparent hits of a tile (per persistent CTA, in HBM).  Every sample owns DEEP_INLINE in-line slots, stored RANK-MAJOR
+// (slot j of sample idx at [j*nsP + idx]): the lanes of a warp work on neighbouring samples, so both the stores of
+// the sampling loop and the loads of the resolve are runs of consecutive records instead of one 32-byte sector
+// per lane.  Hits beyond the in-line slots go to an overflow pool chained per sample.  The per-sample word in shared
+// memory (HideSmem::head) holds the hit count in bits 0-11 and the overflow chain head + 1 in bits 12-31.
+// A hit is two records: A = (depth bits, position index of the micropolygon) -- what orders the list -- and
+// B = (u, v, first Ci/Oi vertex, cu | shading flags) -- what shades it without another look at the grid tables.
+#define DEEP_INLINE AQH_DEEP_INLINE
+#define DEEP_COUNT_MASK 0xfffu
+#define DEEP_COUNT_MAX 4000u
 struct DeepCtx
 {
-	uint4* A; float2* UV; uint32_t cap; uint32_t* count;   // count lives in shared memory
+	uint2* A; uint4* B;    // DEEP_INLINE * nsP in-line records, then ovCap overflow records
+	uint32_t* ovNext;      // overflow chain: next slot + 1, 0 = end
+	uint32_t ovCap;
+	uint32_t* ovCount;     // lives in shared memory
+	uint32_t ovBase;       // DEEP_INLINE * nsP
 };
-template<bool AGG>
+#define DEEP_NIL 0xffffffffu
+// Handles of the entries of one sample: 0 .. DEEP_INLINE-1 = in-line slot, DEEP_INLINE + s = overflow slot s.
+__device__ __forceinline__ uint32_t deepFirst(uint32_t word) { return (word & DEEP_COUNT_MASK) ? 0u : DEEP_NIL; }
+__device__ __forceinline__ uint32_t deepNext(const DeepCtx& dc, uint32_t word, uint32_t h)
+{
+	if(h < DEEP_INLINE)
+	{
+		const uint32_t cnt = word & DEEP_COUNT_MASK;
+		if(h + 1u < DEEP_INLINE && h + 1u < cnt) return h + 1u;
+		const uint32_t ov = word >> 12;
+		return ov ? DEEP_INLINE + ov - 1u : DEEP_NIL;
+	}
+	const uint32_t n = dc.ovNext[h - DEEP_INLINE];
+	return n ? DEEP_INLINE + n - 1u : DEEP_NIL;
+}
+// index of an entry's records
+__device__ __forceinline__ size_t deepAt(const DeepCtx& dc, int nsP, int idx, uint32_t h)
+{
+	return (h < DEEP_INLINE) ? (size_t)h*nsP + idx : (size_t)dc.ovBase + (h - DEEP_INLINE);
+}
 __device__ __forceinline__ void storeDeep(const DevFrame& f, const DeepCtx& dc, const HideSmem& s, int idx,
-                                          float D, uint32_t p, float2 uv, bool cullable = true)
+                                          float D, uint32_t p, float2 uv, uint32_t v0, uint32_t shade, bool cullable = true)
 {
 	const uint32_t occl = (uint32_t)(s.keys[idx] >> 32);
 	if(cullable && !(depthKey(D) < occl)) return;     // isCullable && occlZ <= D
-	uint32_t slot;
-	if(AGG)
-	{
-		// one pool allocation for the lanes that arrive here together (no convergence is assumed:
-		// the group is whatever __activemask() reports), instead of one shared-memory atomic per hit
-		const unsigned m = __activemask();
-		const int lane = threadIdx.x & 31;
-		const int leader = __ffs(m) - 1;
-		uint32_t base = 0;
-		if(lane == leader) base = atomicAdd(dc.count, (uint32_t)__popc(m));
-		base = __shfl_sync(m, base, leader);
-		slot = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
-	}
+	uint32_t* word = &s.head[idx];
+	const uint32_t rank = atomicAdd(word, 1u) & DEEP_COUNT_MASK;
+	size_t at;
+	if(rank < DEEP_INLINE) at = (size_t)rank*s.nsP + idx;
 	else
-		slot = atomicAdd(dc.count, 1u);
-	if(slot >= dc.cap) { atomicOr(f.errorFlags, 1u); return; }
-	uint32_t next = atomicExch(&s.head[idx], slot);
-	dc.A[slot] = make_uint4(next, __float_as_uint(D), p, (uint32_t)idx);
-	dc.UV[slot] = uv;
+	{
+		// (a count about to leave its 12 bits, or a full pool: the frame reports AQH_ERR_DEEP_OVERFLOW)
+		if(rank >= DEEP_COUNT_MAX) { atomicSub(word, 1u); atomicOr(f.errorFlags, 1u); return; }
+		const uint32_t slot = atomicAdd(dc.ovCount, 1u);
+		if(slot >= dc.ovCap) { atomicOr(f.errorFlags, 1u); return; }
+		uint32_t cur = *(volatile uint32_t*)word;
+		for(;;)
+		{
+			const uint32_t prev = atomicCAS(word, cur, (cur & DEEP_COUNT_MASK) | ((slot + 1u) << 12));
+			if(prev == cur) break;
+			cur = prev;
+		}
+		dc.ovNext[slot] = cur >> 12;
+		at = (size_t)dc.ovBase + slot;
+	}
+	dc.A[at] = make_uint2(__float_as_uint(D), p);
+	dc.B[at] = make_uint4(__float_as_uint(uv.x), __float_as_uint(uv.y), v0, shade);
 }
 
 // sample level of detail = lods[i] of the pixel's lod pattern (imagepixel.cpp:356)
@@ -760,17 +816,18 @@ __device__ __forceinline__ void refreshPixZ(const DevFrame& f, const TileCtx& t,
 	if(lane == 0) *(volatile uint32_t*)s.tileZ = tileMax;
 }
 // largest pixZ over the pixel rectangle [sX,eX) x [sY,eY) (global pixel coordinates inside the tile)
-__device__ __forceinline__ uint32_t pixZMax(const DevFrame& f, const TileCtx& t, const HideSmem& s, int sX, int eX, int sY, int eY)
+__device__ __forceinline__ uint32_t pixZMax(const DevFrame& f, const TileCtx& t, const uint32_t* pixZ, int sX, int eX, int sY, int eY)
 {
 	uint32_t m = 0;
 	for(int y = sY; y < eY; ++y)
 		for(int x = sX; x < eX; ++x)
-			m = max(m, s.pixZ[(y - t.tileY0)*f.tileW + (x - t.tileX0)]);
+			m = max(m, pixZ[(y - t.tileY0)*f.tileW + (x - t.tileX0)]);
 	return m;
 }
 
 // ---- static micropolygons, no depth of field: RenderMPG_Static (bucketprocessor.cpp:1097-1218)
-__device__ void setupStaticRec(const DevFrame& f, const TileCtx& t, const HideSmem& s, uint32_t p, bool wantOpaque, StaticRec& r)
+// (inlined: a call would force the caller's TileCtx into local memory)
+__device__ __forceinline__ void setupStaticRec(const DevFrame& f, const TileCtx& t, const uint32_t* pixZ, uint32_t p, bool wantOpaque, StaticRec& r)
 {
 	r.rect = 0;
 	r.p = p;
@@ -806,7 +863,7 @@ __device__ void setupStaticRec(const DevFrame& f, const TileCtx& t, const HideSm
 	int sX = (bminx < (float)t.rx0) ? t.rx0 : max(floorI(bminx), t.rx0);
 	int sY = (bminy < (float)t.ry0) ? t.ry0 : max(floorI(bminy), t.ry0);
 	if(sX >= eX || sY >= eY) return;
-	if(cullableMP && depthKey(B.mnz) > pixZMax(f, t, s, sX, eX, sY, eY)) return;      // hidden behind every sample it could touch
+	if(cullableMP && depthKey(B.mnz) > pixZMax(f, t, pixZ, sX, eX, sY, eY)) return;      // hidden behind every sample it could touch
 	const int xs = f.xs, ys = f.ys;
 	int im = (bminx < (float)sX) ? 0 : floorI((bminx - (float)sX) * (float)xs);
 	int in = (bminy < (float)sY) ? 0 : floorI((bminy - (float)sY) * (float)ys);
@@ -823,6 +880,7 @@ __device__ void setupStaticRec(const DevFrame& f, const TileCtx& t, const HideSm
 		r.z[0] = a.z;
 		r.zminKey = cullableMP ? depthKey(B.mnz) : 0u;
 		r.flags = gi | REC_POINT | ((g.lod0 >= 0.0f) ? REC_RARE : 0u);
+		{ const uint2 si = hitShadeInfo(g, p); r.v0 = si.x; r.shade = si.y; }
 		r.rect = (uint32_t)gx0 | ((uint32_t)gx1 << 8) | ((uint32_t)gy0 << 16) | ((uint32_t)gy1 << 24);
 		return;
 	}
@@ -841,7 +899,15 @@ __device__ void setupStaticRec(const DevFrame& f, const TileCtx& t, const HideSm
 	if(c.linear) fl |= REC_LINEAR;
 	if((g.flags & AQH_GRID_TRIANGULAR) || g.lod0 >= 0.0f) fl |= REC_RARE;
 	r.flags = fl;
+	{ const uint2 si = hitShadeInfo(g, p); r.v0 = si.x; r.shade = si.y; }
 	r.rect = (uint32_t)gx0 | ((uint32_t)gx1 << 8) | ((uint32_t)gy0 << 16) | ((uint32_t)gy1 << 24);
+}
+
+// The motion blur / depth of field kernel meets static micropolygons rarely (frames without depth of field only): one
+// out-of-line copy, its tile passed by value.
+__device__ __noinline__ void setupStaticRecCall(const DevFrame& f, TileCtx t, const uint32_t* pixZ, uint32_t p, bool wantOpaque, StaticRec* r)
+{
+	setupStaticRec(f, t, pixZ, p, wantOpaque, *r);
 }
 
 template<bool OPAQUE, bool AGG>
@@ -898,7 +964,7 @@ __device__ __forceinline__ void sampleStaticRec(const DevFrame& f, const TileCtx
 		if(OPAQUE)
 			storeOpaque(f, s, &s.keys[idx], D, r.p);
 		else
-			storeDeep<AGG>(f, dc, s, idx, D, r.p, uv, zminKey != 0u);
+			storeDeep(f, dc, s, idx, D, r.p, uv, r.v0, r.shade, zminKey != 0u);
 	}
 }
 
@@ -1048,6 +1114,7 @@ struct MovCtx
 	bool moving, opaquePass, cullable;
 	float pointR;            // > 0: a disc (CqMicroPolygonPoints), centre = the staged vertex
 	bool isPoint;
+	uint2 shadeInfo;         // hitShadeInfo() of the micropolygon, for its transparent hit records
 };
 
 // One queued candidate (micropolygon, sample): everything of CqMicroPolygon(Motion)::Sample after the gates
@@ -1073,7 +1140,7 @@ __device__ __forceinline__ void movCandidate(const DevFrame& f, const TileCtx& t
 		const float dx = P0.x - sx, dy = P0.y - sy;
 		if(!((dx*dx + dy*dy) < c.pointR*c.pointR)) return;
 		if(c.opaquePass) storeOpaque(f, s, &s.keys[idx], P0.z, c.m.p);
-		else storeDeep<false>(f, dc, s, idx, P0.z, c.m.p, make_float2(0.f, 0.f), c.cullable);
+		else storeDeep(f, dc, s, idx, P0.z, c.m.p, make_float2(0.f, 0.f), c.shadeInfo.x, c.shadeInfo.y, c.cullable);
 		return;
 	}
 	float px[4], py[4], pz[4];
@@ -1088,7 +1155,7 @@ __device__ __forceinline__ void movCandidate(const DevFrame& f, const TileCtx& t
 	if(c.opaquePass)
 		storeOpaque(f, s, &s.keys[idx], D, c.m.p);
 	else
-		storeDeep<false>(f, dc, s, idx, D, c.m.p, uv, c.cullable);
+		storeDeep(f, dc, s, idx, D, c.m.p, uv, c.shadeInfo.x, c.shadeInfo.y, c.cullable);
 }
 
 // Queue a candidate that passed the cheap gates (called from divergent per-lane loops).
@@ -1120,7 +1187,7 @@ __device__ __forceinline__ void movDrain(const DevFrame& f, const TileCtx& t, co
 
 // Returns false for a static micropolygon in a frame without depth of field: the reference
 // renders those with RenderMPG_Static even when other grids move (bucketprocessor.cpp:1087-1090).
-__device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, MovScratch* ws,
+__device__ __forceinline__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, MovScratch* ws,
                               uint32_t p, int lane, bool opaquePass)
 {
 	MovCtx c;
@@ -1139,6 +1206,7 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 	c.isPoint = (m.g.flags & AQH_GRID_POINTS) != 0;
 	c.pointR = c.isPoint ? f.radius[p] : 0.f;
 	c.cullable = mpCullable(f, m.g);
+	c.shadeInfo = hitShadeInfo(m.g, p);
 	// ---- stage the key vertices and key bounds in the warp's scratch
 	__syncwarp();
 	{
@@ -1202,14 +1270,14 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 		fastShutter = (d <= tol*fabsf(closetime)) || (d <= tol*fabsf(opentime));   // isClose, math.h:174-182
 		if(!fastShutter) timePerSample = (float)n / (closetime - opentime);
 	}
-	// BuildBoundList state (micropolygon.cpp:1689-1756), advanced one division per loop turn
+	// BuildBoundList (micropolygon.cpp:1689-1756): the shutter is cut into `divisions` time ranges, each with the bound of
+	// the micropolygon over that range.
 	int divisions = 1;
-	float dt = 0.f, timeAcc = 0.f;
-	int startKey = 0; uint32_t endKey = 1;
-	B2 runBound = mpBound;
+	float dt = 0.f;
+	B2 kb0 = mpBound;
 	if(moving)
 	{
-		const B2 kb0 = keyBound(f, m, ws, 0);
+		kb0 = keyBound(f, m, ws, 0);
 		float cx = kb0.mxx - kb0.mnx, cy = kb0.mxy - kb0.mny;
 		float polyLen2 = (cy == 0.f) ? cx*cx : ((cx == 0.f) ? cy*cy : cx*cx + cy*cy);
 		const float4 pl = movVert(f, m, ws, m.nkeys-1, 0);
@@ -1219,98 +1287,157 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 		const int timeRanges = max(4, n);
 		divisions = min(polyLengthsMoved, timeRanges);
 		dt = (closetime - opentime) / (float)(unsigned)divisions;
-		timeAcc = opentime + dt;
-		runBound = kb0;
 	}
 	// rows of tile pixels enumerated per round, so that one round queues at most 32 lanes x 32 pixels
 	const int tileRows = t.ry1 - t.ry0;
 	const int bandRows = (f.tileW >= 32) ? 1 : (32 / f.tileW);
 	const int cellRounds = (n + 31) >> 5;
-	// The reference's loops (time sub-bounds, then lens cells or sample-index windows) are flattened into
-	// ROUNDS -- one round queues at most 1024 candidates -- driven by ONE loop with ONE drain call, so that
-	// the heavy per-candidate code exists once in the instruction stream.
-	int bnum = -1, round = 0, nRounds = 0;
-	// state of the current division
+	// The divisions are set up 32 at a time, ONE PER LANE (the reference walks them one after the other; every quantity of
+	// a division only depends on its index -- the running time is re-added from the group's start, the running bound is
+	// the previous division's end bound): time window, bound, sample-index window, depth key, circle of confusion, and
+	// whether anything of it can reach the tile.  The survivors are then enumerated one by one with all lanes:
+	// rounds of at most 1024 candidates driven by ONE loop with ONE drain call, so that the heavy per-candidate code
+	// exists once in the instruction stream.
+	const int nGroups = (divisions + 31) >> 5;
+	int group = -1, round = 0, nRounds = 0;
+	uint32_t survivors = 0;
+	float accBase = opentime + dt;           // the reference's timeAcc at the first division of the group
+	B2 carryBound = kb0;                     // its runBound there: the end bound of the division before
+	uint32_t carryKey = 0;                   // and its startKey: the last key the earlier divisions have passed
+	// this lane's division of the current group
+	B2 dBnd = mpBound;
+	float dTime0 = 0.f, dTime1 = 0.f, dCocX = 0.f, dCocY = 0.f;
+	int dIndexT0 = 0, dIndexT1 = 0;
+	uint32_t dZminKey = 0;
+	// the division being enumerated (warp-uniform)
 	B2 Bnd = mpBound;
 	float time0 = 0.f, time1 = 0.f;
 	int indexT0 = 0, indexT1 = 0;
 	uint32_t zminKey = 0;
 	float maxCocX = 0.f, maxCocY = 0.f;
-	int sX = 0, eX = 0, sY = 0, eY = 0, cnt = 1, total = 0;        // MB-only: pixel window and index window
+	int sX = 0, eX = 0, sY = 0, eY = 0, cnt = 1, total = 0;        // pixel window and index window of the flattened enumerations
+	bool byIndex = false;                                          // depth of field: enumerate (pixel, sample index) instead of (lens cell, pixel)
 	for(;;)
 	{
 		bool last = false;
 		if(round >= nRounds)
 		{
-			// advance to the next division that has anything to enumerate
-			bool found = false;
-			while(++bnum < divisions)
+			for(;;)
 			{
-				Bnd = mpBound;
-				if(moving)
+				if(survivors == 0u)
 				{
-					const float* times = m.times;
-					while(timeAcc > times[endKey] && endKey < m.nkeys - 1) ++endKey;
-					const int endKey_1 = endKey - 1;
-					const B2 end0 = keyBound(f, m, ws, endKey_1), end1 = keyBound(f, m, ws, endKey);
-					const float end0Time = times[endKey_1], end1Time = times[endKey];
-					const float mix = (timeAcc - end0Time) / (end1Time - end0Time);
-					B2 mid = end0;
-					mid.mnx += mix * (end1.mnx - end0.mnx); mid.mny += mix * (end1.mny - end0.mny); mid.mnz += mix * (end1.mnz - end0.mnz);
-					mid.mxx += mix * (end1.mxx - end0.mxx); mid.mxy += mix * (end1.mxy - end0.mxy); mid.mxz += mix * (end1.mxz - end0.mxz);
-					encapsulate(runBound, mid);
-					while(startKey < endKey_1) { startKey++; B2 kb = keyBound(f, m, ws, startKey); encapsulate(runBound, kb); }
-					Bnd = runBound;
-					time0 = timeAcc - dt;
-					const float nextAcc = timeAcc + dt;
-					time1 = (bnum != divisions - 1) ? (nextAcc - dt) : closetime;
-					runBound = mid;
-					timeAcc = nextAcc;
-					if(time1 < opentime || time0 > closetime) continue;
-					if(fastShutter) { indexT0 = 0; indexT1 = n; }
-					else
+					if(++group >= nGroups) { last = true; break; }
+					const int d = (group << 5) + lane;
+					bool ok = d < divisions;
+					dBnd = mpBound;
+					if(moving)
 					{
-						indexT0 = max(0, lfloorF((time0 - opentime) * timePerSample));
-						indexT1 = lceilF((time1 - opentime) * timePerSample);
+						const float* times = m.times;
+						// timeAcc of division d: opentime + dt, then + dt once per earlier division (the same additions in the same order)
+						float acc = accBase;
+						for(int k = 0; k < lane; ++k) acc = acc + dt;
+						uint32_t endKey = 1;
+						while(acc > times[endKey] && endKey < m.nkeys - 1) ++endKey;
+						const uint32_t endKey_1 = endKey - 1;
+						const B2 end0 = keyBound(f, m, ws, endKey_1), end1 = keyBound(f, m, ws, endKey);
+						const float end0Time = times[endKey_1], end1Time = times[endKey];
+						const float mix = (acc - end0Time) / (end1Time - end0Time);
+						B2 mid = end0;
+						mid.mnx += mix * (end1.mnx - end0.mnx); mid.mny += mix * (end1.mny - end0.mny); mid.mnz += mix * (end1.mnz - end0.mnz);
+						mid.mxx += mix * (end1.mxx - end0.mxx); mid.mxy += mix * (end1.mxy - end0.mxy); mid.mxz += mix * (end1.mxz - end0.mxz);
+						// the running bound the reference enters this division with: the end bound of the previous one
+						B2 run;
+						run.mnx = __shfl_up_sync(0xffffffffu, mid.mnx, 1); run.mny = __shfl_up_sync(0xffffffffu, mid.mny, 1); run.mnz = __shfl_up_sync(0xffffffffu, mid.mnz, 1);
+						run.mxx = __shfl_up_sync(0xffffffffu, mid.mxx, 1); run.mxy = __shfl_up_sync(0xffffffffu, mid.mxy, 1); run.mxz = __shfl_up_sync(0xffffffffu, mid.mxz, 1);
+						// ... and the last key it had passed by then (startKey): the end key - 1 of the previous division, 0 at the start
+						uint32_t startKey = __shfl_up_sync(0xffffffffu, endKey_1, 1);
+						if(lane == 0) { run = carryBound; startKey = carryKey; }
+						encapsulate(run, mid);
+						while(startKey < endKey_1) { startKey++; const B2 kb = keyBound(f, m, ws, startKey); encapsulate(run, kb); }
+						dBnd = run;
+						dTime0 = acc - dt;
+						const float nextAcc = acc + dt;
+						dTime1 = (d != divisions - 1) ? (nextAcc - dt) : closetime;
+						// hand the group's end state to the next group
+						accBase = __shfl_sync(0xffffffffu, nextAcc, 31);
+						carryBound.mnx = __shfl_sync(0xffffffffu, mid.mnx, 31); carryBound.mny = __shfl_sync(0xffffffffu, mid.mny, 31); carryBound.mnz = __shfl_sync(0xffffffffu, mid.mnz, 31);
+						carryBound.mxx = __shfl_sync(0xffffffffu, mid.mxx, 31); carryBound.mxy = __shfl_sync(0xffffffffu, mid.mxy, 31); carryBound.mxz = __shfl_sync(0xffffffffu, mid.mxz, 31);
+						carryKey = __shfl_sync(0xffffffffu, endKey_1, 31);
+						if(dTime1 < opentime || dTime0 > closetime) ok = false;
+						if(fastShutter) { dIndexT0 = 0; dIndexT1 = n; }
+						else
+						{
+							dIndexT0 = max(0, lfloorF((dTime0 - opentime) * timePerSample));
+							dIndexT1 = lceilF((dTime1 - opentime) * timePerSample);
+						}
+						if(dIndexT1 > n) dIndexT1 = n;
+						if(dIndexT0 >= n) ok = false;
 					}
-					if(indexT1 > n) indexT1 = n;
-					if(indexT0 >= n) continue;
+					if(dBnd.mnz > f.clipFar || dBnd.mxz < f.clipNear) ok = false;
+					dZminKey = c.cullable ? depthKey(dBnd.mnz) : 0u;      // a CSG micropolygon is never rejected by depth
+					if(f.useDof)
+					{
+						float2 c1 = cocAt(f, dBnd.mnz), c2 = cocAt(f, dBnd.mxz);
+						dCocX = maxA(c1.x, c2.x); dCocY = maxA(c1.y, c2.y);
+					}
+					// quick reject of the whole division: the union of the lens-cell boxes (dofBounds lie in [-1,1], so every cell
+					// box is inside the bound grown by the largest circle of confusion) or the bound itself misses the tile
+					if(!(dBnd.mxx + dCocX >= (float)t.rx0) || !(dBnd.mxy + dCocY >= (float)t.ry0) ||
+					   !(dBnd.mnx - dCocX < (float)t.rx1) || !(dBnd.mny - dCocY < (float)t.ry1)) ok = false;
+					// nothing behind the whole tile can be visible in it
+					if(ok && dZminKey > *(volatile uint32_t*)s.tileZ) ok = false;
+					survivors = __ballot_sync(0xffffffffu, ok);
+					continue;
 				}
-				if(Bnd.mnz > f.clipFar || Bnd.mxz < f.clipNear) continue;
-				zminKey = c.cullable ? depthKey(Bnd.mnz) : 0u;      // a CSG micropolygon is never rejected by depth
-				if(f.useDof)
+				const int src = __ffs(survivors) - 1;
+				survivors &= survivors - 1u;
+				Bnd.mnx = __shfl_sync(0xffffffffu, dBnd.mnx, src); Bnd.mny = __shfl_sync(0xffffffffu, dBnd.mny, src); Bnd.mnz = __shfl_sync(0xffffffffu, dBnd.mnz, src);
+				Bnd.mxx = __shfl_sync(0xffffffffu, dBnd.mxx, src); Bnd.mxy = __shfl_sync(0xffffffffu, dBnd.mxy, src); Bnd.mxz = __shfl_sync(0xffffffffu, dBnd.mxz, src);
+				time0 = __shfl_sync(0xffffffffu, dTime0, src); time1 = __shfl_sync(0xffffffffu, dTime1, src);
+				indexT0 = __shfl_sync(0xffffffffu, dIndexT0, src); indexT1 = __shfl_sync(0xffffffffu, dIndexT1, src);
+				zminKey = __shfl_sync(0xffffffffu, dZminKey, src);
+				maxCocX = __shfl_sync(0xffffffffu, dCocX, src); maxCocY = __shfl_sync(0xffffffffu, dCocY, src);
+				// the pixel window of the flattened enumerations: the bound (grown by the circle of confusion) on the tile
 				{
-					float2 c1 = cocAt(f, Bnd.mnz), c2 = cocAt(f, Bnd.mxz);
-					maxCocX = maxA(c1.x, c2.x); maxCocY = maxA(c1.y, c2.y);
-					// quick reject of the whole division: the union of the lens-cell boxes misses the tile
-					// (dofBounds lie in [-1,1], so every cell box is inside Bnd grown by maxCoc)
-					if(!(Bnd.mxx + maxCocX >= (float)t.rx0) || !(Bnd.mxy + maxCocY >= (float)t.ry0) ||
-					   !(Bnd.mnx - maxCocX < (float)t.rx1) || !(Bnd.mny - maxCocY < (float)t.ry1)) continue;
-					nRounds = ((tileRows + bandRows - 1)/bandRows)*cellRounds;
-				}
-				else
-				{
-					const float bminx = Bnd.mnx, bmaxx = Bnd.mxx, bminy = Bnd.mny, bmaxy = Bnd.mxy;
-					if(!(bmaxx >= (float)t.rx0) || !(bmaxy >= (float)t.ry0) || !(bminx < (float)t.rx1) || !(bminy < (float)t.ry1)) continue;
+					const float bminx = Bnd.mnx - maxCocX, bmaxx = Bnd.mxx + maxCocX, bminy = Bnd.mny - maxCocY, bmaxy = Bnd.mxy + maxCocY;
 					eX = (bmaxx >= (float)t.rx1) ? t.rx1 : min(lceilF(bmaxx), t.rx1);
 					eY = (bmaxy >= (float)t.ry1) ? t.ry1 : min(lceilF(bmaxy), t.ry1);
 					sX = (bminx < (float)t.rx0) ? t.rx0 : max(floorI(bminx), t.rx0);
 					sY = (bminy < (float)t.ry0) ? t.ry0 : max(floorI(bminy), t.ry0);
-					if(sX >= eX || sY >= eY) continue;
+				}
+				if(sX >= eX || sY >= eY) continue;
+				if(f.useDof)
+				{
+					// The reference walks the n lens cells and, for each, the pixels its shifted bound covers; of every such
+					// pixel it tests the one sample that uses the cell -- and rejects it unless its time lies in the division.
+					// Sample times are stratified by sample index, so for a moving micropolygon only the indices of the
+					// division's window (widened by one) can pass that test: when the window is short it is cheaper to walk
+					// (pixel, index) pairs and look the cell up.  Same candidates, same tests.
+					const int w0 = max(0, indexT0 - 1), w1 = min(n, indexT1 + 1);
+					byIndex = moving && !fastShutter && f.jitter && (w1 - w0)*4 <= n;       // (without jitter every sample time is 0: no stratification)
+					if(byIndex)
+					{
+						indexT0 = w0; cnt = w1 - w0;
+						total = (eX - sX)*(eY - sY)*cnt;
+						nRounds = (total + 1023) >> 10;
+					}
+					else nRounds = ((tileRows + bandRows - 1)/bandRows)*cellRounds;
+				}
+				else
+				{
 					// the reference's do-while visits at least one index per pixel
+					byIndex = false;
 					cnt = max(1, indexT1 - indexT0);
 					total = (eX - sX)*(eY - sY)*cnt;
 					nRounds = (total + 1023) >> 10;
 				}
 				round = 0;
-				found = true;
 				break;
 			}
-			if(!found) last = true;
 		}
 		if(!last)
 		{
-			if(f.useDof)
+			if(f.useDof && !byIndex)
 			{
 				const int band0 = (round / cellRounds)*bandRows, c0 = (round % cellRounds) << 5;
 				const int by0 = t.ry0 + band0, by1 = min(t.ry1, by0 + bandRows);
@@ -1351,7 +1478,6 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 			}
 			else
 			{
-				const float bminx = Bnd.mnx, bmaxx = Bnd.mxx, bminy = Bnd.mny, bmaxy = Bnd.mxy;
 				const int Wp = eX - sX;
 				const int k0 = round << 10, kEnd = min(total, k0 + 1024);
 				for(int k = k0 + lane; k < kEnd; k += 32)
@@ -1360,7 +1486,19 @@ __device__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSme
 					const int iY = sY + pi / Wp, iX = sX + pi % Wp;
 					const int pixLocal = (iY - t.tileY0)*f.tileW + (iX - t.tileX0);
 					if(zminKey > s.pixZ[pixLocal]) continue;
-					const int idx = sampleIdx(f, s, iX - t.tileX0, iY - t.tileY0, indexT0 + j);
+					const int index = indexT0 + j;
+					float bminx = Bnd.mnx, bmaxx = Bnd.mxx, bminy = Bnd.mny, bmaxy = Bnd.mxy;
+					if(byIndex)
+					{
+						// the lens cell whose sample this is, its shifted bound, and whether the reference's walk over the pixels of
+						// that bound reaches this pixel: iX in [floor(bminx), ceil(bmaxx)), i.e. bminx < iX + 1 and bmaxx > iX
+						const int cell = f.shufInvTab[(size_t)s.shufPat[pixLocal]*n + index];
+						const float4 db = f.dofBounds[cell];
+						bminx = Bnd.mnx - db.z*maxCocX; bmaxx = Bnd.mxx - db.x*maxCocX;
+						bminy = Bnd.mny - db.w*maxCocY; bmaxy = Bnd.mxy - db.y*maxCocY;
+						if(!(bminx < (float)(iX + 1)) || !(bmaxx > (float)iX) || !(bminy < (float)(iY + 1)) || !(bmaxy > (float)iY)) continue;
+					}
+					const int idx = sampleIdx(f, s, iX - t.tileX0, iY - t.tileY0, index);
 					const float time = s.time ? s.time[idx] : f.shutterOpen;
 					if(moving && (time < time0 || time > time1)) continue;
 					const float x = s.posx[idx], y = s.posy[idx];
@@ -1430,8 +1568,9 @@ __device__ __forceinline__ void resolveSampleMin(const DevFrame& f, const TileCt
 		depth = keyDepth((uint32_t)(key >> 32));
 		opaqueMatte = (g.flags & AQH_GRID_MATTE) != 0;
 	}
-	uint32_t head = s.head ? s.head[idx] : 0xffffffffu;
-	if(head == 0xffffffffu)
+	const uint32_t word = s.head ? s.head[idx] : 0u;
+	const uint32_t nDeep = word & DEEP_COUNT_MASK;
+	if(nDeep == 0u)
 	{
 		valid = haveOpaque;
 		if(opaqueMatte) { col[0] = col[1] = col[2] = 0.f; opa[0] = opa[1] = opa[2] = 0.f; }  // imagepixel.cpp:308-318
@@ -1459,37 +1598,36 @@ __device__ __forceinline__ void resolveSampleMin(const DevFrame& f, const TileCt
 		}
 		if(opa[0] >= f.zthr[0] && opa[1] >= f.zthr[1] && opa[2] >= f.zthr[2]) opaqueDepth0 = depth;
 	}
-	// One walk over the sample's list collects up to DEEP_SORT entries into a register-resident,
-	// descending (depth, submission) order -- the pointer chase through the pool is paid once;
-	// longer lists fall back to repeated selection of the farthest not yet composited entry.
+	// One walk collects up to DEEP_SORT entries into a register-resident, descending (depth, submission) order (the
+	// in-line records of neighbouring samples are neighbours in memory); longer lists fall back to repeated selection
+	// of the farthest not yet composited entry.
 	constexpr int DEEP_SORT = 8;
 	unsigned long long ks[DEEP_SORT];
 	uint32_t sl[DEEP_SORT];
 #pragma unroll
-	for(int j = 0; j < DEEP_SORT; ++j) { ks[j] = 0ull; sl[j] = 0xffffffffu; }
+	for(int j = 0; j < DEEP_SORT; ++j) { ks[j] = 0ull; sl[j] = DEEP_NIL; }
 	int nList = 0;
-	for(uint32_t e = head; e != 0xffffffffu; )
+	for(uint32_t e = deepFirst(word); e != DEEP_NIL; e = deepNext(dc, word, e))
 	{
-		const uint4 A = dc.A[e];
-		unsigned long long k = ((unsigned long long)depthKey(__uint_as_float(A.y)) << 32) | A.z;
+		const uint2 A = dc.A[deepAt(dc, s.nsP, idx, e)];
+		unsigned long long k = ((unsigned long long)depthKey(__uint_as_float(A.x)) << 32) | A.y;
 		uint32_t ce = e;
 #pragma unroll
 		for(int j = 0; j < DEEP_SORT; ++j)
 		{
 			// strict '>' keeps equal keys (a hit stored twice on a time sub-bound boundary) both in the list
-			if(k > ks[j] || (sl[j] == 0xffffffffu && ce != 0xffffffffu))
+			if(k > ks[j] || (sl[j] == DEEP_NIL && ce != DEEP_NIL))
 			{
 				const unsigned long long tk = ks[j]; const uint32_t ts = sl[j];
 				ks[j] = k; sl[j] = ce; k = tk; ce = ts;
 			}
 		}
 		++nList;
-		e = A.x;
 	}
 	unsigned long long prev = ~0ull;
 	for(int step = 0; ; ++step)
 	{
-		uint32_t bestSlot = 0xffffffffu;
+		uint32_t bestSlot = DEEP_NIL;
 		if(nList <= DEEP_SORT)
 		{
 			if(step >= nList) break;
@@ -1500,25 +1638,23 @@ __device__ __forceinline__ void resolveSampleMin(const DevFrame& f, const TileCt
 		{
 			// farthest not yet composited entry: largest (depthKey, p) strictly below prev
 			unsigned long long best = 0;
-			for(uint32_t e = head; e != 0xffffffffu; )
+			for(uint32_t e = deepFirst(word); e != DEEP_NIL; e = deepNext(dc, word, e))
 			{
-				const uint4 A = dc.A[e];
-				unsigned long long k = ((unsigned long long)depthKey(__uint_as_float(A.y)) << 32) | A.z;
-				if(k < prev && (bestSlot == 0xffffffffu || k > best)) { best = k; bestSlot = e; }
-				e = A.x;
+				const uint2 A = dc.A[deepAt(dc, s.nsP, idx, e)];
+				unsigned long long k = ((unsigned long long)depthKey(__uint_as_float(A.x)) << 32) | A.y;
+				if(k < prev && (bestSlot == DEEP_NIL || k > best)) { best = k; bestSlot = e; }
 			}
-			if(bestSlot == 0xffffffffu) break;
+			if(bestSlot == DEEP_NIL) break;
 			prev = best;
 		}
-		const uint4 A = dc.A[bestSlot];
-		const float2 uv = dc.UV[bestSlot];
-		const float4 a = f.P4[A.z];
-		const GridRec g = f.grids[infoOf(a) & VINFO_GRID_MASK];
+		// one entry over the running composite (imagepixel.cpp:191-262)
+		const size_t at = deepAt(dc, s.nsP, idx, bestSlot);
+		const uint2 A = dc.A[at];
+		const uint4 B = dc.B[at];
 		float c2[3], o2[3];
-		shadeHit(f, g, A.z, uv, c2, o2);
-		const float d2 = __uint_as_float(A.y);
-		pNear = A.z;                 // composited back to front: the last entry is the nearest
-		if(g.flags & AQH_GRID_MATTE)
+		shadeAt(f, B.z, B.w & 0xffffu, (B.w & HITF_SMOOTH) != 0, make_float2(__uint_as_float(B.x), __uint_as_float(B.y)), c2, o2);
+		pNear = A.y;                 // composited back to front: the last entry is the nearest
+		if(B.w & HITF_MATTE)
 		{
 #pragma unroll
 			for(int k = 0; k < 3; ++k) { sc[k] = (1.f-o2[k])*sc[k] + o2[k]*0.0f; so[k] = (1.f-c2[k])*so[k] + c2[k]*0.0f; }
@@ -1532,7 +1668,7 @@ __device__ __forceinline__ void resolveSampleMin(const DevFrame& f, const TileCt
 				so[k] = ((1.0f - so[k]) * o2[k]) + so[k];
 			}
 		}
-		if(o2[0] >= f.zthr[0] && o2[1] >= f.zthr[1] && o2[2] >= f.zthr[2]) opaqueDepth0 = d2;
+		if(o2[0] >= f.zthr[0] && o2[1] >= f.zthr[1] && o2[2] >= f.zthr[2]) opaqueDepth0 = __uint_as_float(A.x);
 	}
 	valid = true;
 	out[0] = sc[0]; out[1] = sc[1]; out[2] = sc[2]; out[3] = so[0]; out[4] = so[1]; out[5] = so[2];
@@ -1540,7 +1676,7 @@ __device__ __forceinline__ void resolveSampleMin(const DevFrame& f, const TileCt
 }
 
 template<bool MBDOF>
-__device__ void resolveSampleGeneral(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, int idx,
+__device__ __forceinline__ void resolveSampleGeneral(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, int idx,
                               float out[7], bool& valid, uint32_t& pNear)
 {
 	// keys[nsP + idx]: nearest opaque hit; keys[idx]: the occlusion depth occlZ (the same array unless the midpoint depth
@@ -1566,8 +1702,9 @@ __device__ void resolveSampleGeneral(const DevFrame& f, const TileCtx& t, const 
 		depth = keyDepth((uint32_t)(key >> 32));
 		opaqueMatte = (g.flags & AQH_GRID_MATTE) != 0;
 	}
-	uint32_t head = s.head ? s.head[idx] : 0xffffffffu;
-	if(head == 0xffffffffu)
+	const uint32_t word = s.head ? s.head[idx] : 0u;
+	const uint32_t head = deepFirst(word);
+	if(head == DEEP_NIL)
 	{
 		// opaque-only sample: imagepixel.cpp:304-327
 		valid = haveOpaque;
@@ -1595,9 +1732,9 @@ __device__ void resolveSampleGeneral(const DevFrame& f, const TileCtx& t, const 
 			if(e == OPQ) { k = key; nextE = head; }
 			else
 			{
-				const uint4 A = dc.A[e];
-				k = ((unsigned long long)depthKey(__uint_as_float(A.y)) << 32) | A.z;
-				nextE = A.x;
+				const uint2 A = dc.A[deepAt(dc, s.nsP, idx, e)];
+				k = ((unsigned long long)depthKey(__uint_as_float(A.x)) << 32) | A.y;
+				nextE = deepNext(dc, word, e);
 			}
 			uint32_t ce = e;
 #pragma unroll
@@ -1644,9 +1781,9 @@ __device__ void resolveSampleGeneral(const DevFrame& f, const TileCtx& t, const 
 					if(e == OPQ) { k = key; nextE = head; }
 					else
 					{
-						const uint4 A = dc.A[e];
-						k = ((unsigned long long)depthKey(__uint_as_float(A.y)) << 32) | A.z;
-						nextE = A.x;
+						const uint2 A = dc.A[deepAt(dc, s.nsP, idx, e)];
+						k = ((unsigned long long)depthKey(__uint_as_float(A.x)) << 32) | A.y;
+						nextE = deepNext(dc, word, e);
 					}
 					const bool beyond = (pass == 0) ? (k < prev) : (k > prev);
 					const bool better = (pass == 0) ? (k > best) : (k < best);
@@ -1667,14 +1804,13 @@ __device__ void resolveSampleGeneral(const DevFrame& f, const TileCtx& t, const 
 			}
 			else
 			{
-				const uint4 A = dc.A[bestSlot];
-				if(pass == 0) pNear = A.z;
-				const float2 uv = dc.UV[bestSlot];
-				const float4 a = f.P4[A.z];
-				const GridRec g = f.grids[infoOf(a) & VINFO_GRID_MASK];
-				shadeHit(f, g, A.z, uv, c2, o2);
-				d2 = __uint_as_float(A.y);
-				matte = (g.flags & AQH_GRID_MATTE) != 0;
+				const size_t at = deepAt(dc, s.nsP, idx, bestSlot);
+				const uint2 A = dc.A[at];
+				const uint4 B = dc.B[at];
+				if(pass == 0) pNear = A.y;
+				shadeAt(f, B.z, B.w & 0xffffu, (B.w & HITF_SMOOTH) != 0, make_float2(__uint_as_float(B.x), __uint_as_float(B.y)), c2, o2);
+				d2 = __uint_as_float(A.x);
+				matte = (B.w & HITF_MATTE) != 0;
 			}
 			if(pass == 1)
 			{
@@ -1727,7 +1863,7 @@ __device__ __forceinline__ bool csgEvaluate(int type, uint32_t state, int nKids)
 	return false;
 }
 template<bool MBDOF>
-__device__ __noinline__ void resolveSampleCSG(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, int idx,
+__device__ __noinline__ void resolveSampleCSG(const DevFrame& f, const HideSmem s, const DeepCtx dc, int idx,
                                               float out[7], bool& valid, uint32_t& pNear)
 {
 	constexpr uint32_t NIL = 0xffffffffu, OPQ = 0xfffffffeu;
@@ -1757,17 +1893,18 @@ __device__ __noinline__ void resolveSampleCSG(const DevFrame& f, const TileCtx& 
 	int nd[CSG_MAX_LIST];
 	int cnt = 0;
 	{
-		uint32_t e = haveOpaque ? OPQ : s.head[idx];
+		const uint32_t word = s.head[idx];
+		uint32_t e = haveOpaque ? OPQ : deepFirst(word);
 		while(e != NIL)
 		{
 			unsigned long long k; uint32_t nextE; int node = -1;
-			if(e == OPQ) { k = key; nextE = s.head[idx]; }
+			if(e == OPQ) { k = key; nextE = deepFirst(word); }
 			else
 			{
-				const uint4 A = dc.A[e];
-				k = ((unsigned long long)depthKey(__uint_as_float(A.y)) << 32) | A.z;
-				nextE = A.x;
-				const uint32_t gi = infoOf(f.P4[A.z]) & VINFO_GRID_MASK;
+				const uint2 A = dc.A[deepAt(dc, s.nsP, idx, e)];
+				k = ((unsigned long long)depthKey(__uint_as_float(A.x)) << 32) | A.y;
+				nextE = deepNext(dc, word, e);
+				const uint32_t gi = infoOf(f.P4[A.y]) & VINFO_GRID_MASK;
 				if(f.grids[gi].flags & AQH_GRID_USES_CSG) node = f.gridCsg[gi];
 			}
 			if(cnt >= CSG_MAX_LIST) { atomicOr(f.errorFlags, 8u); break; }
@@ -1841,12 +1978,12 @@ __device__ __noinline__ void resolveSampleCSG(const DevFrame& f, const TileCtx& 
 			}
 			else
 			{
-				const uint4 A = dc.A[sl[j]];
-				const float2 uv = dc.UV[sl[j]];
-				const GridRec g = f.grids[infoOf(f.P4[A.z]) & VINFO_GRID_MASK];
-				shadeHit(f, g, A.z, uv, c2, o2);
-				d2 = __uint_as_float(A.y);
-				matte = (g.flags & AQH_GRID_MATTE) != 0;
+				const size_t at = deepAt(dc, s.nsP, idx, sl[j]);
+				const uint2 A = dc.A[at];
+				const uint4 B = dc.B[at];
+				shadeAt(f, B.z, B.w & 0xffffu, (B.w & HITF_SMOOTH) != 0, make_float2(__uint_as_float(B.x), __uint_as_float(B.y)), c2, o2);
+				d2 = __uint_as_float(A.x);
+				matte = (B.w & HITF_MATTE) != 0;
 			}
 			if(pass == 1)
 			{
@@ -1876,7 +2013,7 @@ __device__ __noinline__ void resolveSampleCSG(const DevFrame& f, const TileCtx& 
 			}
 		}
 	valid = true;
-	pNear = (sl[0] == OPQ) ? p : dc.A[sl[0]].z;
+	pNear = (sl[0] == OPQ) ? p : dc.A[deepAt(dc, s.nsP, idx, sl[0])].y;
 	out[0] = sc[0]; out[1] = sc[1]; out[2] = sc[2]; out[3] = so[0]; out[4] = so[1]; out[5] = so[2];
 	float zout = opaqueDepth0;
 	if(f.depthFilter == AQH_DEPTHFILTER_MIDPOINT) zout = (cnt > 1) ? ((opaqueDepth0 + opaqueDepth1) * 0.5f) : FLT_MAX;
@@ -1892,7 +2029,16 @@ template<bool MBDOF, bool DFGEN>
 __device__ __forceinline__ void resolveSample(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, int idx,
                                               float out[7], bool& valid, uint32_t& pNear)
 {
-	if(f.anyCSG && s.head && s.head[idx] != 0xffffffffu) { resolveSampleCSG<MBDOF>(f, t, s, dc, idx, out, valid, pNear); return; }
+	if(f.anyCSG && s.head && (s.head[idx] & DEEP_COUNT_MASK))
+	{
+		// results through temporaries: only they (not the caller's registers) have their address taken by the call
+		float o[7]; bool v; uint32_t pn;
+		resolveSampleCSG<MBDOF>(f, s, dc, idx, o, v, pn);
+#pragma unroll
+		for(int k = 0; k < 7; ++k) out[k] = o[k];
+		valid = v; pNear = pn;
+		return;
+	}
 	if(!DFGEN) resolveSampleMin<MBDOF>(f, t, s, dc, idx, out, valid, pNear);
 	else resolveSampleGeneral<MBDOF>(f, t, s, dc, idx, out, valid, pNear);
 }
@@ -1938,6 +2084,18 @@ __device__ __forceinline__ uint32_t loadMask(const DevFrame& f, size_t at)
 	return ~reinterpret_cast<const uint32_t*>(f.maskPlane)[at];
 }
 
+// Per-phase timing of k_hide for development builds (python -m aqsis_b200.build --phase-timing, i.e. -DAQH_PHASE_TIMING):
+// every warp adds, per phase, the cycles it worked and the cycles it then waited at the phase's barrier to
+// f.counters[4 + 2*phase], [5 + 2*phase].  Phases: 0 prepare, 1 opaque pass, 2 deep pass, 3 resolve, 4 tile fetch,
+// 5 refresh between the passes, 6 occlusion image.
+#ifdef AQH_PHASE_TIMING
+#define PHASE_BARRIER(ph) do { const long long a_ = clock64(); __syncthreads(); const long long b_ = clock64(); \
+	if(lane == 0) { atomicAdd(&s_ph[2*(ph)], (unsigned long long)(a_ - tPh)); atomicAdd(&s_ph[2*(ph) + 1], (unsigned long long)(b_ - a_)); } \
+	tPh = b_; } while(0)
+#else
+#define PHASE_BARRIER(ph) __syncthreads()
+#endif
+
 // ------------------------------------------------------------------------------------
 // k_hide: persistent CTAs pull tiles from a counter.  Inside a tile every warp runs its own
 // pipeline -- grab RECS_PER_WARP micropolygons of the tile's bin, set them up (one lane each,
@@ -1945,12 +2103,12 @@ __device__ __forceinline__ uint32_t loadMask(const DevFrame& f, size_t at)
 // lanes -- so there is no CTA-wide barrier inside the micropolygon loop.
 // DFGEN: a depth filter other than "min" (kept out of the common kernels: its bookkeeping costs registers)
 template<bool MBDOF, int THREADS, bool PARTIALS, bool DFGEN>
-__global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevFrame f, uint32_t slotBeg, uint32_t slotEnd, uint32_t* cursor)
+__global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(const __grid_constant__ DevFrame f, uint32_t slotBeg, uint32_t slotEnd, uint32_t* cursor)
 {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
 	__shared__ uint32_t s_tile;
 	__shared__ uint32_t s_deepCount;
-	__shared__ uint32_t s_next;
+	__shared__ uint32_t s_next, s_resNext;
 	__shared__ uint32_t s_tileZ, s_dirty, s_lastRef;
 	constexpr int NWARPS = THREADS/32;
 	HideSmem s = carveSmem(f, smemRaw, NWARPS*RECS_PER_WARP, MBDOF ? NWARPS*sizeof(MovScratch) : 0);
@@ -1958,20 +2116,28 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 	s.tileZ = &s_tileZ; s.dirty = &s_dirty;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int n = f.n, xs = f.xs, ys = f.ys;
-	const int rowLen = f.tileW*xs;
 	StaticRec* myRecs = s.recs + warp*RECS_PER_WARP;
 	DeepCtx dc;
-	dc.A = f.deepA + (size_t)blockIdx.x*f.deepCapPerCta;
-	dc.UV = f.deepUV + (size_t)blockIdx.x*f.deepCapPerCta;
-	dc.cap = f.deepCapPerCta;
-	dc.count = &s_deepCount;
+	// this CTA's part of the transparent hit pool: the in-line slots of the tile's samples, then the overflow records
+	dc.ovBase = (uint32_t)DEEP_INLINE*(uint32_t)s.nsP;
+	dc.A = f.deepA + (size_t)blockIdx.x*((size_t)dc.ovBase + f.deepCapPerCta);
+	dc.B = f.deepB + (size_t)blockIdx.x*((size_t)dc.ovBase + f.deepCapPerCta);
+	dc.ovNext = f.deepNext + (size_t)blockIdx.x*f.deepCapPerCta;
+	dc.ovCap = f.deepCapPerCta;
+	dc.ovCount = &s_deepCount;
 	for(int i = tid; i < n; i += THREADS) s.subOfs[i] = (uint16_t)((i / xs)*s.stride + i % xs);
+#ifdef AQH_PHASE_TIMING
+	__shared__ unsigned long long s_ph[14];
+	if(tid < 14) s_ph[tid] = 0;
+	__syncthreads();
+	long long tPh = clock64();
+#endif
 	for(;;)
 	{
-		__syncthreads();
+		PHASE_BARRIER(3);
 		// one band of tile rows per launch: active tiles [slotBeg, slotEnd), handed out through the band's own cursor
-		if(tid == 0) { s_tile = slotBeg + atomicAdd(cursor, 1u); s_deepCount = 0; s_next = 0; }
-		__syncthreads();
+		if(tid == 0) { s_tile = slotBeg + atomicAdd(cursor, 1u); s_deepCount = 0; s_next = 0; s_resNext = 0; }
+		PHASE_BARRIER(4);
 		const uint32_t slot = s_tile;
 		if(slot >= slotEnd) break;
 		// an incremental flush leaves tiles without new micropolygons as they are (their occlusion image is already there)
@@ -1989,11 +2155,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 		{
 			s.keys[idx] = KEY_EMPTY;
 			if(f.midpointZ) s.keys[s.nsP + idx] = KEY_EMPTY;
-			if(s.head) s.head[idx] = 0xffffffffu;
+			if(s.head) s.head[idx] = 0u;
 			s.posx[idx] = -1e30f;
 			s.posy[idx] = -1e30f;
 		}
-		__syncthreads();
+		PHASE_BARRIER(0);
 		// ... then one warp per pixel of the tile, lanes over its samples (no per-sample index arithmetic)
 		for(int pix = warp; pix < f.tileW*f.tileH; pix += NWARPS)
 		{
@@ -2041,11 +2207,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 		}
 		for(int i = tid; i < f.tileW*f.tileH; i += THREADS) s.pixZ[i] = 0xffffffffu;
 		if(tid == 0) { s_tileZ = 0xffffffffu; s_dirty = 0; s_lastRef = 0; }
-		__syncthreads();
+		PHASE_BARRIER(0);
 		if(f.zKeys)
 		{
 			if(warp == 0) refreshPixZ(f, t, s, lane);        // start from the hierarchical z of the stored keys
-			__syncthreads();
+			PHASE_BARRIER(0);
 		}
 		const uint32_t binBeg = f.binOffset[slot], binCnt = f.binOffset[slot+1] - binBeg;
 		const uint32_t tflags = f.tileFlags[slot];
@@ -2059,10 +2225,10 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 			if(pass == 1)
 			{
 				if(f.zOnly || !(f.anyTransparent && (tflags & 1u))) break;      // occlusion only needs the opaque pass
-				__syncthreads();
+				PHASE_BARRIER(1);
 				if(tid == 0) { s_next = 0; s_dirty = 0; s_lastRef = 0; }
 				if(warp == 0) refreshPixZ(f, t, s, lane);        // the opaque depths are final now
-				__syncthreads();
+				PHASE_BARRIER(5);
 			}
 			for(;;)
 			{
@@ -2071,14 +2237,14 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 				// bin turns into culling early.  Once the first wave (one grab per warp) is under way the
 				// hierarchical z is refreshed whenever new hits have landed, and because the bin is sorted
 				// by nearest depth, the first micropolygon found behind the whole tile ends its sorted run.
-				constexpr uint32_t GRAB = MBDOF ? 2u : 8u;
+				const uint32_t GRAB = f.tune[pass] ? (uint32_t)f.tune[pass] : (MBDOF ? 2u : 8u);
 				if(lane == 0) base = atomicAdd(&s_next, GRAB);
 				base = __shfl_sync(0xffffffffu, base, 0);
 				if(base >= binCnt) break;
 				const int cnt = min(GRAB, binCnt - base);
 				// tile-wide pacing: one refresh per REFRESH_EVERY bin entries handed out (whichever warp crosses the
 				// mark takes it) -- 16 warps each refreshing on their own schedule spent 12 % of the kernel here
-				constexpr uint32_t REFRESH_EVERY = MBDOF ? 16u : 96u;
+				const uint32_t REFRESH_EVERY = f.tune[2] ? (uint32_t)f.tune[2] : (MBDOF ? 16u : 96u);
 				{
 					const uint32_t last = *(volatile uint32_t*)&s_lastRef;
 					if(base >= GRAB*NWARPS && base - last >= REFRESH_EVERY && *(volatile uint32_t*)s.dirty)
@@ -2117,7 +2283,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 						if(!handled)
 						{
 							// static micropolygon in a frame without depth of field
-							if(lane == 0) setupStaticRec(f, t, s, p, pass == 0, myRecs[0]);
+							if(lane == 0) setupStaticRecCall(f, t, s.pixZ, p, pass == 0, &myRecs[0]);
 							__syncwarp();
 							if(pass == 0) sampleStaticRec<true, false>(f, t, s, dc, myRecs[0], lane);
 							else sampleStaticRec<false, false>(f, t, s, dc, myRecs[0], lane);
@@ -2127,7 +2293,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 				}
 				else
 				{
-					if(lane < cnt) setupStaticRec(f, t, s, (uint32_t)ent, pass == 0, myRecs[lane]);
+					if(lane < cnt) setupStaticRec(f, t, s.pixZ, (uint32_t)ent, pass == 0, myRecs[lane]);
 					__syncwarp();
 					for(int j = 0; j < cnt; ++j)
 					{
@@ -2138,13 +2304,20 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 				}
 			}
 		}
-		__syncthreads();
-		if(tid == 0 && s_deepCount) atomicAdd(&f.counters[2], (unsigned long long)min(s_deepCount, dc.cap));
+		PHASE_BARRIER((f.anyTransparent && (tflags & 1u) && !f.zOnly) ? 2 : 1);
+		if(s.head && !f.zOnly)
+		{
+			// statistics: transparent hits kept by the tile's samples (padding slots hold 0)
+			uint32_t mine = 0;
+			for(int idx = tid; idx < s.nsP; idx += THREADS) mine += s.head[idx] & DEEP_COUNT_MASK;
+			mine = __reduce_add_sync(0xffffffffu, mine);
+			if(lane == 0 && mine) atomicAdd(&f.counters[2], (unsigned long long)mine);
+		}
 		// ---- occlusion feedback for the front end (CqOcclusionTree, occlusion.cpp:54-225, at pixel granularity)
 		if(f.occlImage)
 		{
 			if(warp == 0) refreshPixZ(f, t, s, lane);
-			__syncthreads();
+			PHASE_BARRIER(6);
 			const int tw0 = t.rx1 - t.rx0, th0 = t.ry1 - t.ry0;
 			for(int pix = tid; pix < tw0*th0; pix += THREADS)
 			{
@@ -2173,19 +2346,30 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 		const int tw = t.rx1 - t.rx0, th = t.ry1 - t.ry0;
 		if(!PARTIALS)
 		{
-			// Planes are [k][y][chunk][x][slot]: one warp per pixel, lanes over its sample slots.
+			// Planes are [k][y][chunk][x][slot].  The unit of work is 32 consecutive sample slots of one pixel, one per
+			// lane; warps take units from a tile-wide counter (samples with long transparent lists cost several times
+			// the others: a static pixel-per-warp split left most warps waiting for the slowest one).
 			const int SC = f.planeSC, nCh = f.planeChunks, nSlots = SC*nCh;
-			for(int pix = warp; pix < tw*th; pix += NWARPS)
+			const int unitsPerPix = (nSlots + 31) >> 5, nUnits = tw*th*unitsPerPix;
+			for(;;)
 			{
+				int unit = 0;
+				if(lane == 0) unit = (int)atomicAdd(&s_resNext, 1u);
+				unit = __shfl_sync(0xffffffffu, unit, 0);
+				if(unit >= nUnits) break;
+				const int pix = unit / unitsPerPix;
 				const int ly = pix / tw, lx = pix - ly*tw;
 				const int X = t.rx0 + lx, Y = t.ry0 + ly;
 				// the planes hold ringRows sample rows at a time (a ring over the bands of the frame)
 				const size_t rowAt = (size_t)((Y - f.sy0) % f.ringRows)*nCh*f.planeW + (size_t)(X - f.sx0);
-				for(int i = lane; i < nSlots; i += 32)
+				const int i = ((unit - pix*unitsPerPix) << 5) + lane;
+				if(i < nSlots)
 				{
 					const int c = i / SC, j = i - c*SC;
 					const size_t at = (rowAt + (size_t)c*f.planeW)*SC + j;
-					if(i >= n) { storeMask(f, at, 0u); continue; }       // padding slot: never included
+					if(i >= n) storeMask(f, at, 0u);       // padding slot: never included
+					else
+					{
 					const int idx = sampleIdx(f, s, lx, ly, i);
 					float out[7]; bool valid; uint32_t pNear;
 					resolveSample<MBDOF, DFGEN>(f, t, s, dc, idx, out, valid, pNear);
@@ -2202,6 +2386,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 							const float* av = f.aov + ((size_t)g.vbase + (pNear - g.pbase))*f.aovFloats;
 							for(int k = 0; k < f.aovFloats; ++k) f.planes[(size_t)(7 + k)*f.planeStride + at] = av[k];
 						}
+					}
 					}
 				}
 			}
@@ -2271,10 +2456,14 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(DevF
 			}
 		}
 	}
+#ifdef AQH_PHASE_TIMING
+	__syncthreads();
+	if(tid < 14 && s_ph[tid]) atomicAdd(&f.counters[4 + tid], s_ph[tid]);
+#endif
 }
 
 // Mark tiles whose bins contain non-opaque micropolygons (drives the deep pass).
-__global__ void __launch_bounds__(256) k_tile_flags(DevFrame f)
+__global__ void __launch_bounds__(256) k_tile_flags(const __grid_constant__ DevFrame f)
 {
 	const int slot = blockIdx.x;
 	__shared__ uint32_t s_any;
@@ -2404,7 +2593,7 @@ __device__ __forceinline__ void finishAovPixel(const DevFrame& f, int x, int y, 
 
 // The deferred tail of the frame: exposure (when an imager ran in between) and the quantisation of every display, one
 // thread per pixel of the crop window.
-__global__ void __launch_bounds__(256) k_finish(DevFrame f, DevDisplays disp, int expose)
+__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ DevFrame f, const __grid_constant__ DevDisplays disp, int expose)
 {
 	const int x = f.cropX0 + blockIdx.x*blockDim.x + threadIdx.x;
 	const int y = f.cropY0 + blockIdx.y*blockDim.y + threadIdx.y;
@@ -2422,7 +2611,7 @@ __global__ void __launch_bounds__(256) k_finish(DevFrame f, DevDisplays disp, in
 }
 
 // Reference-order filter: one running sum per output pixel over the per-sample planes.
-__global__ void __launch_bounds__(256) k_filter(DevFrame f, DevDisplays disp, int weightsInSmem, int yBeg, int yEnd, int kBase, int nVal)
+__global__ void __launch_bounds__(256) k_filter(const __grid_constant__ DevFrame f, const __grid_constant__ DevDisplays disp, int weightsInSmem, int yBeg, int yEnd, int kBase, int nVal)
 {
 	extern __shared__ float s_filtBuf[];
 	const int taps = (2*f.shiftX+1)*(2*f.shiftY+1)*f.n;
@@ -2537,7 +2726,7 @@ __host__ __device__ __forceinline__ int filterPlaneFloats(const DevFrame& f)
 // MB = bytes per mask word (1, 2 or 4).  Four consecutive slots are tested per step:
 // one 32-bit shared load for byte masks, one 64-bit load for 16-bit masks, one 128-bit load for 32-bit masks.
 template<int MB>
-__global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(DevFrame f, DevDisplays disp, int yBeg, int kBase, int nVal)
+__global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(const __grid_constant__ DevFrame f, const __grid_constant__ DevDisplays disp, int yBeg, int kBase, int nVal)
 {
 	constexpr int W = FILTER_W;
 	extern __shared__ __align__(128) unsigned char fsm[];
@@ -2670,7 +2859,7 @@ static size_t filterSpansSmem(const DevFrame& f)
 }
 
 // Tile-partials filter: sum the nine per-(pixel,tap) partial sums over the taps in fy, fx order.
-__global__ void __launch_bounds__(256) k_filter_partials(DevFrame f, DevDisplays disp)
+__global__ void __launch_bounds__(256) k_filter_partials(const __grid_constant__ DevFrame f, const __grid_constant__ DevDisplays disp)
 {
 	const int x = f.cropX0 + blockIdx.x*blockDim.x + threadIdx.x;
 	const int y = f.cropY0 + blockIdx.y*blockDim.y + threadIdx.y;

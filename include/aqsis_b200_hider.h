@@ -174,7 +174,8 @@ typedef struct AqhFrameParams
 	                                   -2: one contiguous strip per rank, rank r owns rows [strip_bounds[r], strip_bounds[r+1])
 	                                       (see aqh_balance_strips) */
 	int32_t strip_bounds[AQH_MAX_RANKS + 1];
-	int32_t deep_hits_per_sample;   /* average capacity of the transparent hit pool; 0 = default */
+	int32_t deep_hits_per_sample;   /* capacity for transparent hits: every sample has 8 in-line slots, the pool behind them holds
+	                                   (deep_hits_per_sample - 8) hits per sample averaged over a tile; 0 = default (16) */
 	int32_t filter_mode;            /* AQH_FILTER_*; 0 = AQH_FILTER_REFERENCE_ORDER (bit-exact sums) */
 	int32_t plane_budget_mb;        /* HBM the resolved samples of the reference-order filter may occupy at a time; the frame
 	                                   is hidden and filtered in bands of tile rows that fit (0 = 4608 MB) */

@@ -259,15 +259,15 @@ def test_bins_longer_than_one_sorted_run(gpu_hider):
 
 def test_deep_pool_overflow_is_reported(gpu_hider):
     from aqsis_b200 import HiderError
-    p, g = scenes.config4(scale=0.02)
-    p.deep_hits_per_sample = 1                 # three transparent layers need three slots per sample
+    p, g = scenes.config4(scale=0.02, layers=7)
+    p.deep_hits_per_sample = 1                 # six transparent layers: two more hits per sample than the four in-line slots
     gpu_hider.begin_frame(p)
     gpu_hider.add_grid_block(g)
     with pytest.raises(HiderError) as e:
         gpu_hider.end_frame()
     assert e.value.status == abi.AQH_ERR_DEEP_OVERFLOW
-    p.deep_hits_per_sample = 8
-    check(gpu_hider, p, g, EXACT)              # and the hider is usable afterwards
+    p.deep_hits_per_sample = 16                # (neighbouring grids overlap: some samples see a layer twice)
+    check(gpu_hider, p, g, EXACT)              # and the hider is usable afterwards (this frame chains two hits per sample in the overflow pool)
 
 
 def test_zero_pdiff_differences(gpu_hider):

@@ -20,9 +20,12 @@ LIB = os.path.join(ROOT, "aqsis_b200", "_lib", "libaqsis_b200_hider.so")
 
 
 def disasm_lines(kernel_re):
-    tmp = tempfile.mkdtemp()
-    subprocess.run(["cuobjdump", "-xelf", "all", LIB], cwd=tmp, capture_output=True)
-    cubin = [f for f in glob.glob(os.path.join(tmp, "*.cubin")) if os.path.basename(f).startswith("hider_kernels.")][0]
+    # NCU_CUBIN / NCU_SRC: a cubin + source of the commit the capture was taken at, when the tree has moved on
+    cubin = os.environ.get("NCU_CUBIN")
+    if not cubin:
+        tmp = tempfile.mkdtemp()
+        subprocess.run(["cuobjdump", "-xelf", "all", LIB], cwd=tmp, capture_output=True)
+        cubin = [f for f in glob.glob(os.path.join(tmp, "*.cubin")) if os.path.basename(f).startswith("hider_kernels.")][0]
     txt = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
     out, cur, line, on = {}, None, 0, False
     for l in txt.splitlines():
@@ -55,28 +58,45 @@ def main():
     end = hdr_i[1] - 1 if len(hdr_i) > 1 else len(rows)
     body = rows[hdr_i[0] + 1:end]
     si, ii, ti = hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
+    l2i, shi = hdr.index("L2 Theoretical Sectors Global"), hdr.index("L1 Wavefronts Shared")
+    stall_cols = [(i, h[6:]) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
     dis = disasm_lines(kre)
     fn = [k for k in dis if len(dis[k]) == len(body)]
     if not fn:
         print("instruction count mismatch", len(body), {k: len(v) for k, v in dis.items()})
         return
     lines = dis[fn[0]]
-    src = open(os.path.join(ROOT, "aqsis_b200", "csrc", "hider_kernels.cu")).read().splitlines()
+    src = open(os.environ.get("NCU_SRC") or os.path.join(ROOT, "aqsis_b200", "csrc", "hider_kernels.cu")).read().splitlines()
     agg = {}
-    tot_s = tot_i = 0
+    tot_s = tot_i = tot_l2 = tot_sh = 0
+    stall_tot = {}
     for (ln, sass), r in zip(lines, body):
         s, i, t = int(r[si]), int(r[ii]), int(r[ti])
-        a = agg.setdefault(ln, [0, 0, 0])
+        a = agg.setdefault(ln, [0, 0, 0, 0, 0, {}])
         a[0] += s
         a[1] += i
         a[2] += t
+        a[3] += int(r[l2i] or 0)
+        a[4] += int(r[shi] or 0)
+        for ci, nm in stall_cols:
+            v = int(r[ci] or 0)
+            if v:
+                a[5][nm] = a[5].get(nm, 0) + v
+                stall_tot[nm] = stall_tot.get(nm, 0) + v
         tot_s += s
         tot_i += i
-    print(f"kernel {kname}: {len(body)} SASS instructions, {tot_s} samples, {tot_i} warp instructions")
-    print(f"{'line':>5} {'samples%':>8} {'inst%':>7} {'lanes':>5}  source")
-    for ln, (s, i, t) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+        tot_l2 += int(r[l2i] or 0)
+        tot_sh += int(r[shi] or 0)
+    print(f"kernel {kname}: {len(body)} SASS instructions, {tot_s} samples, {tot_i} warp instructions, "
+          f"{tot_l2} L2 sectors (global, theoretical), {tot_sh} shared wavefronts")
+    print("stall samples: " + ", ".join(f"{k} {100.0 * v / max(tot_s, 1):.1f}%" for k, v in sorted(stall_tot.items(), key=lambda kv: -kv[1])[:8]))
+    key = {"samples": 0, "inst": 1, "l2": 3, "shared": 4}[os.environ.get("NCU_SORT", "samples")]
+    print(f"{'line':>5} {'samples%':>8} {'inst%':>7} {'lanes':>5} {'L2sec%':>6} {'shwf%':>6} {'top stall':>14}  source")
+    for ln, (s, i, t, l2, sh, st) in sorted(agg.items(), key=lambda kv: -kv[1][key])[:top]:
         text = src[ln - 1].strip() if 0 < ln <= len(src) else "?"
-        print(f"{ln:5d} {100.0 * s / max(tot_s, 1):8.2f} {100.0 * i / max(tot_i, 1):7.2f} {t / max(i, 1):5.1f}  {text[:110]}")
+        ts = max(st.items(), key=lambda kv: kv[1])[0] if st else "-"
+        print(f"{ln:5d} {100.0 * s / max(tot_s, 1):8.2f} {100.0 * i / max(tot_i, 1):7.2f} {t / max(i, 1):5.1f} "
+              f"{100.0 * l2 / max(tot_l2, 1):6.2f} {100.0 * sh / max(tot_sh, 1):6.2f} {ts:>14}  {text[:100]}")
 
 
 if __name__ == "__main__":
