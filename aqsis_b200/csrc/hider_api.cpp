@@ -15,6 +15,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace aqh;
@@ -134,17 +135,14 @@ void chooseTile(const AqhFrameParams& p, bool mbdofHint, int& tw, int& th)
 }
 
 // Build (or reuse) the frame tables: jitter patterns, per-pixel pattern planes, dither, filter
-// weights, lens-cell bounds.  Everything here depends on the options only, not on the geometry.
-int buildTables(AqhHider* h)
+// weights, lens-cell bounds.  Everything here depends on the options only, not on the geometry.  The replay of the
+// renderer's random stream over the frame (the expensive part: one draw sequence per pixel in bucket order) runs on
+// a host thread of its own from aqh_begin_frame on -- while the caller submits its grids -- and is joined by the first
+// thing that needs the tables (joinTables).
+void buildTablesJob(AqhHider* h, std::string key)
 {
+	const double t0 = nowMs();
 	const AqhFrameParams& p = h->params;
-	char key[512];
-	std::snprintf(key, sizeof key, "%d %d|%d %d %d %d|%d %d|%a %a %p|%d %d|%d|%u %u|%d",
-	              p.xres, p.yres, p.crop_xmin, p.crop_xmax, p.crop_ymin, p.crop_ymax, p.xsamples, p.ysamples,
-	              p.filter_xwidth, p.filter_ywidth, (void*)p.filter_func, p.bucket_xsize, p.bucket_ysize, p.jitter,
-	              p.rng_seed, p.rng_predraws, p.n_displays);
-	if(h->tableKey == key && h->tablesUploaded) return AQH_OK;
-	h->layout = replayLayout(p);
 	const ReplayLayout& L = h->layout;
 	// RiWorldBegin reseeds (ri.cpp:660); RenderImage always constructs the jittered sampler
 	// (imagebuffer.cpp:694), which consumes the stream and reseeds with 19.
@@ -172,11 +170,36 @@ int buildTables(AqhHider* h)
 	}
 	h->tableKey = key;
 	h->tablesUploaded = false;
+	h->prepareMs = nowMs() - t0;
+}
+void joinTables(AqhHider* h)
+{
+	if(h->tablesJob.joinable())
+	{
+		h->tablesJob.join();
+		h->stats.prepare_ms = h->prepareMs;
+	}
+}
+int buildTables(AqhHider* h)
+{
+	joinTables(h);
+	const AqhFrameParams& p = h->params;
+	char key[512];
+	std::snprintf(key, sizeof key, "%d %d|%d %d %d %d|%d %d|%a %a %p|%d %d|%d|%u %u|%d",
+	              p.xres, p.yres, p.crop_xmin, p.crop_xmax, p.crop_ymin, p.crop_ymax, p.xsamples, p.ysamples,
+	              p.filter_xwidth, p.filter_ywidth, (void*)p.filter_func, p.bucket_xsize, p.bucket_ysize, p.jitter,
+	              p.rng_seed, p.rng_predraws, p.n_displays);
+	if(h->tableKey == key && h->tablesUploaded) return AQH_OK;
+	h->layout = replayLayout(p);
+	h->tableKey.clear();
+	try { h->tablesJob = std::thread(buildTablesJob, h, std::string(key)); }
+	catch(...) { buildTablesJob(h, key); h->stats.prepare_ms = h->prepareMs; }       // no thread to be had: build in place
 	return AQH_OK;
 }
 
 int uploadTables(AqhHider* h)
 {
+	joinTables(h);
 	if(h->tablesUploaded) return AQH_OK;
 	cudaStream_t st = h->stream;
 	struct Up { DevBuf* b; const void* src; size_t bytes; };
@@ -385,6 +408,8 @@ struct FrameTrace
 	FrameTrace() : on(std::getenv("AQH_TRACE") != nullptr), t0(nowMs()), last(t0) {}
 	void mark(const char* what) { if(!on) return; const double t = nowMs(); std::fprintf(stderr, "[aqh] %-22s +%8.3f ms  (%8.3f)\n", what, t - last, t - t0); last = t; }
 };
+
+int deliverBucketRows(AqhHider* h, const AqhCallbacks* cb, int rowEnd);
 
 int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbacks* imagerCb = nullptr)
 {
@@ -723,6 +748,13 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 	const bool imager = imagerCb && imagerCb->on_imager && download && !zOnly;
 	f.deferDisplay = (h->aovFloats > 0 || imager) ? 1 : 0;
 	f.deferExpose = imager ? 1 : 0;
+	// Streamed delivery: with display callbacks on a single rank the finished rows of every band travel back on the copy
+	// stream as soon as they are filtered, and their buckets are handed to the callbacks (reference order) while the
+	// device hides the next bands.
+	const bool streamed = download && !zOnly && imagerCb && (imagerCb->on_bucket || imagerCb->on_data || imagerCb->on_progress) &&
+	                      std::max(1, p.world_size) == 1 && !f.deferDisplay && h->copyStream && p.filter_mode == AQH_FILTER_REFERENCE_ORDER;
+	if(streamed) bandTileRows = std::min(bandTileRows, std::max(2, (h->nty + 5)/6));
+	h->deliveredRows = -1; h->deliveredBuckets = 0;
 	f.grids = h->dGrids.as<GridRec>(); f.chunkGrid = h->dChunk.as<uint32_t>();
 	f.keyTimes = h->dKeyTimes.as<float>(); f.splitLines = h->dSplit.as<float4>();
 	f.nPos = h->nPos; f.nVerts = h->nVerts; f.nGrids = (int)nGrids;
@@ -879,6 +911,30 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 		}
 	}
 	S.n_bands = (int64_t)bands.size();
+	S.d2h_bytes = 0;
+	std::vector<int> bandRowsDone(bands.size(), -1);         // streamed delivery: the crop rows below this are on their way to the host
+	if(streamed)
+	{
+		const size_t chBytes = size_t(p.xres)*p.yres*nch*4;
+		if(!h->hChannels.reserve(chBytes)) return h->fail(AQH_ERR_NO_MEMORY, "cudaHostAlloc(channel image)");
+		for(int d = 0; d < p.n_displays; ++d)
+			if(!h->hDisplay[d].reserve(size_t(p.xres)*p.yres*disp.d[d].entrySize)) return h->fail(AQH_ERR_NO_MEMORY, "cudaHostAlloc(display image)");
+		// rows outside the crop window never travel: zero like the device images
+		const int outside[2][2] = {{0, p.crop_ymin}, {p.crop_ymax, p.yres}};
+		for(const auto& o : outside)
+		{
+			if(o[1] <= o[0]) continue;
+			std::memset(h->hChannels.as<unsigned char>() + size_t(o[0])*p.xres*nch*4, 0, size_t(o[1] - o[0])*p.xres*nch*4);
+			for(int d = 0; d < p.n_displays; ++d)
+				std::memset(h->hDisplay[d].as<unsigned char>() + size_t(o[0])*p.xres*disp.d[d].entrySize, 0, size_t(o[1] - o[0])*p.xres*disp.d[d].entrySize);
+		}
+		while(h->readyEv.size() < bands.size())
+		{
+			cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+			h->readyEv.push_back(e);
+		}
+		h->hostStripKey.clear();
+	}
 	CU(h->dBandCursor.reserve(std::max<size_t>(bands.size(), 1)*4), "cudaMalloc(band cursors)");
 	CU(cudaMemsetAsync(h->dBandCursor.p, 0, std::max<size_t>(bands.size(), 1)*4, st), "cudaMemsetAsync");
 	std::unique_lock<std::mutex> filterTable(g_filterTableMutex[h->device & 63], std::defer_lock);
@@ -920,6 +976,24 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 			tableUp = true;
 			bandEvKind.push_back(1);
 			CU(cudaEventRecord(h->bandEv[bandEvKind.size()], st), "cudaEventRecord");
+			if(streamed)
+			{
+				// the band's finished rows go home on the copy stream, behind the filter launch that wrote them
+				CU(cudaStreamWaitEvent(h->copyStream, h->bandEv[bandEvKind.size()], 0), "cudaStreamWaitEvent");
+				const size_t chRow = size_t(p.xres)*nch*4;
+				CU(cudaMemcpyAsync(h->hChannels.as<unsigned char>() + chRow*y0, h->dChannels.as<unsigned char>() + chRow*y0, chRow*size_t(y1 - y0),
+				                   cudaMemcpyDeviceToHost, h->copyStream), "cudaMemcpyAsync(channels)");
+				S.d2h_bytes += (int64_t)(chRow*size_t(y1 - y0));
+				for(int d = 0; d < p.n_displays; ++d)
+				{
+					const size_t dRow = size_t(p.xres)*disp.d[d].entrySize;
+					CU(cudaMemcpyAsync(h->hDisplay[d].as<unsigned char>() + dRow*y0, h->dDisplay[d].as<unsigned char>() + dRow*y0, dRow*size_t(y1 - y0),
+					                   cudaMemcpyDeviceToHost, h->copyStream), "cudaMemcpyAsync(display)");
+					S.d2h_bytes += (int64_t)(dRow*size_t(y1 - y0));
+				}
+				CU(cudaEventRecord(h->readyEv[b], h->copyStream), "cudaEventRecord");
+				bandRowsDone[b] = y1;
+			}
 		}
 		filtNext = std::max(filtNext, filtEnd);
 	}
@@ -958,11 +1032,27 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 	CU(cudaEventRecord(h->ev[3], st), "cudaEventRecord");
 
 	// ---- results
-	struct { uint32_t cursor, err; uint32_t pad[2]; unsigned long long ctr[18]; } misc;
-	CU(cudaMemcpyAsync(&misc, h->dMisc.p, sizeof misc, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(counters)");
 	tr.mark("launched filter");
 	const double tDown0 = nowMs();
-	S.d2h_bytes = 0;
+	if(streamed)
+	{
+		// hand over the buckets of every bucket row as soon as all of its crop rows have arrived
+		h->deliveredRows = L.by0;
+		for(size_t b = 0; b < bands.size(); ++b)
+		{
+			if(bandRowsDone[b] < 0) continue;
+			CU(cudaEventSynchronize(h->readyEv[b]), "cudaEventSynchronize(band rows)");
+			int rowEnd = h->deliveredRows;
+			while(rowEnd < L.by1 && std::min(std::min((rowEnd + 1)*p.bucket_ysize, p.yres), p.crop_ymax) <= bandRowsDone[b]) ++rowEnd;
+			h->haveHostImage = true;
+			rc = deliverBucketRows(h, imagerCb, rowEnd);
+			if(rc) return rc;
+		}
+		download = false;             // everything is on the host already
+	}
+	// (a copy into pageable memory: the call returns when the device has done everything queued before it)
+	struct { uint32_t cursor, err; uint32_t pad[2]; unsigned long long ctr[18]; } misc;
+	CU(cudaMemcpyAsync(&misc, h->dMisc.p, sizeof misc, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(counters)");
 	// With a communicator the strips are gathered on the device first (aqh_gather): rank 0 then downloads the whole
 	// frame and the other ranks nothing.
 	const bool gathered = download && h->comm && std::max(1, p.world_size) > 1;
@@ -1013,9 +1103,9 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 		S.d2h_bytes += (int64_t)ob;
 	}
 	CU(cudaStreamSynchronize(st), "cudaStreamSynchronize(frame)");
-	S.download_ms = download ? nowMs() - tDown0 : 0.0;
+	S.download_ms = (download || streamed) ? nowMs() - tDown0 : 0.0;
 	tr.mark("frame sync");
-	h->haveHostImage = download;
+	h->haveHostImage = download || streamed;
 	if(zOnly)
 	{
 		h->haveOccl = true;
@@ -1072,6 +1162,56 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 	return AQH_OK;
 }
 
+// Hand the bucket rows [h->deliveredRows, rowEnd) to the display callbacks, buckets in the reference's row-major order
+// (imagebuffer.cpp:708-733, NextBucket :791-802), from the host images.
+int deliverBucketRows(AqhHider* h, const AqhCallbacks* cb, int rowEnd)
+{
+	const AqhFrameParams& p = h->params;
+	const ReplayLayout& L = h->layout;
+	const int total = (L.bx1 - L.bx0)*(L.by1 - L.by0);
+	std::vector<unsigned char>& bucketData = h->bucketScratch;
+	for(int row = h->deliveredRows; row < rowEnd; ++row)
+	{
+		for(int col = L.bx0; col < L.bx1; ++col)
+		{
+			const int xPos = col*p.bucket_xsize, yPos = row*p.bucket_ysize;
+			const int xSize = std::min(p.bucket_xsize, p.xres - xPos), ySize = std::min(p.bucket_ysize, p.yres - yPos);
+			if(cb->on_bucket)
+			{
+				const float* ch = h->hChannels.as<float>() + (size_t(yPos)*p.xres + xPos)*h->nChannels;
+				if(cb->on_bucket(cb->user, xPos, xPos + xSize, yPos, yPos + ySize, ch, p.xres*h->nChannels, h->nChannels))
+					return h->fail(AQH_ERR_CALLBACK, "on_bucket callback failed");
+			}
+			if(cb->on_data)
+				for(int d = 0; d < p.n_displays; ++d)
+				{
+					const int es = h->dispEntry[d];
+					if(p.display[d].flags & AQH_DISPLAY_SCANLINE_ORDER)
+					{
+						// PkDspyFlagsWantsScanLineOrder: CollapseBucketsToScanlines gathers the buckets of a row; once the bucket
+						// at the right edge arrives SendToDisplay delivers the rows one at a time (ddmanager.cpp:1129-1175)
+						if(xPos + xSize < p.xres) continue;
+						for(int y = yPos; y < yPos + ySize; ++y)
+							if(cb->on_data(cb->user, d, 0, p.xres, y, y + 1, es, h->hDisplay[d].as<unsigned char>() + size_t(y)*p.xres*es))
+								return h->fail(AQH_ERR_CALLBACK, "on_data callback failed");
+						continue;
+					}
+					bucketData.resize(size_t(xSize)*ySize*es);
+					for(int y = 0; y < ySize; ++y)
+						std::memcpy(&bucketData[size_t(y)*xSize*es],
+						            h->hDisplay[d].as<unsigned char>() + (size_t(yPos + y)*p.xres + xPos)*es, size_t(xSize)*es);
+					if(cb->on_data(cb->user, d, xPos, xPos + xSize, yPos, yPos + ySize, es, bucketData.data()))
+						return h->fail(AQH_ERR_CALLBACK, "on_data callback failed");
+				}
+			++h->deliveredBuckets;
+			if(cb->on_progress) cb->on_progress(cb->user, (100.0f*h->deliveredBuckets)/static_cast<float>(total));
+		}
+		h->deliveredRows = row + 1;
+	}
+	if(rowEnd >= L.by1 && cb->on_progress) cb->on_progress(cb->user, 100.0f);
+	return AQH_OK;
+}
+
 } // namespace
 
 // =====================================================================================
@@ -1105,6 +1245,7 @@ int aqh_destroy(AqhHider* h)
 {
 	if(!h) return AQH_OK;
 	cudaSetDevice(h->device);
+	joinTables(h);
 	cudaStreamSynchronize(h->stream);
 	aqh_comm_destroy(h);
 	DevBuf* bufs[] = {&h->dPraw, &h->dCi, &h->dOi, &h->dCulled, &h->dP4, &h->dCO, &h->dGrids, &h->dChunk, &h->dKeyTimes, &h->dSplit,
@@ -1118,6 +1259,7 @@ int aqh_destroy(AqhHider* h)
 	h->hChannels.release(); h->stP.release(); h->stCi.release(); h->stOi.release(); h->stCulled.release();
 	for(int i = 0; i < 8; ++i) if(h->ev[i]) cudaEventDestroy(h->ev[i]);
 	for(cudaEvent_t e : h->chunkEv) cudaEventDestroy(e);
+	for(cudaEvent_t e : h->readyEv) cudaEventDestroy(e);
 	for(cudaEvent_t e : h->bandEv) cudaEventDestroy(e);
 	if(h->copyStream) cudaStreamDestroy(h->copyStream);
 	if(h->ownStream && h->stream) cudaStreamDestroy(h->stream);
@@ -1210,10 +1352,8 @@ int aqh_begin_frame(AqhHider* h, const AqhFrameParams* p)
 	if(h->params.world_size < 1) { h->params.world_size = 1; h->params.rank = 0; }
 	if(!h->params.filter_func) h->params.filter_func = aqh_gaussian_filter;
 	std::memset(&h->stats, 0, sizeof h->stats);
-	const double t0 = nowMs();
-	rc = buildTables(h);
+	rc = buildTables(h);          // starts the frame-table job; prepare_ms is reported when it is joined
 	if(rc) return rc;
-	h->stats.prepare_ms = nowMs() - t0;
 	resetFrameGrids(h);
 	h->aovFloats = 0;
 	for(int a = 0; a < h->params.n_aovs; ++a) h->aovFloats += h->params.aov[a].n_floats;
@@ -1388,49 +1528,9 @@ int aqh_end_frame(AqhHider* h, const AqhCallbacks* cb)
 	if(rc) return rc;
 	if(!cb || (!cb->on_bucket && !cb->on_data && !cb->on_progress)) return AQH_OK;
 	if(!h->haveHostImage) return AQH_OK;          // a rank whose strips were gathered to rank 0: the displays live there
-	// Buckets in the reference's row-major order (imagebuffer.cpp:708-733, NextBucket :791-802).
-	const AqhFrameParams& p = h->params;
-	const ReplayLayout& L = h->layout;
-	std::vector<unsigned char> bucketData;
-	const int total = (L.bx1 - L.bx0)*(L.by1 - L.by0);
-	int done = 0;
-	for(int row = L.by0; row < L.by1; ++row)
-		for(int col = L.bx0; col < L.bx1; ++col)
-		{
-			const int xPos = col*p.bucket_xsize, yPos = row*p.bucket_ysize;
-			const int xSize = std::min(p.bucket_xsize, p.xres - xPos), ySize = std::min(p.bucket_ysize, p.yres - yPos);
-			if(cb->on_bucket)
-			{
-				const float* ch = h->hChannels.as<float>() + (size_t(yPos)*p.xres + xPos)*h->nChannels;
-				if(cb->on_bucket(cb->user, xPos, xPos + xSize, yPos, yPos + ySize, ch, p.xres*h->nChannels, h->nChannels))
-					return h->fail(AQH_ERR_CALLBACK, "on_bucket callback failed");
-			}
-			if(cb->on_data)
-				for(int d = 0; d < p.n_displays; ++d)
-				{
-					const int es = h->dispEntry[d];
-					if(p.display[d].flags & AQH_DISPLAY_SCANLINE_ORDER)
-					{
-						// PkDspyFlagsWantsScanLineOrder: CollapseBucketsToScanlines gathers the buckets of a row; once the bucket
-						// at the right edge arrives SendToDisplay delivers the rows one at a time (ddmanager.cpp:1129-1175)
-						if(xPos + xSize < p.xres) continue;
-						for(int y = yPos; y < yPos + ySize; ++y)
-							if(cb->on_data(cb->user, d, 0, p.xres, y, y + 1, es, h->hDisplay[d].as<unsigned char>() + size_t(y)*p.xres*es))
-								return h->fail(AQH_ERR_CALLBACK, "on_data callback failed");
-						continue;
-					}
-					bucketData.resize(size_t(xSize)*ySize*es);
-					for(int y = 0; y < ySize; ++y)
-						std::memcpy(&bucketData[size_t(y)*xSize*es],
-						            h->hDisplay[d].as<unsigned char>() + (size_t(yPos + y)*p.xres + xPos)*es, size_t(xSize)*es);
-					if(cb->on_data(cb->user, d, xPos, xPos + xSize, yPos, yPos + ySize, es, bucketData.data()))
-						return h->fail(AQH_ERR_CALLBACK, "on_data callback failed");
-				}
-			++done;
-			if(cb->on_progress) cb->on_progress(cb->user, (100.0f*done)/static_cast<float>(total));
-		}
-	if(cb->on_progress) cb->on_progress(cb->user, 100.0f);
-	return AQH_OK;
+	if(h->deliveredRows >= h->layout.by1) return AQH_OK;        // renderFrame handed everything over while the device was busy
+	if(h->deliveredRows < 0) h->deliveredRows = h->layout.by0;
+	return deliverBucketRows(h, cb, h->layout.by1);    // whatever renderFrame has not handed over while the device was still busy
 }
 
 int aqh_set_csg_tree(AqhHider* h, int n_nodes, const int32_t* type, const int32_t* parent)
@@ -1487,6 +1587,7 @@ int aqh_clear_caches(AqhHider* h)
 {
 	if(!h) return AQH_ERR_BAD_PARAMS;
 	if(h->inFrame) return h->fail(AQH_ERR_STATE, "aqh_clear_caches inside a frame");
+	joinTables(h);
 	h->tableKey.clear(); h->tablesUploaded = false;
 	return AQH_OK;
 }

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -117,6 +118,8 @@ struct AqhHider
 	std::vector<float> dither, filterTab, dofBounds;
 	std::vector<uint8_t> shuf8;
 	bool tablesUploaded = false;
+	std::thread tablesJob;         // builds the frame tables while the caller submits grids (hider_api.cpp: buildTables / joinTables)
+	double prepareMs = 0.0;
 	// grids of the frame (host tables)
 	std::vector<int32_t> gcu, gcv, gnkeys;
 	std::vector<uint32_t> gflags;
@@ -176,6 +179,10 @@ struct AqhHider
 	// pipelined upload: host grids travel in chunks on copyStream while the main stream projects/bins the previous chunk
 	cudaStream_t copyStream = nullptr;
 	std::vector<cudaEvent_t> chunkEv;
+	std::vector<cudaEvent_t> readyEv;   // streamed delivery: a band's finished rows have arrived in the host images
+	int deliveredRows = -1;             // bucket rows already handed to the display callbacks (-1: none, not even started)
+	int deliveredBuckets = 0;
+	std::vector<unsigned char> bucketScratch;
 	AqhFrameStats stats{};
 	int nChannels = AQH_NUM_CHANNELS;   // floats per pixel of the channel buffer: 9 + the frame's AOV floats
 	// NCCL communicator for the gather of the strips (hider_shard.cpp)
