@@ -5,7 +5,7 @@ that the shared library exports every symbol the header declares.
 """
 import ctypes as C
 
-AQH_ABI_VERSION = 2
+AQH_ABI_VERSION = 3
 
 # AqhStatus
 AQH_OK = 0
@@ -36,6 +36,7 @@ GRID_USES_CSG = 1 << 5
 GRID_POINTS = 1 << 6
 GRID_CULL_BACKFACING = 1 << 7
 GRID_CULL_TRANSPARENT = 1 << 8
+GRID_TRIM_OUTSIDE = 1 << 9
 CSG_PRIMITIVE, CSG_UNION, CSG_INTERSECTION, CSG_DIFFERENCE = 0, 1, 2, 3
 DISPLAY_SCANLINE_ORDER = 1
 MAX_RANKS, MAX_AOVS, MAX_AOV_FLOATS = 64, 8, 21
@@ -125,7 +126,8 @@ class GridDesc(C.Structure):
         ("N", C.POINTER(C.c_float)),
         ("radius", C.POINTER(C.c_float)),
         ("csg_node", C.c_int32),
-        ("reserved", C.c_int32 * 3),
+        ("trim_set", C.c_int32),
+        ("trim_uv", C.POINTER(C.c_float)),
     ]
 
 
@@ -138,6 +140,7 @@ class GridBlock(C.Structure):
         ("memory_space", C.c_int32),
         ("reserved", C.c_int32 * 3),
         ("aov", C.c_void_p), ("Ng", C.c_void_p), ("N", C.c_void_p), ("radius", C.c_void_p), ("csg_node", C.c_void_p),
+        ("trim_set", C.c_void_p), ("trim_uv", C.c_void_p),
     ]
 
 

@@ -70,7 +70,8 @@ void resetFrameGrids(AqhHider* h)
 	h->nVerts = h->nPos = 0;
 	h->anyCi = h->anyOi = h->anyCulled = false; h->allCi = h->allOi = true;
 	h->gcsg.clear(); h->csgType.clear(); h->csgParent.clear(); h->csgSlot.clear(); h->csgKids.clear(); h->csgOrder.clear();
-	h->hxAov.clear(); h->hxNg.clear(); h->hxN.clear(); h->hxRadius.clear();
+	h->hxAov.clear(); h->hxNg.clear(); h->hxN.clear(); h->hxRadius.clear(); h->hxTrimUV.clear();
+	h->gtrim.clear(); h->trimSetLoop.clear(); h->trimLoopPoint.clear(); h->trimPoints.clear(); h->anyTrim = h->anyTrimUV = false;
 	h->anyAov = h->anyNg = h->anyN = h->anyRadius = h->anyCSG = h->anyPoints = false;
 	h->upPos = h->upVerts = h->upGrids = h->flushedPos = 0; h->upSegs = 0;
 	h->haveZ = h->sawTransparent = false; h->flushBinEntries = h->nFlushes = 0;
@@ -322,8 +323,15 @@ void buildTiling(AqhHider* h, bool mbdof)
 
 // Everything about one grid that can be wrong, checked BEFORE any state is touched: a rejected grid or block
 // leaves the frame exactly as it was (the caller may skip it and go on).
-int checkGrid(AqhHider* h, int cu, int cv, int nkeys, uint32_t flags, const float* times, int csgNode, const float* radius, const float* Ng)
+int checkGrid(AqhHider* h, int cu, int cv, int nkeys, uint32_t flags, const float* times, int csgNode, const float* radius, const float* Ng,
+              int trimSet = 0, const float* trimUV = nullptr)
 {
+	if(trimSet != 0)
+	{
+		if(trimSet < 0 || trimSet + 1 >= (int)h->trimSetLoop.size()) return h->fail(AQH_ERR_BAD_PARAMS, "trimmed grid without a set of the table given to aqh_set_trim_loops");
+		if(!trimUV) return h->fail(AQH_ERR_BAD_PARAMS, "trimmed grid without surface parameters (trim_uv)");
+		if(flags & AQH_GRID_POINTS) return h->fail(AQH_ERR_BAD_PARAMS, "points are not trimmed");
+	}
 	if(flags & AQH_GRID_POINTS)
 	{
 		// CqMicroPolyGridPoints: cu + 1 points, no second dimension
@@ -361,18 +369,19 @@ GridTablesMark markGridTables(const AqhHider* h)
 void rollbackGridTables(AqhHider* h, const GridTablesMark& m)
 {
 	h->gcu.resize(m.nGrids); h->gcv.resize(m.nGrids); h->gnkeys.resize(m.nGrids); h->gflags.resize(m.nGrids);
-	h->glod.resize(2*m.nGrids); h->gkeyTimes.resize(m.nKeyTimes); h->gcsg.resize(m.nGrids);
+	h->glod.resize(2*m.nGrids); h->gkeyTimes.resize(m.nKeyTimes); h->gcsg.resize(m.nGrids); h->gtrim.resize(m.nGrids);
 	h->recs.n = m.nRecs; h->chunk.n = m.nChunk;
 	h->recVb = m.recVb; h->recPb = m.recPb; h->recKo = m.recKo;
 	h->anyMotionG = m.anyMotionG; h->anyLodG = m.anyLodG; h->anyTriG = m.anyTriG; h->anyCamG = m.anyCamG;
 	h->anyCSG = m.anyCSG; h->anyPoints = m.anyPoints;
 }
 
-int appendGridTables(AqhHider* h, int cu, int cv, int nkeys, uint32_t flags, const float* lod, const float* times, int csgNode)
+int appendGridTables(AqhHider* h, int cu, int cv, int nkeys, uint32_t flags, const float* lod, const float* times, int csgNode, int trimSet = 0)
 {
 	if(h->recKo + (uint64_t)nkeys >= (1u << 24)) return h->fail(AQH_ERR_BAD_PARAMS, "too many motion keys in one frame");
 	h->gcu.push_back(cu); h->gcv.push_back(cv); h->gnkeys.push_back(nkeys); h->gflags.push_back(flags);
 	h->gcsg.push_back((flags & AQH_GRID_USES_CSG) ? csgNode : -1);
+	h->gtrim.push_back(trimSet); h->anyTrim |= trimSet != 0;
 	h->anyCSG |= (flags & AQH_GRID_USES_CSG) != 0; h->anyPoints |= (flags & AQH_GRID_POINTS) != 0;
 	h->glod.push_back(lod ? lod[0] : -1.f); h->glod.push_back(lod ? lod[1] : -1.f);
 	for(int k = 0; k < nkeys; ++k) h->gkeyTimes.push_back(nkeys > 1 ? times[k] : 0.f);
@@ -629,7 +638,7 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 	}
 	// ---- the rarely used arrays: arbitrary output variables, normals for the backface cull, point radii, CSG tables.
 	// Plain copies on the main stream (they are ahead of every kernel that reads them).
-	const float* dAov = nullptr; const float* dNg = nullptr; const float* dNn = nullptr; const float* dRadius = nullptr;
+	const float* dAov = nullptr; const float* dNg = nullptr; const float* dNn = nullptr; const float* dRadius = nullptr; const float* dTrimUV = nullptr;
 	{
 		struct Extra { bool any; DevBuf* buf; size_t perVertex, perPos; const float* Segment::* member; std::vector<float>* staged; const float** out; const char* what; };
 		const size_t A = (size_t)h->aovFloats;
@@ -638,6 +647,7 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 			{h->anyNg, &h->dNg, 3, 0, &Segment::Ng, &h->hxNg, &dNg, "cudaMemcpyAsync(Ng)"},
 			{h->anyN, &h->dNn, 3, 0, &Segment::N, &h->hxN, &dNn, "cudaMemcpyAsync(N)"},
 			{h->anyRadius, &h->dRadius, 0, 1, &Segment::radius, &h->hxRadius, &dRadius, "cudaMemcpyAsync(point radii)"},
+			{h->anyTrimUV, &h->dTrimUV, 2, 0, &Segment::trimUV, &h->hxTrimUV, &dTrimUV, "cudaMemcpyAsync(surface parameters of trimmed grids)"},
 		};
 		for(Extra& x : extras)
 		{
@@ -691,6 +701,20 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 		if(nCsgOrder) CU(cudaMemcpyAsync(tab + 4*nCsg, h->csgOrder.data(), nCsgOrder*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(CSG tree)");
 		CU(cudaStreamSynchronize(st), "cudaStreamSynchronize(CSG tree)");
 	}
+	const size_t nTrimSets = h->trimSetLoop.empty() ? 0 : h->trimSetLoop.size() - 1, nTrimLoops = h->trimLoopPoint.empty() ? 0 : h->trimLoopPoint.size() - 1;
+	if(h->anyTrim)
+	{
+		CU(h->dGridTrim.reserve(std::max<size_t>(nRecs, 1)*4), "cudaMalloc(trim sets of the grids)");
+		CU(cudaMemcpyAsync(h->dGridTrim.p, h->gtrim.data(), nRecs*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(trim sets of the grids)");
+		const size_t words = h->trimSetLoop.size() + h->trimLoopPoint.size() + h->trimPoints.size();
+		CU(h->dTrimTab.reserve(std::max<size_t>(words, 1)*4 + 16), "cudaMalloc(trim loops)");
+		int32_t* tab = h->dTrimTab.as<int32_t>();
+		CU(cudaMemcpyAsync(tab, h->trimSetLoop.data(), h->trimSetLoop.size()*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(trim loops)");
+		CU(cudaMemcpyAsync(tab + h->trimSetLoop.size(), h->trimLoopPoint.data(), h->trimLoopPoint.size()*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(trim loops)");
+		if(!h->trimPoints.empty())
+			CU(cudaMemcpyAsync(tab + h->trimSetLoop.size() + h->trimLoopPoint.size(), h->trimPoints.data(), h->trimPoints.size()*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(trim loops)");
+		CU(cudaStreamSynchronize(st), "cudaStreamSynchronize(trim loops)");
+	}
 	if(nRecs) CU(cudaMemcpyAsync(h->dGrids.p, recs, nRecs*sizeof(GridRec), cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(grid table)");
 	CU(cudaMemcpyAsync(h->dChunk.p, h->chunk.data(), nChunkEntries*4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(chunk table)");
 	if(!h->gkeyTimes.empty())
@@ -743,6 +767,16 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 		const int32_t* tab = h->dCsgTab.as<int32_t>();
 		f.csgType = tab; f.csgParent = tab + nCsg; f.csgSlot = tab + 2*nCsg; f.csgKids = tab + 3*nCsg; f.csgOrder = tab + 4*nCsg;
 	}
+	f.anyTrim = (h->anyTrim && dTrimUV) ? 1 : 0;
+	if(f.anyTrim)
+	{
+		const int32_t* tab = h->dTrimTab.as<int32_t>();
+		f.gridTrim = h->dGridTrim.as<int32_t>();
+		f.trimSetLoop = tab; f.trimLoopPoint = tab + h->trimSetLoop.size();
+		f.trimPoints = reinterpret_cast<const float2*>(tab + h->trimSetLoop.size() + h->trimLoopPoint.size());
+		f.trimUV = reinterpret_cast<const float2*>(dTrimUV);
+	}
+	(void)nTrimSets; (void)nTrimLoops;
 	// the displays may show arbitrary output variables (filtered by later passes) and an imager may still change the
 	// pixels: then the filter only writes the float channel buffer and k_finish exposes / quantises afterwards
 	const bool imager = imagerCb && imagerCb->on_imager && download && !zOnly;
@@ -1138,7 +1172,8 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 		                       &h->dPosTab, &h->dVal1d, &h->dShuf, &h->dPat, &h->dFilt, &h->dDofB, &h->dDither, &h->dTileSlot, &h->dActive,
 		                       &h->dBinCount, &h->dBinOffset, &h->dBinEntries, &h->dMisc, &h->dTileFlags, &h->dPlanes, &h->dPartials,
 		                       &h->dDeepA, &h->dDeepB, &h->dDeepUV, &h->dChannels, &h->dRowOwned, &h->dOccl, &h->dBandCursor,
-		                       &h->dAov, &h->dNg, &h->dNn, &h->dRadius, &h->dGridTail, &h->dGridCsg, &h->dCsgTab, &h->dZKeys, &h->dZKeys2};
+		                       &h->dAov, &h->dNg, &h->dNn, &h->dRadius, &h->dGridTail, &h->dGridCsg, &h->dCsgTab, &h->dZKeys, &h->dZKeys2,
+		                       &h->dTrimUV, &h->dGridTrim, &h->dTrimTab};
 		S.device_bytes = 0;
 		for(const DevBuf* b : all) S.device_bytes += (int64_t)b->cap;
 		for(int d = 0; d < AQH_MAX_DISPLAYS; ++d) S.device_bytes += (int64_t)h->dDisplay[d].cap;
@@ -1252,7 +1287,8 @@ int aqh_destroy(AqhHider* h)
 	                  &h->dPosTab, &h->dVal1d, &h->dShuf, &h->dPat, &h->dFilt, &h->dDofB, &h->dDither, &h->dTileSlot, &h->dActive,
 	                  &h->dBinCount, &h->dBinOffset, &h->dBinEntries, &h->dMisc, &h->dTileFlags, &h->dPlanes, &h->dMask, &h->dPartials,
 	                  &h->dDeepA, &h->dDeepB, &h->dDeepUV, &h->dChannels, &h->dRowOwned, &h->dBandCursor,
-	                  &h->dAov, &h->dNg, &h->dNn, &h->dRadius, &h->dGridTail, &h->dGridCsg, &h->dCsgTab, &h->dZKeys, &h->dZKeys2};
+	                  &h->dAov, &h->dNg, &h->dNn, &h->dRadius, &h->dGridTail, &h->dGridCsg, &h->dCsgTab, &h->dZKeys, &h->dZKeys2,
+		                       &h->dTrimUV, &h->dGridTrim, &h->dTrimTab};
 	for(DevBuf* b : bufs) b->release();
 	for(int d = 0; d < AQH_MAX_DISPLAYS; ++d) { h->dDisplay[d].release(); h->hDisplay[d].release(); }
 	h->dOccl.release(); h->hOccl.release(); h->recs.release(); h->chunk.release();
@@ -1370,7 +1406,7 @@ int aqh_add_grid(AqhHider* h, const AqhGridDesc* g)
 	if(!h->inFrame) return h->fail(AQH_ERR_STATE, "aqh_add_grid outside aqh_begin_frame/aqh_end_frame");
 	if(!g->P) return h->fail(AQH_ERR_BAD_PARAMS, "grid without P");
 	// every check and every allocation comes before the first change of state
-	int rc = checkGrid(h, g->cu, g->cv, g->nkeys, g->flags, g->key_times, g->csg_node, g->radius, g->Ng);
+	int rc = checkGrid(h, g->cu, g->cv, g->nkeys, g->flags, g->key_times, g->csg_node, g->radius, g->Ng, g->trim_set, g->trim_uv);
 	if(rc) return rc;
 	for(int k = 0; k < g->nkeys; ++k)
 		if(!g->P[k]) return h->fail(AQH_ERR_BAD_PARAMS, "grid key without P");
@@ -1383,7 +1419,7 @@ int aqh_add_grid(AqhHider* h, const AqhGridDesc* g)
 		return h->fail(AQH_ERR_NO_MEMORY, "cudaHostAlloc(grid staging)");
 	{
 		const GridTablesMark mark = markGridTables(h);
-		rc = appendGridTables(h, g->cu, g->cv, g->nkeys, g->flags, g->lod_bounds, g->key_times, g->csg_node);
+		rc = appendGridTables(h, g->cu, g->cv, g->nkeys, g->flags, g->lod_bounds, g->key_times, g->csg_node, g->trim_set);
 		if(rc) { rollbackGridTables(h, mark); return rc; }
 	}
 	// the rarely used arrays go to frame-global host copies indexed by the grid's vertex / position offsets
@@ -1394,6 +1430,7 @@ int aqh_add_grid(AqhHider* h, const AqhGridDesc* g)
 		if(g->Ng) { h->hxNg.resize((v0 + nv)*3, 0.f); std::memcpy(&h->hxNg[v0*3], g->Ng, nv*12); h->anyNg = true; }
 		if(g->N) { h->hxN.resize((v0 + nv)*3, 0.f); std::memcpy(&h->hxN[v0*3], g->N, nv*12); h->anyN = true; }
 		if(g->radius && (g->flags & AQH_GRID_POINTS)) { h->hxRadius.resize(p0 + np, 0.f); std::memcpy(&h->hxRadius[p0], g->radius, np*4); h->anyRadius = true; }
+		if(g->trim_set && g->trim_uv) { h->hxTrimUV.resize((v0 + nv)*2, 0.f); std::memcpy(&h->hxTrimUV[v0*2], g->trim_uv, nv*8); h->anyTrimUV = true; }
 	}
 	for(int k = 0; k < g->nkeys; ++k)
 		std::memcpy(h->stP.as<float>() + (h->stPUsed + size_t(k)*nv)*3, g->P[k], nv*12);
@@ -1436,7 +1473,7 @@ int aqh_add_grid_block(AqhHider* h, const AqhGridBlock* b)
 	s.firstGrid = (int64_t)h->gcu.size();
 	s.nGrids = b->n_grids;
 	s.P = b->P; s.Ci = b->Ci; s.Oi = b->Oi; s.culled = b->culled;
-	s.aov = h->aovFloats ? b->aov : nullptr; s.Ng = b->Ng; s.N = b->N; s.radius = b->radius;
+	s.aov = h->aovFloats ? b->aov : nullptr; s.Ng = b->Ng; s.N = b->N; s.radius = b->radius; s.trimUV = b->trim_set ? b->trim_uv : nullptr;
 	s.memorySpace = b->memory_space;
 	size_t ko = 0;
 	// a block is accepted or rejected as a whole: all of its grids are checked before the first one is appended
@@ -1444,7 +1481,7 @@ int aqh_add_grid_block(AqhHider* h, const AqhGridBlock* b)
 	{
 		const int nk = b->nkeys ? b->nkeys[g] : 1;
 		int rc = checkGrid(h, b->cu[g], b->cv[g], nk, b->flags[g], (b->key_times && nk > 1) ? b->key_times + ko : nullptr,
-		                   b->csg_node ? b->csg_node[g] : -1, b->radius, b->Ng);
+		                   b->csg_node ? b->csg_node[g] : -1, b->radius, b->Ng, b->trim_set ? b->trim_set[g] : 0, b->trim_uv);
 		if(rc) return rc;
 		ko += nk;
 	}
@@ -1454,7 +1491,7 @@ int aqh_add_grid_block(AqhHider* h, const AqhGridBlock* b)
 	{
 		const int nk = b->nkeys ? b->nkeys[g] : 1;
 		int rc = appendGridTables(h, b->cu[g], b->cv[g], nk, b->flags[g], b->lod_bounds ? b->lod_bounds + 2*g : nullptr,
-		                          (b->key_times && nk > 1) ? b->key_times + ko : nullptr, b->csg_node ? b->csg_node[g] : -1);
+		                          (b->key_times && nk > 1) ? b->key_times + ko : nullptr, b->csg_node ? b->csg_node[g] : -1, b->trim_set ? b->trim_set[g] : 0);
 		if(rc) { rollbackGridTables(h, mark); return rc; }
 		ko += nk;
 		const int64_t nv = int64_t(b->cu[g]+1)*(b->cv[g]+1);
@@ -1470,6 +1507,7 @@ int aqh_add_grid_block(AqhHider* h, const AqhGridBlock* b)
 	if(b->Ng) h->anyNg = true;
 	if(b->N) h->anyN = true;
 	if(b->radius) h->anyRadius = true;
+	if(s.trimUV) h->anyTrimUV = true;
 	return AQH_OK;
 }
 
@@ -1580,6 +1618,31 @@ int aqh_set_csg_tree(AqhHider* h, int n_nodes, const int32_t* type, const int32_
 	}
 	for(int i = 0; i < n_nodes; ++i) if(!seen[i]) return h->fail(AQH_ERR_BAD_PARAMS, "CSG tree: cycle");
 	h->csgType.swap(ty); h->csgParent.swap(pa); h->csgSlot.swap(slot); h->csgKids.swap(kids); h->csgOrder.swap(order);
+	return AQH_OK;
+}
+
+int aqh_set_trim_loops(AqhHider* h, int n_sets, const int32_t* set_first_loop, const int32_t* loop_first_point, const float* points)
+{
+	if(!h) return AQH_ERR_BAD_PARAMS;
+	if(!h->inFrame) return h->fail(AQH_ERR_STATE, "aqh_set_trim_loops outside aqh_begin_frame/aqh_end_frame");
+	if(h->anyTrim) return h->fail(AQH_ERR_STATE, "the trim loops must be set before the first trimmed grid");
+	if(n_sets < 0 || n_sets > (1 << 20) || (n_sets > 0 && (!set_first_loop || !loop_first_point))) return h->fail(AQH_ERR_BAD_PARAMS, "trim loops");
+	h->trimSetLoop.clear(); h->trimLoopPoint.clear(); h->trimPoints.clear();
+	if(n_sets == 0) return AQH_OK;
+	if(set_first_loop[0] != 0) return h->fail(AQH_ERR_BAD_PARAMS, "trim loops: set_first_loop[0] must be 0");
+	for(int s = 0; s < n_sets; ++s)
+		if(set_first_loop[s+1] < set_first_loop[s]) return h->fail(AQH_ERR_BAD_PARAMS, "trim loops: set_first_loop must not decrease");
+	const int nLoops = set_first_loop[n_sets];
+	if(loop_first_point[0] != 0) return h->fail(AQH_ERR_BAD_PARAMS, "trim loops: loop_first_point[0] must be 0");
+	for(int l = 0; l < nLoops; ++l)
+		if(loop_first_point[l+1] < loop_first_point[l]) return h->fail(AQH_ERR_BAD_PARAMS, "trim loops: loop_first_point must not decrease");
+	const int nPoints = loop_first_point[nLoops];
+	if(nPoints > 0 && !points) return h->fail(AQH_ERR_BAD_PARAMS, "trim loops: points missing");
+	// entry 0 of the per-grid trim_set means "untrimmed": set s is addressed as s + 1, so the device tables carry a leading 0
+	h->trimSetLoop.assign(set_first_loop, set_first_loop + n_sets + 1);
+	h->trimSetLoop.insert(h->trimSetLoop.begin(), 0);
+	h->trimLoopPoint.assign(loop_first_point, loop_first_point + nLoops + 1);
+	h->trimPoints.assign(points, points + size_t(nPoints)*2);
 	return AQH_OK;
 }
 

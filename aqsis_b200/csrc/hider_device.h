@@ -28,7 +28,8 @@ enum : uint32_t
 {
 	VINFO_GRID_MASK  = 0x0fffffffu,
 	VINFO_OPAQUE     = 1u << 28,   // Oi >= 1 in all channels at this vertex (or no Oi)
-	VINFO_MP_VALID   = 1u << 29    // a micropolygon starts at this vertex (iu<cu, iv<cv, not culled; every vertex of a points grid)
+	VINFO_MP_VALID   = 1u << 29,   // a micropolygon starts at this vertex (iu<cu, iv<cv, not culled; every vertex of a points grid)
+	VINFO_MP_TRIMMED = 1u << 30    // a trim curve crosses the micropolygon: its hits are tested against the curves (MarkTrimmed)
 };
 
 // Everything the kernels need about the frame; passed by value (<= 4 KB of kernel params).
@@ -73,6 +74,10 @@ struct DevFrame
 	const int32_t* gridCsg;        // nGrids or null
 	const int32_t* csgType; const int32_t* csgParent; const int32_t* csgSlot; const int32_t* csgKids; const int32_t* csgOrder;
 	int cullTransparentOk;         // limits:zthreshold is not black (micropolygon.cpp:496)
+	// trim curves (aqh_set_trim_loops): per grid 1 + its trim set (0 = untrimmed); set s owns loops [trimSetLoop[s], trimSetLoop[s+1])
+	// (entry 0 is the empty set), loop l the points [trimLoopPoint[l], trimLoopPoint[l+1]); trimUV: surface parameters per vertex
+	int anyTrim;
+	const int32_t* gridTrim; const int32_t* trimSetLoop; const int32_t* trimLoopPoint; const float2* trimPoints; const float2* trimUV;
 	// incremental flushes: per-sample occlusion keys kept in HBM between aqh_flush calls ([row][pixel][sample] of the sample
 	// region; null when the frame was never flushed).  A flush hides only the opaque micropolygons at positions >= binFrom
 	// against them and writes them back; the final frame starts from them and skips the opaque micropolygons below flushedPos.

@@ -91,6 +91,7 @@ struct Segment
 	const float* P = nullptr; const float* Ci = nullptr; const float* Oi = nullptr; const uint8_t* culled = nullptr;
 	// rarely used per-vertex / per-position arrays (block route: the caller's pointers; staged route: null, see AqhHider::hx*)
 	const float* aov = nullptr; const float* Ng = nullptr; const float* N = nullptr; const float* radius = nullptr;
+	const float* trimUV = nullptr;
 	int memorySpace = 0;     // 0 host, 1 device
 	bool staged = false;     // lives in the hider's own pinned staging (pointers are offsets to fix up)
 	bool closed = false;     // a flush consumed it: aqh_add_grid opens a new staged run
@@ -125,12 +126,15 @@ struct AqhHider
 	std::vector<uint32_t> gflags;
 	std::vector<float> glod, gkeyTimes;
 	std::vector<int32_t> gcsg;                      // per grid: its primitive node in the CSG tree or -1
+	std::vector<int32_t> gtrim;                     // per grid: 1 + its trim set, 0 = untrimmed
+	std::vector<int32_t> trimSetLoop, trimLoopPoint; std::vector<float> trimPoints;   // aqh_set_trim_loops
+	bool anyTrim = false, anyTrimUV = false;
 	// CSG tree of the frame (aqh_set_csg_tree): type, parent, slot among the parent's children, child count per node,
 	// and the non-primitive nodes children-before-parents
 	std::vector<int32_t> csgType, csgParent, csgSlot, csgKids, csgOrder;
 	// rarely used arrays of grids handed over one by one (aqh_add_grid): frame-global host copies, indexed like the
 	// device arrays (vertex / position offsets), grown on first use
-	std::vector<float> hxAov, hxNg, hxN, hxRadius;
+	std::vector<float> hxAov, hxNg, hxN, hxRadius, hxTrimUV;
 	bool anyAov = false, anyNg = false, anyN = false, anyRadius = false, anyCSG = false, anyPoints = false;
 	int aovFloats = 0;
 	std::vector<Segment> segments;
@@ -151,7 +155,7 @@ struct AqhHider
 	DevBuf dPlanes, dMask, dPartials, dDeepA, dDeepB, dDeepUV, dChannels, dRowOwned;
 	DevBuf dDisplay[AQH_MAX_DISPLAYS];
 	DevBuf dOccl, dBandCursor;
-	DevBuf dAov, dNg, dNn, dRadius, dGridTail, dGridCsg, dCsgTab;
+	DevBuf dAov, dNg, dNn, dRadius, dGridTail, dGridCsg, dCsgTab, dTrimUV, dGridTrim, dTrimTab;
 	// incremental flushes (aqh_flush): what is already on the device and projected, and the per-sample occlusion keys kept
 	// in HBM between flushes -- (depth key << 32 | position of the winning opaque hit) per sample of the sample region,
 	// [row][pixel][sample]; zKeys2: the nearest hit when the midpoint depth filter keeps the second nearest depth as occlZ

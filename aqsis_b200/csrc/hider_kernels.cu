@@ -98,6 +98,72 @@ __device__ __forceinline__ bool mpOpaqueSlot(const DevFrame& f, const GridRec& g
 }
 
 // ------------------------------------------------------------------------------------
+// Trim curves: CqTrimLoopArray::TrimPoint / LineIntersects over the tessellated loops of one surface
+// (geometry/trimcurve.cpp:145-242).  Rare (trimmed NURBS patches only): out of line.
+__device__ __noinline__ bool trimPointSet(const int32_t* setLoop, const int32_t* loopPoint, const float2* pts, int set, float x, float y)
+{
+	const int l0 = setLoop[set], l1 = setLoop[set + 1];
+	if(l1 == l0) return false;                       // no trim loops at all
+	int cCrosses = 0;
+	for(int l = l0; l < l1; ++l)
+	{
+		const int p0 = loopPoint[l], size = loopPoint[l + 1] - p0;
+		bool oddNodes = false;
+		for(int i = 0, j = size - 1; i < size; j = i++)
+		{
+			const float2 a = pts[p0 + i], b = pts[p0 + j];
+			// does the segment span the point in y, and does its crossing lie on the low-x side of the point?
+			if(((a.y < y) && (b.y >= y)) || ((b.y < y) && (a.y >= y)))
+				if(a.x + (y - a.y) / (b.y - a.y) * (b.x - a.x) < x) oddNodes = !oddNodes;
+		}
+		cCrosses += oddNodes ? 1 : 0;
+	}
+	return !(cCrosses & 1);
+}
+__device__ __noinline__ bool trimLineSet(const int32_t* setLoop, const int32_t* loopPoint, const float2* pts, int set, float2 v1, float2 v2)
+{
+	const int l0 = setLoop[set], l1 = setLoop[set + 1];
+	const float x1 = v1.x, y1 = v1.y, x2 = v2.x, y2 = v2.y;
+	for(int l = l0; l < l1; ++l)
+	{
+		const int p0 = loopPoint[l], size = loopPoint[l + 1] - p0;
+		for(int i = 0, j = size - 1; i < size; j = i++)
+		{
+			const float x3 = pts[p0 + i].x, y3 = pts[p0 + i].y, x4 = pts[p0 + j].x, y4 = pts[p0 + j].y;
+			const float d = (x2-x1)*(y4-y3) - (y2-y1)*(x4-x3);
+			if(d == 0.0f) continue;
+			const float r = ((y1-y3)*(x4-x3) - (x1-x3)*(y4-y3)) / d;
+			const float s = ((y1-y3)*(x2-x1) - (x1-x3)*(y2-y1)) / d;
+			if((r >= 0.0f) && (s >= 0.0f) && (r <= 1.0f) && (s <= 1.0f)) return true;
+		}
+	}
+	return false;
+}
+// BilinearEvaluate (libs/core/bilinear.h:190-224), one component
+__device__ __forceinline__ float bilinearEvaluate(float A, float B, float C, float D, float s, float t)
+{
+	float AB, CD;
+	if(s <= 0.0f) { AB = A; CD = C; }
+	else if(s >= 1.0f) { AB = B; CD = D; }
+	else { AB = (B - A)*s + A; CD = (D - C)*s + C; }
+	if(t <= 0.0f) return AB;
+	if(t >= 1.0f) return CD;
+	return (CD - AB)*t + AB;
+}
+// The per-hit test of a micropolygon a trim curve crosses (CqMicroPolygon::Sample, micropolygon.cpp:1594-1628): the hit's
+// surface parameters, interpolated over the four corners, lie in the trimmed-away region -- and the sense is "inside".
+__device__ __noinline__ bool trimRejectHit(const int32_t* gridTrim, const int32_t* setLoop, const int32_t* loopPoint, const float2* pts,
+                                           const float2* trimUV, uint32_t gi, uint32_t gflags, size_t v0, uint32_t cu, float u, float v)
+{
+	if(gflags & AQH_GRID_TRIM_OUTSIDE) return false;
+	const int set = gridTrim[gi];
+	if(set == 0) return false;      // bCanBeTrimmed (a NURBS surface without loops can be trimmed too: TrimPoint is false everywhere)
+	const float2 A = trimUV[v0], B = trimUV[v0 + 1], C = trimUV[v0 + cu + 1], D = trimUV[v0 + cu + 2];
+	const float rx = bilinearEvaluate(A.x, B.x, C.x, D.x, u, v), ry = bilinearEvaluate(A.y, B.y, C.y, D.y, u, v);
+	return trimPointSet(setLoop, loopPoint, pts, set, rx, ry);
+}
+
+// ------------------------------------------------------------------------------------
 // k_project: one thread per position.
 __global__ void __launch_bounds__(256) k_project(const __grid_constant__ DevFrame f, int64_t pA, int64_t pB)
 {
@@ -162,6 +228,29 @@ __global__ void __launch_bounds__(256) k_project(const __grid_constant__ DevFram
 			// fully transparent micropolygons are dropped from the last shading point down to the first one that is not
 			// black (micropolygon.cpp:493-522): remember the last non-black vertex, k_bin drops what lies behind it
 			if(!(oi0 == 0.f && oi1 == 0.f && oi2 == 0.f)) atomicMax(&f.gridTail[lo], v + 1u);
+		}
+		if(valid && f.anyTrim && !(g.flags & AQH_GRID_POINTS))
+		{
+			// micropolygon.cpp:784-835: a micropolygon whose four corners are all trimmed away and whose edges no trim curve
+			// crosses is dropped; one with any corner trimmed away has its hits tested (MarkTrimmed)
+			const int set = f.gridTrim[lo];
+			if(set != 0)
+			{
+				const float2 A = f.trimUV[vid], B = f.trimUV[vid + 1], C = f.trimUV[vid + cu + 2], D = f.trimUV[vid + cu + 1];
+				const bool outside = (g.flags & AQH_GRID_TRIM_OUTSIDE) != 0;
+				const bool tA = trimPointSet(f.trimSetLoop, f.trimLoopPoint, f.trimPoints, set, A.x, A.y) != outside;
+				const bool tB = trimPointSet(f.trimSetLoop, f.trimLoopPoint, f.trimPoints, set, B.x, B.y) != outside;
+				const bool tC = trimPointSet(f.trimSetLoop, f.trimLoopPoint, f.trimPoints, set, C.x, C.y) != outside;
+				const bool tD = trimPointSet(f.trimSetLoop, f.trimLoopPoint, f.trimPoints, set, D.x, D.y) != outside;
+				if(tA && tB && tC && tD)
+				{
+					if(!trimLineSet(f.trimSetLoop, f.trimLoopPoint, f.trimPoints, set, A, B) &&
+					   !trimLineSet(f.trimSetLoop, f.trimLoopPoint, f.trimPoints, set, B, C) &&
+					   !trimLineSet(f.trimSetLoop, f.trimLoopPoint, f.trimPoints, set, C, D) &&
+					   !trimLineSet(f.trimSetLoop, f.trimLoopPoint, f.trimPoints, set, D, A)) valid = false;
+				}
+				if(valid && (tA || tB || tC || tD)) info |= VINFO_MP_TRIMMED;
+			}
 		}
 		if(opaque) info |= VINFO_OPAQUE;
 		if(valid) info |= VINFO_MP_VALID;
@@ -611,7 +700,8 @@ struct StaticRec   // 40 words
 	uint32_t v0, shade; // hitShadeInfo(): what a transparent hit record carries for the resolve
 	uint32_t pad[2];
 };
-enum : uint32_t { REC_LINEAR = 1u << 28, REC_RARE = 1u << 29 /* lod or triangular */, REC_POINT = 1u << 30 /* a disc: centre Ax,Ay radius Ex */ };
+enum : uint32_t { REC_LINEAR = 1u << 28, REC_RARE = 1u << 29 /* lod, triangular or trimmed */, REC_POINT = 1u << 30 /* a disc: centre Ax,Ay radius Ex */,
+                  REC_TRIM = 1u << 31 /* a trim curve crosses the micropolygon */ };
 
 struct TileCtx
 {
@@ -898,6 +988,7 @@ __device__ __forceinline__ void setupStaticRec(const DevFrame& f, const TileCtx&
 	uint32_t fl = gi;
 	if(c.linear) fl |= REC_LINEAR;
 	if((g.flags & AQH_GRID_TRIANGULAR) || g.lod0 >= 0.0f) fl |= REC_RARE;
+	if(info & VINFO_MP_TRIMMED) fl |= REC_RARE | REC_TRIM;
 	r.flags = fl;
 	{ const uint2 si = hitShadeInfo(g, p); r.v0 = si.x; r.shade = si.y; }
 	r.rect = (uint32_t)gx0 | ((uint32_t)gx1 << 8) | ((uint32_t)gy0 << 16) | ((uint32_t)gy1 << 24);
@@ -958,6 +1049,9 @@ __device__ __forceinline__ void sampleStaticRec(const DevFrame& f, const TileCtx
 				const float lod = sampleLod(f, t, s, idx);
 				if(g.lod0 > lod || lod >= g.lod1) continue;
 			}
+			if(r.flags & REC_TRIM)
+				if(trimRejectHit(f.gridTrim, f.trimSetLoop, f.trimLoopPoint, f.trimPoints, f.trimUV, r.flags & VINFO_GRID_MASK, g.flags,
+				                 r.v0, g.cu_cv & 0xffffu, uv.x, uv.y)) continue;
 			if(g.flags & AQH_GRID_TRIANGULAR)
 				if(triangleSplitReject(f, g, make_float2(x, y), make_float2(0.f, 0.f), D, 0.0f)) continue;
 		}
@@ -1115,6 +1209,8 @@ struct MovCtx
 	float pointR;            // > 0: a disc (CqMicroPolygonPoints), centre = the staged vertex
 	bool isPoint;
 	uint2 shadeInfo;         // hitShadeInfo() of the micropolygon, for its transparent hit records
+	bool trimmed;            // a trim curve crosses the micropolygon
+	uint32_t gridIndex;
 };
 
 // One queued candidate (micropolygon, sample): everything of CqMicroPolygon(Motion)::Sample after the gates
@@ -1150,6 +1246,11 @@ __device__ __forceinline__ void movCandidate(const DevFrame& f, const TileCtx& t
 	if(!edgeTests(hc.X, hc.Y, hc.XM, hc.YM, pos.x, pos.y)) return;
 	const float2 uv = invBilinear(hc.Ax, hc.Ay, hc.Ex, hc.Ey, hc.Fx, hc.Fy, hc.Gx, hc.Gy, hc.linear, pos.x, pos.y);
 	const float D = bilerpZ(hc.z, uv);
+	// (CqMicroPolygonMotion::Sample leaves the per-hit trim test as a todo, micropolygon.cpp:1877-1884: only micropolygons
+	// that do not move are tested)
+	if(c.trimmed && !c.moving)
+		if(trimRejectHit(f.gridTrim, f.trimSetLoop, f.trimLoopPoint, f.trimPoints, f.trimUV, c.gridIndex, c.m.g.flags,
+		                 c.shadeInfo.x, c.m.cu, uv.x, uv.y)) return;
 	if(c.m.g.flags & AQH_GRID_TRIANGULAR)
 		if(triangleSplitReject(f, c.m.g, pos, dofOff, D, time)) return;
 	if(c.opaquePass)
@@ -1207,6 +1308,8 @@ __device__ __forceinline__ bool renderMBOrDof(const DevFrame& f, const TileCtx& 
 	c.pointR = c.isPoint ? f.radius[p] : 0.f;
 	c.cullable = mpCullable(f, m.g);
 	c.shadeInfo = hitShadeInfo(m.g, p);
+	c.trimmed = (info & VINFO_MP_TRIMMED) != 0;
+	c.gridIndex = info & VINFO_GRID_MASK;
 	// ---- stage the key vertices and key bounds in the warp's scratch
 	__syncwarp();
 	{

@@ -80,6 +80,7 @@ def lib():
                                        C.POINTER(ci), C.POINTER(ci)]
     L.aqh_filter_table.argtypes = [C.POINTER(FrameParams), vp, C.POINTER(ci)]
     L.aqh_set_csg_tree.argtypes = [vp, ci, vp, vp]
+    L.aqh_set_trim_loops.argtypes = [vp, ci, vp, vp, vp]
     L.aqh_channel_count.argtypes = [vp, C.POINTER(ci)]
     L.aqh_grid_rank_masks.argtypes = [C.POINTER(FrameParams), C.POINTER(GridBlock), vp]
     L.aqh_grid_row_cost.argtypes = [C.POINTER(FrameParams), C.POINTER(GridBlock), vp]
@@ -256,6 +257,8 @@ class GridArrays:
     N: Optional[object] = None
     radius: Optional[object] = None    # (sum nkeys*nverts,) float32, read for GRID_POINTS grids
     csg_node: Optional[np.ndarray] = None
+    trim_set: Optional[np.ndarray] = None   # per grid: 1 + index of the surface's trim loops, 0 = untrimmed
+    trim_uv: Optional[object] = None         # (sum nverts, 2) float32 surface parameters
     _keep: list = field(default_factory=list, repr=False)
 
     @property
@@ -311,6 +314,8 @@ class GridArrays:
         b.N = bulk(self.N, np.float32)
         b.radius = bulk(self.radius, np.float32)
         b.csg_node = host(self.csg_node, np.int32)
+        b.trim_set = host(self.trim_set, np.int32)
+        b.trim_uv = bulk(self.trim_uv, np.float32)
         b.memory_space = 1 if (hasattr(self.P, "is_cuda") and self.P.is_cuda) else 0
         return b
 
@@ -330,7 +335,8 @@ class GridArrays:
                           Ci=conv(self.Ci, np.float32), Oi=conv(self.Oi, np.float32), nkeys=self.nkeys,
                           key_times=self.key_times, lod_bounds=self.lod_bounds, culled=conv(self.culled, np.uint8),
                           aov=conv(self.aov, np.float32), Ng=conv(self.Ng, np.float32), N=conv(self.N, np.float32),
-                          radius=conv(self.radius, np.float32), csg_node=self.csg_node)
+                          radius=conv(self.radius, np.float32), csg_node=self.csg_node,
+                          trim_set=self.trim_set, trim_uv=conv(self.trim_uv, np.float32))
 
 
 class Hider:
@@ -370,9 +376,12 @@ class Hider:
         csg = getattr(params, "_csg", None)          # (types, parents) attached by the scene generators
         if csg:
             self.set_csg_tree(csg[0], csg[1])
+        trim = getattr(params, "_trim", None)        # (set_first_loop, loop_first_point, points) attached by the scene generators
+        if trim:
+            self.set_trim_loops(*trim)
 
     def add_grid(self, P, cu, cv, Ci=None, Oi=None, flags=abi.GRID_SMOOTH, key_times=None, culled=None, lod_bounds=None,
-                 aov=None, Ng=None, N=None, radius=None, csg_node=-1):
+                 aov=None, Ng=None, N=None, radius=None, csg_node=-1, trim_set=0, trim_uv=None):
         """P: (nkeys, nverts, 3) or (nverts, 3) float32."""
         P = np.ascontiguousarray(P, dtype=np.float32)
         if P.ndim == 2:
@@ -388,6 +397,11 @@ class Hider:
             keep.append(kt)
             g.key_times = kt.ctypes.data_as(C.POINTER(C.c_float))
         g.csg_node = int(csg_node)
+        g.trim_set = int(trim_set)
+        if trim_uv is not None:
+            tuv = np.ascontiguousarray(trim_uv, dtype=np.float32)
+            keep.append(tuv)
+            g.trim_uv = tuv.ctypes.data_as(C.POINTER(C.c_float))
         for name, arr, dt in (("Ci", Ci, np.float32), ("Oi", Oi, np.float32), ("culled", culled, np.uint8),
                               ("aov", aov, np.float32), ("Ng", Ng, np.float32), ("N", N, np.float32), ("radius", radius, np.float32)):
             if arr is not None:
@@ -503,6 +517,12 @@ class Hider:
         n = C.c_int()
         self._check(self._L.aqh_channel_count(self._h, C.byref(n)))
         return n.value
+
+    def set_trim_loops(self, set_first_loop, loop_first_point, points):
+        a = np.ascontiguousarray(set_first_loop, np.int32)
+        b = np.ascontiguousarray(loop_first_point, np.int32)
+        c = np.ascontiguousarray(points, np.float32)
+        self._check(self._L.aqh_set_trim_loops(self._h, len(a) - 1, a.ctypes.data, b.ctypes.data, c.ctypes.data))
 
     def set_csg_tree(self, types, parents):
         t = np.ascontiguousarray(types, np.int32)

@@ -358,6 +358,69 @@ def cull_scene(scale=0.12, seed=SEED + 51):
     return p, g
 
 
+def trim_scene(scale=0.12, seed=SEED + 61, outside_every=3, motion=False, dof=False):
+    """Trimmed NURBS patches as the hider sees them (RiTrimCurve): grids with surface parameters (u, v) per vertex and, per
+    surface, closed trim loops tessellated to polylines (CqTrimLoop::Prepare).  Every third trimmed surface has
+    Attribute "trimcurve" "sense" "outside"; some grids are untrimmed; one set has no loops at all; a loop with a hole
+    (two nested loops) exercises the crossing parity.  The loops ride on params._trim."""
+    xres, yres = max(32, int(640 * scale)), max(32, int(480 * scale))
+    rng = np.random.default_rng(seed)
+    kw = {}
+    if dof:
+        s_ = 0.5 * yres / math.tan(math.radians(20.0))
+        kw["dof"] = (2.8, 0.05, 20.0, s_, s_)
+    if motion:
+        kw["shutter"] = (0.0, 1.0)
+    params = default_params(resolution=(xres, yres), samples=(4, 4), filter=("gaussian", 2.0, 2.0), displays=[_RGBA8], **kw)
+    G = 40
+    cu = cv = 12
+    nv = (cu + 1) * (cv + 1)
+    centers = np.stack([rng.uniform(0, xres, G), rng.uniform(0, yres, G)], axis=1).astype(np.float32)
+    opac = np.where(rng.uniform(size=G) < 0.3, 0.6, 1.0).astype(np.float32)
+    P, Ci, Oi = _grids(rng, centers, 18.0, cu, cv, 25.0, 60.0, opacity=opac)
+    # the transparent grids lie in front of every opaque one (a transparent hit BEHIND an opaque surface that is submitted
+    # later stays in the reference's sample list and changes the rounding of the composite: see DESIGN.md, known deviations)
+    P[opac < 1.0, :, 2] = np.float32(5.0) + (P[opac < 1.0, :, 2] - np.float32(25.0)) * np.float32(0.4)
+    P2 = None
+    if motion:
+        P2 = P.copy()
+        P2[:, :, 0] += rng.uniform(-5, 5, (G, 1)).astype(np.float32)
+        P2[:, :, 1] += rng.uniform(-5, 5, (G, 1)).astype(np.float32)
+    g = _pack(P, Ci, Oi, cu, cv, P2=P2, key_times=(0.0, 1.0) if motion else None)
+    # surface parameters: every grid is a sub-rectangle [u0,u1] x [v0,v1] of its patch's unit square
+    u = np.linspace(0.0, 1.0, cu + 1, dtype=np.float32)
+    v = np.linspace(0.0, 1.0, cv + 1, dtype=np.float32)
+    uu, vv = np.meshgrid(u, v)
+    lo = rng.uniform(0.0, 0.3, (G, 2)).astype(np.float32)
+    hi = rng.uniform(0.7, 1.0, (G, 2)).astype(np.float32)
+    uv = np.empty((G, nv, 2), np.float32)
+    uv[:, :, 0] = lo[:, 0:1] + (hi[:, 0:1] - lo[:, 0:1]) * uu.reshape(1, -1)
+    uv[:, :, 1] = lo[:, 1:2] + (hi[:, 1:2] - lo[:, 1:2]) * vv.reshape(1, -1)
+    g.trim_uv = np.ascontiguousarray(uv.reshape(-1, 2))
+    # trim sets: 0 a disc, 1 a disc with a hole, 2 a star-like loop and a separate small loop, 3 no loops at all
+    def circle(cx, cy, r, n, wobble=0.0):
+        t = np.linspace(0, 2 * math.pi, n, endpoint=False)
+        rr = r * (1.0 + wobble * np.sin(5 * t))
+        return np.stack([cx + rr * np.cos(t), cy + rr * np.sin(t)], axis=1).astype(np.float32)
+    sets = [[circle(0.5, 0.5, 0.33, 24)],
+            [circle(0.5, 0.5, 0.4, 32), circle(0.55, 0.45, 0.15, 16)],
+            [circle(0.45, 0.5, 0.3, 40, wobble=0.35), circle(0.85, 0.85, 0.08, 8)],
+            []]
+    set_first, loop_first, pts = [0], [0], []
+    for loops in sets:
+        for lp in loops:
+            pts.append(lp)
+            loop_first.append(loop_first[-1] + len(lp))
+        set_first.append(set_first[-1] + len(loops))
+    params._trim = (np.asarray(set_first, np.int32), np.asarray(loop_first, np.int32), np.concatenate(pts).astype(np.float32))
+    ts = (np.arange(G) % 5).astype(np.int32)              # 0 = untrimmed, 1..4 = the sets
+    g.trim_set = ts
+    fl = g.flags.copy()
+    fl[(np.arange(G) % outside_every == 1) & (ts != 0)] |= np.uint32(abi.GRID_TRIM_OUTSIDE)
+    g.flags = fl.astype(np.uint32)
+    return params, g
+
+
 def config5_filters():
     """The PixelFilter sweep of config 5: (name, width) pairs run on the config-2 scene."""
     return [(name, float(w)) for name in ("box", "triangle", "gaussian", "catmull-rom", "sinc") for w in range(1, 7)]

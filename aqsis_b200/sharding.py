@@ -90,7 +90,8 @@ def split_grids_for_rank(params, grids: GridArrays, rank, world):
                       lod_bounds=None if grids.lod_bounds is None else np.asarray(grids.lod_bounds).reshape(-1, 2)[idx].ravel(),
                       culled=verts(grids.culled), aov=verts(grids.aov), Ng=verts(grids.Ng), N=verts(grids.N),
                       radius=None if grids.radius is None else np.asarray(grids.radius)[pos_idx],
-                      csg_node=None if grids.csg_node is None else np.asarray(grids.csg_node)[idx])
+                      csg_node=None if grids.csg_node is None else np.asarray(grids.csg_node)[idx],
+                      trim_set=None if grids.trim_set is None else np.asarray(grids.trim_set)[idx], trim_uv=verts(grids.trim_uv))
 
 
 class ImageGather:

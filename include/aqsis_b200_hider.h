@@ -45,7 +45,7 @@ extern "C" {
 #  define AQH_EXPORT
 #endif
 
-#define AQH_ABI_VERSION 2
+#define AQH_ABI_VERSION 3
 
 typedef enum AqhStatus
 {
@@ -89,8 +89,9 @@ enum {
 	                                     raster radius `radius`; cv must be 0, the grid has cu+1 points; constant shading */
 	AQH_GRID_CULL_BACKFACING  = 1u << 7, /* Sides 1: drop micropolygons whose corner normal faces away, (Ng . P) >= 0 in
 	                                     camera space (micropolygon.cpp:431-474); needs Ng and AQH_GRID_CAMERA_SPACE */
-	AQH_GRID_CULL_TRANSPARENT = 1u << 8  /* drop the trailing run of micropolygons with Oi == 0 (micropolygon.cpp:493-522,
+	AQH_GRID_CULL_TRANSPARENT = 1u << 8, /* drop the trailing run of micropolygons with Oi == 0 (micropolygon.cpp:493-522,
 	                                     including the reference's early break at the first non-black vertex) */
+	AQH_GRID_TRIM_OUTSIDE     = 1u << 9  /* Attribute "trimcurve" "sense" "outside" of a trimmed surface (micropolygon.cpp:667-671, 1597-1601) */
 };
 
 enum { AQH_MAX_DISPLAYS = 8, AQH_MAX_DISPLAY_CHANNELS = 16, AQH_MAX_RANKS = 64, AQH_MAX_AOVS = 8, AQH_MAX_AOV_FLOATS = 21 };
@@ -203,7 +204,10 @@ typedef struct AqhGridDesc
 	const float* N;                 /* nverts*3 user normals deciding the facing of Ng (micropolygon.cpp:452-458), may be NULL */
 	const float* radius;            /* AQH_GRID_POINTS: nkeys*nverts raster radii, key-major like P */
 	int32_t csg_node;               /* AQH_GRID_USES_CSG: index of the grid's primitive node in the CSG tree */
-	int32_t reserved[3];
+	int32_t trim_set;               /* index of the surface's trim loops in the table given to aqh_set_trim_loops + 1; 0 = the
+	                                   surface cannot be trimmed (CqSurface::bCanBeTrimmed) */
+	const float* trim_uv;           /* trimmed surfaces: nverts*2 floats, the surface parameters (u, v) of every vertex
+	                                   (pVar(EnvVars_u), pVar(EnvVars_v)) */
 } AqhGridDesc;
 
 /* Many grids, concatenated.  memory_space 0 = host pointers, 1 = device pointers
@@ -228,6 +232,8 @@ typedef struct AqhGridBlock
 	const float* N;                 /* sum(nverts)*3 or NULL */
 	const float* radius;            /* sum(nkeys*nverts) floats (only read for AQH_GRID_POINTS grids) or NULL */
 	const int32_t* csg_node;        /* n_grids, NULL = none */
+	const int32_t* trim_set;        /* n_grids (see AqhGridDesc::trim_set), NULL = no trimmed surfaces */
+	const float* trim_uv;           /* sum(nverts)*2 floats (u, v), read for the grids with a trim set; follows memory_space */
 } AqhGridBlock;
 
 /* IqDDManager::DisplayBucket stand-in: region [xmin,xmax1) x [ymin,ymax1) of the bucket and its float channel
@@ -301,6 +307,17 @@ AQH_EXPORT int aqh_begin_frame(AqhHider* h, const AqhFrameParams* p);
  * node in csg_node.  Resolved per sample exactly like CqCSGTreeNode::ProcessTree (csgtree.cpp:144-351). */
 enum { AQH_CSG_PRIMITIVE = 0, AQH_CSG_UNION = 1, AQH_CSG_INTERSECTION = 2, AQH_CSG_DIFFERENCE = 3 };
 AQH_EXPORT int aqh_set_csg_tree(AqhHider* h, int n_nodes, const int32_t* type, const int32_t* parent);
+
+/* Trim curves (RiTrimCurve) as the hider sees them: per trimmed surface a set of closed loops, every loop the polyline of
+ * (u, v) points CqTrimLoop::Prepare leaves in m_aCurvePoints (geometry/trimcurve.cpp:109-135; evaluating the NURBS
+ * curves is the front end's work).  set s owns the loops [set_first_loop[s], set_first_loop[s+1]), loop l the points
+ * [loop_first_point[l], loop_first_point[l+1]) of `points` (2 floats each).  Call inside a frame before the first grid
+ * with a trim set.  Replaces CqSurface::bIsPointTrimmed / bIsLineIntersecting (geometry/nurbs.h:350-357,
+ * CqTrimLoopArray::TrimPoint / LineIntersects, geometry/trimcurve.cpp:145-242): the device drops the micropolygons that
+ * are trimmed away entirely while busting (micropolygon.cpp:784-835) and tests the hits of the ones the curves cross
+ * (micropolygon.cpp:1594-1628). */
+AQH_EXPORT int aqh_set_trim_loops(AqhHider* h, int n_sets, const int32_t* set_first_loop, const int32_t* loop_first_point,
+                                  const float* points);
 /* Floats per pixel of the channel buffer of the current frame: AQH_NUM_CHANNELS + the AOV floats. */
 AQH_EXPORT int aqh_channel_count(const AqhHider* h, int* n);
 AQH_EXPORT int aqh_add_grid(AqhHider* h, const AqhGridDesc* g);

@@ -63,9 +63,25 @@ def shaderdata_stubs(ref):
     return "\n".join(out) + "\n"
 
 
+def attributes_stubs(ref):
+    """IqAttributes (include/aqsis/core/iattributes.h): every pure virtual but GetStringAttribute, which the trim-curve
+    hit test reads ("trimcurve" "sense") and ref_hider.cpp answers."""
+    src = open(os.path.join(ref, "include/aqsis/core/iattributes.h")).read()
+    out = []
+    for d in re.findall(r"virtual\s+([^;{}]*?)\s*=\s*0\s*;", src, re.S):
+        d = " ".join(d.split())
+        m = re.match(r"(.*?)(\w+)\s*\((.*)\)\s*(const)?$", d)
+        ret, name, args, const = m.group(1).strip(), m.group(2), m.group(3), m.group(4) or ""
+        if name == "GetStringAttribute":
+            continue
+        out.append(f"virtual {ret} {name}({strip_defaults(args)}) {const} {{ refStubAbort(\"IqAttributes::{name}\"); }}")
+    return "\n".join(out) + "\n"
+
+
 def main():
     ref, outdir = sys.argv[1], sys.argv[2]
     os.makedirs(outdir, exist_ok=True)
+    open(os.path.join(outdir, "attributes_stubs.inc"), "w").write(attributes_stubs(ref))
     open(os.path.join(outdir, "renderer_stubs.inc"), "w").write(renderer_stubs(ref))
     open(os.path.join(outdir, "shaderdata_stubs.inc"), "w").write(shaderdata_stubs(ref))
 

@@ -641,6 +641,8 @@ struct GridView
 	const F* aov;                      // nverts * aovFloats or null
 	std::vector<const F*> radius;      // AQH_GRID_POINTS: per key, nverts raster radii
 	int csg;                           // primitive node of the grid in the frame's CSG tree or -1
+	int trimSet;                       // 1 + index of the surface's trim loops, 0 = cannot be trimmed
+	const F* trimUV;                   // nverts*2 surface parameters (pVar(EnvVars_u), pVar(EnvVars_v)) or null
 	std::vector<uint8_t> culledAll;    // caller's culled flags + backface / transparency culls (empty = use `culled`)
 	bool isCulled(int i) const { return culledAll.empty() ? (culled && culled[i]) : culledAll[i] != 0; }
 };
@@ -695,6 +697,8 @@ void buildScene(const Frame& f, const AqhGridBlock& b, Scene& sc)
 		gv.culled = b.culled ? b.culled + vOff : 0;
 		gv.aov = (b.aov && f.aovFloats) ? b.aov + vOff*size_t(f.aovFloats) : 0;
 		gv.csg = ((gv.flags & AQH_GRID_USES_CSG) && b.csg_node) ? b.csg_node[g] : -1;
+		gv.trimSet = (b.trim_set && b.trim_uv && !(gv.flags & AQH_GRID_POINTS)) ? b.trim_set[g] : 0;
+		gv.trimUV = b.trim_uv ? b.trim_uv + vOff*2 : 0;
 		if(gv.flags & AQH_GRID_POINTS)
 		{
 			gv.radius.resize(gv.nkeys);
@@ -774,7 +778,7 @@ void buildScene(const Frame& f, const AqhGridBlock& b, Scene& sc)
 
 // ---------------------------------------------------------------------------------
 // One micropolygon, rebuilt on demand from (grid, index): CqMicroPolygon / CqMicroPolygonMotion.
-struct MPRef { int grid; int index; };
+struct MPRef { int grid; int index; bool trimmed; };
 
 const unsigned Degeneracy_Mask = 0x8000000;                       // micropolygon.h:791
 
@@ -786,6 +790,7 @@ struct MicroPoly
 	Bound bound;                       // m_Bound (union over keys when moving)
 	bool moving;
 	bool point; F radius;              // CqMicroPolygonPoints (geometry/points.h:327-371)
+	bool trimmed;                      // MarkTrimmed: a trim curve crosses the micropolygon (micropolygon.cpp:829-832)
 	// moving only
 	std::vector<V3> keyPts;            // nkeys*4: m_Point0..3 = verts index, +1, +cu+1, +cu+2
 	std::vector<Bound> keyBounds;
@@ -1043,6 +1048,74 @@ bool triangleSplitReject(const Frame& f, const GridView& g, const SampleData& s,
 	return v <= 0;
 }
 
+
+// ---- Trim curves: the tessellated loops of every trimmed surface (what CqTrimLoop::Prepare leaves in m_aCurvePoints),
+// CqTrimLoopArray::TrimPoint / LineIntersects (geometry/trimcurve.cpp:145-242) and the per-hit test of
+// CqMicroPolygon::Sample (micropolygon.cpp:1594-1628).
+struct TrimTable { std::vector<int> setLoop, loopPoint; std::vector<F> pts; };     // set s (1-based) owns loops [setLoop[s], setLoop[s+1])
+TrimTable g_trim;
+bool trimCanBeTrimmed(int set) { return set > 0 && set + 1 < (int)g_trim.setLoop.size(); }     // CqSurfaceNURBS::bCanBeTrimmed is true even without loops
+bool trimPoint(int set, F x, F y)
+{
+	const int l0 = g_trim.setLoop[set], l1 = g_trim.setLoop[set+1];
+	if(l1 == l0) return false;
+	int cCrosses = 0;
+	for(int l = l0; l < l1; ++l)
+	{
+		const int p0 = g_trim.loopPoint[l], size = g_trim.loopPoint[l+1] - p0;
+		bool oddNodes = false;
+		for(int i = 0, j = size - 1; i < size; j = i++)
+		{
+			const F ax = g_trim.pts[2*(p0+i)], ay = g_trim.pts[2*(p0+i)+1], bx = g_trim.pts[2*(p0+j)], by = g_trim.pts[2*(p0+j)+1];
+			if(((ay < y) && (by >= y)) || ((by < y) && (ay >= y)))
+				if(ax + (y - ay) / (by - ay) * (bx - ax) < x)
+					oddNodes = !oddNodes;
+		}
+		cCrosses += oddNodes ? 1 : 0;
+	}
+	return !(cCrosses & 1);
+}
+bool trimLineIntersects(int set, F x1, F y1, F x2, F y2)
+{
+	const int l0 = g_trim.setLoop[set], l1 = g_trim.setLoop[set+1];
+	for(int l = l0; l < l1; ++l)
+	{
+		const int p0 = g_trim.loopPoint[l], size = g_trim.loopPoint[l+1] - p0;
+		for(int i = 0, j = size - 1; i < size; j = i++)
+		{
+			const F x3 = g_trim.pts[2*(p0+i)], y3 = g_trim.pts[2*(p0+i)+1], x4 = g_trim.pts[2*(p0+j)], y4 = g_trim.pts[2*(p0+j)+1];
+			const F d = (x2-x1)*(y4-y3) - (y2-y1)*(x4-x3);
+			if(d == 0.0f) continue;
+			const F r = ((y1-y3)*(x4-x3) - (x1-x3)*(y4-y3)) / d;
+			const F s = ((y1-y3)*(x2-x1) - (x1-x3)*(y2-y1)) / d;
+			if((r >= 0.0f) && (s >= 0.0f) && (r <= 1.0f) && (s <= 1.0f)) return true;
+		}
+	}
+	return false;
+}
+// BilinearEvaluate, libs/core/bilinear.h:190-224 (one component)
+inline F bilinearEvaluate(F A, F B, F C, F D, F s, F t)
+{
+	F AB, CD;
+	if(s <= 0.0) { AB = A; CD = C; }
+	else if(s >= 1.0) { AB = B; CD = D; }
+	else { AB = (B - A)*s + A; CD = (D - C)*s + C; }
+	if(t <= 0.0) return AB;
+	if(t >= 1.0) return CD;
+	return (CD - AB)*t + AB;
+}
+bool trimRejectHit(const MicroPoly& mp, V2 uv)
+{
+	const GridView& g = *mp.g;
+	if(!mp.trimmed) return false;
+	const bool bOutside = (g.flags & AQH_GRID_TRIM_OUTSIDE) != 0;
+	const int cu = g.cu, i = mp.index;
+	const F* t = g.trimUV;
+	const F rx = bilinearEvaluate(t[2*i], t[2*(i+1)], t[2*(i+cu+1)], t[2*(i+cu+2)], uv.x, uv.y);
+	const F ry = bilinearEvaluate(t[2*i+1], t[2*(i+1)+1], t[2*(i+cu+1)+1], t[2*(i+cu+2)+1], uv.x, uv.y);
+	return trimCanBeTrimmed(g.trimSet) && trimPoint(g.trimSet, rx, ry) && !bOutside;
+}
+
 // CqMicroPolygon::Sample, micropolygon.cpp:1561-1660
 bool sampleStatic(const Frame& f, const MicroPoly& mp, HitTestCache& c, const SampleData& s, F& D, V2& uv, F time, bool usingDof)
 {
@@ -1072,6 +1145,8 @@ bool sampleStatic(const Frame& f, const MicroPoly& mp, HitTestCache& c, const Sa
 	}
 	if(fContains(c, s.position, D, uv))
 	{
+		if(trimRejectHit(mp, uv))
+			return false;
 		if(mp.g->flags & AQH_GRID_TRIANGULAR)
 			if(triangleSplitReject(f, *mp.g, s, D, time, usingDof))
 				return false;
@@ -1150,6 +1225,8 @@ bool sampleMoving(const Frame& f, const MicroPoly& mp, HitTestCache& c, const Sa
 	cachePointInPolyTest(mp, c, points);
 	if(fContains(c, s.position, D, uv))
 	{
+		// (micropolygon.cpp:1877-1884: "Implement trimming of motion blurred surfaces!" -- moving micropolygons are not
+		// trimmed per hit)
 		if(g.flags & AQH_GRID_TRIANGULAR)
 			if(triangleSplitReject(f, g, s, D, time, usingDof))
 				return false;
@@ -2030,6 +2107,24 @@ int orc_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* chann
 					continue;
 				if(points && g.nkeys > 1)
 					continue;                                         // moving points: outside the implemented path
+				// micropolygon.cpp:784-835: trimmed away entirely / crossed by a trim curve
+				bool fTrimmed = false;
+				if(!points && trimCanBeTrimmed(g.trimSet) && g.trimUV)
+				{
+					const bool bOutside = (g.flags & AQH_GRID_TRIM_OUTSIDE) != 0;
+					const F* t = g.trimUV;
+					const int ia = iIndex, ib = iIndex + 1, ic = iIndex + g.cu + 2, id = iIndex + g.cu + 1;
+					bool fTrimA = trimPoint(g.trimSet, t[2*ia], t[2*ia+1]), fTrimB = trimPoint(g.trimSet, t[2*ib], t[2*ib+1]);
+					bool fTrimC = trimPoint(g.trimSet, t[2*ic], t[2*ic+1]), fTrimD = trimPoint(g.trimSet, t[2*id], t[2*id+1]);
+					if(bOutside) { fTrimA = !fTrimA; fTrimB = !fTrimB; fTrimC = !fTrimC; fTrimD = !fTrimD; }
+					if(fTrimA && fTrimB && fTrimC && fTrimD)
+						if(!trimLineIntersects(g.trimSet, t[2*ia], t[2*ia+1], t[2*ib], t[2*ib+1]) &&
+						   !trimLineIntersects(g.trimSet, t[2*ib], t[2*ib+1], t[2*ic], t[2*ic+1]) &&
+						   !trimLineIntersects(g.trimSet, t[2*ic], t[2*ic+1], t[2*id], t[2*id+1]) &&
+						   !trimLineIntersects(g.trimSet, t[2*id], t[2*id+1], t[2*ia], t[2*ia+1]))
+							continue;
+					if(fTrimA || fTrimB || fTrimC || fTrimD) fTrimmed = true;
+				}
 				Bound B;
 				if(points)
 				{
@@ -2077,7 +2172,7 @@ int orc_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* chann
 				for(int i = iXBa; i <= iXBb; i++)
 					for(int j = iYBa; j <= iYBb; j++)
 					{
-						buckets[size_t(j - f.by0)*nbx + (i - f.bx0)].mps.push_back(MPRef{int(gi), iIndex});
+						buckets[size_t(j - f.by0)*nbx + (i - f.bx0)].mps.push_back(MPRef{int(gi), iIndex, fTrimmed});
 						++nEntries;
 					}
 			}
@@ -2099,6 +2194,7 @@ int orc_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* chann
 		for(size_t i = 0; i < bk.mps.size(); ++i)
 		{
 			makeMicroPoly(sc.grids[bk.mps[i].grid], bk.mps[i].index, mp);
+			mp.trimmed = bk.mps[i].trimmed;
 			renderMicroPoly(ctx, mp);
 		}
 		// CombineElements, bucketprocessor.cpp:365-375
@@ -2207,6 +2303,21 @@ int orc_sampler_tables(int xs, int ys, int jitter, float* pos_xy, float* val1d, 
 float orc_filter(int which, float x, float y, float xw, float yw) { return filterEval(which, x, y, xw, yw); }
 // which: 0 box, 1 triangle, 2 gaussian, 3 catmull-rom, 4 sinc, 5 mitchell, 6 disk, 7 bessel; < 0 = go by AqhFrameParams::filter_func again
 void orc_set_filter(int which) { g_forcedFilterKind = (which >= 0 && which < 8) ? which : -1; }
+// The trim loops of the following orc_render calls (what aqh_set_trim_loops gives the product); n_sets = 0 clears them.
+int orc_set_trim_loops(int n_sets, const int32_t* set_first_loop, const int32_t* loop_first_point, const float* points)
+{
+	g_trim = TrimTable();
+	if(n_sets <= 0) return AQH_OK;
+	g_trim.setLoop.push_back(0);
+	g_trim.setLoop.insert(g_trim.setLoop.end(), set_first_loop, set_first_loop + n_sets + 1);
+	const int nLoops = set_first_loop[n_sets];
+	g_trim.loopPoint.assign(loop_first_point, loop_first_point + nLoops + 1);
+	g_trim.pts.assign(points, points + size_t(loop_first_point[nLoops])*2);
+	return AQH_OK;
+}
+int orc_trim_point(int set, float x, float y) { return trimPoint(set, x, y) ? 1 : 0; }
+int orc_trim_line(int set, float x1, float y1, float x2, float y2) { return trimLineIntersects(set, x1, y1, x2, y2) ? 1 : 0; }
+
 // The CSG tree of the following orc_render calls (what aqh_set_csg_tree gives the product); n_nodes = 0 clears it.
 int orc_set_csg_tree(int n_nodes, const int32_t* type, const int32_t* parent)
 {

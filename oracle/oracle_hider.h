@@ -43,6 +43,9 @@ uint32_t orc_random_int(uint32_t range);
 int orc_sampler_tables(int xs, int ys, int jitter, float* pos_xy, float* val1d, int32_t* shuffled);
 float orc_filter(int which, float x, float y, float xw, float yw);
 int orc_set_csg_tree(int n_nodes, const int32_t* type, const int32_t* parent);   /* CSG tree of the following orc_render calls; 0 nodes = none */
+int orc_set_trim_loops(int n_sets, const int32_t* set_first_loop, const int32_t* loop_first_point, const float* points);   /* trim loops of the following orc_render calls; 0 sets = none */
+int orc_trim_point(int set, float x, float y);                       /* CqTrimLoopArray::TrimPoint of set (1-based) */
+int orc_trim_line(int set, float x1, float y1, float x2, float y2);  /* CqTrimLoopArray::LineIntersects */
 void orc_set_filter(int which);   /* pixel filter of the following orc_render calls by index (see oracle_hider.cpp); < 0 = by filter_func */
 void orc_invbilinear(const float* verts8, float px, float py, float* uv);
 float orc_bilerp(float a, float b, float c, float d, float u, float v);

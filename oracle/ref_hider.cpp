@@ -44,6 +44,11 @@
 #include <aqsis/shadervm/ishaderdata.h>
 #include <aqsis/shadervm/ishaderexecenv.h>
 
+// The trim loops of a surface are private members filled by CqTrimLoop::Prepare from NURBS curves (the front end's
+// work); ref_set_trim_loops below fills the tessellated points in directly.
+#define private public
+#include "trimcurve.h"
+#undef private
 #include "renderer.h"
 #include "imagebuffer.h"
 // The occlusion-feedback checker (ref_can_cull below) asks the bucket processor's own CqOcclusionTree; the tree is a
@@ -66,6 +71,7 @@
 #include <cstring>
 #include <limits>
 #include <list>
+#include <memory>
 #include <vector>
 
 #include "oracle_hider.h"
@@ -234,6 +240,74 @@ private:
 	int m_stride, m_offset, m_n;
 };
 
+// The surface parameters u, v of a trimmed grid (pVar(EnvVars_u) ->GetFloat(u, index), micropolygon.cpp:793-800, 1605-1618).
+class RefFloatData : public RefShaderData
+{
+public:
+	explicit RefFloatData(const float* data) : RefShaderData(0), m_f(data) {}
+	virtual EqVariableType Type() const { return type_float; }
+	virtual void GetFloat(TqFloat& res, TqInt index = 0) const { res = m_f[index]; }
+private:
+	const float* m_f;
+};
+
+// ---------------------------------------------------------------------------------------
+// Trim curves.  CqMicroPolygon::Sample asks the grid's SURFACE (bCanBeTrimmed, bIsPointTrimmed) and its ATTRIBUTES
+// ("trimcurve" "sense").  A real CqSurfaceNURBS needs the whole geometry front end; the three trim virtuals it
+// implements are one-liners over its CqTrimLoopArray (geometry/nurbs.h:346-357).  The stand-in below is an object
+// with nothing but a vtable pointer whose table carries those three entries at the slots the compiler assigned to
+// CqSurface's virtuals (read off the pointers to the member functions: Itanium C++ ABI, 1 + byte offset in the
+// vtable), bound to the REFERENCE'S OWN CqTrimLoopArray::TrimPoint / LineIntersects (geometry/trimcurve.cpp, compiled
+// in place).
+struct RefTrimSurface
+{
+	void** vptr;
+	const CqTrimLoopArray* loops;
+};
+static const bool refSurfCanBeTrimmed(const RefTrimSurface*) { return true; }                      // nurbs.h:346-349
+static const bool refSurfIsPointTrimmed(const RefTrimSurface* s, const CqVector2D& p) { return s->loops->TrimPoint(p); }
+static const bool refSurfIsLineIntersecting(const RefTrimSurface* s, const CqVector2D& a, const CqVector2D& b) { return s->loops->LineIntersects(a, b); }
+static void refSurfOther() { refStubAbort("a CqSurface virtual other than the trim queries"); }
+template<class PMF> static size_t vtableSlot(PMF pmf)
+{
+	struct Raw { std::ptrdiff_t ptr, adj; } raw;
+	static_assert(sizeof(PMF) == sizeof(Raw), "pointer to member function layout");
+	std::memcpy(&raw, &pmf, sizeof raw);
+	return size_t(raw.ptr - 1)/sizeof(void*);
+}
+static void** refSurfaceVtable()
+{
+	static void* table[512];
+	static bool built = false;
+	if(!built)
+	{
+		for(void*& e : table) e = reinterpret_cast<void*>(&refSurfOther);
+		typedef const bool (CqSurface::*Q0)() const;
+		typedef const bool (CqSurface::*Q1)(const CqVector2D&) const;
+		typedef const bool (CqSurface::*Q2)(const CqVector2D&, const CqVector2D&) const;
+		table[vtableSlot<Q0>(&CqSurface::bCanBeTrimmed)] = reinterpret_cast<void*>(&refSurfCanBeTrimmed);
+		table[vtableSlot<Q1>(&CqSurface::bIsPointTrimmed)] = reinterpret_cast<void*>(&refSurfIsPointTrimmed);
+		table[vtableSlot<Q2>(&CqSurface::bIsLineIntersecting)] = reinterpret_cast<void*>(&refSurfIsLineIntersecting);
+		built = true;
+	}
+	return table;
+}
+// Attribute "trimcurve" "sense": the only attribute the hit test reads (micropolygon.cpp:1597-1601).
+class RefAttributes : public IqAttributes
+{
+public:
+	explicit RefAttributes(bool outside) : m_sense(outside ? "outside" : "inside") {}
+	virtual const CqString* GetStringAttribute(const char* strName, const char* strParam) const
+	{
+		return (std::strcmp(strName, "trimcurve") == 0 && std::strcmp(strParam, "sense") == 0) ? &m_sense : 0;
+	}
+#include "attributes_stubs.inc"
+private:
+	CqString m_sense;
+};
+std::vector<CqTrimLoopArray> g_trimSets;        // ref_set_trim_loops
+std::vector<RefTrimSurface> g_trimSurfaces;
+
 // ---------------------------------------------------------------------------------------
 // One shaded grid as the hider sees it.
 class RefGrid : public CqMicroPolyGridBase
@@ -255,8 +329,15 @@ public:
 	virtual void Shade(bool) {}
 	virtual void TransferOutputVariables() {}
 	virtual void DeleteVariables(bool) {}
-	virtual CqSurface* pSurface() const { return 0; }
-	virtual const IqConstAttributesPtr pAttributes() const { return IqConstAttributesPtr(); }
+	virtual CqSurface* pSurface() const { return m_surface; }
+	virtual const IqConstAttributesPtr pAttributes() const { return m_attributes; }
+	void setTrim(CqSurface* surface, const IqConstAttributesPtr& attributes, const float* uv, int nverts)
+	{
+		m_surface = surface; m_attributes = attributes;
+		m_u.assign(nverts, 0.f); m_v.assign(nverts, 0.f);
+		for(int i = 0; i < nverts; ++i) { m_u[i] = uv[2*i]; m_v[i] = uv[2*i+1]; }
+		m_uVar.reset(new RefFloatData(m_u.data())); m_vVar.reset(new RefFloatData(m_v.data()));
+	}
 	virtual bool usesCSG() const { return m_csg.get() != 0; }
 	virtual boost::shared_ptr<CqCSGTreeNode> pCSGNode() const { return m_csg; }
 	void setCSGNode(const boost::shared_ptr<CqCSGTreeNode>& n) { m_csg = n; }
@@ -277,6 +358,8 @@ public:
 			case EnvVars_P: return &m_P;
 			case EnvVars_Ci: return m_Ci.valid() ? &m_Ci : 0;
 			case EnvVars_Oi: return m_Oi.valid() ? &m_Oi : 0;
+			case EnvVars_u: return m_uVar.get();
+			case EnvVars_v: return m_vVar.get();
 			default: return 0;
 		}
 	}
@@ -304,6 +387,10 @@ private:
 	float m_lod[2];
 	boost::shared_ptr<CqCSGTreeNode> m_csg;
 	std::vector<std::pair<std::string, RefAovData*> > m_aovs;
+	CqSurface* m_surface = 0;
+	IqConstAttributesPtr m_attributes;
+	std::vector<float> m_u, m_v;
+	std::unique_ptr<RefFloatData> m_uVar, m_vVar;
 };
 
 // The frame's CSG tree (ref_set_csg_tree): real CqCSGTreeNode objects, children attached in node-index order.
@@ -540,6 +627,14 @@ int ref_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* chann
 			if(node < 0 || node >= (int)g_csgNodes.size()) return AQH_ERR_BAD_PARAMS;
 			grid->setCSGNode(g_csgNodes[node]);
 		}
+		const int trimSet = (grids->trim_set && grids->trim_uv) ? grids->trim_set[g] : 0;
+		const bool bOutside = (flags & AQH_GRID_TRIM_OUTSIDE) != 0;
+		if(trimSet != 0)
+		{
+			if(trimSet < 0 || trimSet > (int)g_trimSurfaces.size()) return AQH_ERR_BAD_PARAMS;
+			grid->setTrim(reinterpret_cast<CqSurface*>(&g_trimSurfaces[trimSet - 1]), IqConstAttributesPtr(new RefAttributes(bOutside)),
+			              grids->trim_uv + vo*2, (int)nv);
+		}
 		if(aovFloats && grids->aov)
 			for(int a = 0, at = 0; a < p.n_aovs; at += p.aov[a].n_floats, ++a)
 				grid->addAov(p.aov[a].name, grids->aov + vo*aovFloats, aovFloats, at, p.aov[a].n_floats);
@@ -596,10 +691,27 @@ int ref_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* chann
 			{
 				const int iIndex = iv*(cu+1) + iu;
 				if(culledAll.empty() ? (grids->culled && grids->culled[vo + iIndex]) : culledAll[iIndex] != 0) continue;
+				// micropolygon.cpp:784-835 (restated like the rest of the loop; the queries are the surface's own)
+				bool fTrimmed = false;
+				if(trimSet != 0 && grid->pSurface()->bCanBeTrimmed())
+				{
+					const float* t = grids->trim_uv + vo*2;
+					CqVector2D vecA(t[2*iIndex], t[2*iIndex+1]), vecB(t[2*(iIndex+1)], t[2*(iIndex+1)+1]);
+					CqVector2D vecC(t[2*(iIndex+cu+2)], t[2*(iIndex+cu+2)+1]), vecD(t[2*(iIndex+cu+1)], t[2*(iIndex+cu+1)+1]);
+					bool fTrimA = grid->pSurface()->bIsPointTrimmed(vecA), fTrimB = grid->pSurface()->bIsPointTrimmed(vecB);
+					bool fTrimC = grid->pSurface()->bIsPointTrimmed(vecC), fTrimD = grid->pSurface()->bIsPointTrimmed(vecD);
+					if(bOutside) { fTrimA = !fTrimA; fTrimB = !fTrimB; fTrimC = !fTrimC; fTrimD = !fTrimD; }
+					if(fTrimA && fTrimB && fTrimC && fTrimD)
+						if(!grid->pSurface()->bIsLineIntersecting(vecA, vecB) && !grid->pSurface()->bIsLineIntersecting(vecB, vecC) &&
+						   !grid->pSurface()->bIsLineIntersecting(vecC, vecD) && !grid->pSurface()->bIsLineIntersecting(vecD, vecA))
+							continue;
+					if(fTrimA || fTrimB || fTrimC || fTrimD) fTrimmed = true;
+				}
 				++nmp;
 				if(nk > 1)
 				{
 					boost::shared_ptr<CqMicroPolygonMotion> pNew(new CqMicroPolygonMotion(grid, iIndex));
+					if(fTrimmed) pNew->MarkTrimmed();
 					for(int k = 0; k < nk; ++k)
 					{
 						const CqVector3D* Pk = reinterpret_cast<const CqVector3D*>(P + size_t(k)*nv*3);
@@ -612,6 +724,7 @@ int ref_render(const AqhFrameParams* pp, const AqhGridBlock* grids, float* chann
 				else
 				{
 					boost::shared_ptr<CqMicroPolygon> pNew(new CqMicroPolygon(grid, iIndex));
+					if(fTrimmed) pNew->MarkTrimmed();
 					pNew->Initialise();
 					image->AddMPG(pNew);
 				}
@@ -669,6 +782,29 @@ int ref_set_csg_tree(int n_nodes, const int32_t* type, const int32_t* parent)
 		if(parent[i] >= 0) g_csgNodes[parent[i]]->AddChild(g_csgNodes[i]);
 	return AQH_OK;
 }
+
+// The trim loops of the following ref_render calls: one CqTrimLoopArray per set, the tessellated points put straight into
+// CqTrimLoop::m_aCurvePoints (what CqTrimLoop::Prepare leaves there).  0 sets = none.
+int ref_set_trim_loops(int n_sets, const int32_t* set_first_loop, const int32_t* loop_first_point, const float* points)
+{
+	g_trimSets.clear(); g_trimSurfaces.clear();
+	if(n_sets <= 0) return AQH_OK;
+	g_trimSets.resize(n_sets);
+	for(int s = 0; s < n_sets; ++s)
+		for(int l = set_first_loop[s]; l < set_first_loop[s+1]; ++l)
+		{
+			CqTrimLoop loop;
+			for(int i = loop_first_point[l]; i < loop_first_point[l+1]; ++i)
+				loop.m_aCurvePoints.push_back(CqVector2D(points[2*i], points[2*i+1]));
+			g_trimSets[s].m_aLoops.push_back(loop);
+		}
+	g_trimSurfaces.resize(n_sets);
+	for(int s = 0; s < n_sets; ++s) { g_trimSurfaces[s].vptr = refSurfaceVtable(); g_trimSurfaces[s].loops = &g_trimSets[s]; }
+	return AQH_OK;
+}
+// CqTrimLoopArray::TrimPoint / LineIntersects of set (1-based) -- the leaves the oracle's restatement is pinned against
+int ref_trim_point(int set, float x, float y) { return g_trimSets[set - 1].TrimPoint(CqVector2D(x, y)) ? 1 : 0; }
+int ref_trim_line(int set, float x1, float y1, float x2, float y2) { return g_trimSets[set - 1].LineIntersects(CqVector2D(x1, y1), CqVector2D(x2, y2)) ? 1 : 0; }
 
 // What aqsis' occlusion culling would do with surfaces of the given raster bounds (xmin, ymin, zmin, xmax, ymax, zmax)
 // arriving after all of `grids` has been rendered: culled[i] = 1 when CqOcclusionTree::canCull(bound) holds in EVERY

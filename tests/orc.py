@@ -26,6 +26,18 @@ def _csg_arrays(params):
     return len(t), t, pa
 
 
+def _trim_arrays(params):
+    """(n_sets, set_first_loop, loop_first_point, points) of the frame's trim loops: carried on the python parameter object
+    as params._trim (the product takes them through aqh_set_trim_loops)."""
+    trim = getattr(params, "_trim", None)
+    if not trim:
+        return 0, None, None, None
+    a = np.ascontiguousarray(trim[0], np.int32)
+    b = np.ascontiguousarray(trim[1], np.int32)
+    c = np.ascontiguousarray(trim[2], np.float32)
+    return len(a) - 1, a, b, c
+
+
 def _filter_name_of(params):
     """The pixel filter to select by NAME: only when the frame carries no function pointer (pure-python parameter
     blocks of bench.py --impl reference); otherwise the checkers recognise the function behind the pointer."""
@@ -92,6 +104,9 @@ def lib():
         L.orc_set_filter.argtypes = [ci]
         L.orc_set_filter.restype = None
         L.orc_set_csg_tree.argtypes = [ci, vp, vp]
+        L.orc_set_trim_loops.argtypes = [ci, vp, vp, vp]
+        L.orc_trim_point.argtypes = [ci, C.c_float, C.c_float]
+        L.orc_trim_line.argtypes = [ci, C.c_float, C.c_float, C.c_float, C.c_float]
         _lib = L
     return _lib
 
@@ -155,9 +170,12 @@ def render(params: FrameParams, grids, nthreads=1):
     L.orc_set_filter(FILTER_INDEX[name] if name else -1)
     n, t, pa = _csg_arrays(params)
     L.orc_set_csg_tree(n, t.ctypes.data if n else None, pa.ctypes.data if n else None)
+    nt, ta, tb, tc = _trim_arrays(params)
+    L.orc_set_trim_loops(nt, ta.ctypes.data if nt else None, tb.ctypes.data if nt else None, tc.ctypes.data if nt else None)
     rc = L.orc_render(C.byref(params), C.byref(b), ch.ctypes.data, ptrs, int(nthreads), C.byref(st))
     L.orc_set_filter(-1)
     L.orc_set_csg_tree(0, None, None)
+    L.orc_set_trim_loops(0, None, None, None)
     if rc:
         raise RuntimeError(f"orc_render failed: {abi.STATUS_NAMES.get(rc, rc)}")
     return ch, outs, st.as_dict()
@@ -176,6 +194,9 @@ def refhider():
         L.ref_set_filter.argtypes = [C.c_char_p]
         L.ref_set_csg_tree.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         L.ref_can_cull.argtypes = [C.POINTER(FrameParams), C.POINTER(GridBlock), C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_set_trim_loops.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_trim_point.argtypes = [C.c_int, C.c_float, C.c_float, ]
+        L.ref_trim_line.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
         _refhider = L
     return _refhider
 
@@ -199,9 +220,12 @@ def render_reference(params: FrameParams, grids):
     L.ref_set_filter(name.encode() if name else None)
     n, t, pa = _csg_arrays(params)
     L.ref_set_csg_tree(n, t.ctypes.data if n else None, pa.ctypes.data if n else None)
+    nt, ta, tb, tc = _trim_arrays(params)
+    L.ref_set_trim_loops(nt, ta.ctypes.data if nt else None, tb.ctypes.data if nt else None, tc.ctypes.data if nt else None)
     rc = L.ref_render(C.byref(params), C.byref(b), ch.ctypes.data, ptrs, C.byref(st))
     L.ref_set_filter(None)
     L.ref_set_csg_tree(0, None, None)
+    L.ref_set_trim_loops(0, None, None, None)
     if rc:
         raise RuntimeError(f"ref_render failed: {abi.STATUS_NAMES.get(rc, rc)}")
     return ch, outs, st.as_dict()

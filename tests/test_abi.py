@@ -48,9 +48,9 @@ def test_struct_layout_matches_header(native_lib):
                                              "rank", "world_size", "strip_rows", "strip_bounds", "deep_hits_per_sample",
                                              "filter_mode", "plane_budget_mb", "reserved"]),
         "AqhGridDesc": (abi.GridDesc, ["cu", "nkeys", "key_times", "P", "Ci", "Oi", "culled", "flags", "lod_bounds", "aov", "Ng", "N",
-                                       "radius", "csg_node"]),
+                                       "radius", "csg_node", "trim_set", "trim_uv"]),
         "AqhGridBlock": (abi.GridBlock, ["n_grids", "cu", "cv", "nkeys", "flags", "lod_bounds", "key_times", "P", "Ci", "Oi",
-                                         "culled", "memory_space", "aov", "Ng", "N", "radius", "csg_node"]),
+                                         "culled", "memory_space", "aov", "Ng", "N", "radius", "csg_node", "trim_set", "trim_uv"]),
         "AqhCallbacks": (abi.Callbacks, ["user", "on_bucket", "on_data", "on_progress", "on_imager"]),
         "AqhFrameStats": (abi.FrameStats, ["prepare_ms", "device_total_ms", "n_grids", "n_deep_hits", "gpu_launches", "d2h_bytes",
                                            "device_bytes", "n_bands", "gather_ms"]),

@@ -163,6 +163,47 @@ def test_special_grids_match_reference():
             assert_identical(p, ch_r, d_r, ch_o, d_o, (flags, lod))
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(motion=True), dict(dof=True), dict(motion=True, dof=True), dict(scale=0.25, outside_every=2)],
+                         ids=["static", "motion", "dof", "motion+dof", "larger"])
+def test_trim_curves_oracle_equals_reference(kw):
+    """Trimmed surfaces: micropolygons trimmed away entirely are dropped while busting, the hits of the ones a trim curve
+    crosses are tested against the curves (micropolygon.cpp:784-835, 1594-1628; moving micropolygons are not tested per hit,
+    :1877-1884).  In the reference run the surface queries are CqTrimLoopArray::TrimPoint / LineIntersects of the
+    reference's own geometry/trimcurve.cpp, asked by the reference's own CqMicroPolygon::Sample."""
+    p, g = scenes.trim_scene(**kw)
+    ch_r, d_r, _ = orc.render_reference(p, g)
+    ch_o, d_o, st = orc.render(p, g, 2)
+    assert_identical(p, ch_r, d_r, ch_o, d_o, ("trim", kw))
+    # and the trimming does something: the untrimmed frame differs
+    g.trim_set, p._trim = None, None
+    ch_u, _, st_u = orc.render(p, g, 2)
+    assert st_u["n_micropolygons"] > st["n_micropolygons"] and not np.array_equal(ch_u, ch_o)
+
+
+def test_trim_leaves_match_reference():
+    """CqTrimLoopArray::TrimPoint / LineIntersects (geometry/trimcurve.cpp:145-242): the oracle's restatement against the
+    reference's own functions on random points and segments, including points exactly on loop vertices' y."""
+    p, g = scenes.trim_scene()
+    n, a, b, c = orc._trim_arrays(p)
+    L, R = orc.lib(), orc.refhider()
+    L.orc_set_trim_loops(n, a.ctypes.data, b.ctypes.data, c.ctypes.data)
+    R.ref_set_trim_loops(n, a.ctypes.data, b.ctypes.data, c.ctypes.data)
+    rng = np.random.default_rng(7)
+    pts = rng.uniform(-0.1, 1.1, (4000, 2)).astype(np.float32)
+    pts[::7, 1] = c.reshape(-1, 2)[rng.integers(0, len(c) // 2, len(pts[::7])), 1]      # on a vertex's y
+    inside = 0
+    for s in range(1, n + 1):
+        for x, y in pts:
+            o, r = L.orc_trim_point(s, float(x), float(y)), R.ref_trim_point(s, float(x), float(y))
+            assert o == r, (s, x, y)
+            inside += 1 - o
+        for (x1, y1), (x2, y2) in zip(pts[:600], pts[600:1200] * 0.2 + pts[:600] * 0.8):
+            assert L.orc_trim_line(s, float(x1), float(y1), float(x2), float(y2)) == R.ref_trim_line(s, float(x1), float(y1), float(x2), float(y2))
+    assert inside > 1000
+    L.orc_set_trim_loops(0, None, None, None)
+    R.ref_set_trim_loops(0, None, None, None)
+
+
 def test_pdiff_reports_zero_differences_between_oracle_and_reference():
     """BASELINE.json's third criterion, with the reference's own tool (thirdparty/pdiff compiled in place): the
     quantised images are binary identical; and the tool does see a real difference (one bucket of pixels shifted)."""
