@@ -37,15 +37,18 @@ def needs_build():
     return False
 
 
-def build(force=False, verbose=False, phase_timing=False):
+def build(force=False, verbose=False, phase_timing=False, defines=(), out=None):
     """phase_timing: a DEVELOPMENT build whose k_hide counts warp cycles per phase (-DAQH_PHASE_TIMING, printed on stderr
     after every frame); never the library that is benchmarked."""
-    if not force and not phase_timing and not needs_build():
+    if not force and not phase_timing and not defines and not out and not needs_build():
         return LIB
+    target = out or LIB
     os.makedirs(LIBDIR, exist_ok=True)
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-O3", "-cudart", "static", "-shared",
-           "-o", LIB + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-o", target + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
+    for d in defines:                      # experimental variants (tools/gpu_ab.sh): python -m aqsis_b200.build --out X -DNAME
+        cmd.insert(1, "-D" + d)
     if phase_timing:
         cmd.insert(1, "-DAQH_PHASE_TIMING")
     if verbose:
@@ -57,9 +60,11 @@ def build(force=False, verbose=False, phase_timing=False):
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stdout + r.stderr)
-    os.replace(LIB + ".tmp", LIB)
-    return LIB
+    os.replace(target + ".tmp", target)
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, phase_timing="--phase-timing" in sys.argv))
+    _out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, phase_timing="--phase-timing" in sys.argv,
+                defines=[a[2:] for a in sys.argv if a.startswith("-D")], out=_out))

@@ -700,7 +700,7 @@ struct StaticRec   // 40 words
 	uint32_t v0, shade; // hitShadeInfo(): what a transparent hit record carries for the resolve
 	uint32_t pad[2];
 };
-enum : uint32_t { REC_LINEAR = 1u << 28, REC_RARE = 1u << 29 /* lod, triangular or trimmed */, REC_POINT = 1u << 30 /* a disc: centre Ax,Ay radius Ex */,
+enum : uint32_t { REC_LINEAR = 1u << 28, REC_RARE = 1u << 29 /* a disc, or lod, triangular or trimmed: sampled by the out-of-line copy */, REC_POINT = 1u << 30 /* a disc: centre Ax,Ay radius Ex */,
                   REC_TRIM = 1u << 31 /* a trim curve crosses the micropolygon */ };
 
 struct TileCtx
@@ -969,7 +969,7 @@ __device__ __forceinline__ void setupStaticRec(const DevFrame& f, const TileCtx&
 		r.Ax = a.x; r.Ay = a.y; r.Ex = pointR;
 		r.z[0] = a.z;
 		r.zminKey = cullableMP ? depthKey(B.mnz) : 0u;
-		r.flags = gi | REC_POINT | ((g.lod0 >= 0.0f) ? REC_RARE : 0u);
+		r.flags = gi | REC_POINT | REC_RARE;
 		{ const uint2 si = hitShadeInfo(g, p); r.v0 = si.x; r.shade = si.y; }
 		r.rect = (uint32_t)gx0 | ((uint32_t)gx1 << 8) | ((uint32_t)gy0 << 16) | ((uint32_t)gy1 << 24);
 		return;
@@ -1001,9 +1001,14 @@ __device__ __noinline__ void setupStaticRecCall(const DevFrame& f, TileCtx t, co
 	setupStaticRec(f, t, pixZ, p, wantOpaque, *r);
 }
 
-template<bool OPAQUE, bool AGG>
-__device__ __forceinline__ void sampleStaticRec(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc,
-                                                const StaticRec& r, int lane)
+// The sampling loop of one record.  RARE = false is the hot instantiation: plain quadrilaterals, nothing but the bound
+// test, the occlusion cull, the edge tests, the inverse bilinear map and the store.  Everything uncommon -- discs of
+// RiPoints, level-of-detail windows, trim curves, the split line of triangular grids -- lives in the RARE = true copy,
+// which exists once per kernel, out of line (sampleStaticRecRare): that code inside the hot loop cost 5-10 % of the
+// whole frame in registers and instruction fetch even when it never ran (profiles/README.md, A/B r2w-r2y).
+template<bool OPAQUE, bool RARE>
+__device__ __forceinline__ void sampleStaticLoop(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc,
+                                                 const StaticRec& r, int lane)
 {
 	const uint32_t rect = r.rect;
 	if(rect == 0) return;
@@ -1027,7 +1032,7 @@ __device__ __forceinline__ void sampleStaticRec(const DevFrame& f, const TileCtx
 		const uint32_t occl = (uint32_t)(s.keys[idx] >> 32);
 		if(zminKey > occl) continue;
 		float2 uv; float D;
-		if(r.flags & REC_POINT)
+		if(RARE && (r.flags & REC_POINT))
 		{
 			// CqMicroPolygonPoints::Sample, geometry/points.cpp:653-664
 			const float dx = r.Ax - x, dy = r.Ay - y;
@@ -1041,7 +1046,7 @@ __device__ __forceinline__ void sampleStaticRec(const DevFrame& f, const TileCtx
 			uv = invBilinear(r.Ax, r.Ay, r.Ex, r.Ey, r.Fx, r.Fy, r.Gx, r.Gy, (r.flags & REC_LINEAR) ? 1 : 0, x, y);
 			D = bilerpZ(r.z, uv);
 		}
-		if(r.flags & REC_RARE)
+		if(RARE)
 		{
 			const GridRec g = f.grids[r.flags & VINFO_GRID_MASK];
 			if(g.lod0 >= 0.0f)
@@ -1060,6 +1065,20 @@ __device__ __forceinline__ void sampleStaticRec(const DevFrame& f, const TileCtx
 		else
 			storeDeep(f, dc, s, idx, D, r.p, uv, r.v0, r.shade, zminKey != 0u);
 	}
+}
+// (the structs travel by value: a reference would pin the caller's copies in local memory)
+__device__ __noinline__ void sampleStaticRecRare(const DevFrame& f, TileCtx t, HideSmem s, DeepCtx dc, const StaticRec* r, int lane, bool opaque)
+{
+	if(opaque) sampleStaticLoop<true, true>(f, t, s, dc, *r, lane);
+	else sampleStaticLoop<false, true>(f, t, s, dc, *r, lane);
+}
+template<bool OPAQUE, bool AGG>
+__device__ __forceinline__ void sampleStaticRec(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc,
+                                                const StaticRec& r, int lane)
+{
+	if(r.rect == 0) return;                                                       // rejected at set-up (its flags are stale)
+	if(r.flags & REC_RARE) sampleStaticRecRare(f, t, s, dc, &r, lane, OPAQUE);      // warp-uniform
+	else sampleStaticLoop<OPAQUE, false>(f, t, s, dc, r, lane);
 }
 
 // ---- motion blur and/or depth of field: RenderMPG_MBOrDof (bucketprocessor.cpp:1221-1469).
