@@ -899,6 +899,7 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 	// carry deep-list heads in shared memory and a deep hit pool in HBM
 	if(devFlags & 2u) h->sawTransparent = true;          // k_project only saw what was new in this call
 	f.anyTransparent = (h->sawTransparent || !f.cullable || h->anyCSG) ? 1 : 0;
+	f.binPartition = (f.useDof || f.anyMotion) ? 0 : 1;
 	LaunchCfg cfg{};
 	CU(hideKernelConfig(f, h->smCount, cfg), "hide kernel configuration (shared memory / occupancy)");
 	if(f.anyTransparent)

@@ -108,9 +108,10 @@ struct DevFrame
 	const uint32_t* activeTiles;   // nActiveTiles tile ids
 	uint32_t* binCount;            // nActiveTiles
 	uint32_t* binOffset;           // nActiveTiles+1
-	unsigned long long* binEntries; // per tile: (depthKey(zmin) << 32 | position index), sorted ascending
+	unsigned long long* binEntries; // per tile: (transparent pass << 63 | depthKey(zmin) >> 1 << 32 | position index), sorted ascending
 	int sortRun;                   // bins are sorted ascending in runs of this many entries
-	uint32_t* tileFlags;           // per active tile: bit0 = has non-opaque MPs
+	int binPartition;              // frames of the static kernel: bin entries carry the pass in their top bit (k_bin<fill>, k_tile_flags)
+	uint32_t* tileFlags;           // per active tile: index of the first bin entry of the transparent pass (k_tile_flags), 0xffffffff = not partitioned
 	// resolved samples: planes [k][y][chunk][x][planeSC] over the sample region: the samples of a pixel are
 	// split in planeChunks chunks of planeSC (<= 64, a multiple of 4) slots, pixel rows padded to planeW pixels
 	// with slack, so that one (row, chunk) of a span of pixels is ONE contiguous, 16-byte aligned piece for the

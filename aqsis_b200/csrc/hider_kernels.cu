@@ -352,6 +352,20 @@ __global__ void __launch_bounds__(256) k_bin(const __grid_constant__ DevFrame f,
 		live = mpTileRange(f, p, a, tr, zminKey);
 	}
 	unsigned nent = 0;
+	unsigned long long entryHi = 0;
+	if(FILL && live)
+	{
+		// bit 63: the micropolygon goes to the transparent pass; bits 32-62: its depth key without the last bit (the order only
+		// steers the culling)
+		// (frames of the static kernel only: binPartition)
+		if(f.binPartition)
+		{
+			const uint32_t info = infoOf(f.P4[p]);
+			const bool deep = f.anyTransparent && !mpOpaqueSlot(f, f.grids[info & VINFO_GRID_MASK], (uint32_t)p, info);
+			entryHi = ((unsigned long long)((zminKey >> 1) | (deep ? 0x80000000u : 0u))) << 32;
+		}
+		else entryHi = (unsigned long long)zminKey << 32;
+	}
 	if(live)
 	for(int ty = tr.ty0; ty <= tr.ty1; ++ty)
 		for(int tx = tr.tx0; tx <= tr.tx1; ++tx)
@@ -361,8 +375,9 @@ __global__ void __launch_bounds__(256) k_bin(const __grid_constant__ DevFrame f,
 			if(FILL)
 			{
 				uint32_t at = atomicAdd(&f.binCount[slot], 1u);
-				// (nearest depth of the micropolygon, position index): sorted per tile by k_bin_sort
-				f.binEntries[f.binOffset[slot] + at] = ((unsigned long long)zminKey << 32) | (uint32_t)p;
+				// (does not use the opaque slot, nearest depth of the micropolygon, position index): sorted per tile by
+				// k_bin_sort -- the opaque micropolygons first, each group front to back
+				f.binEntries[f.binOffset[slot] + at] = entryHi | (uint32_t)p;
 			}
 			else
 			{
@@ -2336,7 +2351,15 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(cons
 			PHASE_BARRIER(0);
 		}
 		const uint32_t binBeg = f.binOffset[slot], binCnt = f.binOffset[slot+1] - binBeg;
+		// Static frames: the opaque micropolygons come first in a (single-run) bin and each pass walks its own part
+		// (tileFlags = where the transparent part starts).  Motion blur / depth of field frames keep whole bins in both
+		// passes (tileFlags bit 0 = the bin has micropolygons for the transparent pass): any extra state in that kernel's
+		// main loop costs more in instruction fetch than the skipped entries would save.
 		const uint32_t tflags = f.tileFlags[slot];
+		const uint32_t split = MBDOF ? 0xffffffffu : (f.anyTransparent ? tflags : binCnt);
+		const bool parted = !MBDOF && split != 0xffffffffu;
+		const bool hasDeep = MBDOF ? (!f.zOnly && f.anyTransparent && (tflags & 1u))
+		                           : (f.anyTransparent && !f.zOnly && (split == 0xffffffffu || split < binCnt));
 		// ---- Render_MPGs: opaque pass, then (if the tile saw non-opaque micropolygons) deep pass
 		// MBDOF kernel: keep ONE copy of the (large) pass body in the instruction stream; the compiler would
 		// otherwise peel the loop.  The static kernel is small enough to profit from the specialised copies.
@@ -2346,12 +2369,13 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(cons
 			if(MBDOF) asm volatile("" : "+r"(pass));
 			if(pass == 1)
 			{
-				if(f.zOnly || !(f.anyTransparent && (tflags & 1u))) break;      // occlusion only needs the opaque pass
+				if(!hasDeep) break;      // (occlusion only needs the opaque pass)
 				PHASE_BARRIER(1);
-				if(tid == 0) { s_next = 0; s_dirty = 0; s_lastRef = 0; }
+				if(tid == 0) { s_next = parted ? split : 0u; s_dirty = 0; s_lastRef = parted ? split : 0u; }
 				if(warp == 0) refreshPixZ(f, t, s, lane);        // the opaque depths are final now
 				PHASE_BARRIER(5);
 			}
+			const uint32_t passBeg = (pass == 1 && parted) ? split : 0u, passEnd = (pass == 0 && parted) ? split : binCnt;
 			for(;;)
 			{
 				uint32_t base = 0;
@@ -2362,14 +2386,14 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(cons
 				const uint32_t GRAB = f.tune[pass] ? (uint32_t)f.tune[pass] : (MBDOF ? 2u : 8u);
 				if(lane == 0) base = atomicAdd(&s_next, GRAB);
 				base = __shfl_sync(0xffffffffu, base, 0);
-				if(base >= binCnt) break;
-				const int cnt = min(GRAB, binCnt - base);
+				if(base >= passEnd) break;
+				const int cnt = min(GRAB, passEnd - base);
 				// tile-wide pacing: one refresh per REFRESH_EVERY bin entries handed out (whichever warp crosses the
 				// mark takes it) -- 16 warps each refreshing on their own schedule spent 12 % of the kernel here
 				const uint32_t REFRESH_EVERY = f.tune[2] ? (uint32_t)f.tune[2] : (MBDOF ? 16u : 96u);
 				{
 					const uint32_t last = *(volatile uint32_t*)&s_lastRef;
-					if(base >= GRAB*NWARPS && base - last >= REFRESH_EVERY && *(volatile uint32_t*)s.dirty)
+					if(base - passBeg >= GRAB*NWARPS && base - last >= REFRESH_EVERY && *(volatile uint32_t*)s.dirty)
 					{
 						uint32_t mine = 0;
 						if(lane == 0) mine = (atomicCAS(&s_lastRef, last, base) == last) ? 1u : 0u;
@@ -2386,11 +2410,13 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(cons
 				// the grab's entries in one coalesced load (one lane each); the first one also decides the early out
 				const unsigned long long ent = (lane < cnt) ? f.binEntries[binBeg + base + lane] : 0ull;
 				{
-					const uint32_t zfirst = __shfl_sync(0xffffffffu, (uint32_t)(ent >> 32), 0);
+					// (partitioned bins carry the depth key without its last bit: a lower bound of the real one)
+					const uint32_t zfirst = MBDOF ? __shfl_sync(0xffffffffu, (uint32_t)(ent >> 32), 0)
+					                              : (__shfl_sync(0xffffffffu, (uint32_t)(ent >> 32), 0) << 1);
 					// (CSG micropolygons are not cullable: with any in the frame the deep pass visits every entry)
 					if(!(pass == 1 && f.anyCSG) && zfirst > *(volatile uint32_t*)s.tileZ)
 					{
-						const uint32_t runEnd = min(binCnt, (base / (uint32_t)f.sortRun + 1u)*(uint32_t)f.sortRun);
+						const uint32_t runEnd = min(passEnd, (base / (uint32_t)f.sortRun + 1u)*(uint32_t)f.sortRun);
 						if(lane == 0) atomicMax(&s_next, runEnd);
 						continue;
 					}
@@ -2426,7 +2452,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(cons
 				}
 			}
 		}
-		PHASE_BARRIER((f.anyTransparent && (tflags & 1u) && !f.zOnly) ? 2 : 1);
+		PHASE_BARRIER(hasDeep ? 2 : 1);
 		if(s.head && !f.zOnly)
 		{
 			// statistics: transparent hits kept by the tile's samples (padding slots hold 0)
@@ -2584,25 +2610,43 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(cons
 #endif
 }
 
-// Mark tiles whose bins contain non-opaque micropolygons (drives the deep pass).
+// Per tile: where the transparent part of its bin starts.  k_bin<fill> puts "goes to the transparent pass" in the top bit of
+// every entry, so a sorted bin is [opaque micropolygons, front to back | the others, front to back] and each pass of k_hide
+// only walks its own part.  A bin longer than one sorted run is only partitioned within its runs: it gets 0xffffffff
+// ("both passes walk everything") unless it is all of one kind.
 __global__ void __launch_bounds__(256) k_tile_flags(const __grid_constant__ DevFrame f)
 {
 	const int slot = blockIdx.x;
-	__shared__ uint32_t s_any;
-	if(threadIdx.x == 0) s_any = 0;
+	__shared__ uint32_t s_opaque;
+	if(threadIdx.x == 0) s_opaque = 0;
 	__syncthreads();
-	uint32_t any = 0;
-	for(uint32_t e = f.binOffset[slot] + threadIdx.x; e < f.binOffset[slot+1] && !any; e += 256)
+	const uint32_t beg = f.binOffset[slot], end = f.binOffset[slot+1];
+	if(!f.binPartition)
 	{
-		const uint32_t p = (uint32_t)f.binEntries[e];
-		const float4 a = f.P4[p];
-		const uint32_t info = infoOf(a);
-		const GridRec g = f.grids[info & VINFO_GRID_MASK];
-		if(!mpOpaqueSlot(f, g, p, info)) any = 1;
+		// motion blur / depth of field frames: bit 0 = the bin holds micropolygons for the transparent pass
+		uint32_t any = 0;
+		for(uint32_t e = beg + threadIdx.x; e < end && !any; e += 256)
+		{
+			const uint32_t p = (uint32_t)f.binEntries[e];
+			const uint32_t info = infoOf(f.P4[p]);
+			if(!mpOpaqueSlot(f, f.grids[info & VINFO_GRID_MASK], p, info)) any = 1;
+		}
+		if(any) s_opaque = 1;
+		__syncthreads();
+		if(threadIdx.x == 0) f.tileFlags[slot] = s_opaque;
+		return;
 	}
-	if(any) s_any = 1;
+	uint32_t mine = 0;
+	for(uint32_t e = beg + threadIdx.x; e < end; e += 256)
+		mine += (f.binEntries[e] >> 63) ? 0u : 1u;
+	mine = __reduce_add_sync(0xffffffffu, mine);
+	if((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_opaque, mine);
 	__syncthreads();
-	if(threadIdx.x == 0) f.tileFlags[slot] = s_any;
+	if(threadIdx.x == 0)
+	{
+		const uint32_t cnt = end - beg, nOpaque = s_opaque;
+		f.tileFlags[slot] = (cnt <= (uint32_t)f.sortRun || nOpaque == 0u || nOpaque == cnt) ? nOpaque : 0xffffffffu;
+	}
 }
 
 // ------------------------------------------------------------------------------------
