@@ -381,8 +381,10 @@ class Bench:
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(str(config))
             if tj and world == 1 and scale == 1.0:
-                traffic = int(tj["dram_bytes_per_launch"])
-                ncu_note = {k: tj[k] for k in ("sm_issue_active_pct", "warp_instructions", "source", "launches_per_frame") if k in tj}
+                # DRAM bytes of the frame's k_hide launches: one captured launch x the launches of a frame (bands)
+                if tj.get("dram_bytes_per_launch"):
+                    traffic = int(tj["dram_bytes_per_launch"]) * int(tj.get("launches_per_frame", 1))
+                ncu_note = {k: tj[k] for k in ("sm_issue_active_pct", "warp_instructions", "source", "launches_per_frame", "dram_bytes_per_launch") if k in tj}
         except Exception:
             pass
         rec["roofline"] = {"bound": "hbm", "kernel": "k_hide", "achieved": achieved, "peak": self.peak, "unit": "GB/s",
