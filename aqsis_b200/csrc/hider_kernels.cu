@@ -17,6 +17,7 @@
 #include "hider_device.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cfloat>
 
 namespace aqh {
@@ -2842,6 +2843,9 @@ __global__ void __launch_bounds__(256) k_filter(const __grid_constant__ DevFrame
 // Weights come from constant memory (uniform index).  Excluded samples are skipped by predication,
 // never multiplied by zero.
 __constant__ float c_filt[49*256 + 64];
+// per (tap, chunk): which groups of four consecutive sample slots can hold a sample inside the tap's filter support at all
+// (launchFilter derives it from the sub-pixel cell every slot's sample lies in); an empty chunk is not even copied
+__constant__ uint16_t c_tapGroups[49*4];
 
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count)
@@ -2891,7 +2895,9 @@ __host__ __device__ __forceinline__ int filterPlaneFloats(const DevFrame& f)
 
 // MB = bytes per mask word (1, 2 or 4).  Four consecutive slots are tested per step:
 // one 32-bit shared load for byte masks, one 64-bit load for 16-bit masks, one 128-bit load for 32-bit masks.
-template<int MB>
+// CHUNKED = more than 64 samples per pixel: a stage is one (fy, fx, 64-slot chunk); chunks and groups of four slots that cannot
+// lie inside the tap's support are skipped (c_tapGroups).  With one chunk per pixel the skip test would cost more than it saves.
+template<int MB, bool CHUNKED>
 __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(const __grid_constant__ DevFrame f, const __grid_constant__ DevDisplays disp, int yBeg, int kBase, int nVal)
 {
 	constexpr int W = FILTER_W;
@@ -2899,7 +2905,7 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(const __grid_consta
 	__shared__ __align__(8) uint64_t s_bar;
 	const int n = f.n, xmax = f.shiftX, ymax = f.shiftY;
 	const int SC = f.planeSC, nCh = f.planeChunks;
-	const bool halo = (nCh == 1);
+	const bool halo = !CHUNKED;
 	const int span = filterSpan(f);
 	const int planeS = filterPlaneFloats(f);
 	float* tile = reinterpret_cast<float*>(fsm);         // [7 value planes][span][SC], planes skewed; ones; mask words
@@ -2930,6 +2936,7 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(const __grid_consta
 		for(int sfx = 0; sfx < nStageFx; ++sfx)
 			for(int c = 0; c < nCh; ++c)
 			{
+				if(CHUNKED && c_tapGroups[(fy*(2*xmax + 1) + sfx)*4 + c] == 0) continue;      // nothing of this chunk can be inside the tap (CTA-uniform)
 				__syncthreads();                         // barrier initialised / everyone is done with the previous stage
 				if(tid == 0)
 				{
@@ -2952,6 +2959,7 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(const __grid_consta
 					const int tap = fy*(2*xmax + 1) + fx;
 					const uint32_t need = (1u << fx) | (1u << (2*xmax + 1 + fy)) | validBit;
 					const float* w = c_filt + tap*n + c*SC;
+					const uint32_t groups = c_tapGroups[tap*4 + c];
 					const int o = (halo ? px + fx : px)*SC;
 					const float* vp = (ch < 7) ? tile + (size_t)ch*planeS + o : ones + (o & 31);
 					if(MB == 1)
@@ -2961,6 +2969,7 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(const __grid_consta
 #pragma unroll 4
 						for(int s4 = 0; s4 < SC/4; ++s4)
 						{
+							if(CHUNKED && !((groups >> s4) & 1u)) continue;
 							const uint32_t m = mp[s4];
 							const float4 v = lds128(vp + 4*s4);
 							if((m & n0) == 0u) { acc += v.x * w[4*s4+0]; ++count; }
@@ -2976,6 +2985,7 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(const __grid_consta
 #pragma unroll 4
 						for(int s4 = 0; s4 < SC/4; ++s4)
 						{
+							if(CHUNKED && !((groups >> s4) & 1u)) continue;
 							const uint2 m = mp[s4];
 							const float4 v = lds128(vp + 4*s4);
 							if((m.x & n0) == 0u) { acc += v.x * w[4*s4+0]; ++count; }
@@ -2990,6 +3000,7 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(const __grid_consta
 #pragma unroll 4
 						for(int s4 = 0; s4 < SC/4; ++s4)
 						{
+							if(CHUNKED && !((groups >> s4) & 1u)) continue;
 							const uint4 m = mp[s4];
 							const float4 v = lds128(vp + 4*s4);
 							if((m.x & need) == 0u) { acc += v.x * w[4*s4+0]; ++count; }
@@ -3180,30 +3191,50 @@ cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, const float
 	cudaError_t e = cudaSuccess;
 	if(spans && uploadTable) e = cudaMemcpyToSymbolAsync(c_filt, hostFilterTab, (size_t)ntapw*4, 0, cudaMemcpyHostToDevice, st);
 	if(e != cudaSuccess) return e;
+	if(spans && uploadTable)
+	{
+		// A sample of sub-pixel cell (sx, sy) lies at an offset in [sx/xs, (sx+1)/xs) x [sy/ys, (sy+1)/ys) of its pixel (jittered
+		// or not); tap (fx, fy) includes it when offset + fx - 0.5 lies within +-xfwo2 (tapMask): cells that cannot satisfy
+		// that -- with one cell of margin -- need not be looked at.  Only a skip list: the per-sample test stays.
+		static uint16_t groupsHost[49*4];
+		const int nx = 2*f.shiftX + 1, ny = 2*f.shiftY + 1;
+		for(int tap = 0; tap < nx*ny && tap < 49; ++tap)
+		{
+			const int fy = tap / nx - f.shiftY, fx = tap % nx - f.shiftX;
+			const double lox = 0.5 - fx - f.xfwo2, hix = 0.5 - fx + f.xfwo2, loy = 0.5 - fy - f.yfwo2, hiy = 0.5 - fy + f.yfwo2;
+			const int sxA = (int)std::floor(lox*f.xs) - 1, sxB = (int)std::ceil(hix*f.xs) + 1;
+			const int syA = (int)std::floor(loy*f.ys) - 1, syB = (int)std::ceil(hiy*f.ys) + 1;
+			for(int c = 0; c < 4; ++c)
+			{
+				uint16_t g = 0;
+				for(int s4 = 0; s4 < f.planeSC/4 && c < f.planeChunks; ++s4)
+					for(int k = 0; k < 4; ++k)
+					{
+						const int i = c*f.planeSC + 4*s4 + k;
+						if(i >= f.n) continue;
+						const int sy = i / f.xs, sx = i % f.xs;
+						if(sx >= sxA && sx <= sxB && sy >= syA && sy <= syB) g |= (uint16_t)(1u << s4);
+					}
+				groupsHost[tap*4 + c] = g;
+			}
+		}
+		e = cudaMemcpyToSymbolAsync(c_tapGroups, groupsHost, sizeof groupsHost, 0, cudaMemcpyHostToDevice, st);
+		if(e != cudaSuccess) return e;
+	}
 	for(int kBase = 0; kBase < 7 + f.aovFloats; kBase += 7)
 	{
 		const int nVal = kBase == 0 ? 7 : std::min(7, 7 + f.aovFloats - kBase);
 		if(spans)
 		{
 			dim3 grid((w + FILTER_W - 1)/FILTER_W, h);
-			if(f.maskBytes == 1)
-			{
-				e = cudaFuncSetAttribute(k_filter_spans<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spanSmem);
-				if(e != cudaSuccess) return e;
-				k_filter_spans<1><<<grid, 8*FILTER_W, spanSmem, st>>>(f, disp, yBeg, kBase, nVal);
-			}
-			else if(f.maskBytes == 2)
-			{
-				e = cudaFuncSetAttribute(k_filter_spans<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spanSmem);
-				if(e != cudaSuccess) return e;
-				k_filter_spans<2><<<grid, 8*FILTER_W, spanSmem, st>>>(f, disp, yBeg, kBase, nVal);
-			}
-			else
-			{
-				e = cudaFuncSetAttribute(k_filter_spans<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spanSmem);
-				if(e != cudaSuccess) return e;
-				k_filter_spans<4><<<grid, 8*FILTER_W, spanSmem, st>>>(f, disp, yBeg, kBase, nVal);
-			}
+#define AQH_SPANS(MB, CH) do { e = cudaFuncSetAttribute(k_filter_spans<MB, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spanSmem); \
+			if(e != cudaSuccess) return e; \
+			k_filter_spans<MB, CH><<<grid, 8*FILTER_W, spanSmem, st>>>(f, disp, yBeg, kBase, nVal); } while(0)
+			const bool chunked = f.planeChunks > 1;
+			if(f.maskBytes == 1) { if(chunked) AQH_SPANS(1, true); else AQH_SPANS(1, false); }
+			else if(f.maskBytes == 2) { if(chunked) AQH_SPANS(2, true); else AQH_SPANS(2, false); }
+			else { if(chunked) AQH_SPANS(4, true); else AQH_SPANS(4, false); }
+#undef AQH_SPANS
 		}
 		else
 		{
