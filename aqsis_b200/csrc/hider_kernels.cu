@@ -1472,8 +1472,10 @@ __device__ __forceinline__ bool renderMBOrDof(const DevFrame& f, const TileCtx& 
 					{
 						const float* times = m.times;
 						// timeAcc of division d: opentime + dt, then + dt once per earlier division (the same additions in the same order)
+						// (lanes past the last division carry no division: they need not add)
 						float acc = accBase;
-						for(int k = 0; k < lane; ++k) acc = acc + dt;
+						const int nAdd = ok ? lane : 0;
+						for(int k = 0; k < nAdd; ++k) acc = acc + dt;
 						uint32_t endKey = 1;
 						while(acc > times[endKey] && endKey < m.nkeys - 1) ++endKey;
 						const uint32_t endKey_1 = endKey - 1;
@@ -1618,10 +1620,16 @@ __device__ __forceinline__ bool renderMBOrDof(const DevFrame& f, const TileCtx& 
 			{
 				const int Wp = eX - sX;
 				const int k0 = round << 10, kEnd = min(total, k0 + 1024);
+				// (k < 2^16 and the quotients are small: a float quotient is off by at most one, which the remainder corrects --
+				// the integer divisions were 6.5 % of the kernel's instructions)
+				const float rCnt = 1.0f/(float)cnt, rWp = 1.0f/(float)Wp;
 				for(int k = k0 + lane; k < kEnd; k += 32)
 				{
-					const int pi = k / cnt, j = k - pi*cnt;
-					const int iY = sY + pi / Wp, iX = sX + pi % Wp;
+					int pi = (int)((float)k*rCnt), j = k - pi*cnt;
+					if(j < 0) { --pi; j += cnt; } else if(j >= cnt) { ++pi; j -= cnt; }
+					int qy = (int)((float)pi*rWp), qx = pi - qy*Wp;
+					if(qx < 0) { --qy; qx += Wp; } else if(qx >= Wp) { ++qy; qx -= Wp; }
+					const int iY = sY + qy, iX = sX + qx;
 					const int pixLocal = (iY - t.tileY0)*f.tileW + (iX - t.tileX0);
 					if(zminKey > s.pixZ[pixLocal]) continue;
 					const int index = indexT0 + j;
@@ -1745,14 +1753,17 @@ __device__ __forceinline__ void resolveSampleMin(const DevFrame& f, const TileCt
 #pragma unroll
 	for(int j = 0; j < DEEP_SORT; ++j) { ks[j] = 0ull; sl[j] = DEEP_NIL; }
 	int nList = 0;
+	const bool shortList = nDeep <= (uint32_t)(DEEP_SORT/2);
 	for(uint32_t e = deepFirst(word); e != DEEP_NIL; e = deepNext(dc, word, e))
 	{
 		const uint2 A = dc.A[deepAt(dc, s.nsP, idx, e)];
 		unsigned long long k = ((unsigned long long)depthKey(__uint_as_float(A.x)) << 32) | A.y;
 		uint32_t ce = e;
+		// (a list of at most four entries -- the common case -- only ever touches the first four slots)
 #pragma unroll
 		for(int j = 0; j < DEEP_SORT; ++j)
 		{
+			if(j == DEEP_SORT/2 && shortList) break;
 			// strict '>' keeps equal keys (a hit stored twice on a time sub-bound boundary) both in the list
 			if(k > ks[j] || (sl[j] == DEEP_NIL && ce != DEEP_NIL))
 			{
@@ -2377,6 +2388,70 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(cons
 				PHASE_BARRIER(5);
 			}
 			const uint32_t passBeg = (pass == 1 && parted) ? split : 0u, passEnd = (pass == 0 && parted) ? split : binCnt;
+			// Motion blur / depth of field: the warps of the CTA take their next micropolygon IN LOCK STEP (one CTA-wide barrier
+			// per micropolygon).  Free-running warps are spread all over the per-micropolygon code (about 40 KB of hot
+			// instructions) and the kernel stalls on instruction fetch -- 57.7 % of its stall samples were `no_inst`,
+			// profiles/r02b_k_hide_config3_scale0.5.txt; started together they run the set-up and the first enumeration rounds
+			// on the same cache lines.  Measured -22 % on config 3 (A/B, profiles/README.md); barriers further inside the
+			// micropolygon (per enumeration round, before the final drain) cost more in waiting than they save in fetch.
+			if(MBDOF)
+			{
+				bool done = false;
+				for(;;)
+				{
+					bool have = false;
+					uint32_t p = 0;
+					if(!done)
+					{
+						uint32_t base = 0;
+						if(lane == 0) base = atomicAdd(&s_next, 1u);
+						base = __shfl_sync(0xffffffffu, base, 0);
+						if(base >= passEnd) done = true;
+						else
+						{
+							// hierarchical-z refresh, paced tile-wide (see the static loop below)
+							const uint32_t REFRESH_EVERY = f.tune[2] ? (uint32_t)f.tune[2] : 16u;
+							const uint32_t last = *(volatile uint32_t*)&s_lastRef;
+							if(base - passBeg >= (uint32_t)NWARPS && base - last >= REFRESH_EVERY && *(volatile uint32_t*)s.dirty)
+							{
+								uint32_t mine = 0;
+								if(lane == 0) mine = (atomicCAS(&s_lastRef, last, base) == last) ? 1u : 0u;
+								mine = __shfl_sync(0xffffffffu, mine, 0);
+								if(mine)
+								{
+									if(lane == 0) *(volatile uint32_t*)s.dirty = 0;
+									__syncwarp();
+									refreshPixZ(f, t, s, lane);
+									__syncwarp();
+								}
+							}
+							const unsigned long long ent = f.binEntries[binBeg + base];
+							// sorted by nearest depth: the first micropolygon behind the whole tile ends its sorted run
+							if(!(pass == 1 && f.anyCSG) && (uint32_t)(ent >> 32) > *(volatile uint32_t*)s.tileZ)
+							{
+								const uint32_t runEnd = min(passEnd, (base / (uint32_t)f.sortRun + 1u)*(uint32_t)f.sortRun);
+								if(lane == 0) atomicMax(&s_next, runEnd);
+							}
+							else { have = true; p = (uint32_t)ent; }
+						}
+					}
+					if(__syncthreads_and(done ? 1 : 0)) break;
+					if(have)
+					{
+						const bool handled = renderMBOrDof(f, t, s, dc, ws, p, lane, pass == 0);
+						if(!handled)
+						{
+							// static micropolygon in a frame without depth of field
+							if(lane == 0) setupStaticRecCall(f, t, s.pixZ, p, pass == 0, &myRecs[0]);
+							__syncwarp();
+							if(pass == 0) sampleStaticRec<true, false>(f, t, s, dc, myRecs[0], lane);
+							else sampleStaticRec<false, false>(f, t, s, dc, myRecs[0], lane);
+							__syncwarp();
+						}
+					}
+				}
+			}
+			else
 			for(;;)
 			{
 				uint32_t base = 0;
@@ -2384,7 +2459,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(cons
 				// bin turns into culling early.  Once the first wave (one grab per warp) is under way the
 				// hierarchical z is refreshed whenever new hits have landed, and because the bin is sorted
 				// by nearest depth, the first micropolygon found behind the whole tile ends its sorted run.
-				const uint32_t GRAB = f.tune[pass] ? (uint32_t)f.tune[pass] : (MBDOF ? 2u : 8u);
+				// a pass with few entries (the opaque part of a bin under many transparent layers) is spread over all warps
+				const uint32_t GRAB = f.tune[pass] ? (uint32_t)f.tune[pass] : min(8u, max(2u, (passEnd - passBeg + NWARPS - 1u)/NWARPS));
 				if(lane == 0) base = atomicAdd(&s_next, GRAB);
 				base = __shfl_sync(0xffffffffu, base, 0);
 				if(base >= passEnd) break;
@@ -2422,25 +2498,6 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(cons
 						continue;
 					}
 				}
-				if(MBDOF)
-				{
-#pragma unroll 1
-					for(int j = 0; j < cnt; ++j)
-					{
-						const uint32_t p = __shfl_sync(0xffffffffu, (uint32_t)ent, j);
-						const bool handled = renderMBOrDof(f, t, s, dc, ws, p, lane, pass == 0);
-						if(!handled)
-						{
-							// static micropolygon in a frame without depth of field
-							if(lane == 0) setupStaticRecCall(f, t, s.pixZ, p, pass == 0, &myRecs[0]);
-							__syncwarp();
-							if(pass == 0) sampleStaticRec<true, false>(f, t, s, dc, myRecs[0], lane);
-							else sampleStaticRec<false, false>(f, t, s, dc, myRecs[0], lane);
-							__syncwarp();
-						}
-					}
-				}
-				else
 				{
 					if(lane < cnt) setupStaticRec(f, t, s.pixZ, (uint32_t)ent, pass == 0, myRecs[lane]);
 					__syncwarp();
