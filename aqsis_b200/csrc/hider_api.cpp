@@ -125,7 +125,12 @@ int validateParams(AqhHider* h, const AqhFrameParams& p)
 void chooseTile(const AqhFrameParams& p, bool mbdofHint, int& tw, int& th)
 {
 	const int n = p.xsamples*p.ysamples;
-	const int target = mbdofHint ? 2048 : 4096;
+	// Static frames: tiles of 2048 samples (256-thread CTAs, four per SM) unless that leaves fewer than 32 pixels per tile --
+	// then 4096 samples (512-thread CTAs, two per SM).  Measured: config 2 (64 samples per pixel) hides 6.5 % faster on the
+	// small tiles, config 4 (256 samples per pixel: 8 instead of 16 pixels per tile) 13 % slower (profiles/README.md).
+	int staticTarget = (32*n <= 2048) ? 2048 : 4096;
+	if(const char* e = std::getenv("AQH_ST_TILE")) staticTarget = std::atoi(e);      // (development: A/B of the tile size)
+	const int target = mbdofHint ? 2048 : staticTarget;
 	tw = 16; th = 16;
 	while(tw*p.xsamples > 255 && tw > 1) tw >>= 1;
 	while(th*p.ysamples > 255 && th > 1) th >>= 1;

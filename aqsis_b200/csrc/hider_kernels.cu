@@ -1754,12 +1754,10 @@ __device__ __forceinline__ void resolveSampleMin(const DevFrame& f, const TileCt
 	for(int j = 0; j < DEEP_SORT; ++j) { ks[j] = 0ull; sl[j] = DEEP_NIL; }
 	int nList = 0;
 	const bool shortList = nDeep <= (uint32_t)(DEEP_SORT/2);
-	for(uint32_t e = deepFirst(word); e != DEEP_NIL; e = deepNext(dc, word, e))
+	// (a list of at most four entries -- the common case -- only ever touches the first four slots)
+	auto insert = [&](const uint2 A, uint32_t ce)
 	{
-		const uint2 A = dc.A[deepAt(dc, s.nsP, idx, e)];
 		unsigned long long k = ((unsigned long long)depthKey(__uint_as_float(A.x)) << 32) | A.y;
-		uint32_t ce = e;
-		// (a list of at most four entries -- the common case -- only ever touches the first four slots)
 #pragma unroll
 		for(int j = 0; j < DEEP_SORT; ++j)
 		{
@@ -1772,7 +1770,9 @@ __device__ __forceinline__ void resolveSampleMin(const DevFrame& f, const TileCt
 			}
 		}
 		++nList;
-	}
+	};
+	for(uint32_t e = deepFirst(word); e != DEEP_NIL; e = deepNext(dc, word, e))
+		insert(dc.A[deepAt(dc, s.nsP, idx, e)], e);
 	unsigned long long prev = ~0ull;
 	for(int step = 0; ; ++step)
 	{
@@ -2252,7 +2252,7 @@ __device__ __forceinline__ uint32_t loadMask(const DevFrame& f, size_t at)
 // lanes -- so there is no CTA-wide barrier inside the micropolygon loop.
 // DFGEN: a depth filter other than "min" (kept out of the common kernels: its bookkeeping costs registers)
 template<bool MBDOF, int THREADS, bool PARTIALS, bool DFGEN>
-__global__ void __launch_bounds__(THREADS, (THREADS >= 512) ? 2 : 2) k_hide(const __grid_constant__ DevFrame f, uint32_t slotBeg, uint32_t slotEnd, uint32_t* cursor)
+__global__ void __launch_bounds__(THREADS, (!MBDOF && THREADS < 512) ? 1024/THREADS : 2) k_hide(const __grid_constant__ DevFrame f, uint32_t slotBeg, uint32_t slotEnd, uint32_t* cursor)
 {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
 	__shared__ uint32_t s_tile;
@@ -3118,6 +3118,9 @@ __global__ void __launch_bounds__(256) k_filter_partials(const __grid_constant__
 
 // ------------------------------------------------------------------------------------
 // launchers
+// Threads per CTA of the static kernel: 512 (two CTAs per SM) for tiles of 4096 samples, 256 (four CTAs per SM) for
+// tiles of at most 2048 samples (chooseTile, hider_api.cpp).
+static inline bool smallStaticTile(const DevFrame& f) { return f.tileW*f.tileH*f.n <= 2048; }
 // Project + count the bin entries of the positions [pA, pB) (whole grids): the two steps that only need
 // the grids uploaded so far, so that they can run while the next chunk of the frame is still on the bus.
 cudaError_t launchProjectCount(const DevFrame& f, int64_t pA, int64_t pB, cudaStream_t st)
@@ -3205,7 +3208,7 @@ cudaError_t hideKernelConfig(const DevFrame& f, int smCount, LaunchCfg& cfg)
 	const bool dfgen = f.depthFilter != AQH_DEPTHFILTER_MIN;
 #define AQH_CFG(MB, TH) (partials ? (dfgen ? configHide<MB, TH, true, true>(f, smCount, cfg) : configHide<MB, TH, true, false>(f, smCount, cfg)) \
                                   : (dfgen ? configHide<MB, TH, false, true>(f, smCount, cfg) : configHide<MB, TH, false, false>(f, smCount, cfg)))
-	return mbdof ? AQH_CFG(true, 256) : AQH_CFG(false, 512);
+	return mbdof ? AQH_CFG(true, 256) : (smallStaticTile(f) ? AQH_CFG(false, 256) : AQH_CFG(false, 512));
 #undef AQH_CFG
 }
 
@@ -3219,7 +3222,7 @@ cudaError_t launchHide(const DevFrame& f, const LaunchCfg& cfg, uint32_t slotBeg
 #define AQH_LAUNCH(MB, TH, PA, DF) k_hide<MB, TH, PA, DF><<<ctas, TH, cfg.hideSmemBytes, st>>>(f, slotBeg, slotEnd, cursor)
 #define AQH_LAUNCH2(MB, TH) do { if(partials) { if(dfgen) AQH_LAUNCH(MB, TH, true, true); else AQH_LAUNCH(MB, TH, true, false); } \
                                  else { if(dfgen) AQH_LAUNCH(MB, TH, false, true); else AQH_LAUNCH(MB, TH, false, false); } } while(0)
-	if(mbdof) AQH_LAUNCH2(true, 256); else AQH_LAUNCH2(false, 512);
+	if(mbdof) AQH_LAUNCH2(true, 256); else if(smallStaticTile(f)) AQH_LAUNCH2(false, 256); else AQH_LAUNCH2(false, 512);
 #undef AQH_LAUNCH2
 #undef AQH_LAUNCH
 	return cudaGetLastError();
