@@ -66,7 +66,7 @@ void resetFrameGrids(AqhHider* h)
 	h->gcu.clear(); h->gcv.clear(); h->gnkeys.clear(); h->gflags.clear(); h->glod.clear(); h->gkeyTimes.clear();
 	h->segments.clear();
 	h->recs.clear(); h->chunk.clear(); h->recVb = h->recPb = h->recKo = 0;
-	h->anyMotionG = h->anyLodG = h->anyTriG = h->anyCamG = false;
+	h->anyMotionG = h->anyLodG = h->anyTriG = h->anyCamG = false; h->maxKeysG = 1;
 	h->nVerts = h->nPos = 0;
 	h->anyCi = h->anyOi = h->anyCulled = false; h->allCi = h->allOi = true;
 	h->gcsg.clear(); h->csgType.clear(); h->csgParent.clear(); h->csgSlot.clear(); h->csgKids.clear(); h->csgOrder.clear();
@@ -365,11 +365,12 @@ struct GridTablesMark
 	size_t nGrids, nKeyTimes, nRecs, nChunk;
 	uint64_t recVb, recPb, recKo;
 	bool anyMotionG, anyLodG, anyTriG, anyCamG, anyCSG, anyPoints;
+	int maxKeysG;
 };
 GridTablesMark markGridTables(const AqhHider* h)
 {
 	return GridTablesMark{h->gcu.size(), h->gkeyTimes.size(), h->recs.n, h->chunk.n, h->recVb, h->recPb, h->recKo,
-	                      h->anyMotionG, h->anyLodG, h->anyTriG, h->anyCamG, h->anyCSG, h->anyPoints};
+	                      h->anyMotionG, h->anyLodG, h->anyTriG, h->anyCamG, h->anyCSG, h->anyPoints, h->maxKeysG};
 }
 void rollbackGridTables(AqhHider* h, const GridTablesMark& m)
 {
@@ -378,7 +379,7 @@ void rollbackGridTables(AqhHider* h, const GridTablesMark& m)
 	h->recs.n = m.nRecs; h->chunk.n = m.nChunk;
 	h->recVb = m.recVb; h->recPb = m.recPb; h->recKo = m.recKo;
 	h->anyMotionG = m.anyMotionG; h->anyLodG = m.anyLodG; h->anyTriG = m.anyTriG; h->anyCamG = m.anyCamG;
-	h->anyCSG = m.anyCSG; h->anyPoints = m.anyPoints;
+	h->anyCSG = m.anyCSG; h->anyPoints = m.anyPoints; h->maxKeysG = m.maxKeysG;
 }
 
 int appendGridTables(AqhHider* h, int cu, int cv, int nkeys, uint32_t flags, const float* lod, const float* times, int csgNode, int trimSet = 0)
@@ -408,7 +409,7 @@ int appendGridTables(AqhHider* h, int cu, int cv, int nkeys, uint32_t flags, con
 		for(uint64_t c = c0; c <= c1; ++c) h->chunk.data()[c] = g;
 		h->chunk.n = std::max<size_t>(h->chunk.n, c1 + 1);
 	}
-	h->anyMotionG |= nkeys > 1; h->anyLodG |= r.lod0 >= 0.f;
+	h->anyMotionG |= nkeys > 1; h->anyLodG |= r.lod0 >= 0.f; h->maxKeysG = std::max(h->maxKeysG, nkeys);
 	h->anyTriG |= (flags & AQH_GRID_TRIANGULAR) != 0; h->anyCamG |= (flags & AQH_GRID_CAMERA_SPACE) != 0;
 	h->recVb += nv; h->recPb += np; h->recKo += (uint64_t)nkeys;
 	return AQH_OK;
@@ -773,6 +774,7 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 		f.csgType = tab; f.csgParent = tab + nCsg; f.csgSlot = tab + 2*nCsg; f.csgKids = tab + 3*nCsg; f.csgOrder = tab + 4*nCsg;
 	}
 	f.anyTrim = (h->anyTrim && dTrimUV) ? 1 : 0;
+	f.mbPlain = (!h->anyPoints && !h->anyLodG && !h->anyTriG && !h->anyTrim && h->maxKeysG <= 4) ? 1 : 0;
 	if(f.anyTrim)
 	{
 		const int32_t* tab = h->dTrimTab.as<int32_t>();

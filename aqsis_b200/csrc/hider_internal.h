@@ -136,6 +136,7 @@ struct AqhHider
 	// device arrays (vertex / position offsets), grown on first use
 	std::vector<float> hxAov, hxNg, hxN, hxRadius, hxTrimUV;
 	bool anyAov = false, anyNg = false, anyN = false, anyRadius = false, anyCSG = false, anyPoints = false;
+	int maxKeysG = 1;               // largest key count of the frame's grids
 	int aovFloats = 0;
 	std::vector<Segment> segments;
 	// device-side grid table and the 256-position chunk index, built as the grids are submitted

@@ -1113,6 +1113,10 @@ struct MovingMP
 	GridRec g;
 };
 
+// PLAIN: the motion blur / depth of field kernel of frames WITHOUT discs, level-of-detail ranges, trim curves, triangular grids
+// or more than MOV_KMAX motion keys (DevFrame::mbPlain, decided on the host from the grids submitted).  The kernel is bound by
+// instruction fetch; dropping those branches shortens its hot code by only 2 % but its time by 11 % (profiles/README.md).
+#define MB_RARE(x) (!PLAIN && (x))
 #define MOV_KMAX 4          /* keys staged in shared memory; further keys are read from HBM */
 #define MOV_QCAP 1056       /* 1024 pushes per enumeration round + the < 32 left by the previous one */
 struct MovScratch           // per warp, 16-byte aligned
@@ -1132,14 +1136,17 @@ __device__ __noinline__ B2 keyBoundGlobal(const float4* Pk, uint32_t cu)
 {
 	return boundOf4(Pk[0], Pk[1], Pk[cu+1], Pk[cu+2]);
 }
+template<bool PLAIN>
 __device__ __forceinline__ float4 movVert(const DevFrame& f, const MovingMP& m, const MovScratch* ws, uint32_t k, int i)
 {
+	if(PLAIN) return ws->kv[k][i];
 	if(ws && k < MOV_KMAX) return ws->kv[k][i];
 	return movVertGlobal(f.P4 + m.p + (size_t)k*m.nverts, m.cu, i);
 }
+template<bool PLAIN>
 __device__ __forceinline__ B2 keyBound(const DevFrame& f, const MovingMP& m, const MovScratch* ws, uint32_t k)
 {
-	if(ws && k < MOV_KMAX)
+	if(PLAIN || (ws && k < MOV_KMAX))
 	{
 		const float4 a = ws->kb[k][0], b = ws->kb[k][1];
 		B2 r; r.mnx = a.x; r.mny = a.y; r.mnz = a.z; r.mxx = a.w; r.mxy = b.x; r.mxz = b.y;
@@ -1150,6 +1157,7 @@ __device__ __forceinline__ B2 keyBound(const DevFrame& f, const MovingMP& m, con
 
 // Vertices of the micropolygon for one sample: CqMicroPolygon(Motion)::Sample,
 // micropolygon.cpp:1561-1589 and 1768-1873.  Returns false when the tight-bound test fails.
+template<bool PLAIN>
 __device__ __forceinline__ bool samplePoints(const DevFrame& f, const MovingMP& m, const MovScratch* ws, bool moving, const B2& mpBound,
                                              float2 cocMin, float2 cocMax, float2 pos, float2 dofOff, float time,
                                              float px[4], float py[4], float pz[4], bool doBoundTest)
@@ -1175,10 +1183,10 @@ __device__ __forceinline__ bool samplePoints(const DevFrame& f, const MovingMP& 
 		if(doBoundTest)
 		{
 			if(Exact)
-				tight = keyBound(f, m, ws, iIndex);
+				tight = keyBound<PLAIN>(f, m, ws, iIndex);
 			else
 			{
-				const B2 b1 = keyBound(f, m, ws, iIndex), b2 = keyBound(f, m, ws, iIndex+1);
+				const B2 b1 = keyBound<PLAIN>(f, m, ws, iIndex), b2 = keyBound<PLAIN>(f, m, ws, iIndex+1);
 				tight.mnx = (1.f-Fraction)*b1.mnx + Fraction*b2.mnx; tight.mny = (1.f-Fraction)*b1.mny + Fraction*b2.mny;
 				tight.mnz = (1.f-Fraction)*b1.mnz + Fraction*b2.mnz;
 				tight.mxx = (1.f-Fraction)*b1.mxx + Fraction*b2.mxx; tight.mxy = (1.f-Fraction)*b1.mxy + Fraction*b2.mxy;
@@ -1207,7 +1215,7 @@ __device__ __forceinline__ bool samplePoints(const DevFrame& f, const MovingMP& 
 	if(Exact)
 	{
 #pragma unroll
-		for(int i = 0; i < 4; ++i) { const float4 v = movVert(f, m, ws, iIndex, i); px[i] = v.x; py[i] = v.y; pz[i] = v.z; }
+		for(int i = 0; i < 4; ++i) { const float4 v = movVert<PLAIN>(f, m, ws, iIndex, i); px[i] = v.x; py[i] = v.y; pz[i] = v.z; }
 	}
 	else
 	{
@@ -1215,7 +1223,7 @@ __device__ __forceinline__ bool samplePoints(const DevFrame& f, const MovingMP& 
 #pragma unroll
 		for(int i = 0; i < 4; ++i)
 		{
-			const float4 a = movVert(f, m, ws, iIndex, i), b = movVert(f, m, ws, iIndex+1, i);
+			const float4 a = movVert<PLAIN>(f, m, ws, iIndex, i), b = movVert<PLAIN>(f, m, ws, iIndex+1, i);
 			px[i] = (F1*a.x) + (Fraction*b.x);
 			py[i] = (F1*a.y) + (Fraction*b.y);
 			pz[i] = (F1*a.z) + (Fraction*b.z);
@@ -1250,18 +1258,19 @@ struct MovCtx
 
 // One queued candidate (micropolygon, sample): everything of CqMicroPolygon(Motion)::Sample after the gates
 // that were evaluated at enumeration time.
+template<bool PLAIN>
 __device__ __forceinline__ void movCandidate(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc,
                                              const MovCtx& c, const MovScratch* ws, int idx)
 {
 	const float2 pos = make_float2(s.posx[idx], s.posy[idx]);
 	const float time = s.time ? s.time[idx] : f.shutterOpen;
-	if(c.m.g.lod0 >= 0.0f)
+	if(MB_RARE(c.m.g.lod0 >= 0.0f))
 	{
 		float lod = sampleLod(f, t, s, idx);
 		if(c.m.g.lod0 > lod || lod >= c.m.g.lod1) return;
 	}
 	const float2 dofOff = s.dof ? s.dof[idx] : make_float2(0.f, 0.f);
-	if(c.isPoint)
+	if(MB_RARE(c.isPoint))
 	{
 		// CqMicroPolygonPoints::Sample under depth of field (geometry/points.cpp:653-664): the SAMPLE is moved by its lens
 		// offset times the point's circle of confusion
@@ -1275,7 +1284,7 @@ __device__ __forceinline__ void movCandidate(const DevFrame& f, const TileCtx& t
 		return;
 	}
 	float px[4], py[4], pz[4];
-	if(!samplePoints(f, c.m, ws, c.moving, c.mpBound, c.cocMin, c.cocMax, pos, dofOff, time, px, py, pz, true)) return;
+	if(!samplePoints<PLAIN>(f, c.m, ws, c.moving, c.mpBound, c.cocMin, c.cocMax, pos, dofOff, time, px, py, pz, true)) return;
 	HitCache hc;
 	cachePointInPolyTest(hc, px, py, pz, c.m.code);
 	if(!edgeTests(hc.X, hc.Y, hc.XM, hc.YM, pos.x, pos.y)) return;
@@ -1283,10 +1292,10 @@ __device__ __forceinline__ void movCandidate(const DevFrame& f, const TileCtx& t
 	const float D = bilerpZ(hc.z, uv);
 	// (CqMicroPolygonMotion::Sample leaves the per-hit trim test as a todo, micropolygon.cpp:1877-1884: only micropolygons
 	// that do not move are tested)
-	if(c.trimmed && !c.moving)
+	if(MB_RARE(c.trimmed && !c.moving))
 		if(trimRejectHit(f.gridTrim, f.trimSetLoop, f.trimLoopPoint, f.trimPoints, f.trimUV, c.gridIndex, c.m.g.flags,
 		                 c.shadeInfo.x, c.m.cu, uv.x, uv.y)) return;
-	if(c.m.g.flags & AQH_GRID_TRIANGULAR)
+	if(MB_RARE(c.m.g.flags & AQH_GRID_TRIANGULAR))
 		if(triangleSplitReject(f, c.m.g, pos, dofOff, D, time)) return;
 	if(c.opaquePass)
 		storeOpaque(f, s, &s.keys[idx], D, c.m.p);
@@ -1304,6 +1313,7 @@ __device__ __forceinline__ void movPush(const DevFrame& f, MovScratch* ws, int i
 
 // Run the heavy part on batches of up to 32 queued candidates while at least `need` are waiting.
 // Called by the whole warp at a converged point.
+template<bool PLAIN>
 __device__ __forceinline__ void movDrain(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc,
                                          const MovCtx& c, MovScratch* ws, int lane, uint32_t need)
 {
@@ -1316,13 +1326,14 @@ __device__ __forceinline__ void movDrain(const DevFrame& f, const TileCtx& t, co
 		const uint32_t take = cnt < 32u ? cnt : 32u, base = cnt - take;
 		__syncwarp();
 		if(lane == 0) *(volatile uint32_t*)&ws->qcount = base;
-		if((uint32_t)lane < take) movCandidate(f, t, s, dc, c, ws, (int)ws->q[base + lane]);
+		if((uint32_t)lane < take) movCandidate<PLAIN>(f, t, s, dc, c, ws, (int)ws->q[base + lane]);
 	}
 	__syncwarp();
 }
 
 // Returns false for a static micropolygon in a frame without depth of field: the reference
 // renders those with RenderMPG_Static even when other grids move (bucketprocessor.cpp:1087-1090).
+template<bool PLAIN>
 __device__ __forceinline__ bool renderMBOrDof(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, MovScratch* ws,
                               uint32_t p, int lane, bool opaquePass)
 {
@@ -1339,7 +1350,7 @@ __device__ __forceinline__ bool renderMBOrDof(const DevFrame& f, const TileCtx& 
 	const bool moving = m.nkeys > 1;
 	if(!moving && !f.useDof) return false;
 	c.moving = moving; c.opaquePass = opaquePass;
-	c.isPoint = (m.g.flags & AQH_GRID_POINTS) != 0;
+	c.isPoint = MB_RARE((m.g.flags & AQH_GRID_POINTS) != 0);
 	c.pointR = c.isPoint ? f.radius[p] : 0.f;
 	c.cullable = mpCullable(f, m.g);
 	c.shadeInfo = hitShadeInfo(m.g, p);
@@ -1375,8 +1386,8 @@ __device__ __forceinline__ bool renderMBOrDof(const DevFrame& f, const TileCtx& 
 	if(opaqueSlot != opaquePass) return true;
 	m.code = c.isPoint ? 0xE4 : computeVertexOrder(P);
 	// m_Bound: union of the key bounds (AppendKey, micropolygon.cpp:1952-1967)
-	B2 mpBound = keyBound(f, m, ws, 0);
-	for(uint32_t k = 1; k < m.nkeys; ++k) { B2 kb = keyBound(f, m, ws, k); encapsulate(mpBound, kb); }
+	B2 mpBound = keyBound<PLAIN>(f, m, ws, 0);
+	for(uint32_t k = 1; k < m.nkeys; ++k) { B2 kb = keyBound<PLAIN>(f, m, ws, k); encapsulate(mpBound, kb); }
 	c.mpBound = mpBound;
 	// CacheHitTestValues (static :1406-1423, moving :1916-1938)
 	float2 cocMin = make_float2(0.f, 0.f), cocMax = make_float2(0.f, 0.f);
@@ -1415,10 +1426,10 @@ __device__ __forceinline__ bool renderMBOrDof(const DevFrame& f, const TileCtx& 
 	B2 kb0 = mpBound;
 	if(moving)
 	{
-		kb0 = keyBound(f, m, ws, 0);
+		kb0 = keyBound<PLAIN>(f, m, ws, 0);
 		float cx = kb0.mxx - kb0.mnx, cy = kb0.mxy - kb0.mny;
 		float polyLen2 = (cy == 0.f) ? cx*cx : ((cx == 0.f) ? cy*cy : cx*cx + cy*cy);
-		const float4 pl = movVert(f, m, ws, m.nkeys-1, 0);
+		const float4 pl = movVert<PLAIN>(f, m, ws, m.nkeys-1, 0);
 		float mx = P[0].x - pl.x, my = P[0].y - pl.y;
 		float moveDist2 = (my == 0.f) ? mx*mx : ((mx == 0.f) ? my*my : mx*mx + my*my);
 		int polyLengthsMoved = max(1, lfloorF(sqrtf(moveDist2/polyLen2)));
@@ -1479,7 +1490,7 @@ __device__ __forceinline__ bool renderMBOrDof(const DevFrame& f, const TileCtx& 
 						uint32_t endKey = 1;
 						while(acc > times[endKey] && endKey < m.nkeys - 1) ++endKey;
 						const uint32_t endKey_1 = endKey - 1;
-						const B2 end0 = keyBound(f, m, ws, endKey_1), end1 = keyBound(f, m, ws, endKey);
+						const B2 end0 = keyBound<PLAIN>(f, m, ws, endKey_1), end1 = keyBound<PLAIN>(f, m, ws, endKey);
 						const float end0Time = times[endKey_1], end1Time = times[endKey];
 						const float mix = (acc - end0Time) / (end1Time - end0Time);
 						B2 mid = end0;
@@ -1493,7 +1504,7 @@ __device__ __forceinline__ bool renderMBOrDof(const DevFrame& f, const TileCtx& 
 						uint32_t startKey = __shfl_up_sync(0xffffffffu, endKey_1, 1);
 						if(lane == 0) { run = carryBound; startKey = carryKey; }
 						encapsulate(run, mid);
-						while(startKey < endKey_1) { startKey++; const B2 kb = keyBound(f, m, ws, startKey); encapsulate(run, kb); }
+						while(startKey < endKey_1) { startKey++; const B2 kb = keyBound<PLAIN>(f, m, ws, startKey); encapsulate(run, kb); }
 						dBnd = run;
 						dTime0 = acc - dt;
 						const float nextAcc = acc + dt;
@@ -1655,7 +1666,7 @@ __device__ __forceinline__ bool renderMBOrDof(const DevFrame& f, const TileCtx& 
 			}
 			++round;
 		}
-		movDrain(f, t, s, dc, c, ws, lane, last ? 1u : 32u);
+		movDrain<PLAIN>(f, t, s, dc, c, ws, lane, last ? 1u : 32u);
 		if(last) break;
 	}
 	return true;
@@ -1683,7 +1694,7 @@ __device__ __forceinline__ void hitUV(const DevFrame& f, const GridRec& g, uint3
 	m.times = f.keyTimes + (g.nkeys_koff >> 8);
 	float px[4], py[4], pz[4];
 	B2 dummy;
-	samplePoints(f, m, nullptr, m.nkeys > 1, dummy, make_float2(0.f, 0.f), make_float2(0.f, 0.f), pos, dofOff, time, px, py, pz, false);
+	samplePoints<false>(f, m, nullptr, m.nkeys > 1, dummy, make_float2(0.f, 0.f), make_float2(0.f, 0.f), pos, dofOff, time, px, py, pz, false);
 	HitCache c;
 	cachePointInPolyTest(c, px, py, pz, 0xE4 /* any valid code: only the uv part is used */);
 	uv = invBilinear(c.Ax, c.Ay, c.Ex, c.Ey, c.Fx, c.Fy, c.Gx, c.Gy, c.linear, pos.x, pos.y);
@@ -2251,7 +2262,7 @@ __device__ __forceinline__ uint32_t loadMask(const DevFrame& f, size_t at)
 // records in the warp's shared-memory slots), then sample them one after the other with all 32
 // lanes -- so there is no CTA-wide barrier inside the micropolygon loop.
 // DFGEN: a depth filter other than "min" (kept out of the common kernels: its bookkeeping costs registers)
-template<bool MBDOF, int THREADS, bool PARTIALS, bool DFGEN>
+template<bool MBDOF, int THREADS, bool PARTIALS, bool DFGEN, bool PLAIN = false>
 __global__ void __launch_bounds__(THREADS, (!MBDOF && THREADS < 512) ? 1024/THREADS : 2) k_hide(const __grid_constant__ DevFrame f, uint32_t slotBeg, uint32_t slotEnd, uint32_t* cursor)
 {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -2438,7 +2449,7 @@ __global__ void __launch_bounds__(THREADS, (!MBDOF && THREADS < 512) ? 1024/THRE
 					if(__syncthreads_and(done ? 1 : 0)) break;
 					if(have)
 					{
-						const bool handled = renderMBOrDof(f, t, s, dc, ws, p, lane, pass == 0);
+						const bool handled = renderMBOrDof<PLAIN>(f, t, s, dc, ws, p, lane, pass == 0);
 						if(!handled)
 						{
 							// static micropolygon in a frame without depth of field
@@ -3181,19 +3192,19 @@ cudaError_t launchBinFill(const DevFrame& f, int64_t pA, int64_t pB, cudaStream_
 	return cudaGetLastError();
 }
 
-template<bool MBDOF, int THREADS, bool PARTIALS, bool DFGEN>
+template<bool MBDOF, int THREADS, bool PARTIALS, bool DFGEN, bool PLAIN = false>
 static cudaError_t configHide(const DevFrame& f, int smCount, LaunchCfg& cfg)
 {
 	cfg.hideThreads = THREADS;
 	cfg.batchMPs = (THREADS/32)*RECS_PER_WARP;
 	cfg.hideSmemBytes = hideSmemBytes(f, cfg.batchMPs, MBDOF ? (THREADS/32)*sizeof(MovScratch) : 0);
 	if(cfg.hideSmemBytes > 227*1024) return cudaErrorInvalidValue;
-	cudaError_t e = cudaFuncSetAttribute(k_hide<MBDOF, THREADS, PARTIALS, DFGEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.hideSmemBytes);
+	cudaError_t e = cudaFuncSetAttribute(k_hide<MBDOF, THREADS, PARTIALS, DFGEN, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.hideSmemBytes);
 	if(e != cudaSuccess) return e;
-	e = cudaFuncSetAttribute(k_hide<MBDOF, THREADS, PARTIALS, DFGEN>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+	e = cudaFuncSetAttribute(k_hide<MBDOF, THREADS, PARTIALS, DFGEN, PLAIN>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
 	if(e != cudaSuccess) return e;
 	int perSm = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_hide<MBDOF, THREADS, PARTIALS, DFGEN>, THREADS, cfg.hideSmemBytes);
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_hide<MBDOF, THREADS, PARTIALS, DFGEN, PLAIN>, THREADS, cfg.hideSmemBytes);
 	if(e != cudaSuccess) return e;
 	if(perSm < 1) perSm = 1;
 	cfg.hideCtas = smCount * perSm;
@@ -3208,6 +3219,7 @@ cudaError_t hideKernelConfig(const DevFrame& f, int smCount, LaunchCfg& cfg)
 	const bool dfgen = f.depthFilter != AQH_DEPTHFILTER_MIN;
 #define AQH_CFG(MB, TH) (partials ? (dfgen ? configHide<MB, TH, true, true>(f, smCount, cfg) : configHide<MB, TH, true, false>(f, smCount, cfg)) \
                                   : (dfgen ? configHide<MB, TH, false, true>(f, smCount, cfg) : configHide<MB, TH, false, false>(f, smCount, cfg)))
+	if(mbdof && f.mbPlain && !partials && !dfgen) return configHide<true, 256, false, false, true>(f, smCount, cfg);
 	return mbdof ? AQH_CFG(true, 256) : (smallStaticTile(f) ? AQH_CFG(false, 256) : AQH_CFG(false, 512));
 #undef AQH_CFG
 }
@@ -3222,7 +3234,8 @@ cudaError_t launchHide(const DevFrame& f, const LaunchCfg& cfg, uint32_t slotBeg
 #define AQH_LAUNCH(MB, TH, PA, DF) k_hide<MB, TH, PA, DF><<<ctas, TH, cfg.hideSmemBytes, st>>>(f, slotBeg, slotEnd, cursor)
 #define AQH_LAUNCH2(MB, TH) do { if(partials) { if(dfgen) AQH_LAUNCH(MB, TH, true, true); else AQH_LAUNCH(MB, TH, true, false); } \
                                  else { if(dfgen) AQH_LAUNCH(MB, TH, false, true); else AQH_LAUNCH(MB, TH, false, false); } } while(0)
-	if(mbdof) AQH_LAUNCH2(true, 256); else if(smallStaticTile(f)) AQH_LAUNCH2(false, 256); else AQH_LAUNCH2(false, 512);
+	if(mbdof && f.mbPlain && !partials && !dfgen) k_hide<true, 256, false, false, true><<<ctas, 256, cfg.hideSmemBytes, st>>>(f, slotBeg, slotEnd, cursor);
+	else if(mbdof) AQH_LAUNCH2(true, 256); else if(smallStaticTile(f)) AQH_LAUNCH2(false, 256); else AQH_LAUNCH2(false, 512);
 #undef AQH_LAUNCH2
 #undef AQH_LAUNCH
 	return cudaGetLastError();
