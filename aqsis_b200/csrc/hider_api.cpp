@@ -774,7 +774,7 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 		f.csgType = tab; f.csgParent = tab + nCsg; f.csgSlot = tab + 2*nCsg; f.csgKids = tab + 3*nCsg; f.csgOrder = tab + 4*nCsg;
 	}
 	f.anyTrim = (h->anyTrim && dTrimUV) ? 1 : 0;
-	f.mbPlain = (!h->anyPoints && !h->anyLodG && !h->anyTriG && !h->anyTrim && h->maxKeysG <= 4) ? 1 : 0;
+	f.mbPlain = (!h->anyPoints && !h->anyLodG && !h->anyTriG && !h->anyTrim && h->maxKeysG <= 2) ? 1 : 0;
 	if(f.anyTrim)
 	{
 		const int32_t* tab = h->dTrimTab.as<int32_t>();
