@@ -1114,9 +1114,12 @@ struct MovingMP
 };
 
 // PLAIN: the motion blur / depth of field kernel of frames WITHOUT discs, level-of-detail ranges, trim curves, triangular grids,
-// more than two motion keys (DevFrame::mbPlain, decided on the host from the grids submitted) or any non-opaque vertex.  The kernel is bound by
-// instruction fetch; dropping those branches shortens its hot code by only 2 % but its time by 11 % (profiles/README.md).
+// or more than two motion keys (DevFrame::mbPlain, decided on the host from the grids submitted; AQH_TUNE=0,0,0,0,1 forces the
+// general kernel, tests/test_features_gpu.py compares the two).  The general kernel is bound by
+// instruction fetch; without those branches the hot code is only a few per cent shorter, but it stays in the instruction cache:
+// config 3 426 ms (general, free-running warps) -> 238 ms (profiles/README.md).
 #define MB_RARE(x) (!PLAIN && (x))
+#define PLAIN_K2 PLAIN        /* at most two motion keys */
 #define MOV_KMAX 4          /* keys staged in shared memory; further keys are read from HBM */
 #define MOV_QCAP 1056       /* 1024 pushes per enumeration round + the < 32 left by the previous one */
 struct MovScratch           // per warp, 16-byte aligned
@@ -1171,11 +1174,11 @@ __device__ __forceinline__ bool samplePoints(const DevFrame& f, const MovingMP& 
 		const float* times = m.times;
 		if(time > times[0])
 		{
-			if(time >= times[PLAIN ? 1u : m.nkeys-1])
-				iIndex = PLAIN ? 1u : m.nkeys - 1;
+			if(time >= times[PLAIN_K2 ? 1u : m.nkeys-1])
+				iIndex = PLAIN_K2 ? 1u : m.nkeys - 1;
 			else
 			{
-				if(!PLAIN) while(time >= times[iIndex+1]) iIndex += 1;
+				if(!PLAIN_K2) while(time >= times[iIndex+1]) iIndex += 1;
 				Fraction = (time - times[iIndex]) / (times[iIndex+1] - times[iIndex]);
 				Exact = (times[iIndex] == time);
 			}
@@ -1297,7 +1300,7 @@ __device__ __forceinline__ void movCandidate(const DevFrame& f, const TileCtx& t
 		                 c.shadeInfo.x, c.m.cu, uv.x, uv.y)) return;
 	if(MB_RARE(c.m.g.flags & AQH_GRID_TRIANGULAR))
 		if(triangleSplitReject(f, c.m.g, pos, dofOff, D, time)) return;
-	if(PLAIN || c.opaquePass)
+	if(c.opaquePass)
 		storeOpaque(f, s, &s.keys[idx], D, c.m.p);
 	else
 		storeDeep(f, dc, s, idx, D, c.m.p, uv, c.shadeInfo.x, c.shadeInfo.y, c.cullable);
@@ -1352,14 +1355,14 @@ __device__ __forceinline__ bool renderMBOrDof(const DevFrame& f, const TileCtx& 
 	c.moving = moving; c.opaquePass = opaquePass;
 	c.isPoint = MB_RARE((m.g.flags & AQH_GRID_POINTS) != 0);
 	c.pointR = c.isPoint ? f.radius[p] : 0.f;
-	c.cullable = PLAIN ? true : mpCullable(f, m.g);
-	if(!PLAIN) c.shadeInfo = hitShadeInfo(m.g, p);
+	c.cullable = mpCullable(f, m.g);
+	c.shadeInfo = hitShadeInfo(m.g, p);
 	c.trimmed = (info & VINFO_MP_TRIMMED) != 0;
 	c.gridIndex = info & VINFO_GRID_MASK;
 	// ---- stage the key vertices and key bounds in the warp's scratch
 	__syncwarp();
 	{
-		const uint32_t nk = PLAIN ? (moving ? 2u : 1u) : (m.nkeys < MOV_KMAX ? m.nkeys : MOV_KMAX);
+		const uint32_t nk = PLAIN_K2 ? (moving ? 2u : 1u) : (m.nkeys < MOV_KMAX ? m.nkeys : MOV_KMAX);
 		if((uint32_t)lane < 4u*nk)
 		{
 			const uint32_t k = (uint32_t)lane >> 2; const int i = lane & 3;
@@ -1379,19 +1382,15 @@ __device__ __forceinline__ bool renderMBOrDof(const DevFrame& f, const TileCtx& 
 	}
 	float4 P[4];
 	P[0] = ws->kv[0][0]; P[1] = ws->kv[0][1]; P[2] = ws->kv[0][2]; P[3] = ws->kv[0][3];
-	if(!PLAIN)
-	{
-		bool opaque = (info & VINFO_OPAQUE) != 0;
-		if((m.g.flags & AQH_GRID_SMOOTH) && !c.isPoint)
-			opaque = opaque && (infoOf(P[1]) & VINFO_OPAQUE) && (infoOf(P[2]) & VINFO_OPAQUE) && (infoOf(P[3]) & VINFO_OPAQUE);
-		const bool opaqueSlot = (opaque || (m.g.flags & AQH_GRID_MATTE_ALPHA)) && c.cullable;
-		if(opaqueSlot != opaquePass) return true;
-	}
-	else if(!opaquePass) return true;       // (a PLAIN frame has no transparent micropolygon)
+	bool opaque = (info & VINFO_OPAQUE) != 0;
+	if((m.g.flags & AQH_GRID_SMOOTH) && !c.isPoint)
+		opaque = opaque && (infoOf(P[1]) & VINFO_OPAQUE) && (infoOf(P[2]) & VINFO_OPAQUE) && (infoOf(P[3]) & VINFO_OPAQUE);
+	const bool opaqueSlot = (opaque || (m.g.flags & AQH_GRID_MATTE_ALPHA)) && c.cullable;
+	if(opaqueSlot != opaquePass) return true;
 	m.code = c.isPoint ? 0xE4 : computeVertexOrder(P);
 	// m_Bound: union of the key bounds (AppendKey, micropolygon.cpp:1952-1967)
 	B2 mpBound = keyBound<PLAIN>(f, m, ws, 0);
-	if(PLAIN) { if(moving) { B2 kb = keyBound<PLAIN>(f, m, ws, 1); encapsulate(mpBound, kb); } }
+	if(PLAIN_K2) { if(moving) { B2 kb = keyBound<PLAIN>(f, m, ws, 1); encapsulate(mpBound, kb); } }
 	else for(uint32_t k = 1; k < m.nkeys; ++k) { B2 kb = keyBound<PLAIN>(f, m, ws, k); encapsulate(mpBound, kb); }
 	c.mpBound = mpBound;
 	// CacheHitTestValues (static :1406-1423, moving :1916-1938)
@@ -1434,7 +1433,7 @@ __device__ __forceinline__ bool renderMBOrDof(const DevFrame& f, const TileCtx& 
 		kb0 = keyBound<PLAIN>(f, m, ws, 0);
 		float cx = kb0.mxx - kb0.mnx, cy = kb0.mxy - kb0.mny;
 		float polyLen2 = (cy == 0.f) ? cx*cx : ((cx == 0.f) ? cy*cy : cx*cx + cy*cy);
-		const float4 pl = movVert<PLAIN>(f, m, ws, PLAIN ? 1u : m.nkeys-1, 0);
+		const float4 pl = movVert<PLAIN>(f, m, ws, PLAIN_K2 ? 1u : m.nkeys-1, 0);
 		float mx = P[0].x - pl.x, my = P[0].y - pl.y;
 		float moveDist2 = (my == 0.f) ? mx*mx : ((mx == 0.f) ? my*my : mx*mx + my*my);
 		int polyLengthsMoved = max(1, lfloorF(sqrtf(moveDist2/polyLen2)));
@@ -1493,7 +1492,7 @@ __device__ __forceinline__ bool renderMBOrDof(const DevFrame& f, const TileCtx& 
 						const int nAdd = ok ? lane : 0;
 						for(int k = 0; k < nAdd; ++k) acc = acc + dt;
 						uint32_t endKey = 1;
-						if(!PLAIN) while(acc > times[endKey] && endKey < m.nkeys - 1) ++endKey;
+						if(!PLAIN_K2) while(acc > times[endKey] && endKey < m.nkeys - 1) ++endKey;
 						const uint32_t endKey_1 = endKey - 1;
 						const B2 end0 = keyBound<PLAIN>(f, m, ws, endKey_1), end1 = keyBound<PLAIN>(f, m, ws, endKey);
 						const float end0Time = times[endKey_1], end1Time = times[endKey];
@@ -1506,7 +1505,7 @@ __device__ __forceinline__ bool renderMBOrDof(const DevFrame& f, const TileCtx& 
 						run.mnx = __shfl_up_sync(0xffffffffu, mid.mnx, 1); run.mny = __shfl_up_sync(0xffffffffu, mid.mny, 1); run.mnz = __shfl_up_sync(0xffffffffu, mid.mnz, 1);
 						run.mxx = __shfl_up_sync(0xffffffffu, mid.mxx, 1); run.mxy = __shfl_up_sync(0xffffffffu, mid.mxy, 1); run.mxz = __shfl_up_sync(0xffffffffu, mid.mxz, 1);
 						// ... and the last key it had passed by then (startKey): the end key - 1 of the previous division, 0 at the start
-						uint32_t startKey = PLAIN ? 0u : __shfl_up_sync(0xffffffffu, endKey_1, 1);
+						uint32_t startKey = PLAIN_K2 ? 0u : __shfl_up_sync(0xffffffffu, endKey_1, 1);
 						if(lane == 0) { run = carryBound; startKey = carryKey; }
 						encapsulate(run, mid);
 						if(!PLAIN) while(startKey < endKey_1) { startKey++; const B2 kb = keyBound<PLAIN>(f, m, ws, startKey); encapsulate(run, kb); }
@@ -1518,7 +1517,7 @@ __device__ __forceinline__ bool renderMBOrDof(const DevFrame& f, const TileCtx& 
 						accBase = __shfl_sync(0xffffffffu, nextAcc, 31);
 						carryBound.mnx = __shfl_sync(0xffffffffu, mid.mnx, 31); carryBound.mny = __shfl_sync(0xffffffffu, mid.mny, 31); carryBound.mnz = __shfl_sync(0xffffffffu, mid.mnz, 31);
 						carryBound.mxx = __shfl_sync(0xffffffffu, mid.mxx, 31); carryBound.mxy = __shfl_sync(0xffffffffu, mid.mxy, 31); carryBound.mxz = __shfl_sync(0xffffffffu, mid.mxz, 31);
-						if(!PLAIN) carryKey = __shfl_sync(0xffffffffu, endKey_1, 31);
+						if(!PLAIN_K2) carryKey = __shfl_sync(0xffffffffu, endKey_1, 31);
 						if(dTime1 < opentime || dTime0 > closetime) ok = false;
 						if(fastShutter) { dIndexT0 = 0; dIndexT1 = n; }
 						else
@@ -2404,12 +2403,13 @@ __global__ void __launch_bounds__(THREADS, (!MBDOF && THREADS < 512) ? 1024/THRE
 				PHASE_BARRIER(5);
 			}
 			const uint32_t passBeg = (pass == 1 && parted) ? split : 0u, passEnd = (pass == 0 && parted) ? split : binCnt;
-			// Motion blur / depth of field: the warps of the CTA take their next micropolygon IN LOCK STEP (one CTA-wide barrier
-			// per micropolygon).  Free-running warps are spread all over the per-micropolygon code (about 40 KB of hot
-			// instructions) and the kernel stalls on instruction fetch -- 57.7 % of its stall samples were `no_inst`,
-			// profiles/r02b_k_hide_config3_scale0.5.txt; started together they run the set-up and the first enumeration rounds
-			// on the same cache lines.  Measured -22 % on config 3 (A/B, profiles/README.md); barriers further inside the
-			// micropolygon (per enumeration round, before the final drain) cost more in waiting than they save in fetch.
+			// Motion blur / depth of field.  The general kernel is bound by instruction fetch: free-running warps are spread all over
+			// its per-micropolygon code (57.7 % of the stall samples were `no_inst`, profiles/r02b_k_hide_config3_scale0.5.txt), so
+			// its warps take their micropolygons IN LOCK STEP -- one CTA-wide barrier per micropolygon, -22 % -- and run the set-up
+			// and the first enumeration rounds on the same cache lines; barriers further inside (per enumeration round, before the
+			// final drain) cost more in waiting than they save in fetch.  The PLAIN kernel is short enough to stay in the
+			// instruction cache: there the barrier only adds waiting (38 % of its stall samples) and the warps run free
+			// (config 3: general 426 ms free / 357 ms lock step, PLAIN 298 ms lock step / 238 ms free; profiles/README.md).
 			if(MBDOF)
 			{
 				bool done = false;
@@ -2426,7 +2426,7 @@ __global__ void __launch_bounds__(THREADS, (!MBDOF && THREADS < 512) ? 1024/THRE
 						else
 						{
 							// hierarchical-z refresh, paced tile-wide (see the static loop below)
-							const uint32_t REFRESH_EVERY = f.tune[2] ? (uint32_t)f.tune[2] : 16u;
+							const uint32_t REFRESH_EVERY = f.tune[2] ? (uint32_t)f.tune[2] : (PLAIN ? 64u : 32u);
 							const uint32_t last = *(volatile uint32_t*)&s_lastRef;
 							if(base - passBeg >= (uint32_t)NWARPS && base - last >= REFRESH_EVERY && *(volatile uint32_t*)s.dirty)
 							{
@@ -2451,7 +2451,8 @@ __global__ void __launch_bounds__(THREADS, (!MBDOF && THREADS < 512) ? 1024/THRE
 							else { have = true; p = (uint32_t)ent; }
 						}
 					}
-					if(__syncthreads_and(done ? 1 : 0)) break;
+					if(PLAIN) { if(done) break; }
+					else if(__syncthreads_and(done ? 1 : 0)) break;
 					if(have)
 					{
 						const bool handled = renderMBOrDof<PLAIN>(f, t, s, dc, ws, p, lane, pass == 0);
@@ -3224,7 +3225,7 @@ cudaError_t hideKernelConfig(const DevFrame& f, int smCount, LaunchCfg& cfg)
 	const bool dfgen = f.depthFilter != AQH_DEPTHFILTER_MIN;
 #define AQH_CFG(MB, TH) (partials ? (dfgen ? configHide<MB, TH, true, true>(f, smCount, cfg) : configHide<MB, TH, true, false>(f, smCount, cfg)) \
                                   : (dfgen ? configHide<MB, TH, false, true>(f, smCount, cfg) : configHide<MB, TH, false, false>(f, smCount, cfg)))
-	if(mbdof && f.mbPlain && !f.anyTransparent && !partials && !dfgen) return configHide<true, 256, false, false, true>(f, smCount, cfg);
+	if(mbdof && f.mbPlain && !f.tune[4] && !partials && !dfgen) return configHide<true, 256, false, false, true>(f, smCount, cfg);
 	return mbdof ? AQH_CFG(true, 256) : (smallStaticTile(f) ? AQH_CFG(false, 256) : AQH_CFG(false, 512));
 #undef AQH_CFG
 }
@@ -3239,7 +3240,7 @@ cudaError_t launchHide(const DevFrame& f, const LaunchCfg& cfg, uint32_t slotBeg
 #define AQH_LAUNCH(MB, TH, PA, DF) k_hide<MB, TH, PA, DF><<<ctas, TH, cfg.hideSmemBytes, st>>>(f, slotBeg, slotEnd, cursor)
 #define AQH_LAUNCH2(MB, TH) do { if(partials) { if(dfgen) AQH_LAUNCH(MB, TH, true, true); else AQH_LAUNCH(MB, TH, true, false); } \
                                  else { if(dfgen) AQH_LAUNCH(MB, TH, false, true); else AQH_LAUNCH(MB, TH, false, false); } } while(0)
-	if(mbdof && f.mbPlain && !f.anyTransparent && !partials && !dfgen) k_hide<true, 256, false, false, true><<<ctas, 256, cfg.hideSmemBytes, st>>>(f, slotBeg, slotEnd, cursor);
+	if(mbdof && f.mbPlain && !f.tune[4] && !partials && !dfgen) k_hide<true, 256, false, false, true><<<ctas, 256, cfg.hideSmemBytes, st>>>(f, slotBeg, slotEnd, cursor);
 	else if(mbdof) AQH_LAUNCH2(true, 256); else if(smallStaticTile(f)) AQH_LAUNCH2(false, 256); else AQH_LAUNCH2(false, 512);
 #undef AQH_LAUNCH2
 #undef AQH_LAUNCH
