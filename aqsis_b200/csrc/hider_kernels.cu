@@ -16,6 +16,8 @@
 //                (bucketprocessor.cpp:584-707, 766-806; ddmanager.cpp:1022-1118)
 #include "hider_device.h"
 
+#include <vector>
+#include <cstring>
 #include <algorithm>
 #include <cmath>
 #include <cfloat>
@@ -2917,7 +2919,7 @@ __global__ void __launch_bounds__(256) k_filter(const __grid_constant__ DevFrame
 // a value of 1.0 (1.0f*w == w exactly) so that all eight lanes run the same instructions.
 // Weights come from constant memory (uniform index).  Excluded samples are skipped by predication,
 // never multiplied by zero.
-__constant__ float c_filt[49*256 + 64];
+__constant__ __align__(16) float c_filt[49*256 + 64];     // [tap][chunk][planeSC] (slots past n hold 0)
 // per (tap, chunk): which groups of four consecutive sample slots can hold a sample inside the tap's filter support at all
 // (launchFilter derives it from the sub-pixel cell every slot's sample lies in); an empty chunk is not even copied
 __constant__ uint16_t c_tapGroups[49*4];
@@ -2970,8 +2972,10 @@ __host__ __device__ __forceinline__ int filterPlaneFloats(const DevFrame& f)
 
 // MB = bytes per mask word (1, 2 or 4).  Four consecutive slots are tested per step:
 // one 32-bit shared load for byte masks, one 64-bit load for 16-bit masks, one 128-bit load for 32-bit masks.
-// CHUNKED = more than 64 samples per pixel: a stage is one (fy, fx, 64-slot chunk); chunks and groups of four slots that cannot
-// lie inside the tap's support are skipped (c_tapGroups).  With one chunk per pixel the skip test would cost more than it saves.
+// CHUNKED = more than 64 samples per pixel: a stage is one (fy, fx, 64-slot chunk) -- the reference sums tap by tap, all samples of
+// a pixel inside each tap, so the chunks of one fx cannot be shared with the next (measured: sharing them would take 20 % off the
+// filter of config 4, and breaks bit parity); chunks and groups of four slots that cannot lie inside the tap's support are skipped
+// (c_tapGroups).  With one chunk per pixel the skip test would cost more than it saves.
 template<int MB, bool CHUNKED>
 __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(const __grid_constant__ DevFrame f, const __grid_constant__ DevDisplays disp, int yBeg, int kBase, int nVal)
 {
@@ -2989,7 +2993,8 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(const __grid_consta
 	if(f.rowOwned && !f.rowOwned[y]) return;             // uniform over the CTA
 	// kBase / nVal: the planes this pass filters -- 0 / 7 for R G B Or Og Ob Z, then groups of up to seven AOV floats;
 	// channel threads beyond nVal idle, channel 7 always sums the weights
-	const bool live = (x0 + px) < f.cropX1 && (ch < nVal || ch == 7);
+	const bool pixLive = (x0 + px) < f.cropX1;
+	const bool live = pixLive && (ch < nVal || ch == 7);
 	// channel 7 reads 1.0f from a region laid out so that its banks continue the skew of the seven planes
 	float* ones = tile + (size_t)7*planeS;
 	const unsigned char* mbase = reinterpret_cast<const unsigned char*>(ones + FILTER_ONES);
@@ -3027,19 +3032,31 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(const __grid_consta
 				}
 				mbarWait(&s_bar, phase);
 				phase ^= 1u;
-				if(!live) continue;
+				if(!pixLive) continue;
 				const int fx0 = halo ? 0 : sfx, fx1 = halo ? 2*xmax : sfx;
 				for(int fx = fx0; fx <= fx1; ++fx)
 				{
 					const int tap = fy*(2*xmax + 1) + fx;
-					const uint32_t need = (1u << fx) | (1u << (2*xmax + 1 + fy)) | validBit;
-					const float* w = c_filt + tap*n + c*SC;
+					const uint32_t tapBits = (1u << fx) | (1u << (2*xmax + 1 + fy));
+					const uint32_t need = tapBits | validBit;
+					// four weights per constant-bank load (the table is padded to whole groups of four slots, launchFilter)
+					const float4* w4 = reinterpret_cast<const float4*>(c_filt) + ((tap*nCh + c)*SC >> 2);
 					const uint32_t groups = c_tapGroups[tap*4 + c];
 					const int o = (halo ? px + fx : px)*SC;
 					const float* vp = (ch < 7) ? tile + (size_t)ch*planeS + o : ones + (o & 31);
+					// SampleCount (the valid samples of the footprint): the eight channel threads of a pixel each count an eighth
+					// of the mask words by bit arithmetic, instead of one add per sample in every thread
+					const uint32_t needV = tapBits | (1u << (2*xmax + 2*ymax + 2));
 					if(MB == 1)
 					{
 						const uint32_t* mp = reinterpret_cast<const uint32_t*>(mbase + o);
+						const uint32_t nv4 = needV*0x01010101u;
+						for(int wI = ch; wI < SC/4; wI += 8)
+						{
+							const uint32_t t = mp[wI] & nv4;
+							count += __popc(~(((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t | 0x7f7f7f7fu));       // zero bytes
+						}
+						if(!live) continue;
 						const uint32_t n0 = need, n1 = need << 8, n2 = need << 16, n3 = need << 24;
 #pragma unroll 4
 						for(int s4 = 0; s4 < SC/4; ++s4)
@@ -3047,15 +3064,25 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(const __grid_consta
 							if(CHUNKED && !((groups >> s4) & 1u)) continue;
 							const uint32_t m = mp[s4];
 							const float4 v = lds128(vp + 4*s4);
-							if((m & n0) == 0u) { acc += v.x * w[4*s4+0]; ++count; }
-							if((m & n1) == 0u) { acc += v.y * w[4*s4+1]; ++count; }
-							if((m & n2) == 0u) { acc += v.z * w[4*s4+2]; ++count; }
-							if((m & n3) == 0u) { acc += v.w * w[4*s4+3]; ++count; }
+							const float4 w = w4[s4];
+							if((m & n0) == 0u) acc += v.x * w.x;
+							if((m & n1) == 0u) acc += v.y * w.y;
+							if((m & n2) == 0u) acc += v.z * w.z;
+							if((m & n3) == 0u) acc += v.w * w.w;
 						}
 					}
 					else if(MB == 2)
 					{
 						const uint2* mp = reinterpret_cast<const uint2*>(mbase + (size_t)o*2);
+						const uint32_t nv2 = needV*0x00010001u;
+						for(int wI = ch; wI < SC/4; wI += 8)
+						{
+							const uint2 m = mp[wI];
+							const uint32_t t0 = m.x & nv2, t1 = m.y & nv2;
+							count += __popc(~(((t0 & 0x7fff7fffu) + 0x7fff7fffu) | t0 | 0x7fff7fffu))      // zero halves
+							       + __popc(~(((t1 & 0x7fff7fffu) + 0x7fff7fffu) | t1 | 0x7fff7fffu));
+						}
+						if(!live) continue;
 						const uint32_t n0 = need, n1 = need << 16;
 #pragma unroll 4
 						for(int s4 = 0; s4 < SC/4; ++s4)
@@ -3063,25 +3090,33 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(const __grid_consta
 							if(CHUNKED && !((groups >> s4) & 1u)) continue;
 							const uint2 m = mp[s4];
 							const float4 v = lds128(vp + 4*s4);
-							if((m.x & n0) == 0u) { acc += v.x * w[4*s4+0]; ++count; }
-							if((m.x & n1) == 0u) { acc += v.y * w[4*s4+1]; ++count; }
-							if((m.y & n0) == 0u) { acc += v.z * w[4*s4+2]; ++count; }
-							if((m.y & n1) == 0u) { acc += v.w * w[4*s4+3]; ++count; }
+							const float4 w = w4[s4];
+							if((m.x & n0) == 0u) acc += v.x * w.x;
+							if((m.x & n1) == 0u) acc += v.y * w.y;
+							if((m.y & n0) == 0u) acc += v.z * w.z;
+							if((m.y & n1) == 0u) acc += v.w * w.w;
 						}
 					}
 					else
 					{
 						const uint4* mp = reinterpret_cast<const uint4*>(mbase + (size_t)o*4);
+						for(int wI = ch; wI < SC/4; wI += 8)
+						{
+							const uint4 m = mp[wI];
+							count += ((m.x & needV) == 0u) + ((m.y & needV) == 0u) + ((m.z & needV) == 0u) + ((m.w & needV) == 0u);
+						}
+						if(!live) continue;
 #pragma unroll 4
 						for(int s4 = 0; s4 < SC/4; ++s4)
 						{
 							if(CHUNKED && !((groups >> s4) & 1u)) continue;
 							const uint4 m = mp[s4];
 							const float4 v = lds128(vp + 4*s4);
-							if((m.x & need) == 0u) { acc += v.x * w[4*s4+0]; ++count; }
-							if((m.y & need) == 0u) { acc += v.y * w[4*s4+1]; ++count; }
-							if((m.z & need) == 0u) { acc += v.z * w[4*s4+2]; ++count; }
-							if((m.w & need) == 0u) { acc += v.w * w[4*s4+3]; ++count; }
+							const float4 w = w4[s4];
+							if((m.x & need) == 0u) acc += v.x * w.x;
+							if((m.y & need) == 0u) acc += v.y * w.y;
+							if((m.z & need) == 0u) acc += v.z * w.z;
+							if((m.w & need) == 0u) acc += v.w * w.w;
 						}
 					}
 				}
@@ -3091,7 +3126,11 @@ __global__ void __launch_bounds__(8*FILTER_W) k_filter_spans(const __grid_consta
 	__syncthreads();
 	float* sums = reinterpret_cast<float*>(fsm);         // [9][W]
 	sums[ch*W + px] = acc;
-	if(ch == 0) sums[8*W + px] = __int_as_float(count);  // channel 0 counted the valid samples of the footprint
+	// the eight channel threads of a pixel (adjacent lanes) each counted an eighth of the footprint's valid samples
+	count += __shfl_xor_sync(0xffffffffu, count, 1);
+	count += __shfl_xor_sync(0xffffffffu, count, 2);
+	count += __shfl_xor_sync(0xffffffffu, count, 4);
+	if(ch == 0) sums[8*W + px] = __int_as_float(count);
 	__syncthreads();
 	if(tid < W && (x0 + tid) < f.cropX1)
 	{
@@ -3268,11 +3307,20 @@ cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, const float
 		k_filter_partials<<<grid, block, 0, st>>>(f, disp);
 		return cudaGetLastError();
 	}
-	const int ntapw = (2*f.shiftX+1)*(2*f.shiftY+1)*f.n;
+	const int ntaps = (2*f.shiftX+1)*(2*f.shiftY+1);
+	const int ntapw = ntaps*f.n;
+	const int nPad = f.planeChunks*f.planeSC;                       // slots per pixel of the sample planes (a multiple of four, >= n)
 	const size_t spanSmem = filterSpansSmem(f);
-	const bool spans = ntapw <= 49*256 && spanSmem <= 113*1024;     // tap bits fit the mask word (shift <= 7 always), weights in 64 KB of constant memory
+	const bool spans = ntaps*nPad <= 49*256 && spanSmem <= 113*1024;     // tap bits fit the mask word (shift <= 7 always), weights in 64 KB of constant memory
 	cudaError_t e = cudaSuccess;
-	if(spans && uploadTable) e = cudaMemcpyToSymbolAsync(c_filt, hostFilterTab, (size_t)ntapw*4, 0, cudaMemcpyHostToDevice, st);
+	if(spans && uploadTable)
+	{
+		// the span filter reads its weights four at a time: [tap][slot] padded to the planes' slots per pixel
+		static std::vector<float> padded;                           // (kept alive for the asynchronous copy; one frame in flight per process is the library's contract for c_filt)
+		padded.assign((size_t)ntaps*nPad, 0.f);
+		for(int t = 0; t < ntaps; ++t) std::memcpy(&padded[(size_t)t*nPad], hostFilterTab + (size_t)t*f.n, (size_t)f.n*4);
+		e = cudaMemcpyToSymbolAsync(c_filt, padded.data(), padded.size()*4, 0, cudaMemcpyHostToDevice, st);
+	}
 	if(e != cudaSuccess) return e;
 	if(spans && uploadTable)
 	{
