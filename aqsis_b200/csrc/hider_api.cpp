@@ -774,7 +774,6 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 		f.csgType = tab; f.csgParent = tab + nCsg; f.csgSlot = tab + 2*nCsg; f.csgKids = tab + 3*nCsg; f.csgOrder = tab + 4*nCsg;
 	}
 	f.anyTrim = (h->anyTrim && dTrimUV) ? 1 : 0;
-	f.mbPlain = (!h->anyPoints && !h->anyLodG && !h->anyTriG && !h->anyTrim && h->maxKeysG <= 2) ? 1 : 0;
 	if(f.anyTrim)
 	{
 		const int32_t* tab = h->dTrimTab.as<int32_t>();
@@ -839,6 +838,8 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 		f.flushedPos = zOnly ? 0 : h->flushedPos;
 	}
 	f.rowOwned = (std::max(1, p.world_size) > 1) ? h->dRowOwned.as<uint8_t>() : nullptr;
+	f.plain = (!h->anyPoints && !h->anyLodG && !h->anyTriG && !h->anyTrim && h->maxKeysG <= 2 && !h->anyCSG && h->aovFloats == 0 &&
+	           !zOnly && !incremental && !f.midpointZ) ? 1 : 0;
 	if(const char* e = std::getenv("AQH_TUNE"))
 	{
 		int k = 0;

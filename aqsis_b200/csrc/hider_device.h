@@ -77,7 +77,7 @@ struct DevFrame
 	// trim curves (aqh_set_trim_loops): per grid 1 + its trim set (0 = untrimmed); set s owns loops [trimSetLoop[s], trimSetLoop[s+1])
 	// (entry 0 is the empty set), loop l the points [trimLoopPoint[l], trimLoopPoint[l+1]); trimUV: surface parameters per vertex
 	int anyTrim;
-	int mbPlain;                   // no discs, level-of-detail ranges, trim curves, triangular grids or more than 2 motion keys: the short motion kernel
+	int plain;                     // none of: discs, level-of-detail ranges, trim curves, triangular grids, > 2 motion keys, CSG, AOVs, incremental flush / occlusion-only pass, midpoint depth filter: the short kernels (k_hide<..., PLAIN>)
 	const int32_t* gridTrim; const int32_t* trimSetLoop; const int32_t* trimLoopPoint; const float2* trimPoints; const float2* trimUV;
 	// incremental flushes: per-sample occlusion keys kept in HBM between aqh_flush calls ([row][pixel][sample] of the sample
 	// region; null when the frame was never flushed).  A flush hides only the opaque micropolygons at positions >= binFrom

@@ -796,13 +796,14 @@ __device__ __forceinline__ int sampleIdx(const DevFrame& f, const HideSmem& s, i
 // Deposit a hit: opaque hits race for the per-sample (depth, order) minimum; transparent ones
 // are appended to the CTA's deep pool if they are in front of the final opaque depth.
 // StoreSample, bucketprocessor.cpp:1471-1569.
+template<bool PL = false>
 __device__ __forceinline__ void storeOpaque(const DevFrame& f, const HideSmem& s, unsigned long long* key, float D, uint32_t p)
 {
 	if(!(D < FLT_MAX)) return;                       // occlZ(=FLT_MAX) <= D
 	unsigned long long nk = ((unsigned long long)depthKey(D) << 32) | p;
 	if(nk < *key)                                    // cheap pre-check; keys only ever decrease
 	{
-		if(f.midpointZ)
+		if(!PL && f.midpointZ)
 		{
 			// midpoint depth filter with a z display (bucketprocessor.cpp:1502-1529): the sample keeps the
 			// nearest hit and occlZ = the second nearest depth.  Order independent: the value that loses
@@ -1024,7 +1025,7 @@ __device__ __noinline__ void setupStaticRecCall(const DevFrame& f, TileCtx t, co
 // RiPoints, level-of-detail windows, trim curves, the split line of triangular grids -- lives in the RARE = true copy,
 // which exists once per kernel, out of line (sampleStaticRecRare): that code inside the hot loop cost 5-10 % of the
 // whole frame in registers and instruction fetch even when it never ran (profiles/README.md, A/B r2w-r2y).
-template<bool OPAQUE, bool RARE>
+template<bool OPAQUE, bool RARE, bool PL = false>
 __device__ __forceinline__ void sampleStaticLoop(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc,
                                                  const StaticRec& r, int lane)
 {
@@ -1079,7 +1080,7 @@ __device__ __forceinline__ void sampleStaticLoop(const DevFrame& f, const TileCt
 				if(triangleSplitReject(f, g, make_float2(x, y), make_float2(0.f, 0.f), D, 0.0f)) continue;
 		}
 		if(OPAQUE)
-			storeOpaque(f, s, &s.keys[idx], D, r.p);
+			storeOpaque<PL>(f, s, &s.keys[idx], D, r.p);
 		else
 			storeDeep(f, dc, s, idx, D, r.p, uv, r.v0, r.shade, zminKey != 0u);
 	}
@@ -1090,13 +1091,14 @@ __device__ __noinline__ void sampleStaticRecRare(const DevFrame& f, TileCtx t, H
 	if(opaque) sampleStaticLoop<true, true>(f, t, s, dc, *r, lane);
 	else sampleStaticLoop<false, true>(f, t, s, dc, *r, lane);
 }
-template<bool OPAQUE, bool AGG>
+// PL: a PLAIN frame (DevFrame::plain) has no uncommon records
+template<bool OPAQUE, bool AGG, bool PL = false>
 __device__ __forceinline__ void sampleStaticRec(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc,
                                                 const StaticRec& r, int lane)
 {
 	if(r.rect == 0) return;                                                       // rejected at set-up (its flags are stale)
-	if(r.flags & REC_RARE) sampleStaticRecRare(f, t, s, dc, &r, lane, OPAQUE);      // warp-uniform
-	else sampleStaticLoop<OPAQUE, false>(f, t, s, dc, r, lane);
+	if(!PL && (r.flags & REC_RARE)) sampleStaticRecRare(f, t, s, dc, &r, lane, OPAQUE);      // warp-uniform
+	else sampleStaticLoop<OPAQUE, false, PL>(f, t, s, dc, r, lane);
 }
 
 // ---- motion blur and/or depth of field: RenderMPG_MBOrDof (bucketprocessor.cpp:1221-1469).
@@ -1115,11 +1117,13 @@ struct MovingMP
 	GridRec g;
 };
 
-// PLAIN: the motion blur / depth of field kernel of frames WITHOUT discs, level-of-detail ranges, trim curves, triangular grids,
-// or more than two motion keys (DevFrame::mbPlain, decided on the host from the grids submitted; AQH_TUNE=0,0,0,0,1 forces the
-// general kernel, tests/test_features_gpu.py compares the two).  The general kernel is bound by
-// instruction fetch; without those branches the hot code is only a few per cent shorter, but it stays in the instruction cache:
-// config 3 426 ms (general, free-running warps) -> 238 ms (profiles/README.md).
+// PLAIN: the instantiations of k_hide for frames WITHOUT discs, level-of-detail ranges, trim curves, triangular grids, more than two
+// motion keys, CSG solids, arbitrary output variables, an incremental flush / occlusion-only pass or the midpoint depth filter
+// (DevFrame::plain, decided on the host from the frame options and the grids submitted; AQH_TUNE=0,0,0,0,1 forces the general
+// kernels, tests/test_features_gpu.py compares the two).  The general motion kernel is bound by instruction fetch; without those
+// branches the hot code is only a few per cent shorter, but it stays in the instruction cache: config 3 426 ms (general,
+// free-running warps) -> 238 ms.  The static kernel loses its out-of-line calls (rare records, CSG resolve) and with them a
+// 960-byte stack frame: 10 968 -> 5 760 SASS instructions, config 2 hide 10.3 -> 9.3 ms, config 4 -7.5 % (profiles/README.md).
 #define MB_RARE(x) (!PLAIN && (x))
 #define PLAIN_K2 PLAIN        /* at most two motion keys */
 #define MOV_KMAX 4          /* keys staged in shared memory; further keys are read from HBM */
@@ -1284,7 +1288,7 @@ __device__ __forceinline__ void movCandidate(const DevFrame& f, const TileCtx& t
 		const float sx = pos.x + dofOff.x*cm.x, sy = pos.y + dofOff.y*cm.y;
 		const float dx = P0.x - sx, dy = P0.y - sy;
 		if(!((dx*dx + dy*dy) < c.pointR*c.pointR)) return;
-		if(c.opaquePass) storeOpaque(f, s, &s.keys[idx], P0.z, c.m.p);
+		if(c.opaquePass) storeOpaque<PLAIN>(f, s, &s.keys[idx], P0.z, c.m.p);
 		else storeDeep(f, dc, s, idx, P0.z, c.m.p, make_float2(0.f, 0.f), c.shadeInfo.x, c.shadeInfo.y, c.cullable);
 		return;
 	}
@@ -1303,7 +1307,7 @@ __device__ __forceinline__ void movCandidate(const DevFrame& f, const TileCtx& t
 	if(MB_RARE(c.m.g.flags & AQH_GRID_TRIANGULAR))
 		if(triangleSplitReject(f, c.m.g, pos, dofOff, D, time)) return;
 	if(c.opaquePass)
-		storeOpaque(f, s, &s.keys[idx], D, c.m.p);
+		storeOpaque<PLAIN>(f, s, &s.keys[idx], D, c.m.p);
 	else
 		storeDeep(f, dc, s, idx, D, c.m.p, uv, c.shadeInfo.x, c.shadeInfo.y, c.cullable);
 }
@@ -2192,11 +2196,11 @@ __device__ __noinline__ void resolveSampleCSG(const DevFrame& f, const HideSmem 
 // Depth filter "min" without the midpoint bookkeeping is the common case and keeps its own lean code; every
 // other depth filter goes through the general restatement of CqImagePixel::Combine above; samples with a hit list in a
 // frame with CSG solids go through the CSG resolve.
-template<bool MBDOF, bool DFGEN>
+template<bool MBDOF, bool DFGEN, bool PL = false>
 __device__ __forceinline__ void resolveSample(const DevFrame& f, const TileCtx& t, const HideSmem& s, const DeepCtx& dc, int idx,
                                               float out[7], bool& valid, uint32_t& pNear)
 {
-	if(f.anyCSG && s.head && (s.head[idx] & DEEP_COUNT_MASK))
+	if(!PL && f.anyCSG && s.head && (s.head[idx] & DEEP_COUNT_MASK))
 	{
 		// results through temporaries: only they (not the caller's registers) have their address taken by the call
 		float o[7]; bool v; uint32_t pn;
@@ -2308,7 +2312,7 @@ __global__ void __launch_bounds__(THREADS, (!MBDOF && THREADS < 512) ? 1024/THRE
 		const uint32_t slot = s_tile;
 		if(slot >= slotEnd) break;
 		// an incremental flush leaves tiles without new micropolygons as they are (their occlusion image is already there)
-		if(f.zOnly && f.zKeys && f.binOffset[slot+1] == f.binOffset[slot]) continue;
+		if((!PLAIN && f.zOnly) && (PLAIN ? (unsigned long long*)nullptr : f.zKeys) && f.binOffset[slot+1] == f.binOffset[slot]) continue;
 		const uint32_t tile = f.activeTiles[slot];
 		TileCtx t;
 		t.tileX0 = f.sx0 + (int)(tile % f.ntx)*f.tileW;
@@ -2321,7 +2325,7 @@ __global__ void __launch_bounds__(THREADS, (!MBDOF && THREADS < 512) ? 1024/THRE
 		for(int idx = tid; idx < s.nsP; idx += THREADS)
 		{
 			s.keys[idx] = KEY_EMPTY;
-			if(f.midpointZ) s.keys[s.nsP + idx] = KEY_EMPTY;
+			if((!PLAIN && f.midpointZ)) s.keys[s.nsP + idx] = KEY_EMPTY;
 			if(s.head) s.head[idx] = 0u;
 			s.posx[idx] = -1e30f;
 			s.posy[idx] = -1e30f;
@@ -2345,11 +2349,11 @@ __global__ void __launch_bounds__(THREADS, (!MBDOF && THREADS < 512) ? 1024/THRE
 				const float2 o = f.posTab[(size_t)patPos*n + i];
 				s.posx[idx] = (float)X + o.x;
 				s.posy[idx] = (float)Y + o.y;
-				if(f.zKeys)
+				if((PLAIN ? (unsigned long long*)nullptr : f.zKeys))
 				{
 					// the occlusion state earlier flushes of this frame left behind
-					s.keys[idx] = f.zKeys[pp*n + i];
-					if(f.midpointZ) s.keys[s.nsP + idx] = f.zKeys2[pp*n + i];
+					s.keys[idx] = (PLAIN ? (unsigned long long*)nullptr : f.zKeys)[pp*n + i];
+					if((!PLAIN && f.midpointZ)) s.keys[s.nsP + idx] = (PLAIN ? (unsigned long long*)nullptr : f.zKeys2)[pp*n + i];
 				}
 				if(s.time)
 					s.time[idx] = (f.shutterClose - f.shutterOpen) * f.val1d[(size_t)patT*n + i] + f.shutterOpen;
@@ -2375,7 +2379,7 @@ __global__ void __launch_bounds__(THREADS, (!MBDOF && THREADS < 512) ? 1024/THRE
 		for(int i = tid; i < f.tileW*f.tileH; i += THREADS) s.pixZ[i] = 0xffffffffu;
 		if(tid == 0) { s_tileZ = 0xffffffffu; s_dirty = 0; s_lastRef = 0; }
 		PHASE_BARRIER(0);
-		if(f.zKeys)
+		if((PLAIN ? (unsigned long long*)nullptr : f.zKeys))
 		{
 			if(warp == 0) refreshPixZ(f, t, s, lane);        // start from the hierarchical z of the stored keys
 			PHASE_BARRIER(0);
@@ -2388,8 +2392,8 @@ __global__ void __launch_bounds__(THREADS, (!MBDOF && THREADS < 512) ? 1024/THRE
 		const uint32_t tflags = f.tileFlags[slot];
 		const uint32_t split = MBDOF ? 0xffffffffu : (f.anyTransparent ? tflags : binCnt);
 		const bool parted = !MBDOF && split != 0xffffffffu;
-		const bool hasDeep = MBDOF ? (!f.zOnly && f.anyTransparent && (tflags & 1u))
-		                           : (f.anyTransparent && !f.zOnly && (split == 0xffffffffu || split < binCnt));
+		const bool hasDeep = MBDOF ? (!(!PLAIN && f.zOnly) && f.anyTransparent && (tflags & 1u))
+		                           : (f.anyTransparent && !(!PLAIN && f.zOnly) && (split == 0xffffffffu || split < binCnt));
 		// ---- Render_MPGs: opaque pass, then (if the tile saw non-opaque micropolygons) deep pass
 		// MBDOF kernel: keep ONE copy of the (large) pass body in the instruction stream; the compiler would
 		// otherwise peel the loop.  The static kernel is small enough to profit from the specialised copies.
@@ -2446,7 +2450,7 @@ __global__ void __launch_bounds__(THREADS, (!MBDOF && THREADS < 512) ? 1024/THRE
 							}
 							const unsigned long long ent = f.binEntries[binBeg + base];
 							// sorted by nearest depth: the first micropolygon behind the whole tile ends its sorted run
-							if(!(pass == 1 && f.anyCSG) && (uint32_t)(ent >> 32) > *(volatile uint32_t*)s.tileZ)
+							if(!(pass == 1 && (!PLAIN && f.anyCSG)) && (uint32_t)(ent >> 32) > *(volatile uint32_t*)s.tileZ)
 							{
 								const uint32_t runEnd = min(passEnd, (base / (uint32_t)f.sortRun + 1u)*(uint32_t)f.sortRun);
 								if(lane == 0) atomicMax(&s_next, runEnd);
@@ -2464,8 +2468,8 @@ __global__ void __launch_bounds__(THREADS, (!MBDOF && THREADS < 512) ? 1024/THRE
 							// static micropolygon in a frame without depth of field
 							if(lane == 0) setupStaticRecCall(f, t, s.pixZ, p, pass == 0, &myRecs[0]);
 							__syncwarp();
-							if(pass == 0) sampleStaticRec<true, false>(f, t, s, dc, myRecs[0], lane);
-							else sampleStaticRec<false, false>(f, t, s, dc, myRecs[0], lane);
+							if(pass == 0) sampleStaticRec<true, false, PLAIN>(f, t, s, dc, myRecs[0], lane);
+							else sampleStaticRec<false, false, PLAIN>(f, t, s, dc, myRecs[0], lane);
 							__syncwarp();
 						}
 					}
@@ -2511,7 +2515,7 @@ __global__ void __launch_bounds__(THREADS, (!MBDOF && THREADS < 512) ? 1024/THRE
 					const uint32_t zfirst = MBDOF ? __shfl_sync(0xffffffffu, (uint32_t)(ent >> 32), 0)
 					                              : (__shfl_sync(0xffffffffu, (uint32_t)(ent >> 32), 0) << 1);
 					// (CSG micropolygons are not cullable: with any in the frame the deep pass visits every entry)
-					if(!(pass == 1 && f.anyCSG) && zfirst > *(volatile uint32_t*)s.tileZ)
+					if(!(pass == 1 && (!PLAIN && f.anyCSG)) && zfirst > *(volatile uint32_t*)s.tileZ)
 					{
 						const uint32_t runEnd = min(passEnd, (base / (uint32_t)f.sortRun + 1u)*(uint32_t)f.sortRun);
 						if(lane == 0) atomicMax(&s_next, runEnd);
@@ -2523,15 +2527,15 @@ __global__ void __launch_bounds__(THREADS, (!MBDOF && THREADS < 512) ? 1024/THRE
 					__syncwarp();
 					for(int j = 0; j < cnt; ++j)
 					{
-						if(pass == 0) sampleStaticRec<true, true>(f, t, s, dc, myRecs[j], lane);
-						else sampleStaticRec<false, true>(f, t, s, dc, myRecs[j], lane);
+						if(pass == 0) sampleStaticRec<true, true, PLAIN>(f, t, s, dc, myRecs[j], lane);
+						else sampleStaticRec<false, true, PLAIN>(f, t, s, dc, myRecs[j], lane);
 					}
 					__syncwarp();
 				}
 			}
 		}
 		PHASE_BARRIER(hasDeep ? 2 : 1);
-		if(s.head && !f.zOnly)
+		if(s.head && !(!PLAIN && f.zOnly))
 		{
 			// statistics: transparent hits kept by the tile's samples (padding slots hold 0)
 			uint32_t mine = 0;
@@ -2540,7 +2544,7 @@ __global__ void __launch_bounds__(THREADS, (!MBDOF && THREADS < 512) ? 1024/THRE
 			if(lane == 0 && mine) atomicAdd(&f.counters[2], (unsigned long long)mine);
 		}
 		// ---- occlusion feedback for the front end (CqOcclusionTree, occlusion.cpp:54-225, at pixel granularity)
-		if(f.occlImage)
+		if((PLAIN ? (float*)nullptr : f.occlImage))
 		{
 			if(warp == 0) refreshPixZ(f, t, s, lane);
 			PHASE_BARRIER(6);
@@ -2549,9 +2553,9 @@ __global__ void __launch_bounds__(THREADS, (!MBDOF && THREADS < 512) ? 1024/THRE
 			{
 				const int ly = pix / tw0, lx = pix - ly*tw0;
 				const int X = t.rx0 + lx, Y = t.ry0 + ly;
-				f.occlImage[(size_t)(Y - f.sy0)*f.sw + (X - f.sx0)] = keyDepth(s.pixZ[ly*f.tileW + lx]);
+				(PLAIN ? (float*)nullptr : f.occlImage)[(size_t)(Y - f.sy0)*f.sw + (X - f.sx0)] = keyDepth(s.pixZ[ly*f.tileW + lx]);
 			}
-			if(f.zOnly && f.zKeys)
+			if((!PLAIN && f.zOnly) && (PLAIN ? (unsigned long long*)nullptr : f.zKeys))
 			{
 				// keep the per-sample occlusion keys for the next flush / the final frame: one warp per pixel
 				for(int pix = warp; pix < tw0*th0; pix += NWARPS)
@@ -2561,12 +2565,12 @@ __global__ void __launch_bounds__(THREADS, (!MBDOF && THREADS < 512) ? 1024/THRE
 					const int base = (ly*ys)*s.stride + lx*xs;
 					for(int i = lane; i < n; i += 32)
 					{
-						f.zKeys[pp*n + i] = s.keys[base + s.subOfs[i]];
-						if(f.midpointZ) f.zKeys2[pp*n + i] = s.keys[s.nsP + base + s.subOfs[i]];
+						(PLAIN ? (unsigned long long*)nullptr : f.zKeys)[pp*n + i] = s.keys[base + s.subOfs[i]];
+						if((!PLAIN && f.midpointZ)) (PLAIN ? (unsigned long long*)nullptr : f.zKeys2)[pp*n + i] = s.keys[s.nsP + base + s.subOfs[i]];
 					}
 				}
 			}
-			if(f.zOnly) continue;          // the next tile's first barrier orders the reads of pixZ above
+			if((!PLAIN && f.zOnly)) continue;          // the next tile's first barrier orders the reads of pixZ above
 		}
 		// ---- Combine_samples + hand the resolved samples to the filter stage.
 		const int tw = t.rx1 - t.rx0, th = t.ry1 - t.ry0;
@@ -2598,19 +2602,19 @@ __global__ void __launch_bounds__(THREADS, (!MBDOF && THREADS < 512) ? 1024/THRE
 					{
 					const int idx = sampleIdx(f, s, lx, ly, i);
 					float out[7]; bool valid; uint32_t pNear;
-					resolveSample<MBDOF, DFGEN>(f, t, s, dc, idx, out, valid, pNear);
+					resolveSample<MBDOF, DFGEN, PLAIN>(f, t, s, dc, idx, out, valid, pNear);
 					storeMask(f, at, packMask(f, tapMask(f, s.posx[idx], s.posy[idx], X, Y, valid)));
 					if(valid)
 					{
 #pragma unroll
 						for(int k = 0; k < 7; ++k) f.planes[(size_t)k*f.planeStride + at] = out[k];
-						if(f.aovFloats)
+						if((PLAIN ? 0 : f.aovFloats))
 						{
 							// StoreExtraData (bucketprocessor.cpp:1573-1643): the values at the index of the micropolygon of the
 							// NEAREST hit, uninterpolated; planes 7.. are filtered like colour
 							const GridRec g = f.grids[infoOf(f.P4[pNear]) & VINFO_GRID_MASK];
-							const float* av = f.aov + ((size_t)g.vbase + (pNear - g.pbase))*f.aovFloats;
-							for(int k = 0; k < f.aovFloats; ++k) f.planes[(size_t)(7 + k)*f.planeStride + at] = av[k];
+							const float* av = f.aov + ((size_t)g.vbase + (pNear - g.pbase))*(PLAIN ? 0 : f.aovFloats);
+							for(int k = 0; k < (PLAIN ? 0 : f.aovFloats); ++k) f.planes[(size_t)(7 + k)*f.planeStride + at] = av[k];
 						}
 					}
 					}
@@ -2637,7 +2641,7 @@ __global__ void __launch_bounds__(THREADS, (!MBDOF && THREADS < 512) ? 1024/THRE
 					{
 						const int idx = sampleIdx(f, s, lx, ly, i);
 						float out[7]; bool valid; uint32_t pNear;
-						resolveSample<MBDOF, DFGEN>(f, t, s, dc, idx, out, valid, pNear);
+						resolveSample<MBDOF, DFGEN, PLAIN>(f, t, s, dc, idx, out, valid, pNear);
 						const uint32_t m = tapMask(f, s.posx[idx], s.posy[idx], X, Y, valid);
 						if(!valid) { out[0] = out[1] = out[2] = out[3] = out[4] = out[5] = out[6] = 0.f; }
 						scratch[2*lane] = make_float4(out[0], out[1], out[2], out[3]);
@@ -3268,7 +3272,11 @@ cudaError_t hideKernelConfig(const DevFrame& f, int smCount, LaunchCfg& cfg)
 	const bool dfgen = f.depthFilter != AQH_DEPTHFILTER_MIN;
 #define AQH_CFG(MB, TH) (partials ? (dfgen ? configHide<MB, TH, true, true>(f, smCount, cfg) : configHide<MB, TH, true, false>(f, smCount, cfg)) \
                                   : (dfgen ? configHide<MB, TH, false, true>(f, smCount, cfg) : configHide<MB, TH, false, false>(f, smCount, cfg)))
-	if(mbdof && f.mbPlain && !f.tune[4] && !partials && !dfgen) return configHide<true, AQH_MBP_THREADS, false, false, true>(f, smCount, cfg);
+	if(f.plain && !f.tune[4] && !partials && !dfgen)
+	{
+		if(mbdof) return configHide<true, AQH_MBP_THREADS, false, false, true>(f, smCount, cfg);
+		return smallStaticTile(f) ? configHide<false, 256, false, false, true>(f, smCount, cfg) : configHide<false, 512, false, false, true>(f, smCount, cfg);
+	}
 	return mbdof ? AQH_CFG(true, 256) : (smallStaticTile(f) ? AQH_CFG(false, 256) : AQH_CFG(false, 512));
 #undef AQH_CFG
 }
@@ -3283,7 +3291,12 @@ cudaError_t launchHide(const DevFrame& f, const LaunchCfg& cfg, uint32_t slotBeg
 #define AQH_LAUNCH(MB, TH, PA, DF) k_hide<MB, TH, PA, DF><<<ctas, TH, cfg.hideSmemBytes, st>>>(f, slotBeg, slotEnd, cursor)
 #define AQH_LAUNCH2(MB, TH) do { if(partials) { if(dfgen) AQH_LAUNCH(MB, TH, true, true); else AQH_LAUNCH(MB, TH, true, false); } \
                                  else { if(dfgen) AQH_LAUNCH(MB, TH, false, true); else AQH_LAUNCH(MB, TH, false, false); } } while(0)
-	if(mbdof && f.mbPlain && !f.tune[4] && !partials && !dfgen) k_hide<true, AQH_MBP_THREADS, false, false, true><<<ctas, AQH_MBP_THREADS, cfg.hideSmemBytes, st>>>(f, slotBeg, slotEnd, cursor);
+	if(f.plain && !f.tune[4] && !partials && !dfgen)
+	{
+		if(mbdof) k_hide<true, AQH_MBP_THREADS, false, false, true><<<ctas, AQH_MBP_THREADS, cfg.hideSmemBytes, st>>>(f, slotBeg, slotEnd, cursor);
+		else if(smallStaticTile(f)) k_hide<false, 256, false, false, true><<<ctas, 256, cfg.hideSmemBytes, st>>>(f, slotBeg, slotEnd, cursor);
+		else k_hide<false, 512, false, false, true><<<ctas, 512, cfg.hideSmemBytes, st>>>(f, slotBeg, slotEnd, cursor);
+	}
 	else if(mbdof) AQH_LAUNCH2(true, 256); else if(smallStaticTile(f)) AQH_LAUNCH2(false, 256); else AQH_LAUNCH2(false, 512);
 #undef AQH_LAUNCH2
 #undef AQH_LAUNCH
@@ -3316,8 +3329,8 @@ cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, const float
 	if(spans && uploadTable)
 	{
 		// the span filter reads its weights four at a time: [tap][slot] padded to the planes' slots per pixel
-		static std::vector<float> padded;                           // (kept alive for the asynchronous copy; one frame in flight per process is the library's contract for c_filt)
-		padded.assign((size_t)ntaps*nPad, 0.f);
+		// (pageable source: the copy has left the buffer when the call returns)
+		std::vector<float> padded((size_t)ntaps*nPad, 0.f);
 		for(int t = 0; t < ntaps; ++t) std::memcpy(&padded[(size_t)t*nPad], hostFilterTab + (size_t)t*f.n, (size_t)f.n*4);
 		e = cudaMemcpyToSymbolAsync(c_filt, padded.data(), padded.size()*4, 0, cudaMemcpyHostToDevice, st);
 	}
@@ -3327,7 +3340,7 @@ cudaError_t launchFilter(const DevFrame& f, const DevDisplays& disp, const float
 		// A sample of sub-pixel cell (sx, sy) lies at an offset in [sx/xs, (sx+1)/xs) x [sy/ys, (sy+1)/ys) of its pixel (jittered
 		// or not); tap (fx, fy) includes it when offset + fx - 0.5 lies within +-xfwo2 (tapMask): cells that cannot satisfy
 		// that -- with one cell of margin -- need not be looked at.  Only a skip list: the per-sample test stays.
-		static uint16_t groupsHost[49*4];
+		uint16_t groupsHost[49*4] = {};
 		const int nx = 2*f.shiftX + 1, ny = 2*f.shiftY + 1;
 		for(int tap = 0; tap < nx*ny && tap < 49; ++tap)
 		{

@@ -375,3 +375,17 @@ def test_both_motion_kernels_on_config3(gpu_hider, monkeypatch):
     ch2, d2, _ = pu.run_product(gpu_hider, p, g)
     monkeypatch.delenv("AQH_TUNE")
     same_bits(p, ch2, d2, ch, d, "general motion kernel vs short motion kernel")
+
+
+@pytest.mark.parametrize("which", ["config1", "config2", "config4"])
+def test_short_and_general_static_kernels_agree(gpu_hider, which, monkeypatch):
+    """Frames without uncommon features run k_hide<.., PLAIN> (no out-of-line rare-record / CSG calls, no AOV / flush code);
+    AQH_TUNE=0,0,0,0,1 forces the general instantiation on the same frame: same bits, and both equal to the oracle."""
+    p, g = {"config1": lambda: scenes.config1(scale=0.3), "config2": lambda: scenes.config2(scale=0.08),
+            "config4": lambda: scenes.config4(scale=0.03)}[which]()
+    ch, d, st = check(gpu_hider, p, g, which + " (short static kernel)", reference=False)
+    monkeypatch.setenv("AQH_TUNE", "0,0,0,0,1")
+    ch2, d2, st2 = pu.run_product(gpu_hider, p, g)
+    monkeypatch.delenv("AQH_TUNE")
+    same_bits(p, ch2, d2, ch, d, "general static kernel vs short static kernel")
+    assert st2["n_deep_hits"] == st["n_deep_hits"]
