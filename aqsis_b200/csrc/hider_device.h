@@ -145,7 +145,7 @@ struct DevFrame
 	float* occlImage;              // sw*sh (the sample region) or null
 	int zOnly;
 	const uint8_t* rowOwned;       // yres: 1 when this rank owns the pixel row
-	int tune[8];                   // development knobs (environment AQH_TUNE="a,b,..."; 0 = the built-in default): [0] bin entries per grab, opaque pass; [1] deep pass; [2] entries between hierarchical-z refreshes
+	int tune[8];                   // development knobs (environment AQH_TUNE="a,b,..."; 0 = the built-in default): [0] bin entries per grab, opaque pass; [1] deep pass; [2] entries between hierarchical-z refreshes; [4] 1 = the general kernels even for a plain frame; [5] factor on the index window up to which a moving micropolygon is enumerated by (pixel, index)
 };
 
 struct DevDisplay
