@@ -441,8 +441,7 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 	tr.mark("entry");
 	const double tUp0 = nowMs();
 	S.h2d_bytes = 0;
-	int rc = uploadTables(h);
-	if(rc) return rc;
+	int rc = AQH_OK;
 
 	// ---- grid records and chunk index were built at submission (appendGridTables); close the chunk index with
 	// two sentinels (k_project reads one entry past the chunk of a position)
@@ -800,9 +799,8 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 	f.nPos = h->nPos; f.nVerts = h->nVerts; f.nGrids = (int)nGrids;
 	f.P4 = h->dP4.as<float4>();
 	f.CO = h->dCO.as<float4>();
-	f.posTab = h->dPosTab.as<float2>(); f.val1d = h->dVal1d.as<float>(); f.shufTab = h->dShuf.as<uint8_t>(); f.shufInvTab = f.shufTab + h->shuf8.size()/2;
-	f.patPlanes = h->dPat.as<uint8_t>(); f.filterTab = h->dFilt.as<float>(); f.dofBounds = h->dDofB.as<float4>();
-	f.dither = h->dDither.as<float>();
+	// (the frame tables -- posTab, val1d, shufTab, patPlanes, filterTab, dofBounds, dither -- are joined and uploaded below, after
+	// the grids: projection and binning do not read them)
 	f.tileSlot = h->dTileSlot.as<int32_t>(); f.activeTiles = h->dActive.as<uint32_t>();
 	f.binCount = h->dBinCount.as<uint32_t>(); f.binOffset = h->dBinOffset.as<uint32_t>();
 	f.tileFlags = h->dTileFlags.as<uint32_t>();
@@ -901,6 +899,14 @@ int renderFrame(AqhHider* h, bool download, bool zOnly = false, const AqhCallbac
 	tr.mark("launched project+count");
 	CU(cudaStreamSynchronize(st), "bin count");
 	tr.mark("bin count sync");
+	// The frame tables: built on a host thread since aqh_begin_frame (the replay of the renderer's random stream), i.e. while
+	// the grids travelled and were projected; first needed by k_hide.  A cached set (same options as the last frame) costs nothing.
+	rc = uploadTables(h);
+	if(rc) return rc;
+	f.posTab = h->dPosTab.as<float2>(); f.val1d = h->dVal1d.as<float>(); f.shufTab = h->dShuf.as<uint8_t>(); f.shufInvTab = f.shufTab + h->shuf8.size()/2;
+	f.patPlanes = h->dPat.as<uint8_t>(); f.filterTab = h->dFilt.as<float>(); f.dofBounds = h->dDofB.as<float4>();
+	f.dither = h->dDither.as<float>();
+	tr.mark("frame tables");
 	CU(h->dBinEntries.reserve(std::max<size_t>(totalEntries, 1)*8), "cudaMalloc(bin entries)");
 	f.binEntries = h->dBinEntries.as<unsigned long long>();
 	// the project kernel reports whether any vertex is non-opaque: only then does the hide kernel
