@@ -131,6 +131,28 @@ def config3(scale=1.0, seed=SEED + 1, motion_px=16.0, fstop=2.8, focallength=0.0
     return params, _pack(P, Ci, Oi, 16, 16, P2=P2, key_times=(0.0, 1.0))
 
 
+def layered_motion(dof=True, scale=0.05, motion_px=6.0):
+    """config-3 style frame (two motion keys per grid) whose nearest grids are semi-transparent and lie in front of every
+    opaque one (no grid in the depth gap between them, so that the known deviation of DESIGN.md section 2 cannot occur):
+    motion blur (and depth of field) feeding the transparent branch of StoreSample and Combine."""
+    p, g = config3(scale=scale, motion_px=motion_px)
+    if not dof:
+        p.use_dof = 0
+    G, nv = g.n_grids, 17 * 17
+    P = np.asarray(g.P).reshape(G, 2, nv, 3)
+    zmin, zmax = P[..., 2].min(axis=(1, 2)), P[..., 2].max(axis=(1, 2))
+    near, far = zmax < 30.0, zmin > 36.0
+    sel = near | far
+    assert near.sum() > 5 and far.sum() > 5
+    Oi = np.asarray(g.Oi).reshape(G, nv, 3).copy()
+    Oi[near] = np.float32([0.5, 0.25, 0.75])
+    g2 = GridArrays(cu=g.cu[sel], cv=g.cv[sel], flags=g.flags[sel], P=np.ascontiguousarray(P[sel].reshape(-1, 3)),
+                    Ci=np.ascontiguousarray(np.asarray(g.Ci).reshape(G, nv, 3)[sel].reshape(-1, 3)),
+                    Oi=np.ascontiguousarray(Oi[sel].reshape(-1, 3)), nkeys=g.nkeys[sel],
+                    key_times=np.ascontiguousarray(np.asarray(g.key_times).reshape(G, 2)[sel].reshape(-1)))
+    return p, g2
+
+
 def to_camera_space(params, grids, fov_deg=40.0):
     """Re-express raster-space grids in camera space and set params.cam_to_raster to the perspective matrix that maps
     them back (row-vector convention of CqMatrix, include/aqsis/math/matrix.h:717-750): the device / the reference then

@@ -330,34 +330,13 @@ def test_scanline_order_display(gpu_hider):
     assert np.array_equal(img, d[0])
 
 
-def _layered_motion_scene(dof, scale=0.05):
-    """config-3 style frame (two motion keys per grid) whose nearest grids are semi-transparent and lie in front of every
-    opaque one (no grid in the depth gap between them), so that the known deviation of DESIGN.md section 2 cannot occur."""
-    p, g = scenes.config3(scale=scale, motion_px=6.0)
-    if not dof:
-        p.use_dof = 0
-    G, nv = g.n_grids, 17 * 17
-    P = np.asarray(g.P).reshape(G, 2, nv, 3)
-    zmin, zmax = P[..., 2].min(axis=(1, 2)), P[..., 2].max(axis=(1, 2))
-    near, far = zmax < 30.0, zmin > 36.0
-    sel = near | far
-    Oi = np.asarray(g.Oi).reshape(G, nv, 3).copy()
-    Oi[near] = np.float32([0.5, 0.25, 0.75])
-    g2 = scenes.GridArrays(cu=g.cu[sel], cv=g.cv[sel], flags=g.flags[sel], P=np.ascontiguousarray(P[sel].reshape(-1, 3)),
-                           Ci=np.ascontiguousarray(np.asarray(g.Ci).reshape(G, nv, 3)[sel].reshape(-1, 3)),
-                           Oi=np.ascontiguousarray(Oi[sel].reshape(-1, 3)), nkeys=g.nkeys[sel],
-                           key_times=np.ascontiguousarray(np.asarray(g.key_times).reshape(G, 2)[sel].reshape(-1)))
-    assert near.sum() > 5 and far.sum() > 5
-    return p, g2
-
-
 @pytest.mark.parametrize("dof", [False, True])
 def test_transparent_motion_blur_and_both_motion_kernels(gpu_hider, dof, monkeypatch):
     """Motion blur (and depth of field) over semi-transparent layers: RenderMPG_MBOrDof feeding StoreSample's transparent
     branch and Combine (bucketprocessor.cpp:1221-1469, 1471-1569; imagepixel.cpp:144-262).  Such a frame runs the short
     motion kernel (k_hide<.., PLAIN>: no discs / level of detail / trim / triangular grids / more than two keys); forcing the
     general kernel on the same frame must give the same bits."""
-    p, g = _layered_motion_scene(dof)
+    p, g = scenes.layered_motion(dof=dof)
     ch, d, st = check(gpu_hider, p, g, "transparent motion blur" + (" + depth of field" if dof else ""))
     assert st["n_deep_hits"] > 0
     monkeypatch.setenv("AQH_TUNE", "0,0,0,0,1")

@@ -98,6 +98,9 @@ CASES["csg-average-rgbaz"] = lambda: _mod(scenes.csg_scene(op="difference", nest
                                            lambda p: _set(p, depth_filter=abi.DEPTHFILTER_AVERAGE, display_mode=abi.DMODE_RGB | abi.DMODE_A | abi.DMODE_Z))
 # the backface / transparency culls of CqMicroPolyGrid::Shade (restated with aqsis' vector and colour classes in the wrapper)
 CASES["culls"] = lambda: scenes.cull_scene()
+# motion blur (and depth of field) over semi-transparent layers: RenderMPG_MBOrDof feeding StoreSample's transparent branch
+CASES["motion-transparent"] = lambda: scenes.layered_motion(dof=False)
+CASES["motion-dof-transparent"] = lambda: scenes.layered_motion(dof=True)
 
 
 def assert_identical(p, ch_r, d_r, ch_o, d_o, what):
